@@ -1,0 +1,524 @@
+// api.cu — C-ABI of libgzb200.so (include/gzb200.h): engine lifecycle, the host-side planner that expands a
+// batch of sections into leaves and tiles, device workspace management, staging of host buffers.
+//
+// Reference interfaces replaced: codec_*_compress / codec_rans_uncompress / codec_arith_uncompress
+// (src/codec_htscodecs.c:40-129) and codec_*_est_size (:26-33).  There is no CPU fallback anywhere in this file.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <numeric>
+#include <mutex>
+#include "../../include/gzb200.h"
+#include "gzb_internal.cuh"
+#include "hts_enc.cuh"
+#include "engine.h"
+
+using namespace gzb;
+
+static std::string g_last_error;
+
+#define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { e->err = std::string (#call) + ": " + cudaGetErrorString (_e); return GZB_E_CUDA; } } while (0)
+
+// ------------------------------------------------------------------------------------------------ bounds (double arithmetic of the reference)
+// rans_compress_bound_4x16 (rANS_static4x16pr.c:357-369) and arith_compress_bound (arith_dynamic.c:74-80).  The reference
+// object evaluates 1.05*size + C as one fused multiply-add followed by plain additions, left to right.
+static double bound_base (uint32_t n, int order)
+{
+    if (order == 0) return std::fma (1.05, (double)n, 257.0 * 3) + 4;
+    double t = std::fma (1.05, (double)n, 257.0 * 257 * 3);
+    t += 4; t += 257 * 3; t += 4;
+    return t;
+}
+static uint32_t rans_bound (uint32_t n, int order)
+{
+    int N = order >> 8; if (!N) N = 4;
+    order &= 0xff;
+    int sz = (int)(bound_base (n, order) + ((order & F_PACK) ? 1 : 0) + ((order & F_RLE) ? 1 + 257*3 + 4 : 0) + 20 + ((order & F_STRIPE) ? 1 + 5*N : 0));
+    return sz + (sz & 1) + 2;
+}
+static uint32_t arith_bound (uint32_t n, int order)
+{
+    return (uint32_t)(bound_base (n, order) + ((order & F_PACK) ? 1 : 0) + ((order & F_RLE) ? 1 + 257*3 + 4 : 0) + 5);
+}
+
+static bool codec_info (int codec, uint8_t *coder, uint8_t *order)
+{
+    switch (codec) {
+        case GZB_CODEC_RANB: *coder = CODER_RANS;  *order = 0x01; return true;
+        case GZB_CODEC_RANW: *coder = CODER_RANS;  *order = 0x19; return true;
+        case GZB_CODEC_RANb: *coder = CODER_RANS;  *order = 0x81; return true;
+        case GZB_CODEC_RANw: *coder = CODER_RANS;  *order = 0x99; return true;
+        case GZB_CODEC_ARTB: *coder = CODER_ARITH; *order = 0x01; return true;
+        case GZB_CODEC_ARTW: *coder = CODER_ARITH; *order = 0x19; return true;
+        case GZB_CODEC_ARTb: *coder = CODER_ARITH; *order = 0x81; return true;
+        case GZB_CODEC_ARTw: *coder = CODER_ARITH; *order = 0x99; return true;
+        default: return false;
+    }
+}
+
+extern "C" uint32_t gzb_est_size (int codec, uint64_t n)
+{
+    uint8_t coder, order;
+    if (!codec_info (codec, &coder, &order)) return 0;
+    return 1024 + (coder == CODER_RANS ? rans_bound ((uint32_t)n, order) : arith_bound ((uint32_t)n, order));
+}
+
+// ------------------------------------------------------------------------------------------------ engine
+extern "C" int gzb_device_count (void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount (&n) != cudaSuccess) { cudaGetLastError (); return 0; }
+    return n;
+}
+
+extern "C" int gzb_engine_create (int device, gzb_engine **out)
+{
+    *out = nullptr;
+    int n = gzb_device_count ();
+    if (n <= 0 || device < 0 || device >= n) { g_last_error = "no usable CUDA device (the product has no CPU fallback)"; return GZB_E_NOCUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties (&prop, device) != cudaSuccess || prop.major < 10) {
+        g_last_error = "device is not sm_100-class: libgzb200 ships sm_100a kernels only"; return GZB_E_NOCUDA;
+    }
+    gzb_engine *e = new gzb_engine ();
+    e->device = device;
+    e->sm_count = prop.multiProcessorCount;
+    if (cudaSetDevice (device) != cudaSuccess || cudaStreamCreateWithFlags (&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        g_last_error = "cudaStreamCreate failed"; delete e; return GZB_E_CUDA;
+    }
+    cudaEventCreate (&e->ev0); cudaEventCreate (&e->ev1);
+    // log tables for the order-1 table-size decision: must come from the same libm the reference links
+    double l10[257], l12[257];
+    for (int k = 0; k <= 256; k++) { l10[k] = log ((double)(1024 + k)); l12[k] = log ((double)(4096 + k)); }
+    upload_log_tables (l10, l12);
+    if (cudaGetLastError () != cudaSuccess) { g_last_error = "no sm_100a kernel image for this device"; delete e; return GZB_E_NOCUDA; }
+    *out = e;
+    return GZB_OK;
+}
+
+extern "C" void gzb_engine_destroy (gzb_engine *e)
+{
+    if (!e) return;
+    cudaSetDevice (e->device);
+    cudaStreamSynchronize (e->stream);
+    if (e->ws) cudaFree (e->ws);
+    if (e->pin) cudaFreeHost (e->pin);
+    cudaEventDestroy (e->ev0); cudaEventDestroy (e->ev1);
+    cudaStreamDestroy (e->stream);
+    delete e;
+}
+
+extern "C" const char *gzb_last_error (gzb_engine *e) { return e ? e->err.c_str () : g_last_error.c_str (); }
+extern "C" void *gzb_engine_stream (gzb_engine *e) { return (void *)e->stream; }
+extern "C" int gzb_engine_sync (gzb_engine *e) { cudaSetDevice (e->device); CK (cudaStreamSynchronize (e->stream)); return GZB_OK; }
+extern "C" int gzb_vb_device (uint32_t vblock_i, int n_devices) { return n_devices > 0 ? (int)((vblock_i ? vblock_i - 1 : 0) % (uint32_t)n_devices) : 0; }
+extern "C" uint64_t gzb_kernel_launches (gzb_engine *e) { return e->launches; }
+extern "C" float gzb_last_chain_ms (gzb_engine *e) { return e->last_chain_ms; }
+
+int engine_reserve (gzb_engine *e, size_t ws_bytes, size_t pin_bytes)
+{
+    if (ws_bytes > e->ws_cap) {
+        CK (cudaStreamSynchronize (e->stream));
+        if (e->ws) cudaFree (e->ws);
+        e->ws = nullptr; e->ws_cap = 0;
+        size_t want = ws_bytes + ws_bytes / 8 + (1u << 20);
+        CK (cudaMalloc (&e->ws, want));
+        e->ws_cap = want;
+    }
+    if (pin_bytes > e->pin_cap) {
+        CK (cudaStreamSynchronize (e->stream));
+        if (e->pin) cudaFreeHost (e->pin);
+        e->pin = nullptr; e->pin_cap = 0;
+        size_t want = pin_bytes + pin_bytes / 8 + (1u << 16);
+        CK (cudaMallocHost (&e->pin, want));
+        e->pin_cap = want;
+    }
+    return GZB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ compress
+namespace {
+
+struct Carver {                        // carves 256-byte aligned regions out of the workspace; first pass measures
+    uint8_t *base; size_t off;
+    template <typename T> T *take (size_t count) {
+        size_t bytes = (count * sizeof (T) + 255) & ~(size_t)255;
+        T *p = base ? reinterpret_cast<T *>(base + off) : nullptr;
+        off += bytes;
+        return p;
+    }
+};
+
+constexpr size_t SMALL_COPY = 65536;   // host sections below this are gathered through the pinned staging buffer
+
+uint32_t leaf_out_cap (uint8_t coder, uint32_t order_req, uint32_t n)
+{
+    double base = 1.06 * n + 2048;
+    if (coder == CODER_RANS && (order_req & 1)) {
+        double tab = std::min (200.0 * 1024, 3.0 * n + 1024);      // O1 table and its nested-compression scratch
+        base += 2 * tab + 1024;
+    }
+    return ((uint32_t)base + 31) & ~15u;
+}
+
+// Host → device input copies.  Large sections go straight from the caller's buffer; runs of consecutive small
+// sections (contiguous in the device input region) are gathered into pinned memory and sent as one transfer.
+template <typename FD, typename FH, typename FL>
+int stage_inputs (gzb_engine *e, uint8_t *stage, uint32_t n, FD dev, FH host, FL len)
+{
+    cudaStream_t st = e->stream;
+    size_t so = 0;
+    uint32_t i = 0;
+    while (i < n) {
+        uint32_t l = len (i);
+        if (!l) { i++; continue; }
+        if (l >= SMALL_COPY) { CK (cudaMemcpyAsync (dev (i), host (i), l, cudaMemcpyHostToDevice, st)); i++; continue; }
+        uint8_t *d0 = dev (i); size_t s0 = so, run = 0;
+        while (i < n && len (i) < SMALL_COPY) {
+            uint32_t li = len (i);
+            if (li) { size_t rel = (size_t)(dev (i) - d0); memcpy (stage + s0 + rel, host (i), li); run = rel + li; }
+            i++;
+        }
+        so = s0 + ((run + 255) & ~(size_t)255);
+        CK (cudaMemcpyAsync (d0, stage + s0, run, cudaMemcpyHostToDevice, st));
+    }
+    return GZB_OK;
+}
+
+int pick_rans_gpw (uint32_t n)  { return n <= 4736 ? 1 : n <= 9472 ? 2 : n <= 18944 ? 4 : 8; }
+int pick_arith_lpw (uint32_t n) { int l = 1; while (l < 32 && (uint64_t)n > 9472ull * l) l *= 2; return l; }
+
+} // namespace
+
+extern "C" int gzb_compress_sections (gzb_engine *e, gzb_section *secs, uint32_t n, uint32_t flags)
+{
+    if (!e) return GZB_E_BADARG;
+    if (!n) return GZB_OK;
+    cudaSetDevice (e->device);
+    const bool devptr = flags & GZB_DEVICE_PTRS;
+
+    // ---- plan on the host
+    std::vector<EncSection> hs (n);
+    std::vector<EncLeaf> hl;
+    std::vector<Tile> tiles, stiles;
+    std::vector<uint32_t> rlist, alist;
+    bool any_pack = false, any_o1 = false;
+    size_t in_total = 0, out_total = 0, plane_total = 0, pack_total = 0, outbuf_total = 0;
+    size_t small_in = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        gzb_section &s = secs[i];
+        uint8_t coder, order;
+        if (!codec_info (s.codec, &coder, &order) || (!s.in && s.in_len) || !s.out) { s.status = GZB_E_BADARG; e->err = "bad section"; return GZB_E_BADARG; }
+        EncSection &S = hs[i];
+        memset (&S, 0, sizeof S);
+        S.n = s.in_len; S.coder = coder; S.order = order; S.out_cap = s.out_cap;
+        S.soft_fail = s.out_cap < gzb_est_size (s.codec, s.in_len);           // the reference returns NULL → false under soft_fail
+        S.stripe = (order & F_STRIPE) && S.n > 20;
+        S.first_leaf = (uint32_t)hl.size ();
+        if (S.soft_fail) { S.n_leaves = 0; continue; }
+        in_total += (S.n + 15) & ~15ull;
+        out_total += ((size_t)std::min<uint32_t> (s.out_cap, gzb_est_size (s.codec, s.in_len)) + 15) & ~15ull;
+        if (!devptr && S.n < SMALL_COPY) small_in += (S.n + 15) & ~15ull;
+        auto add_leaf = [&] (uint32_t ln, uint32_t order_req, size_t plane_off) {
+            EncLeaf L; memset (&L, 0, sizeof L);
+            L.n = ln; L.section = i; L.coder = coder; L.order_req = (uint8_t)order_req;
+            L.out_cap = leaf_out_cap (coder, order_req, ln);
+            L.in = reinterpret_cast<const uint8_t *>(plane_off);              // patched to a pointer after carving
+            uint32_t li = (uint32_t)hl.size ();
+            hl.push_back (L);
+            outbuf_total += L.out_cap;
+            if (order_req & F_PACK) { any_pack = true; pack_total += ((size_t)ln + 1 + 15) & ~15ull; }
+            if (coder == CODER_RANS && (order_req & 1)) any_o1 = true;
+            for (uint32_t off = 0; off < ln; off += TILE) tiles.push_back (Tile { li, off });
+            (coder == CODER_RANS ? rlist : alist).push_back (li);
+        };
+        if (!S.stripe) { add_leaf (S.n, order & ~F_STRIPE, 0); S.n_leaves = 1; }
+        else {
+            // candidate methods per byte-plane, in the reference's try order (rANS :1203-1214; arith :684-687,726-737)
+            static const int rans_m[4] = { 1, 64, 128, 0 };
+            static const int arith_m[4][4] = { {3, 1, 64, 0}, {2, 1, 0, 0}, {2, 1, 128, 0}, {2, 1, 128, 0} };
+            uint32_t counts = 0, idx = 0;
+            for (int p = 0; p < 4; p++) {
+                uint32_t plen = S.n / 4 + ((S.n % 4) > (uint32_t)p), nc = 0;
+                if (coder == CODER_RANS) {
+                    for (int j = 0; j < 4; j++) if ((order & rans_m[j]) == rans_m[j]) { add_leaf (plen, rans_m[j] | F_NOSZ, plane_total + idx); nc++; }
+                }
+                else for (int j = 1; j <= arith_m[p][0]; j++) {
+                    if ((order & 3) == 0 && (arith_m[p][j] & 1)) continue;
+                    add_leaf (plen, arith_m[p][j] | F_NOSZ, plane_total + idx); nc++;
+                }
+                counts |= nc << (4 * p);
+                idx += plen;
+            }
+            S.n_leaves = counts;
+            S.planes = reinterpret_cast<uint8_t *>(plane_total);
+            for (uint32_t off = 0; off < S.n; off += TILE) stiles.push_back (Tile { i, off });
+            plane_total += (S.n + 15) & ~15ull;
+        }
+    }
+    const uint32_t nl = (uint32_t)hl.size ();
+    auto by_len = [&] (uint32_t a, uint32_t b) { return hl[a].n > hl[b].n; };
+    std::stable_sort (rlist.begin (), rlist.end (), by_len);
+    std::stable_sort (alist.begin (), alist.end (), by_len);
+
+    // arena estimate for alphabet-dependent tables; grown and replayed on overflow
+    size_t arena_est = (size_t)4 << 20;
+    for (auto &L : hl) {
+        size_t m = std::min<size_t> (256, (size_t)L.n + 1);
+        if (L.coder == CODER_RANS) arena_est += (L.order_req & 1) ? std::min<size_t> (m * m * 20 + m * CTXB, 64 * 64 * 20 + 64 * CTXB + (size_t)L.n / 8) + 4096 : 4096 + 64;
+        else arena_est += std::min<size_t> ((size_t)256 * 259 * 4, 256 * 68 * 4 + (size_t)L.n / 8) + 258 * 7 * 4 + 64;
+    }
+    if (e->arena_hint > arena_est) arena_est = e->arena_hint;
+
+    for (int attempt = 0; attempt < 4; attempt++) {
+        // ---- carve the workspace (two passes: measure, then place)
+        Carver c { nullptr, 0 };
+        EncPlanDev P; memset (&P, 0, sizeof P);
+        uint8_t *d_in = nullptr, *d_out = nullptr, *d_planes = nullptr, *d_pack = nullptr, *d_outbuf = nullptr, *d_arena = nullptr;
+        uint32_t *d_hist0 = nullptr; unsigned long long *d_cursor = nullptr; int *d_overflow = nullptr;
+        size_t meta_off = 0, meta_bytes = 0;
+        for (int pass = 0; pass < 2; pass++) {
+            c.off = 0;
+            // metadata blob uploaded in one copy: sections | leaves | tiles | stripe tiles | lists
+            meta_off = c.off;
+            P.sections     = c.take<EncSection> (n);
+            P.leaves       = c.take<EncLeaf> (nl ? nl : 1);
+            P.tiles        = c.take<Tile> (tiles.size () + 1);
+            P.stripe_tiles = c.take<Tile> (stiles.size () + 1);
+            P.rans_list    = c.take<uint32_t> (rlist.size () + 1);
+            P.arith_list   = c.take<uint32_t> (alist.size () + 1);
+            meta_bytes = c.off - meta_off;
+            P.dyn          = c.take<EncLeafDyn> (nl ? nl : 1);
+            P.results      = c.take<SectionResult> (n);
+            P.segs         = c.take<CopySeg> ((size_t)n * 16);
+            P.stripe_hdr   = c.take<uint8_t> ((size_t)n * 32);
+            d_cursor       = c.take<unsigned long long> (1);
+            d_overflow     = c.take<int> (1);
+            d_hist0        = c.take<uint32_t> ((size_t)(nl ? nl : 1) * 256);
+            d_in           = c.take<uint8_t> (devptr ? 1 : in_total);
+            d_out          = c.take<uint8_t> (devptr ? 1 : out_total);
+            d_planes       = c.take<uint8_t> (plane_total + 1);
+            d_pack         = c.take<uint8_t> (pack_total + 1);
+            d_outbuf       = c.take<uint8_t> (outbuf_total + 1);
+            d_arena        = c.take<uint8_t> (arena_est);
+            if (pass == 0) {
+                int rc = engine_reserve (e, c.off, (devptr ? 0 : small_in + 512 * (size_t)n) + meta_bytes + 8192);
+                if (rc) return rc;
+                c.base = e->ws;
+            }
+        }
+
+        // ---- fill host copies with device pointers
+        std::vector<uint8_t> meta (meta_bytes);
+        std::vector<EncSection> S2 = hs;
+        std::vector<EncLeaf> L2 = hl;
+        {
+            size_t io = 0, oo = 0, po = 0, bo = 0;
+            for (uint32_t i = 0; i < n; i++) {
+                EncSection &S = S2[i];
+                if (S.soft_fail) continue;
+                if (devptr) { S.in = (const uint8_t *)secs[i].in; S.out = (uint8_t *)secs[i].out; }
+                else {
+                    S.in = d_in + io; io += (S.n + 15) & ~15ull;
+                    S.out = d_out + oo; oo += ((size_t)std::min<uint32_t> (secs[i].out_cap, gzb_est_size (secs[i].codec, secs[i].in_len)) + 15) & ~15ull;
+                }
+                if (S.stripe) S.planes = d_planes + (size_t)hs[i].planes;
+                uint32_t cnt = S.stripe ? ((S.n_leaves & 15) + ((S.n_leaves >> 4) & 15) + ((S.n_leaves >> 8) & 15) + ((S.n_leaves >> 12) & 15)) : 1;
+                for (uint32_t k = 0; k < cnt; k++) {
+                    EncLeaf &L = L2[S.first_leaf + k];
+                    L.in = S.stripe ? d_planes + (size_t)hl[S.first_leaf + k].in : S.in;
+                    L.hist0 = d_hist0 + (size_t)(S.first_leaf + k) * 256;
+                    L.outbuf = d_outbuf + bo; bo += L.out_cap;
+                    if (L.order_req & F_PACK) { L.packbuf = d_pack + po; po += ((size_t)L.n + 1 + 15) & ~15ull; }
+                }
+            }
+            uint8_t *m = meta.data ();
+            auto put = [&] (const void *dev, const void *src, size_t bytes) { if (bytes) memcpy (m + ((const uint8_t *)dev - (e->ws + meta_off)), src, bytes); };
+            put (P.sections, S2.data (), n * sizeof (EncSection));
+            put (P.leaves, L2.data (), nl * sizeof (EncLeaf));
+            put (P.tiles, tiles.data (), tiles.size () * sizeof (Tile));
+            put (P.stripe_tiles, stiles.data (), stiles.size () * sizeof (Tile));
+            put (P.rans_list, rlist.data (), rlist.size () * 4);
+            put (P.arith_list, alist.data (), alist.size () * 4);
+        }
+
+        P.n_sections = n; P.n_leaves = nl; P.n_tiles = (uint32_t)tiles.size (); P.n_stripe_tiles = (uint32_t)stiles.size ();
+        P.n_rans = (uint32_t)rlist.size (); P.n_arith = (uint32_t)alist.size ();
+        P.any_pack = any_pack; P.any_o1 = any_o1;
+        P.rans_gpw = pick_rans_gpw (P.n_rans); P.arith_lpw = pick_arith_lpw (P.n_arith);
+        P.copy_parts = (n <= 64) ? 32 : (n <= 1024 ? 8 : 2);
+        P.arena = Arena { d_arena, (unsigned long long)arena_est, d_cursor, d_overflow };
+        P.ev_chain0 = e->ev0; P.ev_chain1 = e->ev1;
+
+        // ---- upload: metadata blob, inputs (small ones gathered through pinned staging)
+        cudaStream_t st = e->stream;
+        memcpy (e->pin, meta.data (), meta_bytes);
+        CK (cudaMemcpyAsync (e->ws + meta_off, e->pin, meta_bytes, cudaMemcpyHostToDevice, st));
+        if (!devptr) {
+            int rc = stage_inputs (e, e->pin + ((meta_bytes + 255) & ~(size_t)255), n,
+                                   [&] (uint32_t i) { return (uint8_t *)S2[i].in; },
+                                   [&] (uint32_t i) { return (const uint8_t *)secs[i].in; },
+                                   [&] (uint32_t i) { return S2[i].soft_fail ? 0u : S2[i].n; });
+            if (rc) return rc;
+        }
+        CK (cudaMemsetAsync (d_cursor, 0, 512, st));
+        CK (cudaMemsetAsync (d_hist0, 0, (size_t)(nl ? nl : 1) * 1024, st));
+
+        // ---- run
+        enc_run (P, st);
+        e->launches += P.launches;
+        CK (cudaGetLastError ());
+
+        // ---- results
+        std::vector<SectionResult> res (n);
+        int h_over = 0; unsigned long long h_cursor = 0;
+        CK (cudaMemcpyAsync (res.data (), P.results, n * sizeof (SectionResult), cudaMemcpyDeviceToHost, st));
+        CK (cudaMemcpyAsync (&h_over, d_overflow, sizeof (int), cudaMemcpyDeviceToHost, st));
+        CK (cudaMemcpyAsync (&h_cursor, d_cursor, sizeof h_cursor, cudaMemcpyDeviceToHost, st));
+        CK (cudaStreamSynchronize (st));
+        if (h_over) {                                                     // tables did not fit: grow the arena and replay the batch
+            arena_est = (size_t)h_cursor + (h_cursor >> 2) + ((size_t)1 << 20);
+            e->arena_hint = arena_est;
+            continue;
+        }
+        float ms = 0; cudaEventElapsedTime (&ms, e->ev0, e->ev1); e->last_chain_ms = ms;
+
+        for (uint32_t i = 0; i < n; i++) {
+            secs[i].status = res[i].status; secs[i].out_len = res[i].out_len;
+            if (res[i].status == 0 && res[i].out_len > secs[i].out_cap) { secs[i].status = GZB_SOFT_FAIL; secs[i].out_len = 0; }
+        }
+        if (!devptr) {
+            for (uint32_t i = 0; i < n; i++)
+                if (secs[i].status == 0 && secs[i].out_len)
+                    CK (cudaMemcpyAsync (secs[i].out, S2[i].out, secs[i].out_len, cudaMemcpyDeviceToHost, st));
+            CK (cudaStreamSynchronize (st));
+        }
+        return GZB_OK;
+    }
+    e->err = "device arena kept overflowing";
+    return GZB_E_CUDA;
+}
+
+// ------------------------------------------------------------------------------------------------ uncompress
+extern "C" int gzb_uncompress_sections (gzb_engine *e, gzb_section *secs, uint32_t n, uint32_t flags)
+{
+    if (!e) return GZB_E_BADARG;
+    if (!n) return GZB_OK;
+    cudaSetDevice (e->device);
+    const bool devptr = flags & GZB_DEVICE_PTRS;
+
+    std::vector<DecSection> hs (n);
+    std::vector<uint32_t> order_idx (n);
+    size_t in_total = 0, out_total = 0, aux_total = 0, small_in = 0;
+    uint32_t n_rans_sec = 0, n_arith_sec = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        gzb_section &s = secs[i];
+        uint8_t coder, order;
+        // the reference asserts on zero lengths (codec_htscodecs.c:103-104, 120-121)
+        if (!codec_info (s.codec, &coder, &order) || !s.in || !s.out || !s.in_len || !s.out_cap) { s.status = GZB_E_BADARG; e->err = "bad section"; return GZB_E_BADARG; }
+        DecSection &S = hs[i]; memset (&S, 0, sizeof S);
+        S.in_len = s.in_len; S.n = s.out_cap; S.coder = coder;
+        in_total += (S.in_len + 15) & ~15ull; out_total += (S.n + 15) & ~15ull; aux_total += (S.n + 15) & ~15ull;
+        if (!devptr && S.in_len < SMALL_COPY) small_in += (S.in_len + 15) & ~15ull;
+        (coder == CODER_RANS ? n_rans_sec : n_arith_sec)++;
+        order_idx[i] = i;
+    }
+    std::stable_sort (order_idx.begin (), order_idx.end (), [&] (uint32_t a, uint32_t b) { return hs[a].n > hs[b].n; });
+    std::vector<uint32_t> rlist, alist;
+    for (uint32_t k = 0; k < n; k++) { uint32_t i = order_idx[k]; for (int j = 0; j < 4; j++) (hs[i].coder == CODER_RANS ? rlist : alist).push_back (4 * i + j); }
+
+    size_t arena_est = (size_t)4 << 20;
+    for (auto &S : hs) arena_est += (S.coder == CODER_RANS) ? std::min<size_t> ((size_t)1400 << 10, 96 * 1024 + (size_t)S.in_len * 8) + 4 * 16384
+                                                             : std::min<size_t> ((size_t)4 * 272 * 1024, 4 * 80 * 1024 + (size_t)S.n / 4);
+    if (e->arena_hint_dec > arena_est) arena_est = e->arena_hint_dec;
+
+    for (int attempt = 0; attempt < 4; attempt++) {
+        Carver c { nullptr, 0 };
+        DecPlanDev P; memset (&P, 0, sizeof P);
+        uint8_t *d_in = nullptr, *d_out = nullptr, *d_planes = nullptr, *d_tmp = nullptr, *d_arena = nullptr;
+        unsigned long long *d_cursor = nullptr; int *d_overflow = nullptr;
+        size_t meta_off = 0, meta_bytes = 0;
+        for (int pass = 0; pass < 2; pass++) {
+            c.off = 0;
+            meta_off = c.off;
+            P.sections   = c.take<DecSection> (n);
+            P.rans_list  = c.take<uint32_t> (rlist.size () + 1);
+            P.arith_list = c.take<uint32_t> (alist.size () + 1);
+            meta_bytes = c.off - meta_off;
+            P.leaves     = c.take<DecLeaf> ((size_t)4 * n);
+            P.results    = c.take<SectionResult> (n);
+            d_cursor     = c.take<unsigned long long> (1);
+            d_overflow   = c.take<int> (1);
+            d_in         = c.take<uint8_t> (devptr ? 1 : in_total);
+            d_out        = c.take<uint8_t> (devptr ? 1 : out_total);
+            d_planes     = c.take<uint8_t> (aux_total);
+            d_tmp        = c.take<uint8_t> (aux_total);
+            d_arena      = c.take<uint8_t> (arena_est);
+            if (pass == 0) {
+                int rc = engine_reserve (e, c.off, (devptr ? 0 : small_in + 512 * (size_t)n) + meta_bytes + 8192);
+                if (rc) return rc;
+                c.base = e->ws;
+            }
+        }
+        std::vector<DecSection> S2 = hs;
+        {
+            size_t io = 0, oo = 0, ao = 0;
+            for (uint32_t i = 0; i < n; i++) {
+                DecSection &S = S2[i];
+                if (devptr) { S.in = (const uint8_t *)secs[i].in; S.out = (uint8_t *)secs[i].out; }
+                else { S.in = d_in + io; io += (S.in_len + 15) & ~15ull; S.out = d_out + oo; oo += (S.n + 15) & ~15ull; }
+                S.planes = d_planes + ao; S.tmp = d_tmp + ao; ao += (S.n + 15) & ~15ull;
+            }
+        }
+        std::vector<uint8_t> meta (meta_bytes);
+        auto put = [&] (const void *dev, const void *src, size_t bytes) { if (bytes) memcpy (meta.data () + ((const uint8_t *)dev - (e->ws + meta_off)), src, bytes); };
+        put (P.sections, S2.data (), n * sizeof (DecSection));
+        put (P.rans_list, rlist.data (), rlist.size () * 4);
+        put (P.arith_list, alist.data (), alist.size () * 4);
+
+        P.n_sections = n; P.n_rans = (uint32_t)rlist.size (); P.n_arith = (uint32_t)alist.size ();
+        P.rans_gpw = pick_rans_gpw (P.n_rans); P.arith_lpw = pick_arith_lpw (P.n_arith);
+        P.parts = (n <= 64) ? 32 : (n <= 1024 ? 8 : 2);
+        P.arena = Arena { d_arena, (unsigned long long)arena_est, d_cursor, d_overflow };
+        P.ev_chain0 = e->ev0; P.ev_chain1 = e->ev1;
+
+        cudaStream_t st = e->stream;
+        memcpy (e->pin, meta.data (), meta_bytes);
+        CK (cudaMemcpyAsync (e->ws + meta_off, e->pin, meta_bytes, cudaMemcpyHostToDevice, st));
+        if (!devptr) {
+            int rc = stage_inputs (e, e->pin + ((meta_bytes + 255) & ~(size_t)255), n,
+                                   [&] (uint32_t i) { return (uint8_t *)S2[i].in; },
+                                   [&] (uint32_t i) { return (const uint8_t *)secs[i].in; },
+                                   [&] (uint32_t i) { return S2[i].in_len; });
+            if (rc) return rc;
+        }
+        CK (cudaMemsetAsync (d_cursor, 0, 512, st));
+
+        dec_run (P, st);
+        e->launches += P.launches;
+        CK (cudaGetLastError ());
+
+        std::vector<SectionResult> res (n);
+        int h_over = 0; unsigned long long h_cursor = 0;
+        CK (cudaMemcpyAsync (res.data (), P.results, n * sizeof (SectionResult), cudaMemcpyDeviceToHost, st));
+        CK (cudaMemcpyAsync (&h_over, d_overflow, sizeof (int), cudaMemcpyDeviceToHost, st));
+        CK (cudaMemcpyAsync (&h_cursor, d_cursor, sizeof h_cursor, cudaMemcpyDeviceToHost, st));
+        if (!devptr)
+            for (uint32_t i = 0; i < n; i++) CK (cudaMemcpyAsync (secs[i].out, S2[i].out, S2[i].n, cudaMemcpyDeviceToHost, st));
+        CK (cudaStreamSynchronize (st));
+        if (h_over) { arena_est = (size_t)h_cursor + (h_cursor >> 2) + ((size_t)1 << 20); e->arena_hint_dec = arena_est; continue; }
+        float ms = 0; cudaEventElapsedTime (&ms, e->ev0, e->ev1); e->last_chain_ms = ms;
+        int rc = GZB_OK;
+        for (uint32_t i = 0; i < n; i++) {
+            secs[i].status = res[i].status; secs[i].out_len = res[i].status ? 0 : res[i].out_len;
+            if (res[i].status) { rc = GZB_E_CORRUPT; e->err = "malformed compressed section"; }
+        }
+        return rc;
+    }
+    e->err = "device arena kept overflowing";
+    return GZB_E_CUDA;
+}

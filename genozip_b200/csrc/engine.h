@@ -1,0 +1,20 @@
+// engine.h — the per-(host thread, GPU) engine behind the opaque gzb_engine of include/gzb200.h
+#pragma once
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+
+struct gzb_engine {
+    int          device = 0;
+    int          sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t  ev0 = nullptr, ev1 = nullptr;      // bracket the chain kernels of the last batch
+    uint8_t     *ws = nullptr;   size_t ws_cap = 0; // device workspace (grow-only)
+    uint8_t     *pin = nullptr;  size_t pin_cap = 0;// pinned host staging (grow-only)
+    std::string  err;
+    uint64_t     launches = 0;
+    float        last_chain_ms = 0;
+    size_t       arena_hint = 0, arena_hint_dec = 0;
+};
+
+int engine_reserve (gzb_engine *e, size_t ws_bytes, size_t pin_bytes);

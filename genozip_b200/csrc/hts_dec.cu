@@ -1,0 +1,539 @@
+// hts_dec.cu — decode side of the htscodecs "4x16" rANS / adaptive-arithmetic containers on sm_100a.
+//
+// Bit-exact inverse of reference rans_uncompress_to_4x16 (src/htscodecs/rANS_static4x16pr.c:1358-1642) and
+// arith_uncompress_to (src/htscodecs/arith_dynamic.c:860-1104) for every container genozip's order bytes can
+// produce (PACK, STRIPE N=4, CAT, NOSZ, arithmetic RLE).  Phases over all sections of a batch:
+//
+//   parse containers → build decode tables / init models → rANS chains / arithmetic chains → raw copies
+//   → unpack → unstripe
+#include "gzb_internal.cuh"
+#include "hts_enc.cuh"
+
+namespace gzb {
+
+__device__ __forceinline__ uint32_t get_varint (const uint8_t *p, const uint8_t *end, uint32_t *v)   // varint.h:267-300
+{
+    const uint8_t *s = p;
+    uint32_t acc = 0; int limit = 6; uint8_t c;
+    if (p >= end) { *v = 0; return 0; }
+    do { c = *p++; acc = (acc << 7) | (c & 0x7f); } while ((c & 0x80) && p < end && --limit > 0);
+    *v = acc;
+    return (uint32_t)(p - s);
+}
+
+// ------------------------------------------------------------------------------------------------ container parse
+// one non-STRIPE container (:1441-1551 / arith_dynamic.c:945-1025)
+__device__ int parse_leaf (const uint8_t *in, uint32_t in_len, uint32_t expect, uint8_t coder,
+                           uint8_t *fin, uint8_t *tmp, DecLeaf &L)
+{
+    const uint8_t *end = in + in_len;
+    L.valid = 1; L.coder = coder; L.err = 0;
+    L.lut = nullptr; L.sfb = nullptr; L.fb = nullptr; L.models = nullptr;
+    if (!in_len) return -1;
+    uint32_t flags = *in++;
+    if (flags & F_STRIPE) return -1;                                     // nested STRIPE is never produced
+    if (coder == CODER_ARITH && (flags & F_EXT)) return -1;
+    if (coder == CODER_RANS && (flags & F_RLE)) return -1;               // rANS RLE is never requested by genozip
+    L.order = (uint8_t)(flags & (coder == CODER_ARITH ? 3u : 1u));
+    L.cat = (flags & F_CAT) != 0; L.rle = (flags & F_RLE) != 0; L.pack = (flags & F_PACK) != 0;
+    uint32_t osz = expect;
+    if (!(flags & F_NOSZ)) { in += get_varint (in, end, &osz); if (osz != expect) return -1; }
+    L.ulen = osz; L.body_ulen = osz; L.per_byte = 1;
+    L.fin = fin; L.dst = fin;
+    if (L.pack) {                                                        // hts_unpack_meta (pack.c:168-201)
+        if (in >= end) return -1;
+        uint32_t ns = in[0] ? in[0] : 256;
+        if (ns <= 16) {
+            L.per_byte = ns <= 1 ? 0 : ns <= 2 ? 8 : ns <= 4 ? 4 : 2;
+            if (in + 1 + ns > end) return -1;
+            for (uint32_t i = 0; i < 16; i++) L.map[i] = i < ns ? in[1 + i] : 0;
+            in += 1 + ns;
+        }
+        else { L.per_byte = 1; in += 1; }
+        uint32_t psz;
+        in += get_varint (in, end, &psz);
+        if (psz > osz) return -1;
+        L.body_ulen = psz;
+        L.dst = tmp;
+    }
+    L.body = in;
+    L.body_len = (uint32_t)(end - in);
+    if (!L.body_len) L.body_ulen = 0;                                    // :1598-1601
+    if (L.cat && L.body_ulen > L.body_len) return -1;
+    return 0;
+}
+
+__global__ void k_dec_parse (const DecSection *secs, DecLeaf *leaves, SectionResult *res, uint32_t n_secs)
+{
+    uint32_t si = blockIdx.x * blockDim.x + threadIdx.x;
+    if (si >= n_secs) return;
+    const DecSection &S = secs[si];
+    DecLeaf *L = leaves + 4 * (size_t)si;
+    for (int i = 0; i < 4; i++) L[i].valid = 0;
+    res[si].out_len = S.n; res[si].status = 0;
+    if (!S.in_len) { res[si].status = -4; return; }
+    if (!(S.in[0] & F_STRIPE)) {
+        if (parse_leaf (S.in, S.in_len, S.n, S.coder, S.out, S.tmp, L[0])) { L[0].valid = 0; res[si].status = -4; }
+        return;
+    }
+    // STRIPE (:1366-1439): flags, varint ulen, N, N x varint clen, N sub-containers
+    const uint8_t *end = S.in + S.in_len;
+    uint32_t h = 1, ulen;
+    h += get_varint (S.in + h, end, &ulen);
+    if (h >= S.in_len || ulen != S.n) { res[si].status = -4; return; }
+    uint32_t N = S.in[h++];
+    if (N != 4) { res[si].status = -4; return; }                         // genozip always writes N = 4 (:1166-1167)
+    uint32_t clen[4], tot = 0;
+    for (int i = 0; i < 4; i++) {
+        h += get_varint (S.in + h, end, &clen[i]);
+        if (h > S.in_len || clen[i] > S.in_len || clen[i] < 1) { res[si].status = -4; return; }
+        tot += clen[i];
+    }
+    if ((uint64_t)h + tot > S.in_len) { res[si].status = -4; return; }
+    uint32_t idx = 0;
+    const uint32_t end_off = h + tot;
+    for (int i = 0; i < 4; i++) {
+        uint32_t ul = ulen / 4 + ((ulen % 4) > (uint32_t)i);
+        // the reference hands each sub-decoder everything up to the end of the STRIPE container (:1425)
+        if (parse_leaf (S.in + h, end_off - h, ul, S.coder, S.planes + idx, S.tmp + idx, L[i])) { res[si].status = -4; L[i].valid = 0; }
+        h += clen[i];
+        idx += ul;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ rANS decode tables
+struct DTabSmem {
+    uint32_t F[256];
+    uint32_t F0[256];
+    uint32_t start[256];
+    uint32_t scan[8];
+    uint32_t T, ok, consumed, nctx;
+    const uint8_t *p;
+};
+
+// decode_alphabet (:205-252).  returns bytes consumed, 0 on error
+__device__ uint32_t get_alphabet (const uint8_t *p, const uint8_t *end, uint32_t *F)
+{
+    if (p >= end) return 0;
+    const uint8_t *s = p;
+    int run = 0, j = *p++;
+    do {
+        F[j] = 1;
+        if (p >= end) return 0;
+        if (!run && j + 1 == *p) { if (p + 1 >= end) return 0; j = *p++; run = *p++; }
+        else if (run) { run--; if (++j > 255) return 0; }
+        else j = *p++;
+    } while (j);
+    return (uint32_t)(p - s);
+}
+
+// exclusive prefix over sm.F by symbol → sm.start; returns total (all threads)
+__device__ uint32_t scan_F (DTabSmem &sm)
+{
+    const int tid = threadIdx.x;
+    uint32_t f = sm.F[tid], v = f;
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync (0xffffffffu, v, o); if ((tid & 31) >= o) v += t; }
+    if ((tid & 31) == 31) sm.scan[tid >> 5] = v;
+    __syncthreads ();
+    uint32_t base = 0, total = 0;
+    for (int w = 0; w < 8; w++) { if (w < (tid >> 5)) base += sm.scan[w]; total += sm.scan[w]; }
+    sm.start[tid] = base + v - f;
+    __syncthreads ();
+    return total;
+}
+
+// order-0 table at p (:526-549): fills lut[4096]; returns bytes consumed (0 = error).  Whole CTA.
+__device__ uint32_t build_dec_o0 (DTabSmem &sm, const uint8_t *p, const uint8_t *end, uint32_t *lut)
+{
+    const int tid = threadIdx.x;
+    sm.F[tid] = 0;
+    __syncthreads ();
+    if (tid == 0) {
+        const uint8_t *s = p;
+        uint32_t k = get_alphabet (p, end, sm.F), tot = 0;
+        sm.ok = k != 0;
+        p += k;
+        if (k) for (int j = 0; j < 256; j++) if (sm.F[j]) { p += get_varint (p, end, &sm.F[j]); tot += sm.F[j]; }
+        sm.T = tot; sm.consumed = (uint32_t)(p - s);
+    }
+    __syncthreads ();
+    if (!sm.ok || !sm.T || sm.T > 4096 || (sm.T & (sm.T - 1))) return 0;
+    int sh = 0; for (uint32_t t = sm.T; t < 4096; t *= 2) sh++;         // normalise_freq_shift (:165-176)
+    sm.F[tid] <<= sh;
+    __syncthreads ();
+    uint32_t total = scan_F (sm);
+    if (total != 4096) return 0;
+    uint32_t f = sm.F[tid], st = sm.start[tid];
+    for (uint32_t y = 0; y < f; y++) lut[st + y] = (uint32_t)tid | ((f - 1) << 8) | (y << 20);
+    __syncthreads ();
+    return sm.consumed;
+}
+
+// 4 lanes = 4 states decode n symbols from `in` (payload at off) with an order-0 LUT; used for the compressed O1 table
+__device__ void rans_o0_decode_lanes (const uint8_t *body, uint32_t body_len, uint32_t off, const uint32_t *lut,
+                                      uint8_t *out, uint32_t n, int lane, bool valid)
+{
+    const int k = lane & 3, gshift = lane & ~3;
+    uint32_t x = 0, poff = off + 16;
+    if (valid) { const uint8_t *q = body + off + 4 * k; x = q[0] | (q[1] << 8) | (q[2] << 16) | ((uint32_t)q[3] << 24); }
+    uint32_t steps = valid ? (n + 3) >> 2 : 0, maxsteps = steps;
+    for (int o = 16; o; o >>= 1) maxsteps = max (maxsteps, __shfl_xor_sync (0xffffffffu, maxsteps, o));
+    for (uint32_t s = 0; s < maxsteps; s++) {
+        uint32_t idx = 4 * s + k;
+        bool act = valid && s < steps && idx < n;
+        if (act) {
+            uint32_t e = lut[x & 4095];
+            x = (((e >> 8) & 0xfff) + 1) * (x >> 12) + (e >> 20);
+            out[idx] = (uint8_t)e;
+        }
+        bool need = act && x < RANS_L;
+        uint32_t g = (__ballot_sync (0xffffffffu, need) >> gshift) & 0xfu;
+        if (need) {
+            uint32_t a = poff + 2 * __popc (g & ((1u << k) - 1));
+            if (a + 1 < body_len) x = (x << 16) | body[a] | (body[a + 1] << 8);          // RansDecRenormSafe
+        }
+        poff += 2 * __popc (g);
+    }
+}
+
+// one CTA per leaf slot
+__global__ void __launch_bounds__(256) k_dec_tables (DecLeaf *leaves, SectionResult *res, uint32_t n_slots, Arena arena)
+{
+    if (blockIdx.x >= n_slots) return;
+    DecLeaf &L = leaves[blockIdx.x];
+    if (!L.valid || L.coder != CODER_RANS || L.cat || !L.body_ulen) return;
+    __shared__ DTabSmem sm;
+    __shared__ uint8_t *s_ptr[4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint8_t *body = L.body, *end = body + L.body_len;
+    const uint32_t si = blockIdx.x >> 2;
+    bool fail = false;
+
+    if (L.body_len < 16) fail = true;
+    else if (!L.order) {                                                  // ---- order 0 (:498-558)
+        if (tid == 0) s_ptr[0] = arena.alloc (4096 * 4);
+        __syncthreads ();
+        if (!s_ptr[0]) return;                                            // arena overflow: host replays the batch
+        uint32_t used = build_dec_o0 (sm, body, end - 8, reinterpret_cast<uint32_t *>(s_ptr[0]));
+        if (!used || used + 16 > L.body_len) fail = true;
+        else if (tid == 0) { L.lut = reinterpret_cast<uint32_t *>(s_ptr[0]); L.payload_off = used; }
+    }
+    else {                                                                // ---- order 1 (:883-1019)
+        const uint32_t shift = body[0] >> 4;
+        const bool comp = body[0] & 1;
+        const uint8_t *p = body + 1, *fend = end, *tab_end = nullptr;
+        if (shift != 10 && shift != 12) fail = true;
+        if (!fail && comp) {
+            uint32_t usz, csz;
+            p += get_varint (p, end, &usz);
+            p += get_varint (p, end, &csz);
+            if (p + csz + 16 > end || usz > (1u << 20) || csz < 16) fail = true;
+            if (!fail) {
+                if (tid == 0) { s_ptr[0] = arena.alloc (4096 * 4); s_ptr[1] = arena.alloc (usz + 16); }
+                __syncthreads ();
+                if (!s_ptr[0] || !s_ptr[1]) return;
+                uint32_t *nlut = reinterpret_cast<uint32_t *>(s_ptr[0]);
+                uint32_t used = build_dec_o0 (sm, p, p + csz - 8, nlut);
+                if (!used || used + 16 > csz) fail = true;
+                else {
+                    if (warp == 0) rans_o0_decode_lanes (p, csz, used, nlut, s_ptr[1], usz, lane, lane < 4);
+                    __syncthreads ();
+                    tab_end = p + csz;
+                    p = s_ptr[1]; fend = s_ptr[1] + usz;
+                }
+            }
+        }
+        if (!fail) {
+            // alphabet of all symbols, then per present context the frequencies (:970-1011)
+            sm.F0[tid] = 0;
+            __syncthreads ();
+            if (tid == 0) {
+                uint32_t k = get_alphabet (p, fend, sm.F0);
+                sm.ok = k != 0 && p + k < fend;
+                sm.p = p + k;
+                uint32_t nc = 0;
+                for (int i = 0; i < 256; i++) if (sm.F0[i]) nc++;
+                sm.nctx = nc;
+                s_ptr[2] = s_ptr[3] = nullptr;
+                if (sm.ok) {
+                    s_ptr[2] = arena.alloc ((unsigned long long)nc << shift);
+                    s_ptr[3] = arena.alloc ((unsigned long long)nc * 256 * 4);
+                }
+            }
+            __syncthreads ();
+            if (!sm.ok) fail = true;
+            else if (!s_ptr[2] || !s_ptr[3]) return;
+        }
+        if (!fail) {
+            uint8_t  *sfb = s_ptr[2];
+            uint32_t *fb  = reinterpret_cast<uint32_t *>(s_ptr[3]);
+            uint32_t row = 0;
+            for (int i = 0; i < 256 && !fail; i++) {
+                if (!sm.F0[i]) continue;                                  // uniform: F0 is shared
+                sm.F[tid] = 0;
+                __syncthreads ();
+                if (tid == 0) {                                           // decode_freq_d (:324-355)
+                    const uint8_t *q = sm.p;
+                    uint32_t T = 0; int zrun = 0; bool ok = q < fend;
+                    for (int j = 0; ok && j < 256 && q < fend; j++) {
+                        if (!sm.F0[j]) continue;
+                        uint32_t f;
+                        if (zrun) { f = 0; zrun--; }
+                        else {
+                            q += get_varint (q, fend, &f);
+                            if (!f) { if (q >= fend) { ok = false; break; } zrun = *q++; }
+                        }
+                        sm.F[j] = f; T += f;
+                    }
+                    sm.ok = ok; sm.T = T; sm.p = q;
+                }
+                __syncthreads ();
+                if (!sm.ok) { fail = true; break; }
+                if (tid == 0) L.ctxrank[i] = (uint8_t)row;
+                const uint32_t T = sm.T;
+                if (T) {
+                    if (T > (1u << shift) || (T & (T - 1))) { fail = true; break; }
+                    int sh = 0; for (uint32_t t = T; t < (1u << shift); t *= 2) sh++;
+                    sm.F[tid] <<= sh;
+                    __syncthreads ();
+                    uint32_t total = scan_F (sm);
+                    if (total != (1u << shift)) { fail = true; break; }
+                    uint32_t f = sm.F[tid], st = sm.start[tid];
+                    uint8_t *srow = sfb + ((size_t)row << shift);
+                    for (uint32_t y = 0; y < f; y++) srow[st + y] = (uint8_t)tid;
+                    fb[row * 256 + tid] = f | (st << 16);
+                }
+                row++;
+                __syncthreads ();
+            }
+            if (!fail) {
+                const uint8_t *pay = tab_end ? tab_end : sm.p;
+                if (pay + 16 > end) fail = true;
+                else if (tid == 0) { L.sfb = sfb; L.fb = fb; L.shift = (uint8_t)shift; L.payload_off = (uint32_t)(pay - body); }
+            }
+        }
+    }
+    if (fail && tid == 0) { L.err = -4; res[si].status = -4; }
+}
+
+// ------------------------------------------------------------------------------------------------ rANS chain decoder
+// 4 lanes = 4 states; the shared forward read pointer is reproduced with a 4-wide ballot (states renormalise in
+// order 0,1,2,3 within a step, :578-594 / :1062-1066).
+__global__ void k_rans_decode (DecLeaf *leaves, const uint32_t *list, uint32_t n_list, int gpw)
+{
+    const int lane = threadIdx.x, grp = lane >> 2, k = lane & 3, gshift = lane & ~3;
+    const uint32_t slot = blockIdx.x * gpw + grp;
+    bool valid = false, o1 = false;
+    const uint8_t *body = nullptr; uint8_t *out = nullptr;
+    uint32_t n = 0, body_len = 0, poff = 0, shift = 12;
+    const uint32_t *lut = nullptr; const uint8_t *sfb = nullptr; const uint32_t *fb = nullptr; const uint8_t *crank = nullptr;
+    if (grp < gpw && slot < n_list) {
+        const DecLeaf &L = leaves[list[slot]];
+        if (L.valid && !L.err && !L.cat && L.body_ulen && (L.lut || L.sfb)) {
+            valid = true; o1 = L.order; body = L.body; body_len = L.body_len; out = L.dst; n = L.body_ulen;
+            poff = L.payload_off; lut = L.lut; sfb = L.sfb; fb = L.fb; shift = L.shift; crank = L.ctxrank;
+        }
+    }
+    uint32_t x = 0;
+    if (valid) { const uint8_t *q = body + poff + 4 * k; x = q[0] | (q[1] << 8) | (q[2] << 16) | ((uint32_t)q[3] << 24); poff += 16; }
+    const uint32_t q4 = n >> 2;
+    uint32_t steps = !valid ? 0 : o1 ? q4 + (n - 4 * q4) : (n + 3) >> 2;
+    uint32_t maxsteps = steps;
+    for (int o = 16; o; o >>= 1) maxsteps = max (maxsteps, __shfl_xor_sync (0xffffffffu, maxsteps, o));
+    const uint32_t mask = (1u << shift) - 1;
+    uint32_t ctx = 0;                                                     // O1: previous symbol of this chain (context 0 first, :1029)
+    for (uint32_t s = 0; s < maxsteps; s++) {
+        bool act;
+        if (!o1) {
+            uint32_t idx = 4 * s + k;
+            act = valid && idx < n;
+            if (act) {
+                uint32_t e = lut[x & 4095];
+                x = (((e >> 8) & 0xfff) + 1) * (x >> 12) + (e >> 20);
+                out[idx] = (uint8_t)e;
+            }
+        }
+        else {
+            // chains 0-2 decode q4 symbols; chain 3 continues alone over the remainder (:1076-1083)
+            uint32_t idx = (s < q4) ? k * q4 + s : (k == 3 ? 3 * q4 + s : 0xffffffffu);
+            act = valid && s < steps && idx != 0xffffffffu && idx < n;
+            if (act) {
+                uint32_t m = x & mask, row = crank[ctx];
+                uint32_t c = sfb[((size_t)row << shift) + m];
+                uint32_t e = fb[row * 256 + c];
+                x = (e & 0xffffu) * (x >> shift) + m - (e >> 16);
+                out[idx] = (uint8_t)c;
+                ctx = c;
+            }
+        }
+        bool need = act && x < RANS_L;
+        uint32_t g = (__ballot_sync (0xffffffffu, need) >> gshift) & 0xfu;
+        if (need) {
+            uint32_t a = poff + 2 * __popc (g & ((1u << k) - 1));
+            if (a + 1 < body_len) x = (x << 16) | body[a] | (body[a + 1] << 8);
+        }
+        poff += 2 * __popc (g);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ arithmetic decoder
+#define AR_MAXF  65519u
+#define AR_STEP  16u
+struct RCDec { uint32_t code, range; const uint8_t *in, *end; };
+
+__device__ __forceinline__ uint32_t model_decode (uint32_t *m, RCDec &rc)  // c_simple_model.h:148-179 + RC_GetFreq/RC_Decode
+{
+    uint32_t tot = m[0];
+    uint32_t freq = (tot && rc.range >= tot) ? rc.code / (rc.range /= tot) : 0;
+    if (freq > AR_MAXF) return 0;
+    uint32_t i = 2, e = m[2], acc = e & 0xffffu;
+    while (acc <= freq) { e = m[++i]; if (!(e & 0xffffu) && !(e >> 16)) return 0; acc += e & 0xffffu; }   // ran off the live entries: corrupt
+    uint32_t f = e & 0xffffu;
+    acc -= f;
+    rc.code  -= acc * rc.range;
+    rc.range *= f;
+    while (rc.range < (1u << 24)) {
+        if (rc.in >= rc.end) break;
+        rc.code = (rc.code << 8) + *rc.in++;
+        rc.range <<= 8;
+    }
+    f += AR_STEP; tot += AR_STEP;
+    if (tot > AR_MAXF) {
+        m[i] = (e & 0xffff0000u) | f;
+        tot = 0;
+        for (uint32_t j = 2; (m[j] & 0xffffu); j++) { uint32_t g = m[j] & 0xffffu; g -= g >> 1; m[j] = (m[j] & 0xffff0000u) | g; tot += g; }
+        f = m[i] & 0xffffu;
+    }
+    m[0] = tot;
+    uint32_t prev = m[i - 1];
+    if (f > (prev & 0xffffu)) { m[i - 1] = (e & 0xffff0000u) | f; m[i] = prev; }
+    else m[i] = (e & 0xffff0000u) | f;
+    return e >> 16;
+}
+
+__device__ void dmodel_init (uint32_t *m, uint32_t maxs)
+{
+    m[0] = maxs; m[1] = AR_MAXF;
+    for (uint32_t i = 0; i < maxs; i++) m[2 + i] = 1u | (i << 16);
+    m[2 + maxs] = 0;
+}
+
+__global__ void k_arith_dec_init (DecLeaf *leaves, uint32_t n_slots, Arena arena)
+{
+    if (blockIdx.x >= n_slots) return;
+    DecLeaf &L = leaves[blockIdx.x];
+    if (!L.valid || L.coder != CODER_ARITH || L.cat || !L.body_ulen || L.err) return;
+    __shared__ uint32_t *s_m;
+    const uint32_t maxs = L.body[0] ? L.body[0] : 256, stride = maxs + 3, nctx = L.order ? 256 : 1;
+    if (threadIdx.x == 0) { s_m = reinterpret_cast<uint32_t *>(arena.alloc (((unsigned long long)nctx * stride + 258 * 7) * 4)); L.models = s_m; L.nsym = (uint16_t)maxs; }
+    __syncthreads ();
+    if (!s_m) return;
+    for (uint32_t c = threadIdx.x; c < nctx; c += blockDim.x) dmodel_init (s_m + c * stride, maxs);
+    if (L.rle) for (uint32_t c = threadIdx.x; c < 258; c += blockDim.x) dmodel_init (s_m + nctx * stride + c * 7, 4);
+}
+
+__global__ void k_arith_decode (DecLeaf *leaves, const uint32_t *list, uint32_t n_list, int lpw)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (lane >= lpw) return;
+    const uint32_t slot = warp * lpw + lane;
+    if (slot >= n_list) return;
+    DecLeaf &L = leaves[list[slot]];
+    if (!L.valid || L.err || L.cat || !L.body_ulen || !L.models) return;
+    const uint32_t n = L.body_ulen, maxs = L.nsym, stride = maxs + 3;
+    const bool o1 = L.order == 1, rle = L.rle;
+    uint32_t *lit = L.models, *run = lit + (o1 ? 256 : 1) * stride;
+    uint8_t *out = L.dst;
+    RCDec rc; rc.range = 0xffffffffu; rc.code = 0; rc.in = L.body + 1; rc.end = L.body + L.body_len;
+    if (rc.in + 5 > rc.end) rc.in = rc.end;                               // RC_StartDecode (c_range_coder.h:57-68)
+    else for (int i = 0; i < 5; i++) rc.code = (rc.code << 8) | *rc.in++;
+    uint32_t last = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        uint32_t s = model_decode (lit + (o1 ? last : 0) * stride, rc);
+        out[i] = (uint8_t)s; last = s;
+        if (!rle) continue;
+        uint32_t r = 0, part, rctx = last;                                // arith_dynamic.c:473-482 / :591-599
+        do {
+            part = model_decode (run + rctx * 7, rc);
+            if (rctx == last) rctx = 256; else rctx += (rctx < 257);
+            r += part;
+        } while (part == 3 && r < n);
+        while (r-- && i + 1 < n) out[++i] = (uint8_t)last;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ post passes
+// raw (CAT) bodies; grid (slots, parts)
+__global__ void k_dec_cat (const DecLeaf *leaves, uint32_t n_slots)
+{
+    if (blockIdx.x >= n_slots) return;
+    const DecLeaf &L = leaves[blockIdx.x];
+    if (!L.valid || L.err || !L.cat) return;
+    uint32_t n = L.body_ulen, part = ((n + gridDim.y - 1) / gridDim.y + 15) & ~15u;
+    uint32_t b = blockIdx.y * part, e = min (b + part, n);
+    for (uint32_t i = b + threadIdx.x; i < e; i += blockDim.x) L.dst[i] = L.body[i];
+}
+
+// hts_unpack (pack.c:214-351); grid (slots, parts)
+__global__ void k_dec_unpack (const DecLeaf *leaves, SectionResult *res, uint32_t n_slots)
+{
+    if (blockIdx.x >= n_slots) return;
+    const DecLeaf &L = leaves[blockIdx.x];
+    if (!L.valid || L.err || !L.pack) return;
+    const uint32_t per = L.per_byte;
+    uint32_t n = (per == 1) ? L.body_ulen : L.ulen;
+    if (per == 1 && n != L.ulen) { if (!threadIdx.x && !blockIdx.y) res[blockIdx.x >> 2].status = -4; return; }
+    if (per > 1 && (uint64_t)(n + per - 1) / per > L.body_ulen) { if (!threadIdx.x && !blockIdx.y) res[blockIdx.x >> 2].status = -4; return; }
+    uint32_t part = ((n + gridDim.y - 1) / gridDim.y + 15) & ~15u;
+    uint32_t b = blockIdx.y * part, e = min (b + part, n);
+    const uint8_t *src = L.dst; uint8_t *dst = L.fin;
+    if (per == 1) { for (uint32_t i = b + threadIdx.x; i < e; i += blockDim.x) dst[i] = src[i]; return; }
+    if (per == 0) { for (uint32_t i = b + threadIdx.x; i < e; i += blockDim.x) dst[i] = L.map[0]; return; }
+    const uint32_t bits = 8 / per, m = (1u << bits) - 1;
+    for (uint32_t i = b + threadIdx.x; i < e; i += blockDim.x)
+        dst[i] = L.map[(src[i / per] >> ((i % per) * bits)) & m];
+}
+
+// unstripe (utils.h:41-73); grid (sections, parts)
+__global__ void k_dec_unstripe (const DecSection *secs, const SectionResult *res, uint32_t n_secs)
+{
+    if (blockIdx.x >= n_secs) return;
+    const DecSection &S = secs[blockIdx.x];
+    if (res[blockIdx.x].status || !S.in_len || !(S.in[0] & F_STRIPE)) return;
+    const uint32_t n = S.n;
+    uint32_t idx[4], acc = 0;
+    for (int j = 0; j < 4; j++) { idx[j] = acc; acc += n / 4 + ((n % 4) > (uint32_t)j); }
+    uint32_t part = ((n + gridDim.y - 1) / gridDim.y + 15) & ~15u;
+    uint32_t b = blockIdx.y * part, e = min (b + part, n);
+    for (uint32_t i = b + threadIdx.x; i < e; i += blockDim.x) S.out[i] = S.planes[idx[i & 3] + (i >> 2)];
+}
+
+// ------------------------------------------------------------------------------------------------ launcher
+#define LAUNCH(kern, grid, block, ...) do { kern<<<(grid), (block), 0, st>>>(__VA_ARGS__); P.launches++; } while (0)
+
+void dec_run (DecPlanDev &P, cudaStream_t st)
+{
+    const uint32_t ns = P.n_sections, nslots = 4 * ns;
+    if (!ns) return;
+    LAUNCH (k_dec_parse, (ns + 127) / 128, 128, P.sections, P.leaves, P.results, ns);
+    if (P.n_rans)  LAUNCH (k_dec_tables, nslots, 256, P.leaves, P.results, nslots, P.arena);
+    if (P.n_arith) LAUNCH (k_arith_dec_init, nslots, 256, P.leaves, nslots, P.arena);
+    cudaEventRecord (P.ev_chain0, st);
+    if (P.n_rans) {
+        int gpw = P.rans_gpw;
+        LAUNCH (k_rans_decode, (P.n_rans + gpw - 1) / gpw, 32, P.leaves, P.rans_list, P.n_rans, gpw);
+    }
+    if (P.n_arith) {
+        int lpw = P.arith_lpw;
+        uint32_t warps = (P.n_arith + lpw - 1) / lpw;
+        LAUNCH (k_arith_decode, (warps + 3) / 4, 128, P.leaves, P.arith_list, P.n_arith, lpw);
+    }
+    cudaEventRecord (P.ev_chain1, st);
+    dim3 g (nslots, P.parts), gs (ns, P.parts);
+    LAUNCH (k_dec_cat, g, 256, P.leaves, nslots);
+    LAUNCH (k_dec_unpack, g, 256, P.leaves, P.results, nslots);
+    LAUNCH (k_dec_unstripe, gs, 256, P.sections, P.results, ns);
+}
+
+} // namespace gzb

@@ -1,0 +1,41 @@
+// hts_enc.cuh — host-visible plan structures shared between api.cu and the hts kernels
+#pragma once
+#include "gzb_internal.cuh"
+
+namespace gzb {
+
+struct EncPlanDev {              // device pointers of one encode batch
+    EncSection    *sections;   uint32_t n_sections;
+    EncLeaf       *leaves;     uint32_t n_leaves;
+    EncLeafDyn    *dyn;
+    Tile          *tiles;      uint32_t n_tiles;          // TILE-sized pieces of every leaf input
+    Tile          *stripe_tiles; uint32_t n_stripe_tiles; // TILE-sized pieces of every STRIPE section (Tile.leaf = section)
+    uint32_t      *rans_list;  uint32_t n_rans;           // rANS leaves, longest first
+    uint32_t      *arith_list; uint32_t n_arith;          // arithmetic leaves, longest first
+    SectionResult *results;
+    CopySeg       *segs;
+    uint8_t       *stripe_hdr;
+    Arena          arena;
+    int            rans_gpw, arith_lpw, copy_parts;
+    bool           any_pack, any_o1;
+    cudaEvent_t    ev_chain0, ev_chain1;
+    uint64_t       launches;
+};
+
+struct DecPlanDev {
+    DecSection    *sections;   uint32_t n_sections;
+    DecLeaf       *leaves;                                // 4 per section
+    uint32_t      *rans_list;  uint32_t n_rans;           // leaf slots of rANS sections, largest section first
+    uint32_t      *arith_list; uint32_t n_arith;
+    SectionResult *results;
+    Arena          arena;
+    int            rans_gpw, arith_lpw, parts;
+    cudaEvent_t    ev_chain0, ev_chain1;
+    uint64_t       launches;
+};
+
+void upload_log_tables (const double *l10, const double *l12);
+void enc_run (EncPlanDev &P, cudaStream_t st);
+void dec_run (DecPlanDev &P, cudaStream_t st);
+
+} // namespace gzb

@@ -1,0 +1,215 @@
+/* gzb200.h — C-ABI of libgzb200.so: a B200 (sm_100a) implementation of genozip's per-VBlock codec path.
+ *
+ * This is the drop-in boundary.  Two layers:
+ *
+ *  (1) FLAT entry points — plain pointers and sizes, no genozip types, batched ("sections") because one
+ *      launch per section is launch-latency-bound.  These are what a cgo/JNI/ctypes binding would bind, and
+ *      what the thin adapter inside genozip calls.
+ *  (2) PLUG-IN entry points with exactly the reference's COMPRESS / UNCOMPRESS / est_size signatures
+ *      (reference src/codec.h:17-40) so that CODEC_ARGS (src/codec.h:47-115) can point at them; genozip's
+ *      VBlock/Context/SectionHeader/Buffer are opaque here and are touched only through the accessor table
+ *      the adapter registers (gzb_plugin_host).  See INTEGRATION.md for the reference-side stub.
+ *
+ * There is NO CPU fallback: every entry point fails (non-zero return / GZB_E_NOCUDA) when no CUDA device
+ * or kernel image is available.
+ *
+ * Output contract: for a given (codec, uncompressed bytes) the compressed bytes are identical to those the
+ * reference codec function writes (rans_compress_to_4x16 / arith_compress_to and the genozip codecs built
+ * on them), and decompression is bit-exact.
+ */
+#ifndef GZB200_H
+#define GZB200_H
+#include <stdint.h>
+#include <stddef.h>
+#include <stdbool.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- codec ids: numeric values of the reference's `Codec` enum (src/genozip.h:322-360) ---- */
+enum {
+    GZB_CODEC_NONE = 1,
+    GZB_CODEC_RANB = 6,  GZB_CODEC_RANW = 7,  GZB_CODEC_RANb = 8,  GZB_CODEC_RANw = 9,
+    GZB_CODEC_ACGT = 10, GZB_CODEC_XCGT = 11, GZB_CODEC_DOMQ = 13, GZB_CODEC_PBWT = 15,
+    GZB_CODEC_ARTB = 16, GZB_CODEC_ARTW = 17, GZB_CODEC_ARTb = 18, GZB_CODEC_ARTw = 19,
+    GZB_CODEC_LONGR = 26,
+};
+
+/* ---- status codes ---- */
+enum {
+    GZB_OK = 0,
+    GZB_SOFT_FAIL   = 1,    /* output capacity < est_size: the reference returns false under soft_fail (src/compressor.c:90) */
+    GZB_E_NOCUDA    = -1,   /* no device / no sm_100a kernel image: the product never falls back to the CPU */
+    GZB_E_CUDA      = -2,   /* a CUDA call failed (see gzb_last_error) */
+    GZB_E_BADARG    = -3,
+    GZB_E_CORRUPT   = -4,   /* malformed compressed data (the reference ASSERTs, src/codec_htscodecs.c:106-111) */
+};
+
+typedef struct gzb_engine gzb_engine;   /* one per (host thread, GPU): a CUDA stream + reusable device arena */
+
+/* flags for the batch calls */
+#define GZB_DEVICE_PTRS  1u   /* in/out pointers are device pointers on the engine's GPU (inputs resident in HBM) */
+
+/* ---------------------------------------------------------------- lifecycle (SURVEY §8b "lifecycle") */
+int   gzb_device_count (void);                                    /* number of visible CUDA devices, 0 if none */
+int   gzb_engine_create (int device, gzb_engine **out);           /* GZB_E_NOCUDA if no usable device */
+void  gzb_engine_destroy (gzb_engine *e);
+const char *gzb_last_error (gzb_engine *e);                       /* e may be NULL: creation errors */
+void *gzb_engine_stream (gzb_engine *e);                          /* the cudaStream_t all work of this engine is ordered on */
+int   gzb_engine_sync (gzb_engine *e);
+int   gzb_vb_device (uint32_t vblock_i, int n_devices);           /* (vblock_i-1) mod n_devices — the dispatcher's round-robin */
+uint64_t gzb_kernel_launches (gzb_engine *e);                     /* kernels launched by this engine so far */
+/* Device-time of the dominant chain kernels of the LAST batch call, ms (CUDA events on the engine's stream) */
+float gzb_last_chain_ms (gzb_engine *e);
+
+/* ---------------------------------------------------------------- simple codecs: rANS 4x16 and adaptive arithmetic
+ * Replaces codec_{RANB,RANW,RANb,RANw,ARTB,ARTW,ARTb,ARTw}_compress (src/codec_htscodecs.c:77-94) →
+ * rans_compress_to_4x16 (src/htscodecs/rANS_static4x16pr.c:1151) / arith_compress_to (src/htscodecs/arith_dynamic.c:615),
+ * and codec_rans_uncompress / codec_arith_uncompress (src/codec_htscodecs.c:100-129). */
+typedef struct {
+    int32_t     codec;      /* GZB_CODEC_RANB … GZB_CODEC_ARTw */
+    int32_t     status;     /* out: GZB_OK / GZB_SOFT_FAIL / GZB_E_* */
+    const void *in;         /* uncompressed bytes (compress) or compressed bytes (uncompress) */
+    void       *out;
+    uint32_t    in_len;
+    uint32_t    out_cap;    /* compress: capacity of out (must be >= gzb_est_size(codec,in_len) or status=GZB_SOFT_FAIL);
+                               uncompress: the expected uncompressed length */
+    uint32_t    out_len;    /* out: bytes written */
+    uint32_t    reserved;
+} gzb_section;
+
+uint32_t gzb_est_size (int codec, uint64_t uncompressed_len);     /* codec_*_est_size (src/codec_htscodecs.c:26-33): 1 KB + bound */
+int gzb_compress_sections   (gzb_engine *e, gzb_section *secs, uint32_t n, uint32_t flags);
+int gzb_uncompress_sections (gzb_engine *e, gzb_section *secs, uint32_t n, uint32_t flags);
+
+/* ---------------------------------------------------------------- ACGT / XCGT (src/codec_acgt.c)
+ * pack:   codec_acgt_compress up to the sub-codec call (:64-163): bases → LE 2-bit words + exception stream.
+ *         `packed` receives gzb_acgt_packed_len(n) bytes; `x` (n bytes) may be NULL if the caller declares
+ *         acgt_no_x; *x_all_zero is set when the exception stream is all zero (=> header flag acgt_no_x, :136-140).
+ * unpack: codec_acgt_uncompress/codec_xcgt_uncompress after their sub-codec call (:185-248). x may be NULL. */
+uint64_t gzb_acgt_packed_len (uint64_t n_bases);
+int gzb_acgt_pack   (gzb_engine *e, const void *seq, uint64_t n_bases, void *packed, void *x, int *x_all_zero, uint32_t flags);
+int gzb_acgt_unpack (gzb_engine *e, const void *packed, const void *x, uint64_t n_bases, void *seq, uint32_t flags);
+
+/* ---------------------------------------------------------------- DOMQ (src/codec_domq.c)
+ * A VBlock's quality lines are given as a text buffer plus a (offset,len) table (H6 in SURVEY §7: never a per-line callback). */
+typedef struct {
+    const void     *txt;         /* buffer holding the quality strings (vb->txt_data or ctx->local) */
+    uint64_t        txt_len;
+    const uint64_t *line_off;    /* n_lines offsets into txt */
+    const uint32_t *line_len;    /* n_lines lengths (0 = skip line, :421) */
+    uint32_t        n_lines;
+    /* outputs of gzb_domq_prepare (codec_domq_prepare_normalize :252-293) */
+    uint8_t        *line_dom;    /* n_lines: compacted dom index per line */
+    uint8_t        *line_diverse;/* n_lines: 1 if dom < 85% of the line (:141,160) */
+    uint8_t         num_norm_qs; /* no_doms marker; section param = num_norm_qs|0x80 (:234) */
+    uint8_t         num_doms;
+    uint8_t         has_diverse;
+    uint8_t         pad;
+    uint8_t         denorm[95*95];    /* [num_doms][num_norm_qs] — base64-segged into DOMQRUNS by the host (:241-244) */
+    uint8_t         normalize[95*95]; /* [cdom*95 + q-32] */
+    /* outputs of gzb_domq_split (codec_domq_compress :379-500, before the sub-codec) */
+    void *qual;  uint32_t qual_cap,  qual_len;   /* QUAL.local     — capacity >= 2*total_len+1 */
+    void *runs;  uint32_t runs_cap,  runs_len;   /* DOMQRUNS.local — capacity >= total_len+1   */
+    void *mplx;  uint32_t mplx_cap,  mplx_len;   /* QUALMPLX.local — capacity >= n_lines       */
+    void *divr;  uint32_t divr_cap,  divr_len;   /* DIVRQUAL.local — capacity >= total_len     */
+} gzb_domq_vb;
+
+/* prepare: per-line histogram/dom on the GPU, per-dom rank tables on the host with libc qsort (tie order must
+ * match the reference's qsort call).  split: normalise + stream split on the GPU.  All VBs of the
+ * batch are processed together.  With GZB_DEVICE_PTRS txt/line tables/outputs are device pointers. */
+int gzb_domq_prepare (gzb_engine *e, gzb_domq_vb *vbs, uint32_t n_vbs, uint32_t flags);
+int gzb_domq_split   (gzb_engine *e, gzb_domq_vb *vbs, uint32_t n_vbs, uint32_t flags);
+
+/* codec_domq_reconstruct (:774-809) for all lines of a VB at once ("pre-decode the whole VB's QUAL
+ * into a staging buffer so that the per-line reconstructor is a memcpy").  line_len[] are the seq_len the
+ * reconstructor would be called with; out receives the concatenated quality strings. */
+typedef struct {
+    const void *qual;  uint32_t qual_len;
+    const void *runs;  uint32_t runs_len;
+    const void *mplx;  uint32_t mplx_len;
+    const void *divr;  uint32_t divr_len;
+    const uint8_t  *denorm;       /* [num_doms][num_norm_qs] (host memory) */
+    uint32_t        denorm_len;
+    uint8_t         num_norm_qs;  /* section param & 0x7f */
+    const uint32_t *line_len;
+    uint32_t        n_lines;
+    void           *out;          /* sum(line_len) bytes */
+    uint64_t        out_cap;
+} gzb_domq_piz_vb;
+int gzb_domq_reconstruct (gzb_engine *e, gzb_domq_piz_vb *vbs, uint32_t n_vbs, uint32_t flags);
+
+/* ---------------------------------------------------------------- PBWT (src/codec_pbwt.c)
+ * encode: codec_pbwt_compress (:244-287): haplotype matrix → RUNS (uint32) + FGRC ({allele:8,count:24}; the last
+ *         two words are the 64-bit matrix length, :274-276).  Host-endian words.
+ * decode: codec_pbwt_uncompress (:372-402): RUNS + FGRC (host-endian) → matrix. */
+int gzb_pbwt_encode (gzb_engine *e, const void *ht, uint32_t n_lines, uint32_t ht_per_line,
+                     uint32_t *runs, uint32_t runs_cap, uint32_t *n_runs,
+                     uint32_t *fgrc, uint32_t fgrc_cap, uint32_t *n_fgrc, uint32_t flags);
+int gzb_pbwt_decode (gzb_engine *e, const uint32_t *runs, uint32_t n_runs, const uint32_t *fgrc, uint32_t n_fgrc,
+                     uint32_t n_lines, void *ht, uint64_t ht_cap, uint64_t *ht_len, uint32_t flags);
+
+/* ---------------------------------------------------------------- LONGR (src/codec_longr.c, src/codec_longr_alg.c)
+ * encode: codec_longr_compress (:161-247) before its sub-codec: channel per base, stable sort of quals by channel.
+ * decode: codec_longr_reconstruct (:342-373) for all reads of a VB. */
+typedef struct {
+    const void     *txt;        /* buffer holding SEQ and QUAL strings */
+    uint64_t        txt_len;
+    const uint64_t *seq_off;    /* n_lines */
+    const uint64_t *qual_off;   /* n_lines (encode only) */
+    const uint32_t *len;        /* n_lines (seq_len == qual_len) */
+    const uint8_t  *is_rev;     /* n_lines or NULL */
+    uint32_t        n_lines;
+    uint8_t         value_to_bin[256];  /* codec_longr_segconf_calculate_bins (:66-136), computed once by the host */
+    void           *values;     /* sum(len) bytes: encode out / decode in */
+    uint32_t       *lens_be;    /* 65536 big-endian u32: encode out / decode in (:237-240) */
+    void           *qual_out;   /* decode: concatenated quality strings */
+} gzb_longr_vb;
+int gzb_longr_encode (gzb_engine *e, gzb_longr_vb *vbs, uint32_t n_vbs, uint32_t flags);
+int gzb_longr_decode (gzb_engine *e, gzb_longr_vb *vbs, uint32_t n_vbs, uint32_t flags);
+
+/* ================================================================ plug-in layer (reference signatures) */
+typedef struct VBlock        *VBlockP;          /* opaque genozip types */
+typedef struct Context       *ContextP;
+typedef union  SectionHeaderUnion *SectionHeaderP;
+typedef struct Buffer        *BufferP;
+typedef uint8_t Codec;                           /* src/genozip.h: packed enum */
+typedef enum { HARD_FAIL = 0, SOFT_FAIL = 1 } FailType;   /* src/genozip.h */
+typedef void LocalGetLineCB (VBlockP vb, ContextP ctx, uint32_t vb_line_i, char **line_data, uint32_t *line_data_len,
+                             uint32_t maximum_size, bool *is_rev);                                /* src/genozip.h:673-680 */
+
+/* what the ≤200-line adapter inside genozip registers once: the only code that knows genozip's struct layouts */
+typedef struct {
+    uint32_t (*vb_num_lines)  (VBlockP vb);                          /* vb->lines.len32 */
+    uint32_t (*vb_vblock_i)   (VBlockP vb);                          /* vb->vblock_i */
+    char    *(*buffer_data)   (BufferP buf);                         /* buf->data (pre-allocated by the caller, src/zfile.c:229) */
+    void     (*abort_msg)     (const char *msg);                     /* ABORT → error_assert_failed (src/error.c:420); NULL = abort() */
+} gzb_plugin_host;
+void gzb_plugin_register (const gzb_plugin_host *host, int n_devices);
+
+#define GZB_COMPRESS(f) bool f (VBlockP vb, ContextP ctx, SectionHeaderP header, const char *uncompressed, \
+    uint32_t *uncompressed_len, LocalGetLineCB get_line_cb, char *compressed, uint32_t *compressed_len, \
+    FailType soft_fail, const char *name)                                                          /* src/codec.h:17-27 */
+#define GZB_UNCOMPRESS(f) void f (VBlockP vb, ContextP ctx, Codec codec, uint8_t param, const char *compressed, \
+    uint32_t compressed_len, BufferP uncompressed_buf, uint64_t uncompressed_len, Codec sub_codec, const char *name) /* src/codec.h:29-38 */
+
+GZB_COMPRESS (gzb_codec_RANB_compress);  GZB_COMPRESS (gzb_codec_RANW_compress);
+GZB_COMPRESS (gzb_codec_RANb_compress);  GZB_COMPRESS (gzb_codec_RANw_compress);
+GZB_COMPRESS (gzb_codec_ARTB_compress);  GZB_COMPRESS (gzb_codec_ARTW_compress);
+GZB_COMPRESS (gzb_codec_ARTb_compress);  GZB_COMPRESS (gzb_codec_ARTw_compress);
+GZB_UNCOMPRESS (gzb_codec_rans_uncompress);
+GZB_UNCOMPRESS (gzb_codec_arith_uncompress);
+uint32_t gzb_codec_RANB_est_size (Codec codec, uint64_t uncompressed_len);   /* src/codec.h:40 */
+uint32_t gzb_codec_RANW_est_size (Codec codec, uint64_t uncompressed_len);
+uint32_t gzb_codec_RANb_est_size (Codec codec, uint64_t uncompressed_len);
+uint32_t gzb_codec_RANw_est_size (Codec codec, uint64_t uncompressed_len);
+uint32_t gzb_codec_ARTB_est_size (Codec codec, uint64_t uncompressed_len);
+uint32_t gzb_codec_ARTW_est_size (Codec codec, uint64_t uncompressed_len);
+uint32_t gzb_codec_ARTb_est_size (Codec codec, uint64_t uncompressed_len);
+uint32_t gzb_codec_ARTw_est_size (Codec codec, uint64_t uncompressed_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
