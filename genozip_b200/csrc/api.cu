@@ -158,6 +158,7 @@ constexpr size_t SMALL_COPY = 65536;   // host sections below this are gathered 
 uint32_t leaf_out_cap (uint8_t coder, uint32_t order_req, uint32_t n)
 {
     double base = 1.06 * n + 2048;
+    if (coder == CODER_ARITH) base = (double)n + 1024;                   // the arithmetic leaf stops once its body reaches n bytes
     if (coder == CODER_RANS && (order_req & 1)) {
         double tab = std::min (200.0 * 1024, 3.0 * n + 1024);      // O1 table and its nested-compression scratch
         base += 2 * tab + 1024;

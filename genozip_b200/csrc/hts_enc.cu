@@ -229,7 +229,7 @@ __global__ void k_leaf_prep (const EncLeaf *leaves, EncLeafDyn *dyn, uint32_t n_
                 D.hist1    = reinterpret_cast<uint32_t *>(arena.alloc ((unsigned long long)ns * ns * 4));
                 D.symtab   = reinterpret_cast<EncSym *>(arena.alloc ((unsigned long long)ns * ns * sizeof (EncSym)));
                 D.ctxbytes = arena.alloc ((unsigned long long)ns * CTXB);
-                if (!D.hist1 || !D.symtab || !D.ctxbytes) D.hist1 = nullptr;
+                if (!D.hist1 || !D.symtab || !D.ctxbytes) { D.hist1 = nullptr; D.symtab = nullptr; D.ctxbytes = nullptr; }
             }
             else D.symtab = reinterpret_cast<EncSym *>(arena.alloc (256 * sizeof (EncSym)));
         }
@@ -690,8 +690,13 @@ __global__ void k_arith_encode (const EncLeaf *leaves, EncLeafDyn *dyn, const ui
     if (!lit) return;
     out[0] = (uint8_t)maxs;                                               // arith_dynamic.c:105-110 (256 wraps to 0)
     RCEnc rc; rc.low = 0; rc.range = 0xffffffffu; rc.ffnum = 0; rc.cache = 0; rc.carry = 0; rc.out = out + 1;
+    // A body that reaches the input length is discarded for a raw copy (arith_dynamic.c:847-852), so encoding stops
+    // as soon as that is certain; this also bounds the scratch a hostile (expanding) input can touch.
+    const uint8_t *limit = out + n + 8;
+    bool expanded = false;
     uint32_t last = 0;
     for (uint32_t i = 0; i < n; ) {
+        if (rc.out + rc.ffnum > limit) { expanded = true; break; }
         uint32_t s = in[i];
         model_encode (lit + (o1 ? last : 0) * stride, rc, s);
         last = s; i++;
@@ -707,8 +712,8 @@ __global__ void k_arith_encode (const EncLeaf *leaves, EncLeafDyn *dyn, const ui
             if (c == 3 && r == 0) model_encode (run + rctx * 7, rc, 0);
         } while (r);
     }
-    for (int i = 0; i < 5; i++) rc_shift_low (rc);                        // RC_FinishEncode
-    D.tab_len = (uint32_t)(rc.out - out);                                 // whole body at the front of outbuf
+    if (!expanded) for (int i = 0; i < 5; i++) rc_shift_low (rc);         // RC_FinishEncode
+    D.tab_len = expanded ? n + 1 : (uint32_t)(rc.out - out);              // whole body at the front of outbuf
     D.payload_len = 0;
 }
 
