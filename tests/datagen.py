@@ -63,3 +63,101 @@ KINDS = ["skew8", "qual", "uniform256", "all256", "const", "two", "four", "sixte
          "u32le", "runs", "zeros_hi", "text"]
 EDGE_SIZES = [0, 1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 19, 20, 21, 22, 23, 31, 32, 33, 63, 64, 65, 100,
               255, 256, 257, 1000, 4095, 4096, 4097, 10000]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# VBlock-shaped synthetic inputs: what the segmenter hands to the codec path
+def fastq_vb(n_reads, read_len, seed, diverse_frac=0.03, lower_frac=0.0, n_frac=0.001):
+    """Illumina-like FASTQ VBlock: returns (seq, qual) as uint8 arrays of n_reads*read_len bytes (lines are
+    fixed length read_len).  QUAL: binned {F,:,,,#} with Markov run structure (P(stay)=0.97) so that DOMQ
+    triggers; a few lines are 'diverse'.  SEQ: uniform ACGT with n_frac 'N'."""
+    r = np.random.default_rng(seed)
+    n = n_reads * read_len
+    seq = np.frombuffer(b"ACGT", np.uint8)[r.integers(0, 4, size=n)].copy()
+    if n_frac:
+        seq[r.random(n) < n_frac] = ord("N")
+    if lower_frac:
+        m = r.random(n) < lower_frac
+        seq[m] = seq[m] + 32
+    syms = np.frombuffer(b"F:,#", np.uint8)
+    change = r.random(n) > 0.97
+    change[0] = True
+    pick = r.choice(4, size=n, p=[.88, .07, .04, .01])
+    last = np.maximum.accumulate(np.where(change, np.arange(n), 0))
+    qual = syms[pick[last]].copy().reshape(n_reads, read_len)
+    div = np.where(r.random(n_reads) < diverse_frac)[0]
+    for i in div:
+        qual[i] = syms[r.choice(4, size=read_len, p=[.4, .3, .2, .1])]
+    return seq, qual.reshape(-1)
+
+
+def line_table(n_reads, read_len, base=0):
+    off = (np.arange(n_reads, dtype=np.uint64) * np.uint64(read_len)) + np.uint64(base)
+    ln = np.full(n_reads, read_len, dtype=np.uint32)
+    return off, ln
+
+
+def ragged_quals(seed, n_lines=400):
+    """ragged lines incl. empty ones, several doms, long cross-line dom runs, all-dom tails"""
+    r = np.random.default_rng(seed)
+    lens = r.integers(0, 300, size=n_lines).astype(np.uint32)
+    lens[r.random(n_lines) < 0.1] = 0
+    parts = []
+    for L in lens:
+        dom = r.choice(np.frombuffer(b"FI?5", np.uint8), p=[.6, .2, .1, .1])
+        p = r.random()
+        if p < 0.5:
+            line = np.full(L, dom, np.uint8)
+            k = int(r.integers(0, 6))
+            if L and k:
+                line[r.integers(0, L, size=k)] = r.choice(np.frombuffer(b"#,:<", np.uint8), size=k)
+        elif p < 0.8:
+            line = np.where(r.random(L) < 0.9, dom, r.choice(np.frombuffer(b"#,:<AB", np.uint8), size=L)).astype(np.uint8)
+        else:
+            line = r.integers(33, 75, size=L).astype(np.uint8)
+        parts.append(line)
+    txt = np.concatenate(parts) if parts else np.zeros(0, np.uint8)
+    off = np.concatenate([[0], np.cumsum(lens[:-1], dtype=np.uint64)]).astype(np.uint64)
+    return txt, off, lens
+
+
+def haplotype_matrix(n_lines, n_samples, seed, ploidy=2, multi=False):
+    """VCF-like phased genotype matrix: copy model over haplotypes so PBWT runs are long."""
+    r = np.random.default_rng(seed)
+    w = n_samples * ploidy
+    ht = np.empty((n_lines, w), np.uint8)
+    cur = (r.random(w) < 0.1).astype(np.uint8)
+    for i in range(n_lines):
+        af = r.beta(0.3, 2.0)
+        col = (r.random(w) < af).astype(np.uint8)
+        # neighbours tend to share alleles: smooth with a random block structure
+        blocks = np.repeat(r.random(w // 8 + 1) < af, 8)[:w]
+        col = np.where(r.random(w) < 0.8, blocks.astype(np.uint8), col)
+        row = col + ord("0")
+        if multi and i % 7 == 0:
+            row[r.random(w) < 0.02] = ord("2")
+        if multi and i % 11 == 0:
+            row[r.random(w) < 0.01] = ord(".")
+        ht[i] = row
+    return ht
+
+
+def longread_vb(n_reads, mean_len, seed):
+    """Nanopore-like reads: lengths mean_len +-20%, quals from an AR(1) process over Phred 1..50."""
+    r = np.random.default_rng(seed)
+    lens = np.maximum(4, (mean_len * (1 + 0.2 * r.standard_normal(n_reads))).astype(np.int64)).astype(np.uint32)
+    n = int(lens.sum())
+    seq = np.frombuffer(b"ACGT", np.uint8)[r.integers(0, 4, size=n)].copy()
+    e = r.standard_normal(n) * 4.0
+    q = np.empty(n, np.float64)
+    acc = 20.0
+    # AR(1) via scipy-free recursion in blocks (vectorised with lfilter-like cumulative trick is overkill here)
+    phi = 0.9
+    x = np.zeros(n)
+    x[0] = e[0]
+    for i in range(1, min(n, 200000)):
+        x[i] = phi * x[i - 1] + e[i]
+    if n > 200000:
+        x[200000:] = np.resize(x[:200000], n - 200000)
+    q = np.clip(np.rint(20 + x), 1, 50).astype(np.uint8) + 33
+    return seq, q, lens

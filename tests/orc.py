@@ -40,6 +40,29 @@ def port():
         for nm in ("orc_rans_uncompress", "orc_arith_uncompress"):
             getattr(L, nm).restype = C.c_int
             getattr(L, nm).argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, u32p]
+        L.orc_acgt_packed_len.restype = C.c_uint64
+        L.orc_acgt_packed_len.argtypes = [C.c_uint64]
+        L.orc_acgt_pack.restype = C.c_int
+        L.orc_acgt_pack.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.orc_acgt_unpack.restype = None
+        L.orc_acgt_unpack.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        L.orc_domq_prepare.restype = None
+        L.orc_domq_prepare.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_domq_split.restype = None
+        L.orc_domq_split.argtypes = [C.c_void_p] * 3 + [C.c_uint32] + [C.c_void_p] * 3 + [C.c_void_p, u32p] * 4
+        L.orc_domq_reconstruct.restype = C.c_int
+        L.orc_domq_reconstruct.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
+                                           C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint8, C.c_void_p, C.c_uint32, C.c_void_p]
+        L.orc_pbwt_encode.restype = C.c_int
+        L.orc_pbwt_encode.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, u32p, C.c_void_p, u32p]
+        L.orc_pbwt_decode.restype = C.c_int
+        L.orc_pbwt_decode.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, u64p]
+        L.orc_longr_calc_bins.restype = None
+        L.orc_longr_calc_bins.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+        L.orc_longr_encode.restype = C.c_int
+        L.orc_longr_encode.argtypes = [C.c_void_p] * 5 + [C.c_uint32] + [C.c_void_p] * 3
+        L.orc_longr_decode.restype = C.c_int
+        L.orc_longr_decode.argtypes = [C.c_void_p] * 4 + [C.c_uint32] + [C.c_void_p] * 4
         _port = L
     return _port
 
@@ -111,3 +134,106 @@ def uncompress(impl, kind, comp, n):
         assert r, "ref uncompress failed"
     assert ol.value == n
     return out[:n].copy()
+
+
+# ------------------------------------------------------------------ genozip-specific codecs (oracle/gz_port.c)
+class DomqTables(C.Structure):
+    _fields_ = [("n_lines", C.c_uint32), ("num_norm_qs", C.c_uint8), ("num_doms", C.c_uint8), ("has_diverse", C.c_uint8),
+                ("denorm", C.c_uint8 * (95 * 95)), ("normalize", C.c_uint8 * (95 * 95))]
+
+
+def acgt_pack(seq):
+    seq = np.ascontiguousarray(seq, np.uint8)
+    L = port()
+    packed = np.zeros(L.orc_acgt_packed_len(seq.size), np.uint8)
+    x = np.zeros(max(seq.size, 1), np.uint8)
+    allz = L.orc_acgt_pack(_ptr(seq if seq.size else x), seq.size, _ptr(packed if packed.size else x), _ptr(x))
+    return packed, x[:seq.size], bool(allz)
+
+
+def acgt_unpack(packed, x, n):
+    out = np.zeros(max(n, 1), np.uint8)
+    port().orc_acgt_unpack(_ptr(packed if packed.size else out), None if x is None else _ptr(x), n, _ptr(out))
+    return out[:n]
+
+
+def domq_encode(txt, off, lens):
+    """-> dict(tables, line_dom, line_diverse, qual, runs, mplx, divr)"""
+    L = port()
+    txt = np.ascontiguousarray(txt, np.uint8); off = np.ascontiguousarray(off, np.uint64); lens = np.ascontiguousarray(lens, np.uint32)
+    n = lens.size
+    t = DomqTables()
+    dom = np.zeros(max(n, 1), np.uint8); div = np.zeros(max(n, 1), np.uint8)
+    tx = txt if txt.size else np.zeros(1, np.uint8)
+    L.orc_domq_prepare(_ptr(tx), _ptr(off), _ptr(lens), n, _ptr(dom), _ptr(div), C.byref(t))
+    tot = int(lens.sum())
+    qual = np.zeros(2 * tot + 2, np.uint8); runs = np.zeros(tot + 2, np.uint8)
+    mplx = np.zeros(n + 1, np.uint8); divr = np.zeros(tot + 1, np.uint8)
+    ql, rl, ml, dl = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+    L.orc_domq_split(_ptr(tx), _ptr(off), _ptr(lens), n, _ptr(dom), _ptr(div), C.byref(t),
+                     _ptr(qual), C.byref(ql), _ptr(runs), C.byref(rl), _ptr(mplx), C.byref(ml), _ptr(divr), C.byref(dl))
+    nn, nd = t.num_norm_qs, t.num_doms
+    return dict(num_norm_qs=nn, num_doms=nd, has_diverse=t.has_diverse,
+                denorm=np.frombuffer(bytes(t.denorm), np.uint8)[:nd * nn].copy(),
+                normalize=np.frombuffer(bytes(t.normalize), np.uint8).copy(),
+                line_dom=dom[:n].copy(), line_diverse=div[:n].copy(),
+                qual=qual[:ql.value].copy(), runs=runs[:rl.value].copy(), mplx=mplx[:ml.value].copy(), divr=divr[:dl.value].copy())
+
+
+def domq_decode(enc, lens):
+    L = port()
+    lens = np.ascontiguousarray(lens, np.uint32)
+    out = np.zeros(int(lens.sum()) + 1, np.uint8)
+    runs = enc["runs"].copy() if enc["runs"].size else np.zeros(1, np.uint8)
+    z = np.zeros(1, np.uint8)
+    g = lambda a: _ptr(a if a.size else z)
+    rc = L.orc_domq_reconstruct(g(enc["qual"]), enc["qual"].size, _ptr(runs), enc["runs"].size, g(enc["mplx"]), enc["mplx"].size,
+                                g(enc["divr"]), enc["divr"].size, g(enc["denorm"]), enc["num_norm_qs"], _ptr(lens), lens.size, _ptr(out))
+    assert rc == 0, f"orc_domq_reconstruct rc={rc}"
+    return out[:-1]
+
+
+def pbwt_encode(ht):
+    ht = np.ascontiguousarray(ht, np.uint8)
+    n_lines, w = ht.shape
+    runs = np.zeros(2 * ht.size + 4, np.uint32); fgrc = np.zeros(ht.size + 4, np.uint32)
+    nr, nf = C.c_uint32(), C.c_uint32()
+    rc = port().orc_pbwt_encode(_ptr(ht), n_lines, w, _ptr(runs), C.byref(nr), _ptr(fgrc), C.byref(nf))
+    assert rc == 0
+    return runs[:nr.value].copy(), fgrc[:nf.value].copy()
+
+
+def pbwt_decode(runs, fgrc, n_lines, size):
+    ht = np.zeros(size, np.uint8)
+    hl = C.c_uint64()
+    r2, f2 = runs.copy(), fgrc.copy()
+    rc = port().orc_pbwt_decode(_ptr(r2), r2.size, _ptr(f2), f2.size, n_lines, _ptr(ht), C.byref(hl))
+    assert rc == 0 and hl.value == size
+    return ht
+
+
+def longr_bins(qual):
+    hist = np.bincount(np.asarray(qual, np.uint8) - 33, minlength=256).astype(np.uint32)
+    v2b = np.zeros(256, np.uint8)
+    port().orc_longr_calc_bins(_ptr(hist), int(hist.sum()), _ptr(v2b))
+    return v2b
+
+
+def longr_encode(txt, seq_off, qual_off, lens, is_rev, v2b):
+    n = lens.size
+    tot = int(lens.sum())
+    values = np.zeros(tot + 1, np.uint8); lens_be = np.zeros(65536, np.uint32)
+    rc = port().orc_longr_encode(_ptr(txt), _ptr(seq_off), _ptr(qual_off), _ptr(lens), None if is_rev is None else _ptr(is_rev), n,
+                                 _ptr(v2b), _ptr(values), _ptr(lens_be))
+    assert rc == 0
+    return values[:tot].copy(), lens_be
+
+
+def longr_decode(txt, seq_off, lens, is_rev, v2b, values, lens_be):
+    tot = int(lens.sum())
+    out = np.zeros(tot + 1, np.uint8)
+    v = values if values.size else np.zeros(1, np.uint8)
+    rc = port().orc_longr_decode(_ptr(txt), _ptr(seq_off), _ptr(lens), None if is_rev is None else _ptr(is_rev), lens.size,
+                                 _ptr(v2b), _ptr(v), _ptr(lens_be), _ptr(out))
+    assert rc == 0
+    return out[:tot]
