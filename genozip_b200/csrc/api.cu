@@ -106,6 +106,8 @@ extern "C" void gzb_engine_destroy (gzb_engine *e)
     cudaSetDevice (e->device);
     cudaStreamSynchronize (e->stream);
     if (e->ws) cudaFree (e->ws);
+    if (e->dq_buf) cudaFree (e->dq_buf);
+    if (e->dq_session && e->dq_free) e->dq_free (e->dq_session);
     if (e->pin) cudaFreeHost (e->pin);
     cudaEventDestroy (e->ev0); cudaEventDestroy (e->ev1);
     cudaStreamDestroy (e->stream);

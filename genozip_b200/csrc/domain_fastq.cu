@@ -1,0 +1,781 @@
+// domain_fastq.cu — ACGT/XCGT 2-bit sequence packing and DOMQ dominant-quality modelling on sm_100a.
+//
+// Reference functions replaced (all relative to /root/reference/src):
+//   ACGT: codec_acgt_compress up to its sub-codec call (codec_acgt.c:45-55, 64-163), codec_acgt_uncompress /
+//         codec_xcgt_uncompress after theirs (:185-248).
+//   DOMQ: codec_domq_prepare_normalize (codec_domq.c:252-293: per-line histogram + dom :139-178, compaction
+//         :180-197, per-dom rank tables :199-247 — the qsort stays on the host),
+//         codec_domq_compress up to its sub-codec call (:379-500), codec_domq_reconstruct (:774-809) for
+//         all lines of a VBlock at once.
+//
+// These are the bandwidth-shaped kernels of the FASTQ path: bytes in, bytes out, one or two passes.
+#include <cstring>
+#include <cstdlib>
+#include <vector>
+#include <string>
+#include <algorithm>
+#include "../../include/gzb200.h"
+#include "gzb_internal.cuh"
+#include "engine.h"
+
+using namespace gzb;
+
+#define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { e->err = std::string (#call) + ": " + cudaGetErrorString (_e); return GZB_E_CUDA; } } while (0)
+
+namespace {
+
+struct Carver {
+    uint8_t *base; size_t off;
+    template <typename T> T *take (size_t count) {
+        size_t bytes = (count * sizeof (T) + 255) & ~(size_t)255;
+        T *p = base ? reinterpret_cast<T *>(base + off) : nullptr;
+        off += bytes;
+        return p;
+    }
+};
+
+// ================================================================================================ ACGT
+// _acgt_encode (reference.c:45-58): ACGT either case -> 0..3, IUPAC -> lowest participating base, everything else 0
+__device__ __forceinline__ uint32_t acgt_code (uint32_t c)
+{
+    switch (c) {
+        case 'C': case 'c': case 'Y': case 'y': case 'S': case 's': case 'B': case 'b': return 1;
+        case 'G': case 'g': case 'K': case 'k': return 2;
+        case 'T': case 't': case 'U': case 'u': return 3;
+        default: return 0;
+    }
+}
+
+// one thread = 32 bases = one little-endian 64-bit word (codec_acgt.c:45-55) + 32 exception bytes (:67-70,104-107)
+__global__ void k_acgt_pack (const uint8_t *seq, uint64_t n, uint64_t *packed, uint8_t *x, int *x_nonzero)
+{
+    __shared__ uint8_t lut[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = (uint8_t)acgt_code (i);
+    __syncthreads ();
+    const uint64_t nwords = (2 * n + 63) / 64;
+    uint32_t any = 0;
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t base = w * 32;
+        uint64_t word = 0;
+        const bool full = base + 32 <= n;
+        if (full && ((reinterpret_cast<uintptr_t>(seq) + base) & 15) == 0) {
+            const uint4 *p = reinterpret_cast<const uint4 *>(seq + base);
+            uint4 v[2] = { p[0], p[1] };
+            const uint32_t *u = reinterpret_cast<const uint32_t *>(v);
+            uint32_t xe[8];
+            #pragma unroll
+            for (int k = 0; k < 8; k++) {
+                uint32_t cc = u[k], xo = 0;
+                #pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    uint32_t c = (cc >> (8 * b)) & 0xff;
+                    word |= (uint64_t)lut[c] << (2 * (4 * k + b));
+                    uint32_t up = c & 0xdf;
+                    uint32_t e = (up == 'A' || up == 'C' || up == 'G' || up == 'T') ? (c >> 5) & 1 : c;   // upper -> 0, lower -> 1, else verbatim
+                    xo |= e << (8 * b);
+                }
+                xe[k] = xo; any |= xo;
+            }
+            if (x) {
+                if (((reinterpret_cast<uintptr_t>(x) + base) & 15) == 0) {
+                    uint4 *q = reinterpret_cast<uint4 *>(x + base);
+                    q[0] = make_uint4 (xe[0], xe[1], xe[2], xe[3]); q[1] = make_uint4 (xe[4], xe[5], xe[6], xe[7]);
+                }
+                else for (int k = 0; k < 32; k++) x[base + k] = (uint8_t)(xe[k >> 2] >> (8 * (k & 3)));
+            }
+        }
+        else {
+            for (int k = 0; k < 32 && base + k < n; k++) {
+                uint32_t c = seq[base + k];
+                word |= (uint64_t)lut[c] << (2 * k);
+                uint32_t up = c & 0xdf;
+                uint32_t e = (up == 'A' || up == 'C' || up == 'G' || up == 'T') ? (c >> 5) & 1 : c;
+                if (x) x[base + k] = (uint8_t)e;
+                any |= e;
+            }
+        }
+        packed[w] = word;
+    }
+    any = __reduce_or_sync (0xffffffffu, any);
+    if (any && (threadIdx.x & 31) == 0) atomicOr (x_nonzero, 1);
+}
+
+// codec_acgt_uncompress / codec_xcgt_uncompress (:185-248): one thread = 32 bases
+__global__ void k_acgt_unpack (const uint64_t *packed, const uint8_t *x, uint64_t n, uint8_t *seq)
+{
+    const uint64_t nwords = (2 * n + 63) / 64;
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t base = w * 32, word = packed[w];
+        const bool fast = base + 32 <= n && ((reinterpret_cast<uintptr_t>(seq) + base) & 15) == 0 &&
+                          (!x || ((reinterpret_cast<uintptr_t>(x) + base) & 15) == 0);
+        if (fast) {
+            uint32_t xe[8] = {0,0,0,0,0,0,0,0};
+            if (x) { const uint4 *p = reinterpret_cast<const uint4 *>(x + base); uint4 a = p[0], b = p[1];
+                     xe[0]=a.x; xe[1]=a.y; xe[2]=a.z; xe[3]=a.w; xe[4]=b.x; xe[5]=b.y; xe[6]=b.z; xe[7]=b.w; }
+            uint32_t o[8];
+            #pragma unroll
+            for (int k = 0; k < 8; k++) {
+                uint32_t ow = 0;
+                #pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    uint32_t code = (uint32_t)(word >> (2 * (4 * k + b))) & 3;
+                    uint32_t base_c = (0x54474341u >> (8 * code)) & 0xff;         // "ACGT"
+                    uint32_t e = (xe[k] >> (8 * b)) & 0xff;
+                    uint32_t c = e == 0 ? base_c : e == 1 ? base_c + 32 : e;
+                    ow |= c << (8 * b);
+                }
+                o[k] = ow;
+            }
+            uint4 *q = reinterpret_cast<uint4 *>(seq + base);
+            q[0] = make_uint4 (o[0], o[1], o[2], o[3]); q[1] = make_uint4 (o[4], o[5], o[6], o[7]);
+        }
+        else for (int k = 0; k < 32 && base + k < n; k++) {
+            uint32_t code = (uint32_t)(word >> (2 * k)) & 3;
+            uint32_t base_c = (0x54474341u >> (8 * code)) & 0xff;
+            uint32_t e = x ? x[base + k] : 0;
+            seq[base + k] = (uint8_t)(e == 0 ? base_c : e == 1 ? base_c + 32 : e);
+        }
+    }
+}
+
+// ================================================================================================ DOMQ
+constexpr int NQ = 95, FIRST_Q = 32;              // printable qualities ' '..'~' (codec_domq.c:31-33)
+
+struct DqVb {                                      // device view of one VBlock's quality lines
+    const uint8_t  *txt;
+    const uint64_t *line_off;
+    const uint32_t *line_len;
+    uint8_t  *line_dom;        // raw dom (q-32) after the histogram pass, compacted dom after prepare
+    uint8_t  *line_diverse;
+    uint32_t *hist;            // [95][95] per-dom histograms, then [95] lines_with_dom
+    uint32_t *nd_off;          // per line: offset in the concatenation of non-diverse lines
+    uint32_t *dv_off;          // per line: offset in DIVRQUAL
+    uint32_t *mx_idx;          // per line: index in QUALMPLX
+    uint8_t  *E;               // normalised non-diverse concatenation
+    uint8_t  *qual, *runs, *mplx, *divr;
+    uint32_t *lens;            // [8]: qual_len, runs_len, mplx_len, divr_len, M (non-diverse total), last_line_len
+    uint32_t  n_lines;
+    uint8_t   no_doms;
+    uint8_t   pad[3];
+    uint8_t   normalize[NQ * NQ];   // [cdom*95 + q-32] -> rank
+    uint8_t   dom_to_cdom[NQ];
+};
+
+// ---- pass 1: per-line histogram, dom, diversity; per-dom histograms (codec_domq_calc_histogram :139-178)
+constexpr int LINES_PER_BLOCK = 512;
+__global__ void __launch_bounds__(256) k_domq_linehist (const DqVb *vbs, const uint32_t *blk_vb, const uint32_t *blk_first)
+{
+    const DqVb &V = vbs[blk_vb[blockIdx.x]];
+    const uint32_t first = blk_first[blockIdx.x], last = min (first + LINES_PER_BLOCK, V.n_lines);
+    __shared__ uint32_t h2[NQ * NQ];
+    __shared__ uint32_t lwd[NQ];
+    __shared__ uint32_t lh[8][96];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < NQ * NQ; i += 256) h2[i] = 0;
+    if (tid < NQ) lwd[tid] = 0;
+    __syncthreads ();
+    for (uint32_t li = first + warp; li < last; li += 8) {
+        const uint32_t len = V.line_len[li];
+        if (!len) { if (lane == 0) { V.line_dom[li] = 0; V.line_diverse[li] = 0; } continue; }
+        for (int i = lane; i < 96; i += 32) lh[warp][i] = 0;
+        __syncwarp ();
+        const uint8_t *q = V.txt + V.line_off[li];
+        for (uint32_t i = lane; i < len; i += 32) atomicAdd (&lh[warp][q[i] - FIRST_Q], 1u);
+        __syncwarp ();
+        // dom = arg-max, ties -> the higher quality (:153-158)
+        uint32_t bc = 0, bq = 0;
+        for (int k = lane; k < NQ; k += 32) { uint32_t c = lh[warp][k]; if (c >= bc) { bc = c; bq = k; } }
+        for (int o = 16; o; o >>= 1) {
+            uint32_t oc = __shfl_xor_sync (0xffffffffu, bc, o), oq = __shfl_xor_sync (0xffffffffu, bq, o);
+            if (oc > bc || (oc == bc && oq > bq)) { bc = oc; bq = oq; }
+        }
+        if (lane == 0) {
+            V.line_dom[li] = (uint8_t)bq;
+            V.line_diverse[li] = (100u * bc / len < 85u) ? 1 : 0;                 // DOMQ_THRESHOLD (:141,160)
+            atomicAdd (&lwd[bq], 1u);
+        }
+        for (int k = lane; k < NQ; k += 32) { uint32_t c = lh[warp][k]; if (c) atomicAdd (&h2[bq * NQ + k], c); }
+        __syncwarp ();
+    }
+    __syncthreads ();
+    for (int i = tid; i < NQ * NQ; i += 256) if (h2[i]) atomicAdd (&V.hist[i], h2[i]);
+    if (tid < NQ && lwd[tid]) atomicAdd (&V.hist[NQ * NQ + tid], lwd[tid]);
+}
+
+// ---- block scan helpers (512 threads)
+__device__ __forceinline__ uint32_t warp_incl_sum (uint32_t v, int lane)
+{
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync (0xffffffffu, v, o); if (lane >= o) v += t; }
+    return v;
+}
+__device__ __forceinline__ uint32_t warp_incl_max (uint32_t v, int lane)
+{
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync (0xffffffffu, v, o); if (lane >= o) v = max (v, t); }
+    return v;
+}
+// exclusive block sum; *total = block total.  sm needs 17 words.  All threads call.
+__device__ uint32_t block_excl_sum (uint32_t v, uint32_t *sm, uint32_t *total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    uint32_t inc = warp_incl_sum (v, lane);
+    if (lane == 31) sm[warp] = inc;
+    __syncthreads ();
+    if (warp == 0) { uint32_t w = lane < nw ? sm[lane] : 0; uint32_t wi = warp_incl_sum (w, lane); if (lane < nw) sm[lane] = wi - w; if (lane == nw - 1) sm[16] = wi; }
+    __syncthreads ();
+    uint32_t r = sm[warp] + inc - v;
+    *total = sm[16];
+    __syncthreads ();
+    return r;
+}
+__device__ uint32_t block_excl_max (uint32_t v, uint32_t *sm, uint32_t *total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    uint32_t inc = warp_incl_max (v, lane);
+    uint32_t excl_in_warp = __shfl_up_sync (0xffffffffu, inc, 1); if (lane == 0) excl_in_warp = 0;
+    if (lane == 31) sm[warp] = inc;
+    __syncthreads ();
+    if (warp == 0) { uint32_t w = lane < nw ? sm[lane] : 0; uint32_t wi = warp_incl_max (w, lane); uint32_t we = __shfl_up_sync (0xffffffffu, wi, 1); if (lane == 0) we = 0;
+                     if (lane < nw) sm[lane] = we; if (lane == nw - 1) sm[16] = wi; }
+    __syncthreads ();
+    uint32_t r = max (sm[warp], excl_in_warp);
+    *total = sm[16];
+    __syncthreads ();
+    return r;
+}
+
+// ---- pass 2a: per-line output offsets (one CTA per VB)
+__global__ void __launch_bounds__(512) k_domq_lineoffsets (const DqVb *vbs)
+{
+    const DqVb &V = vbs[blockIdx.x];
+    __shared__ uint32_t sm[17];
+    uint32_t nd = 0, dv = 0, mx = 0, t;
+    for (uint32_t base = 0; base < V.n_lines; base += 512) {
+        uint32_t li = base + threadIdx.x;
+        uint32_t len = li < V.n_lines ? V.line_len[li] : 0;
+        bool div = len && V.line_diverse[li];
+        uint32_t a = block_excl_sum (div ? 0 : len, sm, &t); uint32_t ta = t;
+        uint32_t b = block_excl_sum (div ? len : 0, sm, &t); uint32_t tb = t;
+        uint32_t c = block_excl_sum (len ? 1 : 0, sm, &t);   uint32_t tc = t;
+        if (li < V.n_lines) { V.nd_off[li] = nd + a; V.dv_off[li] = dv + b; V.mx_idx[li] = mx + c; }
+        nd += ta; dv += tb; mx += tc;
+    }
+    if (threadIdx.x == 0) { V.lens[4] = nd; V.lens[3] = dv; V.lens[2] = mx; V.lens[5] = V.n_lines ? V.line_len[V.n_lines - 1] : 0; }
+}
+
+// ---- pass 2b: normalise every line with its dom's rank table (:347-366) into E / DIVRQUAL, write QUALMPLX
+__global__ void __launch_bounds__(256) k_domq_normalize (const DqVb *vbs, const uint32_t *blk_vb, const uint32_t *blk_first)
+{
+    const DqVb &V = vbs[blk_vb[blockIdx.x]];
+    const uint32_t first = blk_first[blockIdx.x], last = min (first + LINES_PER_BLOCK, V.n_lines);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t li = first + warp; li < last; li += 8) {
+        const uint32_t len = V.line_len[li];
+        if (!len) continue;
+        const uint32_t cdom = V.dom_to_cdom[V.line_dom[li]];
+        const bool div = V.line_diverse[li];
+        const uint8_t *norm = V.normalize + cdom * NQ;
+        const uint8_t *q = V.txt + V.line_off[li];
+        uint8_t *dst = div ? V.divr + V.dv_off[li] : V.E + V.nd_off[li];
+        for (uint32_t i = lane; i < len; i += 32) dst[i] = norm[q[i] - FIRST_Q];
+        if (lane == 0) { V.mplx[V.mx_idx[li]] = (uint8_t)(cdom | (div ? 0x80 : 0)); V.line_dom[li] = (uint8_t)cdom; }   // :436,446; ql->dom becomes cdom (:283-285)
+    }
+}
+
+// ---- pass 3: stream split over the non-diverse concatenation (:421-500).  One CTA per VB walks E in tiles of
+// 512 threads x 8 elements, carrying (QUAL position, DOMQRUNS position, index of the last non-dom).
+__device__ __forceinline__ uint32_t put_run_bytes (uint8_t *runs, uint32_t pos, uint32_t r)      // codec_domq_add_runs :368-377
+{
+    while (r) { uint32_t sub = r < 254 ? r : 254; runs[pos++] = (uint8_t)(r <= 254 ? sub : 255); r -= sub; }
+    return pos;
+}
+
+__global__ void __launch_bounds__(512) k_domq_split (const DqVb *vbs)
+{
+    const DqVb &V = vbs[blockIdx.x];
+    __shared__ uint32_t sm[17];
+    __shared__ uint8_t s_last[512];
+    const uint32_t M = V.lens[4];
+    const uint8_t no_doms = V.no_doms;
+    uint32_t qpos = 0, rpos = 0, last_nd1 = 0;          // last_nd1 = (index of last non-dom so far) + 1, 0 = none
+    uint32_t carry_prev_dom = 0;                        // was the element before this tile a dom?
+    for (uint32_t base = 0; base < M; base += 4096) {
+        const uint32_t i0 = base + threadIdx.x * 8;
+        uint8_t e[8];
+        #pragma unroll
+        for (int j = 0; j < 8; j++) e[j] = (i0 + j < M) ? V.E[i0 + j] : 0xff;     // 0xff = past the end (treated as non-dom, never written)
+        s_last[threadIdx.x] = e[7];
+        __syncthreads ();
+        uint32_t prev_dom = threadIdx.x ? (s_last[threadIdx.x - 1] == 0) : carry_prev_dom;
+        // local: last non-dom index (+1) within my 8
+        uint32_t my_last = 0;
+        #pragma unroll
+        for (int j = 0; j < 8; j++) if (e[j] != 0 && i0 + j < M) my_last = i0 + j + 1;
+        uint32_t tot_last;
+        uint32_t start_last = max (block_excl_max (my_last, sm, &tot_last), last_nd1);
+        // count bytes
+        uint32_t cq = 0, cr = 0, ln = start_last, pd = prev_dom;
+        #pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (i0 + j >= M) break;
+            if (e[j] == 0) { pd = 1; continue; }
+            if (pd) { uint32_t r = i0 + j - ln; cr += (r + 253) / 254; cq += 1; }
+            else cq += 2;
+            ln = i0 + j + 1; pd = 0;
+        }
+        uint32_t tq, tr;
+        uint32_t oq = block_excl_sum (cq, sm, &tq) + qpos;
+        uint32_t orr = block_excl_sum (cr, sm, &tr) + rpos;
+        // write
+        ln = start_last; pd = prev_dom;
+        #pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (i0 + j >= M) break;
+            if (e[j] == 0) { pd = 1; continue; }
+            if (pd) orr = put_run_bytes (V.runs, orr, i0 + j - ln);
+            else V.qual[oq++] = no_doms;
+            V.qual[oq++] = e[j];
+            ln = i0 + j + 1; pd = 0;
+        }
+        qpos += tq; rpos += tr; last_nd1 = max (last_nd1, tot_last);
+        carry_prev_dom = (s_last[511] == 0);
+        __syncthreads ();
+    }
+    if (threadIdx.x == 0) {
+        uint32_t runlen = M - last_nd1;                                            // trailing dom run (:473-482)
+        if (runlen && (rpos || runlen < V.lens[5])) { rpos = put_run_bytes (V.runs, rpos, runlen); V.qual[qpos++] = no_doms; }
+        if (!qpos) V.qual[qpos++] = 'X';                                           // :497-500
+        V.lens[0] = qpos; V.lens[1] = rpos;
+    }
+}
+
+// ================================================================================================ DOMQ PIZ
+struct DqPiz {
+    const uint8_t *qual, *runs, *mplx, *divr;
+    const uint32_t *line_len;
+    uint8_t  *out;
+    uint8_t  *E;               // M bytes, zero-filled (= dom rank) before literals are scattered
+    uint32_t *cum;             // inclusive prefix of decoded run lengths, one per run
+    uint32_t *nd_off, *dv_off, *out_off;
+    uint8_t  *dom_i;
+    uint32_t *info;            // [0] M, [1] D, [2] err, [3] n_runs
+    uint32_t  qual_len, runs_len, mplx_len, divr_len, n_lines;
+    uint8_t   no_dom;
+    uint8_t   pad[3];
+    uint8_t   denorm[NQ * NQ];
+    uint32_t  denorm_len;
+};
+
+// per-line: mux byte (:790-791), diverse flag (:795-796), offsets.  One CTA per VB.
+__global__ void __launch_bounds__(512) k_dqp_lines (const DqPiz *vbs)
+{
+    const DqPiz &V = vbs[blockIdx.x];
+    __shared__ uint32_t sm[17];
+    uint32_t nd = 0, dv = 0, mx = 0, oo = 0, t;
+    for (uint32_t base = 0; base < V.n_lines; base += 512) {
+        uint32_t li = base + threadIdx.x;
+        uint32_t len = li < V.n_lines ? V.line_len[li] : 0;
+        uint32_t c = block_excl_sum (len ? 1 : 0, sm, &t); uint32_t tc = t;
+        uint8_t d = 0;
+        if (len) { uint32_t k = (V.mplx_len == 1) ? 0 : mx + c; d = k < V.mplx_len ? V.mplx[k] : 0; if (k >= V.mplx_len) V.info[2] = 1; }
+        bool div = len && (d >> 7);
+        uint32_t a = block_excl_sum (div ? 0 : len, sm, &t); uint32_t ta = t;
+        uint32_t b = block_excl_sum (div ? len : 0, sm, &t); uint32_t tb = t;
+        uint32_t o = block_excl_sum (len, sm, &t);           uint32_t to = t;
+        if (li < V.n_lines) { V.nd_off[li] = nd + a; V.dv_off[li] = dv + b; V.out_off[li] = oo + o; V.dom_i[li] = d; }
+        nd += ta; dv += tb; mx += tc; oo += to;
+    }
+    if (threadIdx.x == 0) { V.info[0] = nd; V.info[1] = dv; if (dv > V.divr_len) V.info[2] = 1; }
+}
+
+// DOMQRUNS bytes -> inclusive prefix of run lengths (a run = 255* then one byte != 255; value 254*(n-1)+last, :560-565)
+__global__ void __launch_bounds__(512) k_dqp_runs (const DqPiz *vbs)
+{
+    const DqPiz &V = vbs[blockIdx.x];
+    __shared__ uint32_t sm[17];
+    uint32_t nruns = 0, start1 = 0, cum = 0, t;          // start1 = (index after the previous run end)
+    for (uint32_t base = 0; base < V.runs_len; base += 512) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t b = i < V.runs_len ? V.runs[i] : 255;
+        bool end = i < V.runs_len && b != 255;
+        uint32_t k = block_excl_sum (end ? 1 : 0, sm, &t); uint32_t tk = t;
+        uint32_t tm;
+        uint32_t st = max (block_excl_max (end ? i + 1 : 0, sm, &tm), start1);
+        uint32_t val = end ? 254 * (i - st) + b : 0;
+        uint32_t tv;
+        uint32_t cv = block_excl_sum (val, sm, &tv);
+        if (end) V.cum[nruns + k] = cum + cv + val;
+        nruns += tk; cum += tv; start1 = max (start1, tm);
+    }
+    if (threadIdx.x == 0) V.info[3] = nruns;
+}
+
+// QUAL bytes -> scatter literals into E (:693-735).  A byte equal to no_dom is a marker; a literal not preceded by a
+// marker consumes the next run; a marker in the very last position is the final-run indicator.
+__global__ void __launch_bounds__(512) k_dqp_literals (const DqPiz *vbs)
+{
+    const DqPiz &V = vbs[blockIdx.x];
+    __shared__ uint32_t sm[17];
+    const uint32_t M = V.info[0], nruns = V.info[3], no_dom = V.no_dom;
+    // no DOMQRUNS at all: only (marker, literal) pairs are consumed (:676-690) — a lone 'X' is not a literal
+    const uint32_t qn = V.qual_len;
+    uint32_t lits = 0, cons = 0, t;
+    for (uint32_t base = 0; base < qn; base += 512) {
+        uint32_t j = base + threadIdx.x;
+        uint32_t b = j < qn ? V.qual[j] : no_dom;
+        bool prev_marker = j > 0 && j < qn && V.qual[j - 1] == no_dom;
+        bool is_lit = j < qn && b != no_dom && (V.runs_len || prev_marker);
+        bool consumes = V.runs_len && is_lit && !prev_marker;
+        uint32_t li = block_excl_sum (is_lit ? 1 : 0, sm, &t); uint32_t tl = t;
+        uint32_t ci = block_excl_sum (consumes ? 1 : 0, sm, &t); uint32_t tc = t;
+        if (is_lit) {
+            uint32_t k = cons + ci;                                               // runs consumed before this literal
+            uint32_t before = consumes ? (k < nruns ? V.cum[k] : 0xffffffffu) : (k ? (k - 1 < nruns ? V.cum[k - 1] : 0xffffffffu) : 0);
+            uint64_t pos = (uint64_t)lits + li + before;
+            if (before == 0xffffffffu || pos >= M) V.info[2] = 1;
+            else V.E[pos] = (uint8_t)b;
+        }
+        lits += tl; cons += tc;
+    }
+}
+
+// de-normalise every line (:698,731 and reconstruct_divr :752-766): one warp per line
+__global__ void __launch_bounds__(256) k_dqp_denorm (const DqPiz *vbs, const uint32_t *blk_vb, const uint32_t *blk_first)
+{
+    const DqPiz &V = vbs[blk_vb[blockIdx.x]];
+    const uint32_t first = blk_first[blockIdx.x], last = min (first + LINES_PER_BLOCK, V.n_lines);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (V.info[2]) return;
+    for (uint32_t li = first + warp; li < last; li += 8) {
+        const uint32_t len = V.line_len[li];
+        if (!len) continue;
+        const uint32_t d = V.dom_i[li];
+        const uint32_t row = (d & 0x7f) * V.no_dom;
+        if (row + V.no_dom > V.denorm_len) { V.info[2] = 1; continue; }
+        const uint8_t *dn = V.denorm + row;
+        const uint8_t *src = (d >> 7) ? V.divr + V.dv_off[li] : V.E + V.nd_off[li];
+        uint8_t *dst = V.out + V.out_off[li];
+        for (uint32_t i = lane; i < len; i += 32) { uint32_t r = src[i]; dst[i] = r < V.no_dom ? dn[r] : 0; }
+    }
+}
+
+void line_blocks (const std::vector<uint32_t> &n_lines, std::vector<uint32_t> &bvb, std::vector<uint32_t> &bfirst)
+{
+    for (uint32_t v = 0; v < n_lines.size (); v++)
+        for (uint32_t f = 0; f < n_lines[v]; f += LINES_PER_BLOCK) { bvb.push_back (v); bfirst.push_back (f); }
+}
+
+typedef struct { uint8_t q; uint32_t count; } QMap;
+int qmap_desc (const void *a, const void *b)                                       // DESCENDING_SORTER (sorter.h:16-33)
+{
+    uint32_t ca = ((const QMap *)a)->count, cb = ((const QMap *)b)->count;
+    return -((ca > cb) ? 1 : (ca < cb) ? -1 : 0);
+}
+
+} // namespace
+
+// ================================================================================================ C-ABI: ACGT
+extern "C" uint64_t gzb_acgt_packed_len (uint64_t n) { return ((2 * n + 63) / 64) * 8; }
+
+extern "C" int gzb_acgt_pack (gzb_engine *e, const void *seq, uint64_t n, void *packed, void *x, int *x_all_zero, uint32_t flags)
+{
+    if (!e || (!seq && n) || !packed) return GZB_E_BADARG;
+    cudaSetDevice (e->device);
+    const bool devptr = flags & GZB_DEVICE_PTRS;
+    const uint64_t plen = gzb_acgt_packed_len (n);
+    cudaStream_t st = e->stream;
+    Carver c { nullptr, 0 };
+    uint8_t *d_seq = nullptr, *d_packed = nullptr, *d_x = nullptr; int *d_flag = nullptr;
+    for (int pass = 0; pass < 2; pass++) {
+        c.off = 0;
+        d_flag = c.take<int> (1);
+        if (!devptr) { d_seq = c.take<uint8_t> (n + 32); d_packed = c.take<uint8_t> (plen + 32); d_x = c.take<uint8_t> (n + 32); }
+        if (pass == 0) { int rc = engine_reserve (e, c.off, 4096); if (rc) return rc; c.base = e->ws; }
+    }
+    if (devptr) { d_seq = (uint8_t *)seq; d_packed = (uint8_t *)packed; d_x = (uint8_t *)x; }
+    else if (n) CK (cudaMemcpyAsync (d_seq, seq, n, cudaMemcpyHostToDevice, st));
+    CK (cudaMemsetAsync (d_flag, 0, sizeof (int), st));
+    if (n) {
+        uint64_t nwords = plen / 8;
+        uint32_t grid = (uint32_t)std::min<uint64_t> ((nwords + 255) / 256, (uint64_t)e->sm_count * 16);
+        k_acgt_pack<<<grid, 256, 0, st>>>(d_seq, n, reinterpret_cast<uint64_t *>(d_packed), (devptr && !x) ? nullptr : d_x, d_flag);
+        e->launches++;
+    }
+    int h_flag = 0;
+    CK (cudaMemcpyAsync (&h_flag, d_flag, sizeof (int), cudaMemcpyDeviceToHost, st));
+    if (!devptr && plen) CK (cudaMemcpyAsync (packed, d_packed, plen, cudaMemcpyDeviceToHost, st));
+    CK (cudaStreamSynchronize (st));
+    if (x_all_zero) *x_all_zero = !h_flag;
+    if (!devptr && x && n && h_flag) { CK (cudaMemcpyAsync (x, d_x, n, cudaMemcpyDeviceToHost, st)); CK (cudaStreamSynchronize (st)); }
+    else if (!devptr && x && n) memset (x, 0, n);                                   // all-zero exception stream: no transfer needed
+    return GZB_OK;
+}
+
+extern "C" int gzb_acgt_unpack (gzb_engine *e, const void *packed, const void *x, uint64_t n, void *seq, uint32_t flags)
+{
+    if (!e || (!packed && n) || !seq) return GZB_E_BADARG;
+    cudaSetDevice (e->device);
+    const bool devptr = flags & GZB_DEVICE_PTRS;
+    const uint64_t plen = gzb_acgt_packed_len (n);
+    cudaStream_t st = e->stream;
+    Carver c { nullptr, 0 };
+    uint8_t *d_seq = nullptr, *d_packed = nullptr, *d_x = nullptr;
+    if (!devptr) {
+        for (int pass = 0; pass < 2; pass++) {
+            c.off = 0;
+            d_seq = c.take<uint8_t> (n + 32); d_packed = c.take<uint8_t> (plen + 32); d_x = c.take<uint8_t> (n + 32);
+            if (pass == 0) { int rc = engine_reserve (e, c.off, 4096); if (rc) return rc; c.base = e->ws; }
+        }
+        if (plen) CK (cudaMemcpyAsync (d_packed, packed, plen, cudaMemcpyHostToDevice, st));
+        if (x && n) CK (cudaMemcpyAsync (d_x, x, n, cudaMemcpyHostToDevice, st));
+    }
+    else { d_seq = (uint8_t *)seq; d_packed = (uint8_t *)packed; d_x = (uint8_t *)x; }
+    if (n) {
+        uint64_t nwords = plen / 8;
+        uint32_t grid = (uint32_t)std::min<uint64_t> ((nwords + 255) / 256, (uint64_t)e->sm_count * 16);
+        k_acgt_unpack<<<grid, 256, 0, st>>>(reinterpret_cast<const uint64_t *>(d_packed), x ? d_x : nullptr, n, d_seq);
+        e->launches++;
+    }
+    if (!devptr && n) CK (cudaMemcpyAsync (seq, d_seq, n, cudaMemcpyDeviceToHost, st));
+    CK (cudaStreamSynchronize (st));
+    return GZB_OK;
+}
+
+// ================================================================================================ C-ABI: DOMQ (ZIP)
+// The device state of a prepare call (staged text, line tables, per-line dom/diverse) lives in the engine's DOMQ
+// session buffer until the matching split call, so a host-buffer caller uploads its quality text once.
+namespace {
+
+struct DqLayout {
+    std::vector<DqVb> h;           // host copies of the device descriptors
+    DqVb *d_vbs = nullptr;
+    uint32_t *d_bvb = nullptr, *d_bfirst = nullptr; uint32_t n_blocks = 0;
+    std::vector<uint8_t *> d_linedom, d_linediv;
+};
+
+int dq_stage (gzb_engine *e, gzb_domq_vb *vbs, uint32_t n_vbs, bool devptr, DqLayout &L)
+{
+    std::vector<uint32_t> nl (n_vbs), bvb, bfirst;
+    for (uint32_t v = 0; v < n_vbs; v++) nl[v] = vbs[v].n_lines;
+    line_blocks (nl, bvb, bfirst);
+    L.n_blocks = (uint32_t)bvb.size ();
+    Carver c { nullptr, 0 };
+    L.h.assign (n_vbs, DqVb ());
+    for (int pass = 0; pass < 2; pass++) {
+        c.off = 0;
+        L.d_vbs = c.take<DqVb> (n_vbs);
+        L.d_bvb = c.take<uint32_t> (bvb.size () + 1); L.d_bfirst = c.take<uint32_t> (bfirst.size () + 1);
+        for (uint32_t v = 0; v < n_vbs; v++) {
+            DqVb &D = L.h[v]; const gzb_domq_vb &S = vbs[v];
+            uint64_t tot = 0;   // total quality bytes is unknown on the host in device mode: bound by txt_len
+            tot = S.txt_len;
+            D.n_lines = S.n_lines;
+            D.txt      = devptr ? (const uint8_t *)S.txt : c.take<uint8_t> (S.txt_len + 16);
+            D.line_off = devptr ? S.line_off : c.take<uint64_t> (S.n_lines + 1);
+            D.line_len = devptr ? S.line_len : c.take<uint32_t> (S.n_lines + 1);
+            D.line_dom = devptr ? S.line_dom : c.take<uint8_t> (S.n_lines + 1);
+            D.line_diverse = devptr ? S.line_diverse : c.take<uint8_t> (S.n_lines + 1);
+            D.hist   = c.take<uint32_t> (NQ * NQ + NQ);
+            D.nd_off = c.take<uint32_t> (S.n_lines + 1); D.dv_off = c.take<uint32_t> (S.n_lines + 1); D.mx_idx = c.take<uint32_t> (S.n_lines + 1);
+            D.E      = c.take<uint8_t> (tot + 16);
+            D.lens   = c.take<uint32_t> (8);
+            D.qual   = devptr ? (uint8_t *)S.qual : c.take<uint8_t> (2 * tot + 16);
+            D.runs   = devptr ? (uint8_t *)S.runs : c.take<uint8_t> (tot + 16);
+            D.mplx   = devptr ? (uint8_t *)S.mplx : c.take<uint8_t> (S.n_lines + 16);
+            D.divr   = devptr ? (uint8_t *)S.divr : c.take<uint8_t> (tot + 16);
+        }
+        if (pass == 0) {
+            if (c.off > e->dq_cap) {
+                CK (cudaStreamSynchronize (e->stream));
+                if (e->dq_buf) cudaFree (e->dq_buf);
+                e->dq_buf = nullptr; e->dq_cap = 0;
+                CK (cudaMalloc (&e->dq_buf, c.off + (c.off >> 3)));
+                e->dq_cap = c.off + (c.off >> 3);
+            }
+            c.base = e->dq_buf;
+        }
+    }
+    cudaStream_t st = e->stream;
+    CK (cudaMemcpyAsync (L.d_bvb, bvb.data (), bvb.size () * 4, cudaMemcpyHostToDevice, st));
+    CK (cudaMemcpyAsync (L.d_bfirst, bfirst.data (), bfirst.size () * 4, cudaMemcpyHostToDevice, st));
+    CK (cudaStreamSynchronize (st));       // bvb/bfirst are stack-lifetime vectors
+    return GZB_OK;
+}
+
+} // namespace
+
+extern "C" int gzb_domq_prepare (gzb_engine *e, gzb_domq_vb *vbs, uint32_t n_vbs, uint32_t flags)
+{
+    if (!e || !vbs) return GZB_E_BADARG;
+    if (!n_vbs) return GZB_OK;
+    cudaSetDevice (e->device);
+    const bool devptr = flags & GZB_DEVICE_PTRS;
+    cudaStream_t st = e->stream;
+    DqLayout *L = new DqLayout ();
+    delete reinterpret_cast<DqLayout *>(e->dq_session); e->dq_session = L;
+    e->dq_free = [] (void *p) { delete reinterpret_cast<DqLayout *>(p); };
+    int rc = dq_stage (e, vbs, n_vbs, devptr, *L);
+    if (rc) return rc;
+    for (uint32_t v = 0; v < n_vbs; v++) {
+        DqVb &D = L->h[v];
+        if (!devptr) {
+            if (vbs[v].txt_len) CK (cudaMemcpyAsync ((void *)D.txt, vbs[v].txt, vbs[v].txt_len, cudaMemcpyHostToDevice, st));
+            if (D.n_lines) {
+                CK (cudaMemcpyAsync ((void *)D.line_off, vbs[v].line_off, (size_t)D.n_lines * 8, cudaMemcpyHostToDevice, st));
+                CK (cudaMemcpyAsync ((void *)D.line_len, vbs[v].line_len, (size_t)D.n_lines * 4, cudaMemcpyHostToDevice, st));
+            }
+        }
+        CK (cudaMemsetAsync (D.hist, 0, (NQ * NQ + NQ) * 4, st));
+    }
+    CK (cudaMemcpyAsync (L->d_vbs, L->h.data (), n_vbs * sizeof (DqVb), cudaMemcpyHostToDevice, st));
+    if (L->n_blocks) { k_domq_linehist<<<L->n_blocks, 256, 0, st>>>(L->d_vbs, L->d_bvb, L->d_bfirst); e->launches++; }
+    std::vector<uint32_t> hist ((size_t)n_vbs * (NQ * NQ + NQ));
+    for (uint32_t v = 0; v < n_vbs; v++)
+        CK (cudaMemcpyAsync (hist.data () + (size_t)v * (NQ * NQ + NQ), L->h[v].hist, (NQ * NQ + NQ) * 4, cudaMemcpyDeviceToHost, st));
+    CK (cudaStreamSynchronize (st));
+
+    // host: compaction (:180-197) and per-dom rank tables (:199-247).  qsort's order among equal counts is whatever
+    // this libc does — the same call with the same comparator the reference makes.
+    for (uint32_t v = 0; v < n_vbs; v++) {
+        uint32_t (*H)[NQ] = reinterpret_cast<uint32_t (*)[NQ]>(hist.data () + (size_t)v * (NQ * NQ + NQ));
+        const uint32_t *lwd = hist.data () + (size_t)v * (NQ * NQ + NQ) + NQ * NQ;
+        gzb_domq_vb &S = vbs[v]; DqVb &D = L->h[v];
+        memset (S.denorm, 0, sizeof S.denorm); memset (S.normalize, 0, sizeof S.normalize); memset (D.dom_to_cdom, 0, NQ);
+        int num_doms = 0;
+        for (int k = 0; k < NQ; k++) if (lwd[k]) { D.dom_to_cdom[k] = (uint8_t)num_doms; if (num_doms != k) memcpy (H[num_doms], H[k], sizeof H[0]); num_doms++; }
+        uint8_t denormalize[NQ][NQ]; memset (denormalize, 0, sizeof denormalize);
+        int num_norm_qs = 0;
+        for (int cd = 0; cd < num_doms; cd++) {
+            QMap m[NQ];
+            for (int k = 0; k < NQ; k++) { m[k].q = (uint8_t)k; m[k].count = H[cd][k]; }
+            qsort (m, NQ, sizeof (QMap), qmap_desc);
+            int r = 0;
+            for (; r < NQ && m[r].count; r++) { S.normalize[cd * NQ + m[r].q] = (uint8_t)r; denormalize[cd][r] = (uint8_t)(m[r].q + FIRST_Q); }
+            if (r > num_norm_qs) num_norm_qs = r;
+        }
+        for (int cd = 0; cd < num_doms; cd++) for (int r = 0; r < num_norm_qs; r++) S.denorm[cd * num_norm_qs + r] = denormalize[cd][r];
+        S.num_norm_qs = (uint8_t)num_norm_qs; S.num_doms = (uint8_t)num_doms;
+        D.no_doms = (uint8_t)num_norm_qs;
+        memcpy (D.normalize, S.normalize, sizeof D.normalize);
+    }
+    // per-line outputs: compacted dom + diverse flag
+    CK (cudaMemcpyAsync (L->d_vbs, L->h.data (), n_vbs * sizeof (DqVb), cudaMemcpyHostToDevice, st));
+    k_domq_lineoffsets<<<n_vbs, 512, 0, st>>>(L->d_vbs); e->launches++;
+    if (L->n_blocks) { k_domq_normalize<<<L->n_blocks, 256, 0, st>>>(L->d_vbs, L->d_bvb, L->d_bfirst); e->launches++; }
+    std::vector<uint32_t> lens ((size_t)n_vbs * 8);
+    for (uint32_t v = 0; v < n_vbs; v++) {
+        CK (cudaMemcpyAsync (lens.data () + (size_t)v * 8, L->h[v].lens, 32, cudaMemcpyDeviceToHost, st));
+        if (!devptr && vbs[v].n_lines) {
+            if (vbs[v].line_dom) CK (cudaMemcpyAsync (vbs[v].line_dom, L->h[v].line_dom, vbs[v].n_lines, cudaMemcpyDeviceToHost, st));
+            if (vbs[v].line_diverse) CK (cudaMemcpyAsync (vbs[v].line_diverse, L->h[v].line_diverse, vbs[v].n_lines, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    CK (cudaStreamSynchronize (st));
+    for (uint32_t v = 0; v < n_vbs; v++) {
+        vbs[v].has_diverse = lens[(size_t)v * 8 + 3] != 0;
+        vbs[v].mplx_len = lens[(size_t)v * 8 + 2]; vbs[v].divr_len = lens[(size_t)v * 8 + 3];
+    }
+    L->h.shrink_to_fit ();
+    e->dq_n_vbs = n_vbs; e->dq_devptr = devptr;
+    return GZB_OK;
+}
+
+extern "C" int gzb_domq_split (gzb_engine *e, gzb_domq_vb *vbs, uint32_t n_vbs, uint32_t flags)
+{
+    if (!e || !vbs) return GZB_E_BADARG;
+    if (!n_vbs) return GZB_OK;
+    cudaSetDevice (e->device);
+    const bool devptr = flags & GZB_DEVICE_PTRS;
+    DqLayout *L = reinterpret_cast<DqLayout *>(e->dq_session);
+    if (!L || e->dq_n_vbs != n_vbs || e->dq_devptr != devptr) { e->err = "gzb_domq_split must follow gzb_domq_prepare on the same batch"; return GZB_E_BADARG; }
+    cudaStream_t st = e->stream;
+    k_domq_split<<<n_vbs, 512, 0, st>>>(L->d_vbs); e->launches++;
+    std::vector<uint32_t> lens ((size_t)n_vbs * 8);
+    for (uint32_t v = 0; v < n_vbs; v++) CK (cudaMemcpyAsync (lens.data () + (size_t)v * 8, L->h[v].lens, 32, cudaMemcpyDeviceToHost, st));
+    CK (cudaStreamSynchronize (st));
+    for (uint32_t v = 0; v < n_vbs; v++) {
+        gzb_domq_vb &S = vbs[v]; const uint32_t *l = lens.data () + (size_t)v * 8;
+        S.qual_len = l[0]; S.runs_len = l[1]; S.mplx_len = l[2]; S.divr_len = l[3];
+        if (!devptr) {
+            if (S.qual_len > S.qual_cap || S.runs_len > S.runs_cap || S.mplx_len > S.mplx_cap || S.divr_len > S.divr_cap) { e->err = "DOMQ output capacity too small"; return GZB_E_BADARG; }
+            if (S.qual_len) CK (cudaMemcpyAsync (S.qual, L->h[v].qual, S.qual_len, cudaMemcpyDeviceToHost, st));
+            if (S.runs_len) CK (cudaMemcpyAsync (S.runs, L->h[v].runs, S.runs_len, cudaMemcpyDeviceToHost, st));
+            if (S.mplx_len) CK (cudaMemcpyAsync (S.mplx, L->h[v].mplx, S.mplx_len, cudaMemcpyDeviceToHost, st));
+            if (S.divr_len) CK (cudaMemcpyAsync (S.divr, L->h[v].divr, S.divr_len, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    CK (cudaStreamSynchronize (st));
+    return GZB_OK;
+}
+
+// ================================================================================================ C-ABI: DOMQ (PIZ)
+extern "C" int gzb_domq_reconstruct (gzb_engine *e, gzb_domq_piz_vb *vbs, uint32_t n_vbs, uint32_t flags)
+{
+    if (!e || !vbs) return GZB_E_BADARG;
+    if (!n_vbs) return GZB_OK;
+    cudaSetDevice (e->device);
+    const bool devptr = flags & GZB_DEVICE_PTRS;
+    cudaStream_t st = e->stream;
+    std::vector<uint32_t> nl (n_vbs), bvb, bfirst;
+    std::vector<uint64_t> total (n_vbs, 0);
+    for (uint32_t v = 0; v < n_vbs; v++) {
+        nl[v] = vbs[v].n_lines;
+        if (vbs[v].num_norm_qs == 0 || vbs[v].denorm_len > NQ * NQ) { e->err = "bad DOMQ denorm table"; return GZB_E_BADARG; }
+        total[v] = vbs[v].out_cap;
+    }
+    line_blocks (nl, bvb, bfirst);
+    std::vector<DqPiz> h (n_vbs);
+    Carver c { nullptr, 0 };
+    DqPiz *d_vbs = nullptr; uint32_t *d_bvb = nullptr, *d_bfirst = nullptr;
+    for (int pass = 0; pass < 2; pass++) {
+        c.off = 0;
+        d_vbs = c.take<DqPiz> (n_vbs); d_bvb = c.take<uint32_t> (bvb.size () + 1); d_bfirst = c.take<uint32_t> (bfirst.size () + 1);
+        for (uint32_t v = 0; v < n_vbs; v++) {
+            DqPiz &D = h[v]; const gzb_domq_piz_vb &S = vbs[v];
+            D.qual_len = S.qual_len; D.runs_len = S.runs_len; D.mplx_len = S.mplx_len; D.divr_len = S.divr_len; D.n_lines = S.n_lines;
+            D.no_dom = S.num_norm_qs; D.denorm_len = S.denorm_len;
+            memcpy (D.denorm, S.denorm, S.denorm_len);
+            D.qual = devptr ? (const uint8_t *)S.qual : c.take<uint8_t> (S.qual_len + 16);
+            D.runs = devptr ? (const uint8_t *)S.runs : c.take<uint8_t> (S.runs_len + 16);
+            D.mplx = devptr ? (const uint8_t *)S.mplx : c.take<uint8_t> (S.mplx_len + 16);
+            D.divr = devptr ? (const uint8_t *)S.divr : c.take<uint8_t> (S.divr_len + 16);
+            D.line_len = devptr ? S.line_len : c.take<uint32_t> (S.n_lines + 1);
+            D.out  = devptr ? (uint8_t *)S.out : c.take<uint8_t> (total[v] + 16);
+            D.E    = c.take<uint8_t> (total[v] + 16);
+            D.cum  = c.take<uint32_t> (S.runs_len + 1);
+            D.nd_off = c.take<uint32_t> (S.n_lines + 1); D.dv_off = c.take<uint32_t> (S.n_lines + 1); D.out_off = c.take<uint32_t> (S.n_lines + 1);
+            D.dom_i = c.take<uint8_t> (S.n_lines + 1);
+            D.info = c.take<uint32_t> (8);
+        }
+        if (pass == 0) { int rc = engine_reserve (e, c.off, 4096); if (rc) return rc; c.base = e->ws; }
+    }
+    for (uint32_t v = 0; v < n_vbs; v++) {
+        DqPiz &D = h[v]; const gzb_domq_piz_vb &S = vbs[v];
+        if (!devptr) {
+            if (S.qual_len) CK (cudaMemcpyAsync ((void *)D.qual, S.qual, S.qual_len, cudaMemcpyHostToDevice, st));
+            if (S.runs_len) CK (cudaMemcpyAsync ((void *)D.runs, S.runs, S.runs_len, cudaMemcpyHostToDevice, st));
+            if (S.mplx_len) CK (cudaMemcpyAsync ((void *)D.mplx, S.mplx, S.mplx_len, cudaMemcpyHostToDevice, st));
+            if (S.divr_len) CK (cudaMemcpyAsync ((void *)D.divr, S.divr, S.divr_len, cudaMemcpyHostToDevice, st));
+            if (S.n_lines)  CK (cudaMemcpyAsync ((void *)D.line_len, S.line_len, (size_t)S.n_lines * 4, cudaMemcpyHostToDevice, st));
+        }
+        CK (cudaMemsetAsync (D.E, 0, total[v] + 16, st));
+        CK (cudaMemsetAsync (D.info, 0, 32, st));
+    }
+    CK (cudaMemcpyAsync (d_vbs, h.data (), n_vbs * sizeof (DqPiz), cudaMemcpyHostToDevice, st));
+    CK (cudaMemcpyAsync (d_bvb, bvb.data (), bvb.size () * 4, cudaMemcpyHostToDevice, st));
+    CK (cudaMemcpyAsync (d_bfirst, bfirst.data (), bfirst.size () * 4, cudaMemcpyHostToDevice, st));
+    k_dqp_lines<<<n_vbs, 512, 0, st>>>(d_vbs);
+    k_dqp_runs<<<n_vbs, 512, 0, st>>>(d_vbs);
+    k_dqp_literals<<<n_vbs, 512, 0, st>>>(d_vbs);
+    if (!bvb.empty ()) k_dqp_denorm<<<(uint32_t)bvb.size (), 256, 0, st>>>(d_vbs, d_bvb, d_bfirst);
+    e->launches += 4;
+    std::vector<uint32_t> info ((size_t)n_vbs * 8);
+    for (uint32_t v = 0; v < n_vbs; v++) CK (cudaMemcpyAsync (info.data () + (size_t)v * 8, h[v].info, 32, cudaMemcpyDeviceToHost, st));
+    CK (cudaStreamSynchronize (st));
+    for (uint32_t v = 0; v < n_vbs; v++) {
+        const uint32_t *I = info.data () + (size_t)v * 8;
+        if (I[2] || (uint64_t)I[0] + I[1] > vbs[v].out_cap) { e->err = "malformed DOMQ streams"; return GZB_E_CORRUPT; }
+        if (!devptr && (I[0] + I[1])) CK (cudaMemcpyAsync (vbs[v].out, h[v].out, (size_t)I[0] + I[1], cudaMemcpyDeviceToHost, st));
+    }
+    CK (cudaStreamSynchronize (st));
+    return GZB_OK;
+}

@@ -15,6 +15,11 @@ struct gzb_engine {
     uint64_t     launches = 0;
     float        last_chain_ms = 0;
     size_t       arena_hint = 0, arena_hint_dec = 0;
+    // DOMQ session: device state kept between gzb_domq_prepare and gzb_domq_split of the same batch
+    uint8_t     *dq_buf = nullptr; size_t dq_cap = 0;
+    void        *dq_session = nullptr;
+    void       (*dq_free)(void *) = nullptr;
+    uint32_t     dq_n_vbs = 0; bool dq_devptr = false;
 };
 
 int engine_reserve (gzb_engine *e, size_t ws_bytes, size_t pin_bytes);

@@ -28,6 +28,24 @@ class Section(C.Structure):
                 ("in_len", C.c_uint32), ("out_cap", C.c_uint32), ("out_len", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+class DomqVb(C.Structure):          # gzb_domq_vb
+    _fields_ = [("txt", C.c_void_p), ("txt_len", C.c_uint64), ("line_off", C.c_void_p), ("line_len", C.c_void_p),
+                ("n_lines", C.c_uint32), ("line_dom", C.c_void_p), ("line_diverse", C.c_void_p),
+                ("num_norm_qs", C.c_uint8), ("num_doms", C.c_uint8), ("has_diverse", C.c_uint8), ("pad", C.c_uint8),
+                ("denorm", C.c_uint8 * (95 * 95)), ("normalize", C.c_uint8 * (95 * 95)),
+                ("qual", C.c_void_p), ("qual_cap", C.c_uint32), ("qual_len", C.c_uint32),
+                ("runs", C.c_void_p), ("runs_cap", C.c_uint32), ("runs_len", C.c_uint32),
+                ("mplx", C.c_void_p), ("mplx_cap", C.c_uint32), ("mplx_len", C.c_uint32),
+                ("divr", C.c_void_p), ("divr_cap", C.c_uint32), ("divr_len", C.c_uint32)]
+
+
+class DomqPizVb(C.Structure):       # gzb_domq_piz_vb
+    _fields_ = [("qual", C.c_void_p), ("qual_len", C.c_uint32), ("runs", C.c_void_p), ("runs_len", C.c_uint32),
+                ("mplx", C.c_void_p), ("mplx_len", C.c_uint32), ("divr", C.c_void_p), ("divr_len", C.c_uint32),
+                ("denorm", C.c_void_p), ("denorm_len", C.c_uint32), ("num_norm_qs", C.c_uint8),
+                ("line_len", C.c_void_p), ("n_lines", C.c_uint32), ("out", C.c_void_p), ("out_cap", C.c_uint64)]
+
+
 _lib = None
 
 
@@ -59,6 +77,17 @@ def load():
     for nm in ("gzb_compress_sections", "gzb_uncompress_sections"):
         getattr(L, nm).restype = C.c_int
         getattr(L, nm).argtypes = [C.c_void_p, C.POINTER(Section), C.c_uint32, C.c_uint32]
+    L.gzb_acgt_packed_len.restype = C.c_uint64
+    L.gzb_acgt_packed_len.argtypes = [C.c_uint64]
+    L.gzb_acgt_pack.restype = C.c_int
+    L.gzb_acgt_pack.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_uint32]
+    L.gzb_acgt_unpack.restype = C.c_int
+    L.gzb_acgt_unpack.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32]
+    for nm in ("gzb_domq_prepare", "gzb_domq_split"):
+        getattr(L, nm).restype = C.c_int
+        getattr(L, nm).argtypes = [C.c_void_p, C.POINTER(DomqVb), C.c_uint32, C.c_uint32]
+    L.gzb_domq_reconstruct.restype = C.c_int
+    L.gzb_domq_reconstruct.argtypes = [C.c_void_p, C.POINTER(DomqPizVb), C.c_uint32, C.c_uint32]
     _lib = L
     return L
 
@@ -160,3 +189,87 @@ class Engine:
         rc = self.L.gzb_uncompress_sections(self.h, secs, n, flags)
         if rc != 0:
             raise GzbError(f"gzb_uncompress_sections failed ({rc}): {self._err()}")
+
+    # ---- ACGT (host buffers) ----
+    def acgt_pack(self, seq):
+        """codec_acgt_compress before its sub-codec: -> (packed LE 2-bit words, exception stream x, x_all_zero)"""
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        n = seq.size
+        packed = np.zeros(int(self.L.gzb_acgt_packed_len(n)) or 1, np.uint8)
+        x = np.zeros(max(n, 1), np.uint8)
+        allz = C.c_int(0)
+        rc = self.L.gzb_acgt_pack(self.h, seq.ctypes.data if n else x.ctypes.data, n, packed.ctypes.data, x.ctypes.data, C.byref(allz), 0)
+        if rc != 0:
+            raise GzbError(f"gzb_acgt_pack failed ({rc}): {self._err()}")
+        return packed[:int(self.L.gzb_acgt_packed_len(n))], x[:n], bool(allz.value)
+
+    def acgt_unpack(self, packed, x, n):
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        out = np.zeros(max(n, 1), np.uint8)
+        xp = None if x is None else np.ascontiguousarray(x, dtype=np.uint8).ctypes.data
+        rc = self.L.gzb_acgt_unpack(self.h, packed.ctypes.data if packed.size else out.ctypes.data, xp, n, out.ctypes.data, 0)
+        if rc != 0:
+            raise GzbError(f"gzb_acgt_unpack failed ({rc}): {self._err()}")
+        return out[:n]
+
+    # ---- DOMQ (host buffers): batch of VBlocks, each (txt, line_off, line_len) ----
+    def domq_encode(self, vbs):
+        """codec_domq_prepare_normalize + codec_domq_compress (before the sub-codec) for a batch of VBlocks.
+        vbs: list of (txt u8, line_off u64, line_len u32).  Returns a list of dicts with the four streams,
+        the per-line dom/diverse and the tables."""
+        n = len(vbs)
+        arr = (DomqVb * n)()
+        keep = []
+        for i, (txt, off, ln) in enumerate(vbs):
+            txt = np.ascontiguousarray(txt, np.uint8); off = np.ascontiguousarray(off, np.uint64); ln = np.ascontiguousarray(ln, np.uint32)
+            tot = int(txt.size)
+            bufs = dict(txt=txt if txt.size else np.zeros(1, np.uint8), off=off, ln=ln,
+                        dom=np.zeros(max(ln.size, 1), np.uint8), div=np.zeros(max(ln.size, 1), np.uint8),
+                        qual=np.zeros(2 * tot + 2, np.uint8), runs=np.zeros(tot + 2, np.uint8),
+                        mplx=np.zeros(ln.size + 1, np.uint8), divr=np.zeros(tot + 1, np.uint8))
+            keep.append(bufs)
+            a = arr[i]
+            a.txt = bufs["txt"].ctypes.data; a.txt_len = txt.size
+            a.line_off = off.ctypes.data; a.line_len = ln.ctypes.data; a.n_lines = ln.size
+            a.line_dom = bufs["dom"].ctypes.data; a.line_diverse = bufs["div"].ctypes.data
+            for k in ("qual", "runs", "mplx", "divr"):
+                setattr(a, k, bufs[k].ctypes.data); setattr(a, k + "_cap", bufs[k].size)
+        rc = self.L.gzb_domq_prepare(self.h, arr, n, 0)
+        if rc != 0:
+            raise GzbError(f"gzb_domq_prepare failed ({rc}): {self._err()}")
+        rc = self.L.gzb_domq_split(self.h, arr, n, 0)
+        if rc != 0:
+            raise GzbError(f"gzb_domq_split failed ({rc}): {self._err()}")
+        res = []
+        for i in range(n):
+            a, b = arr[i], keep[i]
+            nn, nd = a.num_norm_qs, a.num_doms
+            res.append(dict(num_norm_qs=nn, num_doms=nd, has_diverse=a.has_diverse,
+                            denorm=np.frombuffer(bytes(a.denorm), np.uint8)[:nn * nd].copy(),
+                            normalize=np.frombuffer(bytes(a.normalize), np.uint8).copy(),
+                            line_dom=b["dom"][:a.n_lines].copy(), line_diverse=b["div"][:a.n_lines].copy(),
+                            qual=b["qual"][:a.qual_len].copy(), runs=b["runs"][:a.runs_len].copy(),
+                            mplx=b["mplx"][:a.mplx_len].copy(), divr=b["divr"][:a.divr_len].copy()))
+        return res
+
+    def domq_decode(self, encs, line_lens):
+        """codec_domq_reconstruct for all lines of each VBlock.  encs: dicts as returned by domq_encode."""
+        n = len(encs)
+        arr = (DomqPizVb * n)()
+        keep, outs = [], []
+        z = np.zeros(1, np.uint8)
+        for i, (enc, ln) in enumerate(zip(encs, line_lens)):
+            ln = np.ascontiguousarray(ln, np.uint32)
+            tot = int(ln.sum())
+            out = np.zeros(tot + 1, np.uint8)
+            b = {k: np.ascontiguousarray(enc[k], np.uint8) for k in ("qual", "runs", "mplx", "divr", "denorm")}
+            keep.append((b, ln)); outs.append(out)
+            a = arr[i]
+            for k in ("qual", "runs", "mplx", "divr"):
+                setattr(a, k, (b[k] if b[k].size else z).ctypes.data); setattr(a, k + "_len", b[k].size)
+            a.denorm = b["denorm"].ctypes.data; a.denorm_len = b["denorm"].size; a.num_norm_qs = enc["num_norm_qs"]
+            a.line_len = ln.ctypes.data; a.n_lines = ln.size; a.out = out.ctypes.data; a.out_cap = tot
+        rc = self.L.gzb_domq_reconstruct(self.h, arr, n, 0)
+        if rc != 0:
+            raise GzbError(f"gzb_domq_reconstruct failed ({rc}): {self._err()}")
+        return [o[:-1] for o in outs]

@@ -1,0 +1,91 @@
+"""GPU parity tests for the FASTQ-side genozip codecs: ACGT/XCGT packing and DOMQ — CUDA path through the C-ABI vs the
+CPU restatement (oracle/gz_port.c), byte-exact both ways, incl. ragged/empty lines and the all-dom / run-length edge cases."""
+import numpy as np, pytest
+import orc
+from datagen import fastq_vb, line_table, ragged_quals
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from genozip_b200 import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def test_acgt(eng):
+    seq, _ = fastq_vb(3000, 151, 1, lower_frac=0.01, n_frac=0.01)
+    for n in (0, 1, 5, 31, 32, 33, 63, 64, 65, 1000, 4097, seq.size):
+        s = seq[:n].copy()
+        p, x, allz = eng.acgt_pack(s)
+        pw, xw, zw = orc.acgt_pack(s)
+        assert np.array_equal(p, pw) and np.array_equal(x, xw) and allz == zw, f"n={n}"
+        assert np.array_equal(eng.acgt_unpack(pw, None if zw else xw, n), s)
+    # pure ACGT: exception stream all zero -> acgt_no_x (codec_acgt.c:136-140)
+    s = np.frombuffer(b"ACGT", np.uint8)[np.random.default_rng(2).integers(0, 4, 100000)].copy()
+    p, x, allz = eng.acgt_pack(s)
+    assert allz and not x.any() and np.array_equal(p, orc.acgt_pack(s)[0])
+    assert np.array_equal(eng.acgt_unpack(p, None, s.size), s)
+    # IUPAC and odd characters
+    s = np.frombuffer(b"ACGTNacgtnRYSWKMBDHVUryswkmbdhvu*-.", np.uint8).copy()
+    p, x, allz = eng.acgt_pack(s)
+    pw, xw, zw = orc.acgt_pack(s)
+    assert np.array_equal(p, pw) and np.array_equal(x, xw)
+    assert np.array_equal(eng.acgt_unpack(p, x, s.size), s)
+
+
+def _check_domq(eng, vbs):
+    got = eng.domq_encode(vbs)
+    for (txt, off, ln), g in zip(vbs, got):
+        w = orc.domq_encode(txt, off, ln)
+        for k in ("num_norm_qs", "num_doms", "has_diverse"):
+            assert g[k] == w[k], k
+        for k in ("denorm", "line_dom", "line_diverse", "qual", "runs", "mplx", "divr"):
+            assert g[k].size == w[k].size and np.array_equal(g[k], w[k]), f"{k}: GPU != oracle (len {g[k].size} vs {w[k].size})"
+    back = eng.domq_decode(got, [v[2] for v in vbs])
+    for (txt, off, ln), b, g in zip(vbs, back, got):
+        want = np.concatenate([txt[int(o):int(o) + int(l)] for o, l in zip(off, ln)]) if ln.sum() else np.zeros(0, np.uint8)
+        assert np.array_equal(b, want), "GPU DOMQ reconstruct mismatch"
+        assert np.array_equal(orc.domq_decode(g, ln), want)
+
+
+def test_domq_fastq_batch(eng):
+    vbs = []
+    for s in range(4):
+        _, q = fastq_vb(5000 + 1000 * s, 150, 10 + s)
+        off, ln = line_table(5000 + 1000 * s, 150)
+        vbs.append((q, off, ln))
+    _check_domq(eng, vbs)
+
+
+def test_domq_ragged(eng):
+    _check_domq(eng, [ragged_quals(s) for s in range(6)])
+
+
+def test_domq_edges(eng):
+    vbs = []
+    q = np.full(10 * 100, ord("F"), np.uint8)              # all dom -> QUAL.local = 'X', no runs
+    vbs.append((q,) + line_table(10, 100))
+    for r in (254, 255, 508, 509, 5000):                    # run-length byte boundaries (codec_domq.c:368-377)
+        L = max(600, r + 10)
+        q = np.concatenate([np.full(r, ord("F"), np.uint8), [ord("#")], np.full(L - r - 1, ord("F"), np.uint8)]).astype(np.uint8)
+        vbs.append((q,) + line_table(1, L))
+    q = np.concatenate([np.frombuffer(b"#:#:", np.uint8), np.full(96, ord("F"), np.uint8)])   # leading non-doms then only doms
+    vbs.append((q.copy(),) + line_table(1, 100))
+    q2 = np.tile(np.frombuffer(b"F#", np.uint8), 3000)       # alternating: no run ever
+    vbs.append((q2.copy(),) + line_table(40, 150))
+    _check_domq(eng, vbs)
+
+
+def test_domq_full_vb_properties(eng):
+    """BASELINE-size VBlock (92K reads x 150): round trip + stream-length identities instead of the slow oracle decode"""
+    _, q = fastq_vb(92000, 150, 77)
+    off, ln = line_table(92000, 150)
+    g = eng.domq_encode([(q, off, ln)])[0]
+    w = orc.domq_encode(q, off, ln)
+    for k in ("qual", "runs", "mplx", "divr", "denorm"):
+        assert np.array_equal(g[k], w[k]), k
+    back = eng.domq_decode([g], [ln])[0]
+    assert np.array_equal(back, q)
