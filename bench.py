@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py — FASTQ input GB/s (zip + piz) of the per-VBlock codec path on B200, next to the reference's CPU path.
+
+One "step" = one zip pass + one piz pass of the hot path over one batch of V synthetic Illumina-like FASTQ VBlocks
+(BASELINE.json configs[1] scaled to one GPU: 150 bp reads, ~32 MB of FASTQ text per VBlock; codec_domq + codec_acgt
+hot, read-name contexts through the simple codecs).  Out of scope and therefore NOT in the timed region: the
+segmenter that produces these streams, and LZMA of the 2-bit sequence words (host).
+
+  python bench.py --gpus N --steps K --warmup W            (N>1 via torchrun, one rank per GPU; weak scaling)
+  python bench.py --impl reference ...                      the reference's CPU implementation of the same path
+"""
+import argparse, json, os, subprocess, sys, threading, time
+import ctypes as C
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fastq_input_GBps_zip_plus_piz"
+UNIT = "GB/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gzb200", choices=["gzb200", "reference"])
+    ap.add_argument("--vblocks", type=int, default=int(os.environ.get("GZB_BENCH_VBLOCKS", "32")), help="VBlocks per GPU per step")
+    ap.add_argument("--reads", type=int, default=92000, help="reads per VBlock (92,000 x 150 bp ~ 32 MB of FASTQ text)")
+    ap.add_argument("--read-len", type=int, default=150)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu):
+        self.gpu, self.p, self.lines = gpu, None, []
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu)],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for ln in self.p.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm, mx, reasons = [], 0, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx = max(mx, float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- reference / CPU arm
+def cpu_path_time(data_np, n_reads, read_len, codec, threads, n_vb):
+    """The reference's CPU implementation of the same path on host cores: htscodecs entry points from oracle/_ref
+    (the reference's own objects) when present, else the CPU restatement; DOMQ/ACGT through the restatement.
+    One task per VBlock, `threads` host threads (ctypes releases the GIL).  Returns (t_zip, t_piz, kind)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import orc                                              # test infrastructure: used here only as the CPU baseline
+    from concurrent.futures import ThreadPoolExecutor
+    kind = "reference" if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libhts_ref.so")) else "port"
+    impl = "ref" if kind == "reference" else "port"
+    orc.port(); (orc.ref() if impl == "ref" else None)
+    off = (np.arange(n_reads, dtype=np.uint64) * np.uint64(read_len)); ln = np.full(n_reads, read_len, np.uint32)
+    names = ("Q_TILE", "Q_X", "Q_Y", "Q_MISC")
+
+    def zip_vb(v):
+        seq, qual = data_np["seq"][v], data_np["qual"][v]
+        packed, x, allz = orc.acgt_pack(seq)
+        enc = orc.domq_encode(qual, off, ln)
+        streams = {"QUAL": enc["qual"], "DOMQRUNS": enc["runs"], "QUALMPLX": enc["mplx"], "DIVRQUAL": enc["divr"]}
+        if not allz:
+            streams["NONREF_X"] = x
+        for k in names:
+            streams[k] = data_np[k][v]
+        comp = {}
+        for s, d in streams.items():
+            if d.size:
+                c = codec[s]
+                comp[s] = (orc.compress(impl, "rans" if c.startswith("RAN") else "arith", d, orc.ORDER[c]), d.size)
+        return dict(packed=packed, allz=allz, enc=enc, comp=comp)
+
+    def piz_vb(z):
+        dec = {}
+        for s, (c, n) in z["comp"].items():
+            cc = codec[s]
+            dec[s] = orc.uncompress(impl, "rans" if cc.startswith("RAN") else "arith", c, n)
+        e = dict(z["enc"]); e.update(qual=dec["QUAL"], runs=dec.get("DOMQRUNS", np.zeros(0, np.uint8)), mplx=dec["QUALMPLX"],
+                                     divr=dec.get("DIVRQUAL", np.zeros(0, np.uint8)))
+        q = orc.domq_decode(e, ln)
+        s = orc.acgt_unpack(z["packed"], None if z["allz"] else dec["NONREF_X"], n_reads * read_len)
+        return q.size + s.size
+
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        t0 = time.perf_counter(); zs = list(ex.map(zip_vb, range(n_vb))); t1 = time.perf_counter()
+        list(ex.map(piz_vb, zs)); t2 = time.perf_counter()
+    return t1 - t0, t2 - t1, kind
+
+
+def synth_numpy(V, n_reads, read_len, seed):
+    """numpy twin of fastq_path.synth_vblocks for the CPU-only arm (no torch.cuda needed)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from datagen import fastq_vb
+    out = {k: [] for k in ("seq", "qual", "Q_TILE", "Q_X", "Q_Y", "Q_MISC")}
+    r = np.random.default_rng(seed)
+    for v in range(V):
+        s, q = fastq_vb(n_reads, read_len, seed * 1000 + v)
+        out["seq"].append(s); out["qual"].append(q)
+        out["Q_TILE"].append((np.arange(n_reads) // 977 % 96).astype(np.uint8))
+        xs = (np.cumsum(r.integers(0, 60, n_reads)) % 30000 + 1000).astype(">u4").view(np.uint8)
+        ys = r.integers(1000, 30000, n_reads).astype(">u4").view(np.uint8)
+        out["Q_X"].append(xs.copy()); out["Q_Y"].append(ys.copy())
+        out["Q_MISC"].append(r.choice(4, n_reads, p=[.9, .05, .03, .02]).astype(np.uint8))
+    return out
+
+
+DEFAULT_CODECS = {"QUAL": "RANB", "DOMQRUNS": "RANB", "QUALMPLX": "RANB", "DIVRQUAL": "RANB", "NONREF_X": "RANB",
+                  "Q_TILE": "RANB", "Q_X": "RANW", "Q_Y": "RANW", "Q_MISC": "RANB"}
+
+
+def run_reference(args):
+    """--impl reference: time the reference's CPU implementation on this box's host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_vb = max(cores, 8)                                     # one VBlock per task keeps every host thread busy
+    from genozip_b200.fastq_path import txt_bytes_per_vb
+    data = synth_numpy(n_vb, args.reads, args.read_len, 2)
+    codec = load_codecs() or DEFAULT_CODECS
+    ts = []
+    for i in range(args.warmup + args.steps):
+        tz, tp, kind = cpu_path_time(data, args.reads, args.read_len, codec, cores, n_vb)
+        if i >= args.warmup:
+            ts.append((tz, tp))
+    tz = sum(t[0] for t in ts); tp = sum(t[1] for t in ts)
+    nbytes = n_vb * txt_bytes_per_vb(args.reads, args.read_len) * len(ts)
+    val = nbytes / (tz + tp) / 1e9
+    sample = f"{n_vb} VBlocks x {args.reads} reads x {args.read_len} bp per step, {cores} host threads, one VBlock per task"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * (tz + tp) / len(ts), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic", "zip_GBps": nbytes / tz / 1e9, "piz_GBps": nbytes / tp / 1e9,
+        "config": {"workload": "fastq_illumina_150bp_paired_vb32MB (BASELINE configs[1] per-GPU share)", "vblocks_per_step": n_vb,
+                   "reads_per_vblock": args.reads, "read_len": args.read_len, "codecs": codec,
+                   "excluded": "segmenter; LZMA of the 2-bit words (both excluded from the GPU arm as well)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+CODEC_CACHE = os.path.join(ROOT, "gpurun_out", "bench_codecs.json")
+
+
+def load_codecs():
+    try:
+        return json.load(open(CODEC_CACHE))
+    except Exception:
+        return None
+
+
+# ---------------------------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from genozip_b200 import Engine
+    from genozip_b200.fastq_path import FastqCodecPath, synth_vblocks, txt_bytes_per_vb, STREAMS
+
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    eng = Engine(local)
+    V = args.vblocks
+    path = FastqCodecPath(eng, V, args.reads, args.read_len)
+    # VBlocks are sharded round-robin by vblock_i: rank r owns vblock_i = r+1, r+1+world, ...  Seeds follow vblock_i.
+    data = synth_vblocks(V, args.reads, args.read_len, 1000 + rank, dev)
+    codecs = path.assign_codecs(data) if rank == 0 else None
+    if world > 1:
+        obj = [codecs]; dist.broadcast_object_list(obj, src=0); codecs = obj[0]
+    path.codec = dict(codecs)
+    if rank == 0:
+        os.makedirs(os.path.dirname(CODEC_CACHE), exist_ok=True)
+        json.dump(codecs, open(CODEC_CACHE, "w"))
+    path.alloc_piz()
+
+    # correctness gate before timing: piz(zip(x)) == x on the device
+    meta = path.zip_device(data)
+    path.piz_device(meta)
+    torch.cuda.synchronize()
+    assert torch.equal(path.seq_out_d, data["seq"]) and torch.equal(path.qual_out_d, data["qual"]), "round trip failed"
+    for s in ("Q_TILE", "Q_X", "Q_Y", "Q_MISC"):
+        assert torch.equal(path.dec_d[s][:, :data[s].shape[1]], data[s]), f"round trip failed: {s}"
+
+    txt_bytes = V * txt_bytes_per_vb(args.reads, args.read_len)
+    stream = path.stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def section_list_gather(meta):
+        """final section-list gather: every rank's per-section compressed lengths to all ranks over NCCL"""
+        if world == 1:
+            return
+        t = torch.tensor([[m["comp_len"].get(s, 0) for s in STREAMS] for m in meta], dtype=torch.int32, device=dev)
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+
+    def timed(fn_zip, fn_piz, steps, warmup):
+        tz = tp = 0.0
+        kern = {"rans_enc": 0.0, "arith_enc": 0.0, "rans_dec": 0.0, "arith_dec": 0.0}
+        for i in range(warmup + steps):
+            barrier()
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            with torch.cuda.stream(stream):
+                e0.record(stream)
+                m = fn_zip()
+                section_list_gather(m if isinstance(m, list) else m[0])
+                kz = (eng.L.gzb_last_kernel_ms(eng.h, 0), eng.L.gzb_last_kernel_ms(eng.h, 1))
+                e1.record(stream)
+                r = fn_piz(m if isinstance(m, list) else m[0])
+                kp = (eng.L.gzb_last_kernel_ms(eng.h, 0), eng.L.gzb_last_kernel_ms(eng.h, 1))
+                e2.record(stream)
+            barrier()
+            if i >= warmup:
+                tz += e0.elapsed_time(e1); tp += e1.elapsed_time(e2)
+                kern["rans_enc"] += kz[0]; kern["arith_enc"] += kz[1]; kern["rans_dec"] += kp[0]; kern["arith_dec"] += kp[1]
+        t = torch.tensor([tz, tp], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)                     # max over ranks
+        return t[0].item() / steps, t[1].item() / steps, {k: v / steps for k, v in kern.items()}, (m, r)
+
+    clocks = ClockSampler(local); clocks.start()
+    l0 = eng.launches
+    zip_ms, piz_ms, kern, (meta, _) = timed(lambda: path.zip_device(data), lambda m: path.piz_device(m), args.steps, args.warmup)
+    launches = (eng.launches - l0) // (args.steps + args.warmup) * args.steps
+    clk = clocks.stop()
+    value = world * txt_bytes / ((zip_ms + piz_ms) * 1e-3) / 1e9
+
+    # e2e: same step through the C-ABI with HOST (pinned) buffers — H2D of the inputs and D2H of the results inside
+    e2e = None
+    if not args.no_e2e:
+        path.alloc_host(data)
+        ez, ep, _, (zr, pr) = timed(lambda: path.zip_host(), lambda m: path.piz_host(m), max(2, args.steps // 2), 1)
+        meta_h, h2d_z, d2h_z = zr
+        h2d_p, d2h_p = pr
+        assert torch.equal(path.h["seq_out"], path.h["seq"]) and torch.equal(path.h["qual_out"], path.h["qual"]), "host round trip failed"
+        e2e = {"value": world * txt_bytes / ((ez + ep) * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d_z + h2d_p), "d2h_bytes_per_step": int(d2h_z + d2h_p),
+               "zip_ms": ez, "piz_ms": ep}
+
+    # roofline of the dominant kernel: algorithmic bytes (N uncompressed + C compressed) / its launch time
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    which_peak = "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    alg = {"rans": 0, "arith": 0}
+    for m in meta:
+        for s, n in m["len"].items():
+            if n:
+                alg["rans" if codecs[s].startswith("RAN") else "arith"] += n + m["comp_len"][s]
+    dom = max(kern, key=lambda k: kern[k])
+    dom_bytes = alg["rans" if dom.startswith("rans") else "arith"]
+    achieved = dom_bytes / (kern[dom] * 1e-3) / 1e9 if kern[dom] > 0 else 0.0
+    kname = {"rans_enc": "k_rans_encode", "rans_dec": "k_rans_decode", "arith_enc": "k_arith_encode", "arith_dec": "k_arith_decode"}[dom]
+    roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "peak_source": which_peak, "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": kern[dom],
+            "note": "entropy chains are dependency-bound (4 chains per rANS leaf, 1 per arithmetic leaf, fixed by the bitstream); "
+                    "see profiles/ for dram__bytes of this kernel", "kernel_ms_per_step": kern}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n_vb = max(4, min(V, cores))
+        dnp = {k: [data[k][v].cpu().numpy() for v in range(n_vb)] for k in data}
+        tz, tp, kind = cpu_path_time(dnp, args.reads, args.read_len, codecs, cores, n_vb)
+        nb = n_vb * txt_bytes_per_vb(args.reads, args.read_len)
+        cpu = {"value": nb / (tz + tp) / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"{n_vb} of the step's {V} VBlocks, one VBlock per task on {cores} host threads (zip {tz:.2f} s, piz {tp:.2f} s)",
+               "zip_GBps": nb / tz / 1e9, "piz_GBps": nb / tp / 1e9}
+
+    if rank == 0:
+        comp_total = sum(sum(m["comp_len"].values()) for m in meta)
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": zip_ms + piz_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "zip_GBps": world * txt_bytes / (zip_ms * 1e-3) / 1e9, "piz_GBps": world * txt_bytes / (piz_ms * 1e-3) / 1e9,
+            "config": {"workload": "fastq_illumina_150bp_paired_vb32MB (BASELINE configs[1] per-GPU share)", "vblocks_per_gpu_per_step": V,
+                       "reads_per_vblock": args.reads, "read_len": args.read_len, "txt_bytes_per_step_per_gpu": txt_bytes,
+                       "codecs": codecs, "l2": "inputs (>= 0.9 GB per step) are larger than L2; no flush needed",
+                       "sections_per_step": sum(1 for m in meta for n in m["len"].values() if n), "compressed_bytes_per_step": comp_total,
+                       "excluded": "segmenter; LZMA of the 2-bit sequence words (host, out of scope)", "sharding": "VBlocks round-robin by vblock_i, no data-path collective; NCCL all_gather of the section list only"},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_gpu(a)

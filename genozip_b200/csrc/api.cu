@@ -90,7 +90,7 @@ extern "C" int gzb_engine_create (int device, gzb_engine **out)
     if (cudaSetDevice (device) != cudaSuccess || cudaStreamCreateWithFlags (&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
         g_last_error = "cudaStreamCreate failed"; delete e; return GZB_E_CUDA;
     }
-    cudaEventCreate (&e->ev0); cudaEventCreate (&e->ev1);
+    cudaEventCreate (&e->ev0); cudaEventCreate (&e->ev1); cudaEventCreate (&e->ev2);
     // log tables for the order-1 table-size decision: must come from the same libm the reference links
     double l10[257], l12[257];
     for (int k = 0; k <= 256; k++) { l10[k] = log ((double)(1024 + k)); l12[k] = log ((double)(4096 + k)); }
@@ -109,7 +109,7 @@ extern "C" void gzb_engine_destroy (gzb_engine *e)
     if (e->dq_buf) cudaFree (e->dq_buf);
     if (e->dq_session && e->dq_free) e->dq_free (e->dq_session);
     if (e->pin) cudaFreeHost (e->pin);
-    cudaEventDestroy (e->ev0); cudaEventDestroy (e->ev1);
+    cudaEventDestroy (e->ev0); cudaEventDestroy (e->ev1); cudaEventDestroy (e->ev2);
     cudaStreamDestroy (e->stream);
     delete e;
 }
@@ -120,6 +120,7 @@ extern "C" int gzb_engine_sync (gzb_engine *e) { cudaSetDevice (e->device); CK (
 extern "C" int gzb_vb_device (uint32_t vblock_i, int n_devices) { return n_devices > 0 ? (int)((vblock_i ? vblock_i - 1 : 0) % (uint32_t)n_devices) : 0; }
 extern "C" uint64_t gzb_kernel_launches (gzb_engine *e) { return e->launches; }
 extern "C" float gzb_last_chain_ms (gzb_engine *e) { return e->last_chain_ms; }
+extern "C" float gzb_last_kernel_ms (gzb_engine *e, int which) { return which ? e->last_arith_ms : e->last_rans_ms; }
 
 int engine_reserve (gzb_engine *e, size_t ws_bytes, size_t pin_bytes)
 {
@@ -202,7 +203,9 @@ extern "C" int gzb_compress_sections (gzb_engine *e, gzb_section *secs, uint32_t
     if (!e) return GZB_E_BADARG;
     if (!n) return GZB_OK;
     cudaSetDevice (e->device);
-    const bool devptr = flags & GZB_DEVICE_PTRS;
+    const bool devall = flags & GZB_DEVICE_PTRS;
+    auto in_dev  = [&] (uint32_t i) { return devall || (secs[i].sflags & GZB_SEC_IN_DEVICE); };
+    auto out_dev = [&] (uint32_t i) { return devall || (secs[i].sflags & GZB_SEC_OUT_DEVICE); };
 
     // ---- plan on the host
     std::vector<EncSection> hs (n);
@@ -223,9 +226,9 @@ extern "C" int gzb_compress_sections (gzb_engine *e, gzb_section *secs, uint32_t
         S.stripe = (order & F_STRIPE) && S.n > 20;
         S.first_leaf = (uint32_t)hl.size ();
         if (S.soft_fail) { S.n_leaves = 0; continue; }
-        in_total += (S.n + 15) & ~15ull;
-        out_total += ((size_t)std::min<uint32_t> (s.out_cap, gzb_est_size (s.codec, s.in_len)) + 15) & ~15ull;
-        if (!devptr && S.n < SMALL_COPY) small_in += (S.n + 15) & ~15ull;
+        if (!in_dev (i))  in_total += (S.n + 15) & ~15ull;
+        if (!out_dev (i)) out_total += ((size_t)std::min<uint32_t> (s.out_cap, gzb_est_size (s.codec, s.in_len)) + 15) & ~15ull;
+        if (!in_dev (i) && S.n < SMALL_COPY) small_in += (S.n + 15) & ~15ull;
         auto add_leaf = [&] (uint32_t ln, uint32_t order_req, size_t plane_off) {
             EncLeaf L; memset (&L, 0, sizeof L);
             L.n = ln; L.section = i; L.coder = coder; L.order_req = (uint8_t)order_req;
@@ -302,14 +305,14 @@ extern "C" int gzb_compress_sections (gzb_engine *e, gzb_section *secs, uint32_t
             d_cursor       = c.take<unsigned long long> (1);
             d_overflow     = c.take<int> (1);
             d_hist0        = c.take<uint32_t> ((size_t)(nl ? nl : 1) * 256);
-            d_in           = c.take<uint8_t> (devptr ? 1 : in_total);
-            d_out          = c.take<uint8_t> (devptr ? 1 : out_total);
+            d_in           = c.take<uint8_t> (in_total + 1);
+            d_out          = c.take<uint8_t> (out_total + 1);
             d_planes       = c.take<uint8_t> (plane_total + 1);
             d_pack         = c.take<uint8_t> (pack_total + 1);
             d_outbuf       = c.take<uint8_t> (outbuf_total + 1);
             d_arena        = c.take<uint8_t> (arena_est);
             if (pass == 0) {
-                int rc = engine_reserve (e, c.off, (devptr ? 0 : small_in + 512 * (size_t)n) + meta_bytes + 8192);
+                int rc = engine_reserve (e, c.off, small_in + 512 * (size_t)n + meta_bytes + 8192);
                 if (rc) return rc;
                 c.base = e->ws;
             }
@@ -324,11 +327,10 @@ extern "C" int gzb_compress_sections (gzb_engine *e, gzb_section *secs, uint32_t
             for (uint32_t i = 0; i < n; i++) {
                 EncSection &S = S2[i];
                 if (S.soft_fail) continue;
-                if (devptr) { S.in = (const uint8_t *)secs[i].in; S.out = (uint8_t *)secs[i].out; }
-                else {
-                    S.in = d_in + io; io += (S.n + 15) & ~15ull;
-                    S.out = d_out + oo; oo += ((size_t)std::min<uint32_t> (secs[i].out_cap, gzb_est_size (secs[i].codec, secs[i].in_len)) + 15) & ~15ull;
-                }
+                if (in_dev (i)) S.in = (const uint8_t *)secs[i].in;
+                else { S.in = d_in + io; io += (S.n + 15) & ~15ull; }
+                if (out_dev (i)) S.out = (uint8_t *)secs[i].out;
+                else { S.out = d_out + oo; oo += ((size_t)std::min<uint32_t> (secs[i].out_cap, gzb_est_size (secs[i].codec, secs[i].in_len)) + 15) & ~15ull; }
                 if (S.stripe) S.planes = d_planes + (size_t)hs[i].planes;
                 uint32_t cnt = S.stripe ? ((S.n_leaves & 15) + ((S.n_leaves >> 4) & 15) + ((S.n_leaves >> 8) & 15) + ((S.n_leaves >> 12) & 15)) : 1;
                 for (uint32_t k = 0; k < cnt; k++) {
@@ -355,17 +357,17 @@ extern "C" int gzb_compress_sections (gzb_engine *e, gzb_section *secs, uint32_t
         P.rans_gpw = pick_rans_gpw (P.n_rans); P.arith_lpw = pick_arith_lpw (P.n_arith);
         P.copy_parts = (n <= 64) ? 32 : (n <= 1024 ? 8 : 2);
         P.arena = Arena { d_arena, (unsigned long long)arena_est, d_cursor, d_overflow };
-        P.ev_chain0 = e->ev0; P.ev_chain1 = e->ev1;
+        P.ev_chain0 = e->ev0; P.ev_chain1 = e->ev1; P.ev_chain2 = e->ev2;
 
         // ---- upload: metadata blob, inputs (small ones gathered through pinned staging)
         cudaStream_t st = e->stream;
         memcpy (e->pin, meta.data (), meta_bytes);
         CK (cudaMemcpyAsync (e->ws + meta_off, e->pin, meta_bytes, cudaMemcpyHostToDevice, st));
-        if (!devptr) {
+        {
             int rc = stage_inputs (e, e->pin + ((meta_bytes + 255) & ~(size_t)255), n,
                                    [&] (uint32_t i) { return (uint8_t *)S2[i].in; },
                                    [&] (uint32_t i) { return (const uint8_t *)secs[i].in; },
-                                   [&] (uint32_t i) { return S2[i].soft_fail ? 0u : S2[i].n; });
+                                   [&] (uint32_t i) { return (S2[i].soft_fail || in_dev (i)) ? 0u : S2[i].n; });
             if (rc) return rc;
         }
         CK (cudaMemsetAsync (d_cursor, 0, 512, st));
@@ -388,18 +390,19 @@ extern "C" int gzb_compress_sections (gzb_engine *e, gzb_section *secs, uint32_t
             e->arena_hint = arena_est;
             continue;
         }
-        float ms = 0; cudaEventElapsedTime (&ms, e->ev0, e->ev1); e->last_chain_ms = ms;
+        float ms = 0; cudaEventElapsedTime (&ms, e->ev0, e->ev1); e->last_rans_ms = ms; cudaEventElapsedTime (&ms, e->ev1, e->ev2); e->last_arith_ms = ms; e->last_chain_ms = e->last_rans_ms + e->last_arith_ms;
 
         for (uint32_t i = 0; i < n; i++) {
             secs[i].status = res[i].status; secs[i].out_len = res[i].out_len;
             if (res[i].status == 0 && res[i].out_len > secs[i].out_cap) { secs[i].status = GZB_SOFT_FAIL; secs[i].out_len = 0; }
         }
-        if (!devptr) {
-            for (uint32_t i = 0; i < n; i++)
-                if (secs[i].status == 0 && secs[i].out_len)
-                    CK (cudaMemcpyAsync (secs[i].out, S2[i].out, secs[i].out_len, cudaMemcpyDeviceToHost, st));
-            CK (cudaStreamSynchronize (st));
-        }
+        bool any_d2h = false;
+        for (uint32_t i = 0; i < n; i++)
+            if (!out_dev (i) && secs[i].status == 0 && secs[i].out_len) {
+                CK (cudaMemcpyAsync (secs[i].out, S2[i].out, secs[i].out_len, cudaMemcpyDeviceToHost, st));
+                any_d2h = true;
+            }
+        if (any_d2h) CK (cudaStreamSynchronize (st));
         return GZB_OK;
     }
     e->err = "device arena kept overflowing";
@@ -412,7 +415,9 @@ extern "C" int gzb_uncompress_sections (gzb_engine *e, gzb_section *secs, uint32
     if (!e) return GZB_E_BADARG;
     if (!n) return GZB_OK;
     cudaSetDevice (e->device);
-    const bool devptr = flags & GZB_DEVICE_PTRS;
+    const bool devall = flags & GZB_DEVICE_PTRS;
+    auto in_dev  = [&] (uint32_t i) { return devall || (secs[i].sflags & GZB_SEC_IN_DEVICE); };
+    auto out_dev = [&] (uint32_t i) { return devall || (secs[i].sflags & GZB_SEC_OUT_DEVICE); };
 
     std::vector<DecSection> hs (n);
     std::vector<uint32_t> order_idx (n);
@@ -425,8 +430,10 @@ extern "C" int gzb_uncompress_sections (gzb_engine *e, gzb_section *secs, uint32
         if (!codec_info (s.codec, &coder, &order) || !s.in || !s.out || !s.in_len || !s.out_cap) { s.status = GZB_E_BADARG; e->err = "bad section"; return GZB_E_BADARG; }
         DecSection &S = hs[i]; memset (&S, 0, sizeof S);
         S.in_len = s.in_len; S.n = s.out_cap; S.coder = coder;
-        in_total += (S.in_len + 15) & ~15ull; out_total += (S.n + 15) & ~15ull; aux_total += (S.n + 15) & ~15ull;
-        if (!devptr && S.in_len < SMALL_COPY) small_in += (S.in_len + 15) & ~15ull;
+        if (!in_dev (i)) in_total += (S.in_len + 15) & ~15ull;
+        if (!out_dev (i)) out_total += (S.n + 15) & ~15ull;
+        aux_total += (S.n + 15) & ~15ull;
+        if (!in_dev (i) && S.in_len < SMALL_COPY) small_in += (S.in_len + 15) & ~15ull;
         (coder == CODER_RANS ? n_rans_sec : n_arith_sec)++;
         order_idx[i] = i;
     }
@@ -456,13 +463,13 @@ extern "C" int gzb_uncompress_sections (gzb_engine *e, gzb_section *secs, uint32
             P.results    = c.take<SectionResult> (n);
             d_cursor     = c.take<unsigned long long> (1);
             d_overflow   = c.take<int> (1);
-            d_in         = c.take<uint8_t> (devptr ? 1 : in_total);
-            d_out        = c.take<uint8_t> (devptr ? 1 : out_total);
+            d_in         = c.take<uint8_t> (in_total + 1);
+            d_out        = c.take<uint8_t> (out_total + 1);
             d_planes     = c.take<uint8_t> (aux_total);
             d_tmp        = c.take<uint8_t> (aux_total);
             d_arena      = c.take<uint8_t> (arena_est);
             if (pass == 0) {
-                int rc = engine_reserve (e, c.off, (devptr ? 0 : small_in + 512 * (size_t)n) + meta_bytes + 8192);
+                int rc = engine_reserve (e, c.off, small_in + 512 * (size_t)n + meta_bytes + 8192);
                 if (rc) return rc;
                 c.base = e->ws;
             }
@@ -472,8 +479,8 @@ extern "C" int gzb_uncompress_sections (gzb_engine *e, gzb_section *secs, uint32
             size_t io = 0, oo = 0, ao = 0;
             for (uint32_t i = 0; i < n; i++) {
                 DecSection &S = S2[i];
-                if (devptr) { S.in = (const uint8_t *)secs[i].in; S.out = (uint8_t *)secs[i].out; }
-                else { S.in = d_in + io; io += (S.in_len + 15) & ~15ull; S.out = d_out + oo; oo += (S.n + 15) & ~15ull; }
+                if (in_dev (i)) S.in = (const uint8_t *)secs[i].in; else { S.in = d_in + io; io += (S.in_len + 15) & ~15ull; }
+                if (out_dev (i)) S.out = (uint8_t *)secs[i].out; else { S.out = d_out + oo; oo += (S.n + 15) & ~15ull; }
                 S.planes = d_planes + ao; S.tmp = d_tmp + ao; ao += (S.n + 15) & ~15ull;
             }
         }
@@ -487,16 +494,16 @@ extern "C" int gzb_uncompress_sections (gzb_engine *e, gzb_section *secs, uint32
         P.rans_gpw = pick_rans_gpw (P.n_rans); P.arith_lpw = pick_arith_lpw (P.n_arith);
         P.parts = (n <= 64) ? 32 : (n <= 1024 ? 8 : 2);
         P.arena = Arena { d_arena, (unsigned long long)arena_est, d_cursor, d_overflow };
-        P.ev_chain0 = e->ev0; P.ev_chain1 = e->ev1;
+        P.ev_chain0 = e->ev0; P.ev_chain1 = e->ev1; P.ev_chain2 = e->ev2;
 
         cudaStream_t st = e->stream;
         memcpy (e->pin, meta.data (), meta_bytes);
         CK (cudaMemcpyAsync (e->ws + meta_off, e->pin, meta_bytes, cudaMemcpyHostToDevice, st));
-        if (!devptr) {
+        {
             int rc = stage_inputs (e, e->pin + ((meta_bytes + 255) & ~(size_t)255), n,
                                    [&] (uint32_t i) { return (uint8_t *)S2[i].in; },
                                    [&] (uint32_t i) { return (const uint8_t *)secs[i].in; },
-                                   [&] (uint32_t i) { return S2[i].in_len; });
+                                   [&] (uint32_t i) { return in_dev (i) ? 0u : S2[i].in_len; });
             if (rc) return rc;
         }
         CK (cudaMemsetAsync (d_cursor, 0, 512, st));
@@ -510,11 +517,10 @@ extern "C" int gzb_uncompress_sections (gzb_engine *e, gzb_section *secs, uint32
         CK (cudaMemcpyAsync (res.data (), P.results, n * sizeof (SectionResult), cudaMemcpyDeviceToHost, st));
         CK (cudaMemcpyAsync (&h_over, d_overflow, sizeof (int), cudaMemcpyDeviceToHost, st));
         CK (cudaMemcpyAsync (&h_cursor, d_cursor, sizeof h_cursor, cudaMemcpyDeviceToHost, st));
-        if (!devptr)
-            for (uint32_t i = 0; i < n; i++) CK (cudaMemcpyAsync (secs[i].out, S2[i].out, S2[i].n, cudaMemcpyDeviceToHost, st));
+        for (uint32_t i = 0; i < n; i++) if (!out_dev (i)) CK (cudaMemcpyAsync (secs[i].out, S2[i].out, S2[i].n, cudaMemcpyDeviceToHost, st));
         CK (cudaStreamSynchronize (st));
         if (h_over) { arena_est = (size_t)h_cursor + (h_cursor >> 2) + ((size_t)1 << 20); e->arena_hint_dec = arena_est; continue; }
-        float ms = 0; cudaEventElapsedTime (&ms, e->ev0, e->ev1); e->last_chain_ms = ms;
+        float ms = 0; cudaEventElapsedTime (&ms, e->ev0, e->ev1); e->last_rans_ms = ms; cudaEventElapsedTime (&ms, e->ev1, e->ev2); e->last_arith_ms = ms; e->last_chain_ms = e->last_rans_ms + e->last_arith_ms;
         int rc = GZB_OK;
         for (uint32_t i = 0; i < n; i++) {
             secs[i].status = res[i].status; secs[i].out_len = res[i].status ? 0 : res[i].out_len;

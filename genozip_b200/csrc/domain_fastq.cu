@@ -552,7 +552,7 @@ struct DqLayout {
     std::vector<uint8_t *> d_linedom, d_linediv;
 };
 
-int dq_stage (gzb_engine *e, gzb_domq_vb *vbs, uint32_t n_vbs, bool devptr, DqLayout &L)
+int dq_stage (gzb_engine *e, gzb_domq_vb *vbs, uint32_t n_vbs, bool devptr, bool outdev, DqLayout &L)
 {
     std::vector<uint32_t> nl (n_vbs), bvb, bfirst;
     for (uint32_t v = 0; v < n_vbs; v++) nl[v] = vbs[v].n_lines;
@@ -578,10 +578,10 @@ int dq_stage (gzb_engine *e, gzb_domq_vb *vbs, uint32_t n_vbs, bool devptr, DqLa
             D.nd_off = c.take<uint32_t> (S.n_lines + 1); D.dv_off = c.take<uint32_t> (S.n_lines + 1); D.mx_idx = c.take<uint32_t> (S.n_lines + 1);
             D.E      = c.take<uint8_t> (tot + 16);
             D.lens   = c.take<uint32_t> (8);
-            D.qual   = devptr ? (uint8_t *)S.qual : c.take<uint8_t> (2 * tot + 16);
-            D.runs   = devptr ? (uint8_t *)S.runs : c.take<uint8_t> (tot + 16);
-            D.mplx   = devptr ? (uint8_t *)S.mplx : c.take<uint8_t> (S.n_lines + 16);
-            D.divr   = devptr ? (uint8_t *)S.divr : c.take<uint8_t> (tot + 16);
+            D.qual   = (devptr || outdev) ? (uint8_t *)S.qual : c.take<uint8_t> (2 * tot + 16);
+            D.runs   = (devptr || outdev) ? (uint8_t *)S.runs : c.take<uint8_t> (tot + 16);
+            D.mplx   = (devptr || outdev) ? (uint8_t *)S.mplx : c.take<uint8_t> (S.n_lines + 16);
+            D.divr   = (devptr || outdev) ? (uint8_t *)S.divr : c.take<uint8_t> (tot + 16);
         }
         if (pass == 0) {
             if (c.off > e->dq_cap) {
@@ -608,12 +608,12 @@ extern "C" int gzb_domq_prepare (gzb_engine *e, gzb_domq_vb *vbs, uint32_t n_vbs
     if (!e || !vbs) return GZB_E_BADARG;
     if (!n_vbs) return GZB_OK;
     cudaSetDevice (e->device);
-    const bool devptr = flags & GZB_DEVICE_PTRS;
+    const bool devptr = flags & GZB_DEVICE_PTRS, outdev = flags & GZB_OUT_DEVICE;
     cudaStream_t st = e->stream;
     DqLayout *L = new DqLayout ();
     delete reinterpret_cast<DqLayout *>(e->dq_session); e->dq_session = L;
     e->dq_free = [] (void *p) { delete reinterpret_cast<DqLayout *>(p); };
-    int rc = dq_stage (e, vbs, n_vbs, devptr, *L);
+    int rc = dq_stage (e, vbs, n_vbs, devptr, outdev, *L);
     if (rc) return rc;
     for (uint32_t v = 0; v < n_vbs; v++) {
         DqVb &D = L->h[v];
@@ -684,7 +684,7 @@ extern "C" int gzb_domq_split (gzb_engine *e, gzb_domq_vb *vbs, uint32_t n_vbs, 
     if (!e || !vbs) return GZB_E_BADARG;
     if (!n_vbs) return GZB_OK;
     cudaSetDevice (e->device);
-    const bool devptr = flags & GZB_DEVICE_PTRS;
+    const bool devptr = flags & GZB_DEVICE_PTRS, outdev = flags & GZB_OUT_DEVICE;
     DqLayout *L = reinterpret_cast<DqLayout *>(e->dq_session);
     if (!L || e->dq_n_vbs != n_vbs || e->dq_devptr != devptr) { e->err = "gzb_domq_split must follow gzb_domq_prepare on the same batch"; return GZB_E_BADARG; }
     cudaStream_t st = e->stream;
@@ -695,7 +695,7 @@ extern "C" int gzb_domq_split (gzb_engine *e, gzb_domq_vb *vbs, uint32_t n_vbs, 
     for (uint32_t v = 0; v < n_vbs; v++) {
         gzb_domq_vb &S = vbs[v]; const uint32_t *l = lens.data () + (size_t)v * 8;
         S.qual_len = l[0]; S.runs_len = l[1]; S.mplx_len = l[2]; S.divr_len = l[3];
-        if (!devptr) {
+        if (!devptr && !outdev) {
             if (S.qual_len > S.qual_cap || S.runs_len > S.runs_cap || S.mplx_len > S.mplx_cap || S.divr_len > S.divr_cap) { e->err = "DOMQ output capacity too small"; return GZB_E_BADARG; }
             if (S.qual_len) CK (cudaMemcpyAsync (S.qual, L->h[v].qual, S.qual_len, cudaMemcpyDeviceToHost, st));
             if (S.runs_len) CK (cudaMemcpyAsync (S.runs, L->h[v].runs, S.runs_len, cudaMemcpyDeviceToHost, st));
@@ -713,7 +713,7 @@ extern "C" int gzb_domq_reconstruct (gzb_engine *e, gzb_domq_piz_vb *vbs, uint32
     if (!e || !vbs) return GZB_E_BADARG;
     if (!n_vbs) return GZB_OK;
     cudaSetDevice (e->device);
-    const bool devptr = flags & GZB_DEVICE_PTRS;
+    const bool devptr = flags & GZB_DEVICE_PTRS, indev = devptr || (flags & GZB_IN_DEVICE);
     cudaStream_t st = e->stream;
     std::vector<uint32_t> nl (n_vbs), bvb, bfirst;
     std::vector<uint64_t> total (n_vbs, 0);
@@ -734,10 +734,10 @@ extern "C" int gzb_domq_reconstruct (gzb_engine *e, gzb_domq_piz_vb *vbs, uint32
             D.qual_len = S.qual_len; D.runs_len = S.runs_len; D.mplx_len = S.mplx_len; D.divr_len = S.divr_len; D.n_lines = S.n_lines;
             D.no_dom = S.num_norm_qs; D.denorm_len = S.denorm_len;
             memcpy (D.denorm, S.denorm, S.denorm_len);
-            D.qual = devptr ? (const uint8_t *)S.qual : c.take<uint8_t> (S.qual_len + 16);
-            D.runs = devptr ? (const uint8_t *)S.runs : c.take<uint8_t> (S.runs_len + 16);
-            D.mplx = devptr ? (const uint8_t *)S.mplx : c.take<uint8_t> (S.mplx_len + 16);
-            D.divr = devptr ? (const uint8_t *)S.divr : c.take<uint8_t> (S.divr_len + 16);
+            D.qual = indev ? (const uint8_t *)S.qual : c.take<uint8_t> (S.qual_len + 16);
+            D.runs = indev ? (const uint8_t *)S.runs : c.take<uint8_t> (S.runs_len + 16);
+            D.mplx = indev ? (const uint8_t *)S.mplx : c.take<uint8_t> (S.mplx_len + 16);
+            D.divr = indev ? (const uint8_t *)S.divr : c.take<uint8_t> (S.divr_len + 16);
             D.line_len = devptr ? S.line_len : c.take<uint32_t> (S.n_lines + 1);
             D.out  = devptr ? (uint8_t *)S.out : c.take<uint8_t> (total[v] + 16);
             D.E    = c.take<uint8_t> (total[v] + 16);
@@ -750,13 +750,13 @@ extern "C" int gzb_domq_reconstruct (gzb_engine *e, gzb_domq_piz_vb *vbs, uint32
     }
     for (uint32_t v = 0; v < n_vbs; v++) {
         DqPiz &D = h[v]; const gzb_domq_piz_vb &S = vbs[v];
-        if (!devptr) {
+        if (!indev) {
             if (S.qual_len) CK (cudaMemcpyAsync ((void *)D.qual, S.qual, S.qual_len, cudaMemcpyHostToDevice, st));
             if (S.runs_len) CK (cudaMemcpyAsync ((void *)D.runs, S.runs, S.runs_len, cudaMemcpyHostToDevice, st));
             if (S.mplx_len) CK (cudaMemcpyAsync ((void *)D.mplx, S.mplx, S.mplx_len, cudaMemcpyHostToDevice, st));
             if (S.divr_len) CK (cudaMemcpyAsync ((void *)D.divr, S.divr, S.divr_len, cudaMemcpyHostToDevice, st));
-            if (S.n_lines)  CK (cudaMemcpyAsync ((void *)D.line_len, S.line_len, (size_t)S.n_lines * 4, cudaMemcpyHostToDevice, st));
         }
+        if (!devptr && S.n_lines) CK (cudaMemcpyAsync ((void *)D.line_len, S.line_len, (size_t)S.n_lines * 4, cudaMemcpyHostToDevice, st));
         CK (cudaMemsetAsync (D.E, 0, total[v] + 16, st));
         CK (cudaMemsetAsync (D.info, 0, 32, st));
     }

@@ -8,12 +8,12 @@ struct gzb_engine {
     int          device = 0;
     int          sm_count = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t  ev0 = nullptr, ev1 = nullptr;      // bracket the chain kernels of the last batch
+    cudaEvent_t  ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;   // ev0..ev1: rANS chain kernel, ev1..ev2: arithmetic chain kernel
     uint8_t     *ws = nullptr;   size_t ws_cap = 0; // device workspace (grow-only)
     uint8_t     *pin = nullptr;  size_t pin_cap = 0;// pinned host staging (grow-only)
     std::string  err;
     uint64_t     launches = 0;
-    float        last_chain_ms = 0;
+    float        last_chain_ms = 0, last_rans_ms = 0, last_arith_ms = 0;
     size_t       arena_hint = 0, arena_hint_dec = 0;
     // DOMQ session: device state kept between gzb_domq_prepare and gzb_domq_split of the same batch
     uint8_t     *dq_buf = nullptr; size_t dq_cap = 0;

@@ -524,12 +524,13 @@ void dec_run (DecPlanDev &P, cudaStream_t st)
         int gpw = P.rans_gpw;
         LAUNCH (k_rans_decode, (P.n_rans + gpw - 1) / gpw, 32, P.leaves, P.rans_list, P.n_rans, gpw);
     }
+    cudaEventRecord (P.ev_chain2, st);
     if (P.n_arith) {
         int lpw = P.arith_lpw;
         uint32_t warps = (P.n_arith + lpw - 1) / lpw;
         LAUNCH (k_arith_decode, (warps + 3) / 4, 128, P.leaves, P.arith_list, P.n_arith, lpw);
     }
-    cudaEventRecord (P.ev_chain1, st);
+    cudaEventRecord (P.ev_chain2, st);
     dim3 g (nslots, P.parts), gs (ns, P.parts);
     LAUNCH (k_dec_cat, g, 256, P.leaves, nslots);
     LAUNCH (k_dec_unpack, g, 256, P.leaves, P.results, nslots);

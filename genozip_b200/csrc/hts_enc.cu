@@ -833,12 +833,13 @@ void enc_run (EncPlanDev &P, cudaStream_t st)
         k_rans_encode<<<(P.n_rans + gpw - 1) / gpw, 32, gpw * (256 * sizeof (EncSym) + 256), st>>>(P.leaves, P.dyn, P.rans_list, P.n_rans, gpw);
         P.launches++;
     }
+    cudaEventRecord (P.ev_chain2, st);
     if (P.n_arith) {
         int lpw = P.arith_lpw;
         uint32_t warps = (P.n_arith + lpw - 1) / lpw;
         LAUNCH (k_arith_encode, (warps + 3) / 4, 128, P.leaves, P.dyn, P.arith_list, P.n_arith, lpw);
     }
-    cudaEventRecord (P.ev_chain1, st);
+    cudaEventRecord (P.ev_chain2, st);
     LAUNCH (k_leaf_final, (nl + 127) / 128, 128, P.leaves, P.dyn, nl);
     LAUNCH (k_section_final, (ns + 127) / 128, 128, P.sections, P.leaves, P.dyn, P.results, P.segs, P.stripe_hdr, ns);
     dim3 g (ns * SEGS_PER_SECTION, P.copy_parts);

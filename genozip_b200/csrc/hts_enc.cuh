@@ -18,7 +18,7 @@ struct EncPlanDev {              // device pointers of one encode batch
     Arena          arena;
     int            rans_gpw, arith_lpw, copy_parts;
     bool           any_pack, any_o1;
-    cudaEvent_t    ev_chain0, ev_chain1;
+    cudaEvent_t    ev_chain0, ev_chain1, ev_chain2;
     uint64_t       launches;
 };
 
@@ -30,7 +30,7 @@ struct DecPlanDev {
     SectionResult *results;
     Arena          arena;
     int            rans_gpw, arith_lpw, parts;
-    cudaEvent_t    ev_chain0, ev_chain1;
+    cudaEvent_t    ev_chain0, ev_chain1, ev_chain2;
     uint64_t       launches;
 };
 

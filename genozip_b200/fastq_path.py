@@ -1,0 +1,309 @@
+"""Host-side driver of the per-VBlock codec path for a batch of FASTQ VBlocks — the Python mirror of what genozip's
+compute thread does between segmentation and z_data assembly for the contexts on this path
+(zip_compress_all_contexts_local → comp_compress → codec_args[].compress, src/zip.c:291, src/compressor.c:18-182;
+and piz_uncompress_all_ctxs → comp_uncompress, src/piz.c:247, src/compressor.c:211-255):
+
+  ZIP   SEQ  (NONREF.local)  --codec_acgt_compress-->  2-bit words (sub-codec LZMA stays on the host: out of scope)
+                                                       + NONREF_X.local --XCGT sub-codec--> section
+        QUAL (QUAL.local)    --codec_domq_compress-->  QUAL.local / DOMQRUNS / QUALMPLX / DIVRQUAL --sub-codecs--> sections
+        read-name contexts   --simple codecs-->        sections
+  PIZ   the inverse.
+
+Everything numeric happens in libgzb200.so (CUDA); torch only owns the device / pinned host buffers.  Independent
+VBlocks are sharded round-robin over the GPUs of the box by vblock_i (gzb_vb_device), one process per GPU.
+"""
+import ctypes as C
+import numpy as np
+import torch
+
+from .lib import (load, Engine, Section, DomqVb, DomqPizVb, CODEC, est_size, GzbError,
+                  GZB_DEVICE_PTRS, GZB_OUT_DEVICE, GZB_IN_DEVICE, GZB_SEC_IN_DEVICE, GZB_SEC_OUT_DEVICE)
+
+NAME_LEN = 45            # "@A00123:45:HXXXXXXXX:1:1101:12345:12345 1:N:0:ACGT" without the newline ~ 45-50
+SIMPLE = ["RANB", "RANW", "RANb", "RANw", "ARTB", "ARTW", "ARTb", "ARTw"]   # ascending Codec enum order (ties -> first)
+STREAMS = ["QUAL", "DOMQRUNS", "QUALMPLX", "DIVRQUAL", "NONREF_X", "Q_TILE", "Q_X", "Q_Y", "Q_MISC"]
+
+
+def txt_bytes_per_vb(n_reads, read_len):
+    """FASTQ text a VBlock of n_reads represents: name line, SEQ, '+', QUAL and 4 newlines per record"""
+    return n_reads * (NAME_LEN + 1 + read_len + 1 + 1 + 1 + read_len + 1)
+
+
+def synth_vblocks(V, n_reads, read_len, seed, device):
+    """Synthetic Illumina-like VBlocks generated on the device: returns dict of uint8 device tensors
+    [V, ...]: seq, qual (fixed-length lines), and the read-name context streams."""
+    g = torch.Generator(device=device); g.manual_seed(seed)
+    n = n_reads * read_len
+    acgt = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
+    seq = acgt[torch.randint(0, 4, (V, n), generator=g, device=device)]
+    seq[torch.rand((V, n), generator=g, device=device) < 0.001] = ord("N")
+    # QUAL: binned Illumina {F:88%, ':':7%, ',':4%, '#':1%} with Markov run structure, P(stay) = 0.97
+    syms = torch.tensor(list(b"F:,#"), dtype=torch.uint8, device=device)
+    pick = torch.multinomial(torch.tensor([.88, .07, .04, .01], device=device), V * n, replacement=True, generator=g).view(V, n)
+    change = torch.rand((V, n), generator=g, device=device) > 0.97
+    change[:, 0] = True
+    idx = torch.where(change, torch.arange(n, device=device).expand(V, n), torch.zeros((), dtype=torch.long, device=device))
+    last = torch.cummax(idx, dim=1).values
+    qual = syms[torch.gather(pick, 1, last)]
+    # ~3% diverse lines
+    q2 = qual.view(V, n_reads, read_len)
+    div = torch.rand((V, n_reads), generator=g, device=device) < 0.03
+    noise = syms[torch.multinomial(torch.tensor([.4, .3, .2, .1], device=device), V * n_reads * read_len, replacement=True, generator=g).view(V, n_reads, read_len)]
+    q2[div] = noise[div]
+    # read-name contexts: tile (b250, long runs), x / y (uint32 big-endian locals), misc b250
+    tile = (torch.arange(n_reads, device=device) // 977 % 96).to(torch.uint8).expand(V, n_reads).contiguous()
+    xs = (torch.cumsum(torch.randint(0, 60, (V, n_reads), generator=g, device=device), 1) % 30000 + 1000).to(torch.int32)
+    ys = torch.randint(1000, 30000, (V, n_reads), generator=g, device=device, dtype=torch.int32)
+
+    def be32(t):
+        b = t.contiguous().view(torch.uint8).view(V, n_reads, 4)
+        return b.flip(2).contiguous().view(V, n_reads * 4)
+    misc = torch.multinomial(torch.tensor([.9, .05, .03, .02], device=device), V * n_reads, replacement=True, generator=g).view(V, n_reads).to(torch.uint8)
+    return dict(seq=seq.contiguous(), qual=qual.contiguous(), Q_TILE=tile, Q_X=be32(xs), Q_Y=be32(ys), Q_MISC=misc.contiguous())
+
+
+class FastqCodecPath:
+    """zip / piz of a batch of V FASTQ VBlocks through libgzb200 on one GPU."""
+
+    def __init__(self, eng: Engine, V, n_reads, read_len):
+        self.eng, self.L = eng, eng.L
+        self.V, self.n_reads, self.read_len = V, n_reads, read_len
+        self.n = n_reads * read_len
+        dev = torch.device("cuda", eng.device)
+        self.dev = dev
+        self.stream = torch.cuda.ExternalStream(self.L.gzb_engine_stream(eng.h), device=dev)
+        n, V = self.n, V
+        self.packed_len = int(self.L.gzb_acgt_packed_len(n))
+        u8 = dict(dtype=torch.uint8, device=dev)
+        self.line_off_h = (torch.arange(n_reads, dtype=torch.int64) * read_len).pin_memory()
+        self.line_len_h = torch.full((n_reads,), read_len, dtype=torch.int32).pin_memory()
+        self.line_off_d, self.line_len_d = self.line_off_h.to(dev), self.line_len_h.to(dev)
+        # device intermediates / outputs (zip)
+        self.packed_d = torch.empty((V, self.packed_len + 32), **u8)
+        self.x_d = torch.empty((V, n), **u8)
+        self.linedom_d = torch.empty((V, n_reads), **u8)
+        self.linediv_d = torch.empty((V, n_reads), **u8)
+        self.dq = {k: torch.empty((V, c), **u8) for k, c in (("QUAL", 2 * n + 16), ("DOMQRUNS", n + 16), ("QUALMPLX", n_reads + 16), ("DIVRQUAL", n + 16))}
+        self.caps = {"QUAL": 2 * n + 16, "DOMQRUNS": n + 16, "QUALMPLX": n_reads + 16, "DIVRQUAL": n + 16, "NONREF_X": n,
+                     "Q_TILE": n_reads, "Q_X": 4 * n_reads, "Q_Y": 4 * n_reads, "Q_MISC": n_reads}
+        self.codec = {s: "RANB" for s in STREAMS}
+        self.comp_d = {}          # compressed sections on device: stream -> [V, est]
+        self.dvb = (DomqVb * V)()
+        self.pvb = (DomqPizVb * V)()
+        self.meta = None          # per-VB dicts from the last zip (lengths, tables)
+        self.h = {}               # pinned host buffers for the host-buffer (e2e) path
+
+    # ------------------------------------------------------------------ codec assignment (host policy, run on the GPU)
+    def assign_codecs(self, data):
+        """codec_assign_best_codec's size criterion (src/codec.c:234-389, sorter :128-173) restricted to the eight
+        in-scope simple codecs: compress the first <=99,999 bytes (CODEC_ASSIGN_SAMPLE_SIZE, src/codec.h:154) of VB 1's
+        stream with each and keep the smallest, ties to the lower Codec value.  The reference also weighs clock() time
+        (timing-dependent, H5) — not reproduced.  Samples are compressed on the GPU (same bytes as the reference)."""
+        self.zip_device(data, only_vb0_streams=True)
+        m = self.meta[0]
+        samples = {}
+        for s in STREAMS:
+            ln = m["len"][s]
+            if ln == 0:
+                continue
+            src = self._stream_dev_tensor(s, 0, data)[:min(ln, 99999)]
+            samples[s] = src.cpu().numpy().copy()
+        items = [(c, samples[s]) for s in samples for c in SIMPLE]
+        outs = self.eng.compress(items)
+        k = 0
+        for s in samples:
+            sizes = [outs[k + j].size for j in range(len(SIMPLE))]
+            k += len(SIMPLE)
+            self.codec[s] = SIMPLE[int(np.argmin(sizes))] if samples[s].size >= 50 else "RANB"   # <50 B would be CODEC_NONE (compressor.c:56-58)
+        return dict(self.codec)
+
+    def _stream_dev_tensor(self, s, v, data):
+        if s in self.dq:
+            return self.dq[s][v]
+        if s == "NONREF_X":
+            return self.x_d[v]
+        return data[s][v]
+
+    def _alloc_comp(self):
+        for s in STREAMS:
+            cap = max(est_size(c, self.caps[s]) for c in SIMPLE)
+            if s not in self.comp_d or self.comp_d[s].shape[1] < cap:
+                self.comp_d[s] = torch.empty((self.V, cap), dtype=torch.uint8, device=self.dev)
+
+    # ------------------------------------------------------------------ ZIP, inputs resident in HBM
+    def zip_device(self, data, only_vb0_streams=False):
+        L, h, V, n = self.L, self.eng.h, self.V, self.n
+        allz = C.c_int(0)
+        meta = [dict(len={}, comp_len={}) for _ in range(V)]
+        for v in range(V):
+            rc = L.gzb_acgt_pack(h, data["seq"][v].data_ptr(), n, self.packed_d[v].data_ptr(), self.x_d[v].data_ptr(), C.byref(allz), GZB_DEVICE_PTRS)
+            if rc:
+                raise GzbError(f"gzb_acgt_pack: {self.eng._err()}")
+            meta[v]["acgt_no_x"] = bool(allz.value)
+            meta[v]["len"]["NONREF_X"] = 0 if allz.value else n
+        for v in range(V):
+            a = self.dvb[v]
+            a.txt = data["qual"][v].data_ptr(); a.txt_len = n
+            a.line_off = self.line_off_d.data_ptr(); a.line_len = self.line_len_d.data_ptr(); a.n_lines = self.n_reads
+            a.line_dom = self.linedom_d[v].data_ptr(); a.line_diverse = self.linediv_d[v].data_ptr()
+            for fld, s in (("qual", "QUAL"), ("runs", "DOMQRUNS"), ("mplx", "QUALMPLX"), ("divr", "DIVRQUAL")):
+                setattr(a, fld, self.dq[s][v].data_ptr()); setattr(a, fld + "_cap", self.caps[s])
+        if L.gzb_domq_prepare(h, self.dvb, V, GZB_DEVICE_PTRS) or L.gzb_domq_split(h, self.dvb, V, GZB_DEVICE_PTRS):
+            raise GzbError(f"gzb_domq: {self.eng._err()}")
+        for v in range(V):
+            a, m = self.dvb[v], meta[v]
+            m["len"].update(QUAL=a.qual_len, DOMQRUNS=a.runs_len, QUALMPLX=a.mplx_len, DIVRQUAL=a.divr_len,
+                            Q_TILE=self.n_reads, Q_X=4 * self.n_reads, Q_Y=4 * self.n_reads, Q_MISC=self.n_reads)
+            m["num_norm_qs"] = a.num_norm_qs
+            m["denorm"] = bytes(a.denorm)[:a.num_norm_qs * a.num_doms]
+        self.meta = meta
+        if only_vb0_streams:
+            return meta
+        self._alloc_comp()
+        secs, idx = self._sections(meta, lambda s, v: self._stream_dev_tensor(s, v, data).data_ptr(), lambda s, v: self.comp_d[s][v].data_ptr(), 0)
+        self.eng.compress_raw(secs, len(idx), GZB_DEVICE_PTRS)
+        self._collect(secs, idx, meta)
+        return meta
+
+    def _sections(self, meta, in_ptr, out_ptr, sflags_for):
+        idx = [(v, s) for v in range(self.V) for s in STREAMS if meta[v]["len"][s] > 0]
+        secs = (Section * len(idx))()
+        for i, (v, s) in enumerate(idx):
+            secs[i].codec = CODEC[self.codec[s]]
+            secs[i].in_ = in_ptr(s, v); secs[i].in_len = meta[v]["len"][s]
+            secs[i].out = out_ptr(s, v); secs[i].out_cap = est_size(self.codec[s], meta[v]["len"][s])
+            secs[i].sflags = sflags_for(s) if callable(sflags_for) else sflags_for
+        return secs, idx
+
+    @staticmethod
+    def _collect(secs, idx, meta):
+        for i, (v, s) in enumerate(idx):
+            if secs[i].status != 0:
+                raise GzbError(f"section {s} of VB {v}: status {secs[i].status}")
+            meta[v]["comp_len"][s] = secs[i].out_len
+
+    # ------------------------------------------------------------------ PIZ, inputs resident in HBM
+    def alloc_piz(self):
+        u8 = dict(dtype=torch.uint8, device=self.dev)
+        self.dec_d = {s: torch.empty((self.V, self.caps[s] + 16), **u8) for s in STREAMS}
+        self.seq_out_d = torch.empty((self.V, self.n), **u8)
+        self.qual_out_d = torch.empty((self.V, self.n), **u8)
+
+    def piz_device(self, meta):
+        L, h, V, n = self.L, self.eng.h, self.V, self.n
+        idx = [(v, s) for v in range(V) for s in STREAMS if meta[v]["len"][s] > 0]
+        secs = (Section * len(idx))()
+        for i, (v, s) in enumerate(idx):
+            secs[i].codec = CODEC[self.codec[s]]
+            secs[i].in_ = self.comp_d[s][v].data_ptr(); secs[i].in_len = meta[v]["comp_len"][s]
+            secs[i].out = self.dec_d[s][v].data_ptr(); secs[i].out_cap = meta[v]["len"][s]
+        self.eng.uncompress_raw(secs, len(idx), GZB_DEVICE_PTRS)
+        keep = []
+        for v in range(V):
+            a, m = self.pvb[v], meta[v]
+            a.qual = self.dec_d["QUAL"][v].data_ptr(); a.qual_len = m["len"]["QUAL"]
+            a.runs = self.dec_d["DOMQRUNS"][v].data_ptr(); a.runs_len = m["len"]["DOMQRUNS"]
+            a.mplx = self.dec_d["QUALMPLX"][v].data_ptr(); a.mplx_len = m["len"]["QUALMPLX"]
+            a.divr = self.dec_d["DIVRQUAL"][v].data_ptr(); a.divr_len = m["len"]["DIVRQUAL"]
+            dn = np.frombuffer(m["denorm"], np.uint8); keep.append(dn)
+            a.denorm = dn.ctypes.data; a.denorm_len = dn.size; a.num_norm_qs = m["num_norm_qs"]
+            a.line_len = self.line_len_d.data_ptr(); a.n_lines = self.n_reads
+            a.out = self.qual_out_d[v].data_ptr(); a.out_cap = n
+        if L.gzb_domq_reconstruct(h, self.pvb, V, GZB_DEVICE_PTRS):
+            raise GzbError(f"gzb_domq_reconstruct: {self.eng._err()}")
+        for v in range(V):
+            x = None if meta[v]["acgt_no_x"] else self.dec_d["NONREF_X"][v].data_ptr()
+            if L.gzb_acgt_unpack(h, self.packed_d[v].data_ptr(), x, n, self.seq_out_d[v].data_ptr(), GZB_DEVICE_PTRS):
+                raise GzbError(f"gzb_acgt_unpack: {self.eng._err()}")
+
+    # ------------------------------------------------------------------ HOST-buffer path (e2e): what the C host would call
+    def alloc_host(self, data):
+        """pinned host copies of the inputs and pinned host buffers for every output"""
+        pin = lambda t: t.cpu().pin_memory()
+        self.h = {k: pin(v) for k, v in data.items()}
+        V, n = self.V, self.n
+        hp = lambda *shape: torch.empty(shape, dtype=torch.uint8).pin_memory()
+        self.h["packed"] = hp(V, self.packed_len + 32)
+        self.h["x"] = hp(V, n)
+        self.h["linedom"] = hp(V, self.n_reads); self.h["linediv"] = hp(V, self.n_reads)
+        self.h["comp"] = {s: hp(V, self.comp_d[s].shape[1]) for s in STREAMS}
+        self.h["seq_out"] = hp(V, n); self.h["qual_out"] = hp(V, n)
+        self.h["dec"] = {s: hp(V, self.caps[s] + 16) for s in ("NONREF_X", "Q_TILE", "Q_X", "Q_Y", "Q_MISC")}
+
+    def zip_host(self):
+        """host buffers in, host buffers out; the DOMQ streams stay on the device between codec_domq_compress and
+        its sub-codec (GZB_OUT_DEVICE / GZB_SEC_IN_DEVICE) exactly as they stay inside one compute thread in the reference.
+        Returns (meta, h2d_bytes, d2h_bytes)."""
+        L, h, V, n, H = self.L, self.eng.h, self.V, self.n, self.h
+        allz = C.c_int(0)
+        meta = [dict(len={}, comp_len={}) for _ in range(V)]
+        h2d = d2h = 0
+        for v in range(V):
+            if L.gzb_acgt_pack(h, H["seq"][v].data_ptr(), n, H["packed"][v].data_ptr(), H["x"][v].data_ptr(), C.byref(allz), 0):
+                raise GzbError(f"gzb_acgt_pack: {self.eng._err()}")
+            meta[v]["acgt_no_x"] = bool(allz.value)
+            meta[v]["len"]["NONREF_X"] = 0 if allz.value else n
+            h2d += n; d2h += self.packed_len + (0 if allz.value else n)
+        for v in range(V):
+            a = self.dvb[v]
+            a.txt = H["qual"][v].data_ptr(); a.txt_len = n
+            a.line_off = self.line_off_h.data_ptr(); a.line_len = self.line_len_h.data_ptr(); a.n_lines = self.n_reads
+            a.line_dom = H["linedom"][v].data_ptr(); a.line_diverse = H["linediv"][v].data_ptr()
+            for fld, s in (("qual", "QUAL"), ("runs", "DOMQRUNS"), ("mplx", "QUALMPLX"), ("divr", "DIVRQUAL")):
+                setattr(a, fld, self.dq[s][v].data_ptr()); setattr(a, fld + "_cap", self.caps[s])
+            h2d += n + 12 * self.n_reads; d2h += 2 * self.n_reads
+        if L.gzb_domq_prepare(h, self.dvb, V, GZB_OUT_DEVICE) or L.gzb_domq_split(h, self.dvb, V, GZB_OUT_DEVICE):
+            raise GzbError(f"gzb_domq: {self.eng._err()}")
+        for v in range(V):
+            a, m = self.dvb[v], meta[v]
+            m["len"].update(QUAL=a.qual_len, DOMQRUNS=a.runs_len, QUALMPLX=a.mplx_len, DIVRQUAL=a.divr_len,
+                            Q_TILE=self.n_reads, Q_X=4 * self.n_reads, Q_Y=4 * self.n_reads, Q_MISC=self.n_reads)
+            m["num_norm_qs"] = a.num_norm_qs
+            m["denorm"] = bytes(a.denorm)[:a.num_norm_qs * a.num_doms]
+
+        def in_ptr(s, v):
+            if s in self.dq: return self.dq[s][v].data_ptr()
+            if s == "NONREF_X": return H["x"][v].data_ptr()
+            return H[s][v].data_ptr()
+        secs, idx = self._sections(meta, in_ptr, lambda s, v: H["comp"][s][v].data_ptr(),
+                                   lambda s: GZB_SEC_IN_DEVICE if s in self.dq else 0)
+        self.eng.compress_raw(secs, len(idx), 0)
+        self._collect(secs, idx, meta)
+        for (v, s) in idx:
+            if s not in self.dq: h2d += meta[v]["len"][s]
+            d2h += meta[v]["comp_len"][s]
+        return meta, h2d, d2h
+
+    def piz_host(self, meta):
+        L, h, V, n, H = self.L, self.eng.h, self.V, self.n, self.h
+        idx = [(v, s) for v in range(V) for s in STREAMS if meta[v]["len"][s] > 0]
+        secs = (Section * len(idx))()
+        h2d = d2h = 0
+        for i, (v, s) in enumerate(idx):
+            secs[i].codec = CODEC[self.codec[s]]
+            secs[i].in_ = H["comp"][s][v].data_ptr(); secs[i].in_len = meta[v]["comp_len"][s]
+            on_dev = s in self.dq
+            secs[i].out = (self.dec_d[s][v] if on_dev else H["dec"][s][v]).data_ptr(); secs[i].out_cap = meta[v]["len"][s]
+            secs[i].sflags = GZB_SEC_OUT_DEVICE if on_dev else 0
+            h2d += meta[v]["comp_len"][s]; d2h += 0 if on_dev else meta[v]["len"][s]
+        self.eng.uncompress_raw(secs, len(idx), 0)
+        keep = []
+        for v in range(V):
+            a, m = self.pvb[v], meta[v]
+            a.qual = self.dec_d["QUAL"][v].data_ptr(); a.qual_len = m["len"]["QUAL"]
+            a.runs = self.dec_d["DOMQRUNS"][v].data_ptr(); a.runs_len = m["len"]["DOMQRUNS"]
+            a.mplx = self.dec_d["QUALMPLX"][v].data_ptr(); a.mplx_len = m["len"]["QUALMPLX"]
+            a.divr = self.dec_d["DIVRQUAL"][v].data_ptr(); a.divr_len = m["len"]["DIVRQUAL"]
+            dn = np.frombuffer(m["denorm"], np.uint8); keep.append(dn)
+            a.denorm = dn.ctypes.data; a.denorm_len = dn.size; a.num_norm_qs = m["num_norm_qs"]
+            a.line_len = self.line_len_h.data_ptr(); a.n_lines = self.n_reads
+            a.out = H["qual_out"][v].data_ptr(); a.out_cap = n
+            h2d += 4 * self.n_reads; d2h += n
+        if L.gzb_domq_reconstruct(h, self.pvb, V, GZB_IN_DEVICE):
+            raise GzbError(f"gzb_domq_reconstruct: {self.eng._err()}")
+        for v in range(V):
+            x = None if meta[v]["acgt_no_x"] else H["dec"]["NONREF_X"][v].data_ptr()
+            if L.gzb_acgt_unpack(h, H["packed"][v].data_ptr(), x, n, H["seq_out"][v].data_ptr(), 0):
+                raise GzbError(f"gzb_acgt_unpack: {self.eng._err()}")
+            h2d += self.packed_len + (0 if x is None else n); d2h += n
+        return h2d, d2h

@@ -15,7 +15,8 @@ LIBPATH = os.path.join(HERE, "libgzb200.so")
 
 CODEC = {"NONE": 1, "RANB": 6, "RANW": 7, "RANb": 8, "RANw": 9, "ACGT": 10, "XCGT": 11, "DOMQ": 13, "PBWT": 15,
          "ARTB": 16, "ARTW": 17, "ARTb": 18, "ARTw": 19, "LONGR": 26}
-GZB_DEVICE_PTRS = 1
+GZB_DEVICE_PTRS, GZB_OUT_DEVICE, GZB_IN_DEVICE = 1, 2, 4
+GZB_SEC_IN_DEVICE, GZB_SEC_OUT_DEVICE = 1, 2
 GZB_OK, GZB_SOFT_FAIL = 0, 1
 
 
@@ -25,7 +26,7 @@ class GzbError(RuntimeError):
 
 class Section(C.Structure):
     _fields_ = [("codec", C.c_int32), ("status", C.c_int32), ("in_", C.c_void_p), ("out", C.c_void_p),
-                ("in_len", C.c_uint32), ("out_cap", C.c_uint32), ("out_len", C.c_uint32), ("reserved", C.c_uint32)]
+                ("in_len", C.c_uint32), ("out_cap", C.c_uint32), ("out_len", C.c_uint32), ("sflags", C.c_uint32)]
 
 
 class DomqVb(C.Structure):          # gzb_domq_vb
@@ -72,6 +73,8 @@ def load():
     L.gzb_kernel_launches.argtypes = [C.c_void_p]
     L.gzb_last_chain_ms.restype = C.c_float
     L.gzb_last_chain_ms.argtypes = [C.c_void_p]
+    L.gzb_last_kernel_ms.restype = C.c_float
+    L.gzb_last_kernel_ms.argtypes = [C.c_void_p, C.c_int]
     L.gzb_est_size.restype = C.c_uint32
     L.gzb_est_size.argtypes = [C.c_int, C.c_uint64]
     for nm in ("gzb_compress_sections", "gzb_uncompress_sections"):

@@ -49,7 +49,12 @@ enum {
 typedef struct gzb_engine gzb_engine;   /* one per (host thread, GPU): a CUDA stream + reusable device arena */
 
 /* flags for the batch calls */
-#define GZB_DEVICE_PTRS  1u   /* in/out pointers are device pointers on the engine's GPU (inputs resident in HBM) */
+#define GZB_DEVICE_PTRS  1u   /* every pointer is a device pointer on the engine's GPU (inputs resident in HBM) */
+#define GZB_OUT_DEVICE   2u   /* bulk OUTPUT streams are device pointers, everything else host (chaining codecs without a PCIe round trip) */
+#define GZB_IN_DEVICE    4u   /* bulk INPUT streams are device pointers, everything else host */
+/* gzb_section.sflags: per-section override when the batch flags are 0 */
+#define GZB_SEC_IN_DEVICE  1u
+#define GZB_SEC_OUT_DEVICE 2u
 
 /* ---------------------------------------------------------------- lifecycle (SURVEY §8b "lifecycle") */
 int   gzb_device_count (void);                                    /* number of visible CUDA devices, 0 if none */
@@ -62,6 +67,8 @@ int   gzb_vb_device (uint32_t vblock_i, int n_devices);           /* (vblock_i-1
 uint64_t gzb_kernel_launches (gzb_engine *e);                     /* kernels launched by this engine so far */
 /* Device-time of the dominant chain kernels of the LAST batch call, ms (CUDA events on the engine's stream) */
 float gzb_last_chain_ms (gzb_engine *e);
+/* the same, split by coder: which = 0 rANS chain kernel, 1 arithmetic chain kernel */
+float gzb_last_kernel_ms (gzb_engine *e, int which);
 
 /* ---------------------------------------------------------------- simple codecs: rANS 4x16 and adaptive arithmetic
  * Replaces codec_{RANB,RANW,RANb,RANw,ARTB,ARTW,ARTb,ARTw}_compress (src/codec_htscodecs.c:77-94) →
@@ -76,7 +83,7 @@ typedef struct {
     uint32_t    out_cap;    /* compress: capacity of out (must be >= gzb_est_size(codec,in_len) or status=GZB_SOFT_FAIL);
                                uncompress: the expected uncompressed length */
     uint32_t    out_len;    /* out: bytes written */
-    uint32_t    reserved;
+    uint32_t    sflags;     /* GZB_SEC_IN_DEVICE | GZB_SEC_OUT_DEVICE */
 } gzb_section;
 
 uint32_t gzb_est_size (int codec, uint64_t uncompressed_len);     /* codec_*_est_size (src/codec_htscodecs.c:26-33): 1 KB + bound */
