@@ -193,7 +193,22 @@ int stage_inputs (gzb_engine *e, uint8_t *stage, uint32_t n, FD dev, FH host, FL
     return GZB_OK;
 }
 
-int pick_rans_gpw (uint32_t n)  { return n <= 4736 ? 1 : n <= 9472 ? 2 : n <= 18944 ? 4 : 8; }
+// Warp jobs over a length-sorted list: an item above BIG bytes is latency-critical and gets a warp of its own; smaller
+// items are packed up to 8 per warp (4 lanes each) so that issue slots are shared.  A job never mixes `cls` values.
+constexpr uint32_t BIG_LEAF = 32768;
+template <typename FL, typename FC> std::vector<uint2> make_jobs (uint32_t n, FL len, FC cls)
+{
+    std::vector<uint2> jobs;
+    uint32_t i = 0;
+    while (i < n) {
+        if (len (i) > BIG_LEAF) { jobs.push_back (make_uint2 (i, 1)); i++; continue; }
+        uint32_t c = 1;
+        while (c < 8 && i + c < n && cls (i + c) == cls (i) && len (i + c) <= BIG_LEAF) c++;
+        jobs.push_back (make_uint2 (i, c));
+        i += c;
+    }
+    return jobs;
+}
 int pick_arith_lpw (uint32_t n) { int l = 1; while (l < 32 && (uint64_t)n > 9472ull * l) l *= 2; return l; }
 
 } // namespace
@@ -268,8 +283,13 @@ extern "C" int gzb_compress_sections (gzb_engine *e, gzb_section *secs, uint32_t
     }
     const uint32_t nl = (uint32_t)hl.size ();
     auto by_len = [&] (uint32_t a, uint32_t b) { return hl[a].n > hl[b].n; };
-    std::stable_sort (rlist.begin (), rlist.end (), by_len);
+    // rANS: requested order 1 first (a warp job runs one order), longest first within each order
+    std::stable_sort (rlist.begin (), rlist.end (), [&] (uint32_t a, uint32_t b) {
+        int oa = hl[a].order_req & 1, ob = hl[b].order_req & 1;
+        return oa != ob ? oa > ob : hl[a].n > hl[b].n; });
     std::stable_sort (alist.begin (), alist.end (), by_len);
+    std::vector<uint2> rjobs = make_jobs ((uint32_t)rlist.size (), [&] (uint32_t i) { return hl[rlist[i]].n; },
+                                          [&] (uint32_t i) { return (uint32_t)(hl[rlist[i]].order_req & 1); });
 
     // arena estimate for alphabet-dependent tables; grown and replayed on overflow
     size_t arena_est = (size_t)4 << 20;
@@ -296,6 +316,7 @@ extern "C" int gzb_compress_sections (gzb_engine *e, gzb_section *secs, uint32_t
             P.tiles        = c.take<Tile> (tiles.size () + 1);
             P.stripe_tiles = c.take<Tile> (stiles.size () + 1);
             P.rans_list    = c.take<uint32_t> (rlist.size () + 1);
+            P.rans_jobs    = c.take<uint2> (rjobs.size () + 1);
             P.arith_list   = c.take<uint32_t> (alist.size () + 1);
             meta_bytes = c.off - meta_off;
             P.dyn          = c.take<EncLeafDyn> (nl ? nl : 1);
@@ -348,13 +369,14 @@ extern "C" int gzb_compress_sections (gzb_engine *e, gzb_section *secs, uint32_t
             put (P.tiles, tiles.data (), tiles.size () * sizeof (Tile));
             put (P.stripe_tiles, stiles.data (), stiles.size () * sizeof (Tile));
             put (P.rans_list, rlist.data (), rlist.size () * 4);
+            put (P.rans_jobs, rjobs.data (), rjobs.size () * sizeof (uint2));
             put (P.arith_list, alist.data (), alist.size () * 4);
         }
 
         P.n_sections = n; P.n_leaves = nl; P.n_tiles = (uint32_t)tiles.size (); P.n_stripe_tiles = (uint32_t)stiles.size ();
         P.n_rans = (uint32_t)rlist.size (); P.n_arith = (uint32_t)alist.size ();
         P.any_pack = any_pack; P.any_o1 = any_o1;
-        P.rans_gpw = pick_rans_gpw (P.n_rans); P.arith_lpw = pick_arith_lpw (P.n_arith);
+        P.n_rans_jobs = (uint32_t)rjobs.size (); P.arith_lpw = pick_arith_lpw (P.n_arith);
         P.copy_parts = (n <= 64) ? 32 : (n <= 1024 ? 8 : 2);
         P.arena = Arena { d_arena, (unsigned long long)arena_est, d_cursor, d_overflow };
         P.ev_chain0 = e->ev0; P.ev_chain1 = e->ev1; P.ev_chain2 = e->ev2;
@@ -440,6 +462,7 @@ extern "C" int gzb_uncompress_sections (gzb_engine *e, gzb_section *secs, uint32
     std::stable_sort (order_idx.begin (), order_idx.end (), [&] (uint32_t a, uint32_t b) { return hs[a].n > hs[b].n; });
     std::vector<uint32_t> rlist, alist;
     for (uint32_t k = 0; k < n; k++) { uint32_t i = order_idx[k]; for (int j = 0; j < 4; j++) (hs[i].coder == CODER_RANS ? rlist : alist).push_back (4 * i + j); }
+    std::vector<uint2> rjobs = make_jobs ((uint32_t)rlist.size (), [&] (uint32_t i) { return hs[rlist[i] >> 2].n; }, [&] (uint32_t) { return 0u; });
 
     size_t arena_est = (size_t)4 << 20;
     for (auto &S : hs) arena_est += (S.coder == CODER_RANS) ? std::min<size_t> ((size_t)1400 << 10, 96 * 1024 + (size_t)S.in_len * 8) + 4 * 16384
@@ -457,6 +480,7 @@ extern "C" int gzb_uncompress_sections (gzb_engine *e, gzb_section *secs, uint32
             meta_off = c.off;
             P.sections   = c.take<DecSection> (n);
             P.rans_list  = c.take<uint32_t> (rlist.size () + 1);
+            P.rans_jobs  = c.take<uint2> (rjobs.size () + 1);
             P.arith_list = c.take<uint32_t> (alist.size () + 1);
             meta_bytes = c.off - meta_off;
             P.leaves     = c.take<DecLeaf> ((size_t)4 * n);
@@ -488,10 +512,11 @@ extern "C" int gzb_uncompress_sections (gzb_engine *e, gzb_section *secs, uint32
         auto put = [&] (const void *dev, const void *src, size_t bytes) { if (bytes) memcpy (meta.data () + ((const uint8_t *)dev - (e->ws + meta_off)), src, bytes); };
         put (P.sections, S2.data (), n * sizeof (DecSection));
         put (P.rans_list, rlist.data (), rlist.size () * 4);
+        put (P.rans_jobs, rjobs.data (), rjobs.size () * sizeof (uint2));
         put (P.arith_list, alist.data (), alist.size () * 4);
 
         P.n_sections = n; P.n_rans = (uint32_t)rlist.size (); P.n_arith = (uint32_t)alist.size ();
-        P.rans_gpw = pick_rans_gpw (P.n_rans); P.arith_lpw = pick_arith_lpw (P.n_arith);
+        P.n_rans_jobs = (uint32_t)rjobs.size (); P.arith_lpw = pick_arith_lpw (P.n_arith);
         P.parts = (n <= 64) ? 32 : (n <= 1024 ? 8 : 2);
         P.arena = Arena { d_arena, (unsigned long long)arena_est, d_cursor, d_overflow };
         P.ev_chain0 = e->ev0; P.ev_chain1 = e->ev1; P.ev_chain2 = e->ev2;

@@ -8,6 +8,7 @@
 //   → unpack → unstripe
 #include "gzb_internal.cuh"
 #include "hts_enc.cuh"
+#include "arith_model.cuh"
 
 namespace gzb {
 
@@ -318,104 +319,131 @@ __global__ void __launch_bounds__(256) k_dec_tables (DecLeaf *leaves, SectionRes
 
 // ------------------------------------------------------------------------------------------------ rANS chain decoder
 // 4 lanes = 4 states; the shared forward read pointer is reproduced with a 4-wide ballot (states renormalise in
-// order 0,1,2,3 within a step, :578-594 / :1062-1066).
-__global__ void k_rans_decode (DecLeaf *leaves, const uint32_t *list, uint32_t n_list, int gpw)
+// order 0,1,2,3 within a step, :578-594 / :1062-1066).  Latency-bound, so: steps run in guard-free blocks of 4, the
+// four candidate renormalisation words of a step are fetched (one 16-byte window) before the table lookup instead of
+// after it, and the order-0 LUT of a single-leaf job is staged in shared memory.
+struct DecLane {
+    const uint8_t *body; uint8_t *out;
+    const uint32_t *lut; const uint8_t *sfb; const uint32_t *fb; const uint8_t *crank;
+    uint32_t n, body_len, shift, q4;
+    bool valid, o1;
+};
+
+__device__ __forceinline__ uint32_t renorm_word (const uint8_t *body, uint32_t body_len, uint32_t a, uint64_t win, uint32_t win_base, bool win_ok)
 {
+    if (win_ok) return (uint32_t)(win >> (8 * (a - win_base))) & 0xffffu;
+    return (a + 1 < body_len) ? (uint32_t)(body[a] | (body[a + 1] << 8)) : 0xffffffffu;   // 0xffffffff = no data (RansDecRenormSafe)
+}
+
+__global__ void __launch_bounds__(32) k_rans_decode (DecLeaf *leaves, const uint32_t *list, const uint2 *jobs, uint32_t n_jobs)
+{
+    __shared__ uint32_t s_lut[4096];
+    if (blockIdx.x >= n_jobs) return;
+    const uint2 job = jobs[blockIdx.x];
     const int lane = threadIdx.x, grp = lane >> 2, k = lane & 3, gshift = lane & ~3;
-    const uint32_t slot = blockIdx.x * gpw + grp;
-    bool valid = false, o1 = false;
-    const uint8_t *body = nullptr; uint8_t *out = nullptr;
-    uint32_t n = 0, body_len = 0, poff = 0, shift = 12;
-    const uint32_t *lut = nullptr; const uint8_t *sfb = nullptr; const uint32_t *fb = nullptr; const uint8_t *crank = nullptr;
-    if (grp < gpw && slot < n_list) {
-        const DecLeaf &L = leaves[list[slot]];
+    DecLane d; d.valid = false; d.o1 = false; d.body = nullptr; d.out = nullptr; d.lut = nullptr; d.sfb = nullptr; d.fb = nullptr; d.crank = nullptr;
+    d.n = d.body_len = d.q4 = 0; d.shift = 12;
+    uint32_t poff = 0;
+    if ((uint32_t)grp < job.y) {
+        const DecLeaf &L = leaves[list[job.x + grp]];
         if (L.valid && !L.err && !L.cat && L.body_ulen && (L.lut || L.sfb)) {
-            valid = true; o1 = L.order; body = L.body; body_len = L.body_len; out = L.dst; n = L.body_ulen;
-            poff = L.payload_off; lut = L.lut; sfb = L.sfb; fb = L.fb; shift = L.shift; crank = L.ctxrank;
+            d.valid = true; d.o1 = L.order; d.body = L.body; d.body_len = L.body_len; d.out = L.dst; d.n = L.body_ulen;
+            poff = L.payload_off; d.lut = L.lut; d.sfb = L.sfb; d.fb = L.fb; d.shift = L.shift; d.crank = L.ctxrank; d.q4 = d.n >> 2;
+        }
+    }
+    if (job.y == 1) {                                                       // single big leaf: order-0 LUT in shared memory
+        const bool use = __shfl_sync (0xffffffffu, (int)(d.valid && !d.o1), 0);
+        if (use) {
+            const unsigned long long lp = __shfl_sync (0xffffffffu, (unsigned long long)d.lut, 0);
+            for (int i = lane; i < 4096; i += 32) s_lut[i] = reinterpret_cast<const uint32_t *>(lp)[i];
+            __syncwarp ();
+            if (d.valid) d.lut = s_lut;
         }
     }
     uint32_t x = 0;
-    if (valid) { const uint8_t *q = body + poff + 4 * k; x = q[0] | (q[1] << 8) | (q[2] << 16) | ((uint32_t)q[3] << 24); poff += 16; }
-    const uint32_t q4 = n >> 2;
-    uint32_t steps = !valid ? 0 : o1 ? q4 + (n - 4 * q4) : (n + 3) >> 2;
+    if (d.valid) { const uint8_t *q = d.body + poff + 4 * k; x = q[0] | (q[1] << 8) | (q[2] << 16) | ((uint32_t)q[3] << 24); poff += 16; }
+    const uint32_t r = d.n - 4 * d.q4;
+    const uint32_t steps = !d.valid ? 0 : d.o1 ? d.q4 + r : (d.n + 3) >> 2;
+    const uint32_t reg_steps = !d.valid ? 0 : d.o1 ? d.q4 : d.n >> 2;      // steps in which all 4 lanes decode
     uint32_t maxsteps = steps;
     for (int o = 16; o; o >>= 1) maxsteps = max (maxsteps, __shfl_xor_sync (0xffffffffu, maxsteps, o));
-    const uint32_t mask = (1u << shift) - 1;
-    uint32_t ctx = 0;                                                     // O1: previous symbol of this chain (context 0 first, :1029)
-    for (uint32_t s = 0; s < maxsteps; s++) {
-        bool act;
-        if (!o1) {
-            uint32_t idx = 4 * s + k;
-            act = valid && idx < n;
-            if (act) {
-                uint32_t e = lut[x & 4095];
-                x = (((e >> 8) & 0xfff) + 1) * (x >> 12) + (e >> 20);
-                out[idx] = (uint8_t)e;
+    const uint32_t mask = (1u << d.shift) - 1;
+    uint32_t ctx = 0;                                                       // O1: row of the previous symbol (context 0 first, :1029)
+    if (d.valid && d.o1) ctx = d.crank[0];
+    uint8_t *op = d.valid ? (d.o1 ? d.out + k * d.q4 : d.out + k) : nullptr;
+    const uint32_t ostride = d.o1 ? 1 : 4;
+    const bool o1 = d.o1;
+
+    for (uint32_t s = 0; s < maxsteps; ) {
+        const bool fin = !d.valid || s >= steps;
+        const bool reg = d.valid && s + 4 <= reg_steps;
+        const bool fast = s + 4 <= maxsteps && __all_sync (0xffffffffu, reg || fin);
+        const int nst = fast ? 4 : 1;
+        for (int t = 0; t < nst; t++, s++) {
+            // candidate renormalisation words: bytes [poff, poff+8) of the body, fetched before the dependent table lookup
+            uint64_t win = 0; uint32_t wbase = poff; bool win_ok = false;
+            if (d.valid) {
+                const uintptr_t A = reinterpret_cast<uintptr_t>(d.body + poff);
+                const uint32_t mis = (uint32_t)(A & 7);
+                if (poff + 16 + 8 <= d.body_len + mis) {                    // both aligned 8-byte loads stay inside the body
+                    const uint64_t *wp = reinterpret_cast<const uint64_t *>(A - mis);
+                    const uint64_t lo = wp[0], hi = wp[1];
+                    win = mis ? (lo >> (8 * mis)) | (hi << (64 - 8 * mis)) : lo;
+                    win_ok = true;
+                }
             }
-        }
-        else {
-            // chains 0-2 decode q4 symbols; chain 3 continues alone over the remainder (:1076-1083)
-            uint32_t idx = (s < q4) ? k * q4 + s : (k == 3 ? 3 * q4 + s : 0xffffffffu);
-            act = valid && s < steps && idx != 0xffffffffu && idx < n;
+            bool act;
+            if (fast) act = !fin;
+            else if (!o1) act = d.valid && 4 * s + k < d.n;
+            else act = d.valid && s < steps && (s < d.q4 || k == 3);
             if (act) {
-                uint32_t m = x & mask, row = crank[ctx];
-                uint32_t c = sfb[((size_t)row << shift) + m];
-                uint32_t e = fb[row * 256 + c];
-                x = (e & 0xffffu) * (x >> shift) + m - (e >> 16);
-                out[idx] = (uint8_t)c;
-                ctx = c;
+                if (!o1) {
+                    const uint32_t e = d.lut[x & 4095];
+                    x = (((e >> 8) & 0xfff) + 1) * (x >> 12) + (e >> 20);
+                    *op = (uint8_t)e; op += 4;
+                }
+                else {
+                    const uint32_t m = x & mask;
+                    const uint32_t c = d.sfb[((size_t)ctx << d.shift) + m];
+                    const uint32_t e = d.fb[ctx * 256 + c];
+                    x = (e & 0xffffu) * (x >> d.shift) + m - (e >> 16);
+                    *op = (uint8_t)c; op += 1;
+                    ctx = d.crank[c];
+                }
             }
+            const bool need = act && x < RANS_L;
+            const uint32_t g = (__ballot_sync (0xffffffffu, need) >> gshift) & 0xfu;
+            if (need) {
+                const uint32_t a = poff + 2 * __popc (g & ((1u << k) - 1));
+                const uint32_t w = renorm_word (d.body, d.body_len, a, win, wbase, win_ok);
+                if (w != 0xffffffffu) x = (x << 16) | w;
+            }
+            poff += 2 * __popc (g);
         }
-        bool need = act && x < RANS_L;
-        uint32_t g = (__ballot_sync (0xffffffffu, need) >> gshift) & 0xfu;
-        if (need) {
-            uint32_t a = poff + 2 * __popc (g & ((1u << k) - 1));
-            if (a + 1 < body_len) x = (x << 16) | body[a] | (body[a + 1] << 8);
-        }
-        poff += 2 * __popc (g);
     }
+    (void)ostride;
 }
 
 // ------------------------------------------------------------------------------------------------ arithmetic decoder
-#define AR_MAXF  65519u
-#define AR_STEP  16u
 struct RCDec { uint32_t code, range; const uint8_t *in, *end; };
 
 __device__ __forceinline__ uint32_t model_decode (uint32_t *m, RCDec &rc)  // c_simple_model.h:148-179 + RC_GetFreq/RC_Decode
 {
-    uint32_t tot = m[0];
-    uint32_t freq = (tot && rc.range >= tot) ? rc.code / (rc.range /= tot) : 0;
+    const uint32_t tot = m[0];
+    const uint32_t freq = (tot && rc.range >= tot) ? rc.code / (rc.range /= tot) : 0;
     if (freq > AR_MAXF) return 0;
-    uint32_t i = 2, e = m[2], acc = e & 0xffffu;
-    while (acc <= freq) { e = m[++i]; if (!(e & 0xffffu) && !(e >> 16)) return 0; acc += e & 0xffffu; }   // ran off the live entries: corrupt
-    uint32_t f = e & 0xffffu;
-    acc -= f;
+    uint32_t e, acc;
+    const uint32_t i = ar_find_freq (m, freq, e, acc);
+    if (!i) return 0;                                                     // ran off the live entries: corrupt stream
     rc.code  -= acc * rc.range;
-    rc.range *= f;
+    rc.range *= e & 0xffffu;
+    ar_model_bump (m, i, e, tot);
     while (rc.range < (1u << 24)) {
         if (rc.in >= rc.end) break;
         rc.code = (rc.code << 8) + *rc.in++;
         rc.range <<= 8;
     }
-    f += AR_STEP; tot += AR_STEP;
-    if (tot > AR_MAXF) {
-        m[i] = (e & 0xffff0000u) | f;
-        tot = 0;
-        for (uint32_t j = 2; (m[j] & 0xffffu); j++) { uint32_t g = m[j] & 0xffffu; g -= g >> 1; m[j] = (m[j] & 0xffff0000u) | g; tot += g; }
-        f = m[i] & 0xffffu;
-    }
-    m[0] = tot;
-    uint32_t prev = m[i - 1];
-    if (f > (prev & 0xffffu)) { m[i - 1] = (e & 0xffff0000u) | f; m[i] = prev; }
-    else m[i] = (e & 0xffff0000u) | f;
     return e >> 16;
-}
-
-__device__ void dmodel_init (uint32_t *m, uint32_t maxs)
-{
-    m[0] = maxs; m[1] = AR_MAXF;
-    for (uint32_t i = 0; i < maxs; i++) m[2 + i] = 1u | (i << 16);
-    m[2 + maxs] = 0;
 }
 
 __global__ void k_arith_dec_init (DecLeaf *leaves, uint32_t n_slots, Arena arena)
@@ -424,12 +452,12 @@ __global__ void k_arith_dec_init (DecLeaf *leaves, uint32_t n_slots, Arena arena
     DecLeaf &L = leaves[blockIdx.x];
     if (!L.valid || L.coder != CODER_ARITH || L.cat || !L.body_ulen || L.err) return;
     __shared__ uint32_t *s_m;
-    const uint32_t maxs = L.body[0] ? L.body[0] : 256, stride = maxs + 3, nctx = L.order ? 256 : 1;
-    if (threadIdx.x == 0) { s_m = reinterpret_cast<uint32_t *>(arena.alloc (((unsigned long long)nctx * stride + 258 * 7) * 4)); L.models = s_m; L.nsym = (uint16_t)maxs; }
+    const uint32_t maxs = L.body[0] ? L.body[0] : 256, stride = ar_stride (maxs), nctx = L.order ? 256 : 1;
+    if (threadIdx.x == 0) { s_m = reinterpret_cast<uint32_t *>(arena.alloc (((unsigned long long)nctx * stride + 258 * AR_RUN_STRIDE) * 4)); L.models = s_m; L.nsym = (uint16_t)maxs; }
     __syncthreads ();
     if (!s_m) return;
-    for (uint32_t c = threadIdx.x; c < nctx; c += blockDim.x) dmodel_init (s_m + c * stride, maxs);
-    if (L.rle) for (uint32_t c = threadIdx.x; c < 258; c += blockDim.x) dmodel_init (s_m + nctx * stride + c * 7, 4);
+    for (uint32_t c = threadIdx.x; c < nctx; c += blockDim.x) ar_model_init (s_m + c * stride, maxs);
+    if (L.rle) for (uint32_t c = threadIdx.x; c < 258; c += blockDim.x) ar_model_init (s_m + nctx * stride + c * AR_RUN_STRIDE, 4);
 }
 
 __global__ void k_arith_decode (DecLeaf *leaves, const uint32_t *list, uint32_t n_list, int lpw)
@@ -441,7 +469,7 @@ __global__ void k_arith_decode (DecLeaf *leaves, const uint32_t *list, uint32_t 
     if (slot >= n_list) return;
     DecLeaf &L = leaves[list[slot]];
     if (!L.valid || L.err || L.cat || !L.body_ulen || !L.models) return;
-    const uint32_t n = L.body_ulen, maxs = L.nsym, stride = maxs + 3;
+    const uint32_t n = L.body_ulen, maxs = L.nsym, stride = ar_stride (maxs);
     const bool o1 = L.order == 1, rle = L.rle;
     uint32_t *lit = L.models, *run = lit + (o1 ? 256 : 1) * stride;
     uint8_t *out = L.dst;
@@ -455,7 +483,7 @@ __global__ void k_arith_decode (DecLeaf *leaves, const uint32_t *list, uint32_t 
         if (!rle) continue;
         uint32_t r = 0, part, rctx = last;                                // arith_dynamic.c:473-482 / :591-599
         do {
-            part = model_decode (run + rctx * 7, rc);
+            part = model_decode (run + rctx * AR_RUN_STRIDE, rc);
             if (rctx == last) rctx = 256; else rctx += (rctx < 257);
             r += part;
         } while (part == 3 && r < n);
@@ -520,11 +548,8 @@ void dec_run (DecPlanDev &P, cudaStream_t st)
     if (P.n_rans)  LAUNCH (k_dec_tables, nslots, 256, P.leaves, P.results, nslots, P.arena);
     if (P.n_arith) LAUNCH (k_arith_dec_init, nslots, 256, P.leaves, nslots, P.arena);
     cudaEventRecord (P.ev_chain0, st);
-    if (P.n_rans) {
-        int gpw = P.rans_gpw;
-        LAUNCH (k_rans_decode, (P.n_rans + gpw - 1) / gpw, 32, P.leaves, P.rans_list, P.n_rans, gpw);
-    }
-    cudaEventRecord (P.ev_chain2, st);
+    if (P.n_rans_jobs) LAUNCH (k_rans_decode, P.n_rans_jobs, 32, P.leaves, P.rans_list, P.rans_jobs, P.n_rans_jobs);
+    cudaEventRecord (P.ev_chain1, st);
     if (P.n_arith) {
         int lpw = P.arith_lpw;
         uint32_t warps = (P.n_arith + lpw - 1) / lpw;

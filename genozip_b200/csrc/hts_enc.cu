@@ -12,6 +12,7 @@
 // bitstream); all other passes are bandwidth-shaped.
 #include "gzb_internal.cuh"
 #include "hts_enc.cuh"
+#include "arith_model.cuh"
 
 namespace gzb {
 
@@ -359,40 +360,169 @@ __device__ uint32_t rans_encode_warp (const ChainIn &c, int lane)
     return c.valid ? used + 16 : 0;
 }
 
-// groups-per-warp leaves per warp; one warp per CTA
-__global__ void k_rans_encode (const EncLeaf *leaves, EncLeafDyn *dyn, const uint32_t *order_list, uint32_t n_list, int gpw)
+// ---- fast chain encoder -------------------------------------------------------------------------------------
+// The chain is latency-bound (one warp walks 4 dependent states per leaf), so the per-step instruction count is what
+// matters.  Steps are executed in blocks of 4 whose table entries were loaded one block ahead (double buffering); a
+// block is "fast" when every lane of the warp is either fully regular over the 4 steps or already finished —
+// otherwise single guarded steps are taken (leaf heads/tails: the O0 remainder step, the O1 chain-3 remainder and the
+// final context-0 step).
+struct FastLane {
+    const uint8_t *in;      // leaf input
+    const EncSym  *tab;     // O0: shared-memory table by symbol; O1: global table by rank pair
+    const uint8_t *rank;    // shared memory
+    uint32_t n, nsym, len, delay, pstart, steps, l;
+    bool valid;
+};
+
+template <bool O1> __device__ __forceinline__ bool block_regular (const FastLane &f, uint32_t s, int k, bool &finished)
 {
-    extern __shared__ __align__(16) uint8_t s_dyn[];                      // gpw x (EncSym[256] + rank[256])
+    const int t0 = (int)s - (int)f.delay;
+    finished = !f.valid || t0 >= (int)f.len;
+    if (O1) return f.valid && t0 >= 0 && t0 + 4 <= (int)f.len - 1;
+    return f.valid && s >= ((f.n & 3) ? 1u : 0u) && s + 4 <= f.steps;
+}
+
+template <bool O1> __device__ __forceinline__ void load_block (FastLane &f, uint32_t s, int k, EncSym (&e)[4])
+{
+    if (O1) {
+        const uint8_t *ip = f.in + (f.pstart - (s - f.delay));
+        uint32_t r0 = f.rank[ip[0]], r1 = f.rank[ip[-1]], r2 = f.rank[ip[-2]], r3 = f.rank[ip[-3]];
+        e[0] = f.tab[r0 * f.nsym + f.l]; e[1] = f.tab[r1 * f.nsym + r0];
+        e[2] = f.tab[r2 * f.nsym + r1];  e[3] = f.tab[r3 * f.nsym + r2];
+        f.l = r3;
+    }
+    else {
+        const uint8_t *ip = f.in + 4 * (f.steps - 1 - s) + k;
+        e[0] = f.tab[ip[0]]; e[1] = f.tab[ip[-4]]; e[2] = f.tab[ip[-8]]; e[3] = f.tab[ip[-12]];
+    }
+}
+
+__device__ __forceinline__ void fast_step (uint32_t &x, uint8_t *&wp, bool act, const EncSym &e, int k, int gshift)
+{
+    const bool emit = act && x >= e.x_max;
+    const uint32_t g = (__ballot_sync (0xffffffffu, emit) >> gshift) & 0xfu;
+    if (emit) { *reinterpret_cast<uint16_t *>(wp - 2 * __popc (g >> k)) = (uint16_t)x; x >>= 16; }
+    wp -= 2 * __popc (g);
+    const uint32_t q = __umulhi (x, e.rcp) >> (e.cmpl_sh >> 16);
+    const uint32_t nx = x + e.bias + q * (e.cmpl_sh & 0xffffu);
+    x = act ? nx : x;                                                      // a finished lane keeps its state for the final flush
+}
+
+template <bool O1> __device__ uint32_t rans_encode_fast (FastLane &f, uint8_t *end, int lane)
+{
+    const int k = lane & 3, gshift = lane & ~3;
+    uint32_t x = RANS_L;
+    uint8_t *wp = end;
+    uint32_t maxsteps = f.valid ? f.steps : 0;
+    for (int o = 16; o; o >>= 1) maxsteps = max (maxsteps, __shfl_xor_sync (0xffffffffu, maxsteps, o));
+    EncSym cur[4], nxt[4];
+    bool pre = false, fin = false, fin_n = false;
+    uint32_t s = 0;
+    while (s < maxsteps) {
+        bool fast;
+        if (pre) {
+            #pragma unroll
+            for (int t = 0; t < 4; t++) cur[t] = nxt[t];
+            fin = fin_n; fast = true;
+        }
+        else {
+            bool reg = block_regular<O1> (f, s, k, fin);
+            fast = s + 4 <= maxsteps && __all_sync (0xffffffffu, reg || fin);
+            if (fast && !fin) load_block<O1> (f, s, k, cur);
+        }
+        if (fast) {
+            pre = false;
+            if (s + 8 <= maxsteps) {
+                bool reg = block_regular<O1> (f, s + 4, k, fin_n);
+                pre = __all_sync (0xffffffffu, reg || fin_n);
+                if (pre && !fin_n) load_block<O1> (f, s + 4, k, nxt);
+            }
+            const bool act = !fin;
+            #pragma unroll
+            for (int t = 0; t < 4; t++) fast_step (x, wp, act, cur[t], k, gshift);
+            s += 4;
+        }
+        else {                                                             // one guarded step
+            bool act = false; EncSym e = cur[0];
+            const int t0 = (int)s - (int)f.delay;
+            if (f.valid && t0 >= 0 && t0 < (int)f.len) {
+                if (O1) {
+                    uint32_t cr = ((uint32_t)t0 == f.len - 1) ? f.rank[0] : f.rank[f.in[f.pstart - t0]];
+                    act = true; e = f.tab[cr * f.nsym + f.l]; f.l = cr;
+                }
+                else {
+                    uint32_t idx = 4 * (f.steps - 1 - s) + k;
+                    if (idx < f.n) { act = true; e = f.tab[f.in[idx]]; }
+                }
+            }
+            const bool emit = act && x >= e.x_max;
+            const uint32_t g = (__ballot_sync (0xffffffffu, emit) >> gshift) & 0xfu;
+            if (emit) { *reinterpret_cast<uint16_t *>(wp - 2 * __popc (g >> k)) = (uint16_t)x; x >>= 16; }
+            wp -= 2 * __popc (g);
+            if (act) { const uint32_t q = __umulhi (x, e.rcp) >> (e.cmpl_sh >> 16); x = x + e.bias + q * (e.cmpl_sh & 0xffffu); }
+            s += 1;
+        }
+    }
+    if (f.valid) {                                                          // RansEncFlush in order 3,2,1,0 (:479-482)
+        uint16_t *w = reinterpret_cast<uint16_t *>(wp - 4 * (4 - k));
+        w[0] = (uint16_t)x; w[1] = (uint16_t)(x >> 16);
+    }
+    return f.valid ? (uint32_t)(end - wp) + 16 : 0;
+}
+
+// One warp per job; a job is 1..8 leaves of the (length-sorted) rANS list, all requested with the same order:
+// big leaves get a warp of their own (latency), small ones are packed 8 per warp (issue slots).
+__global__ void __launch_bounds__(32) k_rans_encode (const EncLeaf *leaves, EncLeafDyn *dyn, const uint32_t *order_list, const uint2 *jobs, uint32_t n_jobs)
+{
+    extern __shared__ __align__(16) uint8_t s_dyn[];                      // 8 x (EncSym[256] + rank[256])
     EncSym  (*s_tab)[256]  = reinterpret_cast<EncSym (*)[256]>(s_dyn);
-    uint8_t (*s_rank)[256] = reinterpret_cast<uint8_t (*)[256]>(s_dyn + (size_t)gpw * 256 * sizeof (EncSym));
-    const int lane = threadIdx.x, grp = lane >> 2;
-    uint32_t slot = blockIdx.x * gpw + grp;
-    ChainIn c; c.valid = false; c.o1 = false; c.n = 0; c.nsym = 0; c.in = nullptr; c.tab = nullptr; c.rank = nullptr; c.end = nullptr;
-    uint32_t li = 0;
-    if (grp < gpw && slot < n_list) {
-        li = order_list[slot];
+    uint8_t (*s_rank)[256] = reinterpret_cast<uint8_t (*)[256]>(s_dyn + (size_t)8 * 256 * sizeof (EncSym));
+    if (blockIdx.x >= n_jobs) return;
+    const uint2 job = jobs[blockIdx.x];
+    const int lane = threadIdx.x, grp = lane >> 2, k = lane & 3;
+    FastLane f; f.valid = false; f.in = nullptr; f.tab = nullptr; f.rank = nullptr; f.n = f.nsym = f.len = f.delay = f.pstart = f.steps = f.l = 0;
+    uint8_t *end = nullptr;
+    uint32_t li = 0; bool o1 = false;
+    if ((uint32_t)grp < job.y) {
+        li = order_list[job.x + grp];
         const EncLeaf &L = leaves[li];
         const EncLeafDyn &D = dyn[li];
         if (D.eff_n && D.symtab) {
-            c.valid = true; c.in = D.eff_in; c.n = D.eff_n; c.o1 = D.eff_order; c.nsym = D.nsym;
-            c.end = L.outbuf + (L.out_cap & ~1u);
-            c.tab = D.symtab; c.rank = D.rank;
+            f.valid = true; f.in = D.eff_in; f.n = D.eff_n; f.nsym = D.nsym; f.tab = D.symtab; f.rank = D.rank;
+            o1 = D.eff_order;
+            end = L.outbuf + (L.out_cap & ~1u);
         }
     }
-    // stage the rank map, and for order-0 the symbol table, of each group in shared memory
-    for (int g = 0; g < gpw; g++) {
-        bool v = __shfl_sync (0xffffffffu, (int)c.valid, g * 4);
+    // a warp runs one order: leaves demoted to order 0 by the "<8 symbols" rule ride along in an O1 job via the O0 routine first
+    const bool any_o1 = __any_sync (0xffffffffu, f.valid && o1), any_o0 = __any_sync (0xffffffffu, f.valid && !o1);
+    for (int g = 0; g < (int)job.y; g++) {                                  // stage rank maps (and O0 tables) in shared memory
+        const bool v = __shfl_sync (0xffffffffu, (int)f.valid, g * 4);
         if (!v) continue;
-        bool o1 = __shfl_sync (0xffffffffu, (int)c.o1, g * 4);
-        unsigned long long rp = __shfl_sync (0xffffffffu, (unsigned long long)c.rank, g * 4);
-        unsigned long long tp = __shfl_sync (0xffffffffu, (unsigned long long)c.tab, g * 4);
+        const bool go1 = __shfl_sync (0xffffffffu, (int)o1, g * 4);
+        const unsigned long long rp = __shfl_sync (0xffffffffu, (unsigned long long)f.rank, g * 4);
+        const unsigned long long tp = __shfl_sync (0xffffffffu, (unsigned long long)f.tab, g * 4);
         for (int i = lane; i < 256; i += 32) s_rank[g][i] = reinterpret_cast<const uint8_t *>(rp)[i];
-        if (!o1) for (int i = lane; i < 256; i += 32) s_tab[g][i] = reinterpret_cast<const EncSym *>(tp)[i];
+        if (!go1) for (int i = lane; i < 256; i += 32) s_tab[g][i] = reinterpret_cast<const EncSym *>(tp)[i];
     }
     __syncwarp ();
-    if (c.valid) { c.rank = s_rank[grp]; if (!c.o1) c.tab = s_tab[grp]; }
-    uint32_t plen = rans_encode_warp (c, lane);
-    if (grp < gpw && slot < n_list && (lane & 3) == 0) dyn[li].payload_len = plen;
+    if (f.valid) { f.rank = s_rank[grp]; if (!o1) f.tab = s_tab[grp]; }
+    uint32_t plen = 0;
+    if (any_o0) {
+        FastLane f0 = f; f0.valid = f.valid && !o1;
+        f0.steps = (f0.n + 3) >> 2; f0.len = f0.steps; f0.delay = 0;
+        uint32_t p = rans_encode_fast<false> (f0, end, lane);
+        if (f0.valid) plen = p;
+    }
+    if (any_o1) {
+        FastLane f1 = f; f1.valid = f.valid && o1;
+        const uint32_t q4 = f1.n >> 2, r = f1.n & 3;
+        f1.steps = q4 + r; f1.len = (k == 3) ? q4 + r : q4; f1.delay = (k == 3) ? 0 : r;
+        f1.pstart = (k == 3) ? f1.n - 2 : (k + 1) * q4 - 2;
+        f1.l = f1.valid ? f1.rank[f1.in[f1.pstart + 1]] : 0;
+        uint32_t p = rans_encode_fast<true> (f1, end, lane);
+        if (f1.valid) plen = p;
+    }
+    if ((uint32_t)grp < job.y && k == 0) dyn[li].payload_len = plen;
 }
 
 // ------------------------------------------------------------------------------------------------ frequency tables + encoder symbols
@@ -597,8 +727,6 @@ __global__ void __launch_bounds__(256) k_tables (const EncLeaf *leaves, EncLeafD
 // ------------------------------------------------------------------------------------------------ adaptive arithmetic coder
 // Model layout per context (words): [0] TotFreq, [1] sentinel, [2 .. 2+maxs) entries (freq | symbol<<16), then a zero
 // terminator — the reference's SIMPLE_MODEL (c_simple_model.h:77-103) restricted to the live entries.
-#define AR_MAXF  65519u
-#define AR_STEP  16u
 struct RCEnc { uint32_t low, range, ffnum, cache, carry; uint8_t *out; };
 
 __device__ __forceinline__ void rc_shift_low (RCEnc &rc)                   // c_range_coder.h:70-88
@@ -615,33 +743,16 @@ __device__ __forceinline__ void rc_shift_low (RCEnc &rc)                   // c_
 
 __device__ __forceinline__ void model_encode (uint32_t *m, RCEnc &rc, uint32_t sym)   // c_simple_model.h:123-146 + RC_Encode :97-109
 {
-    uint32_t i = 2, acc = 0, e = m[2];
-    while ((e >> 16) != sym) { acc += e & 0xffffu; e = m[++i]; }
-    uint32_t f = e & 0xffffu, tot = m[0];
-    uint32_t before = rc.low;
+    uint32_t e, acc;
+    const uint32_t tot = m[0];
+    const uint32_t i = ar_find_sym (m, sym, e, acc);
+    const uint32_t before = rc.low;
     rc.range /= tot;
     rc.low   += acc * rc.range;
-    rc.range *= f;
+    rc.range *= e & 0xffffu;
     rc.carry += rc.low < before;
+    ar_model_bump (m, i, e, tot);
     while (rc.range < (1u << 24)) { rc.range <<= 8; rc_shift_low (rc); }
-    f += AR_STEP; tot += AR_STEP;
-    if (tot > AR_MAXF) {                                                  // normalize (:106-116)
-        m[i] = (e & 0xffff0000u) | f;
-        tot = 0;
-        for (uint32_t j = 2; (m[j] & 0xffffu); j++) { uint32_t g = m[j] & 0xffffu; g -= g >> 1; m[j] = (m[j] & 0xffff0000u) | g; tot += g; }
-        f = m[i] & 0xffffu;
-    }
-    m[0] = tot;
-    uint32_t prev = m[i - 1];
-    if (f > (prev & 0xffffu)) { m[i - 1] = (e & 0xffff0000u) | f; m[i] = prev; }
-    else m[i] = (e & 0xffff0000u) | f;
-}
-
-__device__ void model_init (uint32_t *m, uint32_t maxs)                    // c_simple_model.h:85-103
-{
-    m[0] = maxs; m[1] = AR_MAXF;
-    for (uint32_t i = 0; i < maxs; i++) m[2 + i] = 1u | (i << 16);
-    m[2 + maxs] = 0;
 }
 
 // model initialisation for all arithmetic leaves: one CTA per leaf
@@ -658,16 +769,16 @@ __global__ void k_arith_init (const EncLeaf *leaves, EncLeafDyn *dyn, const uint
         uint32_t m = 0;
         for (int i = 255; i >= 0; i--) if (L.hist0[i]) { m = i; break; }
         s_max = m + 1; D.nsym = (uint16_t)(m + 1);
-        D.models = s_m = reinterpret_cast<uint32_t *>(arena.alloc (((unsigned long long)nctx * (m + 4) + 258 * 7) * 4));
+        D.models = s_m = reinterpret_cast<uint32_t *>(arena.alloc (((unsigned long long)nctx * ar_stride (m + 1) + 258 * AR_RUN_STRIDE) * 4));
     }
     __syncthreads ();
     if (!s_m) return;
-    const uint32_t maxs = s_max, stride = maxs + 3;
+    const uint32_t maxs = s_max, stride = ar_stride (maxs);
     uint32_t *lit = s_m;
-    for (uint32_t c = threadIdx.x; c < nctx; c += blockDim.x) model_init (lit + c * stride, maxs);
+    for (uint32_t c = threadIdx.x; c < nctx; c += blockDim.x) ar_model_init (lit + c * stride, maxs);
     if (D.hdr[0] & F_RLE) {
         uint32_t *run = lit + nctx * stride;
-        for (uint32_t c = threadIdx.x; c < 258; c += blockDim.x) model_init (run + c * 7, 4);
+        for (uint32_t c = threadIdx.x; c < 258; c += blockDim.x) ar_model_init (run + c * AR_RUN_STRIDE, 4);
     }
 }
 
@@ -682,7 +793,7 @@ __global__ void k_arith_encode (const EncLeaf *leaves, EncLeafDyn *dyn, const ui
     const uint32_t li = list[slot];
     const EncLeaf &L = leaves[li];
     EncLeafDyn &D = dyn[li];
-    const uint32_t n = D.eff_n, maxs = D.nsym, stride = maxs + 3;
+    const uint32_t n = D.eff_n, maxs = D.nsym, stride = ar_stride (maxs);
     const uint8_t *in = D.eff_in;
     const bool o1 = D.eff_order, rle = (D.hdr[0] & F_RLE) != 0;
     uint32_t *lit = D.models, *run = lit + (o1 ? 256 : 1) * stride;
@@ -706,10 +817,10 @@ __global__ void k_arith_encode (const EncLeaf *leaves, EncLeafDyn *dyn, const ui
         uint32_t rctx = last;
         do {
             uint32_t c = r < 4 ? r : 3;
-            model_encode (run + rctx * 7, rc, c);
+            model_encode (run + rctx * AR_RUN_STRIDE, rc, c);
             r -= c;
             if (rctx == last) rctx = 256; else rctx += (rctx < 257);
-            if (c == 3 && r == 0) model_encode (run + rctx * 7, rc, 0);
+            if (c == 3 && r == 0) model_encode (run + rctx * AR_RUN_STRIDE, rc, 0);
         } while (r);
     }
     if (!expanded) for (int i = 0; i < 5; i++) rc_shift_low (rc);         // RC_FinishEncode
@@ -828,12 +939,11 @@ void enc_run (EncPlanDev &P, cudaStream_t st)
     }
     if (P.n_arith) LAUNCH (k_arith_init, P.n_arith, 256, P.leaves, P.dyn, P.arith_list, P.n_arith, P.arena);
     cudaEventRecord (P.ev_chain0, st);
-    if (P.n_rans) {
-        int gpw = P.rans_gpw;
-        k_rans_encode<<<(P.n_rans + gpw - 1) / gpw, 32, gpw * (256 * sizeof (EncSym) + 256), st>>>(P.leaves, P.dyn, P.rans_list, P.n_rans, gpw);
+    if (P.n_rans_jobs) {
+        k_rans_encode<<<P.n_rans_jobs, 32, 8 * (256 * sizeof (EncSym) + 256), st>>>(P.leaves, P.dyn, P.rans_list, P.rans_jobs, P.n_rans_jobs);
         P.launches++;
     }
-    cudaEventRecord (P.ev_chain2, st);
+    cudaEventRecord (P.ev_chain1, st);
     if (P.n_arith) {
         int lpw = P.arith_lpw;
         uint32_t warps = (P.n_arith + lpw - 1) / lpw;

@@ -10,7 +10,8 @@ struct EncPlanDev {              // device pointers of one encode batch
     EncLeafDyn    *dyn;
     Tile          *tiles;      uint32_t n_tiles;          // TILE-sized pieces of every leaf input
     Tile          *stripe_tiles; uint32_t n_stripe_tiles; // TILE-sized pieces of every STRIPE section (Tile.leaf = section)
-    uint32_t      *rans_list;  uint32_t n_rans;           // rANS leaves, longest first
+    uint32_t      *rans_list;  uint32_t n_rans;           // rANS leaves: requested order 1 first, then order 0; longest first within each
+    uint2         *rans_jobs;  uint32_t n_rans_jobs;      // warp jobs: (first index into rans_list, count <= 8)
     uint32_t      *arith_list; uint32_t n_arith;          // arithmetic leaves, longest first
     SectionResult *results;
     CopySeg       *segs;
@@ -26,6 +27,7 @@ struct DecPlanDev {
     DecSection    *sections;   uint32_t n_sections;
     DecLeaf       *leaves;                                // 4 per section
     uint32_t      *rans_list;  uint32_t n_rans;           // leaf slots of rANS sections, largest section first
+    uint2         *rans_jobs;  uint32_t n_rans_jobs;      // warp jobs: (first index into rans_list, count <= 8)
     uint32_t      *arith_list; uint32_t n_arith;
     SectionResult *results;
     Arena          arena;

@@ -226,7 +226,11 @@ class FastqCodecPath:
         self.h["packed"] = hp(V, self.packed_len + 32)
         self.h["x"] = hp(V, n)
         self.h["linedom"] = hp(V, self.n_reads); self.h["linediv"] = hp(V, self.n_reads)
-        self.h["comp"] = {s: hp(V, self.comp_d[s].shape[1]) for s in STREAMS}
+        # compressed-section buffers: est_size of the largest actual stream of each kind (the capacity the C-ABI requires)
+        def comp_cap(s):
+            lens = [m["len"][s] for m in (self.meta or [])]
+            return max([est_size(self.codec[s], l) for l in lens] + [4096])
+        self.h["comp"] = {s: hp(V, comp_cap(s)) for s in STREAMS}
         self.h["seq_out"] = hp(V, n); self.h["qual_out"] = hp(V, n)
         self.h["dec"] = {s: hp(V, self.caps[s] + 16) for s in ("NONREF_X", "Q_TILE", "Q_X", "Q_Y", "Q_MISC")}
 
