@@ -117,12 +117,13 @@ struct DecLeaf {                 // device-written by the parse kernel (4 slots 
     uint8_t   map[16];
     uint32_t  payload_off;       // rANS: offset of the 4 initial states inside body
     int32_t   err;
-    uint32_t *lut;               // rANS O0: slot -> sym | (freq-1)<<8 | base<<20 (arena)
-    uint8_t  *sfb;               // rANS O1: [ctx rank][1<<shift] slot -> symbol (arena)
-    uint32_t *fb;                // rANS O1: [ctx rank][256] freq | base<<16 (arena)
+    uint2    *lut;               // rANS O0: slot -> { sym | freq<<16 , slot - start }  (arena)
+    uint32_t *lut1;              // rANS O1: [ctx row][1<<shift] slot -> row(sym) | (freq-1)<<8 | (slot-start)<<20 (arena)
     uint32_t *models;            // arith model memory (arena)
     uint16_t  nsym;              // arith: max symbol + 1
-    uint8_t   ctxrank[256];      // rANS O1: context symbol -> row of sfb/fb
+    uint16_t  nctx;              // rANS O1: number of rows
+    uint8_t   ctxrank[256];      // rANS O1: symbol -> row
+    uint8_t   symof[256];        // rANS O1: row -> symbol
 };
 
 struct DecSection {              // host-planned

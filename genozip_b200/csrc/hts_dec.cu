@@ -29,7 +29,7 @@ __device__ int parse_leaf (const uint8_t *in, uint32_t in_len, uint32_t expect, 
 {
     const uint8_t *end = in + in_len;
     L.valid = 1; L.coder = coder; L.err = 0;
-    L.lut = nullptr; L.sfb = nullptr; L.fb = nullptr; L.models = nullptr;
+    L.lut = nullptr; L.lut1 = nullptr; L.models = nullptr;
     if (!in_len) return -1;
     uint32_t flags = *in++;
     if (flags & F_STRIPE) return -1;                                     // nested STRIPE is never produced
@@ -144,7 +144,7 @@ __device__ uint32_t scan_F (DTabSmem &sm)
 }
 
 // order-0 table at p (:526-549): fills lut[4096]; returns bytes consumed (0 = error).  Whole CTA.
-__device__ uint32_t build_dec_o0 (DTabSmem &sm, const uint8_t *p, const uint8_t *end, uint32_t *lut)
+__device__ uint32_t build_dec_o0 (DTabSmem &sm, const uint8_t *p, const uint8_t *end, uint2 *lut)
 {
     const int tid = threadIdx.x;
     sm.F[tid] = 0;
@@ -165,13 +165,13 @@ __device__ uint32_t build_dec_o0 (DTabSmem &sm, const uint8_t *p, const uint8_t 
     uint32_t total = scan_F (sm);
     if (total != 4096) return 0;
     uint32_t f = sm.F[tid], st = sm.start[tid];
-    for (uint32_t y = 0; y < f; y++) lut[st + y] = (uint32_t)tid | ((f - 1) << 8) | (y << 20);
+    for (uint32_t y = 0; y < f; y++) lut[st + y] = make_uint2 ((uint32_t)tid | (f << 16), y);
     __syncthreads ();
     return sm.consumed;
 }
 
 // 4 lanes = 4 states decode n symbols from `in` (payload at off) with an order-0 LUT; used for the compressed O1 table
-__device__ void rans_o0_decode_lanes (const uint8_t *body, uint32_t body_len, uint32_t off, const uint32_t *lut,
+__device__ void rans_o0_decode_lanes (const uint8_t *body, uint32_t body_len, uint32_t off, const uint2 *lut,
                                       uint8_t *out, uint32_t n, int lane, bool valid)
 {
     const int k = lane & 3, gshift = lane & ~3;
@@ -183,9 +183,9 @@ __device__ void rans_o0_decode_lanes (const uint8_t *body, uint32_t body_len, ui
         uint32_t idx = 4 * s + k;
         bool act = valid && s < steps && idx < n;
         if (act) {
-            uint32_t e = lut[x & 4095];
-            x = (((e >> 8) & 0xfff) + 1) * (x >> 12) + (e >> 20);
-            out[idx] = (uint8_t)e;
+            uint2 e = lut[x & 4095];
+            x = (e.x >> 16) * (x >> 12) + e.y;
+            out[idx] = (uint8_t)e.x;
         }
         bool need = act && x < RANS_L;
         uint32_t g = (__ballot_sync (0xffffffffu, need) >> gshift) & 0xfu;
@@ -212,12 +212,12 @@ __global__ void __launch_bounds__(256) k_dec_tables (DecLeaf *leaves, SectionRes
 
     if (L.body_len < 16) fail = true;
     else if (!L.order) {                                                  // ---- order 0 (:498-558)
-        if (tid == 0) s_ptr[0] = arena.alloc (4096 * 4);
+        if (tid == 0) s_ptr[0] = arena.alloc (4096 * 8);
         __syncthreads ();
         if (!s_ptr[0]) return;                                            // arena overflow: host replays the batch
-        uint32_t used = build_dec_o0 (sm, body, end - 8, reinterpret_cast<uint32_t *>(s_ptr[0]));
+        uint32_t used = build_dec_o0 (sm, body, end - 8, reinterpret_cast<uint2 *>(s_ptr[0]));
         if (!used || used + 16 > L.body_len) fail = true;
-        else if (tid == 0) { L.lut = reinterpret_cast<uint32_t *>(s_ptr[0]); L.payload_off = used; }
+        else if (tid == 0) { L.lut = reinterpret_cast<uint2 *>(s_ptr[0]); L.payload_off = used; }
     }
     else {                                                                // ---- order 1 (:883-1019)
         const uint32_t shift = body[0] >> 4;
@@ -230,10 +230,10 @@ __global__ void __launch_bounds__(256) k_dec_tables (DecLeaf *leaves, SectionRes
             p += get_varint (p, end, &csz);
             if (p + csz + 16 > end || usz > (1u << 20) || csz < 16) fail = true;
             if (!fail) {
-                if (tid == 0) { s_ptr[0] = arena.alloc (4096 * 4); s_ptr[1] = arena.alloc (usz + 16); }
+                if (tid == 0) { s_ptr[0] = arena.alloc (4096 * 8); s_ptr[1] = arena.alloc (usz + 16); }
                 __syncthreads ();
                 if (!s_ptr[0] || !s_ptr[1]) return;
-                uint32_t *nlut = reinterpret_cast<uint32_t *>(s_ptr[0]);
+                uint2 *nlut = reinterpret_cast<uint2 *>(s_ptr[0]);
                 uint32_t used = build_dec_o0 (sm, p, p + csz - 8, nlut);
                 if (!used || used + 16 > csz) fail = true;
                 else {
@@ -255,19 +255,17 @@ __global__ void __launch_bounds__(256) k_dec_tables (DecLeaf *leaves, SectionRes
                 uint32_t nc = 0;
                 for (int i = 0; i < 256; i++) if (sm.F0[i]) nc++;
                 sm.nctx = nc;
-                s_ptr[2] = s_ptr[3] = nullptr;
-                if (sm.ok) {
-                    s_ptr[2] = arena.alloc ((unsigned long long)nc << shift);
-                    s_ptr[3] = arena.alloc ((unsigned long long)nc * 256 * 4);
-                }
+                s_ptr[2] = nullptr;
+                if (sm.ok) s_ptr[2] = arena.alloc (((unsigned long long)nc << shift) * 4);
+                uint32_t rr = 0;
+                for (int i = 0; i < 256; i++) if (sm.F0[i]) { L.ctxrank[i] = (uint8_t)rr; L.symof[rr] = (uint8_t)i; rr++; } else L.ctxrank[i] = 0;
             }
             __syncthreads ();
             if (!sm.ok) fail = true;
-            else if (!s_ptr[2] || !s_ptr[3]) return;
+            else if (!s_ptr[2]) return;
         }
         if (!fail) {
-            uint8_t  *sfb = s_ptr[2];
-            uint32_t *fb  = reinterpret_cast<uint32_t *>(s_ptr[3]);
+            uint32_t *lut1 = reinterpret_cast<uint32_t *>(s_ptr[2]);
             uint32_t row = 0;
             for (int i = 0; i < 256 && !fail; i++) {
                 if (!sm.F0[i]) continue;                                  // uniform: F0 is shared
@@ -290,7 +288,6 @@ __global__ void __launch_bounds__(256) k_dec_tables (DecLeaf *leaves, SectionRes
                 }
                 __syncthreads ();
                 if (!sm.ok) { fail = true; break; }
-                if (tid == 0) L.ctxrank[i] = (uint8_t)row;
                 const uint32_t T = sm.T;
                 if (T) {
                     if (T > (1u << shift) || (T & (T - 1))) { fail = true; break; }
@@ -300,9 +297,9 @@ __global__ void __launch_bounds__(256) k_dec_tables (DecLeaf *leaves, SectionRes
                     uint32_t total = scan_F (sm);
                     if (total != (1u << shift)) { fail = true; break; }
                     uint32_t f = sm.F[tid], st = sm.start[tid];
-                    uint8_t *srow = sfb + ((size_t)row << shift);
-                    for (uint32_t y = 0; y < f; y++) srow[st + y] = (uint8_t)tid;
-                    fb[row * 256 + tid] = f | (st << 16);
+                    uint32_t *srow = lut1 + ((size_t)row << shift);
+                    const uint32_t base_e = (uint32_t)L.ctxrank[tid] | ((f - 1) << 8);
+                    for (uint32_t y = 0; y < f; y++) srow[st + y] = base_e | (y << 20);
                 }
                 row++;
                 __syncthreads ();
@@ -310,118 +307,11 @@ __global__ void __launch_bounds__(256) k_dec_tables (DecLeaf *leaves, SectionRes
             if (!fail) {
                 const uint8_t *pay = tab_end ? tab_end : sm.p;
                 if (pay + 16 > end) fail = true;
-                else if (tid == 0) { L.sfb = sfb; L.fb = fb; L.shift = (uint8_t)shift; L.payload_off = (uint32_t)(pay - body); }
+                else if (tid == 0) { L.lut1 = lut1; L.nctx = (uint16_t)sm.nctx; L.shift = (uint8_t)shift; L.payload_off = (uint32_t)(pay - body); }
             }
         }
     }
     if (fail && tid == 0) { L.err = -4; res[si].status = -4; }
-}
-
-// ------------------------------------------------------------------------------------------------ rANS chain decoder
-// 4 lanes = 4 states; the shared forward read pointer is reproduced with a 4-wide ballot (states renormalise in
-// order 0,1,2,3 within a step, :578-594 / :1062-1066).  Latency-bound, so: steps run in guard-free blocks of 4, the
-// four candidate renormalisation words of a step are fetched (one 16-byte window) before the table lookup instead of
-// after it, and the order-0 LUT of a single-leaf job is staged in shared memory.
-struct DecLane {
-    const uint8_t *body; uint8_t *out;
-    const uint32_t *lut; const uint8_t *sfb; const uint32_t *fb; const uint8_t *crank;
-    uint32_t n, body_len, shift, q4;
-    bool valid, o1;
-};
-
-__device__ __forceinline__ uint32_t renorm_word (const uint8_t *body, uint32_t body_len, uint32_t a, uint64_t win, uint32_t win_base, bool win_ok)
-{
-    if (win_ok) return (uint32_t)(win >> (8 * (a - win_base))) & 0xffffu;
-    return (a + 1 < body_len) ? (uint32_t)(body[a] | (body[a + 1] << 8)) : 0xffffffffu;   // 0xffffffff = no data (RansDecRenormSafe)
-}
-
-__global__ void __launch_bounds__(32) k_rans_decode (DecLeaf *leaves, const uint32_t *list, const uint2 *jobs, uint32_t n_jobs)
-{
-    __shared__ uint32_t s_lut[4096];
-    if (blockIdx.x >= n_jobs) return;
-    const uint2 job = jobs[blockIdx.x];
-    const int lane = threadIdx.x, grp = lane >> 2, k = lane & 3, gshift = lane & ~3;
-    DecLane d; d.valid = false; d.o1 = false; d.body = nullptr; d.out = nullptr; d.lut = nullptr; d.sfb = nullptr; d.fb = nullptr; d.crank = nullptr;
-    d.n = d.body_len = d.q4 = 0; d.shift = 12;
-    uint32_t poff = 0;
-    if ((uint32_t)grp < job.y) {
-        const DecLeaf &L = leaves[list[job.x + grp]];
-        if (L.valid && !L.err && !L.cat && L.body_ulen && (L.lut || L.sfb)) {
-            d.valid = true; d.o1 = L.order; d.body = L.body; d.body_len = L.body_len; d.out = L.dst; d.n = L.body_ulen;
-            poff = L.payload_off; d.lut = L.lut; d.sfb = L.sfb; d.fb = L.fb; d.shift = L.shift; d.crank = L.ctxrank; d.q4 = d.n >> 2;
-        }
-    }
-    if (job.y == 1) {                                                       // single big leaf: order-0 LUT in shared memory
-        const bool use = __shfl_sync (0xffffffffu, (int)(d.valid && !d.o1), 0);
-        if (use) {
-            const unsigned long long lp = __shfl_sync (0xffffffffu, (unsigned long long)d.lut, 0);
-            for (int i = lane; i < 4096; i += 32) s_lut[i] = reinterpret_cast<const uint32_t *>(lp)[i];
-            __syncwarp ();
-            if (d.valid) d.lut = s_lut;
-        }
-    }
-    uint32_t x = 0;
-    if (d.valid) { const uint8_t *q = d.body + poff + 4 * k; x = q[0] | (q[1] << 8) | (q[2] << 16) | ((uint32_t)q[3] << 24); poff += 16; }
-    const uint32_t r = d.n - 4 * d.q4;
-    const uint32_t steps = !d.valid ? 0 : d.o1 ? d.q4 + r : (d.n + 3) >> 2;
-    const uint32_t reg_steps = !d.valid ? 0 : d.o1 ? d.q4 : d.n >> 2;      // steps in which all 4 lanes decode
-    uint32_t maxsteps = steps;
-    for (int o = 16; o; o >>= 1) maxsteps = max (maxsteps, __shfl_xor_sync (0xffffffffu, maxsteps, o));
-    const uint32_t mask = (1u << d.shift) - 1;
-    uint32_t ctx = 0;                                                       // O1: row of the previous symbol (context 0 first, :1029)
-    if (d.valid && d.o1) ctx = d.crank[0];
-    uint8_t *op = d.valid ? (d.o1 ? d.out + k * d.q4 : d.out + k) : nullptr;
-    const uint32_t ostride = d.o1 ? 1 : 4;
-    const bool o1 = d.o1;
-
-    for (uint32_t s = 0; s < maxsteps; ) {
-        const bool fin = !d.valid || s >= steps;
-        const bool reg = d.valid && s + 4 <= reg_steps;
-        const bool fast = s + 4 <= maxsteps && __all_sync (0xffffffffu, reg || fin);
-        const int nst = fast ? 4 : 1;
-        for (int t = 0; t < nst; t++, s++) {
-            // candidate renormalisation words: bytes [poff, poff+8) of the body, fetched before the dependent table lookup
-            uint64_t win = 0; uint32_t wbase = poff; bool win_ok = false;
-            if (d.valid) {
-                const uintptr_t A = reinterpret_cast<uintptr_t>(d.body + poff);
-                const uint32_t mis = (uint32_t)(A & 7);
-                if (poff + 16 + 8 <= d.body_len + mis) {                    // both aligned 8-byte loads stay inside the body
-                    const uint64_t *wp = reinterpret_cast<const uint64_t *>(A - mis);
-                    const uint64_t lo = wp[0], hi = wp[1];
-                    win = mis ? (lo >> (8 * mis)) | (hi << (64 - 8 * mis)) : lo;
-                    win_ok = true;
-                }
-            }
-            bool act;
-            if (fast) act = !fin;
-            else if (!o1) act = d.valid && 4 * s + k < d.n;
-            else act = d.valid && s < steps && (s < d.q4 || k == 3);
-            if (act) {
-                if (!o1) {
-                    const uint32_t e = d.lut[x & 4095];
-                    x = (((e >> 8) & 0xfff) + 1) * (x >> 12) + (e >> 20);
-                    *op = (uint8_t)e; op += 4;
-                }
-                else {
-                    const uint32_t m = x & mask;
-                    const uint32_t c = d.sfb[((size_t)ctx << d.shift) + m];
-                    const uint32_t e = d.fb[ctx * 256 + c];
-                    x = (e & 0xffffu) * (x >> d.shift) + m - (e >> 16);
-                    *op = (uint8_t)c; op += 1;
-                    ctx = d.crank[c];
-                }
-            }
-            const bool need = act && x < RANS_L;
-            const uint32_t g = (__ballot_sync (0xffffffffu, need) >> gshift) & 0xfu;
-            if (need) {
-                const uint32_t a = poff + 2 * __popc (g & ((1u << k) - 1));
-                const uint32_t w = renorm_word (d.body, d.body_len, a, win, wbase, win_ok);
-                if (w != 0xffffffffu) x = (x << 16) | w;
-            }
-            poff += 2 * __popc (g);
-        }
-    }
-    (void)ostride;
 }
 
 // ------------------------------------------------------------------------------------------------ arithmetic decoder
@@ -548,7 +438,7 @@ void dec_run (DecPlanDev &P, cudaStream_t st)
     if (P.n_rans)  LAUNCH (k_dec_tables, nslots, 256, P.leaves, P.results, nslots, P.arena);
     if (P.n_arith) LAUNCH (k_arith_dec_init, nslots, 256, P.leaves, nslots, P.arena);
     cudaEventRecord (P.ev_chain0, st);
-    if (P.n_rans_jobs) LAUNCH (k_rans_decode, P.n_rans_jobs, 32, P.leaves, P.rans_list, P.rans_jobs, P.n_rans_jobs);
+    if (P.n_rans_jobs) { launch_rans_decode (P, st); P.launches++; }
     cudaEventRecord (P.ev_chain1, st);
     if (P.n_arith) {
         int lpw = P.arith_lpw;

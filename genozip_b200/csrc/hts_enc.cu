@@ -360,171 +360,6 @@ __device__ uint32_t rans_encode_warp (const ChainIn &c, int lane)
     return c.valid ? used + 16 : 0;
 }
 
-// ---- fast chain encoder -------------------------------------------------------------------------------------
-// The chain is latency-bound (one warp walks 4 dependent states per leaf), so the per-step instruction count is what
-// matters.  Steps are executed in blocks of 4 whose table entries were loaded one block ahead (double buffering); a
-// block is "fast" when every lane of the warp is either fully regular over the 4 steps or already finished —
-// otherwise single guarded steps are taken (leaf heads/tails: the O0 remainder step, the O1 chain-3 remainder and the
-// final context-0 step).
-struct FastLane {
-    const uint8_t *in;      // leaf input
-    const EncSym  *tab;     // O0: shared-memory table by symbol; O1: global table by rank pair
-    const uint8_t *rank;    // shared memory
-    uint32_t n, nsym, len, delay, pstart, steps, l;
-    bool valid;
-};
-
-template <bool O1> __device__ __forceinline__ bool block_regular (const FastLane &f, uint32_t s, int k, bool &finished)
-{
-    const int t0 = (int)s - (int)f.delay;
-    finished = !f.valid || t0 >= (int)f.len;
-    if (O1) return f.valid && t0 >= 0 && t0 + 4 <= (int)f.len - 1;
-    return f.valid && s >= ((f.n & 3) ? 1u : 0u) && s + 4 <= f.steps;
-}
-
-template <bool O1> __device__ __forceinline__ void load_block (FastLane &f, uint32_t s, int k, EncSym (&e)[4])
-{
-    if (O1) {
-        const uint8_t *ip = f.in + (f.pstart - (s - f.delay));
-        uint32_t r0 = f.rank[ip[0]], r1 = f.rank[ip[-1]], r2 = f.rank[ip[-2]], r3 = f.rank[ip[-3]];
-        e[0] = f.tab[r0 * f.nsym + f.l]; e[1] = f.tab[r1 * f.nsym + r0];
-        e[2] = f.tab[r2 * f.nsym + r1];  e[3] = f.tab[r3 * f.nsym + r2];
-        f.l = r3;
-    }
-    else {
-        const uint8_t *ip = f.in + 4 * (f.steps - 1 - s) + k;
-        e[0] = f.tab[ip[0]]; e[1] = f.tab[ip[-4]]; e[2] = f.tab[ip[-8]]; e[3] = f.tab[ip[-12]];
-    }
-}
-
-__device__ __forceinline__ void fast_step (uint32_t &x, uint8_t *&wp, bool act, const EncSym &e, int k, int gshift)
-{
-    const bool emit = act && x >= e.x_max;
-    const uint32_t g = (__ballot_sync (0xffffffffu, emit) >> gshift) & 0xfu;
-    if (emit) { *reinterpret_cast<uint16_t *>(wp - 2 * __popc (g >> k)) = (uint16_t)x; x >>= 16; }
-    wp -= 2 * __popc (g);
-    const uint32_t q = __umulhi (x, e.rcp) >> (e.cmpl_sh >> 16);
-    const uint32_t nx = x + e.bias + q * (e.cmpl_sh & 0xffffu);
-    x = act ? nx : x;                                                      // a finished lane keeps its state for the final flush
-}
-
-template <bool O1> __device__ uint32_t rans_encode_fast (FastLane &f, uint8_t *end, int lane)
-{
-    const int k = lane & 3, gshift = lane & ~3;
-    uint32_t x = RANS_L;
-    uint8_t *wp = end;
-    uint32_t maxsteps = f.valid ? f.steps : 0;
-    for (int o = 16; o; o >>= 1) maxsteps = max (maxsteps, __shfl_xor_sync (0xffffffffu, maxsteps, o));
-    EncSym cur[4], nxt[4];
-    bool pre = false, fin = false, fin_n = false;
-    uint32_t s = 0;
-    while (s < maxsteps) {
-        bool fast;
-        if (pre) {
-            #pragma unroll
-            for (int t = 0; t < 4; t++) cur[t] = nxt[t];
-            fin = fin_n; fast = true;
-        }
-        else {
-            bool reg = block_regular<O1> (f, s, k, fin);
-            fast = s + 4 <= maxsteps && __all_sync (0xffffffffu, reg || fin);
-            if (fast && !fin) load_block<O1> (f, s, k, cur);
-        }
-        if (fast) {
-            pre = false;
-            if (s + 8 <= maxsteps) {
-                bool reg = block_regular<O1> (f, s + 4, k, fin_n);
-                pre = __all_sync (0xffffffffu, reg || fin_n);
-                if (pre && !fin_n) load_block<O1> (f, s + 4, k, nxt);
-            }
-            const bool act = !fin;
-            #pragma unroll
-            for (int t = 0; t < 4; t++) fast_step (x, wp, act, cur[t], k, gshift);
-            s += 4;
-        }
-        else {                                                             // one guarded step
-            bool act = false; EncSym e = cur[0];
-            const int t0 = (int)s - (int)f.delay;
-            if (f.valid && t0 >= 0 && t0 < (int)f.len) {
-                if (O1) {
-                    uint32_t cr = ((uint32_t)t0 == f.len - 1) ? f.rank[0] : f.rank[f.in[f.pstart - t0]];
-                    act = true; e = f.tab[cr * f.nsym + f.l]; f.l = cr;
-                }
-                else {
-                    uint32_t idx = 4 * (f.steps - 1 - s) + k;
-                    if (idx < f.n) { act = true; e = f.tab[f.in[idx]]; }
-                }
-            }
-            const bool emit = act && x >= e.x_max;
-            const uint32_t g = (__ballot_sync (0xffffffffu, emit) >> gshift) & 0xfu;
-            if (emit) { *reinterpret_cast<uint16_t *>(wp - 2 * __popc (g >> k)) = (uint16_t)x; x >>= 16; }
-            wp -= 2 * __popc (g);
-            if (act) { const uint32_t q = __umulhi (x, e.rcp) >> (e.cmpl_sh >> 16); x = x + e.bias + q * (e.cmpl_sh & 0xffffu); }
-            s += 1;
-        }
-    }
-    if (f.valid) {                                                          // RansEncFlush in order 3,2,1,0 (:479-482)
-        uint16_t *w = reinterpret_cast<uint16_t *>(wp - 4 * (4 - k));
-        w[0] = (uint16_t)x; w[1] = (uint16_t)(x >> 16);
-    }
-    return f.valid ? (uint32_t)(end - wp) + 16 : 0;
-}
-
-// One warp per job; a job is 1..8 leaves of the (length-sorted) rANS list, all requested with the same order:
-// big leaves get a warp of their own (latency), small ones are packed 8 per warp (issue slots).
-__global__ void __launch_bounds__(32) k_rans_encode (const EncLeaf *leaves, EncLeafDyn *dyn, const uint32_t *order_list, const uint2 *jobs, uint32_t n_jobs)
-{
-    extern __shared__ __align__(16) uint8_t s_dyn[];                      // 8 x (EncSym[256] + rank[256])
-    EncSym  (*s_tab)[256]  = reinterpret_cast<EncSym (*)[256]>(s_dyn);
-    uint8_t (*s_rank)[256] = reinterpret_cast<uint8_t (*)[256]>(s_dyn + (size_t)8 * 256 * sizeof (EncSym));
-    if (blockIdx.x >= n_jobs) return;
-    const uint2 job = jobs[blockIdx.x];
-    const int lane = threadIdx.x, grp = lane >> 2, k = lane & 3;
-    FastLane f; f.valid = false; f.in = nullptr; f.tab = nullptr; f.rank = nullptr; f.n = f.nsym = f.len = f.delay = f.pstart = f.steps = f.l = 0;
-    uint8_t *end = nullptr;
-    uint32_t li = 0; bool o1 = false;
-    if ((uint32_t)grp < job.y) {
-        li = order_list[job.x + grp];
-        const EncLeaf &L = leaves[li];
-        const EncLeafDyn &D = dyn[li];
-        if (D.eff_n && D.symtab) {
-            f.valid = true; f.in = D.eff_in; f.n = D.eff_n; f.nsym = D.nsym; f.tab = D.symtab; f.rank = D.rank;
-            o1 = D.eff_order;
-            end = L.outbuf + (L.out_cap & ~1u);
-        }
-    }
-    // a warp runs one order: leaves demoted to order 0 by the "<8 symbols" rule ride along in an O1 job via the O0 routine first
-    const bool any_o1 = __any_sync (0xffffffffu, f.valid && o1), any_o0 = __any_sync (0xffffffffu, f.valid && !o1);
-    for (int g = 0; g < (int)job.y; g++) {                                  // stage rank maps (and O0 tables) in shared memory
-        const bool v = __shfl_sync (0xffffffffu, (int)f.valid, g * 4);
-        if (!v) continue;
-        const bool go1 = __shfl_sync (0xffffffffu, (int)o1, g * 4);
-        const unsigned long long rp = __shfl_sync (0xffffffffu, (unsigned long long)f.rank, g * 4);
-        const unsigned long long tp = __shfl_sync (0xffffffffu, (unsigned long long)f.tab, g * 4);
-        for (int i = lane; i < 256; i += 32) s_rank[g][i] = reinterpret_cast<const uint8_t *>(rp)[i];
-        if (!go1) for (int i = lane; i < 256; i += 32) s_tab[g][i] = reinterpret_cast<const EncSym *>(tp)[i];
-    }
-    __syncwarp ();
-    if (f.valid) { f.rank = s_rank[grp]; if (!o1) f.tab = s_tab[grp]; }
-    uint32_t plen = 0;
-    if (any_o0) {
-        FastLane f0 = f; f0.valid = f.valid && !o1;
-        f0.steps = (f0.n + 3) >> 2; f0.len = f0.steps; f0.delay = 0;
-        uint32_t p = rans_encode_fast<false> (f0, end, lane);
-        if (f0.valid) plen = p;
-    }
-    if (any_o1) {
-        FastLane f1 = f; f1.valid = f.valid && o1;
-        const uint32_t q4 = f1.n >> 2, r = f1.n & 3;
-        f1.steps = q4 + r; f1.len = (k == 3) ? q4 + r : q4; f1.delay = (k == 3) ? 0 : r;
-        f1.pstart = (k == 3) ? f1.n - 2 : (k + 1) * q4 - 2;
-        f1.l = f1.valid ? f1.rank[f1.in[f1.pstart + 1]] : 0;
-        uint32_t p = rans_encode_fast<true> (f1, end, lane);
-        if (f1.valid) plen = p;
-    }
-    if ((uint32_t)grp < job.y && k == 0) dyn[li].payload_len = plen;
-}
-
 // ------------------------------------------------------------------------------------------------ frequency tables + encoder symbols
 // one CTA (256 threads) per rANS leaf.
 struct TabSmem {
@@ -939,10 +774,7 @@ void enc_run (EncPlanDev &P, cudaStream_t st)
     }
     if (P.n_arith) LAUNCH (k_arith_init, P.n_arith, 256, P.leaves, P.dyn, P.arith_list, P.n_arith, P.arena);
     cudaEventRecord (P.ev_chain0, st);
-    if (P.n_rans_jobs) {
-        k_rans_encode<<<P.n_rans_jobs, 32, 8 * (256 * sizeof (EncSym) + 256), st>>>(P.leaves, P.dyn, P.rans_list, P.rans_jobs, P.n_rans_jobs);
-        P.launches++;
-    }
+    if (P.n_rans_jobs) { launch_rans_encode (P, st); P.launches++; }
     cudaEventRecord (P.ev_chain1, st);
     if (P.n_arith) {
         int lpw = P.arith_lpw;

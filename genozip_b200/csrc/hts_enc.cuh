@@ -39,5 +39,7 @@ struct DecPlanDev {
 void upload_log_tables (const double *l10, const double *l12);
 void enc_run (EncPlanDev &P, cudaStream_t st);
 void dec_run (DecPlanDev &P, cudaStream_t st);
+void launch_rans_encode (EncPlanDev &P, cudaStream_t st);
+void launch_rans_decode (DecPlanDev &P, cudaStream_t st);
 
 } // namespace gzb

@@ -1,0 +1,351 @@
+// rans_chain.cu — the latency-bound inner loops of the rANS 4x16 coder: one leaf = 4 lanes = the 4 interleaved states.
+//
+// The bitstream fixes 4 dependency chains per leaf (reference rANS_static4x16pr.c:434-482, 798-851 encode;
+// :555-604, 1021-1083 decode), so a big leaf is walked by ONE warp at the speed of its dependent instruction
+// stream.  What matters is therefore (1) instructions per step — steps run in fully unrolled, guard-free blocks of 4,
+// table entries for the next block are loaded while the current one executes, read-only data goes through
+// __ldg — and (2) running every leaf of every VBlock of the batch at once: big leaves get a warp each, small leaves
+// are packed 8 per warp so they share issue slots (warp "jobs", planned by the host).
+//
+// Shared output / input pointer of the four states: reproduced exactly with a 4-wide ballot per step.
+//   encode: states are served 3,2,1,0 within a step and the stream grows backwards (:453-456, :832-835):
+//           an emitting lane k writes its 16-bit word at  wp - 2*popc(emitters with index >= k)
+//   decode: states renormalise 0,1,2,3 and the stream is read forwards (:578-594, :1062-1066):
+//           a renormalising lane k reads the word at     poff + 2*popc(renormalisers with index < k)
+#include "gzb_internal.cuh"
+#include "hts_enc.cuh"
+
+namespace gzb {
+
+// ================================================================================================ encode
+struct EncLane {
+    const uint8_t * __restrict__ in;
+    const EncSym  * __restrict__ tab;    // O0: shared-memory table by symbol; O1: global table by rank pair
+    const uint8_t *rank;                 // shared memory
+    uint8_t *end;
+    uint32_t n, nsym;
+    bool valid;
+};
+
+__device__ __forceinline__ EncSym __ldg4 (const EncSym *p)
+{
+    const uint4 v = __ldg (reinterpret_cast<const uint4 *>(p));
+    EncSym e; e.x_max = v.x; e.rcp = v.y; e.bias = v.z; e.cmpl_sh = v.w;
+    return e;
+}
+
+__device__ __forceinline__ void enc_step (uint32_t &x, uint8_t *&wp, const EncSym &e, bool act, int k, int gshift)
+{
+    const bool emit = act && x >= e.x_max;
+    const uint32_t g = (__ballot_sync (0xffffffffu, emit) >> gshift) & 0xfu;
+    if (emit) { *reinterpret_cast<uint16_t *>(wp - 2 * __popc (g >> k)) = (uint16_t)x; x >>= 16; }
+    wp -= 2 * __popc (g);
+    const uint32_t q = __umulhi (x, e.rcp) >> (e.cmpl_sh >> 16);
+    const uint32_t nx = x + e.bias + q * (e.cmpl_sh & 0xffffu);
+    x = act ? nx : x;
+}
+
+// Order 0.  Step s covers symbols 4*(S-1-s) .. +3 (symbol i belongs to state i&3; the last symbols first, :439-477).
+__device__ __forceinline__ uint32_t encode_o0 (const EncLane &f, const EncSym *stab, int lane)
+{
+    const int k = lane & 3, gshift = lane & ~3;
+    uint32_t x = RANS_L;
+    uint8_t *wp = f.end;
+    const uint32_t steps = f.valid ? (f.n + 3) >> 2 : 0;
+    uint32_t maxsteps = steps;
+    for (int o = 16; o; o >>= 1) maxsteps = max (maxsteps, __shfl_xor_sync (0xffffffffu, maxsteps, o));
+    uint32_t s = 0;
+    while (s < maxsteps) {
+        const bool active = f.valid && s < steps;
+        // fast region: every active lane has 4 full steps ahead (s >= 1 when the first step is the partial remainder)
+        uint32_t lim = active ? (((f.n & 3) && s == 0) ? 0u : steps) : 0xffffffffu;
+        for (int o = 16; o; o >>= 1) lim = min (lim, __shfl_xor_sync (0xffffffffu, lim, o));
+        if (lim != 0xffffffffu && s + 4 <= lim) {
+            const uint8_t *ip = active ? f.in + 4 * (steps - 1 - s) + k : f.in;
+            EncSym e0, e1, e2, e3;
+            if (active) { e0 = stab[__ldg (ip)]; e1 = stab[__ldg (ip - 4)]; e2 = stab[__ldg (ip - 8)]; e3 = stab[__ldg (ip - 12)]; }
+            for (; s + 4 <= lim; s += 4) {
+                const EncSym c0 = e0, c1 = e1, c2 = e2, c3 = e3;
+                ip -= 16;
+                if (active && s + 8 <= lim) { e0 = stab[__ldg (ip)]; e1 = stab[__ldg (ip - 4)]; e2 = stab[__ldg (ip - 8)]; e3 = stab[__ldg (ip - 12)]; }
+                enc_step (x, wp, c0, active, k, gshift);
+                enc_step (x, wp, c1, active, k, gshift);
+                enc_step (x, wp, c2, active, k, gshift);
+                enc_step (x, wp, c3, active, k, gshift);
+            }
+        }
+        else {                                                               // one guarded step (leaf heads and tails)
+            bool act = false; EncSym e; e.x_max = 0xffffffffu; e.rcp = 0; e.bias = 0; e.cmpl_sh = 0;
+            if (active) {
+                const uint32_t idx = 4 * (steps - 1 - s) + k;
+                if (idx < f.n) { act = true; e = stab[f.in[idx]]; }
+            }
+            enc_step (x, wp, e, act, k, gshift);
+            s++;
+        }
+    }
+    if (f.valid) {                                                           // RansEncFlush 3,2,1,0 (:479-482); 2-byte aligned only
+        uint16_t *w = reinterpret_cast<uint16_t *>(wp - 4 * (4 - k));
+        w[0] = (uint16_t)x; w[1] = (uint16_t)(x >> 16);
+    }
+    return f.valid ? (uint32_t)(f.end - wp) + 16 : 0;
+}
+
+// Order 1.  Lane k walks its quarter backwards, pos = pstart .. k*q4, then one step in context 0 (:806-846); chain 3 also
+// owns the remainder, so lanes 0-2 join `delay` steps later.
+__device__ __forceinline__ uint32_t encode_o1 (const EncLane &f, const uint8_t *srank, int lane)
+{
+    const int k = lane & 3, gshift = lane & ~3;
+    uint32_t x = RANS_L;
+    uint8_t *wp = f.end;
+    const uint32_t q4 = f.n >> 2, r = f.n & 3;
+    const uint32_t steps = f.valid ? q4 + r : 0;
+    const uint32_t len = (k == 3) ? q4 + r : q4, delay = (k == 3) ? 0 : r;
+    const uint32_t pstart = (k == 3) ? f.n - 2 : (k + 1) * q4 - 2;
+    const uint32_t ns = f.nsym;
+    uint32_t l = f.valid ? srank[f.in[pstart + 1]] : 0;
+    uint32_t maxsteps = steps;
+    for (int o = 16; o; o >>= 1) maxsteps = max (maxsteps, __shfl_xor_sync (0xffffffffu, maxsteps, o));
+    uint32_t s = 0;
+    while (s < maxsteps) {
+        const bool active = f.valid && s < steps;
+        // fast region [s, lim): all 4 lanes of every active group regular and not at their final context-0 step:
+        // from s >= r (lanes 0-2 have joined) to steps-1 (exclusive)
+        uint32_t lim = active ? (s >= r ? steps - 1 : 0u) : 0xffffffffu;
+        for (int o = 16; o; o >>= 1) lim = min (lim, __shfl_xor_sync (0xffffffffu, lim, o));
+        if (lim != 0xffffffffu && s + 4 <= lim) {
+            const uint8_t *ip = active ? f.in + (pstart - (s - delay)) : f.in + 3;
+            EncSym e0, e1, e2, e3;
+            #define LOAD_O1() { const uint32_t r0 = srank[__ldg (ip)], r1 = srank[__ldg (ip - 1)], r2 = srank[__ldg (ip - 2)], r3 = srank[__ldg (ip - 3)]; \
+                                e0 = __ldg4 (f.tab + r0 * ns + l); e1 = __ldg4 (f.tab + r1 * ns + r0); e2 = __ldg4 (f.tab + r2 * ns + r1); e3 = __ldg4 (f.tab + r3 * ns + r2); l = r3; }
+            if (active) LOAD_O1 ();
+            for (; s + 4 <= lim; s += 4) {
+                const EncSym c0 = e0, c1 = e1, c2 = e2, c3 = e3;
+                ip -= 4;
+                if (active && s + 8 <= lim) LOAD_O1 ();
+                enc_step (x, wp, c0, active, k, gshift);
+                enc_step (x, wp, c1, active, k, gshift);
+                enc_step (x, wp, c2, active, k, gshift);
+                enc_step (x, wp, c3, active, k, gshift);
+            }
+            #undef LOAD_O1
+        }
+        else {
+            bool act = false; EncSym e; e.x_max = 0xffffffffu; e.rcp = 0; e.bias = 0; e.cmpl_sh = 0;
+            const int t0 = (int)s - (int)delay;
+            if (f.valid && t0 >= 0 && t0 < (int)len) {
+                const uint32_t cr = ((uint32_t)t0 == len - 1) ? srank[0] : srank[f.in[pstart - t0]];
+                act = true; e = __ldg4 (f.tab + cr * ns + l); l = cr;
+            }
+            enc_step (x, wp, e, act, k, gshift);
+            s++;
+        }
+    }
+    if (f.valid) {
+        uint16_t *w = reinterpret_cast<uint16_t *>(wp - 4 * (4 - k));
+        w[0] = (uint16_t)x; w[1] = (uint16_t)(x >> 16);
+    }
+    return f.valid ? (uint32_t)(f.end - wp) + 16 : 0;
+}
+
+__global__ void __launch_bounds__(32) k_rans_encode (const EncLeaf *leaves, EncLeafDyn *dyn, const uint32_t *order_list, const uint2 *jobs, uint32_t n_jobs)
+{
+    extern __shared__ __align__(16) uint8_t s_dyn[];                      // 8 x (EncSym[256] + rank[256])
+    EncSym  (*s_tab)[256]  = reinterpret_cast<EncSym (*)[256]>(s_dyn);
+    uint8_t (*s_rank)[256] = reinterpret_cast<uint8_t (*)[256]>(s_dyn + (size_t)8 * 256 * sizeof (EncSym));
+    if (blockIdx.x >= n_jobs) return;
+    const uint2 job = jobs[blockIdx.x];
+    const int lane = threadIdx.x, grp = lane >> 2, k = lane & 3;
+    EncLane f; f.valid = false; f.in = nullptr; f.tab = nullptr; f.rank = nullptr; f.end = nullptr; f.n = f.nsym = 0;
+    uint32_t li = 0; bool o1 = false;
+    if ((uint32_t)grp < job.y) {
+        li = order_list[job.x + grp];
+        const EncLeaf &L = leaves[li];
+        const EncLeafDyn &D = dyn[li];
+        if (D.eff_n && D.symtab) {
+            f.valid = true; f.in = D.eff_in; f.n = D.eff_n; f.nsym = D.nsym; f.tab = D.symtab; f.rank = D.rank;
+            o1 = D.eff_order;
+            f.end = L.outbuf + (L.out_cap & ~1u);
+        }
+    }
+    for (int g = 0; g < (int)job.y; g++) {                                  // stage rank maps (and O0 tables) in shared memory
+        const bool v = __shfl_sync (0xffffffffu, (int)f.valid, g * 4);
+        if (!v) continue;
+        const bool go1 = __shfl_sync (0xffffffffu, (int)o1, g * 4);
+        const unsigned long long rp = __shfl_sync (0xffffffffu, (unsigned long long)f.rank, g * 4);
+        const unsigned long long tp = __shfl_sync (0xffffffffu, (unsigned long long)f.tab, g * 4);
+        for (int i = lane; i < 256; i += 32) s_rank[g][i] = reinterpret_cast<const uint8_t *>(rp)[i];
+        if (!go1) for (int i = lane; i < 256; i += 32) s_tab[g][i] = reinterpret_cast<const EncSym *>(tp)[i];
+    }
+    __syncwarp ();
+    // a job is planned for one requested order; leaves demoted to order 0 by the "<8 symbols" rule (:1333-1336) run first
+    const bool any_o1 = __any_sync (0xffffffffu, f.valid && o1), any_o0 = __any_sync (0xffffffffu, f.valid && !o1);
+    uint32_t plen = 0;
+    if (any_o0) { EncLane f0 = f; f0.valid = f.valid && !o1; const uint32_t p = encode_o0 (f0, s_tab[grp], lane); if (f0.valid) plen = p; }
+    if (any_o1) { EncLane f1 = f; f1.valid = f.valid && o1;  const uint32_t p = encode_o1 (f1, s_rank[grp], lane); if (f1.valid) plen = p; }
+    if ((uint32_t)grp < job.y && k == 0) dyn[li].payload_len = plen;
+}
+
+void launch_rans_encode (EncPlanDev &P, cudaStream_t st)
+{
+    k_rans_encode<<<P.n_rans_jobs, 32, 8 * (256 * sizeof (EncSym) + 256), st>>>(P.leaves, P.dyn, P.rans_list, P.rans_jobs, P.n_rans_jobs);
+}
+
+// ================================================================================================ decode
+struct DecLane {
+    const uint8_t * __restrict__ body;
+    uint8_t *out;
+    const uint2    *lut;        // O0 (shared memory for single-leaf jobs)
+    const uint32_t * __restrict__ lut1;   // O1 merged LUT
+    const uint8_t  *symof;      // O1 row -> symbol (shared memory)
+    uint32_t n, body_len, shift, row0;
+    bool valid;
+};
+
+__device__ __forceinline__ void dec_renorm (uint32_t &x, uint32_t &poff, bool act, const uint8_t *body, uint32_t body_len, int k, int gshift)
+{
+    const bool need = act && x < RANS_L;
+    const uint32_t g = (__ballot_sync (0xffffffffu, need) >> gshift) & 0xfu;
+    if (need) {
+        const uint32_t a = poff + 2 * __popc (g & ((1u << k) - 1));
+        if (a + 1 < body_len) x = (x << 16) | __ldg (body + a) | (__ldg (body + a + 1) << 8);   // RansDecRenormSafe (rANS_word.h:397-405)
+    }
+    poff += 2 * __popc (g);
+}
+
+template <bool SLUT> __device__ __forceinline__ void decode_o0 (const DecLane &d, const uint2 *slut, uint32_t poff, int lane)
+{
+    const int k = lane & 3, gshift = lane & ~3;
+    uint32_t x = 0;
+    if (d.valid) { const uint8_t *q = d.body + poff + 4 * k; x = q[0] | (q[1] << 8) | (q[2] << 16) | ((uint32_t)q[3] << 24); poff += 16; }
+    const uint32_t steps = d.valid ? (d.n + 3) >> 2 : 0, full = d.valid ? d.n >> 2 : 0;
+    uint32_t maxsteps = steps;
+    for (int o = 16; o; o >>= 1) maxsteps = max (maxsteps, __shfl_xor_sync (0xffffffffu, maxsteps, o));
+    uint8_t *op = d.out + k;
+    uint32_t s = 0;
+    while (s < maxsteps) {
+        const bool active = d.valid && s < steps;
+        uint32_t lim = active ? full : 0xffffffffu;                          // steps in which all 4 lanes of an active group decode
+        for (int o = 16; o; o >>= 1) lim = min (lim, __shfl_xor_sync (0xffffffffu, lim, o));
+        if (lim != 0xffffffffu && s + 4 <= lim) {
+            for (; s + 4 <= lim; s += 4) {
+                #pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    if (active) {
+                        const uint2 e = SLUT ? slut[x & 4095] : __ldg (d.lut + (x & 4095));
+                        x = (e.x >> 16) * (x >> 12) + e.y;
+                        op[4 * t] = (uint8_t)e.x;
+                    }
+                    dec_renorm (x, poff, active, d.body, d.body_len, k, gshift);
+                }
+                op += 16;
+            }
+        }
+        else {
+            const bool act = active && 4 * s + k < d.n;
+            if (act) { const uint2 e = SLUT ? slut[x & 4095] : __ldg (d.lut + (x & 4095)); x = (e.x >> 16) * (x >> 12) + e.y; *op = (uint8_t)e.x; }
+            op += 4;
+            dec_renorm (x, poff, act, d.body, d.body_len, k, gshift);
+            s++;
+        }
+    }
+}
+
+__device__ __forceinline__ void decode_o1 (const DecLane &d, const uint8_t *ssym, uint32_t poff, int lane)
+{
+    const int k = lane & 3, gshift = lane & ~3;
+    uint32_t x = 0;
+    if (d.valid) { const uint8_t *q = d.body + poff + 4 * k; x = q[0] | (q[1] << 8) | (q[2] << 16) | ((uint32_t)q[3] << 24); poff += 16; }
+    const uint32_t q4 = d.n >> 2, r = d.n - 4 * q4;
+    const uint32_t steps = d.valid ? q4 + r : 0;                             // chains 0-2 decode q4 symbols; chain 3 also the remainder (:1076-1083)
+    uint32_t maxsteps = steps;
+    for (int o = 16; o; o >>= 1) maxsteps = max (maxsteps, __shfl_xor_sync (0xffffffffu, maxsteps, o));
+    const uint32_t shift = d.shift, mask = (1u << shift) - 1;
+    uint32_t coff = d.row0 << shift;                                         // LUT row of the previous symbol; context 0 first (:1029)
+    uint8_t *op = d.out + (size_t)k * q4;
+    uint32_t s = 0;
+    while (s < maxsteps) {
+        const bool active = d.valid && s < steps;
+        uint32_t lim = active ? q4 : 0xffffffffu;
+        for (int o = 16; o; o >>= 1) lim = min (lim, __shfl_xor_sync (0xffffffffu, lim, o));
+        if (lim != 0xffffffffu && s + 4 <= lim) {
+            for (; s + 4 <= lim; s += 4) {
+                #pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    if (active) {
+                        const uint32_t m = x & mask;
+                        const uint32_t e = __ldg (d.lut1 + coff + m);
+                        const uint32_t xs = x >> shift;
+                        x = ((e >> 8) & 0xfffu) * xs + (xs + (e >> 20));
+                        coff = (e & 0xffu) << shift;
+                        op[t] = ssym[e & 0xffu];
+                    }
+                    dec_renorm (x, poff, active, d.body, d.body_len, k, gshift);
+                }
+                op += 4;
+            }
+        }
+        else {
+            const bool act = active && (s < q4 || k == 3);
+            if (act) {
+                const uint32_t m = x & mask;
+                const uint32_t e = __ldg (d.lut1 + coff + m);
+                const uint32_t xs = x >> shift;
+                x = ((e >> 8) & 0xfffu) * xs + (xs + (e >> 20));
+                coff = (e & 0xffu) << shift;
+                *op++ = ssym[e & 0xffu];
+            }
+            dec_renorm (x, poff, act, d.body, d.body_len, k, gshift);
+            s++;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(32) k_rans_decode (DecLeaf *leaves, const uint32_t *list, const uint2 *jobs, uint32_t n_jobs)
+{
+    __shared__ uint2 s_lut[4096];                                            // order-0 LUT of a single-leaf job
+    __shared__ uint8_t s_symof[8][256];
+    if (blockIdx.x >= n_jobs) return;
+    const uint2 job = jobs[blockIdx.x];
+    const int lane = threadIdx.x, grp = lane >> 2;
+    DecLane d; d.valid = false; d.body = nullptr; d.out = nullptr; d.lut = nullptr; d.lut1 = nullptr; d.symof = nullptr;
+    d.n = d.body_len = d.row0 = 0; d.shift = 12;
+    bool o1 = false; uint32_t poff = 0;
+    const DecLeaf *Lp = nullptr;
+    if ((uint32_t)grp < job.y) {
+        const DecLeaf &L = leaves[list[job.x + grp]];
+        if (L.valid && !L.err && !L.cat && L.body_ulen && (L.lut || L.lut1)) {
+            d.valid = true; o1 = L.order; d.body = L.body; d.body_len = L.body_len; d.out = L.dst; d.n = L.body_ulen;
+            poff = L.payload_off; d.lut = L.lut; d.lut1 = L.lut1; d.shift = L.shift; d.row0 = L.ctxrank[0];
+            Lp = &L;
+        }
+    }
+    for (int g = 0; g < (int)job.y; g++) {                                  // row -> symbol maps of order-1 leaves
+        const bool v = __shfl_sync (0xffffffffu, (int)(d.valid && o1), g * 4);
+        if (!v) continue;
+        const unsigned long long lp = __shfl_sync (0xffffffffu, (unsigned long long)Lp, g * 4);
+        for (int i = lane; i < 256; i += 32) s_symof[g][i] = reinterpret_cast<const DecLeaf *>(lp)->symof[i];
+    }
+    bool slut = false;
+    if (job.y == 1) {
+        slut = __shfl_sync (0xffffffffu, (int)(d.valid && !o1), 0);
+        if (slut) {
+            const unsigned long long lp = __shfl_sync (0xffffffffu, (unsigned long long)d.lut, 0);
+            for (int i = lane; i < 4096; i += 32) s_lut[i] = reinterpret_cast<const uint2 *>(lp)[i];
+        }
+    }
+    __syncwarp ();
+    const bool any_o1 = __any_sync (0xffffffffu, d.valid && o1), any_o0 = __any_sync (0xffffffffu, d.valid && !o1);
+    if (any_o0) {
+        DecLane d0 = d; d0.valid = d.valid && !o1;
+        if (slut) decode_o0<true> (d0, s_lut, poff, lane); else decode_o0<false> (d0, s_lut, poff, lane);
+    }
+    if (any_o1) { DecLane d1 = d; d1.valid = d.valid && o1; decode_o1 (d1, s_symof[grp & 7], poff, lane); }
+}
+
+void launch_rans_decode (DecPlanDev &P, cudaStream_t st)
+{
+    k_rans_decode<<<P.n_rans_jobs, 32, 0, st>>>(P.leaves, P.rans_list, P.rans_jobs, P.n_rans_jobs);
+}
+
+} // namespace gzb

@@ -31,7 +31,13 @@ def txt_bytes_per_vb(n_reads, read_len):
 
 def synth_vblocks(V, n_reads, read_len, seed, device):
     """Synthetic Illumina-like VBlocks generated on the device: returns dict of uint8 device tensors
-    [V, ...]: seq, qual (fixed-length lines), and the read-name context streams."""
+    [V, ...]: seq, qual (fixed-length lines), and the read-name context streams.  Generated in chunks of 8 VBlocks
+    (torch's samplers index with 32 bits)."""
+    parts = [_synth_chunk(min(8, V - v0), n_reads, read_len, seed * 100003 + v0, device) for v0 in range(0, V, 8)]
+    return {k: torch.cat([p[k] for p in parts], 0).contiguous() for k in parts[0]}
+
+
+def _synth_chunk(V, n_reads, read_len, seed, device):
     g = torch.Generator(device=device); g.manual_seed(seed)
     n = n_reads * read_len
     acgt = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
@@ -45,11 +51,13 @@ def synth_vblocks(V, n_reads, read_len, seed, device):
     idx = torch.where(change, torch.arange(n, device=device).expand(V, n), torch.zeros((), dtype=torch.long, device=device))
     last = torch.cummax(idx, dim=1).values
     qual = syms[torch.gather(pick, 1, last)]
+    del pick, change, idx, last
     # ~3% diverse lines
     q2 = qual.view(V, n_reads, read_len)
     div = torch.rand((V, n_reads), generator=g, device=device) < 0.03
-    noise = syms[torch.multinomial(torch.tensor([.4, .3, .2, .1], device=device), V * n_reads * read_len, replacement=True, generator=g).view(V, n_reads, read_len)]
-    q2[div] = noise[div]
+    nd = int(div.sum().item())
+    if nd:
+        q2[div] = syms[torch.multinomial(torch.tensor([.4, .3, .2, .1], device=device), nd * read_len, replacement=True, generator=g).view(nd, read_len)]
     # read-name contexts: tile (b250, long runs), x / y (uint32 big-endian locals), misc b250
     tile = (torch.arange(n_reads, device=device) // 977 % 96).to(torch.uint8).expand(V, n_reads).contiguous()
     xs = (torch.cumsum(torch.randint(0, 60, (V, n_reads), generator=g, device=device), 1) % 30000 + 1000).to(torch.int32)
