@@ -315,27 +315,6 @@ __global__ void __launch_bounds__(256) k_dec_tables (DecLeaf *leaves, SectionRes
 }
 
 // ------------------------------------------------------------------------------------------------ arithmetic decoder
-struct RCDec { uint32_t code, range; const uint8_t *in, *end; };
-
-__device__ __forceinline__ uint32_t model_decode (uint32_t *m, RCDec &rc)  // c_simple_model.h:148-179 + RC_GetFreq/RC_Decode
-{
-    const uint32_t tot = m[0];
-    const uint32_t freq = (tot && rc.range >= tot) ? rc.code / (rc.range /= tot) : 0;
-    if (freq > AR_MAXF) return 0;
-    uint32_t e, acc;
-    const uint32_t i = ar_find_freq (m, freq, e, acc);
-    if (!i) return 0;                                                     // ran off the live entries: corrupt stream
-    rc.code  -= acc * rc.range;
-    rc.range *= e & 0xffffu;
-    ar_model_bump (m, i, e, tot);
-    while (rc.range < (1u << 24)) {
-        if (rc.in >= rc.end) break;
-        rc.code = (rc.code << 8) + *rc.in++;
-        rc.range <<= 8;
-    }
-    return e >> 16;
-}
-
 __global__ void k_arith_dec_init (DecLeaf *leaves, uint32_t n_slots, Arena arena)
 {
     if (blockIdx.x >= n_slots) return;
@@ -348,37 +327,6 @@ __global__ void k_arith_dec_init (DecLeaf *leaves, uint32_t n_slots, Arena arena
     if (!s_m) return;
     for (uint32_t c = threadIdx.x; c < nctx; c += blockDim.x) ar_model_init (s_m + c * stride, maxs);
     if (L.rle) for (uint32_t c = threadIdx.x; c < 258; c += blockDim.x) ar_model_init (s_m + nctx * stride + c * AR_RUN_STRIDE, 4);
-}
-
-__global__ void k_arith_decode (DecLeaf *leaves, const uint32_t *list, uint32_t n_list, int lpw)
-{
-    const int lane = threadIdx.x & 31;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (lane >= lpw) return;
-    const uint32_t slot = warp * lpw + lane;
-    if (slot >= n_list) return;
-    DecLeaf &L = leaves[list[slot]];
-    if (!L.valid || L.err || L.cat || !L.body_ulen || !L.models) return;
-    const uint32_t n = L.body_ulen, maxs = L.nsym, stride = ar_stride (maxs);
-    const bool o1 = L.order == 1, rle = L.rle;
-    uint32_t *lit = L.models, *run = lit + (o1 ? 256 : 1) * stride;
-    uint8_t *out = L.dst;
-    RCDec rc; rc.range = 0xffffffffu; rc.code = 0; rc.in = L.body + 1; rc.end = L.body + L.body_len;
-    if (rc.in + 5 > rc.end) rc.in = rc.end;                               // RC_StartDecode (c_range_coder.h:57-68)
-    else for (int i = 0; i < 5; i++) rc.code = (rc.code << 8) | *rc.in++;
-    uint32_t last = 0;
-    for (uint32_t i = 0; i < n; i++) {
-        uint32_t s = model_decode (lit + (o1 ? last : 0) * stride, rc);
-        out[i] = (uint8_t)s; last = s;
-        if (!rle) continue;
-        uint32_t r = 0, part, rctx = last;                                // arith_dynamic.c:473-482 / :591-599
-        do {
-            part = model_decode (run + rctx * AR_RUN_STRIDE, rc);
-            if (rctx == last) rctx = 256; else rctx += (rctx < 257);
-            r += part;
-        } while (part == 3 && r < n);
-        while (r-- && i + 1 < n) out[++i] = (uint8_t)last;
-    }
 }
 
 // ------------------------------------------------------------------------------------------------ post passes
@@ -440,11 +388,7 @@ void dec_run (DecPlanDev &P, cudaStream_t st)
     cudaEventRecord (P.ev_chain0, st);
     if (P.n_rans_jobs) { launch_rans_decode (P, st); P.launches++; }
     cudaEventRecord (P.ev_chain1, st);
-    if (P.n_arith) {
-        int lpw = P.arith_lpw;
-        uint32_t warps = (P.n_arith + lpw - 1) / lpw;
-        LAUNCH (k_arith_decode, (warps + 3) / 4, 128, P.leaves, P.arith_list, P.n_arith, lpw);
-    }
+    if (P.n_arith) { launch_arith_decode (P, st); P.launches++; }
     cudaEventRecord (P.ev_chain2, st);
     dim3 g (nslots, P.parts), gs (ns, P.parts);
     LAUNCH (k_dec_cat, g, 256, P.leaves, nslots);

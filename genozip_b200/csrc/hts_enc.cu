@@ -562,34 +562,6 @@ __global__ void __launch_bounds__(256) k_tables (const EncLeaf *leaves, EncLeafD
 // ------------------------------------------------------------------------------------------------ adaptive arithmetic coder
 // Model layout per context (words): [0] TotFreq, [1] sentinel, [2 .. 2+maxs) entries (freq | symbol<<16), then a zero
 // terminator — the reference's SIMPLE_MODEL (c_simple_model.h:77-103) restricted to the live entries.
-struct RCEnc { uint32_t low, range, ffnum, cache, carry; uint8_t *out; };
-
-__device__ __forceinline__ void rc_shift_low (RCEnc &rc)                   // c_range_coder.h:70-88
-{
-    if (rc.low < (255u << 24) || rc.carry) {
-        *rc.out++ = (uint8_t)(rc.cache + rc.carry);
-        while (rc.ffnum) { *rc.out++ = (uint8_t)(rc.carry - 1); rc.ffnum--; }
-        rc.cache = rc.low >> 24;
-        rc.carry = 0;
-    }
-    else rc.ffnum++;
-    rc.low <<= 8;
-}
-
-__device__ __forceinline__ void model_encode (uint32_t *m, RCEnc &rc, uint32_t sym)   // c_simple_model.h:123-146 + RC_Encode :97-109
-{
-    uint32_t e, acc;
-    const uint32_t tot = m[0];
-    const uint32_t i = ar_find_sym (m, sym, e, acc);
-    const uint32_t before = rc.low;
-    rc.range /= tot;
-    rc.low   += acc * rc.range;
-    rc.range *= e & 0xffffu;
-    rc.carry += rc.low < before;
-    ar_model_bump (m, i, e, tot);
-    while (rc.range < (1u << 24)) { rc.range <<= 8; rc_shift_low (rc); }
-}
-
 // model initialisation for all arithmetic leaves: one CTA per leaf
 __global__ void k_arith_init (const EncLeaf *leaves, EncLeafDyn *dyn, const uint32_t *list, uint32_t n_list, Arena arena)
 {
@@ -615,52 +587,6 @@ __global__ void k_arith_init (const EncLeaf *leaves, EncLeafDyn *dyn, const uint
         uint32_t *run = lit + nctx * stride;
         for (uint32_t c = threadIdx.x; c < 258; c += blockDim.x) ar_model_init (run + c * AR_RUN_STRIDE, 4);
     }
-}
-
-// one lane per leaf; lpw leaves per warp
-__global__ void k_arith_encode (const EncLeaf *leaves, EncLeafDyn *dyn, const uint32_t *list, uint32_t n_list, int lpw)
-{
-    const int lane = threadIdx.x & 31;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (lane >= lpw) return;
-    const uint32_t slot = warp * lpw + lane;
-    if (slot >= n_list) return;
-    const uint32_t li = list[slot];
-    const EncLeaf &L = leaves[li];
-    EncLeafDyn &D = dyn[li];
-    const uint32_t n = D.eff_n, maxs = D.nsym, stride = ar_stride (maxs);
-    const uint8_t *in = D.eff_in;
-    const bool o1 = D.eff_order, rle = (D.hdr[0] & F_RLE) != 0;
-    uint32_t *lit = D.models, *run = lit + (o1 ? 256 : 1) * stride;
-    uint8_t *out = L.outbuf;
-    if (!lit) return;
-    out[0] = (uint8_t)maxs;                                               // arith_dynamic.c:105-110 (256 wraps to 0)
-    RCEnc rc; rc.low = 0; rc.range = 0xffffffffu; rc.ffnum = 0; rc.cache = 0; rc.carry = 0; rc.out = out + 1;
-    // A body that reaches the input length is discarded for a raw copy (arith_dynamic.c:847-852), so encoding stops
-    // as soon as that is certain; this also bounds the scratch a hostile (expanding) input can touch.
-    const uint8_t *limit = out + n + 8;
-    bool expanded = false;
-    uint32_t last = 0;
-    for (uint32_t i = 0; i < n; ) {
-        if (rc.out + rc.ffnum > limit) { expanded = true; break; }
-        uint32_t s = in[i];
-        model_encode (lit + (o1 ? last : 0) * stride, rc, s);
-        last = s; i++;
-        if (!rle) continue;
-        uint32_t r = 0;                                                   // :413-438 run length in base-4 digits
-        while (i < n && in[i] == last) { r++; i++; }
-        uint32_t rctx = last;
-        do {
-            uint32_t c = r < 4 ? r : 3;
-            model_encode (run + rctx * AR_RUN_STRIDE, rc, c);
-            r -= c;
-            if (rctx == last) rctx = 256; else rctx += (rctx < 257);
-            if (c == 3 && r == 0) model_encode (run + rctx * AR_RUN_STRIDE, rc, 0);
-        } while (r);
-    }
-    if (!expanded) for (int i = 0; i < 5; i++) rc_shift_low (rc);         // RC_FinishEncode
-    D.tab_len = expanded ? n + 1 : (uint32_t)(rc.out - out);              // whole body at the front of outbuf
-    D.payload_len = 0;
 }
 
 // ------------------------------------------------------------------------------------------------ leaf / section finalisation
@@ -776,11 +702,7 @@ void enc_run (EncPlanDev &P, cudaStream_t st)
     cudaEventRecord (P.ev_chain0, st);
     if (P.n_rans_jobs) { launch_rans_encode (P, st); P.launches++; }
     cudaEventRecord (P.ev_chain1, st);
-    if (P.n_arith) {
-        int lpw = P.arith_lpw;
-        uint32_t warps = (P.n_arith + lpw - 1) / lpw;
-        LAUNCH (k_arith_encode, (warps + 3) / 4, 128, P.leaves, P.dyn, P.arith_list, P.n_arith, lpw);
-    }
+    if (P.n_arith) { launch_arith_encode (P, st); P.launches++; }
     cudaEventRecord (P.ev_chain2, st);
     LAUNCH (k_leaf_final, (nl + 127) / 128, 128, P.leaves, P.dyn, nl);
     LAUNCH (k_section_final, (ns + 127) / 128, 128, P.sections, P.leaves, P.dyn, P.results, P.segs, P.stripe_hdr, ns);

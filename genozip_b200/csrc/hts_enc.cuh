@@ -41,5 +41,7 @@ void enc_run (EncPlanDev &P, cudaStream_t st);
 void dec_run (DecPlanDev &P, cudaStream_t st);
 void launch_rans_encode (EncPlanDev &P, cudaStream_t st);
 void launch_rans_decode (DecPlanDev &P, cudaStream_t st);
+void launch_arith_encode (EncPlanDev &P, cudaStream_t st);
+void launch_arith_decode (DecPlanDev &P, cudaStream_t st);
 
 } // namespace gzb
