@@ -47,6 +47,12 @@ class DomqPizVb(C.Structure):       # gzb_domq_piz_vb
                 ("line_len", C.c_void_p), ("n_lines", C.c_uint32), ("out", C.c_void_p), ("out_cap", C.c_uint64)]
 
 
+class LongrVb(C.Structure):         # gzb_longr_vb
+    _fields_ = [("txt", C.c_void_p), ("txt_len", C.c_uint64), ("seq_off", C.c_void_p), ("qual_off", C.c_void_p),
+                ("len", C.c_void_p), ("is_rev", C.c_void_p), ("n_lines", C.c_uint32), ("value_to_bin", C.c_uint8 * 256),
+                ("values", C.c_void_p), ("lens_be", C.c_void_p), ("qual_out", C.c_void_p)]
+
+
 _lib = None
 
 
@@ -89,6 +95,15 @@ def load():
     for nm in ("gzb_domq_prepare", "gzb_domq_split"):
         getattr(L, nm).restype = C.c_int
         getattr(L, nm).argtypes = [C.c_void_p, C.POINTER(DomqVb), C.c_uint32, C.c_uint32]
+    L.gzb_pbwt_encode.restype = C.c_int
+    L.gzb_pbwt_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32),
+                                  C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32]
+    L.gzb_pbwt_decode.restype = C.c_int
+    L.gzb_pbwt_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64,
+                                  C.POINTER(C.c_uint64), C.c_uint32]
+    for nm in ("gzb_longr_encode", "gzb_longr_decode"):
+        getattr(L, nm).restype = C.c_int
+        getattr(L, nm).argtypes = [C.c_void_p, C.POINTER(LongrVb), C.c_uint32, C.c_uint32]
     L.gzb_domq_reconstruct.restype = C.c_int
     L.gzb_domq_reconstruct.argtypes = [C.c_void_p, C.POINTER(DomqPizVb), C.c_uint32, C.c_uint32]
     _lib = L
@@ -276,3 +291,60 @@ class Engine:
         if rc != 0:
             raise GzbError(f"gzb_domq_reconstruct failed ({rc}): {self._err()}")
         return [o[:-1] for o in outs]
+
+    # ---- PBWT (host buffers) ----
+    def pbwt_encode(self, ht):
+        """codec_pbwt_compress: uint8 matrix [n_lines, ht_per_line] -> (RUNS u32, FGRC u32), host-endian"""
+        ht = np.ascontiguousarray(ht, dtype=np.uint8)
+        n_lines, w = ht.shape
+        runs = np.zeros(2 * ht.size + 8, np.uint32); fgrc = np.zeros(ht.size + 8, np.uint32)
+        nr, nf = C.c_uint32(), C.c_uint32()
+        rc = self.L.gzb_pbwt_encode(self.h, ht.ctypes.data, n_lines, w, runs.ctypes.data, runs.size, C.byref(nr),
+                                    fgrc.ctypes.data, fgrc.size, C.byref(nf), 0)
+        if rc != 0:
+            raise GzbError(f"gzb_pbwt_encode failed ({rc}): {self._err()}")
+        return runs[:nr.value].copy(), fgrc[:nf.value].copy()
+
+    def pbwt_decode(self, runs, fgrc, n_lines, size):
+        runs = np.ascontiguousarray(runs, np.uint32); fgrc = np.ascontiguousarray(fgrc, np.uint32)
+        ht = np.zeros(size, np.uint8)
+        hl = C.c_uint64()
+        rc = self.L.gzb_pbwt_decode(self.h, runs.ctypes.data, runs.size, fgrc.ctypes.data, fgrc.size, n_lines, ht.ctypes.data, size, C.byref(hl), 0)
+        if rc != 0:
+            raise GzbError(f"gzb_pbwt_decode failed ({rc}): {self._err()}")
+        return ht[:hl.value]
+
+    # ---- LONGR (host buffers), batch of VBlocks: each (txt, seq_off, qual_off, lens, is_rev|None, value_to_bin) ----
+    def _longr_arr(self, vbs, values=None, lens_be=None, decode=False):
+        n = len(vbs)
+        arr = (LongrVb * n)()
+        keep = []
+        for i, (txt, seq_off, qual_off, lens, is_rev, v2b) in enumerate(vbs):
+            txt = np.ascontiguousarray(txt, np.uint8); seq_off = np.ascontiguousarray(seq_off, np.uint64)
+            qual_off = np.ascontiguousarray(qual_off, np.uint64); lens = np.ascontiguousarray(lens, np.uint32)
+            tot = int(lens.sum())
+            vals = np.zeros(tot + 1, np.uint8) if values is None else np.ascontiguousarray(values[i], np.uint8)
+            lb = np.zeros(65536, np.uint32) if lens_be is None else np.ascontiguousarray(lens_be[i], np.uint32)
+            qo = np.zeros(tot + 1, np.uint8)
+            rv = None if is_rev is None else np.ascontiguousarray(is_rev, np.uint8)
+            keep.append((txt, seq_off, qual_off, lens, rv, vals, lb, qo))
+            a = arr[i]
+            a.txt = txt.ctypes.data; a.txt_len = txt.size; a.seq_off = seq_off.ctypes.data; a.qual_off = qual_off.ctypes.data
+            a.len = lens.ctypes.data; a.is_rev = None if rv is None else rv.ctypes.data; a.n_lines = lens.size
+            C.memmove(a.value_to_bin, np.ascontiguousarray(v2b, np.uint8).ctypes.data, 256)
+            a.values = vals.ctypes.data; a.lens_be = lb.ctypes.data; a.qual_out = qo.ctypes.data
+        return arr, keep
+
+    def longr_encode(self, vbs):
+        arr, keep = self._longr_arr(vbs)
+        rc = self.L.gzb_longr_encode(self.h, arr, len(vbs), 0)
+        if rc != 0:
+            raise GzbError(f"gzb_longr_encode failed ({rc}): {self._err()}")
+        return [(k[5][:int(k[3].sum())].copy(), k[6].copy()) for k in keep]
+
+    def longr_decode(self, vbs, values, lens_be):
+        arr, keep = self._longr_arr(vbs, values, lens_be, decode=True)
+        rc = self.L.gzb_longr_decode(self.h, arr, len(vbs), 0)
+        if rc != 0:
+            raise GzbError(f"gzb_longr_decode failed ({rc}): {self._err()}")
+        return [k[7][:int(k[3].sum())].copy() for k in keep]
