@@ -24,6 +24,16 @@ __device__ __forceinline__ uint32_t div_small (uint32_t a, uint32_t d)
     return q;
 }
 
+// exact 32-bit division whose QUOTIENT is small (< 2^17): RC_GetFreq's code / range (c_range_coder.h:111-114)
+__device__ __forceinline__ uint32_t div_smallq (uint32_t a, uint32_t d)
+{
+    const float rd = __frcp_rd (__uint2float_ru (d));
+    uint32_t q = __float2uint_rz (__fmul_rz (__uint2float_rz (a), rd));
+    uint32_t r = a - q * d;
+    while (r >= d) { q++; r -= d; }
+    return q;
+}
+
 // ---- warp-wide model access -------------------------------------------------------------------------------------
 // find `sym`: returns the model word index of its entry, its value in e and the cumulative frequency before it in acc
 __device__ __forceinline__ uint32_t warp_find_sym (const uint32_t *m, uint32_t maxs, uint32_t sym, int lane, uint32_t &e, uint32_t &acc)
@@ -112,9 +122,14 @@ __device__ __forceinline__ void rc_shift_low (RCEnc &rc, int lane)          // c
 
 __device__ __forceinline__ void warp_encode (uint32_t *m, uint32_t maxs, RCEnc &rc, uint32_t sym, int lane)   // :123-146 + RC_Encode :97-109
 {
-    uint32_t e, acc;
+    uint32_t e, acc, i;
     const uint32_t tot = m[0];
-    const uint32_t i = warp_find_sym (m, maxs, sym, lane, e, acc);
+    const uint4 v = *reinterpret_cast<const uint4 *>(m + 4);              // the model is approximately sorted by frequency: the
+    if      ((v.x >> 16) == sym && maxs > 0) { e = v.x; acc = 0; i = 4; }   // symbol is almost always among the first four entries
+    else if ((v.y >> 16) == sym && maxs > 1) { e = v.y; acc = v.x & 0xffffu; i = 5; }
+    else if ((v.z >> 16) == sym && maxs > 2) { e = v.z; acc = (v.x & 0xffffu) + (v.y & 0xffffu); i = 6; }
+    else if ((v.w >> 16) == sym && maxs > 3) { e = v.w; acc = (v.x & 0xffffu) + (v.y & 0xffffu) + (v.z & 0xffffu); i = 7; }
+    else i = warp_find_sym (m, maxs, sym, lane, e, acc);
     const uint32_t before = rc.low;
     rc.range = div_small (rc.range, tot);
     rc.low   += acc * rc.range;
@@ -181,10 +196,19 @@ __device__ __forceinline__ uint32_t warp_decode (uint32_t *m, uint32_t maxs, RCD
 {
     const uint32_t tot = m[0];
     uint32_t freq = 0;
-    if (tot && rc.range >= tot) { rc.range = div_small (rc.range, tot); freq = rc.code / rc.range; }   // RC_GetFreq (c_range_coder.h:111-114)
+    if (tot && rc.range >= tot) {                                           // RC_GetFreq (c_range_coder.h:111-114)
+        rc.range = div_small (rc.range, tot);
+        freq = (rc.code >> 17) >= rc.range ? rc.code / rc.range : div_smallq (rc.code, rc.range);   // quotient < 2^17 for any valid stream
+    }
     if (freq > AR_MAXF) return 0;
-    uint32_t e, acc;
-    const uint32_t i = warp_find_freq (m, maxs, freq, lane, e, acc);
+    uint32_t e, acc, i;
+    const uint4 v = *reinterpret_cast<const uint4 *>(m + 4);
+    const uint32_t c0 = v.x & 0xffffu, c1 = c0 + (v.y & 0xffffu), c2 = c1 + (v.z & 0xffffu), c3 = c2 + (v.w & 0xffffu);
+    if      (c0 > freq && maxs > 0) { e = v.x; acc = 0;  i = 4; }
+    else if (c1 > freq && maxs > 1) { e = v.y; acc = c0; i = 5; }
+    else if (c2 > freq && maxs > 2) { e = v.z; acc = c1; i = 6; }
+    else if (c3 > freq && maxs > 3) { e = v.w; acc = c2; i = 7; }
+    else i = warp_find_freq (m, maxs, freq, lane, e, acc);
     if (!i) return 0;
     rc.code  -= acc * rc.range;
     rc.range *= e & 0xffffu;

@@ -385,11 +385,18 @@ void dec_run (DecPlanDev &P, cudaStream_t st)
     LAUNCH (k_dec_parse, (ns + 127) / 128, 128, P.sections, P.leaves, P.results, ns);
     if (P.n_rans)  LAUNCH (k_dec_tables, nslots, 256, P.leaves, P.results, nslots, P.arena);
     if (P.n_arith) LAUNCH (k_arith_dec_init, nslots, 256, P.leaves, nslots, P.arena);
+    // The rANS and the arithmetic leaves are independent and both kernels are latency-bound (a handful of warps per SM),
+    // so they run concurrently: the arithmetic kernel is forked onto the engine's second stream and joined afterwards.
     cudaEventRecord (P.ev_chain0, st);
+    if (P.n_arith) {
+        cudaStreamWaitEvent (P.st2, P.ev_chain0, 0);
+        cudaEventRecord (P.ev_arith0, P.st2);
+        launch_arith_decode (P, P.st2); P.launches++;
+        cudaEventRecord (P.ev_chain2, P.st2);
+    }
     if (P.n_rans_jobs) { launch_rans_decode (P, st); P.launches++; }
     cudaEventRecord (P.ev_chain1, st);
-    if (P.n_arith) { launch_arith_decode (P, st); P.launches++; }
-    cudaEventRecord (P.ev_chain2, st);
+    if (P.n_arith) cudaStreamWaitEvent (st, P.ev_chain2, 0);
     dim3 g (nslots, P.parts), gs (ns, P.parts);
     LAUNCH (k_dec_cat, g, 256, P.leaves, nslots);
     LAUNCH (k_dec_unpack, g, 256, P.leaves, P.results, nslots);

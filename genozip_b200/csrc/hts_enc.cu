@@ -699,11 +699,18 @@ void enc_run (EncPlanDev &P, cudaStream_t st)
         LAUNCH (k_tables, P.n_rans, 256, P.leaves, P.dyn, P.rans_list, P.n_rans);
     }
     if (P.n_arith) LAUNCH (k_arith_init, P.n_arith, 256, P.leaves, P.dyn, P.arith_list, P.n_arith, P.arena);
+    // The rANS and the arithmetic leaves are independent and both kernels are latency-bound (a handful of warps per SM),
+    // so they run concurrently: the arithmetic kernel is forked onto the engine's second stream and joined afterwards.
     cudaEventRecord (P.ev_chain0, st);
+    if (P.n_arith) {
+        cudaStreamWaitEvent (P.st2, P.ev_chain0, 0);
+        cudaEventRecord (P.ev_arith0, P.st2);
+        launch_arith_encode (P, P.st2); P.launches++;
+        cudaEventRecord (P.ev_chain2, P.st2);
+    }
     if (P.n_rans_jobs) { launch_rans_encode (P, st); P.launches++; }
     cudaEventRecord (P.ev_chain1, st);
-    if (P.n_arith) { launch_arith_encode (P, st); P.launches++; }
-    cudaEventRecord (P.ev_chain2, st);
+    if (P.n_arith) cudaStreamWaitEvent (st, P.ev_chain2, 0);
     LAUNCH (k_leaf_final, (nl + 127) / 128, 128, P.leaves, P.dyn, nl);
     LAUNCH (k_section_final, (ns + 127) / 128, 128, P.sections, P.leaves, P.dyn, P.results, P.segs, P.stripe_hdr, ns);
     dim3 g (ns * SEGS_PER_SECTION, P.copy_parts);

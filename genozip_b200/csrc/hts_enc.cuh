@@ -19,7 +19,8 @@ struct EncPlanDev {              // device pointers of one encode batch
     Arena          arena;
     int            rans_gpw, arith_lpw, copy_parts;
     bool           any_pack, any_o1;
-    cudaEvent_t    ev_chain0, ev_chain1, ev_chain2;
+    cudaEvent_t    ev_chain0, ev_chain1, ev_chain2, ev_arith0;   // rANS kernel: chain0..chain1 on the main stream; arithmetic: arith0..chain2 on st2
+    cudaStream_t   st2;
     uint64_t       launches;
 };
 
@@ -32,7 +33,8 @@ struct DecPlanDev {
     SectionResult *results;
     Arena          arena;
     int            rans_gpw, arith_lpw, parts;
-    cudaEvent_t    ev_chain0, ev_chain1, ev_chain2;
+    cudaEvent_t    ev_chain0, ev_chain1, ev_chain2, ev_arith0;
+    cudaStream_t   st2;
     uint64_t       launches;
 };
 
