@@ -26,7 +26,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gzb200", choices=["gzb200", "reference"])
-    ap.add_argument("--vblocks", type=int, default=int(os.environ.get("GZB_BENCH_VBLOCKS", "32")), help="VBlocks per GPU per step")
+    ap.add_argument("--vblocks", type=int, default=int(os.environ.get("GZB_BENCH_VBLOCKS", "0")),
+                    help="VBlocks per GPU per step (0 = as many as fit, at most 256: the chain kernels are latency-bound, so throughput grows with the batch)")
     ap.add_argument("--reads", type=int, default=92000, help="reads per VBlock (92,000 x 150 bp ~ 32 MB of FASTQ text)")
     ap.add_argument("--read-len", type=int, default=150)
     ap.add_argument("--no-e2e", action="store_true")
@@ -199,6 +200,12 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     eng = Engine(local)
     V = args.vblocks
+    if V <= 0:                                                  # BASELINE configs[1] is ~390 VBlocks per GPU; take what fits comfortably
+        free_b, _ = torch.cuda.mem_get_info(dev)
+        per_vb = 13.5 * args.reads * args.read_len + (64 << 20)   # inputs, DOMQ/ACGT intermediates, sections, outputs, engine workspace
+        V = int(max(8, min(256, (0.80 * free_b) // per_vb)))
+        if world > 1:
+            t = torch.tensor([V], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MIN); V = int(t.item())
     path = FastqCodecPath(eng, V, args.reads, args.read_len)
     # VBlocks are sharded round-robin by vblock_i: rank r owns vblock_i = r+1, r+1+world, ...  Seeds follow vblock_i.
     data = synth_vblocks(V, args.reads, args.read_len, 1000 + rank, dev)
@@ -209,10 +216,9 @@ def run_gpu(args):
     if rank == 0:
         os.makedirs(os.path.dirname(CODEC_CACHE), exist_ok=True)
         json.dump(codecs, open(CODEC_CACHE, "w"))
-    path.alloc_piz()
-
     # correctness gate before timing: piz(zip(x)) == x on the device
     meta = path.zip_device(data)
+    path.alloc_piz(meta)
     path.piz_device(meta)
     torch.cuda.synchronize()
     assert torch.equal(path.seq_out_d, data["seq"]) and torch.equal(path.qual_out_d, data["qual"]), "round trip failed"

@@ -132,9 +132,14 @@ class FastqCodecPath:
             return self.x_d[v]
         return data[s][v]
 
-    def _alloc_comp(self):
+    def _stream_cap(self, s, meta):
+        """capacity for stream s: 25% above the longest instance in this batch (the data of a step does not change)"""
+        longest = max(m["len"][s] for m in meta)
+        return min(self.caps[s], int(longest * 1.25) + 4096)
+
+    def _alloc_comp(self, meta):
         for s in STREAMS:
-            cap = max(est_size(c, self.caps[s]) for c in SIMPLE)
+            cap = est_size(self.codec[s], self._stream_cap(s, meta))
             if s not in self.comp_d or self.comp_d[s].shape[1] < cap:
                 self.comp_d[s] = torch.empty((self.V, cap), dtype=torch.uint8, device=self.dev)
 
@@ -167,7 +172,7 @@ class FastqCodecPath:
         self.meta = meta
         if only_vb0_streams:
             return meta
-        self._alloc_comp()
+        self._alloc_comp(meta)
         secs, idx = self._sections(meta, lambda s, v: self._stream_dev_tensor(s, v, data).data_ptr(), lambda s, v: self.comp_d[s][v].data_ptr(), 0)
         self.eng.compress_raw(secs, len(idx), GZB_DEVICE_PTRS)
         self._collect(secs, idx, meta)
@@ -191,9 +196,9 @@ class FastqCodecPath:
             meta[v]["comp_len"][s] = secs[i].out_len
 
     # ------------------------------------------------------------------ PIZ, inputs resident in HBM
-    def alloc_piz(self):
+    def alloc_piz(self, meta):
         u8 = dict(dtype=torch.uint8, device=self.dev)
-        self.dec_d = {s: torch.empty((self.V, self.caps[s] + 16), **u8) for s in STREAMS}
+        self.dec_d = {s: torch.empty((self.V, self._stream_cap(s, meta) + 16), **u8) for s in STREAMS}
         self.seq_out_d = torch.empty((self.V, self.n), **u8)
         self.qual_out_d = torch.empty((self.V, self.n), **u8)
 
@@ -240,7 +245,7 @@ class FastqCodecPath:
             return max([est_size(self.codec[s], l) for l in lens] + [4096])
         self.h["comp"] = {s: hp(V, comp_cap(s)) for s in STREAMS}
         self.h["seq_out"] = hp(V, n); self.h["qual_out"] = hp(V, n)
-        self.h["dec"] = {s: hp(V, self.caps[s] + 16) for s in ("NONREF_X", "Q_TILE", "Q_X", "Q_Y", "Q_MISC")}
+        self.h["dec"] = {s: hp(V, self.dec_d[s].shape[1]) for s in ("NONREF_X", "Q_TILE", "Q_X", "Q_Y", "Q_MISC")}
 
     def zip_host(self):
         """host buffers in, host buffers out; the DOMQ streams stay on the device between codec_domq_compress and
