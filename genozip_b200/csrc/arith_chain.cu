@@ -12,10 +12,18 @@
 
 namespace gzb {
 
+// 1/x rounded safely DOWN: MUFU.RCP (<= 1 ulp, one instruction) scaled by (1 - 5e-7); relative deficit < 7e-7
+__device__ __forceinline__ float rcp_below (float x)
+{
+    float r;
+    asm ("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return __fmul_rz (r, 0.9999995f);
+}
+
 // exact 32-bit division by a divisor < 2^17: float estimates that never exceed the truth + small corrections
 __device__ __forceinline__ uint32_t div_small (uint32_t a, uint32_t d)
 {
-    const float rd = __frcp_rd (__uint2float_ru (d));
+    const float rd = rcp_below (__uint2float_ru (d));
     uint32_t q = __float2uint_rz (__fmul_rz (__uint2float_rz (a), rd));
     uint32_t r = a - q * d;
     const uint32_t q2 = __float2uint_rz (__fmul_rz (__uint2float_rz (r), rd));
@@ -27,7 +35,7 @@ __device__ __forceinline__ uint32_t div_small (uint32_t a, uint32_t d)
 // exact 32-bit division whose QUOTIENT is small (< 2^17): RC_GetFreq's code / range (c_range_coder.h:111-114)
 __device__ __forceinline__ uint32_t div_smallq (uint32_t a, uint32_t d)
 {
-    const float rd = __frcp_rd (__uint2float_ru (d));
+    const float rd = rcp_below (__uint2float_ru (d));
     uint32_t q = __float2uint_rz (__fmul_rz (__uint2float_rz (a), rd));
     uint32_t r = a - q * d;
     while (r >= d) { q++; r -= d; }
@@ -235,10 +243,18 @@ __global__ void __launch_bounds__(128) k_arith_decode (DecLeaf *leaves, const ui
     RCDec rc; rc.range = 0xffffffffu; rc.code = 0; rc.in = L.body + 1; rc.end = L.body + L.body_len;
     if (rc.in + 5 > rc.end) rc.in = rc.end;                               // RC_StartDecode (c_range_coder.h:57-68)
     else for (int i = 0; i < 5; i++) rc.code = (rc.code << 8) | *rc.in++;
-    uint32_t last = 0;
-    for (uint32_t i = 0; i < n; i++) {
+    // Output bytes are gathered in a 32-bit window and written one aligned word at a time (a byte store per symbol from
+    // hundreds of concurrent leaves is what the L2 write path chokes on); head and tail bytes go out singly.
+    uint32_t last = 0, win = 0;
+    const uint32_t head_end = (uint32_t)((4 - ((uintptr_t)out & 3)) & 3);   // bytes before the first aligned word are stored singly
+    #define PUT_BYTE(idx, b) do { win = (win >> 8) | ((uint32_t)(b) << 24); \
+        if (lane == 0) { const uintptr_t A = reinterpret_cast<uintptr_t>(out + (idx)); \
+                         if ((A & 3) == 3 && (idx) >= 3) *reinterpret_cast<uint32_t *>(A - 3) = win; \
+                         else if ((idx) < head_end) out[idx] = (uint8_t)(b); } } while (0)
+    uint32_t i = 0;
+    for (; i < n; i++) {
         const uint32_t s = warp_decode (lit + (o1 ? last : 0) * stride, maxs, rc, lane);
-        if (lane == 0) out[i] = (uint8_t)s;
+        PUT_BYTE (i, s);
         last = s;
         if (!rle) continue;
         uint32_t r = 0, part, rctx = last;                                // arith_dynamic.c:473-482 / :591-599
@@ -247,7 +263,12 @@ __global__ void __launch_bounds__(128) k_arith_decode (DecLeaf *leaves, const ui
             if (rctx == last) rctx = 256; else rctx += (rctx < 257);
             r += part;
         } while (part == 3 && r < n);
-        while (r-- && i + 1 < n) { ++i; if (lane == 0) out[i] = (uint8_t)last; }
+        while (r-- && i + 1 < n) { ++i; PUT_BYTE (i, last); }
+    }
+    #undef PUT_BYTE
+    if (lane == 0) {                                                      // tail: bytes after the last aligned word boundary
+        const uint32_t tail = (uint32_t)(((uintptr_t)(out + n)) & 3);
+        for (uint32_t t = 0; t < tail && t < n; t++) out[n - 1 - t] = (uint8_t)(win >> (24 - 8 * t));
     }
 }
 

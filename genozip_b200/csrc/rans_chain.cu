@@ -262,13 +262,22 @@ __device__ __forceinline__ void decode_o1 (const DecLane &d, const uint8_t *ssym
     for (int o = 16; o; o >>= 1) maxsteps = max (maxsteps, __shfl_xor_sync (0xffffffffu, maxsteps, o));
     const uint32_t shift = d.shift, mask = (1u << shift) - 1;
     uint32_t coff = d.row0 << shift;                                         // LUT row of the previous symbol; context 0 first (:1029)
+    // Each chain writes its own quarter of the output.  Bytes are gathered in a 32-bit window and stored one aligned word
+    // at a time: per-symbol byte stores from hundreds of concurrent leaves saturate the L2 write path long before anything else.
     uint8_t *op = d.out + (size_t)k * q4;
+    const uint8_t *op0 = op;
+    const uint32_t head_end = (uint32_t)((4 - (reinterpret_cast<uintptr_t>(op) & 3)) & 3);
+    uint32_t win = 0;
+    #define PUT_SLOW(b) do { win = __byte_perm (win, (b), 0x4321); const uintptr_t A = reinterpret_cast<uintptr_t>(op); const uint32_t cnt = (uint32_t)(op - op0); \
+                             if ((A & 3) == 3 && cnt >= 3) *reinterpret_cast<uint32_t *>(A - 3) = win; else if (cnt < head_end) *op = (uint8_t)(b); op++; } while (0)
     uint32_t s = 0;
     while (s < maxsteps) {
         const bool active = d.valid && s < steps;
         uint32_t lim = active ? q4 : 0xffffffffu;
         for (int o = 16; o; o >>= 1) lim = min (lim, __shfl_xor_sync (0xffffffffu, lim, o));
-        if (lim != 0xffffffffu && s + 4 <= lim) {
+        if (lim != 0xffffffffu && s >= 4 && s + 4 <= lim) {
+            const uint32_t ph = (uint32_t)(reinterpret_cast<uintptr_t>(op) & 3);   // constant over the region: op advances by 4 per block
+            const bool st0 = ph == 3, st1 = ph == 2, st2 = ph == 1, st3 = ph == 0;
             for (; s + 4 <= lim; s += 4) {
                 #pragma unroll
                 for (int t = 0; t < 4; t++) {
@@ -278,7 +287,9 @@ __device__ __forceinline__ void decode_o1 (const DecLane &d, const uint8_t *ssym
                         const uint32_t xs = x >> shift;
                         x = ((e >> 8) & 0xfffu) * xs + (xs + (e >> 20));
                         coff = (e & 0xffu) << shift;
-                        op[t] = ssym[e & 0xffu];
+                        win = __byte_perm (win, (uint32_t)ssym[e & 0xffu], 0x4321);
+                        const bool stt = t == 0 ? st0 : t == 1 ? st1 : t == 2 ? st2 : st3;
+                        if (stt) *reinterpret_cast<uint32_t *>(op + t - 3) = win;
                     }
                     dec_renorm (x, poff, active, d.body, d.body_len, k, gshift);
                 }
@@ -293,11 +304,16 @@ __device__ __forceinline__ void decode_o1 (const DecLane &d, const uint8_t *ssym
                 const uint32_t xs = x >> shift;
                 x = ((e >> 8) & 0xfffu) * xs + (xs + (e >> 20));
                 coff = (e & 0xffu) << shift;
-                *op++ = ssym[e & 0xffu];
+                PUT_SLOW ((uint32_t)ssym[e & 0xffu]);
             }
             dec_renorm (x, poff, act, d.body, d.body_len, k, gshift);
             s++;
         }
+    }
+    #undef PUT_SLOW
+    if (d.valid) {                                                           // bytes after the last aligned word boundary
+        const uint32_t cnt = (uint32_t)(op - op0), tail = (uint32_t)(reinterpret_cast<uintptr_t>(op) & 3);
+        for (uint32_t t = 0; t < tail && t < cnt; t++) op[-1 - (int)t] = (uint8_t)(win >> (24 - 8 * t));
     }
 }
 
