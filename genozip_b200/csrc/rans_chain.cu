@@ -293,7 +293,7 @@ __device__ __forceinline__ void decode_o1 (const DecLane &d, const uint8_t *ssym
                     }
                     dec_renorm (x, poff, active, d.body, d.body_len, k, gshift);
                 }
-                op += 4;
+                if (active) op += 4;                                         // a finished group's pointer must stay put for its tail flush
             }
         }
         else {
