@@ -322,7 +322,14 @@ def run_gpu(args):
     dom_bytes = alg["rans" if dom.startswith("rans") else "arith"]
     achieved = dom_bytes / (kern[dom] * 1e-3) / 1e9 if kern[dom] > 0 else 0.0
     kname = {"rans_enc": "k_rans_encode", "rans_dec": "k_rans_decode", "arith_enc": "k_arith_encode", "arith_dec": "k_arith_decode"}[dom]
-    roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if kname in tj and tj[kname].get("vblocks") == V:
+            traffic = tj[kname]["bytes_per_launch"]
+    except Exception:
+        pass
+    roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "peak_source": which_peak, "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": kern[dom],
             "note": "entropy chains are dependency-bound (4 chains per rANS leaf, 1 per arithmetic leaf, fixed by the bitstream); "
                     "see profiles/ for dram__bytes of this kernel", "kernel_ms_per_step": kern}
