@@ -302,7 +302,7 @@ def run_gpu(args):
         meta_h, h2d_z, d2h_z = zr
         h2d_p, d2h_p = pr
         assert torch.equal(path.h["seq_out"], path.h["seq"]) and torch.equal(path.h["qual_out"], path.h["qual"]), "host round trip failed"
-        e2e = {"value": world * txt_bytes / ((ez + ep) * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d_z + h2d_p), "d2h_bytes_per_step": int(d2h_z + d2h_p),
+        e2e = {"value": world * txt_bytes / ((ez + ep) * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(world * (h2d_z + h2d_p)), "d2h_bytes_per_step": int(world * (d2h_z + d2h_p)),
                "zip_ms": ez, "piz_ms": ep}
 
     # roofline of the dominant kernel: algorithmic bytes (N uncompressed + C compressed) / its launch time

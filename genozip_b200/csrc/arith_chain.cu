@@ -90,7 +90,7 @@ __device__ __forceinline__ void warp_model_bump (uint32_t *m, uint32_t maxs, uin
     uint32_t f = (e & 0xffffu) + AR_STEP;
     tot += AR_STEP;
     if (tot > AR_MAXF) {                                                    // normalize (:106-116), warp-uniform branch
-        if (lane == 0) m[i] = (e & 0xffff0000u) | f;
+        m[i] = (e & 0xffff0000u) | f;
         __syncwarp ();
         uint32_t sum = 0;
         for (uint32_t base = 0; base < maxs; base += 32) {
@@ -101,13 +101,12 @@ __device__ __forceinline__ void warp_model_bump (uint32_t *m, uint32_t maxs, uin
         __syncwarp ();
         f = m[i] & 0xffffu;
     }
+    // every lane writes the same words (one merged transaction); each lane then reads back its own stores, so the common
+    // path needs no warp synchronisation
     const uint32_t prev = m[i - 1];
-    if (lane == 0) {
-        m[0] = tot;
-        if (f > (prev & 0xffffu)) { m[i - 1] = (e & 0xffff0000u) | f; m[i] = prev; }
-        else m[i] = (e & 0xffff0000u) | f;
-    }
-    __syncwarp ();
+    m[0] = tot;
+    if (f > (prev & 0xffffu)) { m[i - 1] = (e & 0xffff0000u) | f; m[i] = prev; }
+    else m[i] = (e & 0xffff0000u) | f;
 }
 
 // ---- encoder ---------------------------------------------------------------------------------------------------
@@ -116,10 +115,8 @@ struct RCEnc { uint32_t low, range, ffnum, cache, carry; uint8_t *out; };
 __device__ __forceinline__ void rc_shift_low (RCEnc &rc, int lane)          // c_range_coder.h:70-88
 {
     if (rc.low < (255u << 24) || rc.carry) {
-        if (lane == 0) {
-            *rc.out = (uint8_t)(rc.cache + rc.carry);
-            for (uint32_t i = 0; i < rc.ffnum; i++) rc.out[1 + i] = (uint8_t)(rc.carry - 1);
-        }
+        *rc.out = (uint8_t)(rc.cache + rc.carry);                           // all lanes store the same byte: one merged transaction
+        for (uint32_t i = 0; i < rc.ffnum; i++) rc.out[1 + i] = (uint8_t)(rc.carry - 1);
         rc.out += 1 + rc.ffnum; rc.ffnum = 0;
         rc.cache = rc.low >> 24;
         rc.carry = 0;
@@ -133,10 +130,10 @@ __device__ __forceinline__ void warp_encode (uint32_t *m, uint32_t maxs, RCEnc &
     uint32_t e, acc, i;
     const uint32_t tot = m[0];
     const uint4 v = *reinterpret_cast<const uint4 *>(m + 4);              // the model is approximately sorted by frequency: the
-    if      ((v.x >> 16) == sym && maxs > 0) { e = v.x; acc = 0; i = 4; }   // symbol is almost always among the first four entries
-    else if ((v.y >> 16) == sym && maxs > 1) { e = v.y; acc = v.x & 0xffffu; i = 5; }
-    else if ((v.z >> 16) == sym && maxs > 2) { e = v.z; acc = (v.x & 0xffffu) + (v.y & 0xffffu); i = 6; }
-    else if ((v.w >> 16) == sym && maxs > 3) { e = v.w; acc = (v.x & 0xffffu) + (v.y & 0xffffu) + (v.z & 0xffffu); i = 7; }
+    if      ((v.x >> 16) == sym) { e = v.x; acc = 0; i = 4; }               // symbol is almost always among the first four entries
+    else if ((v.y >> 16) == sym) { e = v.y; acc = v.x & 0xffffu; i = 5; }   // (padding entries carry symbol 0xffff: they never match)
+    else if ((v.z >> 16) == sym) { e = v.z; acc = (v.x & 0xffffu) + (v.y & 0xffffu); i = 6; }
+    else if ((v.w >> 16) == sym) { e = v.w; acc = (v.x & 0xffffu) + (v.y & 0xffffu) + (v.z & 0xffffu); i = 7; }
     else i = warp_find_sym (m, maxs, sym, lane, e, acc);
     const uint32_t before = rc.low;
     rc.range = div_small (rc.range, tot);
@@ -161,6 +158,7 @@ __global__ void __launch_bounds__(128) k_arith_encode (const EncLeaf *leaves, En
     uint32_t *lit = D.models, *run = lit + (o1 ? 256 : 1) * stride;
     uint8_t *out = L.outbuf;
     if (!lit) return;
+    __builtin_assume (__isGlobal (lit)); __builtin_assume (__isGlobal (out)); __builtin_assume (__isGlobal (in));
     if (lane == 0) out[0] = (uint8_t)maxs;                                 // arith_dynamic.c:105-110 (256 wraps to 0)
     RCEnc rc; rc.low = 0; rc.range = 0xffffffffu; rc.ffnum = 0; rc.cache = 0; rc.carry = 0; rc.out = out + 1;
     // A body that reaches the input length is discarded for a raw copy (arith_dynamic.c:847-852), so encoding stops
@@ -212,10 +210,10 @@ __device__ __forceinline__ uint32_t warp_decode (uint32_t *m, uint32_t maxs, RCD
     uint32_t e, acc, i;
     const uint4 v = *reinterpret_cast<const uint4 *>(m + 4);
     const uint32_t c0 = v.x & 0xffffu, c1 = c0 + (v.y & 0xffffu), c2 = c1 + (v.z & 0xffffu), c3 = c2 + (v.w & 0xffffu);
-    if      (c0 > freq && maxs > 0) { e = v.x; acc = 0;  i = 4; }
-    else if (c1 > freq && maxs > 1) { e = v.y; acc = c0; i = 5; }
-    else if (c2 > freq && maxs > 2) { e = v.z; acc = c1; i = 6; }
-    else if (c3 > freq && maxs > 3) { e = v.w; acc = c2; i = 7; }
+    if      (c0 > freq) { e = v.x; acc = 0;  i = 4; }                        // padding entries have Freq 0: they never extend the range
+    else if (c1 > freq) { e = v.y; acc = c0; i = 5; }
+    else if (c2 > freq) { e = v.z; acc = c1; i = 6; }
+    else if (c3 > freq) { e = v.w; acc = c2; i = 7; }
     else i = warp_find_freq (m, maxs, freq, lane, e, acc);
     if (!i) return 0;
     rc.code  -= acc * rc.range;
@@ -240,6 +238,7 @@ __global__ void __launch_bounds__(128) k_arith_decode (DecLeaf *leaves, const ui
     const bool o1 = L.order == 1, rle = L.rle;
     uint32_t *lit = L.models, *run = lit + (o1 ? 256 : 1) * stride;
     uint8_t *out = L.dst;
+    __builtin_assume (__isGlobal (lit)); __builtin_assume (__isGlobal (out)); __builtin_assume (__isGlobal (L.body));
     RCDec rc; rc.range = 0xffffffffu; rc.code = 0; rc.in = L.body + 1; rc.end = L.body + L.body_len;
     if (rc.in + 5 > rc.end) rc.in = rc.end;                               // RC_StartDecode (c_range_coder.h:57-68)
     else for (int i = 0; i < 5; i++) rc.code = (rc.code << 8) | *rc.in++;

@@ -21,7 +21,7 @@ __device__ __forceinline__ void ar_model_init (uint32_t *m, uint32_t maxs)      
     m[0] = maxs; m[1] = 0; m[2] = 0; m[3] = AR_MAXF | 0xffff0000u;
     for (uint32_t i = 0; i < maxs; i++) m[4 + i] = 1u | (i << 16);
     const uint32_t st = ar_stride (maxs);
-    for (uint32_t i = 4 + maxs; i < st; i++) m[i] = 0;
+    for (uint32_t i = 4 + maxs; i < st; i++) m[i] = 0xffff0000u;          // Freq 0 (terminates normalise) and a symbol that never matches
 }
 
 // bump the coded entry i (holding e): Freq += STEP, halve everything past MAX_FREQ, one bubble step towards the front
