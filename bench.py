@@ -221,28 +221,45 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     eng = Engine(local)
+    from genozip_b200 import GzbError
     V = args.vblocks
     if V <= 0:                                                  # BASELINE configs[1] is ~390 VBlocks per GPU; take what fits comfortably
         free_b, _ = torch.cuda.mem_get_info(dev)
-        per_vb = 13.5 * args.reads * args.read_len + (64 << 20)   # inputs, DOMQ/ACGT intermediates, sections, outputs, engine workspace
-        V = int(max(8, min(256, (0.80 * free_b) // per_vb)))
+        per_vb = 16.0 * args.reads * args.read_len + (32 << 20)   # inputs, DOMQ/ACGT intermediates, sections, outputs, engine workspace
+        V = int(max(8, min(512, (0.80 * free_b) // per_vb)))
+    while True:                                                  # a batch that does not fit is halved (all ranks agree on the size)
         if world > 1:
             t = torch.tensor([V], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MIN); V = int(t.item())
-    path = FastqCodecPath(eng, V, args.reads, args.read_len)
-    # VBlocks are sharded round-robin by vblock_i: rank r owns vblock_i = r+1, r+1+world, ...  Seeds follow vblock_i.
-    data = synth_vblocks(V, args.reads, args.read_len, 1000 + rank, dev)
-    codecs = path.assign_codecs(data) if rank == 0 else None
-    if world > 1:
-        obj = [codecs]; dist.broadcast_object_list(obj, src=0); codecs = obj[0]
-    path.codec = dict(codecs)
+        path = data = None
+        ok = 1
+        try:
+            path = FastqCodecPath(eng, V, args.reads, args.read_len)
+            # VBlocks are sharded round-robin by vblock_i: rank r owns vblock_i = r+1, r+1+world, ...  Seeds follow vblock_i.
+            data = synth_vblocks(V, args.reads, args.read_len, 1000 + rank, dev)
+            codecs = path.assign_codecs(data) if rank == 0 else None
+            if world > 1:
+                obj = [codecs]; dist.broadcast_object_list(obj, src=0); codecs = obj[0]
+            path.codec = dict(codecs)
+            # correctness gate before timing: piz(zip(x)) == x on the device
+            meta = path.zip_device(data)
+            path.alloc_piz(meta)
+            path.piz_device(meta)
+            torch.cuda.synchronize()
+        except (torch.OutOfMemoryError, GzbError) as ex:
+            if "memory" not in str(ex).lower():
+                raise
+            ok = 0
+        if world > 1:
+            t = torch.tensor([ok], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MIN); ok = int(t.item())
+        if ok:
+            break
+        del path, data
+        eng.close(); torch.cuda.empty_cache()
+        eng = Engine(local)
+        V = max(4, V // 2)
     if rank == 0:
         os.makedirs(os.path.dirname(CODEC_CACHE), exist_ok=True)
         json.dump(codecs, open(CODEC_CACHE, "w"))
-    # correctness gate before timing: piz(zip(x)) == x on the device
-    meta = path.zip_device(data)
-    path.alloc_piz(meta)
-    path.piz_device(meta)
-    torch.cuda.synchronize()
     assert torch.equal(path.seq_out_d, data["seq"]) and torch.equal(path.qual_out_d, data["qual"]), "round trip failed"
     for s in ("Q_TILE", "Q_X", "Q_Y", "Q_MISC"):
         assert torch.equal(path.dec_d[s][:, :data[s].shape[1]], data[s]), f"round trip failed: {s}"
