@@ -480,7 +480,7 @@ extern "C" int gzb_acgt_pack (gzb_engine *e, const void *seq, uint64_t n, void *
 {
     if (!e || (!seq && n) || !packed) return GZB_E_BADARG;
     cudaSetDevice (e->device);
-    const bool devptr = flags & GZB_DEVICE_PTRS;
+    const bool devptr = flags & GZB_DEVICE_PTRS, xdev = !devptr && (flags & GZB_OUT_DEVICE) && x;   // exception stream stays in HBM for its sub-codec
     const uint64_t plen = gzb_acgt_packed_len (n);
     cudaStream_t st = e->stream;
     Carver c { nullptr, 0 };
@@ -488,7 +488,7 @@ extern "C" int gzb_acgt_pack (gzb_engine *e, const void *seq, uint64_t n, void *
     for (int pass = 0; pass < 2; pass++) {
         c.off = 0;
         d_flag = c.take<int> (1);
-        if (!devptr) { d_seq = c.take<uint8_t> (n + 32); d_packed = c.take<uint8_t> (plen + 32); d_x = c.take<uint8_t> (n + 32); }
+        if (!devptr) { d_seq = c.take<uint8_t> (n + 32); d_packed = c.take<uint8_t> (plen + 32); d_x = xdev ? (uint8_t *)x : c.take<uint8_t> (n + 32); }
         if (pass == 0) { int rc = engine_reserve (e, c.off, 4096); if (rc) return rc; c.base = e->ws; }
     }
     if (devptr) { d_seq = (uint8_t *)seq; d_packed = (uint8_t *)packed; d_x = (uint8_t *)x; }
@@ -505,8 +505,8 @@ extern "C" int gzb_acgt_pack (gzb_engine *e, const void *seq, uint64_t n, void *
     if (!devptr && plen) CK (cudaMemcpyAsync (packed, d_packed, plen, cudaMemcpyDeviceToHost, st));
     CK (cudaStreamSynchronize (st));
     if (x_all_zero) *x_all_zero = !h_flag;
-    if (!devptr && x && n && h_flag) { CK (cudaMemcpyAsync (x, d_x, n, cudaMemcpyDeviceToHost, st)); CK (cudaStreamSynchronize (st)); }
-    else if (!devptr && x && n) memset (x, 0, n);                                   // all-zero exception stream: no transfer needed
+    if (!devptr && !xdev && x && n && h_flag) { CK (cudaMemcpyAsync (x, d_x, n, cudaMemcpyDeviceToHost, st)); CK (cudaStreamSynchronize (st)); }
+    else if (!devptr && !xdev && x && n) memset (x, 0, n);                                   // all-zero exception stream: no transfer needed
     return GZB_OK;
 }
 
@@ -514,7 +514,7 @@ extern "C" int gzb_acgt_unpack (gzb_engine *e, const void *packed, const void *x
 {
     if (!e || (!packed && n) || !seq) return GZB_E_BADARG;
     cudaSetDevice (e->device);
-    const bool devptr = flags & GZB_DEVICE_PTRS;
+    const bool devptr = flags & GZB_DEVICE_PTRS, xdev = !devptr && (flags & GZB_IN_DEVICE) && x;
     const uint64_t plen = gzb_acgt_packed_len (n);
     cudaStream_t st = e->stream;
     Carver c { nullptr, 0 };
@@ -526,7 +526,8 @@ extern "C" int gzb_acgt_unpack (gzb_engine *e, const void *packed, const void *x
             if (pass == 0) { int rc = engine_reserve (e, c.off, 4096); if (rc) return rc; c.base = e->ws; }
         }
         if (plen) CK (cudaMemcpyAsync (d_packed, packed, plen, cudaMemcpyHostToDevice, st));
-        if (x && n) CK (cudaMemcpyAsync (d_x, x, n, cudaMemcpyHostToDevice, st));
+        if (xdev) d_x = (uint8_t *)x;
+        else if (x && n) CK (cudaMemcpyAsync (d_x, x, n, cudaMemcpyHostToDevice, st));
     }
     else { d_seq = (uint8_t *)seq; d_packed = (uint8_t *)packed; d_x = (uint8_t *)x; }
     if (n) {

@@ -237,7 +237,6 @@ class FastqCodecPath:
         V, n = self.V, self.n
         hp = lambda *shape: torch.empty(shape, dtype=torch.uint8).pin_memory()
         self.h["packed"] = hp(V, self.packed_len + 32)
-        self.h["x"] = hp(V, n)
         self.h["linedom"] = hp(V, self.n_reads); self.h["linediv"] = hp(V, self.n_reads)
         # compressed-section buffers: est_size of the largest actual stream of each kind (the capacity the C-ABI requires)
         def comp_cap(s):
@@ -245,7 +244,7 @@ class FastqCodecPath:
             return max([est_size(self.codec[s], l) for l in lens] + [4096])
         self.h["comp"] = {s: hp(V, comp_cap(s)) for s in STREAMS}
         self.h["seq_out"] = hp(V, n); self.h["qual_out"] = hp(V, n)
-        self.h["dec"] = {s: hp(V, self.dec_d[s].shape[1]) for s in ("NONREF_X", "Q_TILE", "Q_X", "Q_Y", "Q_MISC")}
+        self.h["dec"] = {s: hp(V, self.dec_d[s].shape[1]) for s in ("Q_TILE", "Q_X", "Q_Y", "Q_MISC")}
 
     def zip_host(self):
         """host buffers in, host buffers out; the DOMQ streams stay on the device between codec_domq_compress and
@@ -256,11 +255,11 @@ class FastqCodecPath:
         meta = [dict(len={}, comp_len={}) for _ in range(V)]
         h2d = d2h = 0
         for v in range(V):
-            if L.gzb_acgt_pack(h, H["seq"][v].data_ptr(), n, H["packed"][v].data_ptr(), H["x"][v].data_ptr(), C.byref(allz), 0):
+            if L.gzb_acgt_pack(h, H["seq"][v].data_ptr(), n, H["packed"][v].data_ptr(), self.x_d[v].data_ptr(), C.byref(allz), GZB_OUT_DEVICE):
                 raise GzbError(f"gzb_acgt_pack: {self.eng._err()}")
             meta[v]["acgt_no_x"] = bool(allz.value)
             meta[v]["len"]["NONREF_X"] = 0 if allz.value else n
-            h2d += n; d2h += self.packed_len + (0 if allz.value else n)
+            h2d += n; d2h += self.packed_len
         for v in range(V):
             a = self.dvb[v]
             a.txt = H["qual"][v].data_ptr(); a.txt_len = n
@@ -278,16 +277,18 @@ class FastqCodecPath:
             m["num_norm_qs"] = a.num_norm_qs
             m["denorm"] = bytes(a.denorm)[:a.num_norm_qs * a.num_doms]
 
+        on_dev = set(self.dq) | {"NONREF_X"}                # intermediate streams stay in HBM until their sub-codec
+
         def in_ptr(s, v):
             if s in self.dq: return self.dq[s][v].data_ptr()
-            if s == "NONREF_X": return H["x"][v].data_ptr()
+            if s == "NONREF_X": return self.x_d[v].data_ptr()
             return H[s][v].data_ptr()
         secs, idx = self._sections(meta, in_ptr, lambda s, v: H["comp"][s][v].data_ptr(),
-                                   lambda s: GZB_SEC_IN_DEVICE if s in self.dq else 0)
+                                   lambda s: GZB_SEC_IN_DEVICE if s in on_dev else 0)
         self.eng.compress_raw(secs, len(idx), 0)
         self._collect(secs, idx, meta)
         for (v, s) in idx:
-            if s not in self.dq: h2d += meta[v]["len"][s]
+            if s not in on_dev: h2d += meta[v]["len"][s]
             d2h += meta[v]["comp_len"][s]
         return meta, h2d, d2h
 
@@ -299,7 +300,7 @@ class FastqCodecPath:
         for i, (v, s) in enumerate(idx):
             secs[i].codec = CODEC[self.codec[s]]
             secs[i].in_ = H["comp"][s][v].data_ptr(); secs[i].in_len = meta[v]["comp_len"][s]
-            on_dev = s in self.dq
+            on_dev = s in self.dq or s == "NONREF_X"
             secs[i].out = (self.dec_d[s][v] if on_dev else H["dec"][s][v]).data_ptr(); secs[i].out_cap = meta[v]["len"][s]
             secs[i].sflags = GZB_SEC_OUT_DEVICE if on_dev else 0
             h2d += meta[v]["comp_len"][s]; d2h += 0 if on_dev else meta[v]["len"][s]
@@ -319,8 +320,8 @@ class FastqCodecPath:
         if L.gzb_domq_reconstruct(h, self.pvb, V, GZB_IN_DEVICE):
             raise GzbError(f"gzb_domq_reconstruct: {self.eng._err()}")
         for v in range(V):
-            x = None if meta[v]["acgt_no_x"] else H["dec"]["NONREF_X"][v].data_ptr()
-            if L.gzb_acgt_unpack(h, H["packed"][v].data_ptr(), x, n, H["seq_out"][v].data_ptr(), 0):
+            x = None if meta[v]["acgt_no_x"] else self.dec_d["NONREF_X"][v].data_ptr()
+            if L.gzb_acgt_unpack(h, H["packed"][v].data_ptr(), x, n, H["seq_out"][v].data_ptr(), GZB_IN_DEVICE):
                 raise GzbError(f"gzb_acgt_unpack: {self.eng._err()}")
-            h2d += self.packed_len + (0 if x is None else n); d2h += n
+            h2d += self.packed_len; d2h += n
         return h2d, d2h

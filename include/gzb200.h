@@ -94,7 +94,9 @@ int gzb_uncompress_sections (gzb_engine *e, gzb_section *secs, uint32_t n, uint3
  * pack:   codec_acgt_compress up to the sub-codec call (:64-163): bases → LE 2-bit words + exception stream.
  *         `packed` receives gzb_acgt_packed_len(n) bytes; `x` (n bytes) may be NULL if the caller declares
  *         acgt_no_x; *x_all_zero is set when the exception stream is all zero (=> header flag acgt_no_x, :136-140).
- * unpack: codec_acgt_uncompress/codec_xcgt_uncompress after their sub-codec call (:185-248). x may be NULL. */
+ * unpack: codec_acgt_uncompress/codec_xcgt_uncompress after their sub-codec call (:185-248). x may be NULL.
+ * With host buffers, GZB_OUT_DEVICE (pack) / GZB_IN_DEVICE (unpack) make `x` alone a device pointer: the exception stream
+ * stays in HBM between ACGT and its XCGT sub-codec section, like NONREF.local is overlaid on NONREF_X.local in the reference (:97-100). */
 uint64_t gzb_acgt_packed_len (uint64_t n_bases);
 int gzb_acgt_pack   (gzb_engine *e, const void *seq, uint64_t n_bases, void *packed, void *x, int *x_all_zero, uint32_t flags);
 int gzb_acgt_unpack (gzb_engine *e, const void *packed, const void *x, uint64_t n_bases, void *seq, uint32_t flags);
