@@ -298,7 +298,7 @@ extern "C" int gzb_compress_sections (gzb_engine *e, gzb_section *secs, uint32_t
     for (auto &L : hl) {
         size_t m = std::min<size_t> (256, (size_t)L.n + 1);
         if (L.coder == CODER_RANS) arena_est += (L.order_req & 1) ? std::min<size_t> (m * m * 20 + m * CTXB, 64 * 64 * 20 + 64 * CTXB + (size_t)L.n / 8) + 4096 : 4096 + 64;
-        else arena_est += std::min<size_t> ((size_t)256 * 259 * 4, 256 * 68 * 4 + (size_t)L.n / 8) + 258 * 7 * 4 + 64;
+        else arena_est += std::min<size_t> ((size_t)256 * 264 * 4, 256 * 72 * 4 + (size_t)L.n / 8) + 258 * 12 * 4 + 64;
     }
     if (e->arena_hint > arena_est) arena_est = e->arena_hint;
 

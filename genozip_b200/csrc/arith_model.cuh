@@ -1,80 +1,538 @@
-// arith_model.cuh — the adaptive frequency model of the htscodecs arithmetic coder (reference SIMPLE_MODEL,
-// src/htscodecs/c_simple_model.h:77-179) in a layout made for 16-byte loads:
-//   word 0      TotFreq
-//   word 3      sentinel (Freq = MAX_FREQ: never swapped past, :98-99)
-//   word 4..    live entries  freq | symbol << 16  (approximately sorted by frequency)
-//   then one zero word (terminates normalise, :101) and padding to a multiple of 4 words.
-// The symbol being coded is almost always among the first four entries, which arrive in one load.
+// arith_model.cuh — the htscodecs adaptive arithmetic coder (reference src/htscodecs/c_simple_model.h:77-179 model,
+// c_range_coder.h:46-126 range coder, arith_dynamic.c:92-226 / 387-608 loops) as ONE dependency chain per leaf, written
+// for the latency of a single warp:
+//
+//   * model layout made for vector loads:   word 0 TotFreq | word 1 float bits of a reciprocal of TotFreq rounded DOWN |
+//     words 4.. entries  Freq | Symbol << 16  (approximately sorted by frequency, like the reference's list), padded with
+//     Freq 0 / Symbol 0xffff entries to a multiple of 8;
+//   * the model of the CURRENT context (TotFreq, reciprocal, first four entries) lives in registers; every update is
+//     written through to memory, so a context switch is two loads and a repeated context costs none;
+//   * range / TotFreq is one float multiply with the stored reciprocal plus an exact integer correction;
+//   * the decoder never divides code by range: "AccFreq <= code / range" (c_simple_model.h:156) is evaluated as
+//     "AccFreq * range <= code" on the first four entries;
+//   * symbols beyond the first four entries are located by the whole warp, 8 entries per lane;
+//   * everything else (halving, bubble step beyond the cached entries) works on memory and reloads the registers.
+//
+// All lanes of the warp carry the coder state redundantly (uniform execution); stores of identical values to identical
+// addresses merge into one transaction.  The same source builds for the host with one "lane" (tests/host_arith.cpp):
+// the CPU suite checks this logic against the oracle without a GPU.
 #pragma once
 #include <stdint.h>
+
+#if defined(__CUDACC__)
+  #define AR_FN __device__ __forceinline__
+  #define AR_SLOW static __device__ __noinline__
+#else
+  #include <string.h>
+  #define AR_FN static inline
+  #define AR_SLOW static
+  struct uint2 { uint32_t x, y; };
+  struct uint4 { uint32_t x, y, z, w; };
+  static inline uint32_t __ldg (const uint8_t *p) { return *p; }
+  static inline void __syncwarp () {}
+  static inline uint32_t __byte_perm (uint32_t a, uint32_t b, uint32_t s)
+  {
+      const uint64_t v = ((uint64_t)b << 32) | a; uint32_t r = 0;
+      for (int i = 0; i < 4; i++) r |= (uint32_t)((v >> (8 * ((s >> (4 * i)) & 7))) & 0xff) << (8 * i);
+      return r;
+  }
+#endif
 
 namespace gzb {
 
 #define AR_MAXF  65519u          // MAX_FREQ = (1<<16)-17 (c_simple_model.h:70)
 #define AR_STEP  16u             // STEP (:73)
+#define AR_TOP   (1u << 24)      // TOP (c_range_coder.h:22)
 
-__host__ __device__ __forceinline__ uint32_t ar_stride (uint32_t maxs) { return (maxs + 5 + 3) & ~3u; }
+AR_FN uint32_t ar_stride (uint32_t maxs) { return 4 + ((maxs + 7) & ~7u); }
 constexpr uint32_t AR_RUN_STRIDE = 12;           // run-length models: 4 live symbols (MAX_RUN, arith_dynamic.c:383)
 
-__device__ __forceinline__ void ar_model_init (uint32_t *m, uint32_t maxs)                 // :85-103
+// ---- reciprocal and division -------------------------------------------------------------------------------------
+// 1/x rounded safely DOWN: MUFU.RCP (<= 1 ulp) scaled by (1 - 5e-7); relative deficit < 7e-7
+AR_FN float ar_rcp_below (uint32_t x)
 {
-    m[0] = maxs; m[1] = 0; m[2] = 0; m[3] = AR_MAXF | 0xffff0000u;
+#ifdef __CUDA_ARCH__
+    float r;
+    asm ("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__uint2float_ru (x)));
+    return __fmul_rz (r, 0.9999995f);
+#else
+    return (float)(0.999999 / (double)x);
+#endif
+}
+
+// exact a / d for d < 2^17 given rd <= 1/d: the float estimate never exceeds the quotient; its deficit is corrected
+// in integers (one step almost always: the deficit is <= q * 1e-6 + 1)
+AR_FN uint32_t ar_div (uint32_t a, uint32_t d, float rd)
+{
+#ifdef __CUDA_ARCH__
+    uint32_t q = __float2uint_rz (__fmul_rz (__uint2float_rz (a), rd));
+    uint32_t r = a - q * d;
+    if (r >= d) {
+        q++; r -= d;
+        if (r >= d) {                                                       // small divisors (young models): a second float round
+            const uint32_t q2 = __float2uint_rz (__fmul_rz (__uint2float_rz (r), rd));
+            q += q2; r -= q2 * d;
+            while (r >= d) { q++; r -= d; }
+        }
+    }
+    return q;
+#else
+    (void)rd;
+    return a / d;
+#endif
+}
+
+// exact a / d when the QUOTIENT is small (< 2^17): the decoder's code / range on the slow path (c_range_coder.h:111-114)
+AR_FN uint32_t ar_div_smallq (uint32_t a, uint32_t d)
+{
+#ifdef __CUDA_ARCH__
+    if ((a >> 17) >= d) return d ? a / d : 0xffffffffu;
+    const float rd = ar_rcp_below (d);
+    uint32_t q = __float2uint_rz (__fmul_rz (__uint2float_rz (a), rd));
+    uint32_t r = a - q * d;
+    while (r >= d) { q++; r -= d; }
+    return q;
+#else
+    return d ? a / d : 0xffffffffu;
+#endif
+}
+
+// ---- warp primitives (one lane on the host) ------------------------------------------------------------------------
+#ifdef __CUDA_ARCH__
+AR_FN uint32_t ar_wsum (uint32_t v) { return __reduce_add_sync (0xffffffffu, v); }
+#else
+AR_FN uint32_t ar_wsum (uint32_t v) { return v; }
+#endif
+
+AR_FN uint32_t ar_f2u (float f) { uint32_t u;
+#ifdef __CUDA_ARCH__
+    u = __float_as_uint (f);
+#else
+    memcpy (&u, &f, 4);
+#endif
+    return u; }
+AR_FN float ar_u2f (uint32_t u) { float f;
+#ifdef __CUDA_ARCH__
+    f = __uint_as_float (u);
+#else
+    memcpy (&f, &u, 4);
+#endif
+    return f; }
+
+// ---- model memory ------------------------------------------------------------------------------------------------------
+AR_FN void ar_model_init (uint32_t *m, uint32_t maxs)                       // c_simple_model.h:85-103
+{
+    m[0] = maxs; m[1] = ar_f2u (ar_rcp_below (maxs)); m[2] = 0; m[3] = 0;
     for (uint32_t i = 0; i < maxs; i++) m[4 + i] = 1u | (i << 16);
     const uint32_t st = ar_stride (maxs);
-    for (uint32_t i = 4 + maxs; i < st; i++) m[i] = 0xffff0000u;          // Freq 0 (terminates normalise) and a symbol that never matches
+    for (uint32_t i = 4 + maxs; i < st; i++) m[i] = 0xffff0000u;            // Freq 0: never selected; Symbol 0xffff: never matches
 }
 
-// bump the coded entry i (holding e): Freq += STEP, halve everything past MAX_FREQ, one bubble step towards the front
-__device__ __forceinline__ void ar_model_bump (uint32_t *m, uint32_t i, uint32_t e, uint32_t tot)   // :131-145 / :164-178
+struct ArCache { uint32_t tot; float rtot; uint32_t e0, e1, e2, e3; };      // the current context's model head, in registers
+
+AR_FN void ar_load (const uint32_t *m, ArCache &c)
 {
-    uint32_t f = (e & 0xffffu) + AR_STEP;
+    const uint2 h = *reinterpret_cast<const uint2 *>(m);
+    const uint4 v = *reinterpret_cast<const uint4 *>(m + 4);
+    c.tot = h.x; c.rtot = ar_u2f (h.y); c.e0 = v.x; c.e1 = v.y; c.e2 = v.z; c.e3 = v.w;
+}
+
+AR_FN void ar_store_head (uint32_t *m, uint32_t tot, float rtot)
+{
+    uint2 h; h.x = tot; h.y = ar_f2u (rtot);
+    *reinterpret_cast<uint2 *>(m) = h;
+}
+
+// Update of entry p directly on memory: Freq += STEP, TotFreq += STEP, halve everything past MAX_FREQ (normalize,
+// :106-116), one bubble step towards the front (:140-145).  e = current value of entry p, tot = current TotFreq.
+// Used for entries beyond the cached four and for every update that triggers the halving.  Leaves memory
+// authoritative; the caller reloads its registers.
+AR_SLOW void ar_update_mem (uint32_t *m, uint32_t maxs, uint32_t p, uint32_t e, uint32_t tot, int lane)
+{
+    uint32_t en = e + AR_STEP;
     tot += AR_STEP;
-    if (tot > AR_MAXF) {                                                                     // normalize (:106-116)
-        m[i] = (e & 0xffff0000u) | f;
-        tot = 0;
-        for (uint32_t j = 4; (m[j] & 0xffffu); j++) { uint32_t g = m[j] & 0xffffu; g -= g >> 1; m[j] = (m[j] & 0xffff0000u) | g; tot += g; }
-        f = m[i] & 0xffffu;
+    if (tot > AR_MAXF) {
+        m[4 + p] = en;
+        __syncwarp ();
+        uint32_t sum = 0;
+#ifdef __CUDA_ARCH__
+        for (uint32_t j = lane; j < maxs; j += 32)
+#else
+        for (uint32_t j = 0; j < maxs; j++)
+#endif
+        { const uint32_t v = m[4 + j]; uint32_t g = v & 0xffffu; g -= g >> 1; m[4 + j] = (v & 0xffff0000u) | g; sum += g; }
+        tot = ar_wsum (sum);
+        __syncwarp ();
+        en = m[4 + p];
     }
-    m[0] = tot;
-    const uint32_t prev = m[i - 1];
-    if (f > (prev & 0xffffu)) { m[i - 1] = (e & 0xffff0000u) | f; m[i] = prev; }
-    else m[i] = (e & 0xffff0000u) | f;
+    if (p) {
+        const uint32_t prev = m[4 + p - 1];
+        if ((en & 0xffffu) > (prev & 0xffffu)) { m[4 + p - 1] = en; m[4 + p] = prev; }
+        else m[4 + p] = en;
+    }
+    else m[4] = en;
+    ar_store_head (m, tot, ar_rcp_below (tot));
+    (void)lane;
 }
 
-// locate `sym`: returns its index, the entry in e and the cumulative frequency before it in acc
-__device__ __forceinline__ uint32_t ar_find_sym (const uint32_t *m, uint32_t sym, uint32_t &e, uint32_t &acc)
+// ---- warp-wide searches beyond the cached entries: lane l owns entries 8l .. 8l+7 ----------------------------------------
+// decoder: first entry p whose cumulative frequency exceeds freq; returns p (>= maxs: none — corrupt input),
+// acc = cumulative frequency before p, e = entry p
+AR_SLOW uint32_t ar_find_freq (const uint32_t *m, uint32_t maxs, uint32_t freq, int lane, uint32_t &acc, uint32_t &e)
 {
-    const uint4 v = *reinterpret_cast<const uint4 *>(m + 4);
-    if ((v.x >> 16) == sym) { e = v.x; acc = 0; return 4; }
-    if ((v.y >> 16) == sym) { e = v.y; acc = v.x & 0xffffu; return 5; }
-    if ((v.z >> 16) == sym) { e = v.z; acc = (v.x & 0xffffu) + (v.y & 0xffffu); return 6; }
-    acc = (v.x & 0xffffu) + (v.y & 0xffffu) + (v.z & 0xffffu);
-    if ((v.w >> 16) == sym) { e = v.w; return 7; }
-    acc += v.w & 0xffffu;
-    uint32_t i = 8; e = m[8];
-    while ((e >> 16) != sym) { acc += e & 0xffffu; e = m[++i]; }
-    return i;
+#ifdef __CUDA_ARCH__
+    const uint32_t j0 = 8u * lane;
+    uint4 a = make_uint4 (0, 0, 0, 0), b = a;
+    if (j0 < maxs) { a = *reinterpret_cast<const uint4 *>(m + 4 + j0); b = *reinterpret_cast<const uint4 *>(m + 8 + j0); }
+    const uint32_t f0 = a.x & 0xffffu, f1 = a.y & 0xffffu, f2 = a.z & 0xffffu, f3 = a.w & 0xffffu,
+                   f4 = b.x & 0xffffu, f5 = b.y & 0xffffu, f6 = b.z & 0xffffu, f7 = b.w & 0xffffu;
+    const uint32_t c1 = f0, c2 = c1 + f1, c3 = c2 + f2, c4 = c3 + f3, c5 = c4 + f4, c6 = c5 + f5, c7 = c6 + f6, c8 = c7 + f7;
+    uint32_t s = c8;                                                        // inclusive scan of the lane sums
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync (0xffffffffu, s, o); if (lane >= o) s += t; }
+    const uint32_t base = s - c8;
+    // entries are counted while their inclusive cumulative frequency is <= freq (monotone: the count is the position)
+    uint32_t k = 0, part = 0;
+    if (base + c1 <= freq) { k++; part += f0; }
+    if (base + c2 <= freq) { k++; part += f1; }
+    if (base + c3 <= freq) { k++; part += f2; }
+    if (base + c4 <= freq) { k++; part += f3; }
+    if (base + c5 <= freq) { k++; part += f4; }
+    if (base + c6 <= freq) { k++; part += f5; }
+    if (base + c7 <= freq) { k++; part += f6; }
+    if (base + c8 <= freq) { k++; part += f7; }
+    if (j0 >= maxs) { k = 0; part = 0; }
+    const uint32_t p = ar_wsum (k);
+    acc = ar_wsum (part);
+    if (p >= maxs) { e = 0; return p; }
+    e = m[4 + p];
+    return p;
+#else
+    (void)lane;
+    acc = 0;
+    for (uint32_t p = 0; p < maxs; p++) {
+        e = m[4 + p];
+        if (acc + (e & 0xffffu) > freq) return p;
+        acc += e & 0xffffu;
+    }
+    e = 0;
+    return maxs;
+#endif
 }
 
-// locate the entry whose cumulative range contains `freq`; returns 0 when the model is exhausted (corrupt input)
-__device__ __forceinline__ uint32_t ar_find_freq (const uint32_t *m, uint32_t freq, uint32_t &e, uint32_t &acc)
+// encoder: the entry holding `sym` (always present for sym < maxs)
+AR_SLOW uint32_t ar_find_sym (const uint32_t *m, uint32_t maxs, uint32_t sym, int lane, uint32_t &acc, uint32_t &e)
 {
-    const uint4 v = *reinterpret_cast<const uint4 *>(m + 4);
-    uint32_t a = v.x & 0xffffu;
-    if (a > freq) { e = v.x; acc = 0; return 4; }
-    uint32_t b = a + (v.y & 0xffffu);
-    if (b > freq) { e = v.y; acc = a; return 5; }
-    uint32_t c = b + (v.z & 0xffffu);
-    if (c > freq) { e = v.z; acc = b; return 6; }
-    uint32_t d = c + (v.w & 0xffffu);
-    if (d > freq) { e = v.w; acc = c; return 7; }
-    uint32_t i = 8; acc = d;
-    for (;;) {
-        e = m[i];
-        if (!e) return 0;
-        if (acc + (e & 0xffffu) > freq) return i;
-        acc += e & 0xffffu; i++;
+#ifdef __CUDA_ARCH__
+    const uint32_t j0 = 8u * lane;
+    uint4 a = make_uint4 (0xffff0000u, 0xffff0000u, 0xffff0000u, 0xffff0000u), b = a;
+    if (j0 < maxs) { a = *reinterpret_cast<const uint4 *>(m + 4 + j0); b = *reinterpret_cast<const uint4 *>(m + 8 + j0); }
+    uint32_t mj = 8, part = 0;                                              // first match inside the lane's 8 entries; frequencies before it
+    if ((b.w >> 16) == sym) mj = 7;
+    if ((b.z >> 16) == sym) mj = 6;
+    if ((b.y >> 16) == sym) mj = 5;
+    if ((b.x >> 16) == sym) mj = 4;
+    if ((a.w >> 16) == sym) mj = 3;
+    if ((a.z >> 16) == sym) mj = 2;
+    if ((a.y >> 16) == sym) mj = 1;
+    if ((a.x >> 16) == sym) mj = 0;
+    if (mj > 0) part += a.x & 0xffffu;
+    if (mj > 1) part += a.y & 0xffffu;
+    if (mj > 2) part += a.z & 0xffffu;
+    if (mj > 3) part += a.w & 0xffffu;
+    if (mj > 4) part += b.x & 0xffffu;
+    if (mj > 5) part += b.y & 0xffffu;
+    if (mj > 6) part += b.z & 0xffffu;
+    if (mj > 7) part += b.w & 0xffffu;
+    const uint32_t hit = __ballot_sync (0xffffffffu, mj < 8);
+    if (!hit) { acc = 0; e = 0; return maxs; }
+    const int w = __ffs (hit) - 1;
+    const uint32_t p = 8u * w + __shfl_sync (0xffffffffu, mj, w);
+    acc = ar_wsum (lane <= w ? part : 0u);
+    e = m[4 + p];
+    return p;
+#else
+    (void)lane;
+    acc = 0;
+    for (uint32_t p = 0; p < maxs; p++) {
+        e = m[4 + p];
+        if ((e >> 16) == sym) return p;
+        acc += e & 0xffffu;
     }
+    e = 0;
+    return maxs;
+#endif
+}
+
+// ---- cached fast-path update ---------------------------------------------------------------------------------------------
+// entry K (0..3) of the cached model was coded: registers and memory are updated identically unless the halving
+// triggers, in which case memory is updated and `stale` asks the caller to reload.
+#define AR_BUMP_CASE(K, EK, EPREV)                                                                              \
+    {                                                                                                           \
+        if (c.tot + AR_STEP > AR_MAXF) { ar_update_mem (m, maxs, K, EK, c.tot, lane); stale = true; }           \
+        else {                                                                                                  \
+            c.tot += AR_STEP; EK += AR_STEP;                                                                    \
+            c.rtot = ar_rcp_below (c.tot);                                                                      \
+            if (K > 0 && (EK & 0xffffu) > (EPREV & 0xffffu)) { const uint32_t t_ = EK; EK = EPREV; EPREV = t_; } \
+            ar_store_head (m, c.tot, c.rtot);                                                                   \
+            uint4 v_; v_.x = c.e0; v_.y = c.e1; v_.z = c.e2; v_.w = c.e3;                                       \
+            *reinterpret_cast<uint4 *>(m + 4) = v_;                                                             \
+        }                                                                                                       \
+    }
+
+// ---- decoder ---------------------------------------------------------------------------------------------------------------
+struct ArDec { uint32_t code, range, ipos, ilen; const uint8_t *in; };
+
+// One symbol (SIMPLE_MODEL_decodeSymbol :148-179 + RC_GetFreq/RC_Decode, c_range_coder.h:111-126).  Returns the symbol;
+// `anomaly` is set when the reference's error return was taken (symbol 0, range divided, nothing else changes).
+// ANY: also handles range < TotFreq (possible only after the input ran dry): the reference then codes entry 0 without
+// dividing the range.
+template <bool ANY>
+AR_FN uint32_t ar_decode_sym (uint32_t *m, uint32_t maxs, ArCache &c, ArDec &rc, int lane, bool &stale, bool &anomaly)
+{
+    uint32_t sym;
+    const bool forced = ANY && rc.range < c.tot;
+    const uint32_t r = forced ? rc.range : ar_div (rc.range, c.tot, c.rtot);
+    const uint32_t f0 = c.e0 & 0xffffu;
+    const uint32_t t1 = f0 * r;
+    if (rc.code < t1 || forced) {
+        rc.range = forced ? rc.range * f0 : t1;
+        sym = c.e0 >> 16;
+        AR_BUMP_CASE (0, c.e0, c.e0)
+    }
+    else {
+        const uint32_t f1 = c.e1 & 0xffffu, f2 = c.e2 & 0xffffu, f3 = c.e3 & 0xffffu;
+        const uint32_t t2 = t1 + f1 * r, t3 = t2 + f2 * r, t4 = t3 + f3 * r;
+        if (rc.code < t2)      { rc.code -= t1; rc.range = f1 * r; sym = c.e1 >> 16; AR_BUMP_CASE (1, c.e1, c.e0) }
+        else if (rc.code < t3) { rc.code -= t2; rc.range = f2 * r; sym = c.e2 >> 16; AR_BUMP_CASE (2, c.e2, c.e1) }
+        else if (rc.code < t4) { rc.code -= t3; rc.range = f3 * r; sym = c.e3 >> 16; AR_BUMP_CASE (3, c.e3, c.e2) }
+        else {
+            uint32_t acc, e;
+            const uint32_t freq = ar_div_smallq (rc.code, r);
+            const uint32_t p = freq > AR_MAXF ? maxs : ar_find_freq (m, maxs, freq, lane, acc, e);
+            if (p >= maxs) { rc.range = r; anomaly = true; return 0; }    // :153-154, :160-161
+            rc.code -= acc * r; rc.range = (e & 0xffffu) * r;
+            sym = e >> 16;
+            ar_update_mem (m, maxs, p, e, c.tot, lane);
+            stale = true;
+        }
+    }
+    return sym;
+}
+
+// RC_Decode's renormalisation (:119-125); false = the input ran dry with range still below TOP
+AR_FN bool ar_dec_renorm (ArDec &rc)
+{
+    while (rc.range < AR_TOP) {
+        if (rc.ipos >= rc.ilen) return false;
+        rc.code = (rc.code << 8) + __ldg (rc.in + rc.ipos++);
+        rc.range <<= 8;
+    }
+    return true;
+}
+
+// Output bytes are gathered in a 32-bit window and written one aligned word at a time (a byte store per symbol from
+// hundreds of concurrent leaves is what the L2 write path chokes on); head and tail bytes go out singly.
+struct ArOut {
+    uint8_t *base;              // out rounded down to 4 bytes
+    uint32_t pos, head, win;    // pos = (out & 3) + symbols written; head = out & 3
+};
+AR_FN void ar_out_init (ArOut &o, uint8_t *out) { o.head = (uint32_t)(reinterpret_cast<uintptr_t>(out) & 3); o.base = out - o.head; o.pos = o.head; o.win = 0; }
+AR_FN void ar_out_put (ArOut &o, uint32_t b)
+{
+    o.win = __byte_perm (o.win, b, 0x4321);
+    if ((o.pos & 3) == 3) {
+        if (o.pos == 3 && o.head) { for (uint32_t t = o.head; t < 4; t++) o.base[t] = (uint8_t)(o.win >> (8 * t)); }
+        else *reinterpret_cast<uint32_t *>(o.base + (o.pos - 3)) = o.win;
+    }
+    o.pos++;
+}
+AR_FN void ar_out_flush (ArOut &o)
+{
+    const uint32_t tail = o.pos & 3;                                        // bytes after the last aligned word boundary
+    const uint32_t first = (o.pos < 4) ? o.head : 0;                        // never touch bytes before the leaf's output
+    for (uint32_t t = first; t < tail; t++) o.base[(o.pos - tail) + t] = (uint8_t)(o.win >> (8 * (4 - tail + t)));
+}
+
+// arith_uncompress_O0 / O1 (arith_dynamic.c:129-152, 200-226) and the RLE variants (:451-493, :564-608)
+template <bool O1>
+AR_FN void ar_decode_leaf (uint32_t *lit, uint32_t maxs, bool rle, const uint8_t *body, uint32_t body_len, uint8_t *out, uint32_t n, int lane)
+{
+    const uint32_t stride = ar_stride (maxs);
+    uint32_t *run = lit + (O1 ? 256 : 1) * stride;
+    ArDec rc; rc.range = 0xffffffffu; rc.code = 0; rc.in = body; rc.ipos = 1; rc.ilen = body_len;
+    if (rc.ipos + 5 > rc.ilen) rc.ipos = rc.ilen;                           // RC_StartDecode (c_range_coder.h:57-68)
+    else for (int i = 0; i < 5; i++) rc.code = (rc.code << 8) | body[rc.ipos++];
+    ArOut o; ar_out_init (o, out);
+    ArCache c;
+    uint32_t ctx = 0, i = 0;
+    uint32_t *m = lit;
+    if (!rle) {
+        // fast loop: invariant range >= TOP (so range >= TotFreq); left for good at the first anomaly
+        ar_load (m, c);
+        bool ok = true;
+        for (; i < n && ok; i++) {
+            bool stale = false, anomaly = false;
+            const uint32_t s = ar_decode_sym<false> (m, maxs, c, rc, lane, stale, anomaly);
+            if (anomaly) ok = false;
+            else if (rc.range < AR_TOP) ok = ar_dec_renorm (rc);
+            ar_out_put (o, s);
+            if (O1 && s != ctx) { ctx = s; m = lit + s * stride; ar_load (m, c); }
+            else if (stale) ar_load (m, c);
+        }
+        for (; i < n; i++) {                                                // after an anomaly: the reference's exact (odd) behaviour
+            bool stale = false, anomaly = false;
+            ar_load (m, c);
+            const uint32_t s = ar_decode_sym<true> (m, maxs, c, rc, lane, stale, anomaly);
+            if (!anomaly) ar_dec_renorm (rc);
+            ar_out_put (o, s);
+            if (O1) { ctx = s; m = lit + s * stride; }
+        }
+    }
+    else {
+        uint32_t last = 0;
+        for (; i < n; i++) {
+            bool stale = false, anomaly = false;
+            m = lit + (O1 ? last : 0) * stride;
+            ar_load (m, c);
+            const uint32_t s = ar_decode_sym<true> (m, maxs, c, rc, lane, stale, anomaly);
+            if (!anomaly) ar_dec_renorm (rc);
+            ar_out_put (o, s);
+            last = s;
+            uint32_t r = 0, part, rctx = last;                              // arith_dynamic.c:473-482 / :591-599
+            do {
+                uint32_t *rm = run + rctx * AR_RUN_STRIDE;
+                anomaly = false;
+                ar_load (rm, c);
+                part = ar_decode_sym<true> (rm, 4, c, rc, lane, stale, anomaly);
+                if (!anomaly) ar_dec_renorm (rc);
+                if (rctx == last) rctx = 256; else rctx += (rctx < 257);
+                r += part;
+            } while (part == 3 && r < n);
+            while (r-- && i + 1 < n) { ++i; ar_out_put (o, last); }
+        }
+    }
+    ar_out_flush (o);
+}
+
+// ---- encoder ---------------------------------------------------------------------------------------------------------------
+struct ArEnc { uint32_t low, range, ffnum, cache, carry; uint8_t *out; };
+
+AR_FN void ar_shift_low (ArEnc &rc)                                          // c_range_coder.h:70-88
+{
+    if (rc.low < (255u << 24) || rc.carry) {
+        *rc.out = (uint8_t)(rc.cache + rc.carry);
+        for (uint32_t i = 0; i < rc.ffnum; i++) rc.out[1 + i] = (uint8_t)(rc.carry - 1);
+        rc.out += 1 + rc.ffnum; rc.ffnum = 0;
+        rc.cache = rc.low >> 24;
+        rc.carry = 0;
+    }
+    else rc.ffnum++;
+    rc.low <<= 8;
+}
+
+// SIMPLE_MODEL_encodeSymbol (:123-146) + RC_Encode (c_range_coder.h:97-109) without its renormalisation loop
+AR_FN void ar_encode_sym (uint32_t *m, uint32_t maxs, ArCache &c, ArEnc &rc, uint32_t sym, int lane, bool &stale)
+{
+    const uint32_t r = ar_div (rc.range, c.tot, c.rtot);
+    const uint32_t before = rc.low;
+    if ((c.e0 >> 16) == sym) {
+        rc.range = (c.e0 & 0xffffu) * r;
+        AR_BUMP_CASE (0, c.e0, c.e0)
+        return;
+    }
+    const uint32_t f0 = c.e0 & 0xffffu;
+    if ((c.e1 >> 16) == sym) {
+        rc.low += f0 * r; rc.range = (c.e1 & 0xffffu) * r;
+        AR_BUMP_CASE (1, c.e1, c.e0)
+    }
+    else if ((c.e2 >> 16) == sym) {
+        rc.low += (f0 + (c.e1 & 0xffffu)) * r; rc.range = (c.e2 & 0xffffu) * r;
+        AR_BUMP_CASE (2, c.e2, c.e1)
+    }
+    else if ((c.e3 >> 16) == sym) {
+        rc.low += (f0 + (c.e1 & 0xffffu) + (c.e2 & 0xffffu)) * r; rc.range = (c.e3 & 0xffffu) * r;
+        AR_BUMP_CASE (3, c.e3, c.e2)
+    }
+    else {
+        uint32_t acc, e;
+        const uint32_t p = ar_find_sym (m, maxs, sym, lane, acc, e);
+        if (p >= maxs) return;                                              // cannot happen for a symbol < maxs
+        rc.low += acc * r; rc.range = (e & 0xffffu) * r;
+        ar_update_mem (m, maxs, p, e, c.tot, lane);
+        stale = true;
+    }
+    rc.carry += rc.low < before;
+}
+
+// arith_compress_O0 / O1 (arith_dynamic.c:92-126, 157-197) and the RLE variants (:387-448, :496-561).  Returns the body
+// length, or n + 1 once the body is certain to reach the input length (it is then discarded for a raw copy, :847-852;
+// stopping early also bounds the scratch a hostile, expanding input can touch).
+template <bool O1>
+AR_FN uint32_t ar_encode_leaf (uint32_t *lit, uint32_t maxs, bool rle, const uint8_t *in, uint32_t n, uint8_t *out, int lane)
+{
+    const uint32_t stride = ar_stride (maxs);
+    uint32_t *run = lit + (O1 ? 256 : 1) * stride;
+    out[0] = (uint8_t)maxs;                                                  // arith_dynamic.c:105-110 (256 wraps to 0)
+    ArEnc rc; rc.low = 0; rc.range = 0xffffffffu; rc.ffnum = 0; rc.cache = 0; rc.carry = 0; rc.out = out + 1;
+    const uint8_t *limit = out + n + 8;
+    ArCache c;
+    uint32_t *m = lit;
+    if (!rle) {
+        uint32_t ctx = 0;
+        ar_load (m, c);
+        uint32_t s_next = n ? __ldg (in) : 0;
+        for (uint32_t i = 0; i < n; i++) {
+            const uint32_t s = s_next;
+            if (i + 1 < n) s_next = __ldg (in + i + 1);
+            // the next symbol's context is this symbol: its model is fetched while this symbol is coded (this symbol
+            // only touches the current context's model)
+            ArCache nx; nx = c;
+            const bool sw = O1 && s != ctx;
+            if (sw) ar_load (lit + s * stride, nx);
+            bool stale = false;
+            ar_encode_sym (m, maxs, c, rc, s, lane, stale);
+            if (rc.range < AR_TOP) {
+                do { rc.range <<= 8; ar_shift_low (rc); } while (rc.range < AR_TOP);
+                if (rc.out + rc.ffnum > limit) return n + 1;
+            }
+            if (sw) { c = nx; ctx = s; m = lit + s * stride; }
+            else if (stale) ar_load (m, c);
+        }
+    }
+    else {
+        uint32_t last = 0;
+        for (uint32_t i = 0; i < n; ) {
+            if (rc.out + rc.ffnum > limit) return n + 1;
+            bool stale = false;
+            const uint32_t s = __ldg (in + i);
+            m = lit + (O1 ? last : 0) * stride;
+            ar_load (m, c);
+            ar_encode_sym (m, maxs, c, rc, s, lane, stale);
+            while (rc.range < AR_TOP) { rc.range <<= 8; ar_shift_low (rc); }
+            last = s; i++;
+            uint32_t r = 0;                                                 // :413-438 run length in base-4 digits
+            while (i < n && __ldg (in + i) == last) { r++; i++; }
+            uint32_t rctx = last;
+            do {
+                const uint32_t d = r < 4 ? r : 3;
+                uint32_t *rm = run + rctx * AR_RUN_STRIDE;
+                ar_load (rm, c);
+                ar_encode_sym (rm, 4, c, rc, d, lane, stale);
+                while (rc.range < AR_TOP) { rc.range <<= 8; ar_shift_low (rc); }
+                r -= d;
+                if (rctx == last) rctx = 256; else rctx += (rctx < 257);
+                if (d == 3 && r == 0) {
+                    rm = run + rctx * AR_RUN_STRIDE;
+                    ar_load (rm, c);
+                    ar_encode_sym (rm, 4, c, rc, 0, lane, stale);
+                    while (rc.range < AR_TOP) { rc.range <<= 8; ar_shift_low (rc); }
+                }
+            } while (r);
+        }
+    }
+    for (int i = 0; i < 5; i++) ar_shift_low (rc);                          // RC_FinishEncode
+    return (uint32_t)(rc.out - out);
 }
 
 } // namespace gzb
