@@ -23,7 +23,7 @@ struct EncLane {
     const EncSym  * __restrict__ tab;    // O0: shared-memory table by symbol; O1: global table by rank pair
     const uint8_t *rank;                 // shared memory
     uint8_t *end;
-    uint32_t n, nsym;
+    uint32_t n, nsym, shift;
     bool valid;
 };
 
@@ -106,6 +106,33 @@ __device__ __forceinline__ uint32_t encode_o1 (const EncLane &f, const uint8_t *
     uint32_t l = f.valid ? srank[f.in[pstart + 1]] : 0;
     uint32_t maxsteps = steps;
     for (int o = 16; o; o >>= 1) maxsteps = max (maxsteps, __shfl_xor_sync (0xffffffffu, maxsteps, o));
+    // ---- the hot transition: a symbol that follows itself with probability >= 63/64 (e.g. the ACGT exception stream, 99.9 %
+    // zeros).  Its encoder symbol is kept in registers and a block of 4 steps in which every lane of the warp codes it is
+    // run without any table access: one aligned word load brings the lane's 4 input bytes, one compare recognises them.
+    uint32_t hrank = 0xffffffffu, hot4b = 0;
+    EncSym H; H.x_max = 0; H.rcp = 0; H.bias = 0; H.cmpl_sh = 0;
+    {
+        const uint32_t size = 1u << f.shift;
+        uint32_t best = 0;
+        if (f.valid) for (uint32_t rr = k; rr < ns; rr += 4) {
+            const EncSym e = __ldg4 (f.tab + rr * ns + rr);
+            const uint32_t fr = size - (e.cmpl_sh & 0xffffu);
+            if (fr <= size && fr >= size - (size >> 6) && e.x_max == ((RANS_L >> f.shift) << 16) * fr) best = max (best, (fr << 8) | rr);
+        }
+        best = max (best, __shfl_xor_sync (0xffffffffu, best, 1));
+        best = max (best, __shfl_xor_sync (0xffffffffu, best, 2));
+        uint32_t b = 0;                                                      // the byte value of that rank (rank 0 is symbol 0: forced present, :741)
+        if (best) {
+            hrank = best & 0xffu;
+            H = __ldg4 (f.tab + hrank * ns + hrank);
+            if (hrank) for (uint32_t c = k ? k : 4; c < 256; c += 4) if (srank[c] == hrank) b = c;
+        }
+        b = max (b, __shfl_xor_sync (0xffffffffu, b, 1));                   // (warp-wide shuffles stay outside divergent code)
+        b = max (b, __shfl_xor_sync (0xffffffffu, b, 2));
+        hot4b = b * 0x01010101u;
+    }
+    const bool hot_on = __any_sync (0xffffffffu, hrank != 0xffffffffu);
+    const uint32_t hsh = H.cmpl_sh >> 16, hcmpl = H.cmpl_sh & 0xffffu;
     uint32_t s = 0;
     while (s < maxsteps) {
         const bool active = f.valid && s < steps;
@@ -113,7 +140,62 @@ __device__ __forceinline__ uint32_t encode_o1 (const EncLane &f, const uint8_t *
         // from s >= r (lanes 0-2 have joined) to steps-1 (exclusive)
         uint32_t lim = active ? (s >= r ? steps - 1 : 0u) : 0xffffffffu;
         for (int o = 16; o; o >>= 1) lim = min (lim, __shfl_xor_sync (0xffffffffu, lim, o));
-        if (lim != 0xffffffffu && s + 4 <= lim) {
+        if (hot_on && lim != 0xffffffffu && s + 4 <= lim) {
+            const uint8_t *ip = active ? f.in + (pstart - (s - delay)) : f.in + 3;
+            // sliding window of aligned words over the lane's bytes: a block's bytes are in[ip-3 .. ip]
+            const uintptr_t A = reinterpret_cast<uintptr_t>(ip) - 3;
+            const uint32_t sh8 = 8u * (uint32_t)(A & 3);
+            const uint32_t *wp32 = reinterpret_cast<const uint32_t *>(A & ~(uintptr_t)3);
+            uint32_t w_lo = 0, w_hi = 0;
+            if (active) { w_lo = __ldg (wp32); if (sh8) w_hi = __ldg (wp32 + 1); }
+            uint32_t cb = __funnelshift_r (w_lo, w_hi, sh8);               // byte 0 = in[ip-3] ... byte 3 = in[ip]
+            uint32_t backoff = 0, hskip = 0, hfail = 0;
+            for (; s + 4 <= lim; s += 4) {
+                const uint32_t bytes = cb;
+                wp32--;
+                if (active && s + 8 <= lim) {
+                    w_hi = w_lo; w_lo = __ldg (wp32); cb = __funnelshift_r (w_lo, w_hi, sh8);
+                }
+                bool done = false;
+                if (hskip == 0) {
+                    const bool ishot = !active || (bytes == hot4b && l == hrank);
+                    if (__all_sync (0xffffffffu, ishot)) {
+                        uint32_t y = x; bool emit = false;
+                        #pragma unroll
+                        for (int t = 0; t < 4; t++) { emit |= y >= H.x_max; y = y + H.bias + (__umulhi (y, H.rcp) >> hsh) * hcmpl; }
+                        if (!__any_sync (0xffffffffu, emit && active)) { if (active) x = y; done = true; }
+                    }
+                    if (done) hfail = 0; else { hfail = min (2 * hfail + 1, 15u); hskip = hfail; }
+                }
+                else hskip--;
+                if (done) continue;
+                EncSym c0, c1, c2, c3;
+                c0.x_max = c1.x_max = c2.x_max = c3.x_max = 0xffffffffu; c0.rcp = c1.rcp = c2.rcp = c3.rcp = 0;
+                c0.bias = c1.bias = c2.bias = c3.bias = 0; c0.cmpl_sh = c1.cmpl_sh = c2.cmpl_sh = c3.cmpl_sh = 0;
+                if (active) {
+                    const uint32_t r0 = srank[bytes >> 24], r1 = srank[(bytes >> 16) & 0xffu], r2 = srank[(bytes >> 8) & 0xffu], r3 = srank[bytes & 0xffu];
+                    c0 = __ldg4 (f.tab + r0 * ns + l); c1 = __ldg4 (f.tab + r1 * ns + r0); c2 = __ldg4 (f.tab + r2 * ns + r1); c3 = __ldg4 (f.tab + r3 * ns + r2);
+                    l = r3;
+                }
+                bool exact = backoff != 0;
+                if (!exact) {
+                    uint32_t y = x; bool emit = false;
+                    #define SPEC(c) { emit |= y >= c.x_max; y = y + c.bias + (__umulhi (y, c.rcp) >> (c.cmpl_sh >> 16)) * (c.cmpl_sh & 0xffffu); }
+                    SPEC (c0) SPEC (c1) SPEC (c2) SPEC (c3)
+                    #undef SPEC
+                    if (__any_sync (0xffffffffu, emit && active)) { exact = true; backoff = 5; }
+                    else if (active) x = y;
+                }
+                if (exact) {
+                    backoff--;
+                    enc_step (x, wp, c0, active, k, gshift);
+                    enc_step (x, wp, c1, active, k, gshift);
+                    enc_step (x, wp, c2, active, k, gshift);
+                    enc_step (x, wp, c3, active, k, gshift);
+                }
+            }
+        }
+        else if (lim != 0xffffffffu && s + 4 <= lim) {
             const uint8_t *ip = active ? f.in + (pstart - (s - delay)) : f.in + 3;
             EncSym e0, e1, e2, e3;
             #define LOAD_O1() { const uint32_t r0 = srank[__ldg (ip)], r1 = srank[__ldg (ip - 1)], r2 = srank[__ldg (ip - 2)], r3 = srank[__ldg (ip - 3)]; \
@@ -173,14 +255,14 @@ __global__ void __launch_bounds__(32) k_rans_encode (const EncLeaf *leaves, EncL
     if (blockIdx.x >= n_jobs) return;
     const uint2 job = jobs[blockIdx.x];
     const int lane = threadIdx.x, grp = lane >> 2, k = lane & 3;
-    EncLane f; f.valid = false; f.in = nullptr; f.tab = nullptr; f.rank = nullptr; f.end = nullptr; f.n = f.nsym = 0;
+    EncLane f; f.valid = false; f.in = nullptr; f.tab = nullptr; f.rank = nullptr; f.end = nullptr; f.n = f.nsym = 0; f.shift = 12;
     uint32_t li = 0; bool o1 = false;
     if ((uint32_t)grp < job.y) {
         li = order_list[job.x + grp];
         const EncLeaf &L = leaves[li];
         const EncLeafDyn &D = dyn[li];
         if (D.eff_n && D.symtab) {
-            f.valid = true; f.in = D.eff_in; f.n = D.eff_n; f.nsym = D.nsym; f.tab = D.symtab; f.rank = D.rank;
+            f.valid = true; f.in = D.eff_in; f.n = D.eff_n; f.nsym = D.nsym; f.tab = D.symtab; f.rank = D.rank; f.shift = D.shift;
             o1 = D.eff_order;
             f.end = L.outbuf + (L.out_cap & ~1u);
         }
@@ -215,7 +297,7 @@ struct DecLane {
     const uint2    *lut;        // O0 (shared memory for single-leaf jobs)
     const uint32_t * __restrict__ lut1;   // O1 merged LUT
     const uint8_t  *symof;      // O1 row -> symbol (shared memory)
-    uint32_t n, body_len, shift, row0;
+    uint32_t n, body_len, shift, row0, nctx;
     bool valid;
 };
 
@@ -287,6 +369,32 @@ __device__ __forceinline__ void decode_o1 (const DecLane &d, const uint8_t *ssym
     uint32_t win = 0;
     #define PUT_SLOW(b) do { win = __byte_perm (win, (b), 0x4321); const uintptr_t A = reinterpret_cast<uintptr_t>(op); const uint32_t cnt = (uint32_t)(op - op0); \
                              if ((A & 3) == 3 && cnt >= 3) *reinterpret_cast<uint32_t *>(A - 3) = win; else if (cnt < head_end) *op = (uint8_t)(b); op++; } while (0)
+    // ---- the hot transition (see encode_o1): a symbol that follows itself with probability >= 63/64 is decoded from
+    // registers — slot range [hotB, hotB + hotF) of LUT row hot_coff — without touching the LUT.  Found by probing the
+    // middle slot of every row (an interval longer than half the table contains it) and verified on both of its ends.
+    uint32_t hotF = 0, hotB = 0, hot_coff = 0xffffffffu, hot4 = 0;
+    {
+        const uint32_t size = 1u << shift, mid = size >> 1;
+        uint32_t best = 0;
+        if (d.valid) for (uint32_t rr = k; rr < d.nctx; rr += 4) {
+            const uint32_t e = __ldg (d.lut1 + (rr << shift) + mid);
+            const uint32_t F = ((e >> 8) & 0xfffu) + 1;
+            if ((e & 0xffu) == rr && F >= size - (size >> 6)) best = max (best, (F << 8) | rr);
+        }
+        best = max (best, __shfl_xor_sync (0xffffffffu, best, 1));
+        best = max (best, __shfl_xor_sync (0xffffffffu, best, 2));
+        if (best) {
+            const uint32_t rr = best & 0xffu, F = best >> 8;
+            const uint32_t e = __ldg (d.lut1 + (rr << shift) + mid);
+            const uint32_t B = mid - (e >> 20);
+            if (B <= mid && B + F <= size) {
+                const uint32_t e_lo = __ldg (d.lut1 + (rr << shift) + B), e_hi = __ldg (d.lut1 + (rr << shift) + B + F - 1);
+                const uint32_t want = rr | ((F - 1) << 8);
+                if (e_lo == want && e_hi == (want | ((F - 1) << 20))) { hotF = F; hotB = B; hot_coff = rr << shift; hot4 = (uint32_t)ssym[rr] * 0x01010101u; }
+            }
+        }
+    }
+    const bool hot_on = __any_sync (0xffffffffu, hotF != 0);
     uint32_t s = 0;
     while (s < maxsteps) {
         const bool active = d.valid && s < steps;
@@ -298,8 +406,33 @@ __device__ __forceinline__ void decode_o1 (const DecLane &d, const uint8_t *ssym
             // Speculation as in the encoder: a block is first decoded without the shared read pointer logic; if any lane of the
             // warp dropped below the renormalisation bound the block is replayed exactly (the speculative word stores are
             // simply overwritten).  16 exact blocks follow a failed speculation.
-            uint32_t backoff = 0;
+            uint32_t backoff = 0, hskip = 0, hfail = 0;
+            const uint32_t hsh = 8u * (4u - ph);                             // bytes of a hot block that complete the lane's current word
             for (; s + 4 <= lim; s += 4) {
+                if (hot_on) {
+                    if (hskip == 0) {
+                        uint32_t y = x; bool bad = false;
+                        #pragma unroll
+                        for (int t = 0; t < 4; t++) {
+                            const uint32_t dd = (y & mask) - hotB;
+                            bad |= dd >= hotF;
+                            y = hotF * (y >> shift) + dd;
+                            bad |= y < RANS_L;
+                        }
+                        bad = active && (bad || coff != hot_coff);
+                        if (!__any_sync (0xffffffffu, bad)) {
+                            if (active) {
+                                x = y;
+                                *reinterpret_cast<uint32_t *>(op - ph) = __funnelshift_rc (win, hot4, hsh);
+                                win = hot4; op += 4;
+                            }
+                            hfail = 0;
+                            continue;
+                        }
+                        hfail = min (2 * hfail + 1, 15u); hskip = hfail;
+                    }
+                    else hskip--;
+                }
                 bool exact = backoff != 0;
                 if (!exact) {
                     uint32_t y = x, yc = coff, yw = win; bool low = false;
@@ -369,14 +502,14 @@ __global__ void __launch_bounds__(32) k_rans_decode (DecLeaf *leaves, const uint
     const uint2 job = jobs[blockIdx.x];
     const int lane = threadIdx.x, grp = lane >> 2;
     DecLane d; d.valid = false; d.body = nullptr; d.out = nullptr; d.lut = nullptr; d.lut1 = nullptr; d.symof = nullptr;
-    d.n = d.body_len = d.row0 = 0; d.shift = 12;
+    d.n = d.body_len = d.row0 = d.nctx = 0; d.shift = 12;
     bool o1 = false; uint32_t poff = 0;
     const DecLeaf *Lp = nullptr;
     if ((uint32_t)grp < job.y) {
         const DecLeaf &L = leaves[list[job.x + grp]];
         if (L.valid && !L.err && !L.cat && L.body_ulen && (L.lut || L.lut1)) {
             d.valid = true; o1 = L.order; d.body = L.body; d.body_len = L.body_len; d.out = L.dst; d.n = L.body_ulen;
-            poff = L.payload_off; d.lut = L.lut; d.lut1 = L.lut1; d.shift = L.shift; d.row0 = L.ctxrank[0];
+            poff = L.payload_off; d.lut = L.lut; d.lut1 = L.lut1; d.shift = L.shift; d.row0 = L.ctxrank[0]; d.nctx = L.nctx;
             Lp = &L;
         }
     }
