@@ -143,6 +143,13 @@ AR_FN void ar_store_head (uint32_t *m, uint32_t tot, float rtot)
     *reinterpret_cast<uint2 *>(m) = h;
 }
 
+AR_FN void ar_flush (uint32_t *m, const ArCache &c)                        // registers -> memory (write-back of the run loop's updates)
+{
+    ar_store_head (m, c.tot, c.rtot);
+    uint4 v; v.x = c.e0; v.y = c.e1; v.z = c.e2; v.w = c.e3;
+    *reinterpret_cast<uint4 *>(m + 4) = v;
+}
+
 // Update of entry p directly on memory: Freq += STEP, TotFreq += STEP, halve everything past MAX_FREQ (normalize,
 // :106-116), one bubble step towards the front (:140-145).  e = current value of entry p, tot = current TotFreq.
 // Used for entries beyond the cached four and for every update that triggers the halving.  Leaves memory
@@ -288,11 +295,11 @@ struct ArDec { uint32_t code, range, ipos, ilen; const uint8_t *in; };
 // ANY: also handles range < TotFreq (possible only after the input ran dry): the reference then codes entry 0 without
 // dividing the range.
 template <bool ANY>
-AR_FN uint32_t ar_decode_sym (uint32_t *m, uint32_t maxs, ArCache &c, ArDec &rc, int lane, bool &stale, bool &anomaly)
+AR_FN uint32_t ar_decode_sym (uint32_t *m, uint32_t maxs, ArCache &c, ArDec &rc, int lane, bool &stale, bool &anomaly, uint32_t r_in = 0)
 {
     uint32_t sym;
     const bool forced = ANY && rc.range < c.tot;
-    const uint32_t r = forced ? rc.range : ar_div (rc.range, c.tot, c.rtot);
+    const uint32_t r = ANY ? (forced ? rc.range : ar_div (rc.range, c.tot, c.rtot)) : r_in;   // !ANY: the caller has divided already
     const uint32_t f0 = c.e0 & 0xffffu;
     const uint32_t t1 = f0 * r;
     if (rc.code < t1 || forced) {
@@ -334,24 +341,25 @@ AR_FN bool ar_dec_renorm (ArDec &rc)
 // Output bytes are gathered in a 32-bit window and written one aligned word at a time (a byte store per symbol from
 // hundreds of concurrent leaves is what the L2 write path chokes on); head and tail bytes go out singly.
 struct ArOut {
-    uint8_t *base;              // out rounded down to 4 bytes
+    uint8_t *wptr;              // address of the aligned word being filled
     uint32_t pos, head, win;    // pos = (out & 3) + symbols written; head = out & 3
 };
-AR_FN void ar_out_init (ArOut &o, uint8_t *out) { o.head = (uint32_t)(reinterpret_cast<uintptr_t>(out) & 3); o.base = out - o.head; o.pos = o.head; o.win = 0; }
+AR_FN void ar_out_init (ArOut &o, uint8_t *out) { o.head = (uint32_t)(reinterpret_cast<uintptr_t>(out) & 3); o.wptr = out - o.head; o.pos = o.head; o.win = 0; }
 AR_FN void ar_out_put (ArOut &o, uint32_t b)
 {
     o.win = __byte_perm (o.win, b, 0x4321);
-    if ((o.pos & 3) == 3) {
-        if (o.pos == 3 && o.head) { for (uint32_t t = o.head; t < 4; t++) o.base[t] = (uint8_t)(o.win >> (8 * t)); }
-        else *reinterpret_cast<uint32_t *>(o.base + (o.pos - 3)) = o.win;
-    }
     o.pos++;
+    if ((o.pos & 3) == 0) {
+        if (o.pos == 4 && o.head) { for (uint32_t t = o.head; t < 4; t++) o.wptr[t] = (uint8_t)(o.win >> (8 * t)); }
+        else *reinterpret_cast<uint32_t *>(o.wptr) = o.win;
+        o.wptr += 4;
+    }
 }
 AR_FN void ar_out_flush (ArOut &o)
 {
     const uint32_t tail = o.pos & 3;                                        // bytes after the last aligned word boundary
     const uint32_t first = (o.pos < 4) ? o.head : 0;                        // never touch bytes before the leaf's output
-    for (uint32_t t = first; t < tail; t++) o.base[(o.pos - tail) + t] = (uint8_t)(o.win >> (8 * (4 - tail + t)));
+    for (uint32_t t = first; t < tail; t++) o.wptr[t] = (uint8_t)(o.win >> (8 * (4 - tail + t)));
 }
 
 // arith_uncompress_O0 / O1 (arith_dynamic.c:129-152, 200-226) and the RLE variants (:451-493, :564-608)
@@ -368,18 +376,37 @@ AR_FN void ar_decode_leaf (uint32_t *lit, uint32_t maxs, bool rle, const uint8_t
     uint32_t ctx = 0, i = 0;
     uint32_t *m = lit;
     if (!rle) {
-        // fast loop: invariant range >= TOP (so range >= TotFreq); left for good at the first anomaly
+        // fast loop: invariant range >= TOP (so range >= TotFreq); left for good at the first anomaly.
+        // RUN STEP: the context's top entry is decoded again and (order 1) it is the context itself — by far the most
+        // frequent case of a low-entropy stream.  It touches registers only: the model head is written back (ar_flush)
+        // when another kind of symbol turns up.
         ar_load (m, c);
-        bool ok = true;
-        for (; i < n && ok; i++) {
+        bool ok = true, dirty = false;
+        bool selfloop = !O1 || (c.e0 >> 16) == ctx;
+        while (i < n && ok) {
+            const uint32_t r = ar_div (rc.range, c.tot, c.rtot);
+            const uint32_t t1 = (c.e0 & 0xffffu) * r;
+            if (rc.code < t1 && selfloop && c.tot + AR_STEP <= AR_MAXF) {
+                rc.range = t1;
+                c.e0 += AR_STEP; c.tot += AR_STEP; c.rtot = ar_rcp_below (c.tot);
+                dirty = true;
+                ar_out_put (o, c.e0 >> 16);
+                i++;
+                if (rc.range < AR_TOP) ok = ar_dec_renorm (rc);
+                continue;
+            }
+            if (dirty) { ar_flush (m, c); dirty = false; }
             bool stale = false, anomaly = false;
-            const uint32_t s = ar_decode_sym<false> (m, maxs, c, rc, lane, stale, anomaly);
+            const uint32_t s = ar_decode_sym<false> (m, maxs, c, rc, lane, stale, anomaly, r);
             if (anomaly) ok = false;
             else if (rc.range < AR_TOP) ok = ar_dec_renorm (rc);
             ar_out_put (o, s);
+            i++;
             if (O1 && s != ctx) { ctx = s; m = lit + s * stride; ar_load (m, c); }
             else if (stale) ar_load (m, c);
+            selfloop = !O1 || (c.e0 >> 16) == ctx;
         }
+        if (dirty) ar_flush (m, c);
         for (; i < n; i++) {                                                // after an anomaly: the reference's exact (odd) behaviour
             bool stale = false, anomaly = false;
             ar_load (m, c);
@@ -481,23 +508,34 @@ AR_FN uint32_t ar_encode_leaf (uint32_t *lit, uint32_t maxs, bool rle, const uin
     if (!rle) {
         uint32_t ctx = 0;
         ar_load (m, c);
+        bool dirty = false;
         uint32_t s_next = n ? __ldg (in) : 0;
         for (uint32_t i = 0; i < n; i++) {
             const uint32_t s = s_next;
             if (i + 1 < n) s_next = __ldg (in + i + 1);
-            // the next symbol's context is this symbol: its model is fetched while this symbol is coded (this symbol
-            // only touches the current context's model)
-            ArCache nx; nx = c;
-            const bool sw = O1 && s != ctx;
-            if (sw) ar_load (lit + s * stride, nx);
-            bool stale = false;
-            ar_encode_sym (m, maxs, c, rc, s, lane, stale);
+            // RUN STEP (see ar_decode_leaf): the symbol is the context's top entry and the context does not change
+            if ((c.e0 >> 16) == s && (!O1 || s == ctx) && c.tot + AR_STEP <= AR_MAXF) {
+                const uint32_t r = ar_div (rc.range, c.tot, c.rtot);
+                rc.range = (c.e0 & 0xffffu) * r;
+                c.e0 += AR_STEP; c.tot += AR_STEP; c.rtot = ar_rcp_below (c.tot);
+                dirty = true;
+            }
+            else {
+                if (dirty) { ar_flush (m, c); dirty = false; }
+                // the next symbol's context is this symbol: its model is fetched while this symbol is coded (this symbol
+                // only touches the current context's model)
+                ArCache nx; nx = c;
+                const bool sw = O1 && s != ctx;
+                if (sw) ar_load (lit + s * stride, nx);
+                bool stale = false;
+                ar_encode_sym (m, maxs, c, rc, s, lane, stale);
+                if (sw) { c = nx; ctx = s; m = lit + s * stride; }
+                else if (stale) ar_load (m, c);
+            }
             if (rc.range < AR_TOP) {
                 do { rc.range <<= 8; ar_shift_low (rc); } while (rc.range < AR_TOP);
                 if (rc.out + rc.ffnum > limit) return n + 1;
             }
-            if (sw) { c = nx; ctx = s; m = lit + s * stride; }
-            else if (stale) ar_load (m, c);
         }
     }
     else {

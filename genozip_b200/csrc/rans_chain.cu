@@ -140,60 +140,67 @@ __device__ __forceinline__ uint32_t encode_o1 (const EncLane &f, const uint8_t *
         // from s >= r (lanes 0-2 have joined) to steps-1 (exclusive)
         uint32_t lim = active ? (s >= r ? steps - 1 : 0u) : 0xffffffffu;
         for (int o = 16; o; o >>= 1) lim = min (lim, __shfl_xor_sync (0xffffffffu, lim, o));
-        if (hot_on && lim != 0xffffffffu && s + 4 <= lim) {
-            const uint8_t *ip = active ? f.in + (pstart - (s - delay)) : f.in + 3;
-            // sliding window of aligned words over the lane's bytes: a block's bytes are in[ip-3 .. ip]
+        if (hot_on && lim != 0xffffffffu && s + 16 <= lim) {
+            // super-blocks of 16 steps.  The lane's 16 input bytes in[ip-15 .. ip] come as 4 funnel-shifted aligned words
+            // (sliding window, loaded one super-block ahead); a super-block in which every lane of the warp sees only the
+            // hot symbol runs from registers: 4 instructions per step, one vote per 16 steps.  The state grows
+            // monotonically under the hot symbol, so testing the value before the last step covers the emit test of all 16.
+            const uint8_t *ip = active ? f.in + (pstart - (s - delay)) : f.in + 15;
             const uintptr_t A = reinterpret_cast<uintptr_t>(ip) - 3;
             const uint32_t sh8 = 8u * (uint32_t)(A & 3);
-            const uint32_t *wp32 = reinterpret_cast<const uint32_t *>(A & ~(uintptr_t)3);
-            uint32_t w_lo = 0, w_hi = 0;
-            if (active) { w_lo = __ldg (wp32); if (sh8) w_hi = __ldg (wp32 + 1); }
-            uint32_t cb = __funnelshift_r (w_lo, w_hi, sh8);               // byte 0 = in[ip-3] ... byte 3 = in[ip]
+            const uint32_t *wp32 = reinterpret_cast<const uint32_t *>(A & ~(uintptr_t)3);     // aligned word holding in[ip-3]
+            uint32_t n0 = 0, n1 = 0, n2 = 0, n3 = 0, wlast = 0;         // n_j: bytes of sub-block j (byte 3 = first coded); wlast: lowest word loaded
+            #define LOAD_SUPER() { const uint32_t a0 = __ldg (wp32), a1 = __ldg (wp32 - 1), a2 = __ldg (wp32 - 2), a3 = __ldg (wp32 - 3); \
+                                   n0 = __funnelshift_r (a0, wlast, sh8); n1 = __funnelshift_r (a1, a0, sh8); n2 = __funnelshift_r (a2, a1, sh8); \
+                                   n3 = __funnelshift_r (a3, a2, sh8); wlast = a3; wp32 -= 4; }
+            if (active) { if (sh8) wlast = __ldg (wp32 + 1); LOAD_SUPER (); }
             uint32_t backoff = 0, hskip = 0, hfail = 0;
-            for (; s + 4 <= lim; s += 4) {
-                const uint32_t bytes = cb;
-                wp32--;
-                if (active && s + 8 <= lim) {
-                    w_hi = w_lo; w_lo = __ldg (wp32); cb = __funnelshift_r (w_lo, w_hi, sh8);
-                }
+            for (; s + 16 <= lim; s += 16) {
+                const uint32_t b0 = n0, b1 = n1, b2 = n2, b3 = n3;
+                if (active && s + 32 <= lim) LOAD_SUPER ();
                 bool done = false;
                 if (hskip == 0) {
-                    const bool ishot = !active || (bytes == hot4b && l == hrank);
+                    const bool ishot = !active || (b0 == hot4b && b1 == hot4b && b2 == hot4b && b3 == hot4b && l == hrank);
                     if (__all_sync (0xffffffffu, ishot)) {
-                        uint32_t y = x; bool emit = false;
+                        uint32_t y = x, ylast = x;
                         #pragma unroll
-                        for (int t = 0; t < 4; t++) { emit |= y >= H.x_max; y = y + H.bias + (__umulhi (y, H.rcp) >> hsh) * hcmpl; }
-                        if (!__any_sync (0xffffffffu, emit && active)) { if (active) x = y; done = true; }
+                        for (int t = 0; t < 16; t++) { ylast = y; y = y + H.bias + (__umulhi (y, H.rcp) >> hsh) * hcmpl; }
+                        if (!__any_sync (0xffffffffu, active && ylast >= H.x_max)) { if (active) x = y; done = true; }
                     }
-                    if (done) hfail = 0; else { hfail = min (2 * hfail + 1, 15u); hskip = hfail; }
+                    if (done) hfail = 0; else { hfail = min (2 * hfail + 1, 7u); hskip = hfail; }
                 }
                 else hskip--;
                 if (done) continue;
-                EncSym c0, c1, c2, c3;
-                c0.x_max = c1.x_max = c2.x_max = c3.x_max = 0xffffffffu; c0.rcp = c1.rcp = c2.rcp = c3.rcp = 0;
-                c0.bias = c1.bias = c2.bias = c3.bias = 0; c0.cmpl_sh = c1.cmpl_sh = c2.cmpl_sh = c3.cmpl_sh = 0;
-                if (active) {
-                    const uint32_t r0 = srank[bytes >> 24], r1 = srank[(bytes >> 16) & 0xffu], r2 = srank[(bytes >> 8) & 0xffu], r3 = srank[bytes & 0xffu];
-                    c0 = __ldg4 (f.tab + r0 * ns + l); c1 = __ldg4 (f.tab + r1 * ns + r0); c2 = __ldg4 (f.tab + r2 * ns + r1); c3 = __ldg4 (f.tab + r3 * ns + r2);
-                    l = r3;
-                }
-                bool exact = backoff != 0;
-                if (!exact) {
-                    uint32_t y = x; bool emit = false;
-                    #define SPEC(c) { emit |= y >= c.x_max; y = y + c.bias + (__umulhi (y, c.rcp) >> (c.cmpl_sh >> 16)) * (c.cmpl_sh & 0xffffu); }
-                    SPEC (c0) SPEC (c1) SPEC (c2) SPEC (c3)
-                    #undef SPEC
-                    if (__any_sync (0xffffffffu, emit && active)) { exact = true; backoff = 5; }
-                    else if (active) x = y;
-                }
-                if (exact) {
-                    backoff--;
-                    enc_step (x, wp, c0, active, k, gshift);
-                    enc_step (x, wp, c1, active, k, gshift);
-                    enc_step (x, wp, c2, active, k, gshift);
-                    enc_step (x, wp, c3, active, k, gshift);
+                #pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t bytes = j == 0 ? b0 : j == 1 ? b1 : j == 2 ? b2 : b3;
+                    EncSym c0, c1, c2, c3;
+                    c0.x_max = c1.x_max = c2.x_max = c3.x_max = 0xffffffffu; c0.rcp = c1.rcp = c2.rcp = c3.rcp = 0;
+                    c0.bias = c1.bias = c2.bias = c3.bias = 0; c0.cmpl_sh = c1.cmpl_sh = c2.cmpl_sh = c3.cmpl_sh = 0;
+                    if (active) {
+                        const uint32_t r0 = srank[bytes >> 24], r1 = srank[(bytes >> 16) & 0xffu], r2 = srank[(bytes >> 8) & 0xffu], r3 = srank[bytes & 0xffu];
+                        c0 = __ldg4 (f.tab + r0 * ns + l); c1 = __ldg4 (f.tab + r1 * ns + r0); c2 = __ldg4 (f.tab + r2 * ns + r1); c3 = __ldg4 (f.tab + r3 * ns + r2);
+                        l = r3;
+                    }
+                    bool exact = backoff != 0;
+                    if (!exact) {
+                        uint32_t y = x; bool emit = false;
+                        #define SPEC(c) { emit |= y >= c.x_max; y = y + c.bias + (__umulhi (y, c.rcp) >> (c.cmpl_sh >> 16)) * (c.cmpl_sh & 0xffffu); }
+                        SPEC (c0) SPEC (c1) SPEC (c2) SPEC (c3)
+                        #undef SPEC
+                        if (__any_sync (0xffffffffu, emit && active)) { exact = true; backoff = 5; }
+                        else if (active) x = y;
+                    }
+                    if (exact) {
+                        backoff--;
+                        enc_step (x, wp, c0, active, k, gshift);
+                        enc_step (x, wp, c1, active, k, gshift);
+                        enc_step (x, wp, c2, active, k, gshift);
+                        enc_step (x, wp, c3, active, k, gshift);
+                    }
                 }
             }
+            #undef LOAD_SUPER
         }
         else if (lim != 0xffffffffu && s + 4 <= lim) {
             const uint8_t *ip = active ? f.in + (pstart - (s - delay)) : f.in + 3;
@@ -408,25 +415,28 @@ __device__ __forceinline__ void decode_o1 (const DecLane &d, const uint8_t *ssym
             // simply overwritten).  16 exact blocks follow a failed speculation.
             uint32_t backoff = 0, hskip = 0, hfail = 0;
             const uint32_t hsh = 8u * (4u - ph);                             // bytes of a hot block that complete the lane's current word
+            const uint32_t hcm = (1u << shift) - hotF;
             for (; s + 4 <= lim; s += 4) {
-                if (hot_on) {
+                if (hot_on && s + 16 <= lim) {
+                    // 16 hot steps from registers: x' = F*(x >> shift) + (x & mask) - B  =  x - (x >> shift)*(size - F) - B, a
+                    // two-instruction dependency per step.  The state only shrinks, so the renormalisation test of the last
+                    // step covers all 16; the slot test (x & mask) - B < F is tracked as a running maximum.
                     if (hskip == 0) {
-                        uint32_t y = x; bool bad = false;
+                        uint32_t y = x, dmax = 0;
                         #pragma unroll
-                        for (int t = 0; t < 4; t++) {
-                            const uint32_t dd = (y & mask) - hotB;
-                            bad |= dd >= hotF;
-                            y = hotF * (y >> shift) + dd;
-                            bad |= y < RANS_L;
+                        for (int t = 0; t < 16; t++) {
+                            dmax = max (dmax, (y & mask) - hotB);
+                            y = (y - hotB) - (y >> shift) * hcm;
                         }
-                        bad = active && (bad || coff != hot_coff);
+                        const bool bad = active && (dmax >= hotF || y < RANS_L || coff != hot_coff);
                         if (!__any_sync (0xffffffffu, bad)) {
                             if (active) {
                                 x = y;
-                                *reinterpret_cast<uint32_t *>(op - ph) = __funnelshift_rc (win, hot4, hsh);
-                                win = hot4; op += 4;
+                                uint32_t *w = reinterpret_cast<uint32_t *>(op - ph);
+                                w[0] = __funnelshift_rc (win, hot4, hsh); w[1] = hot4; w[2] = hot4; w[3] = hot4;
+                                win = hot4; op += 16;
                             }
-                            hfail = 0;
+                            hfail = 0; s += 12;
                             continue;
                         }
                         hfail = min (2 * hfail + 1, 15u); hskip = hfail;
