@@ -253,6 +253,8 @@ def run_gpu(args):
             t = torch.tensor([ok], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MIN); ok = int(t.item())
         if ok:
             break
+        if path is not None:
+            path.close()
         del path, data
         eng.close(); torch.cuda.empty_cache()
         eng = Engine(local)
@@ -290,10 +292,10 @@ def run_gpu(args):
                 e0.record(stream)
                 m = fn_zip()
                 section_list_gather(m if isinstance(m, list) else m[0])
-                kz = (eng.L.gzb_last_kernel_ms(eng.h, 0), eng.L.gzb_last_kernel_ms(eng.h, 1))
+                kz = path.kernel_ms
                 e1.record(stream)
                 r = fn_piz(m if isinstance(m, list) else m[0])
-                kp = (eng.L.gzb_last_kernel_ms(eng.h, 0), eng.L.gzb_last_kernel_ms(eng.h, 1))
+                kp = path.kernel_ms
                 e2.record(stream)
             barrier()
             if i >= warmup:
@@ -305,9 +307,9 @@ def run_gpu(args):
         return t[0].item() / steps, t[1].item() / steps, {k: v / steps for k, v in kern.items()}, (m, r)
 
     clocks = ClockSampler(local); clocks.start()
-    l0 = eng.launches
+    l0 = path.launches
     zip_ms, piz_ms, kern, (meta, _) = timed(lambda: path.zip_device(data), lambda m: path.piz_device(m), args.steps, args.warmup)
-    launches = (eng.launches - l0) // (args.steps + args.warmup) * args.steps
+    launches = (path.launches - l0) // (args.steps + args.warmup) * args.steps
     clk = clocks.stop()
     value = world * txt_bytes / ((zip_ms + piz_ms) * 1e-3) / 1e9
 
@@ -336,7 +338,7 @@ def run_gpu(args):
             if n:
                 alg["rans" if codecs[s].startswith("RAN") else "arith"] += n + m["comp_len"][s]
     dom = max(kern, key=lambda k: kern[k])
-    dom_bytes = alg["rans" if dom.startswith("rans") else "arith"]
+    dom_bytes = alg["rans" if dom.startswith("rans") else "arith"] // len(path.groups)    # each group launches the chain kernel once
     achieved = dom_bytes / (kern[dom] * 1e-3) / 1e9 if kern[dom] > 0 else 0.0
     kname = {"rans_enc": "k_rans_encode", "rans_dec": "k_rans_decode", "arith_enc": "k_arith_encode", "arith_dec": "k_arith_decode"}[dom]
     traffic = None
@@ -372,7 +374,8 @@ def run_gpu(args):
                        "reads_per_vblock": args.reads, "read_len": args.read_len, "txt_bytes_per_step_per_gpu": txt_bytes,
                        "codecs": codecs, "l2": "inputs (>= 0.9 GB per step) are larger than L2; no flush needed",
                        "sections_per_step": sum(1 for m in meta for n in m["len"].values() if n), "compressed_bytes_per_step": comp_total,
-                       "excluded": "segmenter; LZMA of the 2-bit sequence words (host, out of scope)", "sharding": "VBlocks round-robin by vblock_i, no data-path collective; NCCL all_gather of the section list only"},
+                       "excluded": "segmenter; LZMA of the 2-bit sequence words (host, out of scope)", "sharding": "VBlocks round-robin by vblock_i, no data-path collective; NCCL all_gather of the section list only",
+                       "engines_per_gpu": len(path.engs), "device_groups": len(path.groups)},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
         }))
     if world > 1:

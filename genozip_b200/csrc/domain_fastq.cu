@@ -47,7 +47,7 @@ __device__ __forceinline__ uint32_t acgt_code (uint32_t c)
 }
 
 // one thread = 32 bases = one little-endian 64-bit word (codec_acgt.c:45-55) + 32 exception bytes (:67-70,104-107)
-__global__ void k_acgt_pack (const uint8_t *seq, uint64_t n, uint64_t *packed, uint8_t *x, int *x_nonzero)
+__device__ __forceinline__ void acgt_pack_body (const uint8_t * __restrict__ seq, uint64_t n, uint64_t * __restrict__ packed, uint8_t * __restrict__ x, int *x_nonzero)
 {
     __shared__ uint8_t lut[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = (uint8_t)acgt_code (i);
@@ -100,8 +100,14 @@ __global__ void k_acgt_pack (const uint8_t *seq, uint64_t n, uint64_t *packed, u
     if (any && (threadIdx.x & 31) == 0) atomicOr (x_nonzero, 1);
 }
 
+__global__ void k_acgt_pack (const uint8_t *seq, uint64_t n, uint64_t *packed, uint8_t *x, int *x_nonzero) { acgt_pack_body (seq, n, packed, x, x_nonzero); }
+
+// a batch of VBlocks in one launch: blockIdx.y = VBlock
+struct AcgtD { const uint8_t *seq; uint64_t n; uint64_t *packed; uint8_t *x; int *flag; };
+__global__ void k_acgt_pack_batch (const AcgtD *d) { const AcgtD a = d[blockIdx.y]; if (a.n) acgt_pack_body (a.seq, a.n, a.packed, a.x, a.flag); }
+
 // codec_acgt_uncompress / codec_xcgt_uncompress (:185-248): one thread = 32 bases
-__global__ void k_acgt_unpack (const uint64_t *packed, const uint8_t *x, uint64_t n, uint8_t *seq)
+__device__ __forceinline__ void acgt_unpack_body (const uint64_t * __restrict__ packed, const uint8_t * __restrict__ x, uint64_t n, uint8_t * __restrict__ seq)
 {
     const uint64_t nwords = (2 * n + 63) / 64;
     for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += (uint64_t)gridDim.x * blockDim.x) {
@@ -137,6 +143,9 @@ __global__ void k_acgt_unpack (const uint64_t *packed, const uint8_t *x, uint64_
         }
     }
 }
+
+__global__ void k_acgt_unpack (const uint64_t *packed, const uint8_t *x, uint64_t n, uint8_t *seq) { acgt_unpack_body (packed, x, n, seq); }
+__global__ void k_acgt_unpack_batch (const AcgtD *d) { const AcgtD a = d[blockIdx.y]; if (a.n) acgt_unpack_body (a.packed, a.x, a.n, const_cast<uint8_t *>(a.seq)); }
 
 // ================================================================================================ DOMQ
 constexpr int NQ = 95, FIRST_Q = 32;              // printable qualities ' '..'~' (codec_domq.c:31-33)
@@ -537,6 +546,115 @@ extern "C" int gzb_acgt_unpack (gzb_engine *e, const void *packed, const void *x
         e->launches++;
     }
     if (!devptr && n) CK (cudaMemcpyAsync (seq, d_seq, n, cudaMemcpyDeviceToHost, st));
+    CK (cudaStreamSynchronize (st));
+    return GZB_OK;
+}
+
+// Batched forms: every VBlock of the batch in ONE launch (and one stream synchronisation) instead of one per VBlock.
+// Host-pointer mode stages the whole batch in the engine workspace; with GZB_OUT_DEVICE (pack) / GZB_IN_DEVICE (unpack)
+// the exception streams stay in the caller's device buffers, as in the single-VBlock calls.
+extern "C" int gzb_acgt_pack_batch (gzb_engine *e, gzb_acgt_vb *vbs, uint32_t n_vbs, uint32_t flags)
+{
+    if (!e || (!vbs && n_vbs)) return GZB_E_BADARG;
+    if (!n_vbs) return GZB_OK;
+    cudaSetDevice (e->device);
+    const bool devptr = flags & GZB_DEVICE_PTRS, xdev_f = !devptr && (flags & GZB_OUT_DEVICE);
+    cudaStream_t st = e->stream;
+    Carver c { nullptr, 0 };
+    AcgtD *d_desc = nullptr; int *d_flags = nullptr;
+    std::vector<AcgtD> h (n_vbs);
+    uint64_t max_words = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        c.off = 0;
+        d_desc = c.take<AcgtD> (n_vbs); d_flags = c.take<int> (n_vbs);
+        for (uint32_t v = 0; v < n_vbs; v++) {
+            const gzb_acgt_vb &a = vbs[v];
+            if ((!a.seq && a.n_bases) || !a.packed) return GZB_E_BADARG;
+            const uint64_t plen = gzb_acgt_packed_len (a.n_bases);
+            max_words = std::max<uint64_t> (max_words, plen / 8);
+            AcgtD &D = h[v];
+            D.n = a.n_bases;
+            if (devptr) { D.seq = (const uint8_t *)a.seq; D.packed = (uint64_t *)a.packed; D.x = (uint8_t *)a.x; }
+            else {
+                D.seq = c.take<uint8_t> (a.n_bases + 32); D.packed = reinterpret_cast<uint64_t *>(c.take<uint8_t> (plen + 32));
+                D.x = (xdev_f && a.x) ? (uint8_t *)a.x : c.take<uint8_t> (a.n_bases + 32);
+            }
+        }
+        if (pass == 0) { int rc = engine_reserve (e, c.off, (size_t)n_vbs * (sizeof (AcgtD) + sizeof (int)) + 4096); if (rc) return rc; c.base = e->ws; }
+    }
+    for (uint32_t v = 0; v < n_vbs; v++) h[v].flag = d_flags + v;
+    AcgtD *p_desc = reinterpret_cast<AcgtD *>(e->pin); int *p_flags = reinterpret_cast<int *>(e->pin + (size_t)n_vbs * sizeof (AcgtD));
+    memcpy (p_desc, h.data (), (size_t)n_vbs * sizeof (AcgtD));
+    CK (cudaMemcpyAsync (d_desc, p_desc, (size_t)n_vbs * sizeof (AcgtD), cudaMemcpyHostToDevice, st));
+    CK (cudaMemsetAsync (d_flags, 0, (size_t)n_vbs * sizeof (int), st));
+    if (!devptr) for (uint32_t v = 0; v < n_vbs; v++) if (vbs[v].n_bases) CK (cudaMemcpyAsync (const_cast<uint8_t *>(h[v].seq), vbs[v].seq, vbs[v].n_bases, cudaMemcpyHostToDevice, st));
+    if (max_words) {
+        dim3 grid ((uint32_t)std::min<uint64_t> ((max_words + 255) / 256, 4096), n_vbs);
+        k_acgt_pack_batch<<<grid, 256, 0, st>>>(d_desc);
+        e->launches++;
+    }
+    CK (cudaMemcpyAsync (p_flags, d_flags, (size_t)n_vbs * sizeof (int), cudaMemcpyDeviceToHost, st));
+    if (!devptr) for (uint32_t v = 0; v < n_vbs; v++) {
+        const uint64_t plen = gzb_acgt_packed_len (vbs[v].n_bases);
+        if (plen) CK (cudaMemcpyAsync (vbs[v].packed, h[v].packed, plen, cudaMemcpyDeviceToHost, st));
+    }
+    CK (cudaStreamSynchronize (st));
+    bool more = false;
+    for (uint32_t v = 0; v < n_vbs; v++) {
+        vbs[v].x_all_zero = !p_flags[v];
+        const bool xdev = xdev_f && vbs[v].x;
+        if (!devptr && !xdev && vbs[v].x && vbs[v].n_bases) {
+            if (p_flags[v]) { CK (cudaMemcpyAsync (vbs[v].x, h[v].x, vbs[v].n_bases, cudaMemcpyDeviceToHost, st)); more = true; }
+            else memset (vbs[v].x, 0, vbs[v].n_bases);                       // all-zero exception stream: no transfer needed
+        }
+    }
+    if (more) CK (cudaStreamSynchronize (st));
+    return GZB_OK;
+}
+
+extern "C" int gzb_acgt_unpack_batch (gzb_engine *e, const gzb_acgt_vb *vbs, uint32_t n_vbs, uint32_t flags)
+{
+    if (!e || (!vbs && n_vbs)) return GZB_E_BADARG;
+    if (!n_vbs) return GZB_OK;
+    cudaSetDevice (e->device);
+    const bool devptr = flags & GZB_DEVICE_PTRS, xdev_f = !devptr && (flags & GZB_IN_DEVICE);
+    cudaStream_t st = e->stream;
+    Carver c { nullptr, 0 };
+    AcgtD *d_desc = nullptr;
+    std::vector<AcgtD> h (n_vbs);
+    uint64_t max_words = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        c.off = 0;
+        d_desc = c.take<AcgtD> (n_vbs);
+        for (uint32_t v = 0; v < n_vbs; v++) {
+            const gzb_acgt_vb &a = vbs[v];
+            if ((!a.packed && a.n_bases) || !a.seq) return GZB_E_BADARG;
+            const uint64_t plen = gzb_acgt_packed_len (a.n_bases);
+            max_words = std::max<uint64_t> (max_words, plen / 8);
+            AcgtD &D = h[v];
+            D.n = a.n_bases; D.flag = nullptr;
+            if (devptr) { D.seq = (const uint8_t *)a.seq; D.packed = (uint64_t *)a.packed; D.x = (uint8_t *)a.x; }
+            else {
+                D.seq = c.take<uint8_t> (a.n_bases + 32); D.packed = reinterpret_cast<uint64_t *>(c.take<uint8_t> (plen + 32));
+                D.x = !a.x ? nullptr : xdev_f ? (uint8_t *)a.x : c.take<uint8_t> (a.n_bases + 32);
+            }
+        }
+        if (pass == 0) { int rc = engine_reserve (e, c.off, (size_t)n_vbs * sizeof (AcgtD) + 4096); if (rc) return rc; c.base = e->ws; }
+    }
+    AcgtD *p_desc = reinterpret_cast<AcgtD *>(e->pin);
+    memcpy (p_desc, h.data (), (size_t)n_vbs * sizeof (AcgtD));
+    CK (cudaMemcpyAsync (d_desc, p_desc, (size_t)n_vbs * sizeof (AcgtD), cudaMemcpyHostToDevice, st));
+    if (!devptr) for (uint32_t v = 0; v < n_vbs; v++) {
+        const uint64_t plen = gzb_acgt_packed_len (vbs[v].n_bases);
+        if (plen) CK (cudaMemcpyAsync (h[v].packed, vbs[v].packed, plen, cudaMemcpyHostToDevice, st));
+        if (vbs[v].x && !xdev_f && vbs[v].n_bases) CK (cudaMemcpyAsync (h[v].x, vbs[v].x, vbs[v].n_bases, cudaMemcpyHostToDevice, st));
+    }
+    if (max_words) {
+        dim3 grid ((uint32_t)std::min<uint64_t> ((max_words + 255) / 256, 4096), n_vbs);
+        k_acgt_unpack_batch<<<grid, 256, 0, st>>>(d_desc);
+        e->launches++;
+    }
+    if (!devptr) for (uint32_t v = 0; v < n_vbs; v++) if (vbs[v].n_bases) CK (cudaMemcpyAsync (const_cast<void *>(vbs[v].seq), h[v].seq, vbs[v].n_bases, cudaMemcpyDeviceToHost, st));
     CK (cudaStreamSynchronize (st));
     return GZB_OK;
 }

@@ -47,6 +47,11 @@ class DomqPizVb(C.Structure):       # gzb_domq_piz_vb
                 ("line_len", C.c_void_p), ("n_lines", C.c_uint32), ("out", C.c_void_p), ("out_cap", C.c_uint64)]
 
 
+class AcgtVb(C.Structure):         # gzb_acgt_vb
+    _fields_ = [("seq", C.c_void_p), ("n_bases", C.c_uint64), ("packed", C.c_void_p), ("x", C.c_void_p),
+                ("x_all_zero", C.c_int32), ("reserved", C.c_uint32)]
+
+
 class LongrVb(C.Structure):         # gzb_longr_vb
     _fields_ = [("txt", C.c_void_p), ("txt_len", C.c_uint64), ("seq_off", C.c_void_p), ("qual_off", C.c_void_p),
                 ("len", C.c_void_p), ("is_rev", C.c_void_p), ("n_lines", C.c_uint32), ("value_to_bin", C.c_uint8 * 256),
@@ -92,6 +97,9 @@ def load():
     L.gzb_acgt_pack.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_uint32]
     L.gzb_acgt_unpack.restype = C.c_int
     L.gzb_acgt_unpack.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32]
+    for nm in ("gzb_acgt_pack_batch", "gzb_acgt_unpack_batch"):
+        getattr(L, nm).restype = C.c_int
+        getattr(L, nm).argtypes = [C.c_void_p, C.POINTER(AcgtVb), C.c_uint32, C.c_uint32]
     for nm in ("gzb_domq_prepare", "gzb_domq_split"):
         getattr(L, nm).restype = C.c_int
         getattr(L, nm).argtypes = [C.c_void_p, C.POINTER(DomqVb), C.c_uint32, C.c_uint32]
@@ -229,6 +237,41 @@ class Engine:
         if rc != 0:
             raise GzbError(f"gzb_acgt_unpack failed ({rc}): {self._err()}")
         return out[:n]
+
+    def acgt_pack_batch(self, seqs):
+        """gzb_acgt_pack_batch on host buffers: list of uint8 arrays -> list of (packed, x, x_all_zero)"""
+        n = len(seqs)
+        arr = (AcgtVb * n)()
+        keep = []
+        for i, seq in enumerate(seqs):
+            seq = np.ascontiguousarray(seq, dtype=np.uint8)
+            packed = np.zeros(int(self.L.gzb_acgt_packed_len(seq.size)) or 1, np.uint8)
+            x = np.full(max(seq.size, 1), 0xAA, np.uint8)
+            keep.append((seq, packed, x))
+            arr[i].seq = seq.ctypes.data if seq.size else x.ctypes.data; arr[i].n_bases = seq.size
+            arr[i].packed = packed.ctypes.data; arr[i].x = x.ctypes.data
+        rc = self.L.gzb_acgt_pack_batch(self.h, arr, n, 0)
+        if rc != 0:
+            raise GzbError(f"gzb_acgt_pack_batch failed ({rc}): {self._err()}")
+        return [(p[:int(self.L.gzb_acgt_packed_len(s.size))], x[:s.size], bool(arr[i].x_all_zero)) for i, (s, p, x) in enumerate(keep)]
+
+    def acgt_unpack_batch(self, items):
+        """gzb_acgt_unpack_batch on host buffers: list of (packed, x or None, n) -> list of uint8 arrays"""
+        n = len(items)
+        arr = (AcgtVb * n)()
+        keep = []
+        for i, (packed, x, nb) in enumerate(items):
+            packed = np.ascontiguousarray(packed, dtype=np.uint8)
+            x = None if x is None else np.ascontiguousarray(x, dtype=np.uint8)
+            out = np.zeros(max(nb, 1), np.uint8)
+            keep.append((packed, x, out))
+            arr[i].seq = out.ctypes.data; arr[i].n_bases = nb
+            arr[i].packed = packed.ctypes.data if packed.size else out.ctypes.data
+            arr[i].x = None if x is None else x.ctypes.data
+        rc = self.L.gzb_acgt_unpack_batch(self.h, arr, n, 0)
+        if rc != 0:
+            raise GzbError(f"gzb_acgt_unpack_batch failed ({rc}): {self._err()}")
+        return [o[:items[i][2]] for i, (_, _, o) in enumerate(keep)]
 
     # ---- DOMQ (host buffers): batch of VBlocks, each (txt, line_off, line_len) ----
     def domq_encode(self, vbs):

@@ -101,6 +101,21 @@ uint64_t gzb_acgt_packed_len (uint64_t n_bases);
 int gzb_acgt_pack   (gzb_engine *e, const void *seq, uint64_t n_bases, void *packed, void *x, int *x_all_zero, uint32_t flags);
 int gzb_acgt_unpack (gzb_engine *e, const void *packed, const void *x, uint64_t n_bases, void *seq, uint32_t flags);
 
+/* Batched forms — all VBlocks of a batch in one launch and one synchronisation (what a dispatcher that hands the
+ * GPU many VBlocks at once, SURVEY §8b item 4, calls instead of one gzb_acgt_pack per compute thread).
+ * pack:   in  seq, n_bases, packed, x (may be NULL)      out  packed bytes, x bytes, x_all_zero
+ * unpack: in  packed, x (NULL = acgt_no_x), n_bases, seq out  seq bytes */
+typedef struct gzb_acgt_vb {
+    const void *seq;        /* unpack: output buffer (written) */
+    uint64_t    n_bases;
+    void       *packed;
+    void       *x;
+    int32_t     x_all_zero; /* pack: out */
+    uint32_t    reserved;
+} gzb_acgt_vb;
+int gzb_acgt_pack_batch   (gzb_engine *e, gzb_acgt_vb *vbs, uint32_t n_vbs, uint32_t flags);
+int gzb_acgt_unpack_batch (gzb_engine *e, const gzb_acgt_vb *vbs, uint32_t n_vbs, uint32_t flags);
+
 /* ---------------------------------------------------------------- DOMQ (src/codec_domq.c)
  * A VBlock's quality lines are given as a text buffer plus a (offset,len) table (H6 in SURVEY §7: never a per-line callback). */
 typedef struct {

@@ -36,6 +36,21 @@ def test_acgt(eng):
     assert np.array_equal(eng.acgt_unpack(p, x, s.size), s)
 
 
+def test_acgt_batch(eng):
+    """gzb_acgt_pack_batch / gzb_acgt_unpack_batch: ragged VBlocks (incl. empty, all-ACGT) in one launch vs the oracle"""
+    seq, _ = fastq_vb(3000, 151, 3, lower_frac=0.01, n_frac=0.01)
+    pure = np.frombuffer(b"ACGT", np.uint8)[np.random.default_rng(4).integers(0, 4, 70001)].copy()
+    seqs = [seq[:n].copy() for n in (0, 1, 33, 4097, 100000, seq.size)] + [pure]
+    got = eng.acgt_pack_batch(seqs)
+    items = []
+    for s, (p, x, allz) in zip(seqs, got):
+        pw, xw, zw = orc.acgt_pack(s)
+        assert np.array_equal(p, pw) and np.array_equal(x, xw) and allz == zw, f"n={s.size}"
+        items.append((pw, None if zw else xw, s.size))
+    for s, o in zip(seqs, eng.acgt_unpack_batch(items)):
+        assert np.array_equal(o, s), f"n={s.size}"
+
+
 def _check_domq(eng, vbs):
     got = eng.domq_encode(vbs)
     for (txt, off, ln), g in zip(vbs, got):
