@@ -90,8 +90,9 @@ extern "C" int gzb_engine_create (int device, gzb_engine **out)
     if (cudaSetDevice (device) != cudaSuccess || cudaStreamCreateWithFlags (&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
         g_last_error = "cudaStreamCreate failed"; delete e; return GZB_E_CUDA;
     }
-    cudaEventCreate (&e->ev0); cudaEventCreate (&e->ev1); cudaEventCreate (&e->ev2); cudaEventCreate (&e->ev3);
+    cudaEventCreate (&e->ev0); cudaEventCreate (&e->ev1); cudaEventCreate (&e->ev2); cudaEventCreate (&e->ev3); cudaEventCreate (&e->ev4);
     cudaStreamCreateWithFlags (&e->stream2, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags (&e->stream3, cudaStreamNonBlocking);
     // log tables for the order-1 table-size decision: must come from the same libm the reference links
     double l10[257], l12[257];
     for (int k = 0; k <= 256; k++) { l10[k] = log ((double)(1024 + k)); l12[k] = log ((double)(4096 + k)); }
@@ -110,8 +111,9 @@ extern "C" void gzb_engine_destroy (gzb_engine *e)
     if (e->dq_buf) cudaFree (e->dq_buf);
     if (e->dq_session && e->dq_free) e->dq_free (e->dq_session);
     if (e->pin) cudaFreeHost (e->pin);
-    cudaEventDestroy (e->ev0); cudaEventDestroy (e->ev1); cudaEventDestroy (e->ev2); cudaEventDestroy (e->ev3);
+    cudaEventDestroy (e->ev0); cudaEventDestroy (e->ev1); cudaEventDestroy (e->ev2); cudaEventDestroy (e->ev3); cudaEventDestroy (e->ev4);
     if (e->stream2) cudaStreamDestroy (e->stream2);
+    if (e->stream3) cudaStreamDestroy (e->stream3);
     cudaStreamDestroy (e->stream);
     delete e;
 }
@@ -381,7 +383,7 @@ extern "C" int gzb_compress_sections (gzb_engine *e, gzb_section *secs, uint32_t
         P.n_rans_jobs = (uint32_t)rjobs.size (); P.arith_lpw = pick_arith_lpw (P.n_arith);
         P.copy_parts = (n <= 64) ? 32 : (n <= 1024 ? 8 : 2);
         P.arena = Arena { d_arena, (unsigned long long)arena_est, d_cursor, d_overflow };
-        P.ev_chain0 = e->ev0; P.ev_chain1 = e->ev1; P.ev_chain2 = e->ev2; P.ev_arith0 = e->ev3; P.st2 = e->stream2;
+        P.ev_chain0 = e->ev0; P.ev_chain1 = e->ev1; P.ev_chain2 = e->ev2; P.ev_arith0 = e->ev3; P.st2 = e->stream2; P.ev_o0 = e->ev4; P.st3 = e->stream3;
 
         // ---- upload: metadata blob, inputs (small ones gathered through pinned staging)
         cudaStream_t st = e->stream;
@@ -524,7 +526,7 @@ extern "C" int gzb_uncompress_sections (gzb_engine *e, gzb_section *secs, uint32
         P.n_rans_jobs = (uint32_t)rjobs.size (); P.arith_lpw = pick_arith_lpw (P.n_arith);
         P.parts = (n <= 64) ? 32 : (n <= 1024 ? 8 : 2);
         P.arena = Arena { d_arena, (unsigned long long)arena_est, d_cursor, d_overflow };
-        P.ev_chain0 = e->ev0; P.ev_chain1 = e->ev1; P.ev_chain2 = e->ev2; P.ev_arith0 = e->ev3; P.st2 = e->stream2;
+        P.ev_chain0 = e->ev0; P.ev_chain1 = e->ev1; P.ev_chain2 = e->ev2; P.ev_arith0 = e->ev3; P.st2 = e->stream2; P.ev_o0 = e->ev4; P.st3 = e->stream3;
 
         cudaStream_t st = e->stream;
         memcpy (e->pin, meta.data (), meta_bytes);

@@ -8,27 +8,19 @@
 #include "gzb_internal.cuh"
 #include "hts_enc.cuh"
 #include "arith_model.cuh"
+#include "arith_o0.cuh"
 
 namespace gzb {
 
 // Order-0 leaves without the run-length models (the byte planes of the STRIPE codecs, mostly) keep their single model in
-// SHARED memory: ~1 KB per warp, ~25-cycle accesses instead of L1/L2 round trips through global memory, and no
-// dependence on what the write-through L1 does with a line that has just been stored to.
-constexpr uint32_t AR_SMEM_WORDS = 4 + 256 + 8;
+// SHARED memory and search it with per-lane running sums: arith_o0.cuh.
 
-__device__ __forceinline__ void ar_model_init_warp (uint32_t *m, uint32_t maxs, int lane)
-{
-    const uint32_t st = ar_stride (maxs);
-    for (uint32_t i = lane; i < st; i += 32) {
-        uint32_t v;
-        if (i == 0) v = maxs; else if (i == 1) v = ar_f2u (ar_rcp_below (maxs)); else if (i < 4) v = 0;
-        else if (i - 4 < maxs) v = 1u | ((i - 4) << 16); else v = 0xffff0000u;
-        m[i] = v;
-    }
-    __syncwarp ();
-}
+// Two kernels per direction, launched over the same leaf list on two streams: each warp looks at its leaf's class and
+// leaves at once if it belongs to the other kernel (separate kernels = separate register allocation for the two loops).
+__device__ __forceinline__ bool ar_is_o0_class (bool o1, bool rle) { return !o1 && !rle; }
 
-__global__ void __launch_bounds__(128) k_arith_encode (const EncLeaf *leaves, EncLeafDyn *dyn, const uint32_t *list, uint32_t n_list)
+template <bool O0CLASS>
+__global__ void __launch_bounds__(128) k_arith_encode_t (const EncLeaf *leaves, EncLeafDyn *dyn, const uint32_t *list, uint32_t n_list)
 {
     const int lane = threadIdx.x & 31;
     const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -41,14 +33,13 @@ __global__ void __launch_bounds__(128) k_arith_encode (const EncLeaf *leaves, En
     const bool o1 = D.eff_order, rle = (D.hdr[0] & F_RLE) != 0;
     uint32_t *lit = D.models;
     uint8_t *out = L.outbuf;
-    if (!lit) return;
-    __shared__ __align__(16) uint32_t s_model[4][AR_SMEM_WORDS];
+    if (!lit || ar_is_o0_class (o1, rle) != O0CLASS) return;
     __builtin_assume (__isGlobal (lit)); __builtin_assume (__isGlobal (out)); __builtin_assume (__isGlobal (in));
     uint32_t len;
-    if (!o1 && !rle) {
-        uint32_t *sm = s_model[threadIdx.x >> 5];
-        ar_model_init_warp (sm, maxs, lane);
-        len = ar_encode_leaf<false> (sm, maxs, false, in, n, out, lane);
+    if (O0CLASS) {
+        __shared__ __align__(16) uint8_t s_model[4][AR0_SMEM_BYTES];
+        uint8_t *sm = s_model[threadIdx.x >> 5];
+        len = ar0_encode_leaf (reinterpret_cast<uint32_t *>(sm), sm + AR0_E_WORDS * 4, maxs, in, n, out, lane);
     }
     else len = o1 ? ar_encode_leaf<true> (lit, maxs, rle, in, n, out, lane) : ar_encode_leaf<false> (lit, maxs, rle, in, n, out, lane);
     if (lane == 0) {
@@ -59,10 +50,15 @@ __global__ void __launch_bounds__(128) k_arith_encode (const EncLeaf *leaves, En
 
 void launch_arith_encode (EncPlanDev &P, cudaStream_t st)
 {
-    k_arith_encode<<<(P.n_arith + 3) / 4, 128, 0, st>>>(P.leaves, P.dyn, P.arith_list, P.n_arith);
+    k_arith_encode_t<false><<<(P.n_arith + 3) / 4, 128, 0, st>>>(P.leaves, P.dyn, P.arith_list, P.n_arith);
+}
+void launch_arith_encode_o0 (EncPlanDev &P, cudaStream_t st)
+{
+    k_arith_encode_t<true><<<(P.n_arith + 3) / 4, 128, 0, st>>>(P.leaves, P.dyn, P.arith_list, P.n_arith);
 }
 
-__global__ void __launch_bounds__(128) k_arith_decode (DecLeaf *leaves, const uint32_t *list, uint32_t n_list)
+template <bool O0CLASS>
+__global__ void __launch_bounds__(128) k_arith_decode_t (DecLeaf *leaves, const uint32_t *list, uint32_t n_list)
 {
     const int lane = threadIdx.x & 31;
     const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -71,15 +67,23 @@ __global__ void __launch_bounds__(128) k_arith_decode (DecLeaf *leaves, const ui
     if (!L.valid || L.err || L.cat || !L.body_ulen || !L.models) return;
     const uint32_t n = L.body_ulen, maxs = L.nsym;
     const bool o1 = L.order == 1, rle = L.rle;
+    if (ar_is_o0_class (o1, rle) != O0CLASS) return;
     uint32_t *lit = L.models;
     uint8_t *out = L.dst;
     const uint8_t * __restrict__ body = L.body;
-    __shared__ __align__(16) uint32_t s_model[4][AR_SMEM_WORDS];
     __builtin_assume (__isGlobal (lit)); __builtin_assume (__isGlobal (out)); __builtin_assume (__isGlobal (body));
-    if (!o1 && !rle) {
-        uint32_t *sm = s_model[threadIdx.x >> 5];
-        ar_model_init_warp (sm, maxs, lane);
-        ar_decode_leaf<false> (sm, maxs, false, body, L.body_len, out, n, lane);
+    if (O0CLASS) {
+        __shared__ __align__(16) uint8_t s_model[4][AR0_SMEM_BYTES];
+        uint32_t *E = reinterpret_cast<uint32_t *>(s_model[threadIdx.x >> 5]);
+        Ar0 a; ar0_init (E, nullptr, maxs, lane, a);
+        ArDec rc; ar_dec_start (rc, body, L.body_len);
+        ArOut o; ar_out_init (o, out);
+        const uint32_t done = ar0_decode_run (E, maxs, a, rc, o, n, lane);
+        if (done < n) {                                                     // corrupt / truncated stream: finish exactly like the reference, through memory
+            ar0_export (E, a, lit, maxs, lane);
+            ar_decode_tail<false> (lit, maxs, rc, o, done, n, 0, lane);
+        }
+        ar_out_flush (o);
     }
     else if (o1) ar_decode_leaf<true> (lit, maxs, rle, body, L.body_len, out, n, lane);
     else         ar_decode_leaf<false> (lit, maxs, rle, body, L.body_len, out, n, lane);
@@ -87,7 +91,11 @@ __global__ void __launch_bounds__(128) k_arith_decode (DecLeaf *leaves, const ui
 
 void launch_arith_decode (DecPlanDev &P, cudaStream_t st)
 {
-    k_arith_decode<<<(P.n_arith + 3) / 4, 128, 0, st>>>(P.leaves, P.arith_list, P.n_arith);
+    k_arith_decode_t<false><<<(P.n_arith + 3) / 4, 128, 0, st>>>(P.leaves, P.arith_list, P.n_arith);
+}
+void launch_arith_decode_o0 (DecPlanDev &P, cudaStream_t st)
+{
+    k_arith_decode_t<true><<<(P.n_arith + 3) / 4, 128, 0, st>>>(P.leaves, P.arith_list, P.n_arith);
 }
 
 } // namespace gzb

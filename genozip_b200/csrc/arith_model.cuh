@@ -183,66 +183,68 @@ AR_SLOW void ar_update_mem (uint32_t *m, uint32_t maxs, uint32_t p, uint32_t e, 
 }
 
 // ---- warp-wide searches beyond the cached entries: lane l owns entries 8l .. 8l+7 ----------------------------------------
-// decoder: first entry p whose cumulative frequency exceeds freq; returns p (>= maxs: none — corrupt input),
-// acc = cumulative frequency before p, e = entry p
-AR_SLOW uint32_t ar_find_freq (const uint32_t *m, uint32_t maxs, uint32_t freq, int lane, uint32_t &acc, uint32_t &e)
+// decoder: the first entry p whose inclusive cumulative frequency times r exceeds code — the reference's
+// "AccFreq += Freq until it exceeds code / r" (c_simple_model.h:156) without dividing.  Returns p (>= maxs: none — corrupt
+// input), acc = cumulative frequency before p, e = entry p, prev = entry p-1 (p > 0).
+// One scan of the 32 lane sums locates the owning lane; its 8 entries are then walked by all lanes together (uniform,
+// early exit), so no lane-indexed selection and no dependent load follows.
+AR_SLOW uint32_t ar_find_code (const uint32_t *m, uint32_t maxs, uint32_t code, uint32_t r, int lane, uint32_t &acc, uint32_t &e, uint32_t &prev)
 {
 #ifdef __CUDA_ARCH__
     const uint32_t j0 = 8u * lane;
     uint4 a = make_uint4 (0, 0, 0, 0), b = a;
     if (j0 < maxs) { a = *reinterpret_cast<const uint4 *>(m + 4 + j0); b = *reinterpret_cast<const uint4 *>(m + 8 + j0); }
-    const uint32_t f0 = a.x & 0xffffu, f1 = a.y & 0xffffu, f2 = a.z & 0xffffu, f3 = a.w & 0xffffu,
-                   f4 = b.x & 0xffffu, f5 = b.y & 0xffffu, f6 = b.z & 0xffffu, f7 = b.w & 0xffffu;
-    const uint32_t c1 = f0, c2 = c1 + f1, c3 = c2 + f2, c4 = c3 + f3, c5 = c4 + f4, c6 = c5 + f5, c7 = c6 + f6, c8 = c7 + f7;
-    uint32_t s = c8;                                                        // inclusive scan of the lane sums
+    const uint32_t s = ((a.x & 0xffffu) + (a.y & 0xffffu)) + ((a.z & 0xffffu) + (a.w & 0xffffu)) +
+                       ((b.x & 0xffffu) + (b.y & 0xffffu)) + ((b.z & 0xffffu) + (b.w & 0xffffu));
+    uint32_t inc = s;                                                       // inclusive scan of the lane sums
     #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync (0xffffffffu, s, o); if (lane >= o) s += t; }
-    const uint32_t base = s - c8;
-    // entries are counted while their inclusive cumulative frequency is <= freq (monotone: the count is the position)
-    uint32_t k = 0, part = 0;
-    if (base + c1 <= freq) { k++; part += f0; }
-    if (base + c2 <= freq) { k++; part += f1; }
-    if (base + c3 <= freq) { k++; part += f2; }
-    if (base + c4 <= freq) { k++; part += f3; }
-    if (base + c5 <= freq) { k++; part += f4; }
-    if (base + c6 <= freq) { k++; part += f5; }
-    if (base + c7 <= freq) { k++; part += f6; }
-    if (base + c8 <= freq) { k++; part += f7; }
-    if (j0 >= maxs) { k = 0; part = 0; }
-    const uint32_t p = ar_wsum (k);
-    acc = ar_wsum (part);
-    if (p >= maxs) { e = 0; return p; }
-    e = m[4 + p];
-    return p;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync (0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    const uint32_t ball = __ballot_sync (0xffffffffu, j0 < maxs && inc * r > code);      // inc <= TotFreq: inc * r <= range, no overflow
+    if (!ball) { acc = 0; e = 0; prev = 0; return maxs; }
+    const uint32_t owner = __ffs (ball) - 1;
+    acc = __shfl_sync (0xffffffffu, inc - s, owner);
+    const uint32_t *q = m + 4 + 8 * owner;
+    const uint4 v0 = *reinterpret_cast<const uint4 *>(q), v1 = *reinterpret_cast<const uint4 *>(q + 4);
+    const uint32_t pl = q[-1];                                              // entry before the lane's first (owner 0: header padding, unused)
+    uint32_t j = 8;
+    do {
+        #define AR_WALK(J, EJ, EP) { const uint32_t f_ = (EJ) & 0xffffu; if (code < (acc + f_) * r) { e = (EJ); prev = (EP); j = J; break; } acc += f_; }
+        AR_WALK (0, v0.x, pl)   AR_WALK (1, v0.y, v0.x) AR_WALK (2, v0.z, v0.y) AR_WALK (3, v0.w, v0.z)
+        AR_WALK (4, v1.x, v0.w) AR_WALK (5, v1.y, v1.x) AR_WALK (6, v1.z, v1.y) AR_WALK (7, v1.w, v1.z)
+        #undef AR_WALK
+    } while (0);
+    if (j == 8) { acc = 0; e = 0; prev = 0; return maxs; }                  // cannot happen: the owner's inclusive threshold exceeds code
+    return 8 * owner + j;
 #else
     (void)lane;
-    acc = 0;
+    acc = 0; prev = 0;
     for (uint32_t p = 0; p < maxs; p++) {
         e = m[4 + p];
-        if (acc + (e & 0xffffu) > freq) return p;
-        acc += e & 0xffffu;
+        if (code < (acc + (e & 0xffffu)) * r) return p;
+        acc += e & 0xffffu; prev = e;
     }
     e = 0;
     return maxs;
 #endif
 }
 
-// encoder: the entry holding `sym` (always present for sym < maxs)
-AR_SLOW uint32_t ar_find_sym (const uint32_t *m, uint32_t maxs, uint32_t sym, int lane, uint32_t &acc, uint32_t &e)
+// encoder: the entry holding `sym` (always present for sym < maxs); prev = the entry before it (p > 0)
+AR_SLOW uint32_t ar_find_sym (const uint32_t *m, uint32_t maxs, uint32_t sym, int lane, uint32_t &acc, uint32_t &e, uint32_t &prev)
 {
 #ifdef __CUDA_ARCH__
     const uint32_t j0 = 8u * lane;
     uint4 a = make_uint4 (0xffff0000u, 0xffff0000u, 0xffff0000u, 0xffff0000u), b = a;
     if (j0 < maxs) { a = *reinterpret_cast<const uint4 *>(m + 4 + j0); b = *reinterpret_cast<const uint4 *>(m + 8 + j0); }
-    uint32_t mj = 8, part = 0;                                              // first match inside the lane's 8 entries; frequencies before it
-    if ((b.w >> 16) == sym) mj = 7;
-    if ((b.z >> 16) == sym) mj = 6;
-    if ((b.y >> 16) == sym) mj = 5;
-    if ((b.x >> 16) == sym) mj = 4;
-    if ((a.w >> 16) == sym) mj = 3;
-    if ((a.z >> 16) == sym) mj = 2;
-    if ((a.y >> 16) == sym) mj = 1;
-    if ((a.x >> 16) == sym) mj = 0;
+    const uint32_t lastprev = __shfl_up_sync (0xffffffffu, b.w, 1);         // the previous lane's last entry
+    uint32_t mj = 8, esel = 0, psel = 0, part = 0;                          // first match inside the lane's 8 entries; frequencies before it
+    if ((b.w >> 16) == sym) { mj = 7; esel = b.w; psel = b.z; }
+    if ((b.z >> 16) == sym) { mj = 6; esel = b.z; psel = b.y; }
+    if ((b.y >> 16) == sym) { mj = 5; esel = b.y; psel = b.x; }
+    if ((b.x >> 16) == sym) { mj = 4; esel = b.x; psel = a.w; }
+    if ((a.w >> 16) == sym) { mj = 3; esel = a.w; psel = a.z; }
+    if ((a.z >> 16) == sym) { mj = 2; esel = a.z; psel = a.y; }
+    if ((a.y >> 16) == sym) { mj = 1; esel = a.y; psel = a.x; }
+    if ((a.x >> 16) == sym) { mj = 0; esel = a.x; psel = lastprev; }
     if (mj > 0) part += a.x & 0xffffu;
     if (mj > 1) part += a.y & 0xffffu;
     if (mj > 2) part += a.z & 0xffffu;
@@ -252,24 +254,38 @@ AR_SLOW uint32_t ar_find_sym (const uint32_t *m, uint32_t maxs, uint32_t sym, in
     if (mj > 6) part += b.z & 0xffffu;
     if (mj > 7) part += b.w & 0xffffu;
     const uint32_t hit = __ballot_sync (0xffffffffu, mj < 8);
-    if (!hit) { acc = 0; e = 0; return maxs; }
+    if (!hit) { acc = 0; e = 0; prev = 0; return maxs; }
     const int w = __ffs (hit) - 1;
     const uint32_t p = 8u * w + __shfl_sync (0xffffffffu, mj, w);
     acc = ar_wsum (lane <= w ? part : 0u);
-    e = m[4 + p];
+    e = __shfl_sync (0xffffffffu, esel, w);
+    prev = __shfl_sync (0xffffffffu, psel, w);
     return p;
 #else
     (void)lane;
-    acc = 0;
+    acc = 0; prev = 0;
     for (uint32_t p = 0; p < maxs; p++) {
         e = m[4 + p];
         if ((e >> 16) == sym) return p;
-        acc += e & 0xffffu;
+        acc += e & 0xffffu; prev = e;
     }
     e = 0;
     return maxs;
 #endif
 }
+
+// entry p >= 4 (beyond the cached four) was coded: update in memory and in the cached head; the halving goes the long way
+#define AR_BUMP_DEEP(P, E, PREV)                                                                                \
+    {                                                                                                           \
+        if (c.tot + AR_STEP > AR_MAXF) { ar_update_mem (m, maxs, P, E, c.tot, lane); stale = true; }            \
+        else {                                                                                                  \
+            const uint32_t en_ = (E) + AR_STEP;                                                                 \
+            c.tot += AR_STEP; c.rtot = ar_rcp_below (c.tot);                                                    \
+            ar_store_head (m, c.tot, c.rtot);                                                                   \
+            if ((en_ & 0xffffu) > ((PREV) & 0xffffu)) { m[4 + (P) - 1] = en_; m[4 + (P)] = (PREV); if ((P) == 4) c.e3 = en_; } \
+            else m[4 + (P)] = en_;                                                                              \
+        }                                                                                                       \
+    }
 
 // ---- cached fast-path update ---------------------------------------------------------------------------------------------
 // entry K (0..3) of the cached model was coded: registers and memory are updated identically unless the halving
@@ -314,14 +330,12 @@ AR_FN uint32_t ar_decode_sym (uint32_t *m, uint32_t maxs, ArCache &c, ArDec &rc,
         else if (rc.code < t3) { rc.code -= t2; rc.range = f2 * r; sym = c.e2 >> 16; AR_BUMP_CASE (2, c.e2, c.e1) }
         else if (rc.code < t4) { rc.code -= t3; rc.range = f3 * r; sym = c.e3 >> 16; AR_BUMP_CASE (3, c.e3, c.e2) }
         else {
-            uint32_t acc, e;
-            const uint32_t freq = ar_div_smallq (rc.code, r);
-            const uint32_t p = freq > AR_MAXF ? maxs : ar_find_freq (m, maxs, freq, lane, acc, e);
-            if (p >= maxs) { rc.range = r; anomaly = true; return 0; }    // :153-154, :160-161
+            uint32_t acc, e, prev;
+            const uint32_t p = ar_find_code (m, maxs, rc.code, r, lane, acc, e, prev);
+            if (p >= maxs) { rc.range = r; anomaly = true; return 0; }    // code / r >= TotFreq (or > MAX_FREQ): :153-154, :160-161
             rc.code -= acc * r; rc.range = (e & 0xffffu) * r;
             sym = e >> 16;
-            ar_update_mem (m, maxs, p, e, c.tot, lane);
-            stale = true;
+            AR_BUMP_DEEP (p, e, prev)
         }
     }
     return sym;
@@ -362,15 +376,38 @@ AR_FN void ar_out_flush (ArOut &o)
     for (uint32_t t = first; t < tail; t++) o.wptr[t] = (uint8_t)(o.win >> (8 * (4 - tail + t)));
 }
 
+AR_FN void ar_dec_start (ArDec &rc, const uint8_t *body, uint32_t body_len)   // RC_StartDecode (c_range_coder.h:57-68); body[0] = max_sym
+{
+    rc.range = 0xffffffffu; rc.code = 0; rc.in = body; rc.ipos = 1; rc.ilen = body_len;
+    if (rc.ipos + 5 > rc.ilen) rc.ipos = rc.ilen;
+    else for (int i = 0; i < 5; i++) rc.code = (rc.code << 8) | body[rc.ipos++];
+}
+
+// symbols i .. n-1 after an anomaly (reference error return, or input exhausted): the reference's exact (odd) behaviour,
+// every symbol through memory
+template <bool O1>
+AR_FN void ar_decode_tail (uint32_t *lit, uint32_t maxs, ArDec &rc, ArOut &o, uint32_t i, uint32_t n, uint32_t ctx, int lane)
+{
+    const uint32_t stride = ar_stride (maxs);
+    uint32_t *m = lit + (O1 ? ctx : 0) * stride;
+    ArCache c;
+    for (; i < n; i++) {
+        bool stale = false, anomaly = false;
+        ar_load (m, c);
+        const uint32_t s = ar_decode_sym<true> (m, maxs, c, rc, lane, stale, anomaly);
+        if (!anomaly) ar_dec_renorm (rc);
+        ar_out_put (o, s);
+        if (O1) m = lit + s * stride;
+    }
+}
+
 // arith_uncompress_O0 / O1 (arith_dynamic.c:129-152, 200-226) and the RLE variants (:451-493, :564-608)
 template <bool O1>
 AR_FN void ar_decode_leaf (uint32_t *lit, uint32_t maxs, bool rle, const uint8_t *body, uint32_t body_len, uint8_t *out, uint32_t n, int lane)
 {
     const uint32_t stride = ar_stride (maxs);
     uint32_t *run = lit + (O1 ? 256 : 1) * stride;
-    ArDec rc; rc.range = 0xffffffffu; rc.code = 0; rc.in = body; rc.ipos = 1; rc.ilen = body_len;
-    if (rc.ipos + 5 > rc.ilen) rc.ipos = rc.ilen;                           // RC_StartDecode (c_range_coder.h:57-68)
-    else for (int i = 0; i < 5; i++) rc.code = (rc.code << 8) | body[rc.ipos++];
+    ArDec rc; ar_dec_start (rc, body, body_len);
     ArOut o; ar_out_init (o, out);
     ArCache c;
     uint32_t ctx = 0, i = 0;
@@ -407,14 +444,7 @@ AR_FN void ar_decode_leaf (uint32_t *lit, uint32_t maxs, bool rle, const uint8_t
             selfloop = !O1 || (c.e0 >> 16) == ctx;
         }
         if (dirty) ar_flush (m, c);
-        for (; i < n; i++) {                                                // after an anomaly: the reference's exact (odd) behaviour
-            bool stale = false, anomaly = false;
-            ar_load (m, c);
-            const uint32_t s = ar_decode_sym<true> (m, maxs, c, rc, lane, stale, anomaly);
-            if (!anomaly) ar_dec_renorm (rc);
-            ar_out_put (o, s);
-            if (O1) { ctx = s; m = lit + s * stride; }
-        }
+        ar_decode_tail<O1> (lit, maxs, rc, o, i, n, ctx, lane);
     }
     else {
         uint32_t last = 0;
@@ -482,12 +512,11 @@ AR_FN void ar_encode_sym (uint32_t *m, uint32_t maxs, ArCache &c, ArEnc &rc, uin
         AR_BUMP_CASE (3, c.e3, c.e2)
     }
     else {
-        uint32_t acc, e;
-        const uint32_t p = ar_find_sym (m, maxs, sym, lane, acc, e);
+        uint32_t acc, e, prev;
+        const uint32_t p = ar_find_sym (m, maxs, sym, lane, acc, e, prev);
         if (p >= maxs) return;                                              // cannot happen for a symbol < maxs
         rc.low += acc * r; rc.range = (e & 0xffffu) * r;
-        ar_update_mem (m, maxs, p, e, c.tot, lane);
-        stale = true;
+        AR_BUMP_DEEP (p, e, prev)
     }
     rc.carry += rc.low < before;
 }

@@ -7,8 +7,8 @@
 struct gzb_engine {
     int          device = 0;
     int          sm_count = 0;
-    cudaStream_t stream = nullptr, stream2 = nullptr;   // stream2: the arithmetic chain kernel runs beside the rANS one
-    cudaEvent_t  ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;   // ev0..ev1: rANS chain kernel, ev1..ev2: arithmetic chain kernel
+    cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr;   // stream2 / stream3: the arithmetic chain kernels (general / order-0) run beside the rANS one
+    cudaEvent_t  ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev4 = nullptr;   // ev0..ev1: rANS chain kernel, ev1..ev2: arithmetic chain kernel
     uint8_t     *ws = nullptr;   size_t ws_cap = 0; // device workspace (grow-only)
     uint8_t     *pin = nullptr;  size_t pin_cap = 0;// pinned host staging (grow-only)
     std::string  err;

@@ -707,10 +707,13 @@ void enc_run (EncPlanDev &P, cudaStream_t st)
         cudaEventRecord (P.ev_arith0, P.st2);
         launch_arith_encode (P, P.st2); P.launches++;
         cudaEventRecord (P.ev_chain2, P.st2);
+        cudaStreamWaitEvent (P.st3, P.ev_chain0, 0);
+        launch_arith_encode_o0 (P, P.st3); P.launches++;
+        cudaEventRecord (P.ev_o0, P.st3);
     }
     if (P.n_rans_jobs) { launch_rans_encode (P, st); P.launches++; }
     cudaEventRecord (P.ev_chain1, st);
-    if (P.n_arith) cudaStreamWaitEvent (st, P.ev_chain2, 0);
+    if (P.n_arith) { cudaStreamWaitEvent (st, P.ev_chain2, 0); cudaStreamWaitEvent (st, P.ev_o0, 0); }
     LAUNCH (k_leaf_final, (nl + 127) / 128, 128, P.leaves, P.dyn, nl);
     LAUNCH (k_section_final, (ns + 127) / 128, 128, P.sections, P.leaves, P.dyn, P.results, P.segs, P.stripe_hdr, ns);
     dim3 g (ns * SEGS_PER_SECTION, P.copy_parts);

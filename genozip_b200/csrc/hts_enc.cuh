@@ -19,8 +19,8 @@ struct EncPlanDev {              // device pointers of one encode batch
     Arena          arena;
     int            rans_gpw, arith_lpw, copy_parts;
     bool           any_pack, any_o1;
-    cudaEvent_t    ev_chain0, ev_chain1, ev_chain2, ev_arith0;   // rANS kernel: chain0..chain1 on the main stream; arithmetic: arith0..chain2 on st2
-    cudaStream_t   st2;
+    cudaEvent_t    ev_chain0, ev_chain1, ev_chain2, ev_arith0, ev_o0;   // rANS kernel: chain0..chain1 on the main stream; arithmetic: arith0..chain2 on st2; order-0 arithmetic: .. ev_o0 on st3
+    cudaStream_t   st2, st3;
     uint64_t       launches;
 };
 
@@ -33,8 +33,8 @@ struct DecPlanDev {
     SectionResult *results;
     Arena          arena;
     int            rans_gpw, arith_lpw, parts;
-    cudaEvent_t    ev_chain0, ev_chain1, ev_chain2, ev_arith0;
-    cudaStream_t   st2;
+    cudaEvent_t    ev_chain0, ev_chain1, ev_chain2, ev_arith0, ev_o0;
+    cudaStream_t   st2, st3;
     uint64_t       launches;
 };
 
@@ -45,5 +45,7 @@ void launch_rans_encode (EncPlanDev &P, cudaStream_t st);
 void launch_rans_decode (DecPlanDev &P, cudaStream_t st);
 void launch_arith_encode (EncPlanDev &P, cudaStream_t st);
 void launch_arith_decode (DecPlanDev &P, cudaStream_t st);
+void launch_arith_encode_o0 (EncPlanDev &P, cudaStream_t st);
+void launch_arith_decode_o0 (DecPlanDev &P, cudaStream_t st);
 
 } // namespace gzb
