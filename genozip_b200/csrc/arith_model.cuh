@@ -188,8 +188,12 @@ AR_SLOW void ar_update_mem (uint32_t *m, uint32_t maxs, uint32_t p, uint32_t e, 
 // input), acc = cumulative frequency before p, e = entry p, prev = entry p-1 (p > 0).
 // One scan of the 32 lane sums locates the owning lane; its 8 entries are then walked by all lanes together (uniform,
 // early exit), so no lane-indexed selection and no dependent load follows.
-AR_SLOW uint32_t ar_find_code (const uint32_t *m, uint32_t maxs, uint32_t code, uint32_t r, int lane, uint32_t &acc, uint32_t &e, uint32_t &prev)
+// (results by value: a reference into the caller's frame would put those values in local memory)
+struct ArHit { uint32_t p, acc, e, prev; };
+AR_SLOW ArHit ar_find_code (const uint32_t *m, uint32_t maxs, uint32_t code, uint32_t r, int lane)
 {
+    ArHit h; h.p = maxs; h.acc = 0; h.e = 0; h.prev = 0;
+    uint32_t acc = 0, e = 0, prev = 0;
 #ifdef __CUDA_ARCH__
     const uint32_t j0 = 8u * lane;
     uint4 a = make_uint4 (0, 0, 0, 0), b = a;
@@ -200,7 +204,7 @@ AR_SLOW uint32_t ar_find_code (const uint32_t *m, uint32_t maxs, uint32_t code, 
     #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync (0xffffffffu, inc, o); if (lane >= o) inc += t; }
     const uint32_t ball = __ballot_sync (0xffffffffu, j0 < maxs && inc * r > code);      // inc <= TotFreq: inc * r <= range, no overflow
-    if (!ball) { acc = 0; e = 0; prev = 0; return maxs; }
+    if (!ball) return h;
     const uint32_t owner = __ffs (ball) - 1;
     acc = __shfl_sync (0xffffffffu, inc - s, owner);
     const uint32_t *q = m + 4 + 8 * owner;
@@ -213,24 +217,26 @@ AR_SLOW uint32_t ar_find_code (const uint32_t *m, uint32_t maxs, uint32_t code, 
         AR_WALK (4, v1.x, v0.w) AR_WALK (5, v1.y, v1.x) AR_WALK (6, v1.z, v1.y) AR_WALK (7, v1.w, v1.z)
         #undef AR_WALK
     } while (0);
-    if (j == 8) { acc = 0; e = 0; prev = 0; return maxs; }                  // cannot happen: the owner's inclusive threshold exceeds code
-    return 8 * owner + j;
+    if (j == 8) return h;                                                  // cannot happen: the owner's inclusive threshold exceeds code
+    h.p = 8 * owner + j; h.acc = acc; h.e = e; h.prev = prev;
+    return h;
 #else
     (void)lane;
     acc = 0; prev = 0;
     for (uint32_t p = 0; p < maxs; p++) {
         e = m[4 + p];
-        if (code < (acc + (e & 0xffffu)) * r) return p;
+        if (code < (acc + (e & 0xffffu)) * r) { h.p = p; h.acc = acc; h.e = e; h.prev = prev; return h; }
         acc += e & 0xffffu; prev = e;
     }
-    e = 0;
-    return maxs;
+    return h;
 #endif
 }
 
 // encoder: the entry holding `sym` (always present for sym < maxs); prev = the entry before it (p > 0)
-AR_SLOW uint32_t ar_find_sym (const uint32_t *m, uint32_t maxs, uint32_t sym, int lane, uint32_t &acc, uint32_t &e, uint32_t &prev)
+AR_SLOW ArHit ar_find_sym (const uint32_t *m, uint32_t maxs, uint32_t sym, int lane)
 {
+    ArHit h; h.p = maxs; h.acc = 0; h.e = 0; h.prev = 0;
+    uint32_t acc = 0, e = 0, prev = 0;
 #ifdef __CUDA_ARCH__
     const uint32_t j0 = 8u * lane;
     uint4 a = make_uint4 (0xffff0000u, 0xffff0000u, 0xffff0000u, 0xffff0000u), b = a;
@@ -254,23 +260,22 @@ AR_SLOW uint32_t ar_find_sym (const uint32_t *m, uint32_t maxs, uint32_t sym, in
     if (mj > 6) part += b.z & 0xffffu;
     if (mj > 7) part += b.w & 0xffffu;
     const uint32_t hit = __ballot_sync (0xffffffffu, mj < 8);
-    if (!hit) { acc = 0; e = 0; prev = 0; return maxs; }
+    if (!hit) return h;
     const int w = __ffs (hit) - 1;
-    const uint32_t p = 8u * w + __shfl_sync (0xffffffffu, mj, w);
-    acc = ar_wsum (lane <= w ? part : 0u);
-    e = __shfl_sync (0xffffffffu, esel, w);
-    prev = __shfl_sync (0xffffffffu, psel, w);
-    return p;
+    h.p = 8u * w + __shfl_sync (0xffffffffu, mj, w);
+    h.acc = ar_wsum (lane <= w ? part : 0u);
+    h.e = __shfl_sync (0xffffffffu, esel, w);
+    h.prev = __shfl_sync (0xffffffffu, psel, w);
+    return h;
 #else
     (void)lane;
     acc = 0; prev = 0;
     for (uint32_t p = 0; p < maxs; p++) {
         e = m[4 + p];
-        if ((e >> 16) == sym) return p;
+        if ((e >> 16) == sym) { h.p = p; h.acc = acc; h.e = e; h.prev = prev; return h; }
         acc += e & 0xffffu; prev = e;
     }
-    e = 0;
-    return maxs;
+    return h;
 #endif
 }
 
@@ -330,8 +335,8 @@ AR_FN uint32_t ar_decode_sym (uint32_t *m, uint32_t maxs, ArCache &c, ArDec &rc,
         else if (rc.code < t3) { rc.code -= t2; rc.range = f2 * r; sym = c.e2 >> 16; AR_BUMP_CASE (2, c.e2, c.e1) }
         else if (rc.code < t4) { rc.code -= t3; rc.range = f3 * r; sym = c.e3 >> 16; AR_BUMP_CASE (3, c.e3, c.e2) }
         else {
-            uint32_t acc, e, prev;
-            const uint32_t p = ar_find_code (m, maxs, rc.code, r, lane, acc, e, prev);
+            const ArHit h = ar_find_code (m, maxs, rc.code, r, lane);
+            const uint32_t p = h.p, acc = h.acc, e = h.e, prev = h.prev;
             if (p >= maxs) { rc.range = r; anomaly = true; return 0; }    // code / r >= TotFreq (or > MAX_FREQ): :153-154, :160-161
             rc.code -= acc * r; rc.range = (e & 0xffffu) * r;
             sym = e >> 16;
@@ -512,8 +517,8 @@ AR_FN void ar_encode_sym (uint32_t *m, uint32_t maxs, ArCache &c, ArEnc &rc, uin
         AR_BUMP_CASE (3, c.e3, c.e2)
     }
     else {
-        uint32_t acc, e, prev;
-        const uint32_t p = ar_find_sym (m, maxs, sym, lane, acc, e, prev);
+        const ArHit h = ar_find_sym (m, maxs, sym, lane);
+        const uint32_t p = h.p, acc = h.acc, e = h.e, prev = h.prev;
         if (p >= maxs) return;                                              // cannot happen for a symbol < maxs
         rc.low += acc * r; rc.range = (e & 0xffffu) * r;
         AR_BUMP_DEEP (p, e, prev)

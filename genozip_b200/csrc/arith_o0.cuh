@@ -38,7 +38,7 @@ __device__ __forceinline__ void ar0_init (uint32_t *E, uint8_t *POS, uint32_t ma
 }
 
 // normalize (c_simple_model.h:106-116) after entry p was bumped, then the bubble step (:140-145); rebuilds the lane sums
-static __device__ __noinline__ void ar0_halve (uint32_t *E, uint8_t *POS, uint32_t maxs, Ar0 &a, uint32_t p, int lane)
+static __device__ __noinline__ Ar0 ar0_halve (uint32_t *E, uint8_t *POS, uint32_t maxs, Ar0 a, uint32_t p, int lane)   // state by value: a reference would pin the caller's registers in local memory
 {
     __syncwarp ();
     const uint32_t lo = 8u * lane;
@@ -69,13 +69,14 @@ static __device__ __noinline__ void ar0_halve (uint32_t *E, uint8_t *POS, uint32
     }
     __syncwarp ();
     a.e0 = E[0];
+    return a;
 }
 
 // entry p (current value e, predecessor prev when p > 0) was coded: Freq += STEP, TotFreq += STEP, halve, bubble (:131-145)
 __device__ __forceinline__ void ar0_update (uint32_t *E, uint8_t *POS, uint32_t maxs, Ar0 &a, uint32_t p, uint32_t e, uint32_t prev, int lane)
 {
     const uint32_t en = e + AR_STEP, owner = p >> 3;
-    if (a.tot + AR_STEP > AR_MAXF) { E[p] = en; ar0_halve (E, POS, maxs, a, p, lane); return; }
+    if (a.tot + AR_STEP > AR_MAXF) { E[p] = en; const Ar0 t = ar0_halve (E, POS, maxs, a, p, lane); a = t; return; }
     a.tot += AR_STEP; a.rtot = ar_rcp_below (a.tot);
     if ((uint32_t)lane == owner) a.s += AR_STEP; else if ((uint32_t)lane > owner) a.base += AR_STEP;
     if (p && (en & 0xffffu) > (prev & 0xffffu)) {

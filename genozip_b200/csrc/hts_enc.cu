@@ -124,24 +124,49 @@ __global__ void k_stripe_transpose (const EncSection *secs, const Tile *tiles, u
 
 // ------------------------------------------------------------------------------------------------ order-0 histogram
 // pass 0: over the leaf input; pass 1: over packbuf, only for leaves whose PACK succeeded
-__global__ void k_hist0 (const EncLeaf *leaves, const EncLeafDyn *dyn, const Tile *tiles, uint32_t n_tiles, int pass)
+__global__ void __launch_bounds__(256) k_hist0 (const EncLeaf *leaves, const EncLeafDyn *dyn, const Tile *tiles, uint32_t n_tiles, int pass)
 {
     if (blockIdx.x >= n_tiles) return;
     const Tile t = tiles[blockIdx.x];
     const EncLeaf &L = leaves[t.leaf];
-    const uint8_t *src; uint32_t n;
+    const uint8_t * __restrict__ src; uint32_t n;
     if (pass == 0) { src = L.in; n = L.n; }
     else { if (!dyn[t.leaf].packed) return; src = dyn[t.leaf].eff_in; n = dyn[t.leaf].eff_n; }
     if (t.off >= n) return;
-    __shared__ uint32_t h[4][256];
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) (&h[0][0])[i] = 0;
+    // One 256-bin histogram per warp in shared memory.  The streams of this path are low-entropy (one symbol is most of the
+    // tile), and 32 lanes adding to the same shared counter serialise — so the tile's first byte is counted in registers
+    // (4 bytes per SIMD compare) and only the other symbols go through shared-memory atomics.
+    __shared__ uint32_t h[8][256];
+    for (int i = threadIdx.x; i < 8 * 256; i += 256) (&h[0][0])[i] = 0;
     __syncthreads ();
-    uint32_t end = min (t.off + TILE, n);
-    uint32_t *my = h[(threadIdx.x >> 5) & 3];
-    for (uint32_t i = t.off + threadIdx.x; i < end; i += blockDim.x) atomicAdd (&my[src[i]], 1u);
+    const uint32_t end = min (t.off + TILE, n), len = end - t.off;
+    const uint8_t *p = src + t.off;
+    uint32_t *my = h[threadIdx.x >> 5];
+    const uint32_t hot = p[0], hot4 = hot * 0x01010101u;
+    uint32_t cnt_hot = 0;
+    const uint32_t head = min (len, (uint32_t)((16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15));
+    const uint32_t nvec = (len - head) >> 4, tail0 = head + (nvec << 4);
+    #define HIST_BYTE(B) { const uint32_t b_ = (B); if (b_ == hot) cnt_hot++; else atomicAdd (&my[b_], 1u); }
+    if (threadIdx.x < head) HIST_BYTE (p[threadIdx.x])
+    if (tail0 + threadIdx.x < len) HIST_BYTE (p[tail0 + threadIdx.x])          // fewer than 16 bytes
+    const uint4 *pv = reinterpret_cast<const uint4 *>(p + head);
+    for (uint32_t i = threadIdx.x; i < nvec; i += 256) {
+        const uint4 v = __ldg (pv + i);
+        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+        #pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (__vcmpeq4 (w[k], hot4) == 0xffffffffu) cnt_hot += 4;
+            else { HIST_BYTE (w[k] & 0xffu) HIST_BYTE ((w[k] >> 8) & 0xffu) HIST_BYTE ((w[k] >> 16) & 0xffu) HIST_BYTE (w[k] >> 24) }
+        }
+    }
+    #undef HIST_BYTE
+    cnt_hot = __reduce_add_sync (0xffffffffu, cnt_hot);
+    if ((threadIdx.x & 31) == 0 && cnt_hot) atomicAdd (&my[hot], cnt_hot);
     __syncthreads ();
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-        uint32_t v = h[0][i] + h[1][i] + h[2][i] + h[3][i];
+    for (int i = threadIdx.x; i < 256; i += 256) {
+        uint32_t v = 0;
+        #pragma unroll
+        for (int k = 0; k < 8; k++) v += h[k][i];
         if (v) atomicAdd (&L.hist0[i], v);
     }
 }
@@ -247,7 +272,7 @@ __global__ void k_leaf_prep (const EncLeaf *leaves, EncLeafDyn *dyn, uint32_t n_
 // hist1_4 (utils.h:136-210): F[prev][cur], prev = 0 before the first byte.  Compact [rank][rank] counters,
 // accumulated in shared memory when nsym^2 fits, flushed with global atomics.
 constexpr uint32_t H1_SMEM_CELLS = 10240;    // 40 KB of u32: nsym <= 101
-__global__ void k_hist1 (const EncLeaf *leaves, const EncLeafDyn *dyn, const Tile *tiles, uint32_t n_tiles)
+__global__ void __launch_bounds__(256) k_hist1 (const EncLeaf *leaves, const EncLeafDyn *dyn, const Tile *tiles, uint32_t n_tiles)
 {
     if (blockIdx.x >= n_tiles) return;
     const Tile t = tiles[blockIdx.x];
@@ -261,13 +286,37 @@ __global__ void k_hist1 (const EncLeaf *leaves, const EncLeafDyn *dyn, const Til
     for (int i = threadIdx.x; i < 256; i += blockDim.x) rank[i] = D.rank[i];
     if (in_smem) for (uint32_t i = threadIdx.x; i < cells; i += blockDim.x) h[i] = 0;
     __syncthreads ();
-    const uint8_t *src = D.eff_in;
-    uint32_t end = min (t.off + TILE, D.eff_n);
-    for (uint32_t i = t.off + threadIdx.x; i < end; i += blockDim.x) {
-        uint32_t prev = i ? rank[src[i - 1]] : rank[0];
-        uint32_t cell = prev * ns + rank[src[i]];
-        if (in_smem) atomicAdd (&h[cell], 1u); else atomicAdd (&D.hist1[cell], 1u);
+    const uint8_t * __restrict__ src = D.eff_in;
+    const uint32_t end = min (t.off + TILE, D.eff_n), len = end - t.off;
+    const uint8_t *p = src + t.off;
+    // As in k_hist0: the pair (first byte of the tile, itself) — nearly every pair of a low-entropy stream such as the
+    // ACGT exception stream — is counted in registers, 16 bytes per compare; everything else goes through the atomics.
+    const uint32_t hot = p[0], hot4 = hot * 0x01010101u, hot_cell = rank[hot] * ns + rank[hot];
+    uint32_t cnt_hot = 0;
+    #define H1_PAIR(PB, B, IDX) { const uint32_t pb_ = (PB), b_ = (B); \
+        if (pb_ == hot && b_ == hot && (IDX)) cnt_hot++; \
+        else { const uint32_t cell_ = ((IDX) ? rank[pb_] : rank[0]) * ns + rank[b_]; if (in_smem) atomicAdd (&h[cell_], 1u); else atomicAdd (&D.hist1[cell_], 1u); } }
+    const uint32_t head = min (len, (uint32_t)((16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15));
+    const uint32_t nvec = (len - head) >> 4, tail0 = head + (nvec << 4);
+    if (threadIdx.x < head) { const uint32_t idx = t.off + threadIdx.x; H1_PAIR (idx ? src[idx - 1] : 0u, src[idx], idx) }
+    if (tail0 + threadIdx.x < len) { const uint32_t idx = t.off + tail0 + threadIdx.x; H1_PAIR (idx ? src[idx - 1] : 0u, src[idx], idx) }
+    const uint4 *pv = reinterpret_cast<const uint4 *>(p + head);
+    for (uint32_t i = threadIdx.x; i < nvec; i += 256) {
+        const uint4 v = __ldg (pv + i);
+        const uint32_t idx0 = t.off + head + (i << 4);
+        uint32_t pb = idx0 ? src[idx0 - 1] : 0u;
+        if (idx0 && pb == hot && v.x == hot4 && v.y == hot4 && v.z == hot4 && v.w == hot4) { cnt_hot += 16; continue; }
+        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+        #pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const uint32_t b = (w[k >> 2] >> (8 * (k & 3))) & 0xffu;
+            H1_PAIR (pb, b, idx0 + k)
+            pb = b;
+        }
     }
+    #undef H1_PAIR
+    cnt_hot = __reduce_add_sync (0xffffffffu, cnt_hot);
+    if ((threadIdx.x & 31) == 0 && cnt_hot) { if (in_smem) atomicAdd (&h[hot_cell], cnt_hot); else atomicAdd (&D.hist1[hot_cell], cnt_hot); }
     if (in_smem) {
         __syncthreads ();
         for (uint32_t i = threadIdx.x; i < cells; i += blockDim.x) if (h[i]) atomicAdd (&D.hist1[i], h[i]);
