@@ -340,7 +340,7 @@ def run_gpu(args):
     dom = max(kern, key=lambda k: kern[k])
     dom_bytes = alg["rans" if dom.startswith("rans") else "arith"] // len(path.groups)    # each group launches the chain kernel once
     achieved = dom_bytes / (kern[dom] * 1e-3) / 1e9 if kern[dom] > 0 else 0.0
-    kname = {"rans_enc": "k_rans_encode", "rans_dec": "k_rans_decode", "arith_enc": "k_arith_encode", "arith_dec": "k_arith_decode"}[dom]
+    kname = {"rans_enc": "k_rans_encode", "rans_dec": "k_rans_decode", "arith_enc": "k_arith_encode_t<0>", "arith_dec": "k_arith_decode_t<0>"}[dom]
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
@@ -350,8 +350,9 @@ def run_gpu(args):
         pass
     roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "peak_source": which_peak, "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": kern[dom],
-            "note": "entropy chains are dependency-bound (4 chains per rANS leaf, 1 per arithmetic leaf, fixed by the bitstream); "
-                    "see profiles/ for dram__bytes of this kernel", "kernel_ms_per_step": kern}
+            "note": "entropy chains are dependency-bound (4 chains per rANS leaf, 1 per arithmetic leaf, fixed by the bitstream): the launch lasts as long as "
+                    "its longest leaf; traffic (dram__bytes) is null unless profiles/r01_traffic.json holds a capture of this very launch; "
+                    "profiles/r01_k_arith_decode.md has the single-leaf capture", "kernel_ms_per_step": kern}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

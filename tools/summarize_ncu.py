@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Turns the raw ncu outputs brought back in gpurun_out/ into the small, tracked summaries under profiles/.
   python tools/summarize_ncu.py launches gpurun_out/launches_rNN.csv profiles/rNN_launches.md
-  python tools/summarize_ncu.py kernel   gpurun_out/prof_X.ncu-rep   profiles/rNN_X.md
+  python tools/summarize_ncu.py kernel   gpurun_out/prof_X.ncu-rep   profiles/rNN_X.md [kernel-name substring]
 """
 import collections, csv, subprocess, sys
 
@@ -36,10 +36,14 @@ def launches(src, dst):
             f.write(f"| `{k[:70]}` | {len(v)} | {sum(v)/1e6:.2f} | {max(v)/1e6:.2f} | {100*sum(v)/tot:.1f}% |\n")
 
 
-def kernel(src, dst):
+def kernel(src, dst, name=None):
     out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     h, units, v = rows[0], rows[1], rows[2]
+    if name:                                               # last launch whose kernel name contains `name`
+        for r in rows[2:]:
+            if name in r[h.index("Kernel Name")]:
+                v = r
     with open(dst, "w") as f:
         f.write(f"# ncu --set full summary of {src}\n\n| metric | value | unit |\n|---|---:|---|\n")
         name = v[h.index("Kernel Name")] if "Kernel Name" in h else "?"
@@ -51,4 +55,4 @@ def kernel(src, dst):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "kernel": kernel}[sys.argv[1]](*sys.argv[2:])
