@@ -82,21 +82,6 @@ AR_FN uint32_t ar_div (uint32_t a, uint32_t d, float rd)
 #endif
 }
 
-// exact a / d when the QUOTIENT is small (< 2^17): the decoder's code / range on the slow path (c_range_coder.h:111-114)
-AR_FN uint32_t ar_div_smallq (uint32_t a, uint32_t d)
-{
-#ifdef __CUDA_ARCH__
-    if ((a >> 17) >= d) return d ? a / d : 0xffffffffu;
-    const float rd = ar_rcp_below (d);
-    uint32_t q = __float2uint_rz (__fmul_rz (__uint2float_rz (a), rd));
-    uint32_t r = a - q * d;
-    while (r >= d) { q++; r -= d; }
-    return q;
-#else
-    return d ? a / d : 0xffffffffu;
-#endif
-}
-
 // ---- warp primitives (one lane on the host) ------------------------------------------------------------------------
 #ifdef __CUDA_ARCH__
 AR_FN uint32_t ar_wsum (uint32_t v) { return __reduce_add_sync (0xffffffffu, v); }
