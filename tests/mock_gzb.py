@@ -1,0 +1,150 @@
+"""A stand-in for libgzb200.so on a machine WITHOUT a GPU — test infrastructure only.
+
+It exposes the entry points genozip_b200/fastq_path.py calls and computes them with the CPU checkers (tests/orc.py), reading
+and writing the caller's buffers through the very descriptor arrays the real library would receive.  With it the host
+driver (descriptor set-up, stream bookkeeping, per-pipeline threads, buffer sizing, byte accounting) runs end to end in
+the CPU test suite; the CUDA library itself is exercised by the -m gpu tests.  `est_size` / `packed_len` come from the real
+library (they need no device)."""
+import ctypes as C
+import numpy as np
+
+import orc
+from genozip_b200.lib import load, CODEC, GZB_DEVICE_PTRS, GZB_OUT_DEVICE, GZB_IN_DEVICE
+
+NAME = {v: k for k, v in CODEC.items()}
+
+
+def _view(ptr, n, dtype=np.uint8):
+    """numpy view of n items at address ptr (the 'device' memory of the mock is host memory)"""
+    if not n:
+        return np.zeros(0, dtype)
+    nbytes = int(n) * np.dtype(dtype).itemsize
+    return np.frombuffer((C.c_uint8 * nbytes).from_address(int(ptr)), dtype=dtype)
+
+
+class MockLib:
+    def __init__(self):
+        self.real = load()
+        self.calls = []
+
+    # ---- no device needed
+    def gzb_acgt_packed_len(self, n):
+        return self.real.gzb_acgt_packed_len(n)
+
+    def gzb_est_size(self, codec, n):
+        return self.real.gzb_est_size(codec, n)
+
+    def gzb_engine_stream(self, h):
+        return None
+
+    def gzb_last_kernel_ms(self, h, which):
+        return 0.0
+
+    # ---- ACGT
+    def gzb_acgt_pack_batch(self, h, arr, n, flags):
+        self.calls.append(("acgt_pack_batch", n, flags))
+        for i in range(n):
+            a = arr[i]
+            pk, x, allz = orc.acgt_pack(_view(a.seq, a.n_bases))
+            _view(a.packed, pk.size)[:] = pk
+            if a.x:
+                _view(a.x, a.n_bases)[:] = x
+            a.x_all_zero = int(allz)
+        return 0
+
+    def gzb_acgt_unpack_batch(self, h, arr, n, flags):
+        self.calls.append(("acgt_unpack_batch", n, flags))
+        for i in range(n):
+            a = arr[i]
+            plen = int(self.gzb_acgt_packed_len(a.n_bases))
+            x = _view(a.x, a.n_bases).copy() if a.x else None
+            _view(a.seq, a.n_bases)[:] = orc.acgt_unpack(_view(a.packed, plen).copy(), x, a.n_bases)
+        return 0
+
+    # ---- DOMQ
+    def _domq(self, a):
+        off = _view(a.line_off, a.n_lines, np.uint64); ln = _view(a.line_len, a.n_lines, np.uint32)
+        return orc.domq_encode(_view(a.txt, a.txt_len), off, ln)
+
+    def gzb_domq_prepare(self, h, arr, n, flags):
+        self.calls.append(("domq_prepare", n, flags))
+        self._enc = []
+        for i in range(n):
+            a = arr[i]
+            e = self._domq(a)
+            self._enc.append(e)
+            a.num_norm_qs, a.num_doms, a.has_diverse = e["num_norm_qs"], e["num_doms"], e["has_diverse"]
+            C.memmove(a.denorm, e["denorm"].ctypes.data, e["denorm"].size)
+            _view(a.line_dom, a.n_lines)[:] = e["line_dom"]; _view(a.line_diverse, a.n_lines)[:] = e["line_diverse"]
+        return 0
+
+    def gzb_domq_split(self, h, arr, n, flags):
+        self.calls.append(("domq_split", n, flags))
+        for i in range(n):
+            a, e = arr[i], self._enc[i]
+            for fld, k in (("qual", "qual"), ("runs", "runs"), ("mplx", "mplx"), ("divr", "divr")):
+                assert e[k].size <= getattr(a, fld + "_cap")
+                _view(getattr(a, fld), e[k].size)[:] = e[k]
+                setattr(a, fld + "_len", e[k].size)
+        return 0
+
+    def gzb_domq_reconstruct(self, h, arr, n, flags):
+        self.calls.append(("domq_reconstruct", n, flags))
+        for i in range(n):
+            a = arr[i]
+            enc = dict(qual=_view(a.qual, a.qual_len).copy(), runs=_view(a.runs, a.runs_len).copy(), mplx=_view(a.mplx, a.mplx_len).copy(),
+                       divr=_view(a.divr, a.divr_len).copy(), denorm=_view(a.denorm, a.denorm_len).copy(), num_norm_qs=a.num_norm_qs)
+            ln = _view(a.line_len, a.n_lines, np.uint32)
+            out = orc.domq_decode(enc, ln)
+            assert out.size <= a.out_cap
+            _view(a.out, out.size)[:] = out
+        return 0
+
+    # ---- simple codecs
+    def gzb_compress_sections(self, h, secs, n, flags):
+        self.calls.append(("compress", n, flags))
+        for i in range(n):
+            s = secs[i]
+            name = NAME[s.codec]
+            data = _view(s.in_, s.in_len).copy()
+            c = orc.compress("port", "rans" if name.startswith("RAN") else "arith", data, orc.ORDER[name])
+            assert c.size <= s.out_cap, (name, c.size, s.out_cap)
+            _view(s.out, c.size)[:] = c
+            s.out_len = c.size; s.status = 0
+        return 0
+
+    def gzb_uncompress_sections(self, h, secs, n, flags):
+        self.calls.append(("uncompress", n, flags))
+        for i in range(n):
+            s = secs[i]
+            name = NAME[s.codec]
+            d = orc.uncompress("port", "rans" if name.startswith("RAN") else "arith", _view(s.in_, s.in_len).copy(), s.out_cap)
+            _view(s.out, d.size)[:] = d
+            s.out_len = d.size; s.status = 0
+        return 0
+
+
+class MockEngine:
+    """Engine look-alike on top of MockLib (what FastqCodecPath needs of genozip_b200.lib.Engine)"""
+    torch_device = "cpu"
+    _lib = None
+
+    def __init__(self, device=0):
+        if MockEngine._lib is None:
+            MockEngine._lib = MockLib()
+        self.L, self.h, self.device, self.launches = MockEngine._lib, None, device, 0
+
+    def close(self):
+        pass
+
+    def _err(self):
+        return "mock"
+
+    def compress_raw(self, secs, n, flags=0):
+        assert self.L.gzb_compress_sections(self.h, secs, n, flags) == 0
+
+    def uncompress_raw(self, secs, n, flags=0):
+        assert self.L.gzb_uncompress_sections(self.h, secs, n, flags) == 0
+
+    def compress(self, items):
+        return [orc.compress("port", "rans" if c.startswith("RAN") else "arith", np.ascontiguousarray(d, np.uint8), orc.ORDER[c]) for c, d in items]

@@ -1,0 +1,71 @@
+"""CPU: the host driver of the FASTQ codec path (genozip_b200/fastq_path.py — descriptor set-up, per-pipeline engines and
+threads, buffer sizing, stream bookkeeping, byte accounting) run end to end against tests/mock_gzb.py, a stand-in for
+libgzb200.so that computes every entry point with the CPU checkers.  Same assertions as the GPU test of this path."""
+import numpy as np, pytest, torch
+import orc
+from datagen import line_table
+from mock_gzb import MockEngine
+
+
+def _oracle_sections(data, v, n_reads, read_len, codec):
+    seq = data["seq"][v].numpy(); qual = data["qual"][v].numpy()
+    off, ln = line_table(n_reads, read_len)
+    pk, x, allz = orc.acgt_pack(seq)
+    enc = orc.domq_encode(qual, off, ln)
+    streams = {"QUAL": enc["qual"], "DOMQRUNS": enc["runs"], "QUALMPLX": enc["mplx"], "DIVRQUAL": enc["divr"], "NONREF_X": np.zeros(0, np.uint8) if allz else x}
+    for k in ("Q_TILE", "Q_X", "Q_Y", "Q_MISC"):
+        streams[k] = data[k][v].numpy()
+    comp = {s: orc.compress("port", "rans" if codec[s].startswith("RAN") else "arith", d, orc.ORDER[codec[s]]) for s, d in streams.items() if d.size}
+    return pk, streams, comp
+
+
+@pytest.mark.parametrize("n_engines", [1, 3])
+def test_fastq_path_host_driver(n_engines):
+    from genozip_b200.fastq_path import FastqCodecPath, synth_vblocks, STREAMS
+    V, n_reads, read_len = 3, 400, 150
+    data = synth_vblocks(V, n_reads, read_len, 7, torch.device("cpu"))
+    data["seq"][1][data["seq"][1] == ord("N")] = ord("A")                  # VBlock 1: pure ACGT -> acgt_no_x, no NONREF_X section
+    path = FastqCodecPath(MockEngine(0), V, n_reads, read_len, n_engines=n_engines)
+    codec = path.assign_codecs(data)
+    assert set(codec) == set(STREAMS)
+    meta = path.zip_device(data)
+    path.alloc_piz(meta)
+    assert meta[1]["acgt_no_x"] and meta[1]["len"]["NONREF_X"] == 0 and not meta[0]["acgt_no_x"]
+    for v in range(V):
+        pk, streams, comp = _oracle_sections(data, v, n_reads, read_len, codec)
+        assert np.array_equal(path.packed_d[v][:pk.size].numpy(), pk)
+        for s in STREAMS:
+            assert meta[v]["len"][s] == streams[s].size, (s, meta[v]["len"][s], streams[s].size)
+            if streams[s].size:
+                got = path.comp_d[s][v][:meta[v]["comp_len"][s]].numpy()
+                assert got.size == comp[s].size and np.array_equal(got, comp[s]), f"section {s} of VB {v}"
+    path.piz_device(meta)
+    assert torch.equal(path.seq_out_d, data["seq"]) and torch.equal(path.qual_out_d, data["qual"])
+    for s in ("Q_TILE", "Q_X", "Q_Y", "Q_MISC"):
+        assert torch.equal(path.dec_d[s][:, :data[s].shape[1]], data[s])
+    # host-buffer mode: separate host buffers in and out, the DOMQ / exception streams stay in "device" memory
+    path.alloc_host(data)
+    meta_h, h2d, d2h = path.zip_host()
+    for v in range(V):
+        for s in STREAMS:
+            assert meta_h[v]["len"][s] == meta[v]["len"][s] and meta_h[v]["comp_len"].get(s) == meta[v]["comp_len"].get(s)
+            if meta[v]["len"][s]:
+                a = path.h["comp"][s][v][:meta_h[v]["comp_len"][s]].numpy(); b = path.comp_d[s][v][:meta[v]["comp_len"][s]].numpy()
+                assert np.array_equal(a, b), f"host path: section {s}"
+    path.h["seq_out"].zero_(); path.h["qual_out"].zero_()
+    h2d_p, d2h_p = path.piz_host(meta_h)
+    assert torch.equal(path.h["seq_out"], path.h["seq"]) and torch.equal(path.h["qual_out"], path.h["qual"])
+    n = n_reads * read_len
+    assert h2d >= 2 * V * n and d2h_p >= 2 * V * n and d2h > 0 and h2d_p > 0
+    path.close()
+
+
+def test_descriptor_dtypes_match_the_c_structs():
+    """the numpy views used to fill descriptor arrays column-wise must have the C-ABI structs' exact layout"""
+    import ctypes as C
+    from genozip_b200.fastq_path import SEC_DT, DVB_DT, PVB_DT, AVB_DT
+    from genozip_b200.lib import Section, DomqVb, DomqPizVb, AcgtVb
+    for dt, st in ((SEC_DT, Section), (DVB_DT, DomqVb), (PVB_DT, DomqPizVb), (AVB_DT, AcgtVb)):
+        assert dt.itemsize == C.sizeof(st)
+        for name, _ in st._fields_:
+            assert dt.fields[name][1] == getattr(st, name).offset, (st.__name__, name)
