@@ -315,7 +315,7 @@ class FastqCodecPath:
     # ------------------------------------------------------------------ HOST-buffer path (e2e): what the C host would call
     def alloc_host(self, data):
         """pinned host copies of the inputs and pinned host buffers for every output"""
-        pin = lambda t: _pin(t.cpu().clone())
+        pin = lambda t: _pin(t.cpu() if t.is_cuda else t.clone())           # separate host buffers either way
         self.h = {k: pin(v) for k, v in data.items()}
         V, n = self.V, self.n
         hp = lambda *shape: _pin(torch.empty(shape, dtype=torch.uint8))
