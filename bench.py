@@ -338,7 +338,7 @@ def run_gpu(args):
             if n:
                 alg["rans" if codecs[s].startswith("RAN") else "arith"] += n + m["comp_len"][s]
     dom = max(kern, key=lambda k: kern[k])
-    dom_bytes = alg["rans" if dom.startswith("rans") else "arith"]
+    dom_bytes = alg["rans" if dom.startswith("rans") else "arith"] // len(path.groups)    # each group launches the chain kernel once
     achieved = dom_bytes / (kern[dom] * 1e-3) / 1e9 if kern[dom] > 0 else 0.0
     kname = {"rans_enc": "k_rans_encode", "rans_dec": "k_rans_decode", "arith_enc": "k_arith_encode_t<0>", "arith_dec": "k_arith_decode_t<0>"}[dom]
     traffic = None
@@ -376,7 +376,7 @@ def run_gpu(args):
                        "codecs": codecs, "l2": "inputs (>= 0.9 GB per step) are larger than L2; no flush needed",
                        "sections_per_step": sum(1 for m in meta for n in m["len"].values() if n), "compressed_bytes_per_step": comp_total,
                        "excluded": "segmenter; LZMA of the 2-bit sequence words (host, out of scope)", "sharding": "VBlocks round-robin by vblock_i, no data-path collective; NCCL all_gather of the section list only",
-                       "engines_per_gpu": len(path.engs)},
+                       "engines_per_gpu": len(path.engs), "device_groups": len(path.groups)},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
         }))
     if world > 1:

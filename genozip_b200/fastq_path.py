@@ -73,9 +73,6 @@ def _synth_chunk(V, n_reads, read_len, seed, device):
     return dict(seq=seq.contiguous(), qual=qual.contiguous(), Q_TILE=tile, Q_X=be32(xs), Q_Y=be32(ys), Q_MISC=misc.contiguous())
 
 
-SEC_DT, DVB_DT, PVB_DT, AVB_DT = (np.dtype(t) for t in (Section, DomqVb, DomqPizVb, AcgtVb))   # numpy views of the C-ABI descriptor structs
-
-
 def _pin(t):
     """pinned host memory where there is a GPU to transfer to"""
     return t.pin_memory() if torch.cuda.is_available() else t
@@ -85,19 +82,22 @@ class FastqCodecPath:
     """zip / piz of a batch of V FASTQ VBlocks through libgzb200 on one GPU.
 
     The path owns `n_engines` engines (one host thread + CUDA stream + workspace each, the library's unit of concurrency:
-    "one engine per host thread and GPU").  The host-buffer mode gives each of the three independent pipelines of a FASTQ
-    VBlock (QUAL, SEQ, read names) its own engine so that transfers overlap the entropy chains (zip_host / piz_host); the
-    device-resident mode uses one engine (dealing the batch to several engines, by VBlock groups or by pipeline, was
-    measured on B200 and does not help: the chain kernels' duration is set by their longest leaf, not by the batch size)."""
+    "one engine per host thread and GPU").  The host-buffer path gives each of the three independent pipelines of a FASTQ
+    VBlock (QUAL, SEQ, read names) its own engine so that transfers overlap the entropy chains (zip_host / piz_host).
+    The device-resident path can deal the batch to `device_groups` engines in contiguous groups of VBlocks, as genozip's
+    dispatcher hands VBlocks to compute threads; measured on B200 this does not help (the chain kernels' duration is
+    set by their longest leaf, not by the batch size), so the default is one group."""
 
-    def __init__(self, eng: Engine, V, n_reads, read_len, n_engines=3):
+    def __init__(self, eng: Engine, V, n_reads, read_len, n_engines=3, device_groups=1):
         self.eng, self.L = eng, eng.L
         self.V, self.n_reads, self.read_len = V, n_reads, read_len
         self.n = n_reads * read_len
-        dev = torch.device(getattr(eng, "torch_device", None) or f"cuda:{eng.device}")   # (tests drive this class on the CPU through a mock engine)
+        dev = torch.device(getattr(eng, "torch_device", None) or f"cuda:{eng.device}")   # (the CPU test suite drives this class through a mock engine)
         self.dev = dev
         n_engines = max(1, n_engines)
+        K = max(1, min(n_engines, V, device_groups))
         self.engs = [eng] + [type(eng)(eng.device) for _ in range(n_engines - 1)]
+        self.groups = [(g * V // K, (g + 1) * V // K) for g in range(K)]
         self.pool = ThreadPoolExecutor(n_engines) if n_engines > 1 else None
         self.stream = torch.cuda.ExternalStream(self.L.gzb_engine_stream(eng.h), device=dev) if dev.type == "cuda" else None
         n, V = self.n, V
@@ -121,7 +121,7 @@ class FastqCodecPath:
         self.avb = (AcgtVb * V)()
         self.meta = None          # per-VB dicts from the last zip (lengths, tables)
         self.h = {}               # pinned host buffers for the host-buffer (e2e) path
-        self.kernel_ms = (0.0, 0.0)   # chain kernel durations of the last call: (rANS, arithmetic), longest over the engines used
+        self.kernel_ms = (0.0, 0.0)   # chain kernel durations of the last call: (rANS, arithmetic), mean over the engines
 
     @property
     def launches(self):
@@ -134,6 +134,16 @@ class FastqCodecPath:
         for e in self.engs[1:]:
             e.close()
         self.engs = self.engs[:1]
+
+    def _each_group(self, fn):
+        """run fn(g, engine, v0, v1) for every group, one host thread per engine; results in group order"""
+        jobs = [(g, self.engs[g], v0, v1) for g, (v0, v1) in enumerate(self.groups)]
+        if self.pool is None:
+            res = [fn(*j) for j in jobs]
+        else:
+            res = list(self.pool.map(lambda j: fn(*j), jobs))
+        self.kernel_ms = tuple(float(np.mean([self.L.gzb_last_kernel_ms(e.h, w) for e in self.engs[:len(self.groups)]])) for w in (0, 1))
+        return res
 
     @staticmethod
     def _sub(arr, v0, v1):
@@ -182,88 +192,69 @@ class FastqCodecPath:
             if s not in self.comp_d or self.comp_d[s].shape[1] < cap:
                 self.comp_d[s] = torch.empty((self.V, cap), dtype=torch.uint8, device=self.dev)
 
-    # ------------------------------------------------------------------ descriptor arrays, built column-wise with numpy
-    # (a batch has 512 VBlocks x 9 streams: per-element ctypes attribute assignments would cost tens of milliseconds per step)
-    def _rows(self, t):
-        """addresses of the rows of a 2-D uint8 tensor [V, cap]"""
-        assert t.dim() == 2 and t.shape[0] == self.V and t.stride(1) == 1
-        return np.uint64(t.data_ptr()) + np.arange(self.V, dtype=np.uint64) * np.uint64(t.stride(0))
-
-    def _section_array(self, names, in_rows, in_len, out_rows, out_cap, sflags):
-        """Section descriptors of the streams `names` for every VBlock with a non-empty stream, VBlock-major.
-        in_rows / out_rows: s -> (V,) addresses; in_len: s -> (V,) lengths; out_cap: s -> scalar or (V,); sflags: s -> flags.
-        Returns (descriptor array, mask[V, len(names)] of the sections present)."""
-        a = np.zeros((self.V, len(names)), SEC_DT)
-        for j, s in enumerate(names):
-            a["codec"][:, j] = CODEC[self.codec[s]]
-            a["in_"][:, j] = in_rows[s]; a["in_len"][:, j] = in_len[s]
-            a["out"][:, j] = out_rows[s]; a["out_cap"][:, j] = out_cap[s]
-            a["sflags"][:, j] = sflags.get(s, 0)
-        mask = a["in_len"] > 0
-        return np.ascontiguousarray(a[mask]), mask
-
-    @staticmethod
-    def _run_sections(call, secs, flags):
-        if secs.size:
-            call(secs.ctypes.data_as(C.POINTER(Section)), int(secs.size), flags)
-            bad = np.flatnonzero(secs["status"] != 0)
-            if bad.size:
-                raise GzbError(f"section {int(bad[0])} of the batch: status {int(secs['status'][bad[0]])}")
-
-    def _zip_descriptors(self, seq_rows, packed_rows, qual_rows, line_off, line_len, dom_rows, div_rows):
-        n = self.n
-        av = np.frombuffer(self.avb, dtype=AVB_DT)
-        av["seq"] = seq_rows; av["n_bases"] = n; av["packed"] = packed_rows; av["x"] = self._rows(self.x_d)
-        dv = np.frombuffer(self.dvb, dtype=DVB_DT)
-        dv["txt"] = qual_rows; dv["txt_len"] = n
-        dv["line_off"] = line_off.data_ptr(); dv["line_len"] = line_len.data_ptr(); dv["n_lines"] = self.n_reads
-        dv["line_dom"] = dom_rows; dv["line_diverse"] = div_rows
-        for fld, s in (("qual", "QUAL"), ("runs", "DOMQRUNS"), ("mplx", "QUALMPLX"), ("divr", "DIVRQUAL")):
-            dv[fld] = self._rows(self.dq[s]); dv[fld + "_cap"] = self.caps[s]
-        return av, dv
-
-    def _stream_lengths(self, av, dv):
-        """lengths of the nine streams of every VBlock after ACGT pack and DOMQ split"""
-        V, nr = self.V, self.n_reads
-        full = lambda k: np.full(V, k, np.uint32)
-        return {"QUAL": dv["qual_len"].copy(), "DOMQRUNS": dv["runs_len"].copy(), "QUALMPLX": dv["mplx_len"].copy(), "DIVRQUAL": dv["divr_len"].copy(),
-                "NONREF_X": np.where(av["x_all_zero"] != 0, 0, self.n).astype(np.uint32),
-                "Q_TILE": full(nr), "Q_X": full(4 * nr), "Q_Y": full(4 * nr), "Q_MISC": full(nr)}
-
-    def _make_meta(self, av, dv, lens):
-        nq, nd, dn = dv["num_norm_qs"], dv["num_doms"], dv["denorm"]
-        return [dict(len={s: int(lens[s][v]) for s in STREAMS}, comp_len={}, acgt_no_x=bool(av["x_all_zero"][v]),
-                     num_norm_qs=int(nq[v]), denorm=dn[v, :int(nq[v]) * int(nd[v])].tobytes()) for v in range(self.V)]
-
-    @staticmethod
-    def _store_comp_lens(meta, names, secs, mask):
-        vs, js = np.nonzero(mask)
-        for v, j, ln in zip(vs.tolist(), js.tolist(), secs["out_len"].tolist()):
-            meta[v]["comp_len"][names[j]] = ln
-
     # ------------------------------------------------------------------ ZIP, inputs resident in HBM
     def zip_device(self, data, only_vb0_streams=False):
-        L, V, eng = self.L, self.V, self.eng
-        av, dv = self._zip_descriptors(self._rows(data["seq"]), self._rows(self.packed_d), self._rows(data["qual"]),
-                                       self.line_off_d, self.line_len_d, self._rows(self.linedom_d), self._rows(self.linediv_d))
-        if L.gzb_acgt_pack_batch(eng.h, self.avb, V, GZB_DEVICE_PTRS):
-            raise GzbError(f"gzb_acgt_pack_batch: {eng._err()}")
-        if L.gzb_domq_prepare(eng.h, self.dvb, V, GZB_DEVICE_PTRS) or L.gzb_domq_split(eng.h, self.dvb, V, GZB_DEVICE_PTRS):
-            raise GzbError(f"gzb_domq: {eng._err()}")
-        lens = self._stream_lengths(av, dv)
-        meta = self.meta = self._make_meta(av, dv, lens)
-        if only_vb0_streams:
-            return meta
-        self._alloc_comp(meta)                              # (sized from the first batch's streams; a no-op afterwards)
-        in_rows = {s: self._rows(self.dq[s]) for s in self.dq}
-        in_rows["NONREF_X"] = self._rows(self.x_d)
-        in_rows.update({s: self._rows(data[s]) for s in ("Q_TILE", "Q_X", "Q_Y", "Q_MISC")})
-        secs, mask = self._section_array(STREAMS, in_rows, lens, {s: self._rows(self.comp_d[s]) for s in STREAMS},
-                                         {s: self.comp_d[s].shape[1] for s in STREAMS}, {})
-        self._run_sections(eng.compress_raw, secs, GZB_DEVICE_PTRS)
-        self._store_comp_lens(meta, STREAMS, secs, mask)
-        self.kernel_ms = (float(L.gzb_last_kernel_ms(eng.h, 0)), float(L.gzb_last_kernel_ms(eng.h, 1)))
+        L, V, n = self.L, self.V, self.n
+        meta = [dict(len={}, comp_len={}) for _ in range(V)]
+        for v in range(V):
+            b = self.avb[v]
+            b.seq = data["seq"][v].data_ptr(); b.n_bases = n; b.packed = self.packed_d[v].data_ptr(); b.x = self.x_d[v].data_ptr()
+            a = self.dvb[v]
+            a.txt = data["qual"][v].data_ptr(); a.txt_len = n
+            a.line_off = self.line_off_d.data_ptr(); a.line_len = self.line_len_d.data_ptr(); a.n_lines = self.n_reads
+            a.line_dom = self.linedom_d[v].data_ptr(); a.line_diverse = self.linediv_d[v].data_ptr()
+            for fld, s in (("qual", "QUAL"), ("runs", "DOMQRUNS"), ("mplx", "QUALMPLX"), ("divr", "DIVRQUAL")):
+                setattr(a, fld, self.dq[s][v].data_ptr()); setattr(a, fld + "_cap", self.caps[s])
+
+        def domain(g, eng, v0, v1):
+            h = eng.h
+            if L.gzb_acgt_pack_batch(h, self._sub(self.avb, v0, v1), v1 - v0, GZB_DEVICE_PTRS):
+                raise GzbError(f"gzb_acgt_pack_batch: {eng._err()}")
+            dv = self._sub(self.dvb, v0, v1)
+            if L.gzb_domq_prepare(h, dv, v1 - v0, GZB_DEVICE_PTRS) or L.gzb_domq_split(h, dv, v1 - v0, GZB_DEVICE_PTRS):
+                raise GzbError(f"gzb_domq: {eng._err()}")
+            for v in range(v0, v1):
+                a, m = self.dvb[v], meta[v]
+                m["acgt_no_x"] = bool(self.avb[v].x_all_zero)
+                m["len"].update(NONREF_X=0 if self.avb[v].x_all_zero else n, QUAL=a.qual_len, DOMQRUNS=a.runs_len, QUALMPLX=a.mplx_len,
+                                DIVRQUAL=a.divr_len, Q_TILE=self.n_reads, Q_X=4 * self.n_reads, Q_Y=4 * self.n_reads, Q_MISC=self.n_reads)
+                m["num_norm_qs"] = a.num_norm_qs
+                m["denorm"] = bytes(a.denorm)[:a.num_norm_qs * a.num_doms]
+
+        def sections(g, eng, v0, v1):
+            secs, idx = self._sections(meta, lambda s, v: self._stream_dev_tensor(s, v, data).data_ptr(), lambda s, v: self.comp_d[s][v].data_ptr(), 0, v0, v1)
+            eng.compress_raw(secs, len(idx), GZB_DEVICE_PTRS)
+            self._collect(secs, idx, meta)
+
+        if only_vb0_streams or not self.comp_d:
+            # first call of a batch: the compressed-section buffers are sized from the streams' actual lengths
+            self._each_group(domain)
+            self.meta = meta
+            if only_vb0_streams:
+                return meta
+            self._alloc_comp(meta)
+            self._each_group(sections)
+        else:
+            self._each_group(lambda g, eng, v0, v1: (domain(g, eng, v0, v1), sections(g, eng, v0, v1)))
+            self.meta = meta
         return meta
+
+    def _sections(self, meta, in_ptr, out_ptr, sflags_for, v0=0, v1=None):
+        idx = [(v, s) for v in range(v0, self.V if v1 is None else v1) for s in STREAMS if meta[v]["len"][s] > 0]
+        secs = (Section * len(idx))()
+        for i, (v, s) in enumerate(idx):
+            secs[i].codec = CODEC[self.codec[s]]
+            secs[i].in_ = in_ptr(s, v); secs[i].in_len = meta[v]["len"][s]
+            secs[i].out = out_ptr(s, v); secs[i].out_cap = est_size(self.codec[s], meta[v]["len"][s])
+            secs[i].sflags = sflags_for(s) if callable(sflags_for) else sflags_for
+        return secs, idx
+
+    @staticmethod
+    def _collect(secs, idx, meta):
+        for i, (v, s) in enumerate(idx):
+            if secs[i].status != 0:
+                raise GzbError(f"section {s} of VB {v}: status {secs[i].status}")
+            meta[v]["comp_len"][s] = secs[i].out_len
 
     # ------------------------------------------------------------------ PIZ, inputs resident in HBM
     def alloc_piz(self, meta):
@@ -272,45 +263,38 @@ class FastqCodecPath:
         self.seq_out_d = torch.empty((self.V, self.n), **u8)
         self.qual_out_d = torch.empty((self.V, self.n), **u8)
 
-    def _meta_arrays(self, meta):
-        lens = {s: np.fromiter((m["len"][s] for m in meta), np.uint32, self.V) for s in STREAMS}
-        clens = {s: np.fromiter((m["comp_len"].get(s, 0) for m in meta), np.uint32, self.V) for s in STREAMS}
-        return lens, clens
-
-    def _piz_descriptors(self, meta, lens, line_len, qual_out_rows, seq_out_rows, packed_rows):
-        """DOMQ / ACGT reconstruct descriptors; returns the objects that must stay alive during the calls"""
-        V = self.V
-        pv = np.frombuffer(self.pvb, dtype=PVB_DT)
-        for fld, s in (("qual", "QUAL"), ("runs", "DOMQRUNS"), ("mplx", "QUALMPLX"), ("divr", "DIVRQUAL")):
-            pv[fld] = self._rows(self.dec_d[s]); pv[fld + "_len"] = lens[s]
-        width = max([len(m["denorm"]) for m in meta] + [1])
-        dn = np.zeros((V, width), np.uint8)                  # denormalisation tables (host memory), one row per VBlock
-        for v, m in enumerate(meta):
-            dn[v, :len(m["denorm"])] = np.frombuffer(m["denorm"], np.uint8)
-        pv["denorm"] = np.uint64(dn.ctypes.data) + np.arange(V, dtype=np.uint64) * np.uint64(width)
-        pv["denorm_len"] = np.fromiter((len(m["denorm"]) for m in meta), np.uint32, V)
-        pv["num_norm_qs"] = np.fromiter((m["num_norm_qs"] for m in meta), np.uint8, V)
-        pv["line_len"] = line_len.data_ptr(); pv["n_lines"] = self.n_reads
-        pv["out"] = qual_out_rows; pv["out_cap"] = self.n
-        av = np.frombuffer(self.avb, dtype=AVB_DT)
-        av["seq"] = seq_out_rows; av["n_bases"] = self.n; av["packed"] = packed_rows
-        no_x = np.fromiter((m["acgt_no_x"] for m in meta), bool, V)
-        av["x"] = np.where(no_x, np.uint64(0), self._rows(self.dec_d["NONREF_X"]))
-        return dn
-
     def piz_device(self, meta):
-        L, V, eng = self.L, self.V, self.eng
-        lens, clens = self._meta_arrays(meta)
-        secs, _ = self._section_array(STREAMS, {s: self._rows(self.comp_d[s]) for s in STREAMS}, clens,
-                                      {s: self._rows(self.dec_d[s]) for s in STREAMS}, lens, {})
-        self._run_sections(eng.uncompress_raw, secs, GZB_DEVICE_PTRS)
-        self.kernel_ms = (float(L.gzb_last_kernel_ms(eng.h, 0)), float(L.gzb_last_kernel_ms(eng.h, 1)))
-        keep = self._piz_descriptors(meta, lens, self.line_len_d, self._rows(self.qual_out_d), self._rows(self.seq_out_d), self._rows(self.packed_d))
-        if L.gzb_domq_reconstruct(eng.h, self.pvb, V, GZB_DEVICE_PTRS):
-            raise GzbError(f"gzb_domq_reconstruct: {eng._err()}")
-        if L.gzb_acgt_unpack_batch(eng.h, self.avb, V, GZB_DEVICE_PTRS):
-            raise GzbError(f"gzb_acgt_unpack_batch: {eng._err()}")
-        del keep
+        L, n = self.L, self.n
+        keep = []
+
+        def group(g, eng, v0, v1):
+            h = eng.h
+            idx = [(v, s) for v in range(v0, v1) for s in STREAMS if meta[v]["len"][s] > 0]
+            secs = (Section * len(idx))()
+            for i, (v, s) in enumerate(idx):
+                secs[i].codec = CODEC[self.codec[s]]
+                secs[i].in_ = self.comp_d[s][v].data_ptr(); secs[i].in_len = meta[v]["comp_len"][s]
+                secs[i].out = self.dec_d[s][v].data_ptr(); secs[i].out_cap = meta[v]["len"][s]
+            eng.uncompress_raw(secs, len(idx), GZB_DEVICE_PTRS)
+            for v in range(v0, v1):
+                a, m = self.pvb[v], meta[v]
+                a.qual = self.dec_d["QUAL"][v].data_ptr(); a.qual_len = m["len"]["QUAL"]
+                a.runs = self.dec_d["DOMQRUNS"][v].data_ptr(); a.runs_len = m["len"]["DOMQRUNS"]
+                a.mplx = self.dec_d["QUALMPLX"][v].data_ptr(); a.mplx_len = m["len"]["QUALMPLX"]
+                a.divr = self.dec_d["DIVRQUAL"][v].data_ptr(); a.divr_len = m["len"]["DIVRQUAL"]
+                dn = np.frombuffer(m["denorm"], np.uint8); keep.append(dn)
+                a.denorm = dn.ctypes.data; a.denorm_len = dn.size; a.num_norm_qs = m["num_norm_qs"]
+                a.line_len = self.line_len_d.data_ptr(); a.n_lines = self.n_reads
+                a.out = self.qual_out_d[v].data_ptr(); a.out_cap = n
+                b = self.avb[v]
+                b.seq = self.seq_out_d[v].data_ptr(); b.n_bases = n; b.packed = self.packed_d[v].data_ptr()
+                b.x = None if meta[v]["acgt_no_x"] else self.dec_d["NONREF_X"][v].data_ptr()
+            if L.gzb_domq_reconstruct(h, self._sub(self.pvb, v0, v1), v1 - v0, GZB_DEVICE_PTRS):
+                raise GzbError(f"gzb_domq_reconstruct: {eng._err()}")
+            if L.gzb_acgt_unpack_batch(h, self._sub(self.avb, v0, v1), v1 - v0, GZB_DEVICE_PTRS):
+                raise GzbError(f"gzb_acgt_unpack_batch: {eng._err()}")
+
+        self._each_group(group)
 
     # ------------------------------------------------------------------ HOST-buffer path (e2e): what the C host would call
     def alloc_host(self, data):
@@ -329,6 +313,83 @@ class FastqCodecPath:
         self.h["seq_out"] = hp(V, n); self.h["qual_out"] = hp(V, n)
         self.h["dec"] = {s: hp(V, self.dec_d[s].shape[1]) for s in ("Q_TILE", "Q_X", "Q_Y", "Q_MISC")}
 
+    def zip_host(self):
+        """host buffers in, host buffers out; the DOMQ streams stay on the device between codec_domq_compress and
+        its sub-codec (GZB_OUT_DEVICE / GZB_SEC_IN_DEVICE) exactly as they stay inside one compute thread in the reference.
+        The three independent pipelines of a FASTQ VBlock — QUAL (DOMQ + its four sub-streams), SEQ (ACGT + its exception
+        stream) and the read-name contexts — run on one engine (host thread + stream) each, so the transfers of one
+        overlap the entropy chains of another; QUAL's upload goes first because its chains are the longest.
+        Returns (meta, h2d_bytes, d2h_bytes)."""
+        L, V, n, H = self.L, self.V, self.n, self.h
+        meta = [dict(len={}, comp_len={}) for _ in range(V)]
+        for v in range(V):
+            b = self.avb[v]
+            b.seq = H["seq"][v].data_ptr(); b.n_bases = n; b.packed = H["packed"][v].data_ptr(); b.x = self.x_d[v].data_ptr()
+            a = self.dvb[v]
+            a.txt = H["qual"][v].data_ptr(); a.txt_len = n
+            a.line_off = self.line_off_h.data_ptr(); a.line_len = self.line_len_h.data_ptr(); a.n_lines = self.n_reads
+            a.line_dom = H["linedom"][v].data_ptr(); a.line_diverse = H["linediv"][v].data_ptr()
+            for fld, s in (("qual", "QUAL"), ("runs", "DOMQRUNS"), ("mplx", "QUALMPLX"), ("divr", "DIVRQUAL")):
+                setattr(a, fld, self.dq[s][v].data_ptr()); setattr(a, fld + "_cap", self.caps[s])
+        on_dev = set(self.dq) | {"NONREF_X"}                # intermediate streams stay in HBM until their sub-codec
+        qual_up = threading.Event()
+
+        def in_ptr(s, v):
+            if s in self.dq: return self.dq[s][v].data_ptr()
+            if s == "NONREF_X": return self.x_d[v].data_ptr()
+            return H[s][v].data_ptr()
+
+        def compress(eng, names):
+            idx = [(v, s) for v in range(V) for s in names if meta[v]["len"][s] > 0]
+            secs = (Section * len(idx))()
+            for i, (v, s) in enumerate(idx):
+                secs[i].codec = CODEC[self.codec[s]]
+                secs[i].in_ = in_ptr(s, v); secs[i].in_len = meta[v]["len"][s]
+                secs[i].out = H["comp"][s][v].data_ptr(); secs[i].out_cap = est_size(self.codec[s], meta[v]["len"][s])
+                secs[i].sflags = GZB_SEC_IN_DEVICE if s in on_dev else 0
+            eng.compress_raw(secs, len(idx), 0)
+            self._collect(secs, idx, meta)
+
+        def part_qual(eng):
+            try:
+                if L.gzb_domq_prepare(eng.h, self.dvb, V, GZB_OUT_DEVICE):
+                    raise GzbError(f"gzb_domq_prepare: {eng._err()}")
+            finally:
+                qual_up.set()
+            if L.gzb_domq_split(eng.h, self.dvb, V, GZB_OUT_DEVICE):
+                raise GzbError(f"gzb_domq_split: {eng._err()}")
+            for v in range(V):
+                a, m = self.dvb[v], meta[v]
+                m["len"].update(QUAL=a.qual_len, DOMQRUNS=a.runs_len, QUALMPLX=a.mplx_len, DIVRQUAL=a.divr_len)
+                m["num_norm_qs"] = a.num_norm_qs
+                m["denorm"] = bytes(a.denorm)[:a.num_norm_qs * a.num_doms]
+            compress(eng, ("QUAL", "DOMQRUNS", "QUALMPLX", "DIVRQUAL"))
+
+        def part_seq(eng):
+            qual_up.wait()
+            for v0 in range(0, V, 64):                          # bounded staging in the engine workspace
+                if L.gzb_acgt_pack_batch(eng.h, self._sub(self.avb, v0, min(V, v0 + 64)), min(V, v0 + 64) - v0, GZB_OUT_DEVICE):
+                    raise GzbError(f"gzb_acgt_pack_batch: {eng._err()}")
+            for v in range(V):
+                meta[v]["acgt_no_x"] = bool(self.avb[v].x_all_zero)
+                meta[v]["len"]["NONREF_X"] = 0 if self.avb[v].x_all_zero else n
+            compress(eng, ("NONREF_X",))
+
+        def part_names(eng):
+            for v in range(V):
+                meta[v]["len"].update(Q_TILE=self.n_reads, Q_X=4 * self.n_reads, Q_Y=4 * self.n_reads, Q_MISC=self.n_reads)
+            qual_up.wait()
+            compress(eng, ("Q_TILE", "Q_X", "Q_Y", "Q_MISC"))
+
+        self._run_parts([part_qual, part_seq, part_names])
+        h2d = V * (n + n + 12 * self.n_reads); d2h = V * (self.packed_len + 2 * self.n_reads)
+        for m in meta:
+            for s, ln in m["len"].items():
+                if ln:
+                    if s not in on_dev: h2d += ln
+                    d2h += m["comp_len"][s]
+        return meta, h2d, d2h
+
     def _run_parts(self, parts):
         """one engine (host thread + stream) per independent pipeline; with a single engine they run one after the other"""
         if self.pool is None or len(self.engs) < len(parts):
@@ -346,98 +407,55 @@ class FastqCodecPath:
                 raise errs[0]
         self.kernel_ms = tuple(float(np.max([self.L.gzb_last_kernel_ms(e.h, w) for e in self.engs])) for w in (0, 1))
 
-    QUAL_STREAMS = ("QUAL", "DOMQRUNS", "QUALMPLX", "DIVRQUAL")
-    NAME_STREAMS = ("Q_TILE", "Q_X", "Q_Y", "Q_MISC")
-
-    def zip_host(self):
-        """host buffers in, host buffers out; the DOMQ streams stay on the device between codec_domq_compress and
-        its sub-codec (GZB_OUT_DEVICE / GZB_SEC_IN_DEVICE) exactly as they stay inside one compute thread in the reference.
-        The three independent pipelines of a FASTQ VBlock — QUAL (DOMQ + its four sub-streams), SEQ (ACGT + its exception
-        stream) and the read-name contexts — run on one engine (host thread + stream) each, so the transfers of one
-        overlap the entropy chains of another; QUAL's upload goes first because its chains are the longest.
-        Returns (meta, h2d_bytes, d2h_bytes)."""
-        L, V, n, H = self.L, self.V, self.n, self.h
-        av, dv = self._zip_descriptors(self._rows(H["seq"]), self._rows(H["packed"]), self._rows(H["qual"]),
-                                       self.line_off_h, self.line_len_h, self._rows(H["linedom"]), self._rows(H["linediv"]))
-        on_dev = set(self.dq) | {"NONREF_X"}                # intermediate streams stay in HBM until their sub-codec
-        in_rows = {s: self._rows(self.dq[s]) for s in self.dq}
-        in_rows["NONREF_X"] = self._rows(self.x_d)
-        in_rows.update({s: self._rows(H[s]) for s in self.NAME_STREAMS})
-        out_rows = {s: self._rows(H["comp"][s]) for s in STREAMS}
-        out_cap = {s: H["comp"][s].shape[1] for s in STREAMS}
-        sflags = {s: GZB_SEC_IN_DEVICE for s in on_dev}
-        nr = self.n_reads
-        lens = {"Q_TILE": np.full(V, nr, np.uint32), "Q_X": np.full(V, 4 * nr, np.uint32), "Q_Y": np.full(V, 4 * nr, np.uint32), "Q_MISC": np.full(V, nr, np.uint32)}
-        done = {}
-        qual_up = threading.Event()
-
-        def compress(eng, names):
-            secs, mask = self._section_array(names, in_rows, lens, out_rows, out_cap, sflags)
-            self._run_sections(eng.compress_raw, secs, 0)
-            done[names] = (secs, mask)
-
-        def part_qual(eng):
-            try:
-                if L.gzb_domq_prepare(eng.h, self.dvb, V, GZB_OUT_DEVICE):
-                    raise GzbError(f"gzb_domq_prepare: {eng._err()}")
-            finally:
-                qual_up.set()
-            if L.gzb_domq_split(eng.h, self.dvb, V, GZB_OUT_DEVICE):
-                raise GzbError(f"gzb_domq_split: {eng._err()}")
-            lens.update(QUAL=dv["qual_len"].copy(), DOMQRUNS=dv["runs_len"].copy(), QUALMPLX=dv["mplx_len"].copy(), DIVRQUAL=dv["divr_len"].copy())
-            compress(eng, self.QUAL_STREAMS)
-
-        def part_seq(eng):
-            qual_up.wait()
-            for v0 in range(0, V, 64):                          # bounded staging in the engine workspace
-                v1 = min(V, v0 + 64)
-                if L.gzb_acgt_pack_batch(eng.h, self._sub(self.avb, v0, v1), v1 - v0, GZB_OUT_DEVICE):
-                    raise GzbError(f"gzb_acgt_pack_batch: {eng._err()}")
-            lens["NONREF_X"] = np.where(av["x_all_zero"] != 0, 0, n).astype(np.uint32)
-            compress(eng, ("NONREF_X",))
-
-        def part_names(eng):
-            qual_up.wait()
-            compress(eng, self.NAME_STREAMS)
-
-        self._run_parts([part_qual, part_seq, part_names])
-        meta = self._make_meta(av, dv, lens)
-        for names, (secs, mask) in done.items():
-            self._store_comp_lens(meta, names, secs, mask)
-        h2d = V * (n + n + 12 * nr) + int(sum(int(lens[s].sum()) for s in self.NAME_STREAMS))
-        d2h = V * (self.packed_len + 2 * nr) + int(sum(int(secs["out_len"].sum()) for secs, _ in done.values()))
-        return meta, h2d, d2h
-
     def piz_host(self, meta):
         L, V, n, H = self.L, self.V, self.n, self.h
-        lens, clens = self._meta_arrays(meta)
-        on_dev = set(self.dq) | {"NONREF_X"}
-        in_rows = {s: self._rows(H["comp"][s]) for s in STREAMS}
-        out_rows = {s: self._rows(self.dec_d[s] if s in on_dev else H["dec"][s]) for s in STREAMS}
-        sflags = {s: GZB_SEC_OUT_DEVICE for s in on_dev}
-        keep = self._piz_descriptors(meta, lens, self.line_len_h, self._rows(H["qual_out"]), self._rows(H["seq_out"]), self._rows(H["packed"]))
+        keep = []
 
         def uncompress(eng, names):
-            secs, _ = self._section_array(names, in_rows, clens, out_rows, lens, sflags)
-            self._run_sections(eng.uncompress_raw, secs, 0)
+            idx = [(v, s) for v in range(V) for s in names if meta[v]["len"][s] > 0]
+            secs = (Section * len(idx))()
+            for i, (v, s) in enumerate(idx):
+                on_dev = s in self.dq or s == "NONREF_X"
+                secs[i].codec = CODEC[self.codec[s]]
+                secs[i].in_ = H["comp"][s][v].data_ptr(); secs[i].in_len = meta[v]["comp_len"][s]
+                secs[i].out = (self.dec_d[s][v] if on_dev else H["dec"][s][v]).data_ptr(); secs[i].out_cap = meta[v]["len"][s]
+                secs[i].sflags = GZB_SEC_OUT_DEVICE if on_dev else 0
+            eng.uncompress_raw(secs, len(idx), 0)
 
         def part_qual(eng):
-            uncompress(eng, self.QUAL_STREAMS)
+            uncompress(eng, ("QUAL", "DOMQRUNS", "QUALMPLX", "DIVRQUAL"))
+            for v in range(V):
+                a, m = self.pvb[v], meta[v]
+                a.qual = self.dec_d["QUAL"][v].data_ptr(); a.qual_len = m["len"]["QUAL"]
+                a.runs = self.dec_d["DOMQRUNS"][v].data_ptr(); a.runs_len = m["len"]["DOMQRUNS"]
+                a.mplx = self.dec_d["QUALMPLX"][v].data_ptr(); a.mplx_len = m["len"]["QUALMPLX"]
+                a.divr = self.dec_d["DIVRQUAL"][v].data_ptr(); a.divr_len = m["len"]["DIVRQUAL"]
+                dn = np.frombuffer(m["denorm"], np.uint8); keep.append(dn)
+                a.denorm = dn.ctypes.data; a.denorm_len = dn.size; a.num_norm_qs = m["num_norm_qs"]
+                a.line_len = self.line_len_h.data_ptr(); a.n_lines = self.n_reads
+                a.out = H["qual_out"][v].data_ptr(); a.out_cap = n
             if L.gzb_domq_reconstruct(eng.h, self.pvb, V, GZB_IN_DEVICE):
                 raise GzbError(f"gzb_domq_reconstruct: {eng._err()}")
 
         def part_seq(eng):
             uncompress(eng, ("NONREF_X",))
+            for v in range(V):
+                b = self.avb[v]
+                b.seq = H["seq_out"][v].data_ptr(); b.n_bases = n; b.packed = H["packed"][v].data_ptr()
+                b.x = None if meta[v]["acgt_no_x"] else self.dec_d["NONREF_X"][v].data_ptr()
             for v0 in range(0, V, 64):
-                v1 = min(V, v0 + 64)
-                if L.gzb_acgt_unpack_batch(eng.h, self._sub(self.avb, v0, v1), v1 - v0, GZB_IN_DEVICE):
+                if L.gzb_acgt_unpack_batch(eng.h, self._sub(self.avb, v0, min(V, v0 + 64)), min(V, v0 + 64) - v0, GZB_IN_DEVICE):
                     raise GzbError(f"gzb_acgt_unpack_batch: {eng._err()}")
 
         def part_names(eng):
-            uncompress(eng, self.NAME_STREAMS)
+            uncompress(eng, ("Q_TILE", "Q_X", "Q_Y", "Q_MISC"))
 
         self._run_parts([part_qual, part_seq, part_names])
-        del keep
-        h2d = V * (4 * self.n_reads + self.packed_len) + int(sum(int(clens[s].sum()) for s in STREAMS))
-        d2h = V * (n + n) + int(sum(int(lens[s].sum()) for s in self.NAME_STREAMS))
+        on_dev = set(self.dq) | {"NONREF_X"}
+        h2d = V * (4 * self.n_reads + self.packed_len); d2h = V * (n + n)
+        for m in meta:
+            for s, ln in m["len"].items():
+                if ln:
+                    h2d += m["comp_len"][s]
+                    if s not in on_dev: d2h += ln
         return h2d, d2h

@@ -59,13 +59,3 @@ def test_fastq_path_host_driver(n_engines):
     assert h2d >= 2 * V * n and d2h_p >= 2 * V * n and d2h > 0 and h2d_p > 0
     path.close()
 
-
-def test_descriptor_dtypes_match_the_c_structs():
-    """the numpy views used to fill descriptor arrays column-wise must have the C-ABI structs' exact layout"""
-    import ctypes as C
-    from genozip_b200.fastq_path import SEC_DT, DVB_DT, PVB_DT, AVB_DT
-    from genozip_b200.lib import Section, DomqVb, DomqPizVb, AcgtVb
-    for dt, st in ((SEC_DT, Section), (DVB_DT, DomqVb), (PVB_DT, DomqPizVb), (AVB_DT, AcgtVb)):
-        assert dt.itemsize == C.sizeof(st)
-        for name, _ in st._fields_:
-            assert dt.fields[name][1] == getattr(st, name).offset, (st.__name__, name)
