@@ -29,7 +29,7 @@ def _varint_len(n):
     return k
 
 
-@pytest.mark.parametrize("kind", ["qual", "skew8", "text", "u32le", "runs"])
+@pytest.mark.parametrize("kind", ["qual", "skew8", "text", "u32le", "runs", "uniform256", "all256", "const", "zeros_hi", "two"])
 def test_host_arith_bodies_match_reference(har, kind):
     impl = "ref" if orc.have_ref() else "port"
     for n in (1, 2, 5, 50, 1000, 30000, 150000):
