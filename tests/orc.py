@@ -92,6 +92,28 @@ def ref():
     return _ref
 
 
+_gzref = None
+
+
+def have_gz_ref():
+    return os.path.exists(os.path.join(ODIR, "_ref", "libgz_ref.so")) or os.path.isdir("/root/reference/src/htscodecs")
+
+
+def gz_ref():
+    """the reference's own genozip codec objects (codec_domq.c ...) hosted by oracle/ref_gz_shim.c"""
+    global _gzref
+    if _gzref is None:
+        p = os.path.join(ODIR, "_ref", "libgz_ref.so")
+        if not os.path.exists(p):
+            _build()
+        L = C.CDLL(p)
+        L.ref_domq_encode.restype = C.c_int
+        L.ref_domq_encode.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32] + [C.c_void_p, u32p] * 5 + [C.POINTER(C.c_uint8)] * 2
+        L.ref_gz_last_error.restype = C.c_char_p
+        _gzref = L
+    return _gzref
+
+
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
@@ -178,6 +200,24 @@ def domq_encode(txt, off, lens):
                 normalize=np.frombuffer(bytes(t.normalize), np.uint8).copy(),
                 line_dom=dom[:n].copy(), line_diverse=div[:n].copy(),
                 qual=qual[:ql.value].copy(), runs=runs[:rl.value].copy(), mplx=mplx[:ml.value].copy(), divr=divr[:dl.value].copy())
+
+
+def ref_domq_encode(txt, off, lens):
+    """codec_domq_comp_init (forced) + codec_domq_compress of the REFERENCE's compiled codec_domq.c on these lines
+    -> dict(qual, runs, mplx, divr, denorm, num_norm_qs, has_diverse)"""
+    L = gz_ref()
+    txt = np.ascontiguousarray(txt, np.uint8); off = np.ascontiguousarray(off, np.uint64); lens = np.ascontiguousarray(lens, np.uint32)
+    tot = int(lens.sum())
+    qual = np.zeros(2 * tot + 16, np.uint8); runs = np.zeros(tot + 16, np.uint8); mplx = np.zeros(lens.size + 16, np.uint8)
+    divr = np.zeros(tot + 16, np.uint8); den = np.zeros(95 * 95 * 2, np.uint8)
+    ql, rl, ml, dl, nl = (C.c_uint32() for _ in range(5)); prm, hd = C.c_uint8(), C.c_uint8()
+    tx = txt if txt.size else np.zeros(1, np.uint8)
+    rc = L.ref_domq_encode(_ptr(tx), txt.size, _ptr(off), _ptr(lens), lens.size, _ptr(qual), C.byref(ql), _ptr(runs), C.byref(rl),
+                           _ptr(mplx), C.byref(ml), _ptr(divr), C.byref(dl), _ptr(den), C.byref(nl), C.byref(prm), C.byref(hd))
+    assert rc == 0, f"reference codec_domq aborted ({rc}): {L.ref_gz_last_error().decode()}"
+    assert prm.value & 0x80                                                 # MSb set since 14.0.5 (codec_domq.c:234)
+    return dict(qual=qual[:ql.value].copy(), runs=runs[:rl.value].copy(), mplx=mplx[:ml.value].copy(), divr=divr[:dl.value].copy(),
+                denorm=den[:nl.value].copy(), num_norm_qs=prm.value & 0x7f, has_diverse=hd.value)
 
 
 def domq_decode(enc, lens):
