@@ -1,13 +1,12 @@
 /* oracle/gz_port.c — CPU restatement of genozip's own codecs on the hot path: ACGT/XCGT, DOMQ, PBWT, LONGR.
  * TEST INFRASTRUCTURE ONLY — see oracle/oracle.h.
  *
- * Parity status: these reference translation units (src/codec_{acgt,domq,pbwt,longr}.c) cannot be linked
- * without the whole licence-gated program and the reference ships no vectors for them, so this
- * restatement follows each reference function line by line (citations below, relative to
- * /root/reference/src) and is pinned by round-tripping every encoder through a restatement of the
- * reference DECODER, which is written from the decoder's own source and shares no code with the encoder
- * (tests/test_oracle_gz.py).  Interfaces are flat (buffers + line tables) — what the reference reads
- * through VBlock/Context is passed explicitly.
+ * Parity status: the ENCODERS are pinned byte-for-byte against the reference's own compiled translation units
+ * (src/codec_{acgt,domq,pbwt,longr}.c, unmodified, hosted by oracle/ref_gz_shim.c -> oracle/_ref/libgz_ref.so;
+ * tests/test_oracle_gz_ref.py).  The DECODERS restate the reference decoder from its own source (no code shared with
+ * the encoders) and are pinned by inverting the pinned encoders (tests/test_oracle_gz.py).  Each function follows
+ * its reference function line by line (citations below, relative to /root/reference/src).  Interfaces are flat
+ * (buffers + line tables) — what the reference reads through VBlock/Context is passed explicitly.
  */
 #include <stdlib.h>
 #include <string.h>

@@ -8,11 +8,14 @@
  *   - rANS 4x16 / adaptive arithmetic / PACK / STRIPE / CAT (hts_port.c): PINNED — every function is
  *     differential-tested byte-for-byte against oracle/_ref/libhts_ref.so, which is the reference's own
  *     htscodecs translation units compiled unmodified with the reference's flags (oracle/Makefile).
- *   - DOMQ / ACGT / PBWT / LONGR (gz_port.c): the reference ships no golden vectors and those translation
- *     units cannot be linked without the whole (licence-gated) program; the restatement follows the
- *     reference encoder line by line and is pinned by round-tripping through an independent restatement
- *     of the reference DECODER (different code path, cited separately).  Whole-file .genozip identity:
- *     parity unpinned (closed licence.o).
+ *   - DOMQ / ACGT / PBWT / LONGR (gz_port.c): PINNED (encoders) — differential-tested byte-for-byte against
+ *     oracle/_ref/libgz_ref.so: the reference's own codec_domq.c, codec_acgt.c, codec_pbwt.c, codec_longr.c compiled
+ *     unmodified with the reference's flags and hosted outside the (licence-gated) program by oracle/ref_gz_shim.c,
+ *     which is compiled against the reference's headers, hand-makes the VBlock / Contexts a compute thread would
+ *     pass and supplies the ~40 host symbols those objects need; the nucleotide tables are the .rodata of the
+ *     reference's compiled reference.c (tests/test_oracle_gz_ref.py).  The decoders are pinned by round trips:
+ *     a restatement of the reference DECODER (different code path, cited separately) must invert the pinned encoder.
+ *     Whole-file .genozip identity: parity unpinned (closed licence.o).
  *
  * All citations are relative to /root/reference/src.
  */

@@ -2,10 +2,15 @@
 // see oracle/Makefile) outside the genozip program: this file is compiled against the reference's headers (so VBlock, Context,
 // Buffer, CodecArgs ... have the reference's exact layouts), hand-constructs the minimal VBlock a compute thread would hand
 // to the codec, supplies the ~20 host symbols the object needs (buffer allocation, seg_by_ctx, codec table ...) and exports
-// one flat entry point:
+// flat entry points:
 //
 //     ref_domq_encode ()   =  codec_domq_comp_init (force)  +  codec_domq_compress ()          (codec_domq.c:299-323, 379-521)
+//     ref_acgt_pack ()     =  codec_acgt_compress () up to (and capturing) its sub-codec call  (codec_acgt.c:64-177)
+//     ref_longr_encode ()  =  codec_longr_segconf_calculate_bins () + codec_longr_compress ()  (codec_longr.c:66-264)
+//     ref_pbwt_encode ()   =  codec_pbwt_compress ()                                           (codec_pbwt.c:244-287)
 //
+// The nucleotide tables _acgt_encode / _acgt_encode_comp are the reference's own (.rodata of its compiled reference.c,
+// extracted with objcopy: oracle/Makefile).
 // so that the CPU restatement (oracle/gz_port.c) — and through it the CUDA path — is pinned against the reference's compiled
 // code rather than against a reading of it.  Only built where /root/reference exists; nothing here is reference source.
 #include "genozip.h"
@@ -21,6 +26,8 @@
 #include "reconstruct.h"
 #include "profiler.h"
 #include "sam.h"
+#include "fastq.h"
+#include "vcf.h"
 #include "sections.h"
 #include <stdarg.h>
 #include <setjmp.h>
@@ -93,6 +100,32 @@ void buf_copy_do (VBlockP dst_vb, BufferP dst, ConstBufferP src, uint64_t bytes_
     dst->len = n;
 }
 
+void buf_set_shared (BufferP buf) { buf->shared = 1; }                     // (the shim never frees shared memory: the harness is short-lived)
+void buf_overlay_do (VBlockP vb, BufferP top_buf, BufferP bottom_buf, uint64_t start_in_bottom, bool copy_len, FUNCLINE, rom name)
+{
+    top_buf->memory = bottom_buf->memory; top_buf->data = bottom_buf->data + start_in_bottom; top_buf->size = bottom_buf->size - start_in_bottom;
+    top_buf->type = BUF_REGULAR; top_buf->shared = 1; top_buf->vb = vb; top_buf->name = name;
+    if (copy_len) top_buf->len = bottom_buf->len;
+}
+
+// codec scratch (codec.c:30-82): plain heap blocks, all released by codec_free_all
+static void *codec_blocks[64]; static int n_codec_blocks;
+void *codec_alloc_do (VBlockP vb, uint64_t size, float grow_at_least_factor, unsigned *buf_i, FUNCLINE)
+{
+    ASSERT0 (n_codec_blocks < 64, "shim: too many codec_alloc blocks");
+    return codec_blocks[n_codec_blocks++] = malloc (size + 64);
+}
+void codec_free_do (void *vb, void *addr, FUNCLINE) {}
+void codec_free_all (VBlockP vb) { while (n_codec_blocks) free (codec_blocks[--n_codec_blocks]); }
+uint32_t codec_complex_est_size (Codec codec, uint64_t uncompressed_len) { return (uint32_t)uncompressed_len + 1024; }
+void BGEN_u32_buf (BufferP buf, LocalType *lt) { ABORT0 ("shim: BGEN_u32_buf"); }
+void ctx_consolidate_stats (VBlockP vb, int parent, ...) {}
+StrText line_name (VBlockP vb) { StrText t = {}; strcpy (t.s, "line(shim)"); return t; }
+bool sam_is_last_flags_rev_comp (VBlockP vb) { ABORT0 ("shim: sam_is_last_flags_rev_comp"); }
+rom sam_piz_get_textual_seq (VBlockP vb) { ABORT0 ("shim: sam_piz_get_textual_seq"); }
+int64_t reconstruct_from_local_int (VBlockP vb, ContextP ctx, char separator, ReconType reconstruct) { ABORT0 ("shim: reconstruct_from_local_int"); }
+uint32_t str_int_ex (int64_t n, char *str, bool add_nul_terminator) { int k = sprintf (str, "%"PRId64, n); return (uint32_t)k; }
+
 // ---------------------------------------------------------------- segmenter / context services used by codec_domq.c
 static uint8_t denorm_snip[NUM_CODECS * 0 + 95 * 95 * 2];
 static uint32_t denorm_snip_len;
@@ -124,6 +157,17 @@ static uint32_t shim_est_size (Codec codec, uint64_t uncompressed_len) { return 
 CodecArgs codec_args[NUM_CODECS];
 Codec codec_assign_best_codec (VBlockP vb, ContextP ctx, BufferP non_ctx_data, SectionType st) { return CODEC_NONE; }
 
+static void shim_init (void)
+{
+    info_stream = stderr;
+    memset (&flag, 0, sizeof flag);
+    flag.command = ZIP;                                                     // IS_ZIP (genozip.h:405)
+    flag.show_time_comp_i = COMP_NONE;                                      // profiler off (profiler.h:119)
+    memset (&segconf, 0, sizeof segconf);
+    memset (&the_z_file, 0, sizeof the_z_file);
+    for (int c = 0; c < NUM_CODECS; c++) { codec_args[c].compress = shim_store; codec_args[c].est_size = shim_est_size; }
+}
+
 // ---------------------------------------------------------------- the lines of the hand-made VBlock
 static uint8_t *g_txt; static const uint64_t *g_off; static const uint32_t *g_len;
 static COMPRESSOR_CALLBACK (shim_get_line)
@@ -138,9 +182,7 @@ int ref_domq_encode (const uint8_t *txt, uint64_t txt_len, const uint64_t *line_
                      uint8_t *qual, uint32_t *qual_len, uint8_t *runs, uint32_t *runs_len, uint8_t *mplx, uint32_t *mplx_len,
                      uint8_t *divr, uint32_t *divr_len, uint8_t *denorm, uint32_t *denorm_len, uint8_t *param, uint8_t *has_diverse)
 {
-    info_stream = stderr;
-    flag.show_time_comp_i = COMP_NONE;                                      // profiler off (profiler.h:119)
-    for (int c = 0; c < NUM_CODECS; c++) { codec_args[c].compress = shim_store; codec_args[c].est_size = shim_est_size; }
+    shim_init ();
     if (setjmp (on_abort)) return -1;
     VBlockP vb = calloc (1, sizeof (VBlock));
     vb->vblock_i = 1;
@@ -168,6 +210,106 @@ int ref_domq_encode (const uint8_t *txt, uint64_t txt_len, const uint64_t *line_
     memcpy (denorm, denorm_snip, denorm_snip_len); *denorm_len = denorm_snip_len;
     free (comp); free (g_txt);
     for (int k = 0; k < 4; k++) { buf_destroy_do (&qual_ctx[k].local, __FUNCLINE); }
+    free (vb);
+    return 0;
+}
+
+// ================================================================ ACGT
+// NONREF.local = the bases; returns the 2-bit words handed to the sub-codec, the exception stream (NONREF_X.local) and acgt_no_x
+int ref_acgt_pack (const uint8_t *seq, uint64_t n, uint8_t *packed, uint64_t *packed_len, uint8_t *x, int *no_x)
+{
+    shim_init ();
+    if (setjmp (on_abort)) return -1;
+    VBlockP vb = calloc (1, sizeof (VBlock));
+    vb->vblock_i = 1;
+    ContextP nonref = CTX (FASTQ_NONREF);
+    nonref[0].did_i = FASTQ_NONREF; nonref[1].did_i = FASTQ_NONREF + 1;
+    strcpy (nonref[0].tag_name, "NONREF"); strcpy (nonref[1].tag_name, "NONREF_X");
+    buf_alloc_do (vb, &nonref->local, n + 8, 1, "local", __FUNCLINE);
+    memcpy (nonref->local.data, seq, n); nonref->local.len = n;
+    SectionHeaderCtx header = {};
+    uint32_t ulen = (uint32_t)n, clen = (uint32_t)(n / 4 + 1024);
+    char *comp = malloc (clen);
+    cap_out = NULL; cap_len = 0;
+    if (!codec_acgt_compress (vb, nonref, (SectionHeaderP)&header, nonref->local.data, &ulen, NULL, comp, &clen, true, "NONREF")) return -3;
+    memcpy (packed, cap_out, cap_len); *packed_len = cap_len;
+    *no_x = header.flags.ctx.acgt_no_x;
+    if (!*no_x) memcpy (x, nonref[1].local.data, n); else memset (x, 0, n);
+    free (comp); free (vb);
+    return 0;
+}
+
+// ================================================================ LONGR
+static const uint64_t *g_seq_off; static const uint8_t *g_is_rev;
+static COMPRESSOR_CALLBACK (shim_get_qual_rev)
+{
+    *line_data = (char *)g_txt + g_off[vb_line_i];
+    *line_data_len = g_len[vb_line_i];
+    if (is_rev) *is_rev = g_is_rev ? g_is_rev[vb_line_i] : 0;
+}
+static void shim_get_seq (VBlockP vb, LineIType vb_line_i, char **line_data, uint32_t *line_data_len, bool *is_rev)
+{
+    *line_data = (char *)g_txt + g_seq_off[vb_line_i];
+    *line_data_len = g_len[vb_line_i];
+    if (is_rev) *is_rev = g_is_rev ? g_is_rev[vb_line_i] : 0;
+}
+COMPRESSOR_CALLBACK (fastq_zip_seq) { shim_get_seq (vb, vb_line_i, line_data, line_data_len, is_rev); }
+COMPRESSOR_CALLBACK (sam_zip_seq)   { shim_get_seq (vb, vb_line_i, line_data, line_data_len, is_rev); }
+
+// txt holds the SEQ and QUAL strings; is_rev NULL = FASTQ (never reverse-complemented), else SAM-like per-line flags
+int ref_longr_encode (const uint8_t *txt, uint64_t txt_len, const uint64_t *seq_off, const uint64_t *qual_off, const uint32_t *len, const uint8_t *is_rev,
+                      uint32_t n_lines, uint8_t *value_to_bin, uint8_t *values, uint32_t *lens_be)
+{
+    shim_init ();
+    if (setjmp (on_abort)) return -1;
+    VBlockP vb = calloc (1, sizeof (VBlock));
+    evb = calloc (1, sizeof (VBlock));
+    vb->vblock_i = 1; vb->lines.len = n_lines;
+    vb->data_type = is_rev ? DT_SAM : DT_FASTQ;
+    g_txt = malloc (txt_len + 1); memcpy (g_txt, txt, txt_len); g_off = qual_off; g_seq_off = seq_off; g_len = len; g_is_rev = is_rev;
+    vb->txt_data.len = txt_len;                                            // Ltxt: the callbacks' size limit
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n_lines; i++) total += len[i];
+    ContextP qual_ctx = CTX (SAM_QUAL);
+    for (int k = 0; k < 2; k++) { qual_ctx[k].did_i = SAM_QUAL + k; strcpy (qual_ctx[k].tag_name, k ? "DOMQRUNS" : "QUAL"); }
+
+    segconf.running = true;                                                 // main thread, once per file (codec_longr.c:66-136)
+    codec_longr_segconf_calculate_bins (vb, qual_ctx + 1, shim_get_qual_rev);
+    segconf.running = false;
+    memcpy (value_to_bin, ZCTX (SAM_QUAL + 1)->value_to_bin.data, 256);
+
+    SectionHeaderCtx header = {};
+    uint32_t ulen = (uint32_t)total, clen = 65536 * 4 + 4096;
+    char *comp = malloc (clen);
+    cap_out = NULL; cap_len = 0;
+    if (!codec_longr_compress (vb, qual_ctx, (SectionHeaderP)&header, NULL, &ulen, shim_get_qual_rev, comp, &clen, true, "QUAL")) return -3;
+    if (cap_len != 65536 * 4) return -4;
+    memcpy (lens_be, cap_out, cap_len);
+    memcpy (values, qual_ctx[1].local.data, total);
+    free (comp); free (g_txt); free (vb); free (evb); evb = NULL;
+    return 0;
+}
+
+// ================================================================ PBWT
+int ref_pbwt_encode (const uint8_t *ht, uint32_t n_lines, uint32_t ht_per_line, uint32_t *runs, uint32_t *n_runs, uint32_t *fgrc, uint32_t *n_fgrc)
+{
+    shim_init ();
+    if (setjmp (on_abort)) return -1;
+    VBlockP vb = calloc (1, sizeof (VBlock));
+    vb->vblock_i = 1;
+    ContextP ht_ctx = CTX (FORMAT_GT_HT), runs_ctx = CTX (FORMAT_PBWT_RUNS), fgrc_ctx = CTX (FORMAT_PBWT_FGRC);
+    ht_ctx->did_i = FORMAT_GT_HT; runs_ctx->did_i = FORMAT_PBWT_RUNS; fgrc_ctx->did_i = FORMAT_PBWT_FGRC;
+    uint64_t n = (uint64_t)n_lines * ht_per_line;
+    buf_alloc_do (vb, &ht_ctx->local, n + 8, 1, "local", __FUNCLINE);
+    memcpy (ht_ctx->local.data, ht, n); ht_ctx->local.len = n;
+    ht_ctx->ht_per_line = ht_per_line; ht_ctx->HT_n_lines = n_lines;
+    SectionHeaderCtx header = {};
+    uint32_t ulen = (uint32_t)n, clen = 1024;
+    char comp[1024];
+    if (!codec_pbwt_compress (vb, ht_ctx, (SectionHeaderP)&header, NULL, &ulen, NULL, comp, &clen, true, "HT")) return -3;
+    if (clen != 0) return -4;                                               // the matrix itself produces no section (:280-282)
+    *n_runs = runs_ctx->local.len32; memcpy (runs, runs_ctx->local.data, 4ull * *n_runs);
+    *n_fgrc = fgrc_ctx->local.len32; memcpy (fgrc, fgrc_ctx->local.data, 4ull * *n_fgrc);
     free (vb);
     return 0;
 }

@@ -110,6 +110,12 @@ def gz_ref():
         L.ref_domq_encode.restype = C.c_int
         L.ref_domq_encode.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32] + [C.c_void_p, u32p] * 5 + [C.POINTER(C.c_uint8)] * 2
         L.ref_gz_last_error.restype = C.c_char_p
+        L.ref_acgt_pack.restype = C.c_int
+        L.ref_acgt_pack.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, u64p, C.c_void_p, C.POINTER(C.c_int)]
+        L.ref_pbwt_encode.restype = C.c_int
+        L.ref_pbwt_encode.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, u32p, C.c_void_p, u32p]
+        L.ref_longr_encode.restype = C.c_int
+        L.ref_longr_encode.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         _gzref = L
     return _gzref
 
@@ -218,6 +224,41 @@ def ref_domq_encode(txt, off, lens):
     assert prm.value & 0x80                                                 # MSb set since 14.0.5 (codec_domq.c:234)
     return dict(qual=qual[:ql.value].copy(), runs=runs[:rl.value].copy(), mplx=mplx[:ml.value].copy(), divr=divr[:dl.value].copy(),
                 denorm=den[:nl.value].copy(), num_norm_qs=prm.value & 0x7f, has_diverse=hd.value)
+
+
+def _gz_check(rc, what):
+    assert rc == 0, f"reference {what} failed ({rc}): {gz_ref().ref_gz_last_error().decode()}"
+
+
+def ref_acgt_pack(seq):
+    """the REFERENCE's compiled codec_acgt_compress up to its sub-codec call -> (packed LE words, exception stream, acgt_no_x)"""
+    seq = np.ascontiguousarray(seq, np.uint8)
+    packed = np.zeros(seq.size // 4 + 64, np.uint8); x = np.zeros(seq.size + 8, np.uint8)
+    pl, nox = C.c_uint64(), C.c_int()
+    _gz_check(gz_ref().ref_acgt_pack(_ptr(seq), seq.size, _ptr(packed), C.byref(pl), _ptr(x), C.byref(nox)), "codec_acgt")
+    return packed[:pl.value].copy(), x[:seq.size].copy(), bool(nox.value)
+
+
+def ref_pbwt_encode(ht):
+    """the REFERENCE's compiled codec_pbwt_compress -> (RUNS u32, FGRC u32), host-endian"""
+    ht = np.ascontiguousarray(ht, np.uint8)
+    n_lines, w = ht.shape
+    runs = np.zeros(2 * ht.size + 8, np.uint32); fgrc = np.zeros(ht.size + 8, np.uint32)
+    nr, nf = C.c_uint32(), C.c_uint32()
+    _gz_check(gz_ref().ref_pbwt_encode(_ptr(ht), n_lines, w, _ptr(runs), C.byref(nr), _ptr(fgrc), C.byref(nf)), "codec_pbwt")
+    return runs[:nr.value].copy(), fgrc[:nf.value].copy()
+
+
+def ref_longr_encode(txt, seq_off, qual_off, lens, is_rev):
+    """the REFERENCE's compiled codec_longr_segconf_calculate_bins + codec_longr_compress -> (value_to_bin, values, lens_be)"""
+    txt = np.ascontiguousarray(txt, np.uint8); seq_off = np.ascontiguousarray(seq_off, np.uint64)
+    qual_off = np.ascontiguousarray(qual_off, np.uint64); lens = np.ascontiguousarray(lens, np.uint32)
+    rv = None if is_rev is None else np.ascontiguousarray(is_rev, np.uint8)
+    tot = int(lens.sum())
+    v2b = np.zeros(256, np.uint8); values = np.zeros(tot + 8, np.uint8); lens_be = np.zeros(65536, np.uint32)
+    _gz_check(gz_ref().ref_longr_encode(_ptr(txt), txt.size, _ptr(seq_off), _ptr(qual_off), _ptr(lens), None if rv is None else _ptr(rv),
+                                        lens.size, _ptr(v2b), _ptr(values), _ptr(lens_be)), "codec_longr")
+    return v2b, values[:tot].copy(), lens_be
 
 
 def domq_decode(enc, lens):

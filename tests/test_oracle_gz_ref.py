@@ -1,11 +1,16 @@
-"""Pins the CPU restatement of DOMQ (oracle/gz_port.c) against the REFERENCE's own compiled codec_domq.c
-(oracle/_ref/libgz_ref.so: the unmodified translation unit hosted by oracle/ref_gz_shim.c with a hand-made VBlock):
-the four streams, the de-normalisation table and the section parameter must be byte-identical — FASTQ-like VBlocks,
-ragged lines, empty lines, all-dominant and all-diverse VBlocks, dom runs across lines, the 254/255 run-length escapes,
-ties between qualities (dom choice and qsort order of the rank tables)."""
+"""Pins the CPU restatement of genozip's own codecs (oracle/gz_port.c) against the REFERENCE's own compiled translation units
+codec_domq.c, codec_acgt.c, codec_pbwt.c, codec_longr.c (oracle/_ref/libgz_ref.so: unmodified, hosted by oracle/ref_gz_shim.c
+with a hand-made VBlock; nucleotide tables from the reference's compiled reference.c):
+  DOMQ   the four streams, the de-normalisation table and the section parameter — FASTQ-like VBlocks, ragged and empty lines,
+         all-dominant and all-diverse VBlocks, dom runs across lines, the 254/255 run-length escapes, ties between qualities
+         (dom choice and libc qsort order of the rank tables);
+  ACGT   the 2-bit words handed to the sub-codec, the exception stream, acgt_no_x — IUPAC codes, lower case, odd characters;
+  PBWT   RUNS and FGRC — bi- and multi-allelic matrices incl. the pseudo alleles;
+  LONGR  the value-to-bin map, the channel-sorted values and the 65,536 big-endian channel lengths — forward and
+         reverse-complemented reads."""
 import numpy as np, pytest
 import orc
-from datagen import fastq_vb, line_table, ragged_quals
+from datagen import fastq_vb, line_table, ragged_quals, haplotype_matrix, longread_vb
 
 pytestmark = pytest.mark.skipif(not orc.have_gz_ref(), reason="oracle/_ref/libgz_ref.so not built and /root/reference absent")
 
@@ -59,3 +64,48 @@ def test_many_qualities_and_rank_ties():
             line[rng.integers(0, ln, k)] = rng.integers(33, 127, k)      # many distinct rare qualities: equal counts -> qsort tie order
             q[i * ln:(i + 1) * ln] = line
         check(q, *line_table(n_lines, ln))
+
+
+# ------------------------------------------------------------------------------------------------ ACGT
+def test_acgt_against_reference():
+    seq, _ = fastq_vb(300, 151, 1, lower_frac=0.01, n_frac=0.01)
+    pure = np.frombuffer(b"ACGT", np.uint8)[np.random.default_rng(2).integers(0, 4, 100000)].copy()
+    odd = np.frombuffer(b"ACGTNacgtnRYSWKMBDHVUryswkmbdhvu*-.", np.uint8).copy()
+    allb = np.arange(256, dtype=np.uint8)                                   # every byte value
+    for s in [seq, pure, odd, allb] + [seq[:n].copy() for n in (1, 5, 31, 32, 33, 63, 64, 65, 1000, 4097)]:
+        p, x, nox = orc.ref_acgt_pack(s)
+        pw, xw, zw = orc.acgt_pack(s)
+        assert np.array_equal(p, pw) and np.array_equal(x, xw) and nox == zw, f"n={s.size}"
+
+
+# ------------------------------------------------------------------------------------------------ PBWT
+@pytest.mark.parametrize("n_lines,n_samples,multi", [(50, 40, False), (50, 40, True), (200, 1000, False), (200, 1000, True), (7, 3, False), (300, 17, True), (1, 5, False)])
+def test_pbwt_against_reference(n_lines, n_samples, multi):
+    ht = haplotype_matrix(n_lines, n_samples, n_lines + n_samples, multi=multi)
+    r, f = orc.ref_pbwt_encode(ht)
+    rw, fw = orc.pbwt_encode(ht)
+    assert r.size == rw.size and np.array_equal(r, rw) and f.size == fw.size and np.array_equal(f, fw)
+
+
+def test_pbwt_pseudo_alleles_against_reference():
+    rng = np.random.default_rng(5)
+    alleles = np.frombuffer(b"0011122.*%-&", np.uint8)
+    ht = alleles[rng.integers(0, alleles.size, (60, 48))]
+    r, f = orc.ref_pbwt_encode(ht)
+    rw, fw = orc.pbwt_encode(ht)
+    assert np.array_equal(r, rw) and np.array_equal(f, fw)
+
+
+# ------------------------------------------------------------------------------------------------ LONGR
+@pytest.mark.parametrize("n_reads,mean_len,seed,rev", [(12, 3000, 5, False), (12, 3000, 5, True), (40, 500, 6, True), (3, 20, 7, False), (200, 150, 8, True)])
+def test_longr_against_reference(n_reads, mean_len, seed, rev):
+    seq, qual, lens = longread_vb(n_reads, mean_len, seed)
+    n = int(lens.sum())
+    txt = np.concatenate([seq, qual])
+    seq_off = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint64); qual_off = seq_off + np.uint64(n)
+    is_rev = (np.random.default_rng(seed).random(n_reads) < 0.5).astype(np.uint8) if rev else None
+    v2b_ref, values_ref, lens_ref = orc.ref_longr_encode(txt, seq_off, qual_off, lens, is_rev)
+    v2b = orc.longr_bins(qual)
+    values, lens_be = orc.longr_encode(txt, seq_off, qual_off, lens, is_rev, v2b)
+    assert np.array_equal(v2b, v2b_ref), "value_to_bin (codec_longr_segconf_calculate_bins)"
+    assert np.array_equal(values, values_ref) and np.array_equal(lens_be, lens_ref)
