@@ -22,6 +22,9 @@ def test_acgt(eng):
         p, x, allz = eng.acgt_pack(s)
         pw, xw, zw = orc.acgt_pack(s)
         assert np.array_equal(p, pw) and np.array_equal(x, xw) and allz == zw, f"n={n}"
+        if orc.have_gz_ref() and n:                                         # the reference's own compiled codec_acgt.c
+            pr, xr, zr = orc.ref_acgt_pack(s)
+            assert np.array_equal(p, pr) and np.array_equal(x, xr) and allz == zr, f"n={n}: GPU != reference codec_acgt.c"
         assert np.array_equal(eng.acgt_unpack(pw, None if zw else xw, n), s)
     # pure ACGT: exception stream all zero -> acgt_no_x (codec_acgt.c:136-140)
     s = np.frombuffer(b"ACGT", np.uint8)[np.random.default_rng(2).integers(0, 4, 100000)].copy()
@@ -59,6 +62,10 @@ def _check_domq(eng, vbs):
             assert g[k] == w[k], k
         for k in ("denorm", "line_dom", "line_diverse", "qual", "runs", "mplx", "divr"):
             assert g[k].size == w[k].size and np.array_equal(g[k], w[k]), f"{k}: GPU != oracle (len {g[k].size} vs {w[k].size})"
+        if orc.have_gz_ref() and ln.size:                                   # the reference's own compiled codec_domq.c
+            r = orc.ref_domq_encode(txt, off, ln)
+            for k in ("denorm", "qual", "runs", "mplx", "divr"):
+                assert np.array_equal(g[k], r[k]), f"{k}: GPU != reference codec_domq.c"
     back = eng.domq_decode(got, [v[2] for v in vbs])
     for (txt, off, ln), b, g in zip(vbs, back, got):
         want = np.concatenate([txt[int(o):int(o) + int(l)] for o, l in zip(off, ln)]) if ln.sum() else np.zeros(0, np.uint8)

@@ -1,5 +1,6 @@
-"""GPU parity tests for PBWT and LONGR: CUDA path through the C-ABI vs the CPU restatement (oracle/gz_port.c), word- and
-byte-exact, and back through both decoders."""
+"""GPU parity tests for PBWT and LONGR: CUDA path through the C-ABI vs the CPU restatement (oracle/gz_port.c) and, where
+oracle/_ref/libgz_ref.so travelled, vs the reference's own compiled codec_pbwt.c / codec_longr.c — word- and byte-exact —
+and back through both decoders."""
 import numpy as np, pytest
 import orc
 from datagen import haplotype_matrix, longread_vb
@@ -23,6 +24,9 @@ def test_pbwt(eng, shape, multi):
     wr, wf = orc.pbwt_encode(ht)
     assert runs.size == wr.size and np.array_equal(runs, wr), "RUNS differ from the oracle"
     assert fgrc.size == wf.size and np.array_equal(fgrc, wf), "FGRC differ from the oracle"
+    if orc.have_gz_ref():
+        rr, rf = orc.ref_pbwt_encode(ht)
+        assert np.array_equal(runs, rr) and np.array_equal(fgrc, rf), "differs from the reference's compiled codec_pbwt.c"
     back = eng.pbwt_decode(wr, wf, ht.shape[0], ht.size)
     assert np.array_equal(back.reshape(ht.shape), ht)
 
@@ -45,6 +49,9 @@ def test_longr(eng, rev):
         wv, wl = orc.longr_encode(vb[0], vb[1], vb[2], vb[3], vb[4], vb[5])
         assert np.array_equal(lb, wl), "channel lengths differ from the oracle"
         assert np.array_equal(vals, wv), "sorted values differ from the oracle"
+        if orc.have_gz_ref():
+            rb, rv, rl = orc.ref_longr_encode(vb[0], vb[1], vb[2], vb[3], vb[4])
+            assert np.array_equal(rb, vb[5]) and np.array_equal(vals, rv) and np.array_equal(lb, rl), "differs from the reference's compiled codec_longr.c"
     back = eng.longr_decode(list(vbs), [g[0] for g in got], [g[1] for g in got])
     for q, b in zip(quals, back):
         assert np.array_equal(b, q)
