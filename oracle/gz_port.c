@@ -4,7 +4,8 @@
  * Parity status: the ENCODERS are pinned byte-for-byte against the reference's own compiled translation units
  * (src/codec_{acgt,domq,pbwt,longr}.c, unmodified, hosted by oracle/ref_gz_shim.c -> oracle/_ref/libgz_ref.so;
  * tests/test_oracle_gz_ref.py).  The DECODERS restate the reference decoder from its own source (no code shared with
- * the encoders) and are pinned by inverting the pinned encoders (tests/test_oracle_gz.py).  Each function follows
+ * the encoders); they are pinned against the reference's own uncompress / reconstruct functions from the same objects
+ * (same test file) and by inverting the pinned encoders (tests/test_oracle_gz.py).  Each function follows
  * its reference function line by line (citations below, relative to /root/reference/src).  Interfaces are flat
  * (buffers + line tables) — what the reference reads through VBlock/Context is passed explicitly.
  */

@@ -8,13 +8,15 @@
  *   - rANS 4x16 / adaptive arithmetic / PACK / STRIPE / CAT (hts_port.c): PINNED — every function is
  *     differential-tested byte-for-byte against oracle/_ref/libhts_ref.so, which is the reference's own
  *     htscodecs translation units compiled unmodified with the reference's flags (oracle/Makefile).
- *   - DOMQ / ACGT / PBWT / LONGR (gz_port.c): PINNED (encoders) — differential-tested byte-for-byte against
+ *   - DOMQ / ACGT / PBWT / LONGR (gz_port.c): PINNED (encoders and decoders) — differential-tested byte-for-byte against
  *     oracle/_ref/libgz_ref.so: the reference's own codec_domq.c, codec_acgt.c, codec_pbwt.c, codec_longr.c compiled
  *     unmodified with the reference's flags and hosted outside the (licence-gated) program by oracle/ref_gz_shim.c,
  *     which is compiled against the reference's headers, hand-makes the VBlock / Contexts a compute thread would
  *     pass and supplies the ~40 host symbols those objects need; the nucleotide tables are the .rodata of the
- *     reference's compiled reference.c (tests/test_oracle_gz_ref.py).  The decoders are pinned by round trips:
- *     a restatement of the reference DECODER (different code path, cited separately) must invert the pinned encoder.
+ *     reference's compiled reference.c (tests/test_oracle_gz_ref.py).  The decoders (restated from the reference's
+ *     PIZ code, cited separately) are compared with the reference's own codec_acgt_uncompress / codec_xcgt_uncompress,
+ *     codec_pbwt_uncompress, codec_domq_reconstruct and codec_longr_reconstruct hosted the same way, and must invert
+ *     the pinned encoders.
  *     Whole-file .genozip identity: parity unpinned (closed licence.o).
  *
  * All citations are relative to /root/reference/src.

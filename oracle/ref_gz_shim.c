@@ -8,6 +8,10 @@
 //     ref_acgt_pack ()     =  codec_acgt_compress () up to (and capturing) its sub-codec call  (codec_acgt.c:64-177)
 //     ref_longr_encode ()  =  codec_longr_segconf_calculate_bins () + codec_longr_compress ()  (codec_longr.c:66-264)
 //     ref_pbwt_encode ()   =  codec_pbwt_compress ()                                           (codec_pbwt.c:244-287)
+//     ref_acgt_unpack ()   =  codec_acgt_uncompress () [+ codec_xcgt_uncompress ()]            (codec_acgt.c:185-248)
+//     ref_pbwt_decode ()   =  codec_pbwt_uncompress ()                                         (codec_pbwt.c:372-402)
+//     ref_domq_decode ()   =  codec_domq_reconstruct () line by line                           (codec_domq.c:774-809)
+//     ref_longr_decode ()  =  codec_longr_reconstruct () read by read                          (codec_longr.c:342-373)
 //
 // The nucleotide tables _acgt_encode / _acgt_encode_comp are the reference's own (.rodata of its compiled reference.c,
 // extracted with objcopy: oracle/Makefile).
@@ -118,11 +122,12 @@ void *codec_alloc_do (VBlockP vb, uint64_t size, float grow_at_least_factor, uns
 void codec_free_do (void *vb, void *addr, FUNCLINE) {}
 void codec_free_all (VBlockP vb) { while (n_codec_blocks) free (codec_blocks[--n_codec_blocks]); }
 uint32_t codec_complex_est_size (Codec codec, uint64_t uncompressed_len) { return (uint32_t)uncompressed_len + 1024; }
-void BGEN_u32_buf (BufferP buf, LocalType *lt) { ABORT0 ("shim: BGEN_u32_buf"); }
+void BGEN_u32_buf (BufferP buf, LocalType *lt) { uint32_t *w = (uint32_t *)buf->data; for (uint64_t i = 0; i < buf->len; i++) w[i] = __builtin_bswap32 (w[i]); }
 void ctx_consolidate_stats (VBlockP vb, int parent, ...) {}
 StrText line_name (VBlockP vb) { StrText t = {}; strcpy (t.s, "line(shim)"); return t; }
-bool sam_is_last_flags_rev_comp (VBlockP vb) { ABORT0 ("shim: sam_is_last_flags_rev_comp"); }
-rom sam_piz_get_textual_seq (VBlockP vb) { ABORT0 ("shim: sam_piz_get_textual_seq"); }
+static rom cur_seq; static bool cur_is_rev;                                // the read being reconstructed (LONGR decoder harness)
+bool sam_is_last_flags_rev_comp (VBlockP vb) { return cur_is_rev; }
+rom sam_piz_get_textual_seq (VBlockP vb) { return cur_seq; }
 int64_t reconstruct_from_local_int (VBlockP vb, ContextP ctx, char separator, ReconType reconstruct) { ABORT0 ("shim: reconstruct_from_local_int"); }
 uint32_t str_int_ex (int64_t n, char *str, bool add_nul_terminator) { int k = sprintf (str, "%"PRId64, n); return (uint32_t)k; }
 
@@ -138,7 +143,7 @@ WordIndex seg_by_ctx_ex (VBlockP vb, STRp(snip), ContextP ctx, uint32_t add_byte
 unsigned base64_encode (STR8p(in), char *restrict b64_str) { memcpy (b64_str, in, in_len); return in_len; }   // identity: the table is captured raw
 uint32_t base64_decode (STRp(b64_str), STR8c(out)) { memcpy (out, b64_str, b64_str_len); return b64_str_len; }
 void ctx_set_ltype (VBlockP vb, int ltype, ...) {}
-WordIndex ctx_peek_next_snip (VBlockP vb, ContextP ctx, pSTRp (snip)) { *snip = NULL; *snip_len = 0; return 0; }
+WordIndex ctx_peek_next_snip (VBlockP vb, ContextP ctx, pSTRp (snip)) { *snip = (rom)denorm_snip; *snip_len = denorm_snip_len; return 0; }   // DOMQRUNS' single snip: the de-normalisation table
 // PIZ / consensus-read paths of codec_domq.c that the encoder harness never takes
 void sam_reconstruct_missing_quality (VBlockP vb, ReconType reconstruct) { ABORT0 ("shim: sam_reconstruct_missing_quality"); }
 void sam_xcons_reconstruct_QUAL (VBlockP vb, ContextP ctx, uint32_t qual_len, bool reconstruct) { ABORT0 ("shim: sam_xcons_reconstruct_QUAL"); }
@@ -153,6 +158,7 @@ static COMPRESS (shim_store)
     cap_out = (uint8_t *)compressed; cap_len = *uncompressed_len;
     return true;
 }
+static UNCOMPRESS (shim_unstore) { memcpy (uncompressed_buf->data, compressed, compressed_len); }
 static uint32_t shim_est_size (Codec codec, uint64_t uncompressed_len) { return (uint32_t)uncompressed_len + 64; }
 CodecArgs codec_args[NUM_CODECS];
 Codec codec_assign_best_codec (VBlockP vb, ContextP ctx, BufferP non_ctx_data, SectionType st) { return CODEC_NONE; }
@@ -165,7 +171,7 @@ static void shim_init (void)
     flag.show_time_comp_i = COMP_NONE;                                      // profiler off (profiler.h:119)
     memset (&segconf, 0, sizeof segconf);
     memset (&the_z_file, 0, sizeof the_z_file);
-    for (int c = 0; c < NUM_CODECS; c++) { codec_args[c].compress = shim_store; codec_args[c].est_size = shim_est_size; }
+    for (int c = 0; c < NUM_CODECS; c++) { codec_args[c].compress = shim_store; codec_args[c].uncompress = shim_unstore; codec_args[c].est_size = shim_est_size; }
 }
 
 // ---------------------------------------------------------------- the lines of the hand-made VBlock
@@ -310,6 +316,118 @@ int ref_pbwt_encode (const uint8_t *ht, uint32_t n_lines, uint32_t ht_per_line, 
     if (clen != 0) return -4;                                               // the matrix itself produces no section (:280-282)
     *n_runs = runs_ctx->local.len32; memcpy (runs, runs_ctx->local.data, 4ull * *n_runs);
     *n_fgrc = fgrc_ctx->local.len32; memcpy (fgrc, fgrc_ctx->local.data, 4ull * *n_fgrc);
+    free (vb);
+    return 0;
+}
+
+// ================================================================ PIZ side
+static void shim_init_piz (void)
+{
+    shim_init ();
+    flag.command = PIZ;
+    the_z_file.genozip_ver = (Version){ 15, 86 };                           // VER(14), VER2(15,76): the current file format
+}
+
+int ref_acgt_unpack (const uint8_t *packed, uint64_t packed_len, const uint8_t *x /* NULL = acgt_no_x */, uint64_t n, uint8_t *seq)
+{
+    shim_init_piz ();
+    if (setjmp (on_abort)) return -1;
+    VBlockP vb = calloc (1, sizeof (VBlock));
+    vb->vblock_i = 1;
+    ContextP nonref = CTX (FASTQ_NONREF);
+    nonref[0].did_i = FASTQ_NONREF; nonref[1].did_i = FASTQ_NONREF + 1;
+    nonref->flags.acgt_no_x = (x == NULL);
+    buf_alloc_do (vb, &nonref->local, n + 8, 1, "local", __FUNCLINE); nonref->local.len = n;        // allocated by the caller (zfile.c:229)
+    codec_acgt_uncompress (vb, nonref, CODEC_ACGT, 0, (rom)packed, (uint32_t)packed_len, &nonref->local, n, CODEC_NONE, "NONREF");
+    if (x) {
+        buf_alloc_do (vb, &nonref[1].local, n + 8, 1, "local", __FUNCLINE); nonref[1].local.len = n;
+        codec_xcgt_uncompress (vb, nonref + 1, CODEC_XCGT, 0, (rom)x, (uint32_t)n, &nonref[1].local, n, CODEC_NONE, "NONREF_X");
+    }
+    memcpy (seq, nonref->local.data, n);
+    free (vb);
+    return 0;
+}
+
+// runs: host-endian uint32 (as after piz_adjust_one_local); fgrc_be: the FGRC section as stored (big-endian words, :380-381)
+int ref_pbwt_decode (const uint32_t *runs, uint32_t n_runs, const uint32_t *fgrc_be, uint32_t n_fgrc, uint32_t n_lines, uint8_t *ht, uint64_t *ht_len)
+{
+    shim_init_piz ();
+    if (setjmp (on_abort)) return -1;
+    VBlockP vb = calloc (1, sizeof (VBlock) + (1 << 20));                   // (codec_pbwt.c casts to the larger VCF VBlock)
+    vb->vblock_i = 1; vb->lines.len = n_lines;
+    ContextP ht_ctx = CTX (FORMAT_GT_HT), runs_ctx = CTX (FORMAT_PBWT_RUNS), fgrc_ctx = CTX (FORMAT_PBWT_FGRC);
+    ht_ctx->did_i = FORMAT_GT_HT; runs_ctx->did_i = FORMAT_PBWT_RUNS; fgrc_ctx->did_i = FORMAT_PBWT_FGRC;
+    ht_ctx->HT_n_lines = n_lines;
+    buf_alloc_do (vb, &runs_ctx->local, 4ull * n_runs + 8, 1, "local", __FUNCLINE);
+    memcpy (runs_ctx->local.data, runs, 4ull * n_runs); runs_ctx->local.len = n_runs;
+    buf_alloc_do (vb, &vb->scratch, 4ull * n_fgrc + 8, 1, "scratch", __FUNCLINE);                     // a sub-codec's input lives in vb->scratch
+    memcpy (vb->scratch.data, fgrc_be, 4ull * n_fgrc); vb->scratch.len = n_fgrc;
+    codec_pbwt_uncompress (vb, fgrc_ctx, CODEC_PBWT, 0, vb->scratch.data, 4 * n_fgrc, &fgrc_ctx->local, 0, CODEC_NONE, "FGRC");
+    *ht_len = ht_ctx->local.len;
+    memcpy (ht, ht_ctx->local.data, ht_ctx->local.len);
+    free (vb);
+    return 0;
+}
+
+// the four DOMQ streams + table + parameter of one VBlock -> the quality strings of lines of the given lengths
+int ref_domq_decode (const uint8_t *qual, uint32_t qual_len, const uint8_t *runs, uint32_t runs_len, const uint8_t *mplx, uint32_t mplx_len,
+                     const uint8_t *divr, uint32_t divr_len, const uint8_t *denorm, uint32_t denorm_len, uint8_t param,
+                     const uint32_t *line_len, uint32_t n_lines, uint8_t *out)
+{
+    shim_init_piz ();
+    if (setjmp (on_abort)) return -1;
+    VBlockP vb = calloc (1, sizeof (VBlock));
+    vb->vblock_i = 1; vb->lines.len = n_lines;
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n_lines; i++) total += line_len[i];
+    ContextP c = CTX (SAM_QUAL);
+    const uint8_t *src[4] = { qual, runs, mplx, divr }; uint32_t len[4] = { qual_len, runs_len, mplx_len, divr_len };
+    for (int k = 0; k < 4; k++) {
+        c[k].did_i = SAM_QUAL + k; c[k].is_loaded = true;
+        buf_alloc_do (vb, &c[k].local, len[k] + 8, 1, "local", __FUNCLINE);
+        memcpy (c[k].local.data, src[k], len[k]); c[k].local.len = len[k];
+    }
+    c[0].local.prm8[0] = param;
+    c[0].dict_id.num = 0;
+    memcpy (denorm_snip, denorm, denorm_len); denorm_snip_len = denorm_len;
+    buf_alloc_do (vb, &vb->txt_data, total + 64, 1, "txt_data", __FUNCLINE);
+    for (uint32_t i = 0; i < n_lines; i++)
+        if (line_len[i]) codec_domq_reconstruct (vb, CODEC_DOMQ, c, line_len[i], true);            // (empty QUAL lines are not routed to the codec)
+    if (vb->txt_data.len != total) return -5;
+    memcpy (out, vb->txt_data.data, total);
+    free (vb);
+    return 0;
+}
+
+// values + big-endian channel lengths + value_to_bin of one VBlock -> the quality strings; is_rev NULL = FASTQ-like (never reversed)
+int ref_longr_decode (const uint8_t *txt, const uint64_t *seq_off, const uint32_t *len, const uint8_t *is_rev, uint32_t n_lines,
+                      const uint8_t *value_to_bin, const uint8_t *values, const uint32_t *lens_be, uint8_t *out)
+{
+    shim_init_piz ();
+    if (setjmp (on_abort)) return -1;
+    VBlockP vb = calloc (1, sizeof (VBlock));
+    vb->vblock_i = 1; vb->lines.len = n_lines; vb->data_type = DT_SAM;      // SEQ and the strand come through the sam_* accessors above
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n_lines; i++) total += len[i];
+    ContextP c = CTX (SAM_QUAL);
+    c[0].did_i = SAM_QUAL; c[1].did_i = SAM_QUAL + 1;
+    buf_alloc_do (vb, &c[0].local, 65536 * 4 + 8, 1, "local", __FUNCLINE);
+    memcpy (c[0].local.data, lens_be, 65536 * 4); c[0].local.len = 65536 * 4;
+    buf_alloc_do (vb, &c[1].local, total + 8, 1, "local", __FUNCLINE);
+    memcpy (c[1].local.data, values, total); c[1].local.len = total;
+    ContextP zv = ZCTX (SAM_QUAL + 1);                                      // SEC_COUNTS of the values context: the value-to-bin map as 256 x uint64
+    buf_alloc_do (NULL, &zv->counts, 256 * 8, 1, "counts", __FUNCLINE);
+    for (int i = 0; i < 256; i++) ((uint64_t *)zv->counts.data)[i] = value_to_bin[i];
+    zv->counts.len = 256;
+    buf_alloc_do (vb, &vb->txt_data, total + 64, 1, "txt_data", __FUNCLINE);
+    for (uint32_t i = 0; i < n_lines; i++) {
+        if (!len[i]) continue;
+        cur_seq = (rom)txt + seq_off[i]; cur_is_rev = is_rev ? is_rev[i] : false;
+        vb->seq_len = len[i];
+        codec_longr_reconstruct (vb, CODEC_LONGR, c, len[i], true);
+    }
+    if (vb->txt_data.len != total) return -5;
+    memcpy (out, vb->txt_data.data, total);
     free (vb);
     return 0;
 }

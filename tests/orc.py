@@ -116,6 +116,12 @@ def gz_ref():
         L.ref_pbwt_encode.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, u32p, C.c_void_p, u32p]
         L.ref_longr_encode.restype = C.c_int
         L.ref_longr_encode.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        for f in ("ref_acgt_unpack", "ref_pbwt_decode", "ref_domq_decode", "ref_longr_decode"):
+            getattr(L, f).restype = C.c_int
+        L.ref_acgt_unpack.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]
+        L.ref_pbwt_decode.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, u64p]
+        L.ref_domq_decode.argtypes = [C.c_void_p, C.c_uint32] * 5 + [C.c_uint8, C.c_void_p, C.c_uint32, C.c_void_p]
+        L.ref_longr_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _gzref = L
     return _gzref
 
@@ -259,6 +265,50 @@ def ref_longr_encode(txt, seq_off, qual_off, lens, is_rev):
     _gz_check(gz_ref().ref_longr_encode(_ptr(txt), txt.size, _ptr(seq_off), _ptr(qual_off), _ptr(lens), None if rv is None else _ptr(rv),
                                         lens.size, _ptr(v2b), _ptr(values), _ptr(lens_be)), "codec_longr")
     return v2b, values[:tot].copy(), lens_be
+
+
+def ref_acgt_unpack(packed, x, n):
+    """the REFERENCE's compiled codec_acgt_uncompress (+ codec_xcgt_uncompress when x is given) -> the n bases"""
+    packed = np.ascontiguousarray(packed, np.uint8)
+    xx = None if x is None else np.ascontiguousarray(x, np.uint8)
+    seq = np.zeros(n + 8, np.uint8)
+    _gz_check(gz_ref().ref_acgt_unpack(_ptr(packed), packed.size, None if xx is None else _ptr(xx), n, _ptr(seq)), "codec_acgt_uncompress")
+    return seq[:n].copy()
+
+
+def ref_pbwt_decode(runs, fgrc, n_lines, size):
+    """the REFERENCE's compiled codec_pbwt_uncompress; runs/fgrc host-endian as from pbwt_encode (FGRC is handed over as stored: big-endian)"""
+    r = np.ascontiguousarray(runs, np.uint32); f = np.ascontiguousarray(fgrc, np.uint32).byteswap()
+    ht = np.zeros(size + 64, np.uint8); hl = C.c_uint64()
+    _gz_check(gz_ref().ref_pbwt_decode(_ptr(r), r.size, _ptr(f), f.size, n_lines, _ptr(ht), C.byref(hl)), "codec_pbwt_uncompress")
+    assert hl.value == size, (hl.value, size)
+    return ht[:size].copy()
+
+
+def ref_domq_decode(enc, lens):
+    """the REFERENCE's compiled codec_domq_reconstruct, line by line -> all quality strings concatenated"""
+    lens = np.ascontiguousarray(lens, np.uint32)
+    out = np.zeros(int(lens.sum()) + 8, np.uint8)
+    a = [np.ascontiguousarray(enc[k], np.uint8) for k in ("qual", "runs", "mplx", "divr", "denorm")]
+    z = np.zeros(1, np.uint8)
+    args = []
+    for v in a:
+        args += [_ptr(v if v.size else z), v.size]
+    _gz_check(gz_ref().ref_domq_decode(*args, 0x80 | int(enc["num_norm_qs"]), _ptr(lens), lens.size, _ptr(out)), "codec_domq_reconstruct")
+    return out[:int(lens.sum())].copy()
+
+
+def ref_longr_decode(txt, seq_off, lens, is_rev, v2b, values, lens_be):
+    """the REFERENCE's compiled codec_longr_reconstruct, read by read"""
+    txt = np.ascontiguousarray(txt, np.uint8); seq_off = np.ascontiguousarray(seq_off, np.uint64); lens = np.ascontiguousarray(lens, np.uint32)
+    rv = None if is_rev is None else np.ascontiguousarray(is_rev, np.uint8)
+    tot = int(lens.sum())
+    out = np.zeros(tot + 8, np.uint8)
+    v = np.ascontiguousarray(values, np.uint8) if values.size else np.zeros(1, np.uint8)
+    lb = np.ascontiguousarray(lens_be, np.uint32); vb = np.ascontiguousarray(v2b, np.uint8)
+    _gz_check(gz_ref().ref_longr_decode(_ptr(txt), _ptr(seq_off), _ptr(lens), None if rv is None else _ptr(rv), lens.size, _ptr(vb), _ptr(v), _ptr(lb),
+                                        _ptr(out)), "codec_longr_reconstruct")
+    return out[:tot].copy()
 
 
 def domq_decode(enc, lens):

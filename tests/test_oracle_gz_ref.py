@@ -7,7 +7,10 @@ with a hand-made VBlock; nucleotide tables from the reference's compiled referen
   ACGT   the 2-bit words handed to the sub-codec, the exception stream, acgt_no_x — IUPAC codes, lower case, odd characters;
   PBWT   RUNS and FGRC — bi- and multi-allelic matrices incl. the pseudo alleles;
   LONGR  the value-to-bin map, the channel-sorted values and the 65,536 big-endian channel lengths — forward and
-         reverse-complemented reads."""
+         reverse-complemented reads.
+The PIZ side is pinned the same way: the reference's codec_acgt_uncompress / codec_xcgt_uncompress, codec_pbwt_uncompress,
+codec_domq_reconstruct (line by line) and codec_longr_reconstruct (read by read) must reproduce the input from the streams, and
+the restated decoders must agree with them byte for byte (incl. on streams the reference encoder produced)."""
 import numpy as np, pytest
 import orc
 from datagen import fastq_vb, line_table, ragged_quals, haplotype_matrix, longread_vb
@@ -21,6 +24,11 @@ def check(txt, off, lens):
     for k in ("qual", "runs", "mplx", "divr", "denorm"):
         assert r[k].size == w[k].size and np.array_equal(r[k], w[k]), f"{k}: restatement != reference (len {w[k].size} vs {r[k].size})"
     assert r["num_norm_qs"] == w["num_norm_qs"] and bool(r["has_diverse"]) == bool(w["has_diverse"])
+    # PIZ side: the reference's codec_domq_reconstruct and the restated decoder, both on the reference's streams
+    lens = np.asarray(lens, np.uint32)
+    want = np.concatenate([txt[int(o):int(o) + int(l)] for o, l in zip(off, lens)]) if lens.sum() else np.zeros(0, np.uint8)
+    assert np.array_equal(orc.ref_domq_decode(r, lens), want), "reference codec_domq_reconstruct does not give back the input"
+    assert np.array_equal(orc.domq_decode(r, lens), want), "restated DOMQ decoder != reference"
 
 
 @pytest.mark.parametrize("n_reads,read_len,seed", [(200, 150, 1), (3000, 151, 2), (50, 37, 3), (1000, 100, 4), (20000, 150, 5), (7, 1, 6), (1, 150, 7)])
@@ -76,6 +84,12 @@ def test_acgt_against_reference():
         p, x, nox = orc.ref_acgt_pack(s)
         pw, xw, zw = orc.acgt_pack(s)
         assert np.array_equal(p, pw) and np.array_equal(x, xw) and nox == zw, f"n={s.size}"
+        back = orc.ref_acgt_unpack(p, None if nox else x, s.size)           # codec_acgt_uncompress [+ codec_xcgt_uncompress]
+        lossless = s > 1                                                    # the format itself maps bytes 0 and 1 to 'A' and 'a' (exception codes 0 / 1)
+        assert np.array_equal(back[lossless], s[lossless]) and set(back[~lossless]) <= {65, 97}, f"n={s.size}: reference unpack does not give back the input"
+        assert np.array_equal(orc.acgt_unpack(p, None if nox else x, s.size), back), f"n={s.size}: restated unpack != reference"
+        if nox:                                                             # an all-zero exception stream given explicitly is a no-op
+            assert np.array_equal(orc.ref_acgt_unpack(p, x, s.size), back)
 
 
 # ------------------------------------------------------------------------------------------------ PBWT
@@ -85,6 +99,9 @@ def test_pbwt_against_reference(n_lines, n_samples, multi):
     r, f = orc.ref_pbwt_encode(ht)
     rw, fw = orc.pbwt_encode(ht)
     assert r.size == rw.size and np.array_equal(r, rw) and f.size == fw.size and np.array_equal(f, fw)
+    back = orc.ref_pbwt_decode(r, f, n_lines, ht.size)                      # codec_pbwt_uncompress
+    assert np.array_equal(back, ht.reshape(-1)), "reference codec_pbwt_uncompress does not give back the matrix"
+    assert np.array_equal(orc.pbwt_decode(r, f, n_lines, ht.size), back), "restated PBWT decoder != reference"
 
 
 def test_pbwt_pseudo_alleles_against_reference():
@@ -94,6 +111,8 @@ def test_pbwt_pseudo_alleles_against_reference():
     r, f = orc.ref_pbwt_encode(ht)
     rw, fw = orc.pbwt_encode(ht)
     assert np.array_equal(r, rw) and np.array_equal(f, fw)
+    back = orc.ref_pbwt_decode(r, f, 60, ht.size)
+    assert np.array_equal(back, ht.reshape(-1)) and np.array_equal(orc.pbwt_decode(r, f, 60, ht.size), back)
 
 
 # ------------------------------------------------------------------------------------------------ LONGR
@@ -109,3 +128,6 @@ def test_longr_against_reference(n_reads, mean_len, seed, rev):
     values, lens_be = orc.longr_encode(txt, seq_off, qual_off, lens, is_rev, v2b)
     assert np.array_equal(v2b, v2b_ref), "value_to_bin (codec_longr_segconf_calculate_bins)"
     assert np.array_equal(values, values_ref) and np.array_equal(lens_be, lens_ref)
+    back = orc.ref_longr_decode(txt, seq_off, lens, is_rev, v2b_ref, values_ref, lens_ref)   # codec_longr_reconstruct
+    assert np.array_equal(back, qual), "reference codec_longr_reconstruct does not give back QUAL"
+    assert np.array_equal(orc.longr_decode(txt, seq_off, lens, is_rev, v2b, values, lens_be), back), "restated LONGR decoder != reference"
