@@ -8,3 +8,21 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on the B200 box)")
+    if config.getoption("--dry-gpu"):
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        import mock_gzb
+        mock_gzb.install()
+
+
+def pytest_addoption(parser):
+    parser.addoption("--dry-gpu", action="store_true", default=False,
+                     help="run the -m gpu tests' own logic on a machine WITHOUT a GPU: genozip_b200.Engine's marshalling code on top of "
+                          "tests/mock_gzb.py (CPU checkers behind the C-ABI's entry points). Checks the tests and the binding, not the kernels.")
+
+
+def pytest_collection_modifyitems(config, items):
+    if config.getoption("--dry-gpu"):
+        skip = pytest.mark.skip(reason="--dry-gpu: needs device memory (covered by tests/test_fastq_path_cpu.py)")
+        for it in items:
+            if "test_gpu_fastq_path" in it.nodeid:
+                it.add_marker(skip)
