@@ -19,7 +19,7 @@
 #pragma once
 #include <stdint.h>
 
-#if defined(__CUDACC__)
+#if defined(__CUDACC__) || defined(GZB_SIMT_EMULATION)       // (the second: tests/host/simt, g++ build of this source for the SIMT emulator)
   #define AR_FN __device__ __forceinline__
   #define AR_SLOW static __device__ __noinline__
 #else
@@ -39,6 +39,17 @@
 #endif
 
 namespace gzb {
+
+// All 32 lanes of the warp run the chain redundantly and store identical values to the models.  A lane must therefore not
+// store to a model before every lane has read it.  The lanes of a converged warp issue each instruction together, so on
+// the GPU this holds as the code stands and the marker below compiles to nothing; the SIMT emulator of the CPU test suite
+// (tests/host/simt) runs lanes one after the other between rendez-vous points and turns the marker into one.  It stands
+// after every group of model reads that a store may follow.
+#if defined(GZB_SIMT_EMULATION)
+  #define AR_READS_DONE() __syncwarp ()
+#else
+  #define AR_READS_DONE()
+#endif
 
 #define AR_MAXF  65519u          // MAX_FREQ = (1<<16)-17 (c_simple_model.h:70)
 #define AR_STEP  16u             // STEP (:73)
@@ -120,6 +131,7 @@ AR_FN void ar_load (const uint32_t *m, ArCache &c)
     const uint2 h = *reinterpret_cast<const uint2 *>(m);
     const uint4 v = *reinterpret_cast<const uint4 *>(m + 4);
     c.tot = h.x; c.rtot = ar_u2f (h.y); c.e0 = v.x; c.e1 = v.y; c.e2 = v.z; c.e3 = v.w;
+    AR_READS_DONE ();
 }
 
 AR_FN void ar_store_head (uint32_t *m, uint32_t tot, float rtot)
@@ -159,6 +171,7 @@ AR_SLOW void ar_update_mem (uint32_t *m, uint32_t maxs, uint32_t p, uint32_t e, 
     }
     if (p) {
         const uint32_t prev = m[4 + p - 1];
+        AR_READS_DONE ();
         if ((en & 0xffffu) > (prev & 0xffffu)) { m[4 + p - 1] = en; m[4 + p] = prev; }
         else m[4 + p] = en;
     }
@@ -195,6 +208,7 @@ AR_SLOW ArHit ar_find_code (const uint32_t *m, uint32_t maxs, uint32_t code, uin
     const uint32_t *q = m + 4 + 8 * owner;
     const uint4 v0 = *reinterpret_cast<const uint4 *>(q), v1 = *reinterpret_cast<const uint4 *>(q + 4);
     const uint32_t pl = q[-1];                                              // entry before the lane's first (owner 0: header padding, unused)
+    AR_READS_DONE ();
     uint32_t j = 8;
     do {
         #define AR_WALK(J, EJ, EP) { const uint32_t f_ = (EJ) & 0xffffu; if (code < (acc + f_) * r) { e = (EJ); prev = (EP); j = J; break; } acc += f_; }

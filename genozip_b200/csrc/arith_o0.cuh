@@ -69,6 +69,7 @@ static __device__ __noinline__ Ar0 ar0_halve (uint32_t *E, uint8_t *POS, uint32_
     }
     __syncwarp ();
     a.e0 = E[0];
+    AR_READS_DONE ();
     return a;
 }
 
@@ -136,6 +137,7 @@ __device__ __forceinline__ uint32_t ar0_decode_run (uint32_t *E, uint32_t maxs, 
             if (j == 0 && p) prev = E[p - 1];
             rc.code -= acc * r; rc.range = (e & 0xffffu) * r;
             sym = e >> 16;
+            AR_READS_DONE ();
             ar0_update (E, nullptr, maxs, a, p, e, prev, lane);
         }
         ar_out_put (o, sym);
@@ -173,6 +175,7 @@ __device__ __forceinline__ void ar0_encode_sym (uint32_t *E, uint8_t *POS, uint3
     const uint32_t before = rc.low;
     rc.low += acc * r; rc.range = (e & 0xffffu) * r;
     rc.carry += rc.low < before;
+    AR_READS_DONE ();
     ar0_update (E, POS, maxs, a, p, e, prev, lane);
 }
 

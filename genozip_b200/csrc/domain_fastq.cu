@@ -286,6 +286,7 @@ __global__ void __launch_bounds__(256) k_domq_normalize (const DqVb *vbs, const 
         const uint8_t *q = V.txt + V.line_off[li];
         uint8_t *dst = div ? V.divr + V.dv_off[li] : V.E + V.nd_off[li];
         for (uint32_t i = lane; i < len; i += 32) dst[i] = norm[q[i] - FIRST_Q];
+        GZB_WARP_READS_DONE ();                                             // every lane has read line_dom[li]
         if (lane == 0) { V.mplx[V.mx_idx[li]] = (uint8_t)(cdom | (div ? 0x80 : 0)); V.line_dom[li] = (uint8_t)cdom; }   // :436,446; ql->dom becomes cdom (:283-285)
     }
 }

@@ -10,6 +10,18 @@
 #include <stdint.h>
 #include <cuda_runtime.h>
 
+// Warp-synchronous assumptions, made explicit.  Where the lanes of a CONVERGED warp all read a location that one of them
+// (or all, redundantly) stores to a few instructions later, the code relies on the lanes issuing each instruction together:
+// every lane has read before any lane stores.  That holds on the GPU as the code stands, so the marker compiles to nothing
+// there; the SIMT emulator of the CPU test suite (tests/host/simt) runs lanes one after the other between rendez-vous points
+// and turns the marker into one.  It stands after every such group of reads.  (Turning the markers into real __syncwarp()
+// would make the code independent of the assumption at the price of one WARPSYNC each — DESIGN.md §4.1.)
+#if defined(GZB_SIMT_EMULATION)
+  #define GZB_WARP_READS_DONE() __syncwarp ()
+#else
+  #define GZB_WARP_READS_DONE()
+#endif
+
 namespace gzb {
 
 // container flag bits (reference htscodecs/rANS_static4x16.h:38-44, arith_dynamic.h:41-48)

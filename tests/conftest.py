@@ -8,6 +8,12 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on the B200 box)")
+    if config.getoption("--simt"):
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "host", "simt"))
+        import build as simt_build
+        import genozip_b200.lib as lib
+        lib.LIBPATH = simt_build.build()
+        lib._lib = None
     if config.getoption("--dry-gpu"):
         sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
         import mock_gzb
@@ -15,14 +21,17 @@ def pytest_configure(config):
 
 
 def pytest_addoption(parser):
+    parser.addoption("--simt", action="store_true", default=False,
+                     help="run the -m gpu tests against tests/host/_build/libgzb200_simt.so: the product's .cu sources compiled by g++ and "
+                          "executed by the lock-step SIMT emulator (tests/host/simt). Checks kernel LOGIC on a machine without a GPU.")
     parser.addoption("--dry-gpu", action="store_true", default=False,
                      help="run the -m gpu tests' own logic on a machine WITHOUT a GPU: genozip_b200.Engine's marshalling code on top of "
                           "tests/mock_gzb.py (CPU checkers behind the C-ABI's entry points). Checks the tests and the binding, not the kernels.")
 
 
 def pytest_collection_modifyitems(config, items):
-    if config.getoption("--dry-gpu"):
-        skip = pytest.mark.skip(reason="--dry-gpu: needs device memory (covered by tests/test_fastq_path_cpu.py)")
+    if config.getoption("--dry-gpu") or config.getoption("--simt"):
+        skip = pytest.mark.skip(reason="--dry-gpu / --simt: needs torch device memory (covered by tests/test_fastq_path_cpu.py)")
         for it in items:
             if "test_gpu_fastq_path" in it.nodeid:
                 it.add_marker(skip)

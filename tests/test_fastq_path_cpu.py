@@ -1,6 +1,8 @@
 """CPU: the host driver of the FASTQ codec path (genozip_b200/fastq_path.py — descriptor set-up, per-pipeline engines and
 threads, buffer sizing, stream bookkeeping, byte accounting) run end to end against tests/mock_gzb.py, a stand-in for
-libgzb200.so that computes every entry point with the CPU checkers.  Same assertions as the GPU test of this path."""
+libgzb200.so that computes every entry point with the CPU checkers — and against the product's own CUDA sources executed by
+the SIMT emulator (tests/host/simt; "device" memory is host memory there), which takes the whole path, kernels included,
+through the C-ABI on a machine without a GPU.  Same assertions as the GPU test of this path."""
 import numpy as np, pytest, torch
 import orc
 from datagen import line_table
@@ -19,13 +21,18 @@ def _oracle_sections(data, v, n_reads, read_len, codec):
     return pk, streams, comp
 
 
-@pytest.mark.parametrize("n_engines", [1, 3])
-def test_fastq_path_host_driver(n_engines):
+@pytest.mark.parametrize("backend,n_engines", [("mock", 1), ("mock", 3), ("simt", 1), ("simt", 3)])
+def test_fastq_path_host_driver(backend, n_engines):
     from genozip_b200.fastq_path import FastqCodecPath, synth_vblocks, STREAMS
+    if backend == "simt":
+        from simt_lib import simt_engine_class
+        Eng = simt_engine_class()
+    else:
+        Eng = MockEngine
     V, n_reads, read_len = 3, 400, 150
     data = synth_vblocks(V, n_reads, read_len, 7, torch.device("cpu"))
     data["seq"][1][data["seq"][1] == ord("N")] = ord("A")                  # VBlock 1: pure ACGT -> acgt_no_x, no NONREF_X section
-    path = FastqCodecPath(MockEngine(0), V, n_reads, read_len, n_engines=n_engines)
+    path = FastqCodecPath(Eng(0), V, n_reads, read_len, n_engines=n_engines)
     codec = path.assign_codecs(data)
     assert set(codec) == set(STREAMS)
     meta = path.zip_device(data)

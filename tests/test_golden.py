@@ -30,11 +30,13 @@ def test_restatement_reproduces_golden_vectors(codec):
 
 
 @pytest.mark.gpu
-def test_cuda_path_reproduces_golden_vectors():
+def test_cuda_path_reproduces_golden_vectors(pytestconfig):
     from genozip_b200 import Engine
     eng = Engine(0)
     try:
         gold = GOLD[::3]                                     # every third vector: all codecs, kinds and sizes still occur
+        if pytestconfig.getoption("--simt") and os.environ.get("GZB_SIMT_QUICK"):
+            gold = GOLD[::17]                                # (the emulator's quick pass inside the CPU suite)
         items = [(c["codec"], stream(c["kind"], c["n"], c["seed"])) for c in gold]
         for i in range(0, len(items), 256):
             got = eng.compress(items[i:i + 256])
