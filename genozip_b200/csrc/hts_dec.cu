@@ -59,7 +59,10 @@ __device__ int parse_leaf (const uint8_t *in, uint32_t in_len, uint32_t expect, 
     }
     L.body = in;
     L.body_len = (uint32_t)(end - in);
-    if (!L.body_len) L.body_ulen = 0;                                    // :1598-1601
+    if (!L.body_len) {                                                   // :1598-1601: nothing is decoded, tmp1_size = 0 ...
+        if (!(L.pack && L.per_byte == 0)) return -1;                     // ... so the result is empty (or hts_unpack fails, pack.c:242) and the plug-in's
+        L.body_ulen = 0;                                                 //     out_len == uncompressed_len check aborts (codec_htscodecs.c:111,126); only a
+    }                                                                    //     one-symbol PACK map rebuilds the output from no payload at all
     if (L.cat && L.body_ulen > L.body_len) return -1;
     return 0;
 }
@@ -197,6 +200,16 @@ __device__ void rans_o0_decode_lanes (const uint8_t *body, uint32_t body_len, ui
     }
 }
 
+// RansDecInit + "if (R < RANS_BYTE_L) goto err" for the four states (:555-558, :1023-1026)
+__device__ bool rans_states_low (const uint8_t *q)
+{
+    for (int k = 0; k < 4; k++) {
+        const uint32_t x = q[4 * k] | (q[4 * k + 1] << 8) | (q[4 * k + 2] << 16) | ((uint32_t)q[4 * k + 3] << 24);
+        if (x < RANS_L) return true;
+    }
+    return false;
+}
+
 // one CTA per leaf slot
 __global__ void __launch_bounds__(256) k_dec_tables (DecLeaf *leaves, SectionResult *res, uint32_t n_slots, Arena arena)
 {
@@ -216,7 +229,7 @@ __global__ void __launch_bounds__(256) k_dec_tables (DecLeaf *leaves, SectionRes
         __syncthreads ();
         if (!s_ptr[0]) return;                                            // arena overflow: host replays the batch
         uint32_t used = build_dec_o0 (sm, body, end - 8, reinterpret_cast<uint2 *>(s_ptr[0]));
-        if (!used || used + 16 > L.body_len) fail = true;
+        if (!used || used + 16 > L.body_len || rans_states_low (body + used)) fail = true;
         else if (tid == 0) { L.lut = reinterpret_cast<uint2 *>(s_ptr[0]); L.payload_off = used; }
     }
     else {                                                                // ---- order 1 (:883-1019)
@@ -235,7 +248,7 @@ __global__ void __launch_bounds__(256) k_dec_tables (DecLeaf *leaves, SectionRes
                 if (!s_ptr[0] || !s_ptr[1]) return;
                 uint2 *nlut = reinterpret_cast<uint2 *>(s_ptr[0]);
                 uint32_t used = build_dec_o0 (sm, p, p + csz - 8, nlut);
-                if (!used || used + 16 > csz) fail = true;
+                if (!used || used + 16 > csz || rans_states_low (p + used)) fail = true;
                 else {
                     if (warp == 0) rans_o0_decode_lanes (p, csz, used, nlut, s_ptr[1], usz, lane, lane < 4);
                     __syncthreads ();
@@ -301,12 +314,19 @@ __global__ void __launch_bounds__(256) k_dec_tables (DecLeaf *leaves, SectionRes
                     const uint32_t base_e = (uint32_t)L.ctxrank[tid] | ((f - 1) << 8);
                     for (uint32_t y = 0; y < f; y++) srow[st + y] = base_e | (y << 20);
                 }
+                else {
+                    // a context without frequencies (:994-997): a valid stream never enters it.  The reference's decoder would read
+                    // whatever an earlier call left in its table; here a damaged stream finds a defined row (row 0's symbol,
+                    // next context row 0) instead of arena leftovers that could point the next look-up outside the table
+                    uint32_t *srow = lut1 + ((size_t)row << shift);
+                    for (uint32_t y = tid; y < (1u << shift); y += 256) srow[y] = 0;
+                }
                 row++;
                 __syncthreads ();
             }
             if (!fail) {
                 const uint8_t *pay = tab_end ? tab_end : sm.p;
-                if (pay + 16 > end) fail = true;
+                if (pay + 16 > end || rans_states_low (pay)) fail = true;
                 else if (tid == 0) { L.lut1 = lut1; L.nctx = (uint16_t)sm.nctx; L.shift = (uint8_t)shift; L.payload_off = (uint32_t)(pay - body); }
             }
         }
