@@ -184,9 +184,11 @@ HANG = "hang"
 def ref_uncompress(kind, comp, n, timeout=10.0, scramble=False):
     """the reference's decoder on a damaged stream, in a child process (it can crash or spin on such input)
     -> bytes, None where it rejects the stream, HANG where it does not come back or dies"""
-    import select, signal
+    import select, signal, warnings
     rd, wr = os.pipe()
-    pid = os.fork()
+    with warnings.catch_warnings():                                         # (the child only calls into the reference's C code and exits;
+        warnings.simplefilter("ignore", DeprecationWarning)                 #  a child that does not answer is killed and counted)
+        pid = os.fork()
     if pid == 0:
         try:
             os.close(rd)
