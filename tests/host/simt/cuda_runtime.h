@@ -50,7 +50,7 @@ struct Thread { uint3 tid, bid; dim3 bdim, gdim; };
 extern thread_local Thread *cur;                                            // the fibre that is running on this OS thread
 void  launch (dim3 grid, dim3 block, size_t dyn_smem, const std::function<void ()> &body);
 void *dyn_smem ();
-enum Kind { K_SHFL_IDX, K_SHFL_UP, K_SHFL_DOWN, K_SHFL_XOR, K_BALLOT, K_REDUCE_ADD, K_REDUCE_OR, K_REDUCE_AND, K_REDUCE_MIN, K_REDUCE_MAX, K_SYNCWARP };
+enum Kind { K_SHFL_IDX, K_SHFL_UP, K_SHFL_DOWN, K_SHFL_XOR, K_BALLOT, K_REDUCE_ADD, K_REDUCE_OR, K_REDUCE_AND, K_REDUCE_MIN, K_REDUCE_MAX, K_MATCH_ANY, K_SYNCWARP };
 uint64_t collective (const char *file, int line, Kind kind, uint32_t mask, uint64_t v, int arg, int width);
 void     syncthreads (const char *file, int line);
 }
@@ -79,6 +79,7 @@ template <class T> inline T shfl (const char *f, int l, Kind k, uint32_t mask, T
 #define __reduce_and_sync(m, v) ((uint32_t)simt::collective (__FILE__, __LINE__, simt::K_REDUCE_AND, (m), (uint32_t)(v), 0, 32))
 #define __reduce_min_sync(m, v) ((uint32_t)simt::collective (__FILE__, __LINE__, simt::K_REDUCE_MIN, (m), (uint32_t)(v), 0, 32))
 #define __reduce_max_sync(m, v) ((uint32_t)simt::collective (__FILE__, __LINE__, simt::K_REDUCE_MAX, (m), (uint32_t)(v), 0, 32))
+#define __match_any_sync(m, v) ((uint32_t)simt::collective (__FILE__, __LINE__, simt::K_MATCH_ANY, (m), simt::to_bits (v), 0, 32))
 #define __syncwarp(...)       ((void)simt::collective (__FILE__, __LINE__, simt::K_SYNCWARP, simt::mask_or_full (__VA_ARGS__), 0, 0, 32))
 #define __syncthreads()       simt::syncthreads (__FILE__, __LINE__)
 namespace simt { inline uint32_t mask_or_full () { return 0xffffffffu; } inline uint32_t mask_or_full (uint32_t m) { return m; } }

@@ -20,6 +20,7 @@ __global__ void k_collectives (uint32_t *out, int *bad)
     CHECK (__all_sync (0xffffffffu, lane < 32) && !__all_sync (0xffffffffu, lane < 31));
     CHECK (__reduce_add_sync (0xffffffffu, (uint32_t)lane) == 496u);
     CHECK (__reduce_or_sync (0xffffffffu, 1u << (lane & 7)) == 0xffu);
+    { uint32_t mm = 0; for (int l = 0; l < 32; l++) if (l % 5 == lane % 5) mm |= 1u << l; CHECK (__match_any_sync (0xffffffffu, (uint32_t)(lane % 5)) == mm); }
     float f = 0.5f * lane; CHECK (__shfl_sync (0xffffffffu, f, 31) == 15.5f);
     uint64_t w = 0x100000000ull * lane; CHECK (__shfl_sync (0xffffffffu, w, 2) == 0x200000000ull);
     // disjoint sub-masks pending side by side, reached in different orders

@@ -140,6 +140,7 @@ static uint64_t lane_result (Slot &w, int lane)
             return w.in[src];
         }
         case K_BALLOT: { uint32_t r = 0; for (int l = 0; l < 32; l++) if ((m >> l & 1) && w.in[l]) r |= 1u << l; return r; }
+        case K_MATCH_ANY: { uint32_t r = 0; for (int l = 0; l < 32; l++) if ((m >> l & 1) && (w.arrived >> l & 1) && w.in[l] == w.in[lane]) r |= 1u << l; return r; }
         case K_REDUCE_ADD: { uint32_t r = 0; for (int l = 0; l < 32; l++) if (m >> l & 1) r += (uint32_t)w.in[l]; return r; }
         case K_REDUCE_OR:  { uint32_t r = 0; for (int l = 0; l < 32; l++) if (m >> l & 1) r |= (uint32_t)w.in[l]; return r; }
         case K_REDUCE_AND: { uint32_t r = ~0u; for (int l = 0; l < 32; l++) if (m >> l & 1) r &= (uint32_t)w.in[l]; return r; }
