@@ -90,6 +90,7 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
     gen = os.path.join(OUTDIR, "gen", "genozip_b200", "csrc")              # (the sources include "../../include/gzb200.h")
+    shutil.rmtree(os.path.join(OUTDIR, "gen"), ignore_errors=True)          # (no stale sources of another checkout)
     os.makedirs(gen, exist_ok=True)
     os.makedirs(os.path.join(OUTDIR, "gen", "include"), exist_ok=True)
     shutil.copy(os.path.join(ROOT, "include", "gzb200.h"), os.path.join(OUTDIR, "gen", "include", "gzb200.h"))
