@@ -119,9 +119,15 @@ def o1_table_has_empty_context(b):
                     return True
                 p += cl
             return False
-        if flags & 0x80 or not flags & 1:
+        if not flags & 1:
             return False
         if not flags & 0x10:
+            while b[p] & 0x80:
+                p += 1
+            p += 1
+        if flags & 0x80:                                                    # PACK meta: symbol count, map, packed length (pack.c:168-201)
+            ns = b[p] or 256
+            p += 1 + (ns if ns <= 16 else 0)
             while b[p] & 0x80:
                 p += 1
             p += 1
