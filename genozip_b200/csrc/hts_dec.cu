@@ -33,7 +33,6 @@ __device__ int parse_leaf (const uint8_t *in, uint32_t in_len, uint32_t expect, 
     if (!in_len) return -1;
     uint32_t flags = *in++;
     if (flags & F_STRIPE) return -1;                                     // nested STRIPE is never produced
-    if (coder == CODER_ARITH && (flags & F_EXT)) return -1;
     if (coder == CODER_RANS && (flags & F_RLE)) return -1;               // rANS RLE is never requested by genozip
     L.order = (uint8_t)(flags & (coder == CODER_ARITH ? 3u : 1u));
     L.cat = (flags & F_CAT) != 0; L.rle = (flags & F_RLE) != 0; L.pack = (flags & F_PACK) != 0;
@@ -59,6 +58,8 @@ __device__ int parse_leaf (const uint8_t *in, uint32_t in_len, uint32_t expect, 
     }
     L.body = in;
     L.body_len = (uint32_t)(end - in);
+    if (coder == CODER_ARITH && (flags & F_EXT) && L.body_len && !L.cat) return -1;   // bzip2 payload: never written by genozip, refused by the reference's
+                                                                         // build too (arith_dynamic.c:1050-1058); without a payload (:1037) or under CAT (:1043) the flag is never looked at
     if (!L.body_len) {                                                   // :1598-1601: nothing is decoded, tmp1_size = 0 ...
         if (!(L.pack && L.per_byte == 0)) return -1;                     // ... so the result is empty (or hts_unpack fails, pack.c:242) and the plug-in's
         L.body_ulen = 0;                                                 //     out_len == uncompressed_len check aborts (codec_htscodecs.c:111,126); only a

@@ -59,7 +59,11 @@ def test_container_without_payload_is_refused(eng):
             assert _rejects(eng, codec, [flags, n], n), (codec, flags, n)
             with pytest.raises(AssertionError):
                 orc.uncompress("ref", "rans" if codec.startswith("RAN") else "arith", np.array([flags, n], np.uint8), n)
-    # ... but a one-symbol PACK map needs no payload: a constant stream decodes from its meta data alone
+    # ... but a one-symbol PACK map needs no payload: a constant stream decodes from its meta data alone — whatever the other flags say
+    for flags in (0x80 | 0x20 | 0x04, 0x80 | 0x40 | 0x10 | 0x04 | 0x01):
+        body = [flags] + ([] if flags & 0x10 else [4]) + [1, 232, 0]
+        assert list(orc.uncompress("ref", "arith", np.array(body, np.uint8), 4)) == [232] * 4
+        assert list(eng.uncompress([("ARTb", np.array(body, np.uint8), 4)])[0]) == [232] * 4
     x = np.full(1000, 65, np.uint8)
     for codec in ("RANb", "ARTb"):
         comp = orc.compress("ref", "rans" if codec.startswith("RAN") else "arith", x, orc.ORDER[codec])

@@ -170,6 +170,8 @@ def o1_table_has_empty_context(b):
 
 def known_stricter(codec, b):
     """damaged streams that the reference decodes (to garbage) and the kernels refuse — by design"""
+    if codec.startswith("RAN") and b.size > 1 and (int(b[0]) & 0x48) == 0x40:
+        return "rANS container with the RLE flag: never written by genozip (codec_htscodecs.c:17-20), not implemented"
     if codec.startswith("RAN") and b.size > 4:
         flags = int(b[0])
         i = 1
