@@ -231,12 +231,12 @@ def ref_uncompress(kind, comp, n, timeout=10.0, scramble=False):
     return None if buf[:1] == b"R" else np.frombuffer(buf[1:], np.uint8)
 
 
-def run(seconds, seed, do_corrupt, max_n, verbose=False, stricter=None):
+def run(seconds, seed, do_corrupt, max_n, verbose=False, stricter=None, max_streams=None):
     from genozip_b200 import GzbError
     eng = simt_engine_class()(0)
     r = np.random.default_rng(seed)
     t0, n_cases, n_bytes, n_corrupt, n_rejected = time.time(), 0, 0, 0, 0
-    while time.time() - t0 < seconds:
+    while time.time() - t0 < seconds and (max_streams is None or n_cases < max_streams):
         batch = []
         for _ in range(int(r.integers(1, 24))):
             x, what = random_stream(r, max_n)

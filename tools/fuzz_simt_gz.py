@@ -139,13 +139,13 @@ def fuzz_longr(r, eng):
 FUZZERS = {"domq": fuzz_domq, "acgt": fuzz_acgt, "pbwt": fuzz_pbwt, "longr": fuzz_longr}
 
 
-def run(seconds, seed, which=None, verbose=False):
+def run(seconds, seed, which=None, verbose=False, max_cases=None):
     eng = simt_engine_class()(0)
     r = np.random.default_rng(seed)
     names = list(which or FUZZERS)
     t0, count = time.time(), {k: 0 for k in names}
     i = 0
-    while time.time() - t0 < seconds:
+    while time.time() - t0 < seconds and (max_cases is None or i < max_cases):
         name = names[i % len(names)]; i += 1
         state = r.bit_generator.state
         try:
