@@ -68,6 +68,7 @@ struct Block {
     uint32_t n_done = 0, n_at_barrier = 0, barrier_gen = 0;
     bool progress = false;
     const char *bar_file = nullptr; int bar_line = 0;                        // where the pending barrier's first thread waits
+    uint32_t sched_rand = 12345;
     std::vector<uint8_t> dyn;
 };
 
@@ -208,6 +209,8 @@ void syncthreads (const char *file, int line)
 
 void *dyn_smem () { return blk->dyn.data (); }
 
+static const int lane_order = [] { const char *v = getenv ("SIMT_LANE_ORDER"); return !v ? 0 : !strcmp (v, "desc") ? 1 : !strcmp (v, "random") ? 2 : 0; } ();
+
 static void run_block (Block &b, dim3 grid, dim3 block, uint3 bid)
 {
     const uint32_t n = block.x * block.y * block.z;
@@ -237,7 +240,12 @@ static void run_block (Block &b, dim3 grid, dim3 block, uint3 bid)
             bool again = true;
             while (again) {
                 again = false;
-                for (uint32_t l = 0; l < 32 && wi * 32 + l < n; l++) {
+                const uint32_t rot = (b.sched_rand = b.sched_rand * 1103515245u + 12345u) >> 16;
+                for (uint32_t k = 0; k < 32; k++) {
+                    // SIMT_LANE_ORDER=desc / random: lanes are not taken in ascending order.  Code that is correct only because lane 0
+                    // (or lane 31) happens to run first between two rendez-vous points shows up under the other orders.
+                    const uint32_t l = lane_order == 1 ? 31 - k : lane_order == 2 ? (k * 13 + rot) % 32 : k;   // (13 is odd: a permutation)
+                    if (wi * 32 + l >= n) continue;
                     Fibre &f = b.f[wi * 32 + l];
                     if (f.state != RUN) continue;
                     b.running = &f;

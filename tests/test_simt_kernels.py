@@ -15,6 +15,22 @@ QUICK = ("edge_sizes or acgt or domq_ragged or domq_edges or domq_fastq_batch or
          "or golden or hot_streams and not 450001 and not 3000000")
 
 
+import pytest
+
+
+@pytest.mark.parametrize("order", ["desc", "random"])
+def test_kernels_do_not_depend_on_the_lane_order(order):
+    """between two rendez-vous points the emulator runs the lanes of a warp one after the other; results must not depend on which
+    lane goes first (SIMT_LANE_ORDER) — code that only works because lane 0 happens to run first would rely on more than the
+    markers GZB_WARP_READS_DONE / AR_READS_DONE state"""
+    env = dict(os.environ, GZB_SIMT_QUICK="1", SIMT_LANE_ORDER=order)
+    k = "(edge_sizes and (RANB or ARTB or ARTw)) or acgt or domq_ragged or domq_edges or pbwt or longr or share_warp"
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests"), "-m", "gpu", "--simt", "-k", k, "-x", "-q", "-p", "no:cacheprovider"],
+                       cwd=ROOT, capture_output=True, text=True, timeout=1500, env=env)
+    tail = (r.stdout + r.stderr)[-4000:]
+    assert r.returncode == 0 and " passed" in tail and "failed" not in tail, tail
+
+
 def test_kernels_on_the_simt_emulator():
     env = dict(os.environ, GZB_SIMT_QUICK="1")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests"), "-m", "gpu", "--simt", "-k", QUICK, "-x", "-q", "-p", "no:cacheprovider"],
