@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIBPATH = os.path.join(HERE, "libgzb200.so")
+# GZB200_LIB: another BUILD of this same library (an A/B run of a kernel variant, tools/ab_build.py) — never a different implementation
+LIBPATH = os.environ.get("GZB200_LIB") or os.path.join(HERE, "libgzb200.so")
 
 CODEC = {"NONE": 1, "RANB": 6, "RANW": 7, "RANb": 8, "RANw": 9, "ACGT": 10, "XCGT": 11, "DOMQ": 13, "PBWT": 15,
          "ARTB": 16, "ARTW": 17, "ARTb": 18, "ARTw": 19, "LONGR": 26}
