@@ -68,6 +68,15 @@ extern "C" uint32_t gzb_est_size (int codec, uint64_t n)
 }
 
 // ------------------------------------------------------------------------------------------------ engine
+extern "C" int gzb_build_is_emulation (void)
+{
+#ifdef GZB_SIMT_EMULATION
+    return 1;
+#else
+    return 0;
+#endif
+}
+
 extern "C" int gzb_device_count (void)
 {
     int n = 0;

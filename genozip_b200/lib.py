@@ -60,6 +60,7 @@ class LongrVb(C.Structure):         # gzb_longr_vb
 
 
 _lib = None
+_TESTS_MAY_LOAD_EMULATION = False      # set by tests/simt_lib.py and tests/conftest.py (--simt) only
 
 
 def load():
@@ -70,6 +71,9 @@ def load():
     if not os.path.exists(LIBPATH):
         raise GzbError(f"{LIBPATH} not built: run `python genozip_b200/build.py` (nvcc, sm_100a). No CPU fallback exists.")
     L = C.CDLL(LIBPATH)
+    L.gzb_build_is_emulation.restype = C.c_int
+    if L.gzb_build_is_emulation() and not _TESTS_MAY_LOAD_EMULATION:
+        raise GzbError(f"{LIBPATH} is the test suite's host build of the kernels (tests/host/simt), not the CUDA library: the product never loads it.")
     L.gzb_device_count.restype = C.c_int
     L.gzb_engine_create.restype = C.c_int
     L.gzb_engine_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]

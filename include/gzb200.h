@@ -58,6 +58,8 @@ typedef struct gzb_engine gzb_engine;   /* one per (host thread, GPU): a CUDA st
 
 /* ---------------------------------------------------------------- lifecycle (SURVEY §8b "lifecycle") */
 int   gzb_device_count (void);                                    /* number of visible CUDA devices, 0 if none */
+int   gzb_build_is_emulation (void);                              /* 0 for the product (nvcc, sm_100a); 1 for the test suite's host build of the same
+                                                                     sources (tests/host/simt), which no binding may load outside the tests */
 int   gzb_engine_create (int device, gzb_engine **out);           /* GZB_E_NOCUDA if no usable device */
 void  gzb_engine_destroy (gzb_engine *e);
 const char *gzb_last_error (gzb_engine *e);                       /* e may be NULL: creation errors */

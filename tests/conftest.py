@@ -14,6 +14,7 @@ def pytest_configure(config):
         import genozip_b200.lib as lib
         lib.LIBPATH = simt_build.build()
         lib._lib = None
+        lib._TESTS_MAY_LOAD_EMULATION = True
     if config.getoption("--dry-gpu"):
         sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
         import mock_gzb

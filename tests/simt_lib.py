@@ -17,10 +17,11 @@ def simt_lib():
         import genozip_b200.lib as lib
         saved = (lib.LIBPATH, lib._lib)
         try:                                                               # lib.load() sets the argtypes; borrow it for the other path
-            lib.LIBPATH, lib._lib = simt_build.build(), None
+            lib.LIBPATH, lib._lib, lib._TESTS_MAY_LOAD_EMULATION = simt_build.build(), None, True
             _L = lib.load()
         finally:
             lib.LIBPATH, lib._lib = saved
+            lib._TESTS_MAY_LOAD_EMULATION = False
     return _L
 
 
