@@ -45,7 +45,7 @@ namespace gzb {
 // the GPU this holds as the code stands and the marker below compiles to nothing; the SIMT emulator of the CPU test suite
 // (tests/host/simt) runs lanes one after the other between rendez-vous points and turns the marker into one.  It stands
 // after every group of model reads that a store may follow.
-#if defined(GZB_SIMT_EMULATION)
+#if defined(GZB_SIMT_EMULATION) || defined(GZB_READS_DONE_SYNCWARP)
   #define AR_READS_DONE() __syncwarp ()
 #else
   #define AR_READS_DONE()

@@ -16,7 +16,7 @@
 // there; the SIMT emulator of the CPU test suite (tests/host/simt) runs lanes one after the other between rendez-vous points
 // and turns the marker into one.  It stands after every such group of reads.  (Turning the markers into real __syncwarp()
 // would make the code independent of the assumption at the price of one WARPSYNC each — DESIGN.md §4.1.)
-#if defined(GZB_SIMT_EMULATION)
+#if defined(GZB_SIMT_EMULATION) || defined(GZB_READS_DONE_SYNCWARP)   // (the second: an nvcc build with real barriers, for the A/B run)
   #define GZB_WARP_READS_DONE() __syncwarp ()
 #else
   #define GZB_WARP_READS_DONE()
