@@ -41,14 +41,14 @@
 namespace gzb {
 
 // All 32 lanes of the warp run the chain redundantly and store identical values to the models.  A lane must therefore not
-// store to a model before every lane has read it.  The lanes of a converged warp issue each instruction together, so on
-// the GPU this holds as the code stands and the marker below compiles to nothing; the SIMT emulator of the CPU test suite
-// (tests/host/simt) runs lanes one after the other between rendez-vous points and turns the marker into one.  It stands
-// after every group of model reads that a store may follow.
-#if defined(GZB_SIMT_EMULATION) || defined(GZB_READS_DONE_SYNCWARP)
-  #define AR_READS_DONE() __syncwarp ()
-#else
+// store to a model before every lane has read it: AR_READS_DONE () — a __syncwarp () — stands after every group of model
+// reads that a store may follow.  (Round 1 relied on the lanes of a converged warp issuing together and compiled the marker
+// to nothing; measured on B200 the real barrier costs 0.3 % of the step — gpurun_out/ab_main*.json of round 2 — so the code
+// no longer depends on more than CUDA guarantees.  -DGZB_READS_DONE_LOCKSTEP restores the old build for an A/B run.)
+#if defined(GZB_READS_DONE_LOCKSTEP) && !defined(GZB_SIMT_EMULATION)
   #define AR_READS_DONE()
+#else
+  #define AR_READS_DONE() __syncwarp ()
 #endif
 
 #define AR_MAXF  65519u          // MAX_FREQ = (1<<16)-17 (c_simple_model.h:70)

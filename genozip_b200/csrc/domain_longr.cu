@@ -3,12 +3,28 @@
 // Reference functions replaced (relative to /root/reference/src): codec_longr_compress before its sub-codec
 // (codec_longr.c:161-247: codec_longr_calc_channels :138-159, counting sort :193-230, lens :232-240),
 // codec_longr_reconstruct for all reads of a VBlock (:270-373), the state machine codec_longr_update_state /
-// _alg_init / _alg_init_read (codec_longr_alg.c:108-159).
+// _alg_init / _alg_init_read (codec_longr_alg.c:108-159), codec_longr_segconf_calculate_bins (codec_longr.c:66-136).
 //
-// The channel computation is serial across the whole VBlock (state tables indexed by a 21-bit context are carried
-// from read to read): one thread walks one VBlock, many VBlocks run concurrently.  The thread records, per
-// base, its channel and its rank inside the channel, which turns the reference's second (also serial) pass — the
-// stable counting sort of the qualities by channel — into a fully parallel scatter.
+// What the algorithm is, seen from a GPU.  Every base is one EVENT: a read-modify-write of two tables at a context that the
+// INPUT alone determines — u = (last six bases : 12 | capped interlaced difference of the two previous qualities : 4 |
+// bin of the previous quality : 5), and Q = the upper 9 bits of u:
+//      (avg, err) = st[u];  t = tot[Q]                      the base's channel = (u >> 12) | bin(avg) << 9 | class(err, t) << 14
+//      st[u] <- update (avg, err, q);  tot[Q] <- update (t, |q - avg|)
+// (the three updates codec_longr_alg_init_read makes at the start of a read are events without a channel).  The tables are
+// carried from read to read through the VBlock, so a VBlock is one serial stream of events; VBlocks are independent.
+//
+//   encode  k_longr_channels: ONE WARP PER VBLOCK takes 32 consecutive events at a time.  The contexts of all 32 are known up
+//           front, so their table entries are fetched together; events of a tile that share a context (or a Q) are chained in
+//           order inside the warp (__match_any_sync groups, one round per member), everything else is parallel.  The loads of the
+//           next tile are issued as soon as this tile's stores are, and overlap the rest of its work.  st is one 32-bit word per
+//           context (avg | err << 16), tot lives in shared memory.  The stable counting sort by channel (:193-230) is
+//           k_longr_prefix + k_longr_place (one warp per VBlock, ranks inside a tile from __match_any_sync, one atomic per
+//           channel and tile, consumed one tile later).
+//   decode  k_longr_decode: the next quality is only known once the previous base's channel is, so a VBlock decodes one base
+//           at a time — lane 0 of one warp per VBlock.  The chain per base is two dependent memory round trips (st[u], then
+//           the channel's cursor) instead of the reference's four; the cursor of a channel is one 64-bit word that carries the
+//           index AND the next four qualities of the channel (refilled off the critical path).  Throughput comes from the
+//           number of VBlocks in flight.
 #include <cstring>
 #include <vector>
 #include <string>
@@ -23,14 +39,18 @@ using namespace gzb;
 namespace {
 
 constexpr uint32_t NCTX = 1u << 21, NCHAN = 1u << 16, NQ9 = 1u << 9;
+constexpr uint32_t FULL = 0xffffffffu;
 
 struct LrVb {
     const uint8_t *txt; const uint64_t *seq_off, *qual_off; const uint32_t *len; const uint8_t *is_rev;
+    const uint32_t *qlen;                // encode: quality length where it differs from len (a line without quality: ' '), or nullptr
     uint32_t n_lines;
-    uint16_t *avg_sums, *err_sums;       // [1<<21] each (codec_longr_alg.c:99-100)
-    uint32_t *chan_num;                  // [65536] bases per channel, then reused as next_of_chan
-    uint16_t *base_chan; uint32_t *base_rank; uint8_t *base_q;   // per base, in processing order
-    uint8_t  *values; uint32_t *lens_be; uint8_t *qual_out;
+    uint32_t *st;                        // [1<<21] avg_sums | err_sums << 16 (codec_longr_alg.c:99-100)
+    uint32_t *chan_num;                  // [65536] bases per channel, then the exclusive prefix next_of_chan
+    unsigned long long *cur;             // decode: [65536] cursor of each channel: next index << 32 | up to four next values
+    uint16_t *base_chan;                 // encode: channel of each base, in processing order
+    uint8_t  *values; uint32_t *lens_be; uint8_t *qual_out; uint8_t *missing;
+    uint32_t *err;                       // != 0: damaged LENS / VALUES
     uint64_t  total;
     uint8_t   v2b[256];
 };
@@ -54,144 +74,296 @@ __device__ __forceinline__ uint32_t acgt_code_comp (uint32_t c)             // _
     }
 }
 
-// channel word (codec_longr_alg.c:65-95), LSB first: B:12 | difq:4 | qbin:5 | avg:5 | err_c:2
-struct LrState { uint16_t *avg, *err; uint32_t *tot; const uint8_t *v2b; uint32_t chan; };
-
-__device__ __forceinline__ void lr_update (LrState &s, uint32_t b, int32_t q1, int32_t q2)   // codec_longr_update_state :108-136
+// the three table updates of one event (codec_longr_update_state :112-118); returns the new st word
+__device__ __forceinline__ uint32_t lr_st_update (uint32_t st, int32_t q, uint32_t &abs_err)
 {
-    uint32_t c = s.chan;
-    const uint32_t nc = c & 0x1fffffu, qn = (c >> 12) & 0x1ffu;
-    const int32_t err = q1 - (((int32_t)s.avg[nc] + 8) >> 4);
-    s.avg[nc] = (uint16_t)(s.avg[nc] + err);
-    const int32_t ae = err < 0 ? -err : err;
-    s.err[nc] = (uint16_t)((int32_t)s.err[nc] + ae - (((int32_t)s.err[nc] + 8) >> 4));
-    s.tot[qn] = s.tot[qn] + (uint32_t)ae - ((s.tot[qn] + 8u) >> 4);
-    const uint32_t B = (((c & 0xfffu) << 2) | b) & 0xfffu;
+    const int32_t avg = (int32_t)(st & 0xffffu), er = (int32_t)(st >> 16);
+    const int32_t d = q - ((avg + 8) >> 4);
+    abs_err = (uint32_t)(d < 0 ? -d : d);
+    return ((uint32_t)(avg + d) & 0xffffu) | (((uint32_t)(er + (int32_t)abs_err - ((er + 8) >> 4)) & 0xffffu) << 16);
+}
+__device__ __forceinline__ uint32_t lr_tot_update (uint32_t t, uint32_t abs_err) { return t + abs_err - ((t + 8u) >> 4); }
+// avg : 5 | err_c : 2 of the channel (:128-135), from the table words as they are BEFORE this event's update
+__device__ __forceinline__ uint32_t lr_chan_hi (uint32_t st, uint32_t t, const uint8_t *v2b)
+{
+    const uint32_t avg = v2b[(((st & 0xffffu) + 8u) >> 4) & 0xffu] & 0x1fu, er = st >> 16;
+    const uint32_t ec = er < (t >> 1) ? 0u : er < t ? 1u : er < (t << 1) ? 2u : 3u;
+    return avg | (ec << 5);
+}
+__device__ __forceinline__ uint32_t lr_difq (int32_t q1, int32_t q2)         // INTERLACE (context.h:100), capped (:122)
+{
     const int32_t d = q1 - q2;
-    const uint32_t il = d < 0 ? (((uint32_t)(-d)) << 1) - 1 : ((uint32_t)d) << 1;     // INTERLACE (context.h:100)
-    const uint32_t difq = il < 15 ? il : 15;
-    const uint32_t qbin = s.v2b[q1 & 0xff] & 0x1fu;
-    c = (c & ~0x1fffffu) | B | (difq << 12) | (qbin << 16);
-    const uint32_t nc2 = c & 0x1fffffu, qn2 = (c >> 12) & 0x1ffu;
-    const uint32_t avg = s.v2b[((((int32_t)s.avg[nc2]) + 8) >> 4) & 0xff] & 0x1fu;
-    const uint32_t tot = s.tot[qn2];                                        // TOTAL_ERR_SHIFT - AVG_SHIFT = 0
-    const uint32_t ae2 = s.err[nc2];
-    const uint32_t ec = ae2 < (tot >> 1) ? 0 : ae2 < tot ? 1 : ae2 < (tot << 1) ? 2 : 3;
-    s.chan = (c & ~(0x7fu << 21)) | (avg << 21) | (ec << 26);
+    const uint32_t il = d < 0 ? (((uint32_t)(-d)) << 1) - 1 : ((uint32_t)d) << 1;
+    return il < 15 ? il : 15;
 }
 
-__device__ __forceinline__ void lr_init_read (LrState &s, const uint8_t *seq, uint32_t len, bool rev)   // codec_longr_alg_init_read :148-159
-{
-    s.chan = 0;
-    for (int i = 0; i < 3; i++)
-        lr_update (s, rev ? acgt_code_comp ((int)len - 1 - i >= 0 ? seq[len - 1 - i] : 'T') : acgt_code (i < (int)len ? seq[i] : 'A'), 0, 0);
-}
-
-// state tables: chan_avgs_sums[n] = qbin(n) << AVG_SHIFT (:138-146); err sums 0; chan counters 0
+// state tables: chan_avgs_sums[n] = qbin(n) << AVG_SHIFT (:138-146); err sums 0; channel counters 0
 __global__ void k_longr_init (const LrVb *vbs)
 {
     const LrVb &V = vbs[blockIdx.y];
-    for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < NCTX; n += gridDim.x * blockDim.x) {
-        V.avg_sums[n] = (uint16_t)(((n >> 16) & 0x1f) << 4);
-        V.err_sums[n] = 0;
-        if (n < NCHAN) V.chan_num[n] = 0;
+    uint4 *st4 = reinterpret_cast<uint4 *>(V.st);
+    for (uint32_t n4 = blockIdx.x * blockDim.x + threadIdx.x; n4 < NCTX / 4; n4 += gridDim.x * blockDim.x) {
+        const uint32_t v = (((n4 * 4) >> 16) & 0x1f) << 4;                  // (the bin is the same for four neighbours)
+        st4[n4] = make_uint4 (v, v, v, v);
+        if (n4 < NCHAN / 4) reinterpret_cast<uint4 *>(V.chan_num)[n4] = make_uint4 (0, 0, 0, 0);
     }
 }
 
-// one VBlock per CTA; thread 0 walks the reads (codec_longr_calc_channels :138-159 for every line, :185-203)
-__global__ void k_longr_channels (const LrVb *vbs)
+// value of lane (lane - d) of `cur`, continued into the previous tile's `prev`
+__device__ __forceinline__ uint32_t lr_up (uint32_t cur, uint32_t prev, int d, int lane)
+{
+    const uint32_t a = __shfl_up_sync (FULL, cur, d), b = __shfl_sync (FULL, prev, (lane - d) & 31);
+    return lane >= d ? a : b;
+}
+
+struct LrTileIn { uint32_t P, Qv; };     // per lane: base code of processing position e-1, quality of base e-3 (0 where there is none)
+
+__device__ __forceinline__ LrTileIn lr_tile_load (const uint8_t *seq, const uint8_t *q, uint32_t L, uint32_t Lq, bool rev, uint32_t e, const uint8_t *lut)
+{
+    LrTileIn t; t.P = 0; t.Qv = 0;
+    if (e >= 1 && e - 1 < L) t.P = lut[(rev ? 256 : 0) + seq[rev ? L - e : e - 1]];
+    if (e >= 3 && e - 3 < Lq) t.Qv = (uint8_t)(q[rev ? Lq + 2 - e : e - 3] - '!');
+    return t;
+}
+
+// encode, first pass: the channel of every base and the number of bases per channel (codec_longr_calc_channels :138-159 for
+// every line, :185-203).  One warp per VBlock.
+__global__ void __launch_bounds__(32) k_longr_channels (const LrVb *vbs)
 {
     const LrVb &V = vbs[blockIdx.x];
     __shared__ uint32_t tot[NQ9];
-    __shared__ uint8_t v2b[256];
-    for (int i = threadIdx.x; i < (int)NQ9; i += blockDim.x) tot[i] = 0x10101010u;   // memset (.., 1<<4, ..) on uint32 (:142)
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) v2b[i] = V.v2b[i];
-    __syncthreads ();
-    if (threadIdx.x) return;
-    LrState s; s.avg = V.avg_sums; s.err = V.err_sums; s.tot = tot; s.v2b = v2b; s.chan = 0;
+    __shared__ uint8_t v2b[256], lut[512];
+    const int lane = threadIdx.x;
+    const uint32_t lt = (1u << lane) - 1;
+    for (int i = lane; i < (int)NQ9; i += 32) tot[i] = 0x10101010u;          // memset (.., 1<<4, ..) on uint32 (:142)
+    for (int i = lane; i < 256; i += 32) { v2b[i] = V.v2b[i]; lut[i] = (uint8_t)acgt_code (i); lut[256 + i] = (uint8_t)acgt_code_comp (i); }
+    __syncwarp ();
+    uint32_t *st = V.st;
     uint64_t nb = 0;
     for (uint32_t li = 0; li < V.n_lines; li++) {
-        const uint32_t L = V.len[li];
-        if (!L) continue;
+        const uint32_t L = V.len[li], Lq = V.qlen ? V.qlen[li] : L;
+        if (!Lq) continue;                                                  // (:188)
         const uint8_t *seq = V.txt + V.seq_off[li], *q = V.txt + V.qual_off[li];
         const bool rev = V.is_rev ? V.is_rev[li] : false;
-        lr_init_read (s, seq, L, rev);
-        int32_t prev = 0;
-        for (uint32_t k = 0; k < L; k++, nb++) {
-            const uint32_t i = rev ? L - 1 - k : k;
-            const uint32_t ch = (s.chan >> 12) & 0xffffu;
-            V.base_chan[nb] = (uint16_t)ch;
-            V.base_rank[nb] = V.chan_num[ch]++;
-            const uint32_t b = rev ? acgt_code_comp (i >= 3 ? seq[i - 3] : 'T') : acgt_code (i + 3 < L ? seq[i + 3] : 'A');
-            const int32_t qq = (uint8_t)(q[i] - '!');
-            V.base_q[nb] = (uint8_t)qq;
-            lr_update (s, b, qq, prev);
-            prev = qq;
+        const uint32_t nE = Lq + 3;                                         // three events without a base, then one per quality
+        uint32_t Pprev = 0, W1prev = 0, Qprev = 0;
+        LrTileIn in = lr_tile_load (seq, q, L, Lq, rev, lane, lut);
+        // context and table word of the first tile
+        uint32_t u, val; int32_t q1;
+        {
+            const uint32_t W1 = in.P | (lr_up (in.P, Pprev, 1, lane) << 2), W2 = W1 | (lr_up (W1, W1prev, 2, lane) << 4), B = (W2 | (lr_up (W1, W1prev, 4, lane) << 8)) & 0xfffu;
+            const uint32_t qm1 = lr_up (in.Qv, Qprev, 1, lane), qm2 = lr_up (in.Qv, Qprev, 2, lane);
+            u = B | (lr_difq ((int32_t)qm1, (int32_t)qm2) << 12) | (lane == 0 ? 0u : (uint32_t)(v2b[qm1] & 0x1f) << 16);
+            q1 = (int32_t)in.Qv; Pprev = in.P; W1prev = W1; Qprev = in.Qv;
+            val = lane < nE ? st[u] : 0;
         }
+        for (uint32_t e0 = 0; e0 < nE; e0 += 32) {
+            const uint32_t e = e0 + lane;
+            const bool active = e < nE;
+            const bool more = e0 + 32 < nE;
+            LrTileIn nx; nx.P = 0; nx.Qv = 0;
+            if (more) nx = lr_tile_load (seq, q, L, Lq, rev, e + 32, lut);      // (in flight while this tile's entries arrive)
+
+            // ---- st: events of the tile that share a context are chained in order
+            const uint32_t g = __match_any_sync (FULL, active ? u : (0x80000000u | lane));
+            const uint32_t rank = __popc (g & lt);
+            const int prevlane = rank ? 31 - __clz ((int)(g & lt)) : lane;
+            uint32_t ae, nv = lr_st_update (val, q1, ae);
+            const uint32_t maxrank = __reduce_max_sync (FULL, rank);
+            for (uint32_t r = 1; r <= maxrank; r++) {
+                const uint32_t pv = __shfl_sync (FULL, nv, prevlane);
+                if (rank == r) { val = pv; nv = lr_st_update (val, q1, ae); }
+            }
+            if (active && !(g >> lane >> 1)) st[u] = nv;                    // the last event of a context stores
+            __syncwarp ();                                                  // (the next tile's loads, by other lanes, see these stores)
+
+            // ---- the next tile's contexts and loads
+            uint32_t u2 = 0, val2 = 0; int32_t q1n = 0;
+            if (more) {
+                const uint32_t W1 = nx.P | (lr_up (nx.P, Pprev, 1, lane) << 2), W2 = W1 | (lr_up (W1, W1prev, 2, lane) << 4), B = (W2 | (lr_up (W1, W1prev, 4, lane) << 8)) & 0xfffu;
+                const uint32_t qm1 = lr_up (nx.Qv, Qprev, 1, lane), qm2 = lr_up (nx.Qv, Qprev, 2, lane);
+                u2 = B | (lr_difq ((int32_t)qm1, (int32_t)qm2) << 12) | ((uint32_t)(v2b[qm1] & 0x1f) << 16);
+                q1n = (int32_t)nx.Qv; Pprev = nx.P; W1prev = W1; Qprev = nx.Qv;
+                if (e + 32 < nE) val2 = st[u2];
+            }
+
+            // ---- tot: events that share a Q are chained in order
+            const uint32_t Qn = (u >> 12) & 0x1ffu;
+            const uint32_t gq = __match_any_sync (FULL, active ? Qn : (0x8000u | lane));
+            const uint32_t qrank = __popc (gq & lt), maxq = __reduce_max_sync (FULL, qrank);
+            uint32_t t_pre = 0;
+            for (uint32_t r = 0; r <= maxq; r++) {
+                if (active && qrank == r) { t_pre = tot[Qn]; tot[Qn] = lr_tot_update (t_pre, ae); }
+                __syncwarp ();
+            }
+
+            // ---- channels of the tile's bases, bases per channel
+            const uint32_t ch = ((u >> 12) & 0x1ffu) | (lr_chan_hi (val, t_pre, v2b) << 9);
+            const bool isbase = active && e >= 3;
+            const uint32_t gc = __match_any_sync (FULL, isbase ? ch : (0x10000u | lane));
+            if (isbase) {
+                V.base_chan[nb + (e - 3)] = (uint16_t)ch;
+                if (!(gc & lt)) atomicAdd (&V.chan_num[ch], (uint32_t)__popc (gc));
+            }
+            u = u2; val = val2; q1 = q1n;
+        }
+        nb += Lq;
     }
 }
 
-// lens (BGEN32, :237-240) and the exclusive prefix next_of_chan (:193-196); one CTA per VBlock
+// lens (BGEN32, :237-240) and the exclusive prefix next_of_chan (:193-196); one CTA per VBlock.  Decode: the lengths are
+// untrusted — their sum must be the number of bases.
 __global__ void __launch_bounds__(1024) k_longr_prefix (const LrVb *vbs, int write_lens)
 {
     const LrVb &V = vbs[blockIdx.x];
     __shared__ uint32_t sm[33];
-    uint32_t acc = 0;
+    uint64_t acc = 0;
     for (uint32_t base = 0; base < NCHAN; base += 1024) {
         const uint32_t c = base + threadIdx.x;
         uint32_t v = write_lens ? V.chan_num[c] : __byte_perm (V.lens_be[c], 0, 0x0123);
         if (write_lens) V.lens_be[c] = __byte_perm (v, 0, 0x0123);
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         uint32_t inc = v;
-        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync (0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync (FULL, inc, o); if (lane >= o) inc += t; }
         if (lane == 31) sm[warp] = inc;
         __syncthreads ();
-        if (warp == 0) { uint32_t w = sm[lane], wi = w; for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync (0xffffffffu, wi, o); if (lane >= o) wi += t; } sm[lane] = wi - w; if (lane == 31) sm[32] = wi; }
+        if (warp == 0) { uint32_t w = sm[lane], wi = w; for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync (FULL, wi, o); if (lane >= o) wi += t; } sm[lane] = wi - w; if (lane == 31) sm[32] = wi; }
         __syncthreads ();
-        V.chan_num[c] = acc + sm[warp] + inc - v;
+        const uint64_t start = acc + sm[warp] + inc - v;
+        V.chan_num[c] = (uint32_t)(start < V.total ? start : V.total);
+        if (!write_lens) {
+            // cursor of the channel: next index, and the values up to the next 4-byte boundary
+            const uint32_t idx = V.chan_num[c];
+            uint32_t vals = 0;
+            const uint32_t va = (uint32_t)((uintptr_t)V.values & 3);
+            for (uint32_t k = idx; k < ((idx + va + 4) & ~3u) - va && k < V.total; k++) vals |= (uint32_t)V.values[k] << (8 * (k - idx));
+            V.cur[c] = ((unsigned long long)idx << 32) | vals;
+        }
         acc += sm[32];
         __syncthreads ();
     }
+    if (!write_lens && threadIdx.x == 0 && acc != V.total) *V.err = 1;
 }
 
-// stable scatter of the qualities into their channel segments (:205-230)
-__global__ void k_longr_scatter (const LrVb *vbs)
+// encode, second pass: stable scatter of the qualities into their channel segments (:205-230).  One warp per VBlock; the rank
+// of a base among the tile's bases of its channel comes from __match_any_sync, the segment position from one atomic per channel
+// and tile whose result is consumed one tile later.
+__global__ void __launch_bounds__(32) k_longr_place (const LrVb *vbs)
 {
-    const LrVb &V = vbs[blockIdx.y];
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < V.total; i += (uint64_t)gridDim.x * blockDim.x)
-        V.values[V.chan_num[V.base_chan[i]] + V.base_rank[i]] = V.base_q[i];
+    const LrVb &V = vbs[blockIdx.x];
+    const int lane = threadIdx.x;
+    const uint32_t lt = (1u << lane) - 1;
+    uint64_t nb = 0;
+    // pending tile
+    bool p_act = false; uint32_t p_old = 0, p_rank = 0, p_q = 0; int p_leader = 0;
+    for (uint32_t li = 0; li < V.n_lines; li++) {
+        const uint32_t L = V.qlen ? V.qlen[li] : V.len[li];
+        if (!L) continue;
+        const uint8_t *q = V.txt + V.qual_off[li];
+        const bool rev = V.is_rev ? V.is_rev[li] : false;
+        for (uint32_t k0 = 0; k0 < L; k0 += 32) {
+            const uint32_t k = k0 + lane;
+            const bool act = k < L;
+            const uint32_t ch = act ? V.base_chan[nb + k] : 0, qv = act ? (uint8_t)(q[rev ? L - 1 - k : k] - '!') : 0;
+            const uint32_t g = __match_any_sync (FULL, act ? ch : (0x10000u | lane));
+            const int leader = __ffs ((int)g) - 1;
+            uint32_t old = 0;
+            if (act && lane == leader) old = atomicAdd (&V.chan_num[ch], (uint32_t)__popc (g));
+            // the tile before: its atomics have had a tile's time to come back
+            const uint32_t po = __shfl_sync (FULL, p_old, p_leader);
+            if (p_act) V.values[po + p_rank] = (uint8_t)p_q;
+            __syncwarp ();                                                  // atomics of different lanes on one counter stay in tile order
+            p_act = act; p_old = old; p_rank = __popc (g & lt); p_q = qv; p_leader = leader;
+        }
+        nb += L;
+    }
+    const uint32_t po = __shfl_sync (FULL, p_old, p_leader);
+    if (p_act) V.values[po + p_rank] = (uint8_t)p_q;
 }
 
-// codec_longr_recon_one_read (:270-296) for every read; one VBlock per CTA, thread 0
-__global__ void k_longr_decode (const LrVb *vbs)
+// codec_longr_recon_one_read (:270-296) for every read of a VBlock; one warp per VBlock, lane 0 walks
+__global__ void __launch_bounds__(32) k_longr_decode (const LrVb *vbs)
 {
     const LrVb &V = vbs[blockIdx.x];
     __shared__ uint32_t tot[NQ9];
-    __shared__ uint8_t v2b[256];
-    for (int i = threadIdx.x; i < (int)NQ9; i += blockDim.x) tot[i] = 0x10101010u;
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) v2b[i] = V.v2b[i];
-    __syncthreads ();
-    if (threadIdx.x) return;
-    LrState s; s.avg = V.avg_sums; s.err = V.err_sums; s.tot = tot; s.v2b = v2b; s.chan = 0;
+    __shared__ uint8_t v2b[256], lut[512];
+    const int lane = threadIdx.x;
+    for (int i = lane; i < (int)NQ9; i += 32) tot[i] = 0x10101010u;
+    for (int i = lane; i < 256; i += 32) { v2b[i] = V.v2b[i]; lut[i] = (uint8_t)acgt_code (i); lut[256 + i] = (uint8_t)acgt_code_comp (i); }
+    __syncwarp ();
+    if (lane) return;
+    uint32_t *st = V.st; unsigned long long *cur = V.cur;
+    const uint8_t *values = V.values; const uint64_t total = V.total;
+    const uint32_t va = (uint32_t)((uintptr_t)values & 3);                  // refills are aligned 4-byte loads
     uint8_t *out = V.qual_out;
+    uint32_t bad = 0;
+    // a cursor whose refill is still in flight: written back when the next base has issued its own loads
+    uint32_t p_ch = 0xffffffffu, p_idx = 0, p_vals = 0;
     for (uint32_t li = 0; li < V.n_lines; li++) {
         const uint32_t L = V.len[li];
         if (!L) continue;
         const uint8_t *seq = V.txt + V.seq_off[li];
         const bool rev = V.is_rev ? V.is_rev[li] : false;
-        lr_init_read (s, seq, L, rev);
+        const uint8_t *lu = lut + (rev ? 256 : 0);
+        uint32_t B = 0, u = 0, u_prev = 0xffffffffu, nv_prev = 0;
         int32_t prev = 0;
-        for (uint32_t k = 0; k < L; k++) {
-            const uint32_t i = rev ? L - 1 - k : k;
-            const uint32_t b = rev ? acgt_code_comp (i >= 3 ? seq[i - 3] : 'T') : acgt_code (i + 3 < L ? seq[i + 3] : 'A');
-            const uint32_t ch = (s.chan >> 12) & 0xffffu;
-            const int32_t qq = V.values[V.chan_num[ch]++];
-            lr_update (s, b, qq, prev);
+        bool missing = false;
+        for (uint32_t e = 0; e < L + 3; e++) {
+            uint32_t val = u == u_prev ? nv_prev : st[u];
+            const uint32_t Qn = (u >> 12) & 0x1ffu, t_pre = tot[Qn];
+            int32_t qq = 0;
+            if (e >= 3) {
+                const uint32_t ch = Qn | (lr_chan_hi (val, t_pre, v2b) << 9);
+                uint32_t idx, vals;
+                if (ch == p_ch) { idx = p_idx; vals = p_vals; p_ch = 0xffffffffu; }
+                else {
+                    const unsigned long long c = cur[ch];
+                    if (p_ch != 0xffffffffu) { cur[p_ch] = ((unsigned long long)p_idx << 32) | p_vals; p_ch = 0xffffffffu; }
+                    idx = (uint32_t)(c >> 32); vals = (uint32_t)c;
+                }
+                qq = (int32_t)(vals & 0xffu);
+                if (idx >= total) { bad = 1; qq = 0; }
+                idx++; vals >>= 8;
+                if (!((idx + va) & 3u)) { p_vals = idx < total ? *reinterpret_cast<const uint32_t *>(values + idx) : 0; p_ch = ch; p_idx = idx; }   // refill, off the chain
+                else cur[ch] = ((unsigned long long)idx << 32) | vals;
+                const uint32_t k = e - 3;
+                out[rev ? L - 1 - k : k] = (uint8_t)(qq + '!');
+                missing = qq == 255;                                        // 255 + '!' == ' ': the line has no quality (:278)
+            }
+            uint32_t ae;
+            const uint32_t nv = lr_st_update (val, qq, ae);
+            st[u] = nv; tot[Qn] = lr_tot_update (t_pre, ae);
+            u_prev = u; nv_prev = nv;
+            // the context of the next event: base code of processing position e
+            const uint32_t b = e < L ? lu[seq[rev ? L - 1 - e : e]] : 0;
+            B = ((B << 2) | b) & 0xfffu;
+            u = B | (lr_difq (qq, prev) << 12) | ((uint32_t)(v2b[qq & 0xff] & 0x1f) << 16);
             prev = qq;
-            out[i] = (uint8_t)(qq + '!');
+            if (missing) break;                                             // after the state update, like RECON_ONE_QUAL
         }
+        if (missing) out[0] = '*';                                          // sam_reconstruct_missing_quality (sam_qual.c:532-541); the rest of the line is undefined
+        if (V.missing) V.missing[li] = missing;
         out += L;
     }
+    if (p_ch != 0xffffffffu) cur[p_ch] = ((unsigned long long)p_idx << 32) | p_vals;
+    if (bad) *V.err = 2;
+}
+
+// histogram of the quality values of a VBlock's lines (add_to_histogram, codec_longr.c:60-64)
+__global__ void k_longr_hist (const LrVb *vbs, uint32_t *hist)
+{
+    const LrVb &V = vbs[0];
+    __shared__ uint32_t h[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) h[i] = 0;
+    __syncthreads ();
+    for (uint32_t li = blockIdx.x; li < V.n_lines; li += gridDim.x) {
+        const uint32_t L = V.qlen ? V.qlen[li] : V.len[li];
+        const uint8_t *q = V.txt + V.qual_off[li];
+        if (L == 1 && q[0] == ' ') continue;                                // IS_SPACE: a missing quality (:88)
+        for (uint32_t k = threadIdx.x; k < L; k += blockDim.x) atomicAdd (&h[(uint8_t)(q[k] - '!')], 1u);
+    }
+    __syncthreads ();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) if (h[i]) atomicAdd (&hist[i], h[i]);
 }
 
 struct Carver {
@@ -204,39 +376,48 @@ struct Carver {
     }
 };
 
-int longr_run (gzb_engine *e, gzb_longr_vb *vbs, uint32_t n_vbs, uint32_t flags, bool encode)
+int longr_run (gzb_engine *e, gzb_longr_vb *vbs, uint32_t n_vbs, uint32_t flags, int mode /* 0 encode, 1 decode, 2 histogram */, uint32_t *hist_out)
 {
     if (!e || !vbs) return GZB_E_BADARG;
     if (!n_vbs) return GZB_OK;
     cudaSetDevice (e->device);
     const bool devptr = flags & GZB_DEVICE_PTRS;
+    const bool encode = mode == 0, decode = mode == 1;
     cudaStream_t st = e->stream;
     std::vector<LrVb> h (n_vbs);
     std::vector<uint64_t> total (n_vbs, 0);
     for (uint32_t v = 0; v < n_vbs; v++) {
-        if (devptr) total[v] = vbs[v].txt_len;                  // lengths live on the device: bound by the text size
-        else for (uint32_t i = 0; i < vbs[v].n_lines; i++) total[v] += vbs[v].len[i];
+        if (devptr) total[v] = vbs[v].n_bases ? vbs[v].n_bases : vbs[v].txt_len;   // lengths live on the device: the caller's count, else bound by the text size
+        else for (uint32_t i = 0; i < vbs[v].n_lines; i++) total[v] += (mode != 1 && vbs[v].qual_len) ? vbs[v].qual_len[i] : vbs[v].len[i];
+        if (total[v] >= (1ull << 32)) { e->err = "LONGR: more than 4 G qualities in a VBlock"; return GZB_E_BADARG; }
     }
     Carver c { nullptr, 0 };
-    LrVb *d_vbs = nullptr;
+    LrVb *d_vbs = nullptr; uint32_t *d_err = nullptr, *d_hist = nullptr;
     for (int pass = 0; pass < 2; pass++) {
         c.off = 0;
-        d_vbs = c.take<LrVb> (n_vbs);
+        d_vbs = c.take<LrVb> (n_vbs); d_err = c.take<uint32_t> (n_vbs); d_hist = c.take<uint32_t> (256);
         for (uint32_t v = 0; v < n_vbs; v++) {
             LrVb &D = h[v]; const gzb_longr_vb &S = vbs[v];
+            memset (&D, 0, sizeof D);
             D.n_lines = S.n_lines; D.total = total[v];
+            D.err = d_err ? d_err + v : nullptr;
             memcpy (D.v2b, S.value_to_bin, 256);
-            D.avg_sums = c.take<uint16_t> (NCTX); D.err_sums = c.take<uint16_t> (NCTX); D.chan_num = c.take<uint32_t> (NCHAN);
             D.txt      = devptr ? (const uint8_t *)S.txt : c.take<uint8_t> (S.txt_len + 16);
             D.seq_off  = devptr ? S.seq_off : c.take<uint64_t> (S.n_lines + 1);
-            D.qual_off = devptr ? S.qual_off : (encode ? c.take<uint64_t> (S.n_lines + 1) : nullptr);
+            D.qual_off = devptr ? S.qual_off : (!decode ? c.take<uint64_t> (S.n_lines + 1) : nullptr);
             D.len      = devptr ? S.len : c.take<uint32_t> (S.n_lines + 1);
             D.is_rev   = S.is_rev ? (devptr ? S.is_rev : c.take<uint8_t> (S.n_lines + 1)) : nullptr;
+            D.qlen     = (!decode && S.qual_len) ? (devptr ? S.qual_len : c.take<uint32_t> (S.n_lines + 1)) : nullptr;
+            if (mode == 2) continue;
+            D.st = c.take<uint32_t> (NCTX); D.chan_num = c.take<uint32_t> (NCHAN);
             D.values   = devptr ? (uint8_t *)S.values : c.take<uint8_t> (total[v] + 16);
             D.lens_be  = devptr ? S.lens_be : c.take<uint32_t> (NCHAN);
-            D.qual_out = (!encode) ? (devptr ? (uint8_t *)S.qual_out : c.take<uint8_t> (total[v] + 16)) : nullptr;
-            if (encode) { D.base_chan = c.take<uint16_t> (total[v] + 1); D.base_rank = c.take<uint32_t> (total[v] + 1); D.base_q = c.take<uint8_t> (total[v] + 1); }
-            else D.base_chan = nullptr, D.base_rank = nullptr, D.base_q = nullptr;
+            if (decode) {
+                D.cur = c.take<unsigned long long> (NCHAN);
+                D.qual_out = devptr ? (uint8_t *)S.qual_out : c.take<uint8_t> (total[v] + 16);
+                D.missing  = S.missing ? (devptr ? S.missing : c.take<uint8_t> (S.n_lines + 1)) : nullptr;
+            }
+            else D.base_chan = c.take<uint16_t> (total[v] + 1);
         }
         if (pass == 0) { int rc = engine_reserve (e, c.off, 4096); if (rc) return rc; c.base = e->ws; }
     }
@@ -246,43 +427,87 @@ int longr_run (gzb_engine *e, gzb_longr_vb *vbs, uint32_t n_vbs, uint32_t flags,
             if (S.txt_len) CK (cudaMemcpyAsync ((void *)D.txt, S.txt, S.txt_len, cudaMemcpyHostToDevice, st));
             if (S.n_lines) {
                 CK (cudaMemcpyAsync ((void *)D.seq_off, S.seq_off, (size_t)S.n_lines * 8, cudaMemcpyHostToDevice, st));
-                if (encode) CK (cudaMemcpyAsync ((void *)D.qual_off, S.qual_off, (size_t)S.n_lines * 8, cudaMemcpyHostToDevice, st));
+                if (!decode) CK (cudaMemcpyAsync ((void *)D.qual_off, S.qual_off, (size_t)S.n_lines * 8, cudaMemcpyHostToDevice, st));
                 CK (cudaMemcpyAsync ((void *)D.len, S.len, (size_t)S.n_lines * 4, cudaMemcpyHostToDevice, st));
                 if (S.is_rev) CK (cudaMemcpyAsync ((void *)D.is_rev, S.is_rev, S.n_lines, cudaMemcpyHostToDevice, st));
+                if (D.qlen) CK (cudaMemcpyAsync ((void *)D.qlen, S.qual_len, (size_t)S.n_lines * 4, cudaMemcpyHostToDevice, st));
             }
-            if (!encode) {
+            if (decode) {
                 if (total[v]) CK (cudaMemcpyAsync (D.values, S.values, total[v], cudaMemcpyHostToDevice, st));
                 CK (cudaMemcpyAsync (D.lens_be, S.lens_be, NCHAN * 4, cudaMemcpyHostToDevice, st));
             }
         }
     }
     CK (cudaMemcpyAsync (d_vbs, h.data (), n_vbs * sizeof (LrVb), cudaMemcpyHostToDevice, st));
-    k_longr_init<<<dim3 (256, n_vbs), 256, 0, st>>>(d_vbs);
+    CK (cudaMemsetAsync (d_err, 0, 4 * (size_t)n_vbs, st));
+    if (mode == 2) {
+        CK (cudaMemsetAsync (d_hist, 0, 1024, st));
+        k_longr_hist<<<592, 256, 0, st>>>(d_vbs, d_hist); e->launches++;
+        CK (cudaMemcpyAsync (hist_out, d_hist, 1024, cudaMemcpyDeviceToHost, st));
+        CK (cudaStreamSynchronize (st));
+        CK (cudaGetLastError ());
+        return GZB_OK;
+    }
+    k_longr_init<<<dim3 (64, n_vbs), 256, 0, st>>>(d_vbs);
     if (encode) {
-        k_longr_channels<<<n_vbs, 256, 0, st>>>(d_vbs);
+        k_longr_channels<<<n_vbs, 32, 0, st>>>(d_vbs);
         k_longr_prefix<<<n_vbs, 1024, 0, st>>>(d_vbs, 1);
-        k_longr_scatter<<<dim3 (512, n_vbs), 256, 0, st>>>(d_vbs);
+        k_longr_place<<<n_vbs, 32, 0, st>>>(d_vbs);
         e->launches += 4;
     }
     else {
         k_longr_prefix<<<n_vbs, 1024, 0, st>>>(d_vbs, 0);
-        k_longr_decode<<<n_vbs, 256, 0, st>>>(d_vbs);
+        k_longr_decode<<<n_vbs, 32, 0, st>>>(d_vbs);
         e->launches += 3;
     }
+    std::vector<uint32_t> errs (n_vbs, 0);
+    CK (cudaMemcpyAsync (errs.data (), d_err, 4 * (size_t)n_vbs, cudaMemcpyDeviceToHost, st));
     if (!devptr)
         for (uint32_t v = 0; v < n_vbs; v++) {
             if (encode) {
                 if (total[v]) CK (cudaMemcpyAsync (vbs[v].values, h[v].values, total[v], cudaMemcpyDeviceToHost, st));
                 CK (cudaMemcpyAsync (vbs[v].lens_be, h[v].lens_be, NCHAN * 4, cudaMemcpyDeviceToHost, st));
             }
-            else if (total[v]) CK (cudaMemcpyAsync (vbs[v].qual_out, h[v].qual_out, total[v], cudaMemcpyDeviceToHost, st));
+            else {
+                if (total[v]) CK (cudaMemcpyAsync (vbs[v].qual_out, h[v].qual_out, total[v], cudaMemcpyDeviceToHost, st));
+                if (vbs[v].missing && vbs[v].n_lines) CK (cudaMemcpyAsync (vbs[v].missing, h[v].missing, vbs[v].n_lines, cudaMemcpyDeviceToHost, st));
+            }
         }
     CK (cudaStreamSynchronize (st));
     CK (cudaGetLastError ());
+    for (uint32_t v = 0; v < n_vbs; v++)
+        if (errs[v]) { e->err = errs[v] == 1 ? "LONGR: channel lengths do not add up to the number of qualities" : "LONGR: a channel runs past the end of the values"; return GZB_E_CORRUPT; }
     return GZB_OK;
 }
 
 } // namespace
 
-extern "C" int gzb_longr_encode (gzb_engine *e, gzb_longr_vb *vbs, uint32_t n_vbs, uint32_t flags) { return longr_run (e, vbs, n_vbs, flags, true); }
-extern "C" int gzb_longr_decode (gzb_engine *e, gzb_longr_vb *vbs, uint32_t n_vbs, uint32_t flags) { return longr_run (e, vbs, n_vbs, flags, false); }
+extern "C" int gzb_longr_encode (gzb_engine *e, gzb_longr_vb *vbs, uint32_t n_vbs, uint32_t flags) { return longr_run (e, vbs, n_vbs, flags, 0, nullptr); }
+extern "C" int gzb_longr_decode (gzb_engine *e, gzb_longr_vb *vbs, uint32_t n_vbs, uint32_t flags) { return longr_run (e, vbs, n_vbs, flags, 1, nullptr); }
+
+// codec_longr_segconf_calculate_bins (codec_longr.c:66-136): histogram of the VBlock's qualities on the GPU, the 32 bins on the host
+extern "C" int gzb_longr_calculate_bins (gzb_engine *e, gzb_longr_vb *vb, uint32_t flags, uint8_t value_to_bin[256])
+{
+    if (!e || !vb || !value_to_bin) return GZB_E_BADARG;
+    uint32_t histogram[256];
+    int rc = longr_run (e, vb, 1, flags, 2, histogram);
+    if (rc) return rc;
+    uint64_t num_values = 0;
+    for (int i = 0; i < 256; i++) num_values += histogram[i];
+    if (!num_values) return GZB_SOFT_FAIL;                                  // flag.no_longr (:100-103)
+    const unsigned NUM_BINS = 32, fixed = 11;
+    uint32_t next_val = 0;
+    for (unsigned bin_i = 0; bin_i < NUM_BINS; bin_i++) {
+        const uint64_t at_least = num_values / (NUM_BINS - bin_i);
+        if (bin_i < fixed) { num_values -= histogram[next_val]; value_to_bin[next_val] = (uint8_t)bin_i; next_val++; }
+        else {
+            uint64_t bin_content = 0;
+            while (bin_content < at_least && next_val < 256) {
+                bin_content += histogram[next_val]; num_values -= histogram[next_val];
+                value_to_bin[next_val] = (uint8_t)bin_i; next_val++;
+            }
+        }
+    }
+    memset (value_to_bin + next_val, NUM_BINS - 1, 256 - next_val);
+    return GZB_OK;
+}

@@ -10,16 +10,14 @@
 #include <stdint.h>
 #include <cuda_runtime.h>
 
-// Warp-synchronous assumptions, made explicit.  Where the lanes of a CONVERGED warp all read a location that one of them
-// (or all, redundantly) stores to a few instructions later, the code relies on the lanes issuing each instruction together:
-// every lane has read before any lane stores.  That holds on the GPU as the code stands, so the marker compiles to nothing
-// there; the SIMT emulator of the CPU test suite (tests/host/simt) runs lanes one after the other between rendez-vous points
-// and turns the marker into one.  It stands after every such group of reads.  (Turning the markers into real __syncwarp()
-// would make the code independent of the assumption at the price of one WARPSYNC each — DESIGN.md §4.1.)
-#if defined(GZB_SIMT_EMULATION) || defined(GZB_READS_DONE_SYNCWARP)   // (the second: an nvcc build with real barriers, for the A/B run)
-  #define GZB_WARP_READS_DONE() __syncwarp ()
-#else
+// Where the lanes of a warp all read a location that one of them (or all, redundantly) stores to a few instructions later,
+// every lane must have read before any lane stores: GZB_WARP_READS_DONE () — a __syncwarp () — stands after every such group
+// of reads.  (Round 1 compiled it to nothing on the GPU, relying on lock-step issue of a converged warp; the real barrier
+// measured within noise on B200, so it is now always there.  -DGZB_READS_DONE_LOCKSTEP restores the old build for an A/B run.)
+#if defined(GZB_READS_DONE_LOCKSTEP) && !defined(GZB_SIMT_EMULATION)
   #define GZB_WARP_READS_DONE()
+#else
+  #define GZB_WARP_READS_DONE() __syncwarp ()
 #endif
 
 namespace gzb {

@@ -56,7 +56,14 @@ class AcgtVb(C.Structure):         # gzb_acgt_vb
 class LongrVb(C.Structure):         # gzb_longr_vb
     _fields_ = [("txt", C.c_void_p), ("txt_len", C.c_uint64), ("seq_off", C.c_void_p), ("qual_off", C.c_void_p),
                 ("len", C.c_void_p), ("is_rev", C.c_void_p), ("n_lines", C.c_uint32), ("value_to_bin", C.c_uint8 * 256),
-                ("values", C.c_void_p), ("lens_be", C.c_void_p), ("qual_out", C.c_void_p)]
+                ("values", C.c_void_p), ("lens_be", C.c_void_p), ("qual_out", C.c_void_p),
+                ("missing", C.c_void_p), ("qual_len", C.c_void_p), ("n_bases", C.c_uint64)]
+
+
+class PbwtVb(C.Structure):          # gzb_pbwt_vb
+    _fields_ = [("ht", C.c_void_p), ("ht_cap", C.c_uint64), ("ht_len", C.c_uint64), ("n_lines", C.c_uint32), ("ht_per_line", C.c_uint32),
+                ("runs", C.c_void_p), ("runs_cap", C.c_uint32), ("n_runs", C.c_uint32),
+                ("fgrc", C.c_void_p), ("fgrc_cap", C.c_uint32), ("n_fgrc", C.c_uint32), ("status", C.c_int32), ("reserved", C.c_uint32)]
 
 
 _lib = None
@@ -111,6 +118,11 @@ def load():
     L.gzb_pbwt_encode.restype = C.c_int
     L.gzb_pbwt_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32),
                                   C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32]
+    for f in ("gzb_pbwt_encode_batch", "gzb_pbwt_decode_batch"):
+        getattr(L, f).restype = C.c_int
+        getattr(L, f).argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+    L.gzb_longr_calculate_bins.restype = C.c_int
+    L.gzb_longr_calculate_bins.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
     L.gzb_pbwt_decode.restype = C.c_int
     L.gzb_pbwt_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64,
                                   C.POINTER(C.c_uint64), C.c_uint32]
@@ -362,25 +374,60 @@ class Engine:
             raise GzbError(f"gzb_pbwt_decode failed ({rc}): {self._err()}")
         return ht[:hl.value]
 
+    def pbwt_encode_batch(self, hts, runs_cap=None, fgrc_cap=None):
+        """codec_pbwt_compress for the matrices of a batch of VBlocks in one call -> [(RUNS, FGRC)]"""
+        hts = [np.ascontiguousarray(h, dtype=np.uint8) for h in hts]
+        arr = (PbwtVb * len(hts))()
+        keep = []
+        for a, ht in zip(arr, hts):
+            runs = np.zeros(runs_cap or (2 * ht.size + 8), np.uint32); fgrc = np.zeros(fgrc_cap or (ht.size + 8), np.uint32)
+            keep.append((runs, fgrc))
+            a.ht = ht.ctypes.data; a.n_lines, a.ht_per_line = ht.shape
+            a.runs = runs.ctypes.data; a.runs_cap = runs.size; a.fgrc = fgrc.ctypes.data; a.fgrc_cap = fgrc.size
+        rc = self.L.gzb_pbwt_encode_batch(self.h, arr, len(hts), 0)
+        if rc != 0:
+            raise GzbError(f"gzb_pbwt_encode_batch failed ({rc}): {self._err()}")
+        return [(r[:a.n_runs].copy(), f[:a.n_fgrc].copy()) for a, (r, f) in zip(arr, keep)]
+
+    def pbwt_decode_batch(self, streams, n_lines, sizes):
+        """codec_pbwt_uncompress for a batch: streams = [(RUNS, FGRC)], n_lines / sizes per VBlock -> [matrix bytes]"""
+        arr = (PbwtVb * len(streams))()
+        keep = []
+        for a, (runs, fgrc), nl, size in zip(arr, streams, n_lines, sizes):
+            runs = np.ascontiguousarray(runs, np.uint32); fgrc = np.ascontiguousarray(fgrc, np.uint32); ht = np.zeros(size, np.uint8)
+            keep.append((runs, fgrc, ht))
+            a.ht = ht.ctypes.data; a.ht_cap = size; a.n_lines = nl
+            a.runs = runs.ctypes.data; a.n_runs = runs.size; a.fgrc = fgrc.ctypes.data; a.n_fgrc = fgrc.size
+        rc = self.L.gzb_pbwt_decode_batch(self.h, arr, len(streams), 0)
+        if rc != 0:
+            raise GzbError(f"gzb_pbwt_decode_batch failed ({rc}): {self._err()}")
+        return [k[2][:a.ht_len] for a, k in zip(arr, keep)]
+
     # ---- LONGR (host buffers), batch of VBlocks: each (txt, seq_off, qual_off, lens, is_rev|None, value_to_bin) ----
     def _longr_arr(self, vbs, values=None, lens_be=None, decode=False):
         n = len(vbs)
         arr = (LongrVb * n)()
         keep = []
-        for i, (txt, seq_off, qual_off, lens, is_rev, v2b) in enumerate(vbs):
+        for i, vb in enumerate(vbs):
+            txt, seq_off, qual_off, lens, is_rev, v2b = vb[:6]
+            qlens = vb[6] if len(vb) > 6 else None                           # quality lengths where they differ from lens (lines without quality)
             txt = np.ascontiguousarray(txt, np.uint8); seq_off = np.ascontiguousarray(seq_off, np.uint64)
             qual_off = np.ascontiguousarray(qual_off, np.uint64); lens = np.ascontiguousarray(lens, np.uint32)
+            ql = None if qlens is None else np.ascontiguousarray(qlens, np.uint32)
             tot = int(lens.sum())
             vals = np.zeros(tot + 1, np.uint8) if values is None else np.ascontiguousarray(values[i], np.uint8)
             lb = np.zeros(65536, np.uint32) if lens_be is None else np.ascontiguousarray(lens_be[i], np.uint32)
             qo = np.zeros(tot + 1, np.uint8)
             rv = None if is_rev is None else np.ascontiguousarray(is_rev, np.uint8)
-            keep.append((txt, seq_off, qual_off, lens, rv, vals, lb, qo))
+            ms = np.zeros(lens.size + 1, np.uint8)
+            keep.append((txt, seq_off, qual_off, lens, rv, vals, lb, qo, ms, ql))
             a = arr[i]
             a.txt = txt.ctypes.data; a.txt_len = txt.size; a.seq_off = seq_off.ctypes.data; a.qual_off = qual_off.ctypes.data
             a.len = lens.ctypes.data; a.is_rev = None if rv is None else rv.ctypes.data; a.n_lines = lens.size
             C.memmove(a.value_to_bin, np.ascontiguousarray(v2b, np.uint8).ctypes.data, 256)
             a.values = vals.ctypes.data; a.lens_be = lb.ctypes.data; a.qual_out = qo.ctypes.data
+            a.missing = ms.ctypes.data if decode else None
+            a.qual_len = None if (ql is None or decode) else ql.ctypes.data
         return arr, keep
 
     def longr_encode(self, vbs):
@@ -388,11 +435,23 @@ class Engine:
         rc = self.L.gzb_longr_encode(self.h, arr, len(vbs), 0)
         if rc != 0:
             raise GzbError(f"gzb_longr_encode failed ({rc}): {self._err()}")
-        return [(k[5][:int(k[3].sum())].copy(), k[6].copy()) for k in keep]
+        return [(k[5][:int((k[3] if k[9] is None else k[9]).sum())].copy(), k[6].copy()) for k in keep]
 
     def longr_decode(self, vbs, values, lens_be):
         arr, keep = self._longr_arr(vbs, values, lens_be, decode=True)
         rc = self.L.gzb_longr_decode(self.h, arr, len(vbs), 0)
         if rc != 0:
             raise GzbError(f"gzb_longr_decode failed ({rc}): {self._err()}")
+        self.longr_missing = [k[8][:k[3].size].copy() for k in keep]
         return [k[7][:int(k[3].sum())].copy() for k in keep]
+
+    def longr_calculate_bins(self, vb):
+        """codec_longr_segconf_calculate_bins -> value_to_bin (256 bytes), or None when the VBlock has no quality"""
+        arr, keep = self._longr_arr([tuple(vb[:5]) + (np.zeros(256, np.uint8),) + tuple(vb[6:])])
+        v2b = np.zeros(256, np.uint8)
+        rc = self.L.gzb_longr_calculate_bins(self.h, arr, 0, v2b.ctypes.data)
+        if rc == 1:
+            return None
+        if rc != 0:
+            raise GzbError(f"gzb_longr_calculate_bins failed ({rc}): {self._err()}")
+        return v2b

@@ -176,6 +176,25 @@ int gzb_pbwt_encode (gzb_engine *e, const void *ht, uint32_t n_lines, uint32_t h
 int gzb_pbwt_decode (gzb_engine *e, const uint32_t *runs, uint32_t n_runs, const uint32_t *fgrc, uint32_t n_fgrc,
                      uint32_t n_lines, void *ht, uint64_t ht_cap, uint64_t *ht_len, uint32_t flags);
 
+/* Batched forms — the matrices of all VBlocks of a batch in one call: one CTA per VBlock walks its rows, so a batch of >= 148
+ * VBlocks (one per SM; several fit) is what fills the GPU.  The per-VBlock outcome is in `status`; the call returns the first
+ * non-zero one.
+ * encode: in  ht, n_lines, ht_per_line, runs/runs_cap, fgrc/fgrc_cap      out  n_runs, n_fgrc, status
+ * decode: in  runs/n_runs, fgrc/n_fgrc, n_lines, ht/ht_cap                 out  ht bytes, ht_len, status */
+typedef struct gzb_pbwt_vb {
+    void     *ht;           /* the haplotype matrix, n_lines x ht_per_line alleles (encode: read; decode: written) */
+    uint64_t  ht_cap;       /* decode: capacity of ht */
+    uint64_t  ht_len;       /* decode out: bytes of matrix = the 64-bit length in the last two FGRC words */
+    uint32_t  n_lines;      /* ht_ctx->HT_n_lines */
+    uint32_t  ht_per_line;  /* encode in */
+    uint32_t *runs;  uint32_t runs_cap, n_runs;
+    uint32_t *fgrc;  uint32_t fgrc_cap, n_fgrc;
+    int32_t   status;
+    uint32_t  reserved;
+} gzb_pbwt_vb;
+int gzb_pbwt_encode_batch (gzb_engine *e, gzb_pbwt_vb *vbs, uint32_t n_vbs, uint32_t flags);
+int gzb_pbwt_decode_batch (gzb_engine *e, gzb_pbwt_vb *vbs, uint32_t n_vbs, uint32_t flags);
+
 /* ---------------------------------------------------------------- LONGR (src/codec_longr.c, src/codec_longr_alg.c)
  * encode: codec_longr_compress (:161-247) before its sub-codec: channel per base, stable sort of quals by channel.
  * decode: codec_longr_reconstruct (:342-373) for all reads of a VB. */
@@ -190,10 +209,18 @@ typedef struct {
     uint8_t         value_to_bin[256];  /* codec_longr_segconf_calculate_bins (:66-136), computed once by the host */
     void           *values;     /* sum(len) bytes: encode out / decode in */
     uint32_t       *lens_be;    /* 65536 big-endian u32: encode out / decode in (:237-240) */
-    void           *qual_out;   /* decode: concatenated quality strings */
+    void           *qual_out;   /* decode: concatenated quality strings, len[i] bytes per line */
+    uint8_t        *missing;    /* decode, optional (n_lines): 1 where the line has no quality — its first value is 255 (:278); the line's
+                                   first byte is then '*' (sam_reconstruct_missing_quality, src/sam_qual.c:532) and the rest undefined */
+    const uint32_t *qual_len;   /* encode, optional (n_lines): quality length where it differs from len — a SAM line without quality is the
+                                   one byte ' ' whatever its seq_len (:188,:190-192); NULL = len */
+    uint64_t        n_bases;    /* with GZB_DEVICE_PTRS: the number of qualities in the VBlock (0 = take txt_len as the bound) */
 } gzb_longr_vb;
 int gzb_longr_encode (gzb_engine *e, gzb_longr_vb *vbs, uint32_t n_vbs, uint32_t flags);
 int gzb_longr_decode (gzb_engine *e, gzb_longr_vb *vbs, uint32_t n_vbs, uint32_t flags);
+/* codec_longr_segconf_calculate_bins (:66-136): value_to_bin of the 32 equal-population bins from the qualities of one VBlock
+ * (histogram on the GPU).  GZB_SOFT_FAIL when there is no quality at all (flag.no_longr, :100-103). */
+int gzb_longr_calculate_bins (gzb_engine *e, gzb_longr_vb *vb, uint32_t flags, uint8_t value_to_bin[256]);
 
 /* ================================================================ plug-in layer (reference signatures) */
 typedef struct VBlock        *VBlockP;          /* opaque genozip types */
