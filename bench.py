@@ -18,6 +18,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "fastq_input_GBps_zip_plus_piz"
 UNIT = "GB/s"
+WORKLOAD = "fastq_illumina_150bp_paired_vb32MB (BASELINE configs[1] per-GPU share)"
+EXCLUDED = "segmenter; LZMA of the 2-bit sequence words (host, out of scope) — in both arms"
 
 
 def parse():
@@ -30,6 +32,10 @@ def parse():
                     help="VBlocks per GPU per step (0 = as many as fit, at most 256: the chain kernels are latency-bound, so throughput grows with the batch)")
     ap.add_argument("--reads", type=int, default=92000, help="reads per VBlock (92,000 x 150 bp ~ 32 MB of FASTQ text)")
     ap.add_argument("--read-len", type=int, default=150)
+    ap.add_argument("--workload", default="fastq", choices=["fastq", "vcf", "longread"],
+                    help="fastq = BASELINE configs[1] (the headline metric); vcf = configs[3] (codec_pbwt); longread = configs[4] (codec_longr) — bench_domain.py")
+    ap.add_argument("--vcf-lines", type=int, default=38000); ap.add_argument("--vcf-samples", type=int, default=1000)
+    ap.add_argument("--lr-bases", type=int, default=16_000_000); ap.add_argument("--lr-read-len", type=int, default=50000)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -89,11 +95,14 @@ def _cpu_worker(wid, n_workers, n_vb, bar, q):
     off = (np.arange(n_reads, dtype=np.uint64) * np.uint64(read_len)); ln = np.full(n_reads, read_len, np.uint32)
     names = ("Q_TILE", "Q_X", "Q_Y", "Q_MISC")
     mine = list(range(wid, n_vb, n_workers))
+    gz = orc.have_gz_ref()                                   # the reference's own compiled codec_domq.c / codec_acgt.c (-O3), else the restatement
+    acgt_pack, domq_encode = (orc.ref_acgt_pack, orc.ref_domq_encode) if gz else (orc.acgt_pack, orc.domq_encode)
+    acgt_unpack, domq_decode = (orc.ref_acgt_unpack, orc.ref_domq_decode) if gz else (orc.acgt_unpack, orc.domq_decode)
     bar.wait()
     zs = []
     for v in mine:
-        packed, x, allz = orc.acgt_pack(data_np["seq"][v])
-        enc = orc.domq_encode(data_np["qual"][v], off, ln)
+        packed, x, allz = acgt_pack(data_np["seq"][v])
+        enc = domq_encode(data_np["qual"][v], off, ln)
         streams = {"QUAL": enc["qual"], "DOMQRUNS": enc["runs"], "QUALMPLX": enc["mplx"], "DIVRQUAL": enc["divr"]}
         if not allz:
             streams["NONREF_X"] = x
@@ -114,11 +123,11 @@ def _cpu_worker(wid, n_workers, n_vb, bar, q):
             dec[s_] = orc.uncompress(impl, "rans" if cc.startswith("RAN") else "arith", c, n)
         e = dict(z["enc"]); e.update(qual=dec["QUAL"], runs=dec.get("DOMQRUNS", np.zeros(0, np.uint8)), mplx=dec["QUALMPLX"],
                                      divr=dec.get("DIVRQUAL", np.zeros(0, np.uint8)))
-        q_ = orc.domq_decode(e, ln)
-        s2 = orc.acgt_unpack(z["packed"], None if z["allz"] else dec["NONREF_X"], n_reads * read_len)
-        ok = ok and q_.size == s2.size
+        q_ = domq_decode(e, ln)
+        s2 = acgt_unpack(z["packed"], None if z["allz"] else dec["NONREF_X"], n_reads * read_len)
+        ok = ok and np.array_equal(q_, data_np["qual"][v]) and np.array_equal(s2, data_np["seq"][v])
     bar.wait()
-    q.put(ok)
+    q.put((ok, sum(len(c) for z in zs for c, _ in z["comp"].values())))
 
 
 def cpu_path_time(data_np, n_reads, read_len, codec, workers, n_vb):
@@ -140,31 +149,35 @@ def cpu_path_time(data_np, n_reads, read_len, codec, workers, n_vb):
     bar.wait(); t0 = time.perf_counter()
     bar.wait(); t1 = time.perf_counter()
     bar.wait(); t2 = time.perf_counter()
-    oks = [q.get(timeout=600) for _ in ps]
+    res = [q.get(timeout=600) for _ in ps]
     [p.join() for p in ps]
-    assert all(oks)
+    assert all(r[0] for r in res), "CPU arm: round trip failed"
+    _CPU["compressed_bytes"] = int(sum(r[1] for r in res))
     return t1 - t0, t2 - t1, kind
 
 
 def synth_numpy(V, n_reads, read_len, seed):
-    """numpy twin of fastq_path.synth_vblocks for the CPU-only arm (no torch.cuda needed)"""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from datagen import fastq_vb
-    out = {k: [] for k in ("seq", "qual", "Q_TILE", "Q_X", "Q_Y", "Q_MISC")}
-    r = np.random.default_rng(seed)
-    for v in range(V):
-        s, q = fastq_vb(n_reads, read_len, seed * 1000 + v)
-        out["seq"].append(s); out["qual"].append(q)
-        out["Q_TILE"].append((np.arange(n_reads) // 977 % 96).astype(np.uint8))
-        xs = (np.cumsum(r.integers(0, 60, n_reads)) % 30000 + 1000).astype(">u4").view(np.uint8)
-        ys = r.integers(1000, 30000, n_reads).astype(">u4").view(np.uint8)
-        out["Q_X"].append(xs.copy()); out["Q_Y"].append(ys.copy())
-        out["Q_MISC"].append(r.choice(4, n_reads, p=[.9, .05, .03, .02]).astype(np.uint8))
-    return out
+    """the bytes of the GPU arm's first V VBlocks for the CPU-only arm: the same torch generator, on the GPU when the box has one
+    (the GPU arm generates there, and CUDA's random streams differ from the CPU's), else on the CPU (same distribution, other bytes)"""
+    import torch
+    from genozip_b200.fastq_path import synth_vblocks
+    dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+    d = synth_vblocks(V, n_reads, read_len, seed, dev)
+    out = {k: [t[v].cpu().numpy() for v in range(V)] for k, t in d.items()}
+    del d
+    if dev.type == "cuda":
+        torch.cuda.empty_cache()
+    return out, dev.type
 
 
-DEFAULT_CODECS = {"QUAL": "RANB", "DOMQRUNS": "RANB", "QUALMPLX": "RANB", "DIVRQUAL": "RANB", "NONREF_X": "RANB",
-                  "Q_TILE": "RANB", "Q_X": "RANW", "Q_Y": "RANW", "Q_MISC": "RANB"}
+# Codec of each stream: codec_assign_best_codec's size criterion over the eight in-scope codecs on VB 1 (fastq_path.assign_codecs).
+# The table is COMMITTED so that both arms run the same codecs whatever runs first; the GPU arm re-derives it every run and reports
+# whether it still agrees (`codecs_rederived_equal`).
+CODEC_TABLE = os.path.join(ROOT, "bench_codecs.json")
+
+
+def load_codecs():
+    return json.load(open(CODEC_TABLE))
 
 
 def run_reference(args):
@@ -175,8 +188,8 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     n_vb = max(2 * cores, 8)                                 # two VBlocks per host process per step
     from genozip_b200.fastq_path import txt_bytes_per_vb
-    data = synth_numpy(n_vb, args.reads, args.read_len, 2)
-    codec = load_codecs() or DEFAULT_CODECS
+    data, gen = synth_numpy(n_vb, args.reads, args.read_len, 1000)          # = the GPU arm's rank-0 VBlocks 0 .. n_vb-1
+    codec = load_codecs()
     ts = []
     for i in range(args.warmup + args.steps):
         tz, tp, kind = cpu_path_time(data, args.reads, args.read_len, codec, cores, n_vb)
@@ -190,22 +203,14 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * (tz + tp) / len(ts), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic", "zip_GBps": nbytes / tz / 1e9, "piz_GBps": nbytes / tp / 1e9,
-        "config": {"workload": "fastq_illumina_150bp_paired_vb32MB (BASELINE configs[1] per-GPU share)", "vblocks_per_step": n_vb,
+        "config": {"workload": WORKLOAD, "vblocks_per_step": n_vb,
                    "reads_per_vblock": args.reads, "read_len": args.read_len, "codecs": codec,
-                   "excluded": "segmenter; LZMA of the 2-bit words (both excluded from the GPU arm as well)"},
+                   "compressed_bytes_per_vblock": _CPU.get("compressed_bytes", 0) / n_vb,
+                   "data_generator": f"torch-{gen} (the GPU arm's rank-0 VBlocks 0..{n_vb - 1}" + (")" if gen == "cuda" else "; no GPU here: same distribution, other bytes)"),
+                   "excluded": EXCLUDED},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
-
-
-CODEC_CACHE = os.path.join(ROOT, "gpurun_out", "bench_codecs.json")
-
-
-def load_codecs():
-    try:
-        return json.load(open(CODEC_CACHE))
-    except Exception:
-        return None
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
@@ -259,9 +264,13 @@ def run_gpu(args):
         eng.close(); torch.cuda.empty_cache()
         eng = Engine(local)
         V = max(4, V // 2)
-    if rank == 0:
-        os.makedirs(os.path.dirname(CODEC_CACHE), exist_ok=True)
-        json.dump(codecs, open(CODEC_CACHE, "w"))
+    committed = load_codecs()
+    rederived_equal = committed == dict(codecs)
+    codecs = committed                                         # both arms run the committed table (see CODEC_TABLE)
+    path.codec = dict(codecs)
+    if not rederived_equal:                                    # (sizes were planned for the re-derived table)
+        path.comp_d = {}
+        meta = path.zip_device(data); path.alloc_piz(meta); path.piz_device(meta); torch.cuda.synchronize()
     assert torch.equal(path.seq_out_d, data["seq"]) and torch.equal(path.qual_out_d, data["qual"]), "round trip failed"
     for s in ("Q_TILE", "Q_X", "Q_Y", "Q_MISC"):
         assert torch.equal(path.dec_d[s][:, :data[s].shape[1]], data[s]), f"round trip failed: {s}"
@@ -371,11 +380,11 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": zip_ms + piz_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "zip_GBps": world * txt_bytes / (zip_ms * 1e-3) / 1e9, "piz_GBps": world * txt_bytes / (piz_ms * 1e-3) / 1e9,
-            "config": {"workload": "fastq_illumina_150bp_paired_vb32MB (BASELINE configs[1] per-GPU share)", "vblocks_per_gpu_per_step": V,
+            "config": {"workload": WORKLOAD, "vblocks_per_gpu_per_step": V,
                        "reads_per_vblock": args.reads, "read_len": args.read_len, "txt_bytes_per_step_per_gpu": txt_bytes,
-                       "codecs": codecs, "l2": "inputs (>= 0.9 GB per step) are larger than L2; no flush needed",
+                       "codecs": codecs, "codecs_rederived_equal": rederived_equal, "compressed_bytes_per_vblock": comp_total / V, "l2": "inputs (>= 0.9 GB per step) are larger than L2; no flush needed",
                        "sections_per_step": sum(1 for m in meta for n in m["len"].values() if n), "compressed_bytes_per_step": comp_total,
-                       "excluded": "segmenter; LZMA of the 2-bit sequence words (host, out of scope)", "sharding": "VBlocks round-robin by vblock_i, no data-path collective; NCCL all_gather of the section list only",
+                       "excluded": EXCLUDED, "sharding": "VBlocks round-robin by vblock_i, no data-path collective; NCCL all_gather of the section list only",
                        "engines_per_gpu": len(path.engs), "device_groups": len(path.groups)},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
         }))
@@ -385,7 +394,11 @@ def run_gpu(args):
 
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
+    a.seed_base = 0
+    if a.workload != "fastq":
+        import bench_domain
+        bench_domain.run_reference(a) if a.impl == "reference" else bench_domain.run_gpu(a, ClockSampler)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_gpu(a)

@@ -133,7 +133,7 @@ extern "C" int gzb_engine_sync (gzb_engine *e) { cudaSetDevice (e->device); CK (
 extern "C" int gzb_vb_device (uint32_t vblock_i, int n_devices) { return n_devices > 0 ? (int)((vblock_i ? vblock_i - 1 : 0) % (uint32_t)n_devices) : 0; }
 extern "C" uint64_t gzb_kernel_launches (gzb_engine *e) { return e->launches; }
 extern "C" float gzb_last_chain_ms (gzb_engine *e) { return e->last_chain_ms; }
-extern "C" float gzb_last_kernel_ms (gzb_engine *e, int which) { return which ? e->last_arith_ms : e->last_rans_ms; }
+extern "C" float gzb_last_kernel_ms (gzb_engine *e, int which) { return which == 2 ? e->last_domain_ms : which ? e->last_arith_ms : e->last_rans_ms; }
 
 int engine_reserve (gzb_engine *e, size_t ws_bytes, size_t pin_bytes)
 {

@@ -385,10 +385,13 @@ int longr_run (gzb_engine *e, gzb_longr_vb *vbs, uint32_t n_vbs, uint32_t flags,
     const bool encode = mode == 0, decode = mode == 1;
     cudaStream_t st = e->stream;
     std::vector<LrVb> h (n_vbs);
-    std::vector<uint64_t> total (n_vbs, 0);
+    std::vector<uint64_t> total (n_vbs, 0), out_len (n_vbs, 0);     // qualities in the VBlock (= bytes of values); decode: bytes of qual_out
     for (uint32_t v = 0; v < n_vbs; v++) {
-        if (devptr) total[v] = vbs[v].n_bases ? vbs[v].n_bases : vbs[v].txt_len;   // lengths live on the device: the caller's count, else bound by the text size
-        else for (uint32_t i = 0; i < vbs[v].n_lines; i++) total[v] += (mode != 1 && vbs[v].qual_len) ? vbs[v].qual_len[i] : vbs[v].len[i];
+        if (devptr) total[v] = out_len[v] = vbs[v].n_bases ? vbs[v].n_bases : vbs[v].txt_len;   // lengths live on the device: the caller's count, else bound by the text size
+        else {
+            for (uint32_t i = 0; i < vbs[v].n_lines; i++) { total[v] += (mode != 1 && vbs[v].qual_len) ? vbs[v].qual_len[i] : vbs[v].len[i]; out_len[v] += vbs[v].len[i]; }
+            if (mode == 1 && vbs[v].n_bases) { if (vbs[v].n_bases > total[v]) return GZB_E_BADARG; total[v] = vbs[v].n_bases; }   // fewer values than bases: lines without quality
+        }
         if (total[v] >= (1ull << 32)) { e->err = "LONGR: more than 4 G qualities in a VBlock"; return GZB_E_BADARG; }
     }
     Carver c { nullptr, 0 };
@@ -414,7 +417,7 @@ int longr_run (gzb_engine *e, gzb_longr_vb *vbs, uint32_t n_vbs, uint32_t flags,
             D.lens_be  = devptr ? S.lens_be : c.take<uint32_t> (NCHAN);
             if (decode) {
                 D.cur = c.take<unsigned long long> (NCHAN);
-                D.qual_out = devptr ? (uint8_t *)S.qual_out : c.take<uint8_t> (total[v] + 16);
+                D.qual_out = devptr ? (uint8_t *)S.qual_out : c.take<uint8_t> (out_len[v] + 16);
                 D.missing  = S.missing ? (devptr ? S.missing : c.take<uint8_t> (S.n_lines + 1)) : nullptr;
             }
             else D.base_chan = c.take<uint16_t> (total[v] + 1);
@@ -450,14 +453,18 @@ int longr_run (gzb_engine *e, gzb_longr_vb *vbs, uint32_t n_vbs, uint32_t flags,
     }
     k_longr_init<<<dim3 (64, n_vbs), 256, 0, st>>>(d_vbs);
     if (encode) {
+        cudaEventRecord (e->ev0, st);
         k_longr_channels<<<n_vbs, 32, 0, st>>>(d_vbs);
+        cudaEventRecord (e->ev1, st);
         k_longr_prefix<<<n_vbs, 1024, 0, st>>>(d_vbs, 1);
         k_longr_place<<<n_vbs, 32, 0, st>>>(d_vbs);
         e->launches += 4;
     }
     else {
         k_longr_prefix<<<n_vbs, 1024, 0, st>>>(d_vbs, 0);
+        cudaEventRecord (e->ev0, st);
         k_longr_decode<<<n_vbs, 32, 0, st>>>(d_vbs);
+        cudaEventRecord (e->ev1, st);
         e->launches += 3;
     }
     std::vector<uint32_t> errs (n_vbs, 0);
@@ -469,12 +476,13 @@ int longr_run (gzb_engine *e, gzb_longr_vb *vbs, uint32_t n_vbs, uint32_t flags,
                 CK (cudaMemcpyAsync (vbs[v].lens_be, h[v].lens_be, NCHAN * 4, cudaMemcpyDeviceToHost, st));
             }
             else {
-                if (total[v]) CK (cudaMemcpyAsync (vbs[v].qual_out, h[v].qual_out, total[v], cudaMemcpyDeviceToHost, st));
+                if (out_len[v]) CK (cudaMemcpyAsync (vbs[v].qual_out, h[v].qual_out, out_len[v], cudaMemcpyDeviceToHost, st));
                 if (vbs[v].missing && vbs[v].n_lines) CK (cudaMemcpyAsync (vbs[v].missing, h[v].missing, vbs[v].n_lines, cudaMemcpyDeviceToHost, st));
             }
         }
     CK (cudaStreamSynchronize (st));
     CK (cudaGetLastError ());
+    cudaEventElapsedTime (&e->last_domain_ms, e->ev0, e->ev1);
     for (uint32_t v = 0; v < n_vbs; v++)
         if (errs[v]) { e->err = errs[v] == 1 ? "LONGR: channel lengths do not add up to the number of qualities" : "LONGR: a channel runs past the end of the values"; return GZB_E_CORRUPT; }
     return GZB_OK;

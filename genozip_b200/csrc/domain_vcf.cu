@@ -580,7 +580,9 @@ extern "C" int gzb_pbwt_encode_batch (gzb_engine *e, gzb_pbwt_vb *vbs, uint32_t 
     CK (cudaMemsetAsync (d_res, 0, 16 * (size_t)n_vbs, st));
     if (any_narrow) {
         CK (cudaFuncSetAttribute (k_pbwt_rows<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PB_SMEM_MAX));
+        cudaEventRecord (e->ev0, st);
         k_pbwt_rows<0><<<n_vbs, PBT, smem, st>>>(d_vbs);
+        cudaEventRecord (e->ev1, st);
         k_pbwt_emit<<<n_vbs, PB_THREADS, 0, st>>>(d_vbs);
         e->launches += 2;
     }
@@ -590,6 +592,8 @@ extern "C" int gzb_pbwt_encode_batch (gzb_engine *e, gzb_pbwt_vb *vbs, uint32_t 
     CK (cudaMemcpyAsync (res.data (), d_res, 16 * (size_t)n_vbs, cudaMemcpyDeviceToHost, st));
     CK (cudaStreamSynchronize (st));
     CK (cudaGetLastError ());
+    e->last_domain_ms = 0;
+    if (any_narrow) cudaEventElapsedTime (&e->last_domain_ms, e->ev0, e->ev1);
     int rc = GZB_OK;
     for (uint32_t v = 0; v < n_vbs; v++) {
         uint32_t *r = &res[4 * (size_t)v];
@@ -673,7 +677,9 @@ extern "C" int gzb_pbwt_decode_batch (gzb_engine *e, gzb_pbwt_vb *vbs, uint32_t 
         const uint32_t tiles = (uint32_t)std::min<uint64_t> ((max_len + PB_TILE - 1) / PB_TILE, 8192);
         k_pbwt_expand<<<dim3 (tiles, n_vbs), 256, 0, st>>>(d_vbs, d_pal);
         CK (cudaFuncSetAttribute (k_pbwt_rows<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PB_SMEM_MAX));
+        cudaEventRecord (e->ev0, st);
         k_pbwt_rows<1><<<n_vbs, PBT, smem, st>>>(d_vbs);
+        cudaEventRecord (e->ev1, st);
         e->launches += 2;
     }
     for (uint32_t v = 0; v < n_vbs; v++)
@@ -684,6 +690,8 @@ extern "C" int gzb_pbwt_decode_batch (gzb_engine *e, gzb_pbwt_vb *vbs, uint32_t 
         for (uint32_t v = 0; v < n_vbs; v++) CK (cudaMemcpyAsync (vbs[v].ht, h[v].dst, h[v].len, cudaMemcpyDeviceToHost, st));
     CK (cudaStreamSynchronize (st));
     CK (cudaGetLastError ());
+    e->last_domain_ms = 0;
+    if (any_narrow) cudaEventElapsedTime (&e->last_domain_ms, e->ev0, e->ev1);
     int rc = GZB_OK;
     for (uint32_t v = 0; v < n_vbs; v++) {
         vbs[v].status = pb_status (e, res[4 * (size_t)v + 2]);

@@ -14,6 +14,7 @@ struct gzb_engine {
     std::string  err;
     uint64_t     launches = 0;
     float        last_chain_ms = 0, last_rans_ms = 0, last_arith_ms = 0;
+    float        last_domain_ms = 0;                // dominant kernel of the last PBWT / LONGR batch call (k_pbwt_rows, k_longr_channels, k_longr_decode)
     size_t       arena_hint = 0, arena_hint_dec = 0;
     // DOMQ session: device state kept between gzb_domq_prepare and gzb_domq_split of the same batch
     uint8_t     *dq_buf = nullptr; size_t dq_cap = 0;

@@ -155,11 +155,13 @@ __device__ uint32_t build_dec_o0 (DTabSmem &sm, const uint8_t *p, const uint8_t 
     __syncthreads ();
     if (tid == 0) {
         const uint8_t *s = p;
-        uint32_t k = get_alphabet (p, end, sm.F), tot = 0;
-        sm.ok = k != 0;
+        uint32_t k = get_alphabet (p, end, sm.F);
+        uint64_t tot = 0;                                                  // a varint is any 32-bit value: sums must not wrap (the reference checks
+        bool ok = k != 0;                                                  // every F[j] against what is left of TOTFREQ, :538)
         p += k;
-        if (k) for (int j = 0; j < 256; j++) if (sm.F[j]) { p += get_varint (p, end, &sm.F[j]); tot += sm.F[j]; }
-        sm.T = tot; sm.consumed = (uint32_t)(p - s);
+        if (k) for (int j = 0; j < 256; j++) if (sm.F[j]) { p += get_varint (p, end, &sm.F[j]); if (sm.F[j] > 4096) ok = false; tot += sm.F[j]; }
+        sm.ok = ok && tot <= 4096;
+        sm.T = (uint32_t)(tot <= 4096 ? tot : 0); sm.consumed = (uint32_t)(p - s);
     }
     __syncthreads ();
     if (!sm.ok || !sm.T || sm.T > 4096 || (sm.T & (sm.T - 1))) return 0;
@@ -169,6 +171,7 @@ __device__ uint32_t build_dec_o0 (DTabSmem &sm, const uint8_t *p, const uint8_t 
     uint32_t total = scan_F (sm);
     if (total != 4096) return 0;
     uint32_t f = sm.F[tid], st = sm.start[tid];
+    if (st + f > 4096) f = 0;                                              // (cannot happen once the sums are exact; the arena must never be overrun)
     for (uint32_t y = 0; y < f; y++) lut[st + y] = make_uint2 ((uint32_t)tid | (f << 16), y);
     __syncthreads ();
     return sm.consumed;
@@ -287,7 +290,7 @@ __global__ void __launch_bounds__(256) k_dec_tables (DecLeaf *leaves, SectionRes
                 __syncthreads ();
                 if (tid == 0) {                                           // decode_freq_d (:324-355)
                     const uint8_t *q = sm.p;
-                    uint32_t T = 0; int zrun = 0; bool ok = q < fend;
+                    uint64_t T = 0; int zrun = 0; bool ok = q < fend;           // (64-bit: a varint is any 32-bit value, :1003)
                     for (int j = 0; ok && j < 256 && q < fend; j++) {
                         if (!sm.F0[j]) continue;
                         uint32_t f;
@@ -296,9 +299,10 @@ __global__ void __launch_bounds__(256) k_dec_tables (DecLeaf *leaves, SectionRes
                             q += get_varint (q, fend, &f);
                             if (!f) { if (q >= fend) { ok = false; break; } zrun = *q++; }
                         }
+                        if (f > (1u << shift)) ok = false;
                         sm.F[j] = f; T += f;
                     }
-                    sm.ok = ok; sm.T = T; sm.p = q;
+                    sm.ok = ok && T <= (1u << shift); sm.T = (uint32_t)(T <= (1u << shift) ? T : 0); sm.p = q;
                 }
                 __syncthreads ();
                 if (!sm.ok) { fail = true; break; }
@@ -311,6 +315,7 @@ __global__ void __launch_bounds__(256) k_dec_tables (DecLeaf *leaves, SectionRes
                     uint32_t total = scan_F (sm);
                     if (total != (1u << shift)) { fail = true; break; }
                     uint32_t f = sm.F[tid], st = sm.start[tid];
+                    if (st + f > (1u << shift)) f = 0;
                     uint32_t *srow = lut1 + ((size_t)row << shift);
                     const uint32_t base_e = (uint32_t)L.ctxrank[tid] | ((f - 1) << 8);
                     for (uint32_t y = 0; y < f; y++) srow[st + y] = base_e | (y << 20);

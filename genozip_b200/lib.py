@@ -427,6 +427,7 @@ class Engine:
             C.memmove(a.value_to_bin, np.ascontiguousarray(v2b, np.uint8).ctypes.data, 256)
             a.values = vals.ctypes.data; a.lens_be = lb.ctypes.data; a.qual_out = qo.ctypes.data
             a.missing = ms.ctypes.data if decode else None
+            a.n_bases = vals.size if (decode and values is not None) else 0
             a.qual_len = None if (ql is None or decode) else ql.ctypes.data
         return arr, keep
 

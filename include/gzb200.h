@@ -69,7 +69,8 @@ int   gzb_vb_device (uint32_t vblock_i, int n_devices);           /* (vblock_i-1
 uint64_t gzb_kernel_launches (gzb_engine *e);                     /* kernels launched by this engine so far */
 /* Device-time of the dominant chain kernels of the LAST batch call, ms (CUDA events on the engine's stream) */
 float gzb_last_chain_ms (gzb_engine *e);
-/* the same, split by coder: which = 0 rANS chain kernel, 1 arithmetic chain kernel */
+/* the same, split by coder: which = 0 rANS chain kernel, 1 arithmetic chain kernel; which = 2: the dominant kernel of the last
+ * PBWT / LONGR batch call (the row walk k_pbwt_rows, the channel walk k_longr_channels / k_longr_decode) */
 float gzb_last_kernel_ms (gzb_engine *e, int which);
 
 /* ---------------------------------------------------------------- simple codecs: rANS 4x16 and adaptive arithmetic
@@ -214,7 +215,8 @@ typedef struct {
                                    first byte is then '*' (sam_reconstruct_missing_quality, src/sam_qual.c:532) and the rest undefined */
     const uint32_t *qual_len;   /* encode, optional (n_lines): quality length where it differs from len — a SAM line without quality is the
                                    one byte ' ' whatever its seq_len (:188,:190-192); NULL = len */
-    uint64_t        n_bases;    /* with GZB_DEVICE_PTRS: the number of qualities in the VBlock (0 = take txt_len as the bound) */
+    uint64_t        n_bases;    /* the number of qualities in the VBlock = bytes of `values`.  Host pointers: 0 = sum(len); decode of a VBlock that
+                                   has lines without quality passes the length of VALUES.local.  GZB_DEVICE_PTRS: 0 = take txt_len as the bound */
 } gzb_longr_vb;
 int gzb_longr_encode (gzb_engine *e, gzb_longr_vb *vbs, uint32_t n_vbs, uint32_t flags);
 int gzb_longr_decode (gzb_engine *e, gzb_longr_vb *vbs, uint32_t n_vbs, uint32_t flags);

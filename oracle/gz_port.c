@@ -432,9 +432,11 @@ void orc_longr_calc_bins (const uint32_t histogram[256], uint64_t num_values, ui
     memset (v2b + next_val, 31, 256 - next_val);
 }
 
-int orc_longr_encode (const uint8_t *txt, const uint64_t *seq_off, const uint64_t *qual_off, const uint32_t *len,
-                      const uint8_t *is_rev, uint32_t n_lines, const uint8_t v2b[256],
-                      uint8_t *values, uint32_t *lens_be)                             /* codec_longr.c:161-247 */
+/* len = quality length of each line; seq_len (NULL = len) its sequence length where that differs: a SAM line without quality
+   is the single byte ' ' whatever its seq_len (codec_longr.c:188-192) */
+int orc_longr_encode2 (const uint8_t *txt, const uint64_t *seq_off, const uint64_t *qual_off, const uint32_t *len, const uint32_t *seq_len,
+                       const uint8_t *is_rev, uint32_t n_lines, const uint8_t v2b[256],
+                       uint8_t *values, uint32_t *lens_be)                            /* codec_longr.c:161-247 */
 {
     LrState s; lr_init (&s, v2b);
     uint64_t total = 0;
@@ -447,13 +449,14 @@ int orc_longr_encode (const uint8_t *txt, const uint64_t *seq_off, const uint64_
         if (!L) continue;
         const uint8_t *seq = txt + seq_off[li], *q = txt + qual_off[li];
         int rev = is_rev ? is_rev[li] : 0;
-        lr_init_read (&s, seq, L, rev);
+        const uint32_t Ls = seq_len ? seq_len[li] : L;
+        lr_init_read (&s, seq, Ls, rev);
         uint8_t prev = 0;
         for (uint32_t k = 0; k < L; k++) {
             uint32_t i = rev ? L - 1 - k : k;
             uint32_t ch = LR_CHAN (s.chan);
             base_chan[nb++] = (uint16_t)ch; num[ch]++;
-            uint8_t b = rev ? acgt_code_comp (i >= 3 ? seq[i - 3] : 'T') : acgt_code (i + 3 < L ? seq[i + 3] : 'A');
+            uint8_t b = rev ? acgt_code_comp (i >= 3 ? seq[i - 3] : 'T') : acgt_code (i + 3 < Ls ? seq[i + 3] : 'A');
             uint8_t qq = (uint8_t)(q[i] - '!');
             lr_update (&s, b, qq, prev);
             prev = qq;
@@ -474,9 +477,27 @@ int orc_longr_encode (const uint8_t *txt, const uint64_t *seq_off, const uint64_
     return 0;
 }
 
+int orc_longr_encode (const uint8_t *txt, const uint64_t *seq_off, const uint64_t *qual_off, const uint32_t *len,
+                      const uint8_t *is_rev, uint32_t n_lines, const uint8_t v2b[256],
+                      uint8_t *values, uint32_t *lens_be)
+{
+    return orc_longr_encode2 (txt, seq_off, qual_off, len, NULL, is_rev, n_lines, v2b, values, lens_be);
+}
+
+/* missing (NULL or n_lines bytes): set where a line has no quality — its first value is 255 (codec_longr.c:278): the line takes
+   that one value, its first output byte is '*' (sam_reconstruct_missing_quality, sam_qual.c:532) and the rest is left alone */
+int orc_longr_decode2 (const uint8_t *txt, const uint64_t *seq_off, const uint32_t *len, const uint8_t *is_rev,
+                       uint32_t n_lines, const uint8_t v2b[256],
+                       const uint8_t *values, const uint32_t *lens_be, uint8_t *qual_out, uint8_t *missing);
 int orc_longr_decode (const uint8_t *txt, const uint64_t *seq_off, const uint32_t *len, const uint8_t *is_rev,
                       uint32_t n_lines, const uint8_t v2b[256],
-                      const uint8_t *values, const uint32_t *lens_be, uint8_t *qual_out)   /* codec_longr.c:270-373 */
+                      const uint8_t *values, const uint32_t *lens_be, uint8_t *qual_out)
+{
+    return orc_longr_decode2 (txt, seq_off, len, is_rev, n_lines, v2b, values, lens_be, qual_out, NULL);
+}
+int orc_longr_decode2 (const uint8_t *txt, const uint64_t *seq_off, const uint32_t *len, const uint8_t *is_rev,
+                       uint32_t n_lines, const uint8_t v2b[256],
+                       const uint8_t *values, const uint32_t *lens_be, uint8_t *qual_out, uint8_t *missing)   /* codec_longr.c:270-373 */
 {
     LrState s; lr_init (&s, v2b);
     uint32_t *next = malloc (65536 * sizeof (uint32_t));                              /* reconstruct_init :301-338 */
@@ -493,6 +514,7 @@ int orc_longr_decode (const uint8_t *txt, const uint64_t *seq_off, const uint32_
             uint8_t b = rev ? acgt_code_comp (i >= 3 ? seq[i - 3] : 'T') : acgt_code (i + 3 < L ? seq[i + 3] : 'A');
             uint8_t qq = values[next[LR_CHAN (s.chan)]++];
             lr_update (&s, b, qq, prev);
+            if (missing && qq == 255) { missing[li] = 1; qual_out[0] = '*'; break; }   /* RECON_ONE_QUAL: after the state update */
             prev = qq;
             qual_out[i] = (uint8_t)(qq + '!');
         }

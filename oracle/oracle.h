@@ -88,6 +88,10 @@ int  orc_pbwt_decode (uint32_t *runs, uint32_t n_runs, uint32_t *fgrc, uint32_t 
 /* LONGR (codec_longr.c, codec_longr_alg.c) */
 void orc_longr_calc_bins (const uint32_t histogram[256], uint64_t num_values, uint8_t value_to_bin[256]); /* codec_longr.c:66-136 */
 /* :161-247: lens_be = 65536 big-endian u32; values = n_quals bytes; is_rev may be NULL */
+int  orc_longr_decode2 (const uint8_t *txt, const uint64_t *seq_off, const uint32_t *len, const uint8_t *is_rev, uint32_t n_lines,
+                        const uint8_t v2b[256], const uint8_t *values, const uint32_t *lens_be, uint8_t *qual_out, uint8_t *missing);
+int  orc_longr_encode2 (const uint8_t *txt, const uint64_t *seq_off, const uint64_t *qual_off, const uint32_t *len, const uint32_t *seq_len,
+                        const uint8_t *is_rev, uint32_t n_lines, const uint8_t v2b[256], uint8_t *values, uint32_t *lens_be);
 int  orc_longr_encode (const uint8_t *txt, const uint64_t *seq_off, const uint64_t *qual_off, const uint32_t *len,
                        const uint8_t *is_rev, uint32_t n_lines, const uint8_t value_to_bin[256],
                        uint8_t *values, uint32_t *lens_be);

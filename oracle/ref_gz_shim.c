@@ -246,7 +246,7 @@ int ref_acgt_pack (const uint8_t *seq, uint64_t n, uint8_t *packed, uint64_t *pa
 }
 
 // ================================================================ LONGR
-static const uint64_t *g_seq_off; static const uint8_t *g_is_rev;
+static const uint64_t *g_seq_off; static const uint8_t *g_is_rev; static const uint32_t *g_seq_len;
 static COMPRESSOR_CALLBACK (shim_get_qual_rev)
 {
     *line_data = (char *)g_txt + g_off[vb_line_i];
@@ -256,15 +256,23 @@ static COMPRESSOR_CALLBACK (shim_get_qual_rev)
 static void shim_get_seq (VBlockP vb, LineIType vb_line_i, char **line_data, uint32_t *line_data_len, bool *is_rev)
 {
     *line_data = (char *)g_txt + g_seq_off[vb_line_i];
-    *line_data_len = g_len[vb_line_i];
+    *line_data_len = (g_seq_len ? g_seq_len : g_len)[vb_line_i];
     if (is_rev) *is_rev = g_is_rev ? g_is_rev[vb_line_i] : 0;
 }
 COMPRESSOR_CALLBACK (fastq_zip_seq) { shim_get_seq (vb, vb_line_i, line_data, line_data_len, is_rev); }
 COMPRESSOR_CALLBACK (sam_zip_seq)   { shim_get_seq (vb, vb_line_i, line_data, line_data_len, is_rev); }
 
 // txt holds the SEQ and QUAL strings; is_rev NULL = FASTQ (never reverse-complemented), else SAM-like per-line flags
+// seq_len (NULL = len): sequence lengths where they differ from the quality lengths — a SAM line without quality is ' ' (:188-192)
+int ref_longr_encode2 (const uint8_t *txt, uint64_t txt_len, const uint64_t *seq_off, const uint64_t *qual_off, const uint32_t *len, const uint32_t *seq_len,
+                       const uint8_t *is_rev, uint32_t n_lines, uint8_t *value_to_bin, uint8_t *values, uint32_t *lens_be);
 int ref_longr_encode (const uint8_t *txt, uint64_t txt_len, const uint64_t *seq_off, const uint64_t *qual_off, const uint32_t *len, const uint8_t *is_rev,
                       uint32_t n_lines, uint8_t *value_to_bin, uint8_t *values, uint32_t *lens_be)
+{
+    return ref_longr_encode2 (txt, txt_len, seq_off, qual_off, len, NULL, is_rev, n_lines, value_to_bin, values, lens_be);
+}
+int ref_longr_encode2 (const uint8_t *txt, uint64_t txt_len, const uint64_t *seq_off, const uint64_t *qual_off, const uint32_t *len, const uint32_t *seq_len,
+                       const uint8_t *is_rev, uint32_t n_lines, uint8_t *value_to_bin, uint8_t *values, uint32_t *lens_be)
 {
     shim_init ();
     if (setjmp (on_abort)) return -1;
@@ -272,7 +280,7 @@ int ref_longr_encode (const uint8_t *txt, uint64_t txt_len, const uint64_t *seq_
     evb = calloc (1, sizeof (VBlock));
     vb->vblock_i = 1; vb->lines.len = n_lines;
     vb->data_type = is_rev ? DT_SAM : DT_FASTQ;
-    g_txt = malloc (txt_len + 1); memcpy (g_txt, txt, txt_len); g_off = qual_off; g_seq_off = seq_off; g_len = len; g_is_rev = is_rev;
+    g_txt = malloc (txt_len + 1); memcpy (g_txt, txt, txt_len); g_off = qual_off; g_seq_off = seq_off; g_len = len; g_is_rev = is_rev; g_seq_len = seq_len;
     vb->txt_data.len = txt_len;                                            // Ltxt: the callbacks' size limit
     uint64_t total = 0;
     for (uint32_t i = 0; i < n_lines; i++) total += len[i];

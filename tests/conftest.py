@@ -8,6 +8,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "fullsize: BASELINE-config-size input (GPU only; skipped on the emulator / mock)")
     if config.getoption("--simt"):
         sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "host", "simt"))
         import build as simt_build
@@ -36,3 +37,5 @@ def pytest_collection_modifyitems(config, items):
         for it in items:
             if "test_gpu_fastq_path" in it.nodeid:
                 it.add_marker(skip)
+            if "fullsize" in it.keywords:
+                it.add_marker(pytest.mark.skip(reason="--dry-gpu / --simt: BASELINE-size inputs are for the GPU"))

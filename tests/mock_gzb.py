@@ -86,6 +86,30 @@ class MockLib:
         hl._obj.value = size
         return 0
 
+    def gzb_pbwt_encode_batch(self, h, arr, n, flags):
+        rc = 0
+        for i in range(n):
+            a = arr[i]
+            r, f = orc.pbwt_encode(_view(a.ht, a.n_lines * a.ht_per_line).reshape(a.n_lines, a.ht_per_line))
+            if r.size > a.runs_cap or f.size > a.fgrc_cap:
+                a.status = -3; rc = rc or -3; self.err = "PBWT: RUNS/FGRC capacity too small"
+                continue
+            _view(a.runs, r.size, np.uint32)[:] = r; _view(a.fgrc, f.size, np.uint32)[:] = f
+            a.n_runs, a.n_fgrc, a.status = r.size, f.size, 0
+        return rc
+
+    def gzb_pbwt_decode_batch(self, h, arr, n, flags):
+        for i in range(n):
+            a = arr[i]
+            runs, fgrc = _view(a.runs, a.n_runs, np.uint32), _view(a.fgrc, a.n_fgrc, np.uint32)
+            size = int(fgrc[-2]) | (int(fgrc[-1]) << 32)
+            if int(runs.sum(dtype=np.uint64)) < size or size > a.ht_cap:
+                a.status = -4; self.err = "PBWT: runs do not cover the matrix"
+                return -4
+            _view(a.ht, size)[:] = orc.pbwt_decode(runs, fgrc, a.n_lines, size)
+            a.ht_len, a.status = size, 0
+        return 0
+
     def _longr(self, a):
         n = a.n_lines
         ln = _view(a.len, n, np.uint32)
@@ -96,15 +120,35 @@ class MockLib:
         for i in range(n):
             a = arr[i]
             txt, so, qo, ln, rv, v2b, tot = self._longr(a)
-            vals, lb = orc.longr_encode(txt, so, qo, ln, rv, v2b)
-            _view(a.values, tot)[:] = vals; _view(a.lens_be, 65536, np.uint32)[:] = lb
+            ql = _view(a.qual_len, a.n_lines, np.uint32) if a.qual_len else None
+            vals, lb = orc.longr_encode(txt, so, qo, ln, rv, v2b) if ql is None else orc.longr_encode(txt, so, qo, ql, rv, v2b, seq_lens=ln)
+            _view(a.values, vals.size)[:] = vals; _view(a.lens_be, 65536, np.uint32)[:] = lb
         return 0
 
     def gzb_longr_decode(self, h, arr, n, flags):
+        """line by line, like codec_longr_reconstruct: a line whose first value is 255 has no quality and takes that one value"""
         for i in range(n):
             a = arr[i]
             txt, so, qo, ln, rv, v2b, tot = self._longr(a)
-            _view(a.qual_out, tot)[:] = orc.longr_decode(txt, so, ln, rv, v2b, _view(a.values, tot), _view(a.lens_be, 65536, np.uint32))
+            lb = _view(a.lens_be, 65536, np.uint32)
+            nvals = int(lb.byteswap().sum(dtype=np.uint64))
+            if nvals != (a.n_bases or tot):
+                self.err = "LONGR: channel lengths do not add up to the number of qualities"
+                return -4
+            out, miss = orc.longr_decode_lines(txt, so, ln, rv, v2b, _view(a.values, nvals), lb)
+            _view(a.qual_out, tot)[:] = out
+            if a.missing:
+                _view(a.missing, a.n_lines)[:] = miss
+        return 0
+
+    def gzb_longr_calculate_bins(self, h, arr, flags, v2b):
+        a = arr[0]
+        txt, so, qo, ln, rv, _, tot = self._longr(a)
+        ql = _view(a.qual_len, a.n_lines, np.uint32) if a.qual_len else ln
+        parts = [txt[int(o): int(o) + int(l)] for o, l in zip(qo, ql) if l and not (l == 1 and txt[int(o)] == 32)]
+        if not parts:
+            return 1
+        _view(v2b, 256)[:] = orc.longr_bins(np.concatenate(parts))
         return 0
 
     # ---- ACGT

@@ -59,6 +59,8 @@ def port():
         L.orc_pbwt_decode.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, u64p]
         L.orc_longr_calc_bins.restype = None
         L.orc_longr_calc_bins.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+        L.orc_longr_encode2.restype = C.c_int
+        L.orc_longr_encode2.argtypes = [C.c_void_p] * 6 + [C.c_uint32] + [C.c_void_p] * 3
         L.orc_longr_encode.restype = C.c_int
         L.orc_longr_encode.argtypes = [C.c_void_p] * 5 + [C.c_uint32] + [C.c_void_p] * 3
         L.orc_longr_decode.restype = C.c_int
@@ -114,6 +116,8 @@ def gz_ref():
         L.ref_acgt_pack.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, u64p, C.c_void_p, C.POINTER(C.c_int)]
         L.ref_pbwt_encode.restype = C.c_int
         L.ref_pbwt_encode.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, u32p, C.c_void_p, u32p]
+        L.ref_longr_encode2.restype = C.c_int
+        L.ref_longr_encode2.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_longr_encode.restype = C.c_int
         L.ref_longr_encode.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         for f in ("ref_acgt_unpack", "ref_pbwt_decode", "ref_domq_decode", "ref_longr_decode"):
@@ -255,15 +259,17 @@ def ref_pbwt_encode(ht):
     return runs[:nr.value].copy(), fgrc[:nf.value].copy()
 
 
-def ref_longr_encode(txt, seq_off, qual_off, lens, is_rev):
-    """the REFERENCE's compiled codec_longr_segconf_calculate_bins + codec_longr_compress -> (value_to_bin, values, lens_be)"""
+def ref_longr_encode(txt, seq_off, qual_off, lens, is_rev, seq_lens=None):
+    """the REFERENCE's compiled codec_longr_segconf_calculate_bins + codec_longr_compress -> (value_to_bin, values, lens_be);
+    lens = quality lengths, seq_lens = sequence lengths where they differ (lines without quality)"""
     txt = np.ascontiguousarray(txt, np.uint8); seq_off = np.ascontiguousarray(seq_off, np.uint64)
     qual_off = np.ascontiguousarray(qual_off, np.uint64); lens = np.ascontiguousarray(lens, np.uint32)
     rv = None if is_rev is None else np.ascontiguousarray(is_rev, np.uint8)
     tot = int(lens.sum())
     v2b = np.zeros(256, np.uint8); values = np.zeros(tot + 8, np.uint8); lens_be = np.zeros(65536, np.uint32)
-    _gz_check(gz_ref().ref_longr_encode(_ptr(txt), txt.size, _ptr(seq_off), _ptr(qual_off), _ptr(lens), None if rv is None else _ptr(rv),
-                                        lens.size, _ptr(v2b), _ptr(values), _ptr(lens_be)), "codec_longr")
+    sl = None if seq_lens is None else np.ascontiguousarray(seq_lens, np.uint32)
+    _gz_check(gz_ref().ref_longr_encode2(_ptr(txt), txt.size, _ptr(seq_off), _ptr(qual_off), _ptr(lens), None if sl is None else _ptr(sl),
+                                         None if rv is None else _ptr(rv), lens.size, _ptr(v2b), _ptr(values), _ptr(lens_be)), "codec_longr")
     return v2b, values[:tot].copy(), lens_be
 
 
@@ -350,14 +356,29 @@ def longr_bins(qual):
     return v2b
 
 
-def longr_encode(txt, seq_off, qual_off, lens, is_rev, v2b):
+def longr_encode(txt, seq_off, qual_off, lens, is_rev, v2b, seq_lens=None):
     n = lens.size
     tot = int(lens.sum())
     values = np.zeros(tot + 1, np.uint8); lens_be = np.zeros(65536, np.uint32)
-    rc = port().orc_longr_encode(_ptr(txt), _ptr(seq_off), _ptr(qual_off), _ptr(lens), None if is_rev is None else _ptr(is_rev), n,
-                                 _ptr(v2b), _ptr(values), _ptr(lens_be))
+    sl = None if seq_lens is None else np.ascontiguousarray(seq_lens, np.uint32)
+    rc = port().orc_longr_encode2(_ptr(txt), _ptr(seq_off), _ptr(qual_off), _ptr(lens), None if sl is None else _ptr(sl),
+                                  None if is_rev is None else _ptr(is_rev), n, _ptr(v2b), _ptr(values), _ptr(lens_be))
     assert rc == 0
     return values[:tot].copy(), lens_be
+
+
+def longr_decode_lines(txt, seq_off, lens, is_rev, v2b, values, lens_be):
+    """the decoder with the missing-quality rule -> (qualities, missing flag per line)"""
+    L = port()
+    L.orc_longr_decode2.restype = C.c_int
+    L.orc_longr_decode2.argtypes = [C.c_void_p] * 4 + [C.c_uint32] + [C.c_void_p] * 5
+    tot = int(lens.sum())
+    out = np.zeros(tot + 1, np.uint8); miss = np.zeros(lens.size + 1, np.uint8)
+    v = np.ascontiguousarray(values, np.uint8) if values.size else np.zeros(1, np.uint8)
+    rc = L.orc_longr_decode2(_ptr(txt), _ptr(seq_off), _ptr(lens), None if is_rev is None else _ptr(is_rev), lens.size,
+                             _ptr(v2b), _ptr(v), _ptr(np.ascontiguousarray(lens_be, np.uint32)), _ptr(out), _ptr(miss))
+    assert rc == 0
+    return out[:tot], miss[:lens.size]
 
 
 def longr_decode(txt, seq_off, lens, is_rev, v2b, values, lens_be):

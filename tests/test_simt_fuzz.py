@@ -105,3 +105,19 @@ def test_order1_context_without_frequencies_is_defined(eng):
             outs.append(None)
         eng.compress([("RANB", np.random.default_rng(len(outs)).integers(0, 256, 30000, dtype=np.uint8))])   # other traffic through the arena
     assert all((o is None) == (outs[0] is None) and (o is None or np.array_equal(o, outs[0])) for o in outs)
+
+
+def test_frequency_sums_that_wrap_are_refused(eng):
+    """a varint is any 32-bit value: F['A'] = 0xFFFFFFFF and F['C'] = 4097 sum to 4096 modulo 2^32.  The reference checks every
+    frequency against what is left of the table (rANS_static4x16pr.c:538, :1003-1005); a table build that only looks at the
+    32-bit total would fill billions of LUT slots past its arena"""
+    states = [0, 128, 0, 0] * 4
+    o0 = [0x00, 100, 0x41, 0x43, 0x00, 0x8F, 0xFF, 0xFF, 0xFF, 0x7F, 0xA0, 0x01] + states
+    assert _rejects(eng, "RANB", o0, 100)
+    with pytest.raises(AssertionError):
+        orc.uncompress("ref", "rans", np.array(o0, np.uint8), 100)
+    ctl = [0x00, 100, 0x41, 0x43, 0x00, 0x90, 0x00, 0x90, 0x00] + states       # the control: 2048 / 2048 decodes
+    assert eng.uncompress([("RANB", np.array(ctl, np.uint8), 100)])[0].size == 100
+    # order 1: alphabet {0, 65}; context 0's row carries the wrapping pair
+    o1 = [0x01, 40, 0xC0, 0, 65, 0] + [0x8F, 0xFF, 0xFF, 0xFF, 0x7F, 0xA0, 0x01] + [0x90, 0x00, 0x90, 0x00] + states
+    assert _rejects(eng, "RANb", o1, 40)
