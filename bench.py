@@ -300,10 +300,10 @@ def run_gpu(args):
             with torch.cuda.stream(stream):
                 e0.record(stream)
                 m = fn_zip()
-                section_list_gather(m if isinstance(m, list) else m[0])
+                section_list_gather(m[0] if isinstance(m, tuple) else m)
                 kz = path.kernel_ms
                 e1.record(stream)
-                r = fn_piz(m if isinstance(m, list) else m[0])
+                r = fn_piz(m[0] if isinstance(m, tuple) else m)
                 kp = path.kernel_ms
                 e2.record(stream)
             barrier()

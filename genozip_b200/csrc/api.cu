@@ -226,14 +226,17 @@ int pick_arith_lpw (uint32_t n) { int l = 1; while (l < 32 && (uint64_t)n > 9472
 
 } // namespace
 
-extern "C" int gzb_compress_sections (gzb_engine *e, gzb_section *secs, uint32_t n, uint32_t flags)
+namespace { struct PackOut { void *arena; uint64_t cap; uint64_t *used; bool dev; }; }
+
+static int compress_impl (gzb_engine *e, gzb_section *secs, uint32_t n, uint32_t flags, const PackOut *pk)
 {
     if (!e) return GZB_E_BADARG;
+    if (pk && pk->used) *pk->used = 0;
     if (!n) return GZB_OK;
     cudaSetDevice (e->device);
     const bool devall = flags & GZB_DEVICE_PTRS;
     auto in_dev  = [&] (uint32_t i) { return devall || (secs[i].sflags & GZB_SEC_IN_DEVICE); };
-    auto out_dev = [&] (uint32_t i) { return devall || (secs[i].sflags & GZB_SEC_OUT_DEVICE); };
+    auto out_dev = [&] (uint32_t i) { return pk ? true : (devall || (secs[i].sflags & GZB_SEC_OUT_DEVICE)); };   // (packed: no per-section staging)
 
     // ---- plan on the host
     std::vector<EncSection> hs (n);
@@ -246,9 +249,10 @@ extern "C" int gzb_compress_sections (gzb_engine *e, gzb_section *secs, uint32_t
     for (uint32_t i = 0; i < n; i++) {
         gzb_section &s = secs[i];
         uint8_t coder, order;
-        if (!codec_info (s.codec, &coder, &order) || (!s.in && s.in_len) || !s.out) { s.status = GZB_E_BADARG; e->err = "bad section"; return GZB_E_BADARG; }
+        if (!codec_info (s.codec, &coder, &order) || (!s.in && s.in_len) || (!s.out && !pk)) { s.status = GZB_E_BADARG; e->err = "bad section"; return GZB_E_BADARG; }
         EncSection &S = hs[i];
         memset (&S, 0, sizeof S);
+        if (pk) s.out_cap = gzb_est_size (s.codec, s.in_len);                 // packed: the buffer as a whole has a capacity, a section has none
         S.n = s.in_len; S.coder = coder; S.order = order; S.out_cap = s.out_cap;
         S.soft_fail = s.out_cap < gzb_est_size (s.codec, s.in_len);           // the reference returns NULL → false under soft_fail
         S.stripe = (order & F_STRIPE) && S.n > 20;
@@ -336,6 +340,8 @@ extern "C" int gzb_compress_sections (gzb_engine *e, gzb_section *secs, uint32_t
             P.results      = c.take<SectionResult> (n);
             P.segs         = c.take<CopySeg> ((size_t)n * 16);
             P.stripe_hdr   = c.take<uint8_t> ((size_t)n * 32);
+            if (pk) { P.pack_off = c.take<unsigned long long> ((size_t)n + 1); P.pack_cap = pk->cap;
+                      P.pack_arena = pk->dev ? (uint8_t *)pk->arena : c.take<uint8_t> (pk->cap + 16); }
             d_cursor       = c.take<unsigned long long> (1);
             d_overflow     = c.take<int> (1);
             d_hist0        = c.take<uint32_t> ((size_t)(nl ? nl : 1) * 256);
@@ -363,7 +369,8 @@ extern "C" int gzb_compress_sections (gzb_engine *e, gzb_section *secs, uint32_t
                 if (S.soft_fail) continue;
                 if (in_dev (i)) S.in = (const uint8_t *)secs[i].in;
                 else { S.in = d_in + io; io += (S.n + 15) & ~15ull; }
-                if (out_dev (i)) S.out = (uint8_t *)secs[i].out;
+                if (pk) S.out = nullptr;                                  // destinations relative to the section until k_pack_place
+                else if (out_dev (i)) S.out = (uint8_t *)secs[i].out;
                 else { S.out = d_out + oo; oo += ((size_t)std::min<uint32_t> (secs[i].out_cap, gzb_est_size (secs[i].codec, secs[i].in_len)) + 15) & ~15ull; }
                 if (S.stripe) S.planes = d_planes + (size_t)hs[i].planes;
                 uint32_t cnt = S.stripe ? ((S.n_leaves & 15) + ((S.n_leaves >> 4) & 15) + ((S.n_leaves >> 8) & 15) + ((S.n_leaves >> 12) & 15)) : 1;
@@ -434,6 +441,20 @@ extern "C" int gzb_compress_sections (gzb_engine *e, gzb_section *secs, uint32_t
             secs[i].status = res[i].status; secs[i].out_len = res[i].out_len;
             if (res[i].status == 0 && res[i].out_len > secs[i].out_cap) { secs[i].status = GZB_SOFT_FAIL; secs[i].out_len = 0; }
         }
+        if (pk) {
+            std::vector<unsigned long long> off ((size_t)n + 1);
+            CK (cudaMemcpyAsync (off.data (), P.pack_off, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, st));
+            CK (cudaStreamSynchronize (st));
+            if (pk->used) *pk->used = off[n];
+            if (off[n] > pk->cap) {                                          // nothing was written: the caller grows the buffer and calls again
+                for (uint32_t i = 0; i < n; i++) { secs[i].status = GZB_SOFT_FAIL; secs[i].out_len = 0; secs[i].out = nullptr; }
+                e->err = "packed output: the buffer is too small";
+                return GZB_SOFT_FAIL;
+            }
+            for (uint32_t i = 0; i < n; i++) secs[i].out = (uint8_t *)pk->arena + off[i];
+            if (!pk->dev && off[n]) { CK (cudaMemcpyAsync (pk->arena, P.pack_arena, off[n], cudaMemcpyDeviceToHost, st)); CK (cudaStreamSynchronize (st)); }
+            return GZB_OK;
+        }
         bool any_d2h = false;
         for (uint32_t i = 0; i < n; i++)
             if (!out_dev (i) && secs[i].status == 0 && secs[i].out_len) {
@@ -445,6 +466,49 @@ extern "C" int gzb_compress_sections (gzb_engine *e, gzb_section *secs, uint32_t
     }
     e->err = "device arena kept overflowing";
     return GZB_E_CUDA;
+}
+
+extern "C" int gzb_compress_sections (gzb_engine *e, gzb_section *secs, uint32_t n, uint32_t flags) { return compress_impl (e, secs, n, flags, nullptr); }
+
+extern "C" int gzb_compress_sections_packed (gzb_engine *e, gzb_section *secs, uint32_t n, void *arena, uint64_t arena_cap, uint64_t *arena_used, uint32_t flags)
+{
+    if (!arena && arena_cap) return GZB_E_BADARG;
+    PackOut pk { arena, arena_cap, arena_used, (flags & (GZB_DEVICE_PTRS | GZB_OUT_DEVICE)) != 0 };
+    return compress_impl (e, secs, n, flags, &pk);
+}
+
+// ------------------------------------------------------------------------------------------------ batched copies on the device
+namespace {
+__global__ void k_copy_batch (const gzb_copy *cp, uint32_t n)
+{
+    if (blockIdx.x >= n) return;
+    const gzb_copy c = cp[blockIdx.x];
+    const uint8_t *s = (const uint8_t *)c.src; uint8_t *d = (uint8_t *)c.dst;
+    const uint64_t part = ((c.len + gridDim.y - 1) / gridDim.y + 15) & ~15ull, b = blockIdx.y * part, en = b + part < c.len ? b + part : c.len;
+    if (b >= en) return;
+    if ((((uintptr_t)s | (uintptr_t)d) & 15) == 0) {
+        const uint64_t n16 = (en - b) >> 4;
+        for (uint64_t i = threadIdx.x; i < n16; i += blockDim.x) reinterpret_cast<uint4 *>(d + b)[i] = reinterpret_cast<const uint4 *>(s + b)[i];
+        for (uint64_t i = b + (n16 << 4) + threadIdx.x; i < en; i += blockDim.x) d[i] = s[i];
+    }
+    else for (uint64_t i = b + threadIdx.x; i < en; i += blockDim.x) d[i] = s[i];
+}
+}
+
+extern "C" int gzb_copy_batch (gzb_engine *e, const gzb_copy *copies, uint32_t n)
+{
+    if (!e || (!copies && n)) return GZB_E_BADARG;
+    if (!n) return GZB_OK;
+    cudaSetDevice (e->device);
+    int rc = engine_reserve (e, (size_t)n * sizeof (gzb_copy) + 256, (size_t)n * sizeof (gzb_copy) + 256); if (rc) return rc;
+    memcpy (e->pin, copies, (size_t)n * sizeof (gzb_copy));
+    CK (cudaMemcpyAsync (e->ws, e->pin, (size_t)n * sizeof (gzb_copy), cudaMemcpyHostToDevice, e->stream));
+    uint64_t longest = 0; for (uint32_t i = 0; i < n; i++) longest = std::max<uint64_t> (longest, copies[i].len);
+    const uint32_t parts = (uint32_t)std::min<uint64_t> (64, std::max<uint64_t> (1, longest >> 16));
+    k_copy_batch<<<dim3 (n, parts), 256, 0, e->stream>>>(reinterpret_cast<const gzb_copy *>(e->ws), n); e->launches++;
+    CK (cudaStreamSynchronize (e->stream));                                 // (the pinned staging and the workspace are reused by the next call)
+    CK (cudaGetLastError ());
+    return GZB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ uncompress

@@ -716,6 +716,42 @@ __global__ void k_section_final (const EncSection *secs, const EncLeaf *leaves, 
     res[si].out_len = (uint32_t)(dst - S.out); res[si].status = 0;
 }
 
+// packed output: the sections of a batch are appended to one buffer in section order, as zfile_compress_local_data appends
+// a section to vb->z_data (src/zfile.c:229-262).  One CTA: offsets = exclusive prefix of the 16-byte aligned section lengths;
+// the copy plan's destinations (relative to their section while S.out is NULL) are then moved into the buffer.  If the batch
+// does not fit, nothing is copied and the host reports the size that is needed.
+__global__ void __launch_bounds__(1024) k_pack_place (const SectionResult *res, CopySeg *segs, unsigned long long *off, uint32_t n_secs,
+                                                      uint8_t *arena, unsigned long long cap)
+{
+    __shared__ unsigned long long sm[33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long acc = 0;
+    for (uint32_t base = 0; base < n_secs; base += 1024) {
+        const uint32_t si = base + threadIdx.x;
+        const unsigned long long v = si < n_secs && res[si].status == 0 ? ((unsigned long long)res[si].out_len + 15ull) & ~15ull : 0;
+        unsigned long long inc = v;
+        for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync (0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) sm[warp] = inc;
+        __syncthreads ();
+        if (warp == 0) {
+            const unsigned long long x = sm[lane]; unsigned long long xi = x;
+            for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync (0xffffffffu, xi, o); if (lane >= o) xi += t; }
+            sm[lane] = xi - x;
+            if (lane == 31) sm[32] = xi;
+        }
+        __syncthreads ();
+        if (si < n_secs) off[si] = acc + sm[warp] + inc - v;
+        acc += sm[32];
+        __syncthreads ();
+    }
+    if (threadIdx.x == 0) off[n_secs] = acc;
+    const bool fits = acc <= cap;
+    for (uint32_t k = threadIdx.x; k < n_secs * SEGS_PER_SECTION; k += 1024) {
+        if (!fits) segs[k].len = 0;
+        else if (segs[k].len) segs[k].dst = arena + off[k / SEGS_PER_SECTION] + (size_t)segs[k].dst;
+    }
+}
+
 // grid (n_segs, parts): each segment is split into gridDim.y parts
 __global__ void k_copy_segs (const CopySeg *segs, uint32_t n_segs)
 {
@@ -765,6 +801,7 @@ void enc_run (EncPlanDev &P, cudaStream_t st)
     if (P.n_arith) { cudaStreamWaitEvent (st, P.ev_chain2, 0); cudaStreamWaitEvent (st, P.ev_o0, 0); }
     LAUNCH (k_leaf_final, (nl + 127) / 128, 128, P.leaves, P.dyn, nl);
     LAUNCH (k_section_final, (ns + 127) / 128, 128, P.sections, P.leaves, P.dyn, P.results, P.segs, P.stripe_hdr, ns);
+    if (P.pack_off) LAUNCH (k_pack_place, 1, 1024, P.results, P.segs, P.pack_off, ns, P.pack_arena, P.pack_cap);
     dim3 g (ns * SEGS_PER_SECTION, P.copy_parts);
     k_copy_segs<<<g, 256, 0, st>>>(P.segs, ns * SEGS_PER_SECTION); P.launches++;
 }

@@ -16,6 +16,8 @@ struct EncPlanDev {              // device pointers of one encode batch
     SectionResult *results;
     CopySeg       *segs;
     uint8_t       *stripe_hdr;
+    uint8_t       *pack_arena;                            // packed output (gzb_compress_sections_packed): sections are appended to this
+    unsigned long long pack_cap, *pack_off;               //   buffer, 16-byte aligned; pack_off[n_sections] = offset of each, [n_sections] = total
     Arena          arena;
     int            rans_gpw, arith_lpw, copy_parts;
     bool           any_pack, any_o1;

@@ -19,7 +19,7 @@ import torch
 
 from concurrent.futures import ThreadPoolExecutor
 
-from .lib import (load, Engine, Section, DomqVb, DomqPizVb, AcgtVb, CODEC, est_size, GzbError,
+from .lib import (load, Engine, Section, DomqVb, DomqPizVb, AcgtVb, Copy, CODEC, est_size, GzbError,
                   GZB_DEVICE_PTRS, GZB_OUT_DEVICE, GZB_IN_DEVICE, GZB_SEC_IN_DEVICE, GZB_SEC_OUT_DEVICE)
 
 NAME_LEN = 45            # "@A00123:45:HXXXXXXXX:1:1101:12345:12345 1:N:0:ACGT" without the newline ~ 45-50
@@ -78,54 +78,111 @@ def _pin(t):
     return t.pin_memory() if torch.cuda.is_available() else t
 
 
+S_IDX = {s: i for i, s in enumerate(STREAMS)}
+DQ = ("QUAL", "DOMQRUNS", "QUALMPLX", "DIVRQUAL")                            # the four streams codec_domq_compress hands on
+DQ_FLD = ("qual", "runs", "mplx", "divr")
+NAMES = ("Q_TILE", "Q_X", "Q_Y", "Q_MISC")
+
+
+def struct_view(arr):
+    """numpy structured view of a ctypes Structure array (shares memory): descriptor arrays are filled column-wise, not field by field"""
+    T = arr._type_
+    names, formats, offsets = [], [], []
+    for name, ct in T._fields_:
+        names.append(name); offsets.append(getattr(T, name).offset)
+        if issubclass(ct, C.Array):
+            formats.append((np.uint8, (ct._length_,)))
+        else:
+            formats.append("i4" if ct is C.c_int32 else {1: "u1", 2: "u2", 4: "u4", 8: "u8"}[C.sizeof(ct)])
+    dt = np.dtype(dict(names=names, formats=formats, offsets=offsets, itemsize=C.sizeof(T)))
+    return np.frombuffer(arr, dtype=dt)
+
+
+class ZipMeta:
+    """what a zip pass leaves behind for the piz pass and the section list: per VBlock and stream the uncompressed length, the
+    compressed length and where the compressed section lies (address inside the packed output buffer)."""
+
+    def __init__(self, V):
+        self.V = V
+        self.len = np.zeros((V, len(STREAMS)), np.int64)
+        self.comp_len = np.zeros((V, len(STREAMS)), np.int64)
+        self.comp_ptr = np.zeros((V, len(STREAMS)), np.uint64)
+        self.dq_off = np.zeros((V, 4), np.int64)                             # offsets of the DOMQ streams inside the compact intermediate buffer
+        self.acgt_no_x = np.zeros(V, bool)
+        self.num_norm_qs = np.zeros(V, np.uint8); self.num_doms = np.zeros(V, np.uint8)
+        self.denorm = np.zeros((V, 95 * 95), np.uint8)
+
+    def __len__(self):
+        return self.V
+
+    def __getitem__(self, v):
+        return dict(len={s: int(self.len[v, i]) for i, s in enumerate(STREAMS)},
+                    comp_len={s: int(self.comp_len[v, i]) for i, s in enumerate(STREAMS) if self.len[v, i]},
+                    acgt_no_x=bool(self.acgt_no_x[v]), num_norm_qs=int(self.num_norm_qs[v]),
+                    denorm=bytes(self.denorm[v, :int(self.num_norm_qs[v]) * int(self.num_doms[v])]))
+
+    def __iter__(self):
+        return (self[v] for v in range(self.V))
+
+
 class FastqCodecPath:
     """zip / piz of a batch of V FASTQ VBlocks through libgzb200 on one GPU.
 
-    The path owns `n_engines` engines (one host thread + CUDA stream + workspace each, the library's unit of concurrency:
-    "one engine per host thread and GPU").  The host-buffer path gives each of the three independent pipelines of a FASTQ
-    VBlock (QUAL, SEQ, read names) its own engine so that transfers overlap the entropy chains (zip_host / piz_host).
-    The device-resident path can deal the batch to `device_groups` engines in contiguous groups of VBlocks, as genozip's
-    dispatcher hands VBlocks to compute threads; measured on B200 this does not help (the chain kernels' duration is
-    set by their longest leaf, not by the batch size), so the default is one group."""
+    Memory is what bounds the batch, and the batch is what bounds throughput (the entropy chains are latency-bound: a launch lasts
+    as long as its longest leaf whatever the number of VBlocks).  So nothing of worst-case size exists per VBlock:
+      * codec_domq_compress writes its four streams into worst-case buffers (QUAL.local 2n, DOMQRUNS n, DIVRQUAL n: codec_domq.c:
+        395-410) of a SUB-BATCH of VBlocks; the streams are then moved, at their real lengths, into one compact buffer
+        (gzb_copy_batch) — the reference does the same when it truncates ctx->local.len after the codec ran;
+      * compressed sections are appended to one packed buffer (gzb_compress_sections_packed), as zfile_compress_local_data
+        appends to vb->z_data;
+      * piz decodes the intermediate streams into the buffers zip's intermediates occupied (scrub_intermediates() empties them
+        first when a test wants to see that piz really produced them).
+    Descriptor arrays are filled column-wise through numpy views (no per-section Python work).
 
-    def __init__(self, eng: Engine, V, n_reads, read_len, n_engines=3, device_groups=1):
+    The host-buffer path gives each of the three independent pipelines of a FASTQ VBlock (QUAL, SEQ, read names) its own engine
+    (host thread + CUDA stream) so that transfers overlap the entropy chains (zip_host / piz_host)."""
+
+    def __init__(self, eng: Engine, V, n_reads, read_len, n_engines=3, sub_batch=32):
         self.eng, self.L = eng, eng.L
         self.V, self.n_reads, self.read_len = V, n_reads, read_len
-        self.n = n_reads * read_len
+        self.n = n = n_reads * read_len
         dev = torch.device(getattr(eng, "torch_device", None) or f"cuda:{eng.device}")   # (the CPU test suite drives this class through a mock engine)
         self.dev = dev
         n_engines = max(1, n_engines)
-        K = max(1, min(n_engines, V, device_groups))
         self.engs = [eng] + [type(eng)(eng.device) for _ in range(n_engines - 1)]
-        self.groups = [(g * V // K, (g + 1) * V // K) for g in range(K)]
         self.pool = ThreadPoolExecutor(n_engines) if n_engines > 1 else None
         self.stream = torch.cuda.ExternalStream(self.L.gzb_engine_stream(eng.h), device=dev) if dev.type == "cuda" else None
-        n, V = self.n, V
+        self.SB = max(1, min(sub_batch, V))
         self.packed_len = int(self.L.gzb_acgt_packed_len(n))
         u8 = dict(dtype=torch.uint8, device=dev)
         self.line_off_h = _pin(torch.arange(n_reads, dtype=torch.int64) * read_len)
         self.line_len_h = _pin(torch.full((n_reads,), read_len, dtype=torch.int32))
         self.line_off_d, self.line_len_d = self.line_off_h.to(dev), self.line_len_h.to(dev)
-        # device intermediates / outputs (zip)
         self.packed_d = torch.empty((V, self.packed_len + 32), **u8)
         self.x_d = torch.empty((V, n), **u8)
         self.linedom_d = torch.empty((V, n_reads), **u8)
         self.linediv_d = torch.empty((V, n_reads), **u8)
-        self.dq = {k: torch.empty((V, c), **u8) for k, c in (("QUAL", 2 * n + 16), ("DOMQRUNS", n + 16), ("QUALMPLX", n_reads + 16), ("DIVRQUAL", n + 16))}
-        self.caps = {"QUAL": 2 * n + 16, "DOMQRUNS": n + 16, "QUALMPLX": n_reads + 16, "DIVRQUAL": n + 16, "NONREF_X": n,
-                     "Q_TILE": n_reads, "Q_X": 4 * n_reads, "Q_Y": 4 * n_reads, "Q_MISC": n_reads}
+        self.caps = {"QUAL": 2 * n + 16, "DOMQRUNS": n + 16, "QUALMPLX": n_reads + 16, "DIVRQUAL": n + 16}
+        # worst-case scratch of one sub-batch per engine that runs codec_domq_compress (engine 0 only)
+        self.dqs = {s: torch.empty((self.SB, c), **u8) for s, c in self.caps.items()}
+        self.name_len = {"Q_TILE": n_reads, "Q_X": 4 * n_reads, "Q_Y": 4 * n_reads, "Q_MISC": n_reads}
+        self.dq_arena = None                                                  # compact DOMQ streams of all V VBlocks
+        self.comp_arena = None                                                # packed compressed sections (device)
         self.codec = {s: "RANB" for s in STREAMS}
-        self.comp_d = {}          # compressed sections on device: stream -> [V, est]
-        self.dvb = (DomqVb * V)()
-        self.pvb = (DomqPizVb * V)()
-        self.avb = (AcgtVb * V)()
-        self.meta = None          # per-VB dicts from the last zip (lengths, tables)
-        self.h = {}               # pinned host buffers for the host-buffer (e2e) path
-        self.kernel_ms = (0.0, 0.0)   # chain kernel durations of the last call: (rANS, arithmetic), mean over the engines
+        self.dvb = (DomqVb * V)(); self.pvb = (DomqPizVb * V)(); self.avb = (AcgtVb * V)()
+        self.dvb_np, self.pvb_np, self.avb_np = struct_view(self.dvb), struct_view(self.pvb), struct_view(self.avb)
+        self.meta = None
+        self.h = {}
+        self.kernel_ms = (0.0, 0.0)   # chain kernel durations of the last call: (rANS, arithmetic), max over the engines
+        self.names_dec_d = None; self.seq_out_d = None; self.qual_out_d = None
 
     @property
     def launches(self):
         return sum(e.launches for e in self.engs)
+
+    @property
+    def groups(self):
+        return [(0, self.V)]
 
     def close(self):
         """release the engines this path created (not the caller's) and its host threads"""
@@ -135,20 +192,18 @@ class FastqCodecPath:
             e.close()
         self.engs = self.engs[:1]
 
-    def _each_group(self, fn):
-        """run fn(g, engine, v0, v1) for every group, one host thread per engine; results in group order"""
-        jobs = [(g, self.engs[g], v0, v1) for g, (v0, v1) in enumerate(self.groups)]
-        if self.pool is None:
-            res = [fn(*j) for j in jobs]
-        else:
-            res = list(self.pool.map(lambda j: fn(*j), jobs))
-        self.kernel_ms = tuple(float(np.mean([self.L.gzb_last_kernel_ms(e.h, w) for e in self.engs[:len(self.groups)]])) for w in (0, 1))
-        return res
-
     @staticmethod
     def _sub(arr, v0, v1):
         """ctypes view of elements [v0, v1) of a ctypes array (shares memory)"""
         return (arr._type_ * (v1 - v0)).from_buffer(arr, v0 * C.sizeof(arr._type_))
+
+    @staticmethod
+    def _rows(t):
+        """addresses of the rows of a contiguous 2-D tensor"""
+        return np.uint64(t.data_ptr()) + np.arange(t.shape[0], dtype=np.uint64) * np.uint64(t.stride(0) * t.element_size())
+
+    def _kernel_ms(self, engs):
+        self.kernel_ms = tuple(float(np.max([self.L.gzb_last_kernel_ms(e.h, w) for e in engs])) for w in (0, 1))
 
     # ------------------------------------------------------------------ codec assignment (host policy, run on the GPU)
     def assign_codecs(self, data):
@@ -156,15 +211,15 @@ class FastqCodecPath:
         in-scope simple codecs: compress the first <=99,999 bytes (CODEC_ASSIGN_SAMPLE_SIZE, src/codec.h:154) of VB 1's
         stream with each and keep the smallest, ties to the lower Codec value.  The reference also weighs clock() time
         (timing-dependent, H5) — not reproduced.  Samples are compressed on the GPU (same bytes as the reference)."""
-        self.zip_device(data, only_vb0_streams=True)
-        m = self.meta[0]
+        meta = ZipMeta(self.V)
+        self._acgt_pack_device(data, meta, 0, 1)
+        self._domq_device(lambda v: data["qual"][v].data_ptr(), self.engs[0], meta, GZB_DEVICE_PTRS, 0, 1)
+        meta.len[0, [S_IDX[s] for s in NAMES]] = [self.name_len[s] for s in NAMES]
         samples = {}
         for s in STREAMS:
-            ln = m["len"][s]
-            if ln == 0:
-                continue
-            src = self._stream_dev_tensor(s, 0, data)[:min(ln, 99999)]
-            samples[s] = src.cpu().numpy().copy()
+            ln = int(meta.len[0, S_IDX[s]])
+            if ln:
+                samples[s] = self._stream_tensor(s, 0, data, meta)[:min(ln, 99999)].cpu().numpy().copy()
         items = [(c, samples[s]) for s in samples for c in SIMPLE]
         outs = self.eng.compress(items)
         k = 0
@@ -174,127 +229,188 @@ class FastqCodecPath:
             self.codec[s] = SIMPLE[int(np.argmin(sizes))] if samples[s].size >= 50 else "RANB"   # <50 B would be CODEC_NONE (compressor.c:56-58)
         return dict(self.codec)
 
-    def _stream_dev_tensor(self, s, v, data):
-        if s in self.dq:
-            return self.dq[s][v]
+    def _stream_tensor(self, s, v, data, meta):
+        """device tensor holding stream s of VBlock v (whole capacity for the inputs; the real length for the DOMQ streams)"""
+        if s in DQ:
+            o = int(meta.dq_off[v, DQ.index(s)])
+            return self.dq_arena[o: o + int(meta.len[v, S_IDX[s]])]
         if s == "NONREF_X":
             return self.x_d[v]
         return data[s][v]
 
-    def _stream_cap(self, s, meta):
-        """capacity for stream s: 25% above the longest instance in this batch (the data of a step does not change)"""
-        longest = max(m["len"][s] for m in meta)
-        return min(self.caps[s], int(longest * 1.25) + 4096)
+    # ------------------------------------------------------------------ the domain codecs of a batch
+    def _acgt_pack_device(self, data, meta, v0, v1):
+        a = self.avb_np
+        a["seq"][v0:v1] = self._rows(data["seq"])[v0:v1]; a["n_bases"][v0:v1] = self.n
+        a["packed"][v0:v1] = self._rows(self.packed_d)[v0:v1]; a["x"][v0:v1] = self._rows(self.x_d)[v0:v1]
+        if self.L.gzb_acgt_pack_batch(self.eng.h, self._sub(self.avb, v0, v1), v1 - v0, GZB_DEVICE_PTRS):
+            raise GzbError(f"gzb_acgt_pack_batch: {self.eng._err()}")
+        meta.acgt_no_x[v0:v1] = a["x_all_zero"][v0:v1] != 0
+        meta.len[v0:v1, S_IDX["NONREF_X"]] = np.where(meta.acgt_no_x[v0:v1], 0, self.n)
 
-    def _alloc_comp(self, meta):
-        for s in STREAMS:
-            cap = est_size(self.codec[s], self._stream_cap(s, meta))
-            if s not in self.comp_d or self.comp_d[s].shape[1] < cap:
-                self.comp_d[s] = torch.empty((self.V, cap), dtype=torch.uint8, device=self.dev)
+    def _dq_reserve(self, need, used, total_guess):
+        """the compact buffer of the DOMQ streams: sized from the first sub-batch, grown (contents kept) if that was too little"""
+        if self.dq_arena is None or self.dq_arena.numel() < need:
+            new = torch.empty(max(need, int(total_guess)), dtype=torch.uint8, device=self.dev)
+            if self.dq_arena is not None and used:
+                new[:used] = self.dq_arena[:used]
+            self.dq_arena = new
+
+    def _domq_device(self, txt_ptr, eng, meta, flags, v0, v1, line_tables=None):
+        """codec_domq_compress for VBlocks [v0, v1) in sub-batches: worst-case scratch -> the compact buffer.  txt_ptr(v) = address
+        of the VBlock's quality text (device with GZB_DEVICE_PTRS, host with GZB_OUT_DEVICE)."""
+        L, d = self.L, self.dvb_np
+        host = not (flags & GZB_DEVICE_PTRS)
+        lo, ll = (self.line_off_h, self.line_len_h) if host else (self.line_off_d, self.line_len_d)
+        cursor = int(meta._dq_cursor) if hasattr(meta, "_dq_cursor") else 0
+        for b0 in range(v0, v1, self.SB):
+            b1 = min(v1, b0 + self.SB); k = b1 - b0
+            d["txt"][b0:b1] = [txt_ptr(v) for v in range(b0, b1)]; d["txt_len"][b0:b1] = self.n
+            d["line_off"][b0:b1] = lo.data_ptr(); d["line_len"][b0:b1] = ll.data_ptr(); d["n_lines"][b0:b1] = self.n_reads
+            d["line_dom"][b0:b1] = self._rows(self.h["linedom"] if host else self.linedom_d)[b0:b1]
+            d["line_diverse"][b0:b1] = self._rows(self.h["linediv"] if host else self.linediv_d)[b0:b1]
+            for fld, s in zip(DQ_FLD, DQ):
+                d[fld][b0:b1] = self._rows(self.dqs[s])[:k]; d[fld + "_cap"][b0:b1] = self.caps[s]
+            dv = self._sub(self.dvb, b0, b1)
+            if L.gzb_domq_prepare(eng.h, dv, k, flags) or L.gzb_domq_split(eng.h, dv, k, flags):
+                raise GzbError(f"gzb_domq: {eng._err()}")
+            lens = np.stack([d[f + "_len"][b0:b1].astype(np.int64) for f in DQ_FLD], 1)          # [k, 4]
+            al = (lens + 255) & ~255
+            offs = cursor + np.concatenate([[0], np.cumsum(al.reshape(-1))[:-1]]).reshape(k, 4)
+            need = cursor + int(al.sum())
+            self._dq_reserve(need, cursor, need * (1.0 + 1.1 * (self.V - b1) / max(1, b1 - v0)) if b0 == v0 else need * 1.25)
+            cp = (Copy * (4 * k))(); c = struct_view(cp)
+            c["src"] = np.stack([d[f][b0:b1] for f in DQ_FLD], 1).reshape(-1)
+            c["dst"] = (np.uint64(self.dq_arena.data_ptr()) + offs.astype(np.uint64)).reshape(-1)
+            c["len"] = lens.reshape(-1)
+            if L.gzb_copy_batch(eng.h, cp, 4 * k):
+                raise GzbError(f"gzb_copy_batch: {eng._err()}")
+            cursor = need
+            meta.dq_off[b0:b1] = offs
+            for j, s in enumerate(DQ):
+                meta.len[b0:b1, S_IDX[s]] = lens[:, j]
+            meta.num_norm_qs[b0:b1] = d["num_norm_qs"][b0:b1]; meta.num_doms[b0:b1] = d["num_doms"][b0:b1]
+            meta.denorm[b0:b1] = d["denorm"][b0:b1]
+        meta._dq_cursor = cursor
+
+    def _section_array(self, meta, in_ptr, names, sflags=0):
+        """gzb_section descriptors of the non-empty streams `names` of every VBlock, VBlock-major; returns (array, view, v index, stream index)"""
+        cols = [S_IDX[s] for s in names]
+        ln = meta.len[:, cols]
+        vv, jj = np.nonzero(ln)
+        ss = np.asarray(cols)[jj]
+        secs = (Section * max(1, vv.size))(); a = struct_view(secs)
+        a["codec"][:vv.size] = np.asarray([CODEC[self.codec[s]] for s in STREAMS], np.int32)[ss]
+        a["in_"][:vv.size] = in_ptr[vv, ss]; a["in_len"][:vv.size] = ln[vv, jj]
+        a["sflags"][:vv.size] = np.asarray(sflags, np.uint32)[ss] if not np.isscalar(sflags) else sflags
+        return secs, a, vv, ss
+
+    def _in_ptrs(self, meta, name_rows, dq_base):
+        """[V, 9] addresses of the uncompressed streams: DOMQ streams in the compact buffer, the exception stream, the read-name contexts"""
+        p = np.zeros((self.V, len(STREAMS)), np.uint64)
+        for j, s in enumerate(DQ):
+            p[:, S_IDX[s]] = np.uint64(dq_base) + meta.dq_off[:, j].astype(np.uint64)
+        p[:, S_IDX["NONREF_X"]] = self._rows(self.x_d)
+        for s in NAMES:
+            p[:, S_IDX[s]] = name_rows[s]
+        return p
+
+    def _compress_packed(self, eng, secs, a, n, flags, arena_attr, host):
+        """gzb_compress_sections_packed into the buffer self.<arena_attr> (device or pinned host), grown and repeated when too small"""
+        if not n:
+            return
+        while True:
+            arena = getattr(self, arena_attr, None) if not host else self.h.get(arena_attr)
+            if arena is None:
+                guess = int(a["in_len"][:n].sum() // 8) + (1 << 20)
+                arena = _pin(torch.empty(guess, dtype=torch.uint8)) if host else torch.empty(guess, dtype=torch.uint8, device=self.dev)
+                if host: self.h[arena_attr] = arena
+                else: setattr(self, arena_attr, arena)
+            used = C.c_uint64()
+            rc = self.L.gzb_compress_sections_packed(eng.h, secs, n, arena.data_ptr(), arena.numel(), C.byref(used), flags)
+            if rc == 1 and used.value > arena.numel():
+                bigger = int(used.value * 1.1) + 4096
+                new = _pin(torch.empty(bigger, dtype=torch.uint8)) if host else torch.empty(bigger, dtype=torch.uint8, device=self.dev)
+                if host: self.h[arena_attr] = new
+                else: setattr(self, arena_attr, new)
+                continue
+            if rc:
+                raise GzbError(f"gzb_compress_sections_packed failed ({rc}): {eng._err()}")
+            if a["status"][:n].any():
+                i = int(np.nonzero(a["status"][:n])[0][0])
+                raise GzbError(f"section {i}: status {int(a['status'][i])}")
+            return
 
     # ------------------------------------------------------------------ ZIP, inputs resident in HBM
-    def zip_device(self, data, only_vb0_streams=False):
-        L, V, n = self.L, self.V, self.n
-        meta = [dict(len={}, comp_len={}) for _ in range(V)]
-        for v in range(V):
-            b = self.avb[v]
-            b.seq = data["seq"][v].data_ptr(); b.n_bases = n; b.packed = self.packed_d[v].data_ptr(); b.x = self.x_d[v].data_ptr()
-            a = self.dvb[v]
-            a.txt = data["qual"][v].data_ptr(); a.txt_len = n
-            a.line_off = self.line_off_d.data_ptr(); a.line_len = self.line_len_d.data_ptr(); a.n_lines = self.n_reads
-            a.line_dom = self.linedom_d[v].data_ptr(); a.line_diverse = self.linediv_d[v].data_ptr()
-            for fld, s in (("qual", "QUAL"), ("runs", "DOMQRUNS"), ("mplx", "QUALMPLX"), ("divr", "DIVRQUAL")):
-                setattr(a, fld, self.dq[s][v].data_ptr()); setattr(a, fld + "_cap", self.caps[s])
-
-        def domain(g, eng, v0, v1):
-            h = eng.h
-            if L.gzb_acgt_pack_batch(h, self._sub(self.avb, v0, v1), v1 - v0, GZB_DEVICE_PTRS):
-                raise GzbError(f"gzb_acgt_pack_batch: {eng._err()}")
-            dv = self._sub(self.dvb, v0, v1)
-            if L.gzb_domq_prepare(h, dv, v1 - v0, GZB_DEVICE_PTRS) or L.gzb_domq_split(h, dv, v1 - v0, GZB_DEVICE_PTRS):
-                raise GzbError(f"gzb_domq: {eng._err()}")
-            for v in range(v0, v1):
-                a, m = self.dvb[v], meta[v]
-                m["acgt_no_x"] = bool(self.avb[v].x_all_zero)
-                m["len"].update(NONREF_X=0 if self.avb[v].x_all_zero else n, QUAL=a.qual_len, DOMQRUNS=a.runs_len, QUALMPLX=a.mplx_len,
-                                DIVRQUAL=a.divr_len, Q_TILE=self.n_reads, Q_X=4 * self.n_reads, Q_Y=4 * self.n_reads, Q_MISC=self.n_reads)
-                m["num_norm_qs"] = a.num_norm_qs
-                m["denorm"] = bytes(a.denorm)[:a.num_norm_qs * a.num_doms]
-
-        def sections(g, eng, v0, v1):
-            secs, idx = self._sections(meta, lambda s, v: self._stream_dev_tensor(s, v, data).data_ptr(), lambda s, v: self.comp_d[s][v].data_ptr(), 0, v0, v1)
-            eng.compress_raw(secs, len(idx), GZB_DEVICE_PTRS)
-            self._collect(secs, idx, meta)
-
-        if only_vb0_streams or not self.comp_d:
-            # first call of a batch: the compressed-section buffers are sized from the streams' actual lengths
-            self._each_group(domain)
-            self.meta = meta
-            if only_vb0_streams:
-                return meta
-            self._alloc_comp(meta)
-            self._each_group(sections)
-        else:
-            self._each_group(lambda g, eng, v0, v1: (domain(g, eng, v0, v1), sections(g, eng, v0, v1)))
-            self.meta = meta
+    def zip_device(self, data):
+        V = self.V
+        meta = ZipMeta(V)
+        self._acgt_pack_device(data, meta, 0, V)
+        self._domq_device(lambda v: data["qual"][v].data_ptr(), self.eng, meta, GZB_DEVICE_PTRS, 0, V)
+        for s in NAMES:
+            meta.len[:, S_IDX[s]] = self.name_len[s]
+        inp = self._in_ptrs(meta, {s: self._rows(data[s]) for s in NAMES}, self.dq_arena.data_ptr())
+        secs, a, vv, ss = self._section_array(meta, inp, STREAMS)
+        self._compress_packed(self.eng, secs, a, vv.size, GZB_DEVICE_PTRS, "comp_arena", False)
+        meta.comp_len[vv, ss] = a["out_len"][:vv.size]; meta.comp_ptr[vv, ss] = a["out"][:vv.size]
+        self._kernel_ms([self.eng])
+        self.meta = meta
         return meta
 
-    def _sections(self, meta, in_ptr, out_ptr, sflags_for, v0=0, v1=None):
-        idx = [(v, s) for v in range(v0, self.V if v1 is None else v1) for s in STREAMS if meta[v]["len"][s] > 0]
-        secs = (Section * len(idx))()
-        for i, (v, s) in enumerate(idx):
-            secs[i].codec = CODEC[self.codec[s]]
-            secs[i].in_ = in_ptr(s, v); secs[i].in_len = meta[v]["len"][s]
-            secs[i].out = out_ptr(s, v); secs[i].out_cap = est_size(self.codec[s], meta[v]["len"][s])
-            secs[i].sflags = sflags_for(s) if callable(sflags_for) else sflags_for
-        return secs, idx
+    def section_bytes(self, meta, v, s, host=False):
+        """the compressed section of stream s of VBlock v as a numpy array"""
+        i = S_IDX[s]
+        ln = int(meta.comp_len[v, i])
+        arena = self.h["comp_" + self._pipeline_of(s)] if host else self.comp_arena
+        o = int(meta.comp_ptr[v, i]) - arena.data_ptr()
+        return arena[o: o + ln].cpu().numpy()
 
     @staticmethod
-    def _collect(secs, idx, meta):
-        for i, (v, s) in enumerate(idx):
-            if secs[i].status != 0:
-                raise GzbError(f"section {s} of VB {v}: status {secs[i].status}")
-            meta[v]["comp_len"][s] = secs[i].out_len
+    def _pipeline_of(s):
+        return "qual" if s in DQ else "seq" if s == "NONREF_X" else "names"
 
     # ------------------------------------------------------------------ PIZ, inputs resident in HBM
     def alloc_piz(self, meta):
         u8 = dict(dtype=torch.uint8, device=self.dev)
-        self.dec_d = {s: torch.empty((self.V, self._stream_cap(s, meta) + 16), **u8) for s in STREAMS}
+        self.names_dec_d = {s: torch.empty((self.V, self.name_len[s] + 16), **u8) for s in NAMES}
         self.seq_out_d = torch.empty((self.V, self.n), **u8)
         self.qual_out_d = torch.empty((self.V, self.n), **u8)
+        self.dec_d = self.names_dec_d                                          # (the decoded read-name contexts, by stream)
+
+    def scrub_intermediates(self):
+        """empty every buffer piz decodes into that zip had filled with the same bytes (the DOMQ streams, the exception stream), so
+        that a round-trip check sees what piz produced"""
+        if self.dq_arena is not None: self.dq_arena.zero_()
+        self.x_d.zero_()
+        if self.names_dec_d is not None:
+            for t in self.names_dec_d.values(): t.zero_()
+        if self.seq_out_d is not None: self.seq_out_d.zero_(); self.qual_out_d.zero_()
+
+    def _fill_piz_descriptors(self, meta, qual_out_rows, seq_out_rows, packed_rows, line_len):
+        p, a = self.pvb_np, self.avb_np
+        base = np.uint64(self.dq_arena.data_ptr())
+        for j, (fld, s) in enumerate(zip(DQ_FLD, DQ)):
+            p[fld] = base + meta.dq_off[:, j].astype(np.uint64); p[fld + "_len"] = meta.len[:, S_IDX[s]]
+        p["denorm"] = np.uint64(meta.denorm.ctypes.data) + np.arange(self.V, dtype=np.uint64) * np.uint64(95 * 95)
+        p["denorm_len"] = meta.num_norm_qs.astype(np.uint32) * meta.num_doms.astype(np.uint32); p["num_norm_qs"] = meta.num_norm_qs
+        p["line_len"] = line_len.data_ptr(); p["n_lines"] = self.n_reads
+        p["out"] = qual_out_rows; p["out_cap"] = self.n
+        a["seq"] = seq_out_rows; a["n_bases"] = self.n; a["packed"] = packed_rows
+        a["x"] = np.where(meta.acgt_no_x, np.uint64(0), self._rows(self.x_d))
 
     def piz_device(self, meta):
-        L, n = self.L, self.n
-        keep = []
-
-        def group(g, eng, v0, v1):
-            h = eng.h
-            idx = [(v, s) for v in range(v0, v1) for s in STREAMS if meta[v]["len"][s] > 0]
-            secs = (Section * len(idx))()
-            for i, (v, s) in enumerate(idx):
-                secs[i].codec = CODEC[self.codec[s]]
-                secs[i].in_ = self.comp_d[s][v].data_ptr(); secs[i].in_len = meta[v]["comp_len"][s]
-                secs[i].out = self.dec_d[s][v].data_ptr(); secs[i].out_cap = meta[v]["len"][s]
-            eng.uncompress_raw(secs, len(idx), GZB_DEVICE_PTRS)
-            for v in range(v0, v1):
-                a, m = self.pvb[v], meta[v]
-                a.qual = self.dec_d["QUAL"][v].data_ptr(); a.qual_len = m["len"]["QUAL"]
-                a.runs = self.dec_d["DOMQRUNS"][v].data_ptr(); a.runs_len = m["len"]["DOMQRUNS"]
-                a.mplx = self.dec_d["QUALMPLX"][v].data_ptr(); a.mplx_len = m["len"]["QUALMPLX"]
-                a.divr = self.dec_d["DIVRQUAL"][v].data_ptr(); a.divr_len = m["len"]["DIVRQUAL"]
-                dn = np.frombuffer(m["denorm"], np.uint8); keep.append(dn)
-                a.denorm = dn.ctypes.data; a.denorm_len = dn.size; a.num_norm_qs = m["num_norm_qs"]
-                a.line_len = self.line_len_d.data_ptr(); a.n_lines = self.n_reads
-                a.out = self.qual_out_d[v].data_ptr(); a.out_cap = n
-                b = self.avb[v]
-                b.seq = self.seq_out_d[v].data_ptr(); b.n_bases = n; b.packed = self.packed_d[v].data_ptr()
-                b.x = None if meta[v]["acgt_no_x"] else self.dec_d["NONREF_X"][v].data_ptr()
-            if L.gzb_domq_reconstruct(h, self._sub(self.pvb, v0, v1), v1 - v0, GZB_DEVICE_PTRS):
-                raise GzbError(f"gzb_domq_reconstruct: {eng._err()}")
-            if L.gzb_acgt_unpack_batch(h, self._sub(self.avb, v0, v1), v1 - v0, GZB_DEVICE_PTRS):
-                raise GzbError(f"gzb_acgt_unpack_batch: {eng._err()}")
-
-        self._each_group(group)
+        L, eng = self.L, self.eng
+        outp = self._in_ptrs(meta, {s: self._rows(self.names_dec_d[s]) for s in NAMES}, self.dq_arena.data_ptr())
+        secs, a, vv, ss = self._section_array(meta, meta.comp_ptr, STREAMS)
+        a["in_len"][:vv.size] = meta.comp_len[vv, ss]; a["out"][:vv.size] = outp[vv, ss]; a["out_cap"][:vv.size] = meta.len[vv, ss]
+        if vv.size:
+            eng.uncompress_raw(secs, vv.size, GZB_DEVICE_PTRS)
+        self._fill_piz_descriptors(meta, self._rows(self.qual_out_d), self._rows(self.seq_out_d), self._rows(self.packed_d), self.line_len_d)
+        if L.gzb_domq_reconstruct(eng.h, self.pvb, self.V, GZB_DEVICE_PTRS):
+            raise GzbError(f"gzb_domq_reconstruct: {eng._err()}")
+        if L.gzb_acgt_unpack_batch(eng.h, self.avb, self.V, GZB_DEVICE_PTRS):
+            raise GzbError(f"gzb_acgt_unpack_batch: {eng._err()}")
+        self._kernel_ms([eng])
 
     # ------------------------------------------------------------------ HOST-buffer path (e2e): what the C host would call
     def alloc_host(self, data):
@@ -305,90 +421,12 @@ class FastqCodecPath:
         hp = lambda *shape: _pin(torch.empty(shape, dtype=torch.uint8))
         self.h["packed"] = hp(V, self.packed_len + 32)
         self.h["linedom"] = hp(V, self.n_reads); self.h["linediv"] = hp(V, self.n_reads)
-        # compressed-section buffers: est_size of the largest actual stream of each kind (the capacity the C-ABI requires)
-        def comp_cap(s):
-            lens = [m["len"][s] for m in (self.meta or [])]
-            return max([est_size(self.codec[s], l) for l in lens] + [4096])
-        self.h["comp"] = {s: hp(V, comp_cap(s)) for s in STREAMS}
         self.h["seq_out"] = hp(V, n); self.h["qual_out"] = hp(V, n)
-        self.h["dec"] = {s: hp(V, self.dec_d[s].shape[1]) for s in ("Q_TILE", "Q_X", "Q_Y", "Q_MISC")}
-
-    def zip_host(self):
-        """host buffers in, host buffers out; the DOMQ streams stay on the device between codec_domq_compress and
-        its sub-codec (GZB_OUT_DEVICE / GZB_SEC_IN_DEVICE) exactly as they stay inside one compute thread in the reference.
-        The three independent pipelines of a FASTQ VBlock — QUAL (DOMQ + its four sub-streams), SEQ (ACGT + its exception
-        stream) and the read-name contexts — run on one engine (host thread + stream) each, so the transfers of one
-        overlap the entropy chains of another; QUAL's upload goes first because its chains are the longest.
-        Returns (meta, h2d_bytes, d2h_bytes)."""
-        L, V, n, H = self.L, self.V, self.n, self.h
-        meta = [dict(len={}, comp_len={}) for _ in range(V)]
-        for v in range(V):
-            b = self.avb[v]
-            b.seq = H["seq"][v].data_ptr(); b.n_bases = n; b.packed = H["packed"][v].data_ptr(); b.x = self.x_d[v].data_ptr()
-            a = self.dvb[v]
-            a.txt = H["qual"][v].data_ptr(); a.txt_len = n
-            a.line_off = self.line_off_h.data_ptr(); a.line_len = self.line_len_h.data_ptr(); a.n_lines = self.n_reads
-            a.line_dom = H["linedom"][v].data_ptr(); a.line_diverse = H["linediv"][v].data_ptr()
-            for fld, s in (("qual", "QUAL"), ("runs", "DOMQRUNS"), ("mplx", "QUALMPLX"), ("divr", "DIVRQUAL")):
-                setattr(a, fld, self.dq[s][v].data_ptr()); setattr(a, fld + "_cap", self.caps[s])
-        on_dev = set(self.dq) | {"NONREF_X"}                # intermediate streams stay in HBM until their sub-codec
-        qual_up = threading.Event()
-
-        def in_ptr(s, v):
-            if s in self.dq: return self.dq[s][v].data_ptr()
-            if s == "NONREF_X": return self.x_d[v].data_ptr()
-            return H[s][v].data_ptr()
-
-        def compress(eng, names):
-            idx = [(v, s) for v in range(V) for s in names if meta[v]["len"][s] > 0]
-            secs = (Section * len(idx))()
-            for i, (v, s) in enumerate(idx):
-                secs[i].codec = CODEC[self.codec[s]]
-                secs[i].in_ = in_ptr(s, v); secs[i].in_len = meta[v]["len"][s]
-                secs[i].out = H["comp"][s][v].data_ptr(); secs[i].out_cap = est_size(self.codec[s], meta[v]["len"][s])
-                secs[i].sflags = GZB_SEC_IN_DEVICE if s in on_dev else 0
-            eng.compress_raw(secs, len(idx), 0)
-            self._collect(secs, idx, meta)
-
-        def part_qual(eng):
-            try:
-                if L.gzb_domq_prepare(eng.h, self.dvb, V, GZB_OUT_DEVICE):
-                    raise GzbError(f"gzb_domq_prepare: {eng._err()}")
-            finally:
-                qual_up.set()
-            if L.gzb_domq_split(eng.h, self.dvb, V, GZB_OUT_DEVICE):
-                raise GzbError(f"gzb_domq_split: {eng._err()}")
-            for v in range(V):
-                a, m = self.dvb[v], meta[v]
-                m["len"].update(QUAL=a.qual_len, DOMQRUNS=a.runs_len, QUALMPLX=a.mplx_len, DIVRQUAL=a.divr_len)
-                m["num_norm_qs"] = a.num_norm_qs
-                m["denorm"] = bytes(a.denorm)[:a.num_norm_qs * a.num_doms]
-            compress(eng, ("QUAL", "DOMQRUNS", "QUALMPLX", "DIVRQUAL"))
-
-        def part_seq(eng):
-            qual_up.wait()
-            for v0 in range(0, V, 64):                          # bounded staging in the engine workspace
-                if L.gzb_acgt_pack_batch(eng.h, self._sub(self.avb, v0, min(V, v0 + 64)), min(V, v0 + 64) - v0, GZB_OUT_DEVICE):
-                    raise GzbError(f"gzb_acgt_pack_batch: {eng._err()}")
-            for v in range(V):
-                meta[v]["acgt_no_x"] = bool(self.avb[v].x_all_zero)
-                meta[v]["len"]["NONREF_X"] = 0 if self.avb[v].x_all_zero else n
-            compress(eng, ("NONREF_X",))
-
-        def part_names(eng):
-            for v in range(V):
-                meta[v]["len"].update(Q_TILE=self.n_reads, Q_X=4 * self.n_reads, Q_Y=4 * self.n_reads, Q_MISC=self.n_reads)
-            qual_up.wait()
-            compress(eng, ("Q_TILE", "Q_X", "Q_Y", "Q_MISC"))
-
-        self._run_parts([part_qual, part_seq, part_names])
-        h2d = V * (n + n + 12 * self.n_reads); d2h = V * (self.packed_len + 2 * self.n_reads)
-        for m in meta:
-            for s, ln in m["len"].items():
-                if ln:
-                    if s not in on_dev: h2d += ln
-                    d2h += m["comp_len"][s]
-        return meta, h2d, d2h
+        self.h["dec"] = {s: hp(V, self.name_len[s] + 16) for s in NAMES}
+        if self.meta is not None:                                            # packed section buffers of the three pipelines, sized from the device pass
+            for pl, names in (("qual", DQ), ("seq", ("NONREF_X",)), ("names", NAMES)):
+                need = int(((self.meta.comp_len[:, [S_IDX[s] for s in names]] + 15) & ~15).sum())
+                self.h["comp_" + pl] = hp(int(need * 1.05) + 65536)
 
     def _run_parts(self, parts):
         """one engine (host thread + stream) per independent pipeline; with a single engine they run one after the other"""
@@ -405,57 +443,97 @@ class FastqCodecPath:
                     errs.append(ex)
             if errs:
                 raise errs[0]
-        self.kernel_ms = tuple(float(np.max([self.L.gzb_last_kernel_ms(e.h, w) for e in self.engs])) for w in (0, 1))
+        self._kernel_ms(self.engs)
+
+    def zip_host(self):
+        """host buffers in, host buffers out; the DOMQ streams and the exception stream stay on the device between the complex codec
+        and its sub-codec (GZB_OUT_DEVICE / GZB_SEC_IN_DEVICE) exactly as they stay inside one compute thread in the reference.
+        The three independent pipelines of a FASTQ VBlock — QUAL (DOMQ + its four sub-streams), SEQ (ACGT + its exception
+        stream) and the read-name contexts — run on one engine (host thread + stream) each, so the transfers of one
+        overlap the entropy chains of another; QUAL's upload goes first because its chains are the longest.
+        Returns (meta, h2d_bytes, d2h_bytes)."""
+        L, V, n, H = self.L, self.V, self.n, self.h
+        meta = ZipMeta(V)
+        for s in NAMES:
+            meta.len[:, S_IDX[s]] = self.name_len[s]
+        dev_in = np.zeros(len(STREAMS), np.uint32)
+        for s in DQ + ("NONREF_X",):
+            dev_in[S_IDX[s]] = GZB_SEC_IN_DEVICE                 # intermediate streams stay in HBM until their sub-codec
+        qual_up = threading.Event()
+        name_rows = {s: self._rows(H[s]) for s in NAMES}
+
+        def compress(eng, names, arena):
+            inp = self._in_ptrs(meta, name_rows, self.dq_arena.data_ptr() if self.dq_arena is not None else 0)
+            secs, a, vv, ss = self._section_array(meta, inp, names, dev_in)
+            self._compress_packed(eng, secs, a, vv.size, 0, arena, True)
+            meta.comp_len[vv, ss] = a["out_len"][:vv.size]; meta.comp_ptr[vv, ss] = a["out"][:vv.size]
+
+        def part_qual(eng):
+            try:
+                first = min(V, self.SB)
+                self._domq_device(lambda v: H["qual"][v].data_ptr(), eng, meta, GZB_OUT_DEVICE, 0, first)
+            finally:
+                qual_up.set()
+            if first < V:
+                self._domq_device(lambda v: H["qual"][v].data_ptr(), eng, meta, GZB_OUT_DEVICE, first, V)
+            compress(eng, DQ, "comp_qual")
+
+        def part_seq(eng):
+            qual_up.wait()
+            a = self.avb_np
+            a["seq"] = self._rows(H["seq"]); a["n_bases"] = n; a["packed"] = self._rows(H["packed"]); a["x"] = self._rows(self.x_d)
+            for v0 in range(0, V, 64):                          # bounded staging in the engine workspace
+                v1 = min(V, v0 + 64)
+                if L.gzb_acgt_pack_batch(eng.h, self._sub(self.avb, v0, v1), v1 - v0, GZB_OUT_DEVICE):
+                    raise GzbError(f"gzb_acgt_pack_batch: {eng._err()}")
+            meta.acgt_no_x[:] = a["x_all_zero"] != 0
+            meta.len[:, S_IDX["NONREF_X"]] = np.where(meta.acgt_no_x, 0, n)
+            compress(eng, ("NONREF_X",), "comp_seq")
+
+        def part_names(eng):
+            qual_up.wait()
+            compress(eng, NAMES, "comp_names")
+
+        self._run_parts([part_qual, part_seq, part_names])
+        on_dev = [S_IDX[s] for s in DQ + ("NONREF_X",)]
+        host_in = np.ones(len(STREAMS), bool); host_in[on_dev] = False
+        h2d = V * (n + n + 12 * self.n_reads) + int(meta.len[:, host_in].sum())
+        d2h = V * (self.packed_len + 2 * self.n_reads) + int(meta.comp_len.sum())
+        return meta, h2d, d2h
 
     def piz_host(self, meta):
         L, V, n, H = self.L, self.V, self.n, self.h
-        keep = []
+        dev_out = np.zeros(len(STREAMS), np.uint32)
+        for s in DQ + ("NONREF_X",):
+            dev_out[S_IDX[s]] = GZB_SEC_OUT_DEVICE
+        outp = self._in_ptrs(meta, {s: self._rows(H["dec"][s]) for s in NAMES}, self.dq_arena.data_ptr())
 
         def uncompress(eng, names):
-            idx = [(v, s) for v in range(V) for s in names if meta[v]["len"][s] > 0]
-            secs = (Section * len(idx))()
-            for i, (v, s) in enumerate(idx):
-                on_dev = s in self.dq or s == "NONREF_X"
-                secs[i].codec = CODEC[self.codec[s]]
-                secs[i].in_ = H["comp"][s][v].data_ptr(); secs[i].in_len = meta[v]["comp_len"][s]
-                secs[i].out = (self.dec_d[s][v] if on_dev else H["dec"][s][v]).data_ptr(); secs[i].out_cap = meta[v]["len"][s]
-                secs[i].sflags = GZB_SEC_OUT_DEVICE if on_dev else 0
-            eng.uncompress_raw(secs, len(idx), 0)
+            secs, a, vv, ss = self._section_array(meta, meta.comp_ptr, names, dev_out)
+            a["in_len"][:vv.size] = meta.comp_len[vv, ss]; a["out"][:vv.size] = outp[vv, ss]; a["out_cap"][:vv.size] = meta.len[vv, ss]
+            if vv.size:
+                eng.uncompress_raw(secs, vv.size, 0)
+
+        self._fill_piz_descriptors(meta, self._rows(H["qual_out"]), self._rows(H["seq_out"]), self._rows(H["packed"]), self.line_len_h)
 
         def part_qual(eng):
-            uncompress(eng, ("QUAL", "DOMQRUNS", "QUALMPLX", "DIVRQUAL"))
-            for v in range(V):
-                a, m = self.pvb[v], meta[v]
-                a.qual = self.dec_d["QUAL"][v].data_ptr(); a.qual_len = m["len"]["QUAL"]
-                a.runs = self.dec_d["DOMQRUNS"][v].data_ptr(); a.runs_len = m["len"]["DOMQRUNS"]
-                a.mplx = self.dec_d["QUALMPLX"][v].data_ptr(); a.mplx_len = m["len"]["QUALMPLX"]
-                a.divr = self.dec_d["DIVRQUAL"][v].data_ptr(); a.divr_len = m["len"]["DIVRQUAL"]
-                dn = np.frombuffer(m["denorm"], np.uint8); keep.append(dn)
-                a.denorm = dn.ctypes.data; a.denorm_len = dn.size; a.num_norm_qs = m["num_norm_qs"]
-                a.line_len = self.line_len_h.data_ptr(); a.n_lines = self.n_reads
-                a.out = H["qual_out"][v].data_ptr(); a.out_cap = n
+            uncompress(eng, DQ)
             if L.gzb_domq_reconstruct(eng.h, self.pvb, V, GZB_IN_DEVICE):
                 raise GzbError(f"gzb_domq_reconstruct: {eng._err()}")
 
         def part_seq(eng):
             uncompress(eng, ("NONREF_X",))
-            for v in range(V):
-                b = self.avb[v]
-                b.seq = H["seq_out"][v].data_ptr(); b.n_bases = n; b.packed = H["packed"][v].data_ptr()
-                b.x = None if meta[v]["acgt_no_x"] else self.dec_d["NONREF_X"][v].data_ptr()
             for v0 in range(0, V, 64):
-                if L.gzb_acgt_unpack_batch(eng.h, self._sub(self.avb, v0, min(V, v0 + 64)), min(V, v0 + 64) - v0, GZB_IN_DEVICE):
+                v1 = min(V, v0 + 64)
+                if L.gzb_acgt_unpack_batch(eng.h, self._sub(self.avb, v0, v1), v1 - v0, GZB_IN_DEVICE):
                     raise GzbError(f"gzb_acgt_unpack_batch: {eng._err()}")
 
         def part_names(eng):
-            uncompress(eng, ("Q_TILE", "Q_X", "Q_Y", "Q_MISC"))
+            uncompress(eng, NAMES)
 
         self._run_parts([part_qual, part_seq, part_names])
-        on_dev = set(self.dq) | {"NONREF_X"}
-        h2d = V * (4 * self.n_reads + self.packed_len); d2h = V * (n + n)
-        for m in meta:
-            for s, ln in m["len"].items():
-                if ln:
-                    h2d += m["comp_len"][s]
-                    if s not in on_dev: d2h += ln
+        on_dev = [S_IDX[s] for s in DQ + ("NONREF_X",)]
+        host_out = np.ones(len(STREAMS), bool); host_out[on_dev] = False
+        h2d = V * (4 * self.n_reads + self.packed_len) + int(meta.comp_len.sum())
+        d2h = V * (n + n) + int(meta.len[:, host_out].sum())
         return h2d, d2h

@@ -53,6 +53,10 @@ class AcgtVb(C.Structure):         # gzb_acgt_vb
                 ("x_all_zero", C.c_int32), ("reserved", C.c_uint32)]
 
 
+class Copy(C.Structure):            # gzb_copy
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("len", C.c_uint64)]
+
+
 class LongrVb(C.Structure):         # gzb_longr_vb
     _fields_ = [("txt", C.c_void_p), ("txt_len", C.c_uint64), ("seq_off", C.c_void_p), ("qual_off", C.c_void_p),
                 ("len", C.c_void_p), ("is_rev", C.c_void_p), ("n_lines", C.c_uint32), ("value_to_bin", C.c_uint8 * 256),
@@ -123,6 +127,10 @@ def load():
         getattr(L, f).argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
     L.gzb_longr_calculate_bins.restype = C.c_int
     L.gzb_longr_calculate_bins.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    L.gzb_compress_sections_packed.restype = C.c_int
+    L.gzb_compress_sections_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32]
+    L.gzb_copy_batch.restype = C.c_int
+    L.gzb_copy_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
     L.gzb_pbwt_decode.restype = C.c_int
     L.gzb_pbwt_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64,
                                   C.POINTER(C.c_uint64), C.c_uint32]
@@ -221,6 +229,28 @@ class Engine:
         if rc != 0:
             raise GzbError(f"gzb_uncompress_sections failed ({rc}): {self._err()}")
         return outs
+
+    def compress_packed(self, items, arena_cap=None):
+        """gzb_compress_sections_packed on host buffers: the sections appended to ONE buffer (zfile_compress_local_data's z_data
+        append) -> (list of compressed bodies, bytes used).  A buffer that is too small is grown and the call repeated, like the
+        soft-fail retry of compressor.c:90-110."""
+        n = len(items)
+        secs = (Section * n)()
+        keep = [np.ascontiguousarray(d, dtype=np.uint8) for _, d in items]
+        dummy = np.zeros(16, np.uint8)
+        for i, ((codec, _), data) in enumerate(zip(items, keep)):
+            secs[i].codec = CODEC[codec]; secs[i].in_ = data.ctypes.data if data.size else dummy.ctypes.data; secs[i].in_len = data.size
+        cap = arena_cap if arena_cap is not None else max(4096, sum(d.size for d in keep) // 2)
+        while True:
+            arena = np.empty(max(cap, 16), np.uint8); used = C.c_uint64()
+            rc = self.L.gzb_compress_sections_packed(self.h, secs, n, arena.ctypes.data, cap, C.byref(used), 0)
+            if rc == 1 and used.value > cap:
+                cap = used.value
+                continue
+            if rc != 0:
+                raise GzbError(f"gzb_compress_sections_packed failed ({rc}): {self._err()}")
+            base = arena.ctypes.data
+            return [arena[secs[i].out - base: secs[i].out - base + secs[i].out_len].copy() for i in range(n)], used.value
 
     # ---- raw access for bench.py (device pointers / prebuilt section arrays) ----
     def compress_raw(self, secs, n, flags=0):

@@ -93,6 +93,18 @@ uint32_t gzb_est_size (int codec, uint64_t uncompressed_len);     /* codec_*_est
 int gzb_compress_sections   (gzb_engine *e, gzb_section *secs, uint32_t n, uint32_t flags);
 int gzb_uncompress_sections (gzb_engine *e, gzb_section *secs, uint32_t n, uint32_t flags);
 
+/* Packed output: the compressed sections of the batch are APPENDED to one buffer in section order, 16-byte aligned, the way
+ * zfile_compress_local_data appends a section to vb->z_data (src/zfile.c:229-262) — no per-section capacity of est_size bytes
+ * has to exist anywhere.  secs[i].out / out_cap are ignored on entry; on return secs[i].out points into `arena` and out_len is
+ * set.  *arena_used = bytes needed; if that exceeds arena_cap nothing is written and the call returns GZB_SOFT_FAIL (grow the
+ * buffer and call again, like the soft-fail retry of src/compressor.c:90-110).  `arena` is a device pointer with GZB_DEVICE_PTRS
+ * or GZB_OUT_DEVICE, else host memory (one transfer for the whole batch). */
+int gzb_compress_sections_packed (gzb_engine *e, gzb_section *secs, uint32_t n, void *arena, uint64_t arena_cap, uint64_t *arena_used, uint32_t flags);
+
+/* n device-to-device copies in one launch (compacting the streams a complex codec produced into right-sized buffers) */
+typedef struct { const void *src; void *dst; uint64_t len; } gzb_copy;
+int gzb_copy_batch (gzb_engine *e, const gzb_copy *copies, uint32_t n);
+
 /* ---------------------------------------------------------------- ACGT / XCGT (src/codec_acgt.c)
  * pack:   codec_acgt_compress up to the sub-codec call (:64-163): bases → LE 2-bit words + exception stream.
  *         `packed` receives gzb_acgt_packed_len(n) bytes; `x` (n bytes) may be NULL if the caller declares

@@ -15,6 +15,7 @@ import numpy as np
 
 import orc
 from genozip_b200.lib import load, CODEC, GZB_DEVICE_PTRS, GZB_OUT_DEVICE, GZB_IN_DEVICE
+from genozip_b200.lib import Section as lib_Section
 
 NAME = {v: k for k, v in CODEC.items()}
 
@@ -225,6 +226,35 @@ class MockLib:
                 continue
             _view(s.out, c.size)[:] = c
             s.out_len = c.size; s.status = 0
+        return 0
+
+    def gzb_compress_sections_packed(self, h, secs, n, arena, cap, used, flags):
+        self.calls.append(("compress_packed", n, flags))
+        secs = C.cast(secs, C.POINTER(lib_Section)) if not hasattr(secs, "__getitem__") else secs
+        outs = []
+        for i in range(n):
+            s = secs[i]
+            name = NAME[s.codec]
+            outs.append(orc.compress("port", "rans" if name.startswith("RAN") else "arith", _view(s.in_, s.in_len).copy(), orc.ORDER[name]))
+        total = sum((c.size + 15) & ~15 for c in outs)
+        if used is not None:
+            used._obj.value = total
+        if total > cap:
+            for i in range(n):
+                secs[i].status = 1; secs[i].out_len = 0
+            return 1
+        off = 0
+        for i, c in enumerate(outs):
+            _view(int(arena) + off, c.size)[:] = c
+            secs[i].out = int(arena) + off; secs[i].out_len = c.size; secs[i].status = 0
+            off += (c.size + 15) & ~15
+        return 0
+
+    def gzb_copy_batch(self, h, cps, n):
+        for i in range(n):
+            c = cps[i]
+            if c.len:
+                _view(c.dst, c.len)[:] = _view(c.src, c.len)
         return 0
 
     def gzb_uncompress_sections(self, h, secs, n, flags):

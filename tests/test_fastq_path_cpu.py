@@ -21,8 +21,8 @@ def _oracle_sections(data, v, n_reads, read_len, codec):
     return pk, streams, comp
 
 
-@pytest.mark.parametrize("backend,n_engines", [("mock", 1), ("mock", 3), ("simt", 1), ("simt", 3)])
-def test_fastq_path_host_driver(backend, n_engines):
+@pytest.mark.parametrize("backend,n_engines,sub_batch", [("mock", 1, 32), ("mock", 3, 2), ("simt", 1, 1), ("simt", 3, 32)])
+def test_fastq_path_host_driver(backend, n_engines, sub_batch):
     from genozip_b200.fastq_path import FastqCodecPath, synth_vblocks, STREAMS
     if backend == "simt":
         from simt_lib import simt_engine_class
@@ -32,7 +32,7 @@ def test_fastq_path_host_driver(backend, n_engines):
     V, n_reads, read_len = 3, 400, 150
     data = synth_vblocks(V, n_reads, read_len, 7, torch.device("cpu"))
     data["seq"][1][data["seq"][1] == ord("N")] = ord("A")                  # VBlock 1: pure ACGT -> acgt_no_x, no NONREF_X section
-    path = FastqCodecPath(Eng(0), V, n_reads, read_len, n_engines=n_engines)
+    path = FastqCodecPath(Eng(0), V, n_reads, read_len, n_engines=n_engines, sub_batch=sub_batch)   # (small sub-batches: the compact buffer grows on the way)
     codec = path.assign_codecs(data)
     assert set(codec) == set(STREAMS)
     meta = path.zip_device(data)
@@ -44,8 +44,9 @@ def test_fastq_path_host_driver(backend, n_engines):
         for s in STREAMS:
             assert meta[v]["len"][s] == streams[s].size, (s, meta[v]["len"][s], streams[s].size)
             if streams[s].size:
-                got = path.comp_d[s][v][:meta[v]["comp_len"][s]].numpy()
+                got = path.section_bytes(meta, v, s)
                 assert got.size == comp[s].size and np.array_equal(got, comp[s]), f"section {s} of VB {v}"
+    path.scrub_intermediates()                                             # piz decodes into the buffers zip's intermediates occupied
     path.piz_device(meta)
     assert torch.equal(path.seq_out_d, data["seq"]) and torch.equal(path.qual_out_d, data["qual"])
     for s in ("Q_TILE", "Q_X", "Q_Y", "Q_MISC"):
@@ -57,9 +58,9 @@ def test_fastq_path_host_driver(backend, n_engines):
         for s in STREAMS:
             assert meta_h[v]["len"][s] == meta[v]["len"][s] and meta_h[v]["comp_len"].get(s) == meta[v]["comp_len"].get(s)
             if meta[v]["len"][s]:
-                a = path.h["comp"][s][v][:meta_h[v]["comp_len"][s]].numpy(); b = path.comp_d[s][v][:meta[v]["comp_len"][s]].numpy()
+                a = path.section_bytes(meta_h, v, s, host=True); b = path.section_bytes(meta, v, s)
                 assert np.array_equal(a, b), f"host path: section {s}"
-    path.h["seq_out"].zero_(); path.h["qual_out"].zero_()
+    path.h["seq_out"].zero_(); path.h["qual_out"].zero_(); path.scrub_intermediates()
     h2d_p, d2h_p = path.piz_host(meta_h)
     assert torch.equal(path.h["seq_out"], path.h["seq"]) and torch.equal(path.h["qual_out"], path.h["qual"])
     n = n_reads * read_len

@@ -45,8 +45,9 @@ def test_fastq_path_device_and_host(eng, n_reads):
         for s in STREAMS:
             assert meta[v]["len"][s] == streams[s].size, (s, meta[v]["len"][s], streams[s].size)
             if streams[s].size:
-                got = path.comp_d[s][v][:meta[v]["comp_len"][s]].cpu().numpy()
+                got = path.section_bytes(meta, v, s)
                 assert got.size == comp[s].size and np.array_equal(got, comp[s]), f"section {s} of VB {v} differs from the reference bytes"
+    path.scrub_intermediates()                                             # piz decodes into the buffers zip's intermediates occupied
     path.piz_device(meta)
     torch.cuda.synchronize()
     assert torch.equal(path.seq_out_d, data["seq"]) and torch.equal(path.qual_out_d, data["qual"])
@@ -57,8 +58,9 @@ def test_fastq_path_device_and_host(eng, n_reads):
         for s in STREAMS:
             assert meta_h[v]["len"][s] == meta[v]["len"][s] and meta_h[v]["comp_len"].get(s) == meta[v]["comp_len"].get(s)
             if meta[v]["len"][s]:
-                a = path.h["comp"][s][v][:meta_h[v]["comp_len"][s]].numpy(); b = path.comp_d[s][v][:meta[v]["comp_len"][s]].cpu().numpy()
+                a = path.section_bytes(meta_h, v, s, host=True); b = path.section_bytes(meta, v, s)
                 assert np.array_equal(a, b), f"host path: section {s} differs from the device path"
+    path.h["seq_out"].zero_(); path.h["qual_out"].zero_(); path.scrub_intermediates()
     path.piz_host(meta_h)
     assert torch.equal(path.h["seq_out"], path.h["seq"]) and torch.equal(path.h["qual_out"], path.h["qual"])
     assert h2d > 0 and d2h > 0

@@ -118,3 +118,19 @@ def test_corrupt_is_reported(eng):
     comp[0] = 0x08 | 0x40   # claims STRIPE + rubbish
     with pytest.raises(GzbError):
         eng.uncompress([("RANB", comp, data.size)])
+
+
+def test_packed_output(eng):
+    """gzb_compress_sections_packed: the same bytes as the per-section call, appended to one buffer; a buffer that is too small
+    is reported with the size that is needed and nothing is written"""
+    from datagen import stream
+    items = [(c, stream(k, n, 5 + i)) for i, (c, k, n) in enumerate((("RANB", "skew8", 40000), ("ARTW", "u32le", 9000), ("RANw", "qual", 77), ("ARTb", "qual", 30001),
+                                                                     ("RANW", "u32le", 20), ("ARTB", "skew8", 1), ("RANb", "const", 100000)))]
+    want = eng.compress(items)
+    got, used = eng.compress_packed(items, arena_cap=64)                    # too small at first: grown to the reported size
+    assert used == sum((len(w) + 15) & ~15 for w in want)
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+    got2, _ = eng.compress_packed(items)
+    for g, w in zip(got2, want):
+        assert np.array_equal(g, w)
