@@ -308,12 +308,19 @@ static int compress_impl (gzb_engine *e, gzb_section *secs, uint32_t n, uint32_t
     std::vector<uint2> rjobs = make_jobs ((uint32_t)rlist.size (), [&] (uint32_t i) { return hl[rlist[i]].n; },
                                           [&] (uint32_t i) { return (uint32_t)(hl[rlist[i]].order_req & 1); });
 
+    // the split encoder (arith_split.cu) takes order-1 arithmetic leaves of at least GZB_AR_SPLIT_MIN symbols (default 32768; "off" disables)
+    static const uint32_t split_min = [] { const char *v = getenv ("GZB_AR_SPLIT_MIN"); return !v ? 32768u : !strcmp (v, "off") ? 0xffffffffu : (uint32_t)strtoul (v, nullptr, 10); } ();
+    uint32_t n_arith_big = 0;
+    while (n_arith_big < alist.size () && hl[alist[n_arith_big]].n >= split_min) n_arith_big++;
     // arena estimate for alphabet-dependent tables; grown and replayed on overflow
     size_t arena_est = (size_t)4 << 20;
     for (auto &L : hl) {
         size_t m = std::min<size_t> (256, (size_t)L.n + 1);
         if (L.coder == CODER_RANS) arena_est += (L.order_req & 1) ? std::min<size_t> (m * m * 20 + m * CTXB, 64 * 64 * 20 + 64 * CTXB + (size_t)L.n / 8) + 4096 : 4096 + 64;
-        else arena_est += std::min<size_t> ((size_t)256 * 264 * 4, 256 * 72 * 4 + (size_t)L.n / 8) + 258 * 12 * 4 + 64;
+        else {
+            arena_est += std::min<size_t> ((size_t)256 * 264 * 4, 256 * 72 * 4 + (size_t)L.n / 8) + 258 * 12 * 4 + 64;
+            if ((L.order_req & 1) && L.n >= split_min) arena_est += 12 * (size_t)L.n + 257 * 4 + 64;   // split encoder: positions + records
+        }
     }
     if (e->arena_hint > arena_est) arena_est = e->arena_hint;
 
@@ -395,6 +402,7 @@ static int compress_impl (gzb_engine *e, gzb_section *secs, uint32_t n, uint32_t
 
         P.n_sections = n; P.n_leaves = nl; P.n_tiles = (uint32_t)tiles.size (); P.n_stripe_tiles = (uint32_t)stiles.size ();
         P.n_rans = (uint32_t)rlist.size (); P.n_arith = (uint32_t)alist.size ();
+        P.n_arith_big = n_arith_big; P.split_min = split_min;
         P.any_pack = any_pack; P.any_o1 = any_o1;
         P.n_rans_jobs = (uint32_t)rjobs.size (); P.arith_lpw = pick_arith_lpw (P.n_arith);
         P.copy_parts = (n <= 64) ? 32 : (n <= 1024 ? 8 : 2);

@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(128) k_arith_encode_t (const EncLeaf *leaves, 
     const bool o1 = D.eff_order, rle = (D.hdr[0] & F_RLE) != 0;
     uint32_t *lit = D.models;
     uint8_t *out = L.outbuf;
-    if (!lit || ar_is_o0_class (o1, rle) != O0CLASS) return;
+    if (!lit || ar_is_o0_class (o1, rle) != O0CLASS || D.split_pos) return;    // (split_pos: the leaf goes through arith_split.cu)
     __builtin_assume (__isGlobal (lit)); __builtin_assume (__isGlobal (out)); __builtin_assume (__isGlobal (in));
     uint32_t len;
     if (O0CLASS) {

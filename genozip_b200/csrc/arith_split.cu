@@ -1,0 +1,188 @@
+// arith_split.cu — the adaptive arithmetic ENCODER of a long order-1 leaf, taken apart.
+//
+// In the encoder the adaptive models evolve with the symbols alone: what the range coder does never feeds back into them
+// (c_simple_model.h:123-146 reads and bumps the model; c_range_coder.h:97-109 only consumes cumFreq / freq / totFreq).  And
+// under order 1 the 256 context models do not see each other: context c sees, in order, exactly the symbols that follow a c.
+// So the one chain "model step + coder step" per symbol of arith_chain.cu splits into
+//   A  per context, in parallel: its sub-sequence through its own model -> one record (cumFreq, freq, totFreq) per symbol;
+//   B  per leaf: the range coder's recurrence over the records — a division, two multiplies, the carry and the renormalisation.
+// The bytes are the reference's: the same models see the same symbols in the same order, the same coder sees the same triples.
+// The decoder cannot be split this way (the symbol depends on the code).
+//
+//   k_ar_split_bucket   one CTA per leaf: positions grouped by context, in order (a stable counting sort by the previous symbol)
+//   k_ar_split_model    one warp per (leaf, context): stage A, on arith_model.cuh's model code
+//   k_ar_split_code     one warp per leaf: stage B
+#include "gzb_internal.cuh"
+#include "hts_enc.cuh"
+#include "arith_model.cuh"
+
+namespace gzb {
+
+constexpr int SPLIT_WARPS = 32;                  // warps of the bucket CTA; each owns a contiguous segment of the leaf
+
+__device__ __forceinline__ bool ar_split_leaf (const EncLeafDyn &D) { return D.split_pos != nullptr; }
+
+// ------------------------------------------------------------------------------------------------ positions by context
+__global__ void __launch_bounds__(SPLIT_WARPS * 32) k_ar_split_bucket (EncLeafDyn *dyn, const uint32_t *list, uint32_t n_list)
+{
+    if (blockIdx.x >= n_list) return;
+    EncLeafDyn &D = dyn[list[blockIdx.x]];
+    if (!ar_split_leaf (D)) return;
+    __shared__ uint32_t cur[SPLIT_WARPS][256];                               // counts, then write cursors, per warp segment and context
+    __shared__ uint32_t tot[256];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n = D.eff_n;
+    const uint8_t * __restrict__ in = D.eff_in;
+    uint32_t *pos = D.split_pos, *start = D.split_start;
+    const uint32_t seg = (((n + SPLIT_WARPS - 1) / SPLIT_WARPS) + 31) & ~31u;
+    const uint32_t b = min (n, (uint32_t)warp * seg), e = min (n, b + seg);
+    for (int i = tid; i < SPLIT_WARPS * 256; i += SPLIT_WARPS * 32) (&cur[0][0])[i] = 0;
+    __syncthreads ();
+    for (uint32_t i = b + lane; i < e; i += 32) atomicAdd (&cur[warp][i ? in[i - 1] : 0], 1u);   // the context of symbol i (arith_dynamic.c:176: last = 0 at the start)
+    __syncthreads ();
+    if (tid < 256) { uint32_t t = 0; for (int w = 0; w < SPLIT_WARPS; w++) t += cur[w][tid]; tot[tid] = t; }
+    __syncthreads ();
+    if (warp == 0) {                                                         // exclusive scan of the 256 totals: 8 per lane
+        uint32_t s = 0, v[8];
+        for (int k = 0; k < 8; k++) { v[k] = tot[8 * lane + k]; s += v[k]; }
+        uint32_t inc = s;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync (0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        uint32_t x = inc - s;
+        for (int k = 0; k < 8; k++) { tot[8 * lane + k] = x; x += v[k]; }
+    }
+    __syncthreads ();
+    if (tid < 256) {
+        uint32_t x = tot[tid];
+        start[tid] = x;
+        for (int w = 0; w < SPLIT_WARPS; w++) { const uint32_t c = cur[w][tid]; cur[w][tid] = x; x += c; }
+        if (tid == 255) start[256] = x;
+    }
+    __syncthreads ();
+    for (uint32_t i0 = b; i0 < e; i0 += 32) {                                // in order within the segment: ranks among equal contexts by lane
+        const uint32_t i = i0 + lane;
+        const bool act = i < e;
+        const uint32_t key = act ? (i ? in[i - 1] : 0u) : 256u + lane;
+        const uint32_t peers = __match_any_sync (0xffffffffu, key);
+        const uint32_t base = act ? cur[warp][key] : 0;
+        __syncwarp ();
+        if (act) {
+            pos[base + __popc (peers & ((1u << lane) - 1))] = i;
+            if ((peers >> lane) == 1) cur[warp][key] = base + __popc (peers);   // the highest lane of the group moves the cursor
+        }
+        __syncwarp ();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ stage A
+// One symbol of one context through its model: SIMPLE_MODEL_encodeSymbol (c_simple_model.h:123-146) up to the call of RC_Encode,
+// whose arguments are returned: x = cumFreq | freq << 16, y = totFreq (all below 2^16: MAX_FREQ, :70).
+__device__ __forceinline__ uint2 ar_model_rec (uint32_t *m, uint32_t maxs, ArCache &c, uint32_t sym, int lane, bool &stale)
+{
+    uint2 rec; rec.y = c.tot;
+    const uint32_t f0 = c.e0 & 0xffffu;
+    if ((c.e0 >> 16) == sym)      { rec.x = f0 << 16; AR_BUMP_CASE (0, c.e0, c.e0) }
+    else if ((c.e1 >> 16) == sym) { rec.x = f0 | (c.e1 << 16); AR_BUMP_CASE (1, c.e1, c.e0) }
+    else if ((c.e2 >> 16) == sym) { rec.x = (f0 + (c.e1 & 0xffffu)) | (c.e2 << 16); AR_BUMP_CASE (2, c.e2, c.e1) }
+    else if ((c.e3 >> 16) == sym) { rec.x = (f0 + (c.e1 & 0xffffu) + (c.e2 & 0xffffu)) | (c.e3 << 16); AR_BUMP_CASE (3, c.e3, c.e2) }
+    else {
+        const ArHit h = ar_find_sym (m, maxs, sym, lane);
+        const uint32_t p = h.p, e = h.e, prev = h.prev;
+        if (p >= maxs) { rec.x = 1u << 16; return rec; }                    // cannot happen for a symbol < maxs
+        rec.x = h.acc | (e << 16);
+        AR_BUMP_DEEP (p, e, prev)
+    }
+    return rec;
+}
+
+__global__ void __launch_bounds__(128) k_ar_split_model (EncLeafDyn *dyn, const uint32_t *list, uint32_t n_list)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;       // (leaf slot, context)
+    const uint32_t slot = w >> 8, ctx = w & 255;
+    if (slot >= n_list) return;
+    EncLeafDyn &D = dyn[list[slot]];
+    if (!ar_split_leaf (D)) return;
+    const uint32_t maxs = D.nsym;
+    if (ctx >= maxs) return;
+    const uint32_t j0 = D.split_start[ctx], j1 = D.split_start[ctx + 1];
+    if (j0 == j1) return;
+    const uint8_t * __restrict__ in = D.eff_in;
+    const uint32_t * __restrict__ pos = D.split_pos;
+    uint2 *recs = D.split_rec;
+    uint32_t *m = D.models + ctx * ar_stride (maxs);
+    ArCache c; ar_load (m, c);
+    bool dirty = false;
+    for (uint32_t j = j0; j < j1; j += 32) {
+        const uint32_t cnt = min (32u, j1 - j);
+        uint32_t my_p = 0, my_s = 0;
+        if ((uint32_t)lane < cnt) { my_p = pos[j + lane]; my_s = in[my_p]; }   // 32 symbols of the sub-sequence at once: the loads are off the chain
+        uint32_t my_x = 0, my_y = 0;
+        for (uint32_t t = 0; t < cnt; t++) {
+            const uint32_t s = __shfl_sync (0xffffffffu, my_s, t);
+            uint2 rec;
+            if ((c.e0 >> 16) == s && c.tot + AR_STEP <= AR_MAXF) {           // the top entry again: registers only (written back when another symbol comes)
+                rec.x = c.e0 << 16; rec.y = c.tot;
+                c.e0 += AR_STEP; c.tot += AR_STEP;
+                dirty = true;
+            }
+            else {
+                if (dirty) { c.rtot = ar_rcp_below (c.tot); ar_flush (m, c); dirty = false; }
+                bool stale = false;
+                rec = ar_model_rec (m, maxs, c, s, lane, stale);
+                if (stale) ar_load (m, c);
+            }
+            if ((uint32_t)lane == t) { my_x = rec.x; my_y = rec.y; }
+        }
+        if ((uint32_t)lane < cnt) recs[my_p] = make_uint2 (my_x, my_y);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ stage B
+__global__ void __launch_bounds__(128) k_ar_split_code (const EncLeaf *leaves, EncLeafDyn *dyn, const uint32_t *list, uint32_t n_list)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (slot >= n_list) return;
+    const uint32_t li = list[slot];
+    EncLeafDyn &D = dyn[li];
+    if (!ar_split_leaf (D)) return;
+    const uint32_t n = D.eff_n;
+    const uint2 * __restrict__ recs = D.split_rec;
+    uint8_t *out = leaves[li].outbuf;
+    out[0] = (uint8_t)D.nsym;                                                // arith_dynamic.c:162-167 (256 wraps to 0)
+    ArEnc rc; rc.low = 0; rc.range = 0xffffffffu; rc.ffnum = 0; rc.cache = 0; rc.carry = 0; rc.out = out + 1;
+    const uint8_t *limit = out + n + 8;
+    uint32_t len = 0;
+    bool full = false;
+    for (uint32_t i0 = 0; i0 < n && !full; i0 += 32) {
+        const uint32_t cnt = min (32u, n - i0);
+        uint2 my = make_uint2 (1u << 16, 1u);
+        if ((uint32_t)lane < cnt) my = recs[i0 + lane];
+        const float my_r = ar_rcp_below (my.y);                              // 32 reciprocals at once, off the chain
+        for (uint32_t t = 0; t < cnt; t++) {
+            const uint32_t x = __shfl_sync (0xffffffffu, my.x, t), tot = __shfl_sync (0xffffffffu, my.y, t);
+            const float rt = __shfl_sync (0xffffffffu, my_r, t);
+            const uint32_t r = ar_div (rc.range, tot, rt);                   // RC_Encode (c_range_coder.h:97-109)
+            const uint32_t before = rc.low;
+            rc.low += (x & 0xffffu) * r; rc.range = (x >> 16) * r;
+            rc.carry += rc.low < before;
+            if (rc.range < AR_TOP) {
+                do { rc.range <<= 8; ar_shift_low (rc); } while (rc.range < AR_TOP);
+                if (rc.out + rc.ffnum > limit) { full = true; break; }       // certain to reach the input length: stored raw (arith_dynamic.c:847-852)
+            }
+        }
+    }
+    if (full) len = n + 1;
+    else { for (int i = 0; i < 5; i++) ar_shift_low (rc); len = (uint32_t)(rc.out - out); }   // RC_FinishEncode
+    if (lane == 0) { D.tab_len = len; D.payload_len = 0; }
+}
+
+void launch_arith_encode_split (EncPlanDev &P, cudaStream_t st)
+{
+    if (!P.n_arith_big) return;
+    k_ar_split_bucket<<<P.n_arith_big, SPLIT_WARPS * 32, 0, st>>>(P.dyn, P.arith_list, P.n_arith_big);
+    k_ar_split_model<<<P.n_arith_big * 64, 128, 0, st>>>(P.dyn, P.arith_list, P.n_arith_big);
+    k_ar_split_code<<<(P.n_arith_big + 3) / 4, 128, 0, st>>>(P.leaves, P.dyn, P.arith_list, P.n_arith_big);
+}
+
+} // namespace gzb

@@ -72,6 +72,9 @@ struct EncLeafDyn {              // device-written state of a leaf
     EncSym   *symtab;            // rANS: [256] by symbol (O0) or [nsym][nsym] by rank (O1) (arena)
     uint8_t  *ctxbytes;          // rANS O1: nsym x CTXB temp for per-context encoded frequencies (arena)
     uint32_t *models;            // arith: adaptive model memory (arena)
+    uint32_t *split_pos;         // arith, split encoder (arith_split.cu): positions grouped by context, in order (arena); nullptr = not split
+    uint32_t *split_start;       //   257 offsets into split_pos
+    uint2    *split_rec;         //   per symbol: cumFreq | freq << 16, totFreq
     uint32_t eff_n;
     uint32_t hdr_len;            // container header: flags byte, [varint n], [pack meta, varint packed_len]
     uint32_t tab_len;            // bytes of frequency table at outbuf[0..)

@@ -249,7 +249,7 @@ __global__ void k_leaf_prep (const EncLeaf *leaves, EncLeafDyn *dyn, uint32_t n_
             if (L.hist0[i] || (i == 0 && order && L.coder == CODER_RANS)) D.rank[i] = (uint8_t)ns++;   // O1: symbol 0 forced present (:741)
             else D.rank[i] = 0;
         D.nsym = (uint16_t)ns; s_nsym = ns;
-        D.hist1 = nullptr; D.symtab = nullptr; D.ctxbytes = nullptr; D.models = nullptr;
+        D.hist1 = nullptr; D.symtab = nullptr; D.ctxbytes = nullptr; D.models = nullptr; D.split_pos = nullptr; D.split_start = nullptr; D.split_rec = nullptr;
         if (L.coder == CODER_RANS && D.eff_n) {
             if (order) {
                 D.hist1    = reinterpret_cast<uint32_t *>(arena.alloc ((unsigned long long)ns * ns * 4));
@@ -612,7 +612,7 @@ __global__ void __launch_bounds__(256) k_tables (const EncLeaf *leaves, EncLeafD
 // Model layout per context (words): [0] TotFreq, [1] sentinel, [2 .. 2+maxs) entries (freq | symbol<<16), then a zero
 // terminator — the reference's SIMPLE_MODEL (c_simple_model.h:77-103) restricted to the live entries.
 // model initialisation for all arithmetic leaves: one CTA per leaf
-__global__ void k_arith_init (const EncLeaf *leaves, EncLeafDyn *dyn, const uint32_t *list, uint32_t n_list, Arena arena)
+__global__ void k_arith_init (const EncLeaf *leaves, EncLeafDyn *dyn, const uint32_t *list, uint32_t n_list, Arena arena, uint32_t split_min)
 {
     if (blockIdx.x >= n_list) return;
     const uint32_t li = list[blockIdx.x];
@@ -626,6 +626,12 @@ __global__ void k_arith_init (const EncLeaf *leaves, EncLeafDyn *dyn, const uint
         for (int i = 255; i >= 0; i--) if (L.hist0[i]) { m = i; break; }
         s_max = m + 1; D.nsym = (uint16_t)(m + 1);
         D.models = s_m = reinterpret_cast<uint32_t *>(arena.alloc (((unsigned long long)nctx * ar_stride (m + 1) + 258 * AR_RUN_STRIDE) * 4));
+        if (s_m && D.eff_order && !(D.hdr[0] & F_RLE) && D.eff_n >= split_min) {       // long order-1 leaf: the split encoder (arith_split.cu)
+            uint32_t *sp = reinterpret_cast<uint32_t *>(arena.alloc (4ull * D.eff_n));
+            uint32_t *ss = reinterpret_cast<uint32_t *>(arena.alloc (4ull * 257));
+            uint2    *sr = reinterpret_cast<uint2 *>(arena.alloc (8ull * D.eff_n));
+            if (sp && ss && sr) { D.split_pos = sp; D.split_start = ss; D.split_rec = sr; }   // (else: the arena overflowed and the batch is replayed)
+        }
     }
     __syncthreads ();
     if (!s_m) return;
@@ -783,7 +789,7 @@ void enc_run (EncPlanDev &P, cudaStream_t st)
         if (P.any_o1) LAUNCH (k_hist1, P.n_tiles, 256, P.leaves, P.dyn, P.tiles, P.n_tiles);
         LAUNCH (k_tables, P.n_rans, 256, P.leaves, P.dyn, P.rans_list, P.n_rans);
     }
-    if (P.n_arith) LAUNCH (k_arith_init, P.n_arith, 256, P.leaves, P.dyn, P.arith_list, P.n_arith, P.arena);
+    if (P.n_arith) LAUNCH (k_arith_init, P.n_arith, 256, P.leaves, P.dyn, P.arith_list, P.n_arith, P.arena, P.split_min);
     // The rANS and the arithmetic leaves are independent and both kernels are latency-bound (a handful of warps per SM),
     // so they run concurrently: the arithmetic kernel is forked onto the engine's second stream and joined afterwards.
     cudaEventRecord (P.ev_chain0, st);
@@ -791,6 +797,7 @@ void enc_run (EncPlanDev &P, cudaStream_t st)
         cudaStreamWaitEvent (P.st2, P.ev_chain0, 0);
         cudaEventRecord (P.ev_arith0, P.st2);
         launch_arith_encode (P, P.st2); P.launches++;
+        if (P.n_arith_big) { launch_arith_encode_split (P, P.st2); P.launches += 3; }
         cudaEventRecord (P.ev_chain2, P.st2);
         cudaStreamWaitEvent (P.st3, P.ev_chain0, 0);
         launch_arith_encode_o0 (P, P.st3); P.launches++;

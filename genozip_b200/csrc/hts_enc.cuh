@@ -13,6 +13,7 @@ struct EncPlanDev {              // device pointers of one encode batch
     uint32_t      *rans_list;  uint32_t n_rans;           // rANS leaves: requested order 1 first, then order 0; longest first within each
     uint2         *rans_jobs;  uint32_t n_rans_jobs;      // warp jobs: (first index into rans_list, count <= 8)
     uint32_t      *arith_list; uint32_t n_arith;          // arithmetic leaves, longest first
+    uint32_t       n_arith_big, split_min;                // the first n_arith_big of them are at least split_min long: candidates of the split encoder
     SectionResult *results;
     CopySeg       *segs;
     uint8_t       *stripe_hdr;
@@ -48,6 +49,7 @@ void launch_rans_decode (DecPlanDev &P, cudaStream_t st);
 void launch_arith_encode (EncPlanDev &P, cudaStream_t st);
 void launch_arith_decode (DecPlanDev &P, cudaStream_t st);
 void launch_arith_encode_o0 (EncPlanDev &P, cudaStream_t st);
+void launch_arith_encode_split (EncPlanDev &P, cudaStream_t st);
 void launch_arith_decode_o0 (DecPlanDev &P, cudaStream_t st);
 
 } // namespace gzb
