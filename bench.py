@@ -228,10 +228,17 @@ def run_gpu(args):
     eng = Engine(local)
     from genozip_b200 import GzbError
     V = args.vblocks
-    if V <= 0:                                                  # BASELINE configs[1] is ~390 VBlocks per GPU; take what fits comfortably
+    if V <= 0:                                                  # the entropy chains are latency-bound: throughput grows with the batch, memory bounds it
         free_b, _ = torch.cuda.mem_get_info(dev)
-        per_vb = 16.0 * args.reads * args.read_len + (32 << 20)   # inputs, DOMQ/ACGT intermediates, sections, outputs, engine workspace
-        V = int(max(8, min(512, (0.80 * free_b) // per_vb)))
+        n = args.reads * args.read_len
+        per_vb = 9.3 * n + 14 * args.reads + (6 << 20)          # inputs 2n, 2-bit words n/4, exception stream n, DOMQ streams ~0.4n, outputs 2n, engine workspace ~3.5n
+        V = int(max(8, min(768, (0.86 * free_b) // per_vb)))     # (measured on B200: 512 -> 17.7, 768 -> 22.2, 819 -> 21.7 GB/s: beyond ~768 the chain kernels are issue-bound)
+        if not args.no_e2e:                                     # the host-buffer leg keeps pinned copies of inputs and outputs: ~4.6n per VBlock
+            try:
+                import psutil
+                V = int(max(8, min(V, (0.45 * psutil.virtual_memory().available) // (4.6 * n))))
+            except Exception:
+                pass
     while True:                                                  # a batch that does not fit is halved (all ranks agree on the size)
         if world > 1:
             t = torch.tensor([V], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MIN); V = int(t.item())
@@ -241,6 +248,7 @@ def run_gpu(args):
             path = FastqCodecPath(eng, V, args.reads, args.read_len)
             # VBlocks are sharded round-robin by vblock_i: rank r owns vblock_i = r+1, r+1+world, ...  Seeds follow vblock_i.
             data = synth_vblocks(V, args.reads, args.read_len, 1000 + rank, dev)
+            torch.cuda.empty_cache()                           # (the generator's temporaries: the engines allocate with cudaMalloc, outside torch's cache)
             codecs = path.assign_codecs(data) if rank == 0 else None
             if world > 1:
                 obj = [codecs]; dist.broadcast_object_list(obj, src=0); codecs = obj[0]
@@ -248,6 +256,7 @@ def run_gpu(args):
             # correctness gate before timing: piz(zip(x)) == x on the device
             meta = path.zip_device(data)
             path.alloc_piz(meta)
+            path.scrub_intermediates()                         # piz decodes into the buffers zip's intermediates occupied: empty them for the gate
             path.piz_device(meta)
             torch.cuda.synchronize()
         except (torch.OutOfMemoryError, GzbError) as ex:
@@ -261,16 +270,16 @@ def run_gpu(args):
         if path is not None:
             path.close()
         del path, data
+        import gc; gc.collect()
         eng.close(); torch.cuda.empty_cache()
         eng = Engine(local)
-        V = max(4, V // 2)
+        V = max(4, int(V * 0.8))
     committed = load_codecs()
     rederived_equal = committed == dict(codecs)
     codecs = committed                                         # both arms run the committed table (see CODEC_TABLE)
     path.codec = dict(codecs)
     if not rederived_equal:                                    # (sizes were planned for the re-derived table)
-        path.comp_d = {}
-        meta = path.zip_device(data); path.alloc_piz(meta); path.piz_device(meta); torch.cuda.synchronize()
+        meta = path.zip_device(data); path.scrub_intermediates(); path.piz_device(meta); torch.cuda.synchronize()
     assert torch.equal(path.seq_out_d, data["seq"]) and torch.equal(path.qual_out_d, data["qual"]), "round trip failed"
     for s in ("Q_TILE", "Q_X", "Q_Y", "Q_MISC"):
         assert torch.equal(path.dec_d[s][:, :data[s].shape[1]], data[s]), f"round trip failed: {s}"
@@ -384,6 +393,8 @@ def run_gpu(args):
                        "reads_per_vblock": args.reads, "read_len": args.read_len, "txt_bytes_per_step_per_gpu": txt_bytes,
                        "codecs": codecs, "codecs_rederived_equal": rederived_equal, "compressed_bytes_per_vblock": comp_total / V, "l2": "inputs (>= 0.9 GB per step) are larger than L2; no flush needed",
                        "sections_per_step": sum(1 for m in meta for n in m["len"].values() if n), "compressed_bytes_per_step": comp_total,
+                       "txt_accounting": "input bytes = the FASTQ text the VBlocks represent (45-byte name line, SEQ, '+', QUAL, 4 newlines per read); of the name line, "
+                                         "10 B/read of segmented read-name contexts flow through the path (the segmenter is out of scope); the same count in both arms",
                        "excluded": EXCLUDED, "sharding": "VBlocks round-robin by vblock_i, no data-path collective; NCCL all_gather of the section list only",
                        "engines_per_gpu": len(path.engs), "device_groups": len(path.groups)},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,

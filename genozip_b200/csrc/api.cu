@@ -19,7 +19,7 @@
 
 using namespace gzb;
 
-static std::string g_last_error;
+static thread_local std::string g_last_error;       // creation errors, per calling thread (engines are made by the thread that owns them)
 
 #define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { e->err = std::string (#call) + ": " + cudaGetErrorString (_e); return GZB_E_CUDA; } } while (0)
 
@@ -93,20 +93,29 @@ extern "C" int gzb_engine_create (int device, gzb_engine **out)
     if (cudaGetDeviceProperties (&prop, device) != cudaSuccess || prop.major < 10) {
         g_last_error = "device is not sm_100-class: libgzb200 ships sm_100a kernels only"; return GZB_E_NOCUDA;
     }
+    cudaGetLastError ();                                                    // (an earlier failure of this thread — an allocation that did not fit, say — is not this engine's)
     gzb_engine *e = new gzb_engine ();
     e->device = device;
     e->sm_count = prop.multiProcessorCount;
-    if (cudaSetDevice (device) != cudaSuccess || cudaStreamCreateWithFlags (&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
-        g_last_error = "cudaStreamCreate failed"; delete e; return GZB_E_CUDA;
+    bool ok = cudaSetDevice (device) == cudaSuccess && cudaStreamCreateWithFlags (&e->stream, cudaStreamNonBlocking) == cudaSuccess;
+    cudaEvent_t *evs[5] = { &e->ev0, &e->ev1, &e->ev2, &e->ev3, &e->ev4 };
+    for (int i = 0; ok && i < 5; i++) ok = cudaEventCreate (evs[i]) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags (&e->stream2, cudaStreamNonBlocking) == cudaSuccess
+            && cudaStreamCreateWithFlags (&e->stream3, cudaStreamNonBlocking) == cudaSuccess;
+    if (!ok) {                                                              // a half-made engine would fork its chains onto null streams
+        g_last_error = std::string ("engine creation failed: ") + cudaGetErrorString (cudaGetLastError ());
+        gzb_engine_destroy (e); return GZB_E_CUDA;
     }
-    cudaEventCreate (&e->ev0); cudaEventCreate (&e->ev1); cudaEventCreate (&e->ev2); cudaEventCreate (&e->ev3); cudaEventCreate (&e->ev4);
-    cudaStreamCreateWithFlags (&e->stream2, cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags (&e->stream3, cudaStreamNonBlocking);
     // log tables for the order-1 table-size decision: must come from the same libm the reference links
     double l10[257], l12[257];
     for (int k = 0; k <= 256; k++) { l10[k] = log ((double)(1024 + k)); l12[k] = log ((double)(4096 + k)); }
     upload_log_tables (l10, l12);
-    if (cudaGetLastError () != cudaSuccess) { g_last_error = "no sm_100a kernel image for this device"; delete e; return GZB_E_NOCUDA; }
+    const cudaError_t err = cudaGetLastError ();
+    if (err != cudaSuccess) {
+        g_last_error = err == cudaErrorNoKernelImageForDevice || err == cudaErrorInvalidDeviceFunction ? "no sm_100a kernel image for this device"
+                                                                                                      : std::string ("engine creation failed: ") + cudaGetErrorString (err);
+        gzb_engine_destroy (e); return err == cudaErrorNoKernelImageForDevice || err == cudaErrorInvalidDeviceFunction ? GZB_E_NOCUDA : GZB_E_CUDA;
+    }
     *out = e;
     return GZB_OK;
 }
@@ -115,16 +124,30 @@ extern "C" void gzb_engine_destroy (gzb_engine *e)
 {
     if (!e) return;
     cudaSetDevice (e->device);
-    cudaStreamSynchronize (e->stream);
+    if (e->stream) cudaStreamSynchronize (e->stream);
     if (e->ws) cudaFree (e->ws);
     if (e->dq_buf) cudaFree (e->dq_buf);
     if (e->dq_session && e->dq_free) e->dq_free (e->dq_session);
     if (e->pin) cudaFreeHost (e->pin);
-    cudaEventDestroy (e->ev0); cudaEventDestroy (e->ev1); cudaEventDestroy (e->ev2); cudaEventDestroy (e->ev3); cudaEventDestroy (e->ev4);
+    cudaEvent_t evs[5] = { e->ev0, e->ev1, e->ev2, e->ev3, e->ev4 };
+    for (cudaEvent_t ev : evs) if (ev) cudaEventDestroy (ev);
     if (e->stream2) cudaStreamDestroy (e->stream2);
     if (e->stream3) cudaStreamDestroy (e->stream3);
-    cudaStreamDestroy (e->stream);
+    if (e->stream) cudaStreamDestroy (e->stream);
     delete e;
+}
+
+// give the grow-only workspace and staging back (a batch of another shape follows, or other engines need the memory)
+extern "C" int gzb_engine_trim (gzb_engine *e)
+{
+    if (!e) return GZB_E_BADARG;
+    cudaSetDevice (e->device);
+    CK (cudaStreamSynchronize (e->stream));
+    if (e->ws) { cudaFree (e->ws); e->ws = nullptr; e->ws_cap = 0; }
+    if (e->dq_session && e->dq_free) { e->dq_free (e->dq_session); e->dq_session = nullptr; }
+    if (e->dq_buf) { cudaFree (e->dq_buf); e->dq_buf = nullptr; e->dq_cap = 0; }
+    if (e->pin) { cudaFreeHost (e->pin); e->pin = nullptr; e->pin_cap = 0; }
+    return GZB_OK;
 }
 
 extern "C" const char *gzb_last_error (gzb_engine *e) { return e ? e->err.c_str () : g_last_error.c_str (); }

@@ -142,7 +142,7 @@ class FastqCodecPath:
     The host-buffer path gives each of the three independent pipelines of a FASTQ VBlock (QUAL, SEQ, read names) its own engine
     (host thread + CUDA stream) so that transfers overlap the entropy chains (zip_host / piz_host)."""
 
-    def __init__(self, eng: Engine, V, n_reads, read_len, n_engines=3, sub_batch=32):
+    def __init__(self, eng: Engine, V, n_reads, read_len, n_engines=3, sub_batch=128):
         self.eng, self.L = eng, eng.L
         self.V, self.n_reads, self.read_len = V, n_reads, read_len
         self.n = n = n_reads * read_len
@@ -416,6 +416,8 @@ class FastqCodecPath:
     def alloc_host(self, data):
         """pinned host copies of the inputs and pinned host buffers for every output"""
         pin = lambda t: _pin(t.cpu() if t.is_cuda else t.clone())           # separate host buffers either way
+        for e in self.engs:                                                  # the host-buffer mode deals the leaves to three engines: the device mode's single big
+            if hasattr(e, "trim"): e.trim()                                  # workspace goes back first
         self.h = {k: pin(v) for k, v in data.items()}
         V, n = self.V, self.n
         hp = lambda *shape: _pin(torch.empty(shape, dtype=torch.uint8))

@@ -183,6 +183,11 @@ class Engine:
     def sync(self):
         self.L.gzb_engine_sync(self.h)
 
+    def trim(self):
+        """give the engine's grow-only workspace back (it is re-allocated on demand)"""
+        if hasattr(self.L, "gzb_engine_trim"):
+            self.L.gzb_engine_trim(self.h)
+
     # ---- simple codecs, host buffers (numpy uint8 arrays) ----
     def compress(self, items):
         """items: list of (codec_name, np.uint8 array) -> list of np.uint8 arrays (compressed section bodies)."""

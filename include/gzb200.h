@@ -65,6 +65,7 @@ void  gzb_engine_destroy (gzb_engine *e);
 const char *gzb_last_error (gzb_engine *e);                       /* e may be NULL: creation errors */
 void *gzb_engine_stream (gzb_engine *e);                          /* the cudaStream_t all work of this engine is ordered on */
 int   gzb_engine_sync (gzb_engine *e);
+int   gzb_engine_trim (gzb_engine *e);                            /* frees the engine's grow-only device workspace and pinned staging (they come back on demand) */
 int   gzb_vb_device (uint32_t vblock_i, int n_devices);           /* (vblock_i-1) mod n_devices — the dispatcher's round-robin */
 uint64_t gzb_kernel_launches (gzb_engine *e);                     /* kernels launched by this engine so far */
 /* Device-time of the dominant chain kernels of the LAST batch call, ms (CUDA events on the engine's stream) */
@@ -275,6 +276,87 @@ uint32_t gzb_codec_ARTB_est_size (Codec codec, uint64_t uncompressed_len);
 uint32_t gzb_codec_ARTW_est_size (Codec codec, uint64_t uncompressed_len);
 uint32_t gzb_codec_ARTb_est_size (Codec codec, uint64_t uncompressed_len);
 uint32_t gzb_codec_ARTw_est_size (Codec codec, uint64_t uncompressed_len);
+
+
+/* ---------------------------------------------------------------- the complex codecs behind the reference's signatures
+ * Table rows src/codec.h:99-101,108-109:  DOMQ { codec_domq_compress, USE_SUBCODEC, codec_domq_reconstruct },
+ * PBWT { codec_pbwt_compress, codec_pbwt_uncompress, codec_pbwt_reconstruct }, LONGR { codec_longr_compress, USE_SUBCODEC,
+ * codec_longr_reconstruct }, ACGT { codec_acgt_compress, codec_acgt_uncompress }, XCGT { USE_SUBCODEC, codec_xcgt_uncompress }.
+ * These reach into sibling contexts, the section header, vb->scratch and the codec table, so the adapter inside
+ * genozip registers a second accessor table.  `sibling` counts contexts from the one the codec was called with, as the
+ * reference's `ctx + 1` does (DOMQ: 0 QUAL, 1 DOMQRUNS, 2 QUALMPLX, 3 DIVRQUAL — declare_domq_contexts, src/codec_domq.c:34-38;
+ * ACGT: 0 NONREF, 1 NONREF_X; LONGR: 0 the lengths, 1 the values; PBWT: 0 the matrix, 1 RUNS, 2 FGRC — decl_pbwt_contexts). */
+typedef void CodecReconstructFn (VBlockP vb, Codec codec, ContextP ctx, uint32_t len, bool reconstruct);   /* src/codec.h:42-43 */
+enum { GZB_HDR_SUB_CODEC = 1, GZB_HDR_ACGT_NO_X = 2 };
+typedef struct {
+    /* ---- ZIP ---- */
+    char    *(*local_alloc)     (VBlockP vb, ContextP ctx, int sibling, uint64_t bytes);    /* buf_alloc (vb, &(ctx+sibling)->local, …) → .data (contents kept) */
+    char    *(*local_data)      (ContextP ctx, int sibling, uint64_t *len_bytes);           /* (ctx+sibling)->local.data and its length in bytes */
+    void     (*local_set_len)   (ContextP ctx, int sibling, uint64_t len_bytes);
+    void     (*local_free)      (VBlockP vb, ContextP ctx, int sibling);                    /* buf_free / buf_destroy */
+    uint8_t *(*local_prm8)      (ContextP ctx, int sibling);                                /* &(ctx+sibling)->local.prm8[0] */
+    char    *(*scratch_alloc)   (VBlockP vb, uint64_t bytes);                               /* vb->scratch: buf_alloc → .data; bytes = 0: the buffer as it stands */
+    void     (*scratch_free)    (VBlockP vb);
+    bool     (*ctx_acgt_no_x)   (ContextP ctx, int sibling);                                /* (ctx+sibling)->flags.acgt_no_x */
+    void     (*header_set)      (SectionHeaderP header, int field, uint32_t value);         /* GZB_HDR_SUB_CODEC: header->sub_codec; GZB_HDR_ACGT_NO_X: header->flags.ctx.acgt_no_x */
+    Codec    (*assign_sub_codec)(VBlockP vb, ContextP ctx, int sibling);                    /* codec_assign_best_codec (vb, ctx+sibling, &local, SEC_LOCAL); never CODEC_UNKNOWN (→ CODEC_NONE);
+                                                                                               for ACGT's sibling 1 the adapter also sets lsubcodec_piz / lcodec = XCGT (src/codec_acgt.c:143-152) */
+    bool     (*sub_compress)    (Codec c, VBlockP vb, ContextP ctx, SectionHeaderP header, const char *data, uint32_t *len,
+                                 char *compressed, uint32_t *compressed_len, FailType soft_fail, const char *name);   /* codec_args[c].compress */
+    uint32_t (*sub_est_size)    (Codec c, uint64_t len);                                    /* codec_args[c].est_size */
+    void     (*seg_denorm)      (VBlockP vb, ContextP qual_ctx, const uint8_t *denorm, uint32_t len);   /* base64 + seg_by_ctx into DOMQRUNS (src/codec_domq.c:241-244) */
+    bool     (*seq_line)        (VBlockP vb, ContextP ctx, uint32_t vb_line_i, char **seq, uint32_t *seq_len, bool *is_rev);   /* fastq_zip_seq / sam_zip_seq (src/codec_longr.c:170) */
+    const uint8_t *(*codec_table) (VBlockP vb, ContextP ctx);                              /* the codec's small table, for the ctx the codec was called with.  LONGR: the 256-byte value-to-bin map of ctx+1
+                                                                                               (ZCTX(values)->value_to_bin in ZIP, from SEC_COUNTS in PIZ, src/codec_longr.c:316-330).  DOMQ reconstruct: the
+                                                                                               de-normalisation table from DOMQRUNS' dictionary: byte 0 = number of doms, then [num_doms][num_norm_qs] */
+    void     (*pbwt_dims)       (VBlockP vb, ContextP ht_ctx, uint32_t *n_lines, uint32_t *ht_per_line, int set);   /* ht_ctx->HT_n_lines, ->ht_per_line (get; set != 0: store ht_per_line) */
+    void     (*add_lines)       (int which, uint64_t n);                                    /* z_file->domq_lines / longr_lines (src/codec_domq.c:489-492, src/codec_longr.c:181): 0 DOMQ dom, 1 DOMQ diverse, 2 LONGR */
+    void     (*account_time)    (VBlockP vb, int which, uint64_t nanosec);                  /* COPY_TIMER (compressor_domq …), src/profiler.h:18-24: 0 domq 1 acgt 2 xcgt 3 pbwt 4 longr */
+    /* ---- PIZ ---- */
+    void     (*sub_uncompress)  (Codec c, VBlockP vb, ContextP ctx, uint8_t param, const char *compressed, uint32_t compressed_len,
+                                 BufferP uncompressed_buf, uint64_t uncompressed_len, const char *name);               /* codec_args[c].uncompress */
+    BufferP  (*packed_buffer)   (VBlockP vb, ContextP ctx, int sibling, uint64_t bytes);   /* (ctx+sibling)->flags.acgt_no_x ? &vb->scratch : &(ctx+sibling)->packed, allocated to `bytes` when > 0 */
+    void    **(*codec_state)    (VBlockP vb, ContextP ctx);                                 /* one pointer slot that lives with the VBlock's context (like lens_ctx->longr_state): the staging of a bulk decode */
+    const uint32_t *(*recon_line_lens) (VBlockP vb, ContextP ctx, uint32_t *n_lines);      /* the `len` of every future reconstruct call of this context in this VBlock, in order */
+    bool     (*recon_seq_table) (VBlockP vb, ContextP ctx, const char **txt, uint64_t *txt_len, const uint64_t **seq_off, const uint8_t **is_rev);   /* LONGR: every read's SEQ up front (bulk SEQ reconstruct) */
+    char    *(*recon_at)        (VBlockP vb);                                               /* BAFTtxt */
+    void     (*recon_advance)   (VBlockP vb, int32_t n);                                    /* Ltxt += n (n < 0: remove characters) */
+    int64_t  (*pbwt_big_allele) (VBlockP vb);                                               /* reconstruct_from_local_int (vb, CTX(FORMAT_GT_HT_BIG), 0, RECON_OFF) */
+    bool     (*drop_curr_line)  (VBlockP vb);
+    void     (*missing_quality) (VBlockP vb, bool reconstruct);                             /* sam_reconstruct_missing_quality */
+} gzb_plugin_host2;
+void gzb_plugin_register2 (const gzb_plugin_host2 *host);
+void gzb_plugin_shutdown (void);                                   /* destroys the pooled engines (process exit / plug-in unregistered) */
+
+/* ZIP */
+bool gzb_codec_domq_comp_init (VBlockP vb, ContextP qual_ctx, LocalGetLineCB get_line_cb, bool force);   /* codec_domq_comp_init (src/codec_domq.c:299-323) */
+GZB_COMPRESS (gzb_codec_domq_compress);                            /* src/codec_domq.c:379-521 */
+GZB_COMPRESS (gzb_codec_acgt_compress);                            /* src/codec_acgt.c:64-176 */
+GZB_COMPRESS (gzb_codec_pbwt_compress);                            /* src/codec_pbwt.c:244-287 */
+GZB_COMPRESS (gzb_codec_longr_compress);                           /* src/codec_longr.c:161-264 */
+uint32_t gzb_codec_complex_est_size (Codec codec, uint64_t uncompressed_len);    /* src/codec.c codec_complex_est_size */
+uint32_t gzb_codec_longr_est_size   (Codec codec, uint64_t uncompressed_len);    /* src/codec_longr.c:53-56 */
+/* PIZ */
+GZB_UNCOMPRESS (gzb_codec_acgt_uncompress);                        /* src/codec_acgt.c:216-248 */
+GZB_UNCOMPRESS (gzb_codec_xcgt_uncompress);                        /* src/codec_acgt.c:185-209 */
+GZB_UNCOMPRESS (gzb_codec_pbwt_uncompress);                        /* src/codec_pbwt.c:372-402 */
+CodecReconstructFn gzb_codec_domq_reconstruct;                     /* src/codec_domq.c:774-809 */
+CodecReconstructFn gzb_codec_pbwt_reconstruct;                     /* src/codec_pbwt.c:406-449 */
+CodecReconstructFn gzb_codec_longr_reconstruct;                    /* src/codec_longr.c:342-373 */
+
+/* ---------------------------------------------------------------- combining submission
+ * comp_compress calls a codec once per section from every compute thread (src/compressor.c:82-86); one launch per section is
+ * launch-latency-bound.  A combiner gathers the sections that several compute threads submit at about the same time into ONE
+ * gzb_compress_sections / gzb_uncompress_sections call: every thread submits its section and waits; the first waiter becomes the
+ * leader, takes everything that is pending (after giving the others `linger_us` to arrive) and runs the batch for all of them.
+ * The plug-in entry points above go through the process-wide combiners when gzb_plugin_set_combining (1) was called. */
+typedef struct gzb_combiner gzb_combiner;
+gzb_combiner *gzb_combiner_create (int device, int compress /* 1 = compress, 0 = uncompress */, uint32_t linger_us);
+void gzb_combiner_destroy (gzb_combiner *c);
+int  gzb_submit (gzb_combiner *c, const gzb_section *sec, uint64_t *ticket);         /* host pointers; thread-safe */
+int  gzb_wait   (gzb_combiner *c, uint64_t ticket, gzb_section *result);             /* status / out_len of the section; thread-safe */
+uint64_t gzb_combiner_batches (gzb_combiner *c);                                      /* batches run so far (sections / batches = the combining factor) */
+void gzb_plugin_set_combining (int on, uint32_t linger_us);
 
 #ifdef __cplusplus
 }
