@@ -84,28 +84,38 @@ __device__ __forceinline__ uint64_t pb_scan64 (uint64_t v, uint64_t (*ws)[PBT / 
 
 constexpr uint32_t NOKEY = 0xffffu;
 
+// SIMD helpers on the eight alleles a thread holds in one 64-bit word
+__device__ __forceinline__ uint32_t pb_cnt_eq (uint32_t lo, uint32_t hi, uint32_t key4, uint32_t vlo, uint32_t vhi)   // bytes of (lo, hi) equal to key among the valid ones
+{
+    return __popc (__vcmpeq4 (lo, key4) & vlo) + __popc (__vcmpeq4 (hi, key4) & vhi);
+}
+
+// One CTA per VBlock.  A thread owns a contiguous chunk of C8 (a multiple of 8) columns; it handles them eight at a time as
+// one 64-bit word of alleles and one 128-bit word of permutation indices.  A row whose alleles are all among '0' '1' '2' (the
+// common case) takes the SIMD path: three barriers — the gather (which also tells, through its OR, whether any other allele
+// turned up), one packed scan, the scatter.  Any other row takes the general passes over the set of alleles present.
 template <int DEC>
 __global__ void __launch_bounds__(PBT) k_pbwt_rows (const PbVb *vbs)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint64_t ws[2][PBT / 32];
-    __shared__ uint32_t bm[2][8];
+    __shared__ uint32_t bm[8];
     __shared__ uint64_t bar[PB_RING];
     const PbVb &V = vbs[blockIdx.x];
     const uint32_t w = V.w, n_lines = V.n_lines;
     if (V.wide || !w || !n_lines) return;
     const uint8_t *src = V.src; const uint64_t len = V.len;
-    const uint32_t slot = tma_slot_bytes (w);
-    uint16_t *P   = reinterpret_cast<uint16_t *>(smem);                      // two permutations of w 16-bit indices
-    uint8_t  *al  = smem + ((4 * (size_t)w + 15) & ~(size_t)15);             // the permuted row
-    uint8_t  *ring = al + ((w + 16 + 15) & ~15u);
+    const uint32_t slot = tma_slot_bytes (w), wp = (w + 7) & ~7u;
+    uint16_t *P   = reinterpret_cast<uint16_t *>(smem);                      // two permutations of w 16-bit indices (stride wp)
+    uint8_t  *al  = smem + 4 * (size_t)wp;                                   // the permuted row
+    uint8_t  *ring = al + ((wp + 16 + 15) & ~15u);
     uint8_t  *orow = ring + (size_t)PB_RING * slot;                          // decode: the un-permuted row, staged for aligned stores
-    const int tid = threadIdx.x, lane = tid & 31;
-    const uint32_t C = (w + PBT - 1) / PBT, lo = min (w, tid * C), hi = min (w, lo + C);
+    const int tid = threadIdx.x;
+    const uint32_t C8 = ((w + PBT * 8 - 1) / (PBT * 8)) * 8, lo = min (w, tid * C8), hi = min (w, lo + C8);
 
-    if (tid < 16) bm[tid >> 3][tid & 7] = 0;
+    if (tid < 8) bm[tid] = 0;
     if (tid == 0) { for (int s = 0; s < PB_RING; s++) mbar_init (&bar[s], 1); mbar_fence_init (); }
-    for (uint32_t i = tid; i < w; i += PBT) P[i] = (uint16_t)i;              // first line: identity (:146-148)
+    for (uint32_t i = tid; i < wp; i += PBT) P[i] = (uint16_t)i;             // first line: identity (:146-148)
     __syncthreads ();
     if (tid == 0)
         for (uint32_t r = 0; r < PB_RING && r < n_lines; r++) {
@@ -118,7 +128,7 @@ __global__ void __launch_bounds__(PBT) k_pbwt_rows (const PbVb *vbs)
     uint8_t carry = 0;                                                       // allele of the run that is open when a row starts
     for (uint32_t r = 0; r < n_lines; r++) {
         const uint32_t s = r % PB_RING, cur = r & 1;
-        const uint16_t *Pc = P + (size_t)cur * w; uint16_t *Pn = P + (size_t)(cur ^ 1) * w;
+        const uint16_t *Pc = P + (size_t)cur * wp; uint16_t *Pn = P + (size_t)(cur ^ 1) * wp;
         const uint8_t *g = src + (uint64_t)r * w;
         const bool staged = tma_superset_ok (g, w, src, len);
         mbar_wait (&bar[s], (r / PB_RING) & 1);
@@ -127,24 +137,30 @@ __global__ void __launch_bounds__(PBT) k_pbwt_rows (const PbVb *vbs)
         uint8_t *so = nullptr;
         if (DEC) so = orow + ((uintptr_t)(V.dst + (uint64_t)r * w) & 15);
 
-        // ---- the row in permuted order (:151-153 / :340-343) and the set of alleles it holds
-        uint32_t m0 = 0;
-        for (uint32_t i = lo; i < hi; i++) {
-            uint8_t a;
-            if (DEC) { a = row[back ? w - 1 - i : i]; so[Pc[i]] = a; }
-            else a = row[Pc[i]];
-            al[i] = a;
-            const uint32_t o = pb_ord (a);
-            if (o < 32) m0 |= 1u << o; else atomicOr (&bm[cur][o >> 5], 1u << (o & 31));
+        // ---- the row in permuted order (:151-153 / :340-343), eight columns at a time
+        uint32_t other = 0;
+        for (uint32_t i0 = lo; i0 < hi; i0 += 8) {
+            const uint32_t nv = min (8u, hi - i0);
+            const uint4 pv = *reinterpret_cast<const uint4 *>(Pc + i0);
+            const uint32_t pw[4] = { pv.x, pv.y, pv.z, pv.w };
+            uint32_t alo = 0x30303030u, ahi = 0x30303030u;                   // (columns past the end read as '0' and are masked where it matters)
+            #pragma unroll
+            for (uint32_t j = 0; j < 8; j++)
+                if (j < nv) {
+                    const uint32_t idx = (pw[j >> 1] >> (16 * (j & 1))) & 0xffffu;
+                    uint32_t a;
+                    if (DEC) { a = row[back ? w - 1 - (i0 + j) : i0 + j]; so[idx] = (uint8_t)a; }
+                    else a = row[idx];
+                    if (j < 4) alo = (alo & ~(0xffu << (8 * j))) | (a << (8 * j)); else ahi = (ahi & ~(0xffu << (8 * (j - 4)))) | (a << (8 * (j - 4)));
+                }
+            *reinterpret_cast<uint2 *>(al + i0) = make_uint2 (alo, ahi);
+            other |= __vcmpgtu4 (__vsub4 (alo, 0x30303030u), 0x02020202u) | __vcmpgtu4 (__vsub4 (ahi, 0x30303030u), 0x02020202u);
         }
-        m0 = __reduce_or_sync (0xffffffffu, m0);
-        if (lane == 0 && m0) atomicOr (&bm[cur][0], m0);
-        __syncthreads ();                                                    // B1: al, bm[cur] (and orow) complete; the ring slot is free
+        const int general = __syncthreads_or (other != 0);                   // B1: al (and orow) complete; the ring slot is free
         if (tid == 0 && r + PB_RING < n_lines) {
             const uint8_t *g2 = src + (uint64_t)(r + PB_RING) * w;
             if (tma_superset_ok (g2, w, src, len)) tma_row_issue (ring + (size_t)s * slot, g2, w, &bar[s]); else mbar_arrive (&bar[s]);
         }
-        if (tid < 8) bm[cur ^ 1][tid] = 0;                                   // for the next row (nobody reads it before B4)
 
         if (DEC) {                                                           // the finished row: head bytes, 16-byte body, tail bytes
             uint8_t *gd = V.dst + (uint64_t)r * w;
@@ -154,48 +170,122 @@ __global__ void __launch_bounds__(PBT) k_pbwt_rows (const PbVb *vbs)
             if ((uint32_t)tid < w - t0) gd[t0 + tid] = so[t0 + tid];
         }
 
-        // ---- passes of up to three alleles each: stable partition into the next permutation (:132-141); the first pass also
-        //      counts and records the run boundaries of the row in traversal order (:213-238)
-        uint32_t base = 0, k0 = NOKEY, k1 = NOKEY, k2 = NOKEY, nk = 0;
-        bool first = true;
-        for (uint32_t wd = 0; wd <= 8; wd++) {
-            uint32_t bits = (wd < 8 && part) ? bm[cur][wd] : 0;
-            while (bits || (wd == 8 && (nk || (first && !DEC)))) {
-                if (bits) {
-                    const uint32_t key = wd * 32 + (__ffs ((int)bits) - 1);
-                    bits &= bits - 1;
-                    if (nk == 0) k0 = key; else if (nk == 1) k1 = key; else k2 = key;
-                    if (++nk < 3) continue;
-                }
-                uint32_t c0 = 0, c1 = 0, c2 = 0, cb = 0;
-                for (uint32_t i = lo; i < hi; i++) { const uint32_t o = pb_ord (al[i]); c0 += o == k0; c1 += o == k1; c2 += o == k2; }
-                if (first && !DEC)
-                    for (uint32_t j = lo; j < hi; j++) {
-                        const uint8_t c = al[back ? w - 1 - j : j], p = j ? al[back ? w - j : j - 1] : carry;
-                        cb += c != p;
+        if (!general) {
+            // ---- SIMD path: alleles '0' '1' '2' only.  Counts of the three and of the run boundaries of the chunk, one scan,
+            //      then the stable partition into the next permutation (:132-141) and the boundary records (:213-238)
+            uint32_t c0 = 0, c1 = 0, c2 = 0, cb = 0;
+            if (part || !DEC)
+                for (uint32_t i0 = lo; i0 < hi; i0 += 8) {
+                    const uint32_t nv = min (8u, hi - i0);
+                    const uint2 a = *reinterpret_cast<const uint2 *>(al + i0);
+                    const uint32_t vlo = nv >= 4 ? 0x01010101u : (0x01010101u >> (8 * (4 - nv))), vhi = nv > 4 ? (0x01010101u >> (8 * (8 - nv))) : 0u;
+                    const uint32_t tl = __vsub4 (a.x, 0x30303030u), th = __vsub4 (a.y, 0x30303030u);
+                    c0 += pb_cnt_eq (tl, th, 0u, vlo, vhi); c1 += pb_cnt_eq (tl, th, 0x01010101u, vlo, vhi); c2 += pb_cnt_eq (tl, th, 0x02020202u, vlo, vhi);
+                    if (!DEC) {
+                        // neighbour in traversal order: the column before (forward rows) or after (backward rows); across the chunk
+                        // edge it comes from shared memory, at the row's first column in traversal order from the open run
+                        uint32_t nlo, nhi;
+                        if (!back) {
+                            const uint32_t pb = i0 ? al[i0 - 1] : carry;
+                            nlo = (a.x << 8) | pb; nhi = (a.y << 8) | (a.x >> 24);
+                        }
+                        else {
+                            const uint32_t sb = i0 + nv < w ? al[i0 + nv] : carry;        // successor of the last valid column
+                            uint32_t xl = a.x, xh = a.y;
+                            if (nv < 8) { if (nv < 4) xl = (xl & ~(0xffu << (8 * nv))) | (sb << (8 * nv)); else if (nv > 4) xh = (xh & ~(0xffu << (8 * (nv - 4)))) | (sb << (8 * (nv - 4))); else xh = (xh & ~0xffu) | sb; }
+                            nlo = (xl >> 8) | (xh << 24); nhi = (xh >> 8) | (nv == 8 ? sb << 24 : 0u);
+                        }
+                        cb += __popc (__vcmpne4 (a.x, nlo) & vlo) + __popc (__vcmpne4 (a.y, nhi) & vhi);
                     }
+                }
+            if (part || !DEC) {
                 uint64_t tot;
                 const uint64_t ex = pb_scan64 ((uint64_t)c0 | ((uint64_t)c1 << 16) | ((uint64_t)c2 << 32) | ((uint64_t)cb << 48), ws, flip, tot);
-                const uint32_t t0 = (uint32_t)tot & 0xffff, t1 = (uint32_t)(tot >> 16) & 0xffff, t2 = (uint32_t)(tot >> 32) & 0xffff;
-                uint32_t p0 = base + ((uint32_t)ex & 0xffff), p1 = base + t0 + ((uint32_t)(ex >> 16) & 0xffff), p2 = base + t0 + t1 + ((uint32_t)(ex >> 32) & 0xffff);
+                const uint32_t t0 = (uint32_t)tot & 0xffff, t1 = (uint32_t)(tot >> 16) & 0xffff;
+                uint32_t p0 = (uint32_t)ex & 0xffff, p1 = t0 + ((uint32_t)(ex >> 16) & 0xffff), p2 = t0 + t1 + ((uint32_t)(ex >> 32) & 0xffff);
                 if (part)
-                    for (uint32_t i = lo; i < hi; i++) {
-                        const uint32_t o = pb_ord (al[i]);
-                        if (o == k0) Pn[p0++] = Pc[i]; else if (o == k1) Pn[p1++] = Pc[i]; else if (o == k2) Pn[p2++] = Pc[i];
+                    for (uint32_t i0 = lo; i0 < hi; i0 += 8) {
+                        const uint32_t nv = min (8u, hi - i0);
+                        const uint2 a = *reinterpret_cast<const uint2 *>(al + i0);
+                        const uint4 pv = *reinterpret_cast<const uint4 *>(Pc + i0);
+                        const uint32_t pw[4] = { pv.x, pv.y, pv.z, pv.w };
+                        #pragma unroll
+                        for (uint32_t j = 0; j < 8; j++)
+                            if (j < nv) {
+                                const uint32_t t = (((j < 4 ? a.x : a.y) >> (8 * (j & 3))) - 0x30u) & 0xffu;
+                                const uint16_t idx = (uint16_t)(pw[j >> 1] >> (16 * (j & 1)));
+                                const uint32_t d = t == 0 ? p0++ : t == 1 ? p1++ : p2++;
+                                Pn[d] = idx;
+                            }
                     }
-                if (first && !DEC) {
-                    uint32_t bi = nbnd + (uint32_t)(ex >> 48);
-                    for (uint32_t j = lo; j < hi; j++) {
-                        const uint8_t c = al[back ? w - 1 - j : j], p = j ? al[back ? w - j : j - 1] : carry;
-                        if (c != p) {
-                            if (bi < V.bcap) { V.bpos[bi] = (uint32_t)((uint64_t)r * w + j); V.bal[bi] = c; } else err = PBE_CAP;
-                            bi++;
+                if (!DEC) {
+                    const uint32_t tb = (uint32_t)(tot >> 48), eb = (uint32_t)(ex >> 48);
+                    if (cb) {                                                // (few: a thread's boundaries are written one by one, in traversal order)
+                        uint32_t bi = nbnd + (back ? tb - eb - cb : eb);
+                        for (uint32_t k = 0; k < hi - lo; k++) {
+                            const uint32_t i = back ? hi - 1 - k : lo + k;
+                            const uint8_t c = al[i], nb = back ? (i + 1 < w ? al[i + 1] : carry) : (i ? al[i - 1] : carry);
+                            if (c != nb) {
+                                if (bi < V.bcap) { V.bpos[bi] = (uint32_t)((uint64_t)r * w + (back ? w - 1 - i : i)); V.bal[bi] = c; } else err = PBE_CAP;
+                                bi++;
+                            }
                         }
                     }
-                    nbnd += (uint32_t)(tot >> 48);
+                    nbnd += tb;
                 }
-                base += t0 + t1 + t2;
-                first = false; nk = 0; k0 = k1 = k2 = NOKEY;
+            }
+        }
+        else {
+            // ---- general path: the set of alleles of the row, then passes of up to three alleles each; the first pass also counts
+            //      and records the run boundaries
+            if (tid < 8) bm[tid] = 0;
+            __syncthreads ();
+            uint32_t m0 = 0;
+            for (uint32_t i = lo; i < hi; i++) { const uint32_t o = pb_ord (al[i]); if (o < 32) m0 |= 1u << o; else atomicOr (&bm[o >> 5], 1u << (o & 31)); }
+            m0 = __reduce_or_sync (0xffffffffu, m0);
+            if ((tid & 31) == 0 && m0) atomicOr (&bm[0], m0);
+            __syncthreads ();
+            uint32_t base = 0, k0 = NOKEY, k1 = NOKEY, k2 = NOKEY, nk = 0;
+            bool first = true;
+            for (uint32_t wd = 0; wd <= 8; wd++) {
+                uint32_t bits = (wd < 8 && part) ? bm[wd] : 0;
+                while (bits || (wd == 8 && (nk || (first && !DEC)))) {
+                    if (bits) {
+                        const uint32_t key = wd * 32 + (__ffs ((int)bits) - 1);
+                        bits &= bits - 1;
+                        if (nk == 0) k0 = key; else if (nk == 1) k1 = key; else k2 = key;
+                        if (++nk < 3) continue;
+                    }
+                    uint32_t c0 = 0, c1 = 0, c2 = 0, cb = 0;
+                    for (uint32_t i = lo; i < hi; i++) { const uint32_t o = pb_ord (al[i]); c0 += o == k0; c1 += o == k1; c2 += o == k2; }
+                    if (first && !DEC)
+                        for (uint32_t j = lo; j < hi; j++) {
+                            const uint8_t c = al[back ? w - 1 - j : j], p = j ? al[back ? w - j : j - 1] : carry;
+                            cb += c != p;
+                        }
+                    uint64_t tot;
+                    const uint64_t ex = pb_scan64 ((uint64_t)c0 | ((uint64_t)c1 << 16) | ((uint64_t)c2 << 32) | ((uint64_t)cb << 48), ws, flip, tot);
+                    const uint32_t t0 = (uint32_t)tot & 0xffff, t1 = (uint32_t)(tot >> 16) & 0xffff, t2 = (uint32_t)(tot >> 32) & 0xffff;
+                    uint32_t p0 = base + ((uint32_t)ex & 0xffff), p1 = base + t0 + ((uint32_t)(ex >> 16) & 0xffff), p2 = base + t0 + t1 + ((uint32_t)(ex >> 32) & 0xffff);
+                    if (part)
+                        for (uint32_t i = lo; i < hi; i++) {
+                            const uint32_t o = pb_ord (al[i]);
+                            if (o == k0) Pn[p0++] = Pc[i]; else if (o == k1) Pn[p1++] = Pc[i]; else if (o == k2) Pn[p2++] = Pc[i];
+                        }
+                    if (first && !DEC) {
+                        uint32_t bi = nbnd + (uint32_t)(ex >> 48);
+                        for (uint32_t j = lo; j < hi; j++) {
+                            const uint8_t c = al[back ? w - 1 - j : j], p = j ? al[back ? w - j : j - 1] : carry;
+                            if (c != p) {
+                                if (bi < V.bcap) { V.bpos[bi] = (uint32_t)((uint64_t)r * w + j); V.bal[bi] = c; } else err = PBE_CAP;
+                                bi++;
+                            }
+                        }
+                        nbnd += (uint32_t)(tot >> 48);
+                    }
+                    base += t0 + t1 + t2;
+                    first = false; nk = 0; k0 = k1 = k2 = NOKEY;
+                }
             }
         }
         carry = al[back ? 0 : w - 1];
@@ -514,8 +604,8 @@ __global__ void __launch_bounds__(PB_THREADS) k_pbwt_decode_wide (const PbVb *vb
 
 size_t pb_rows_smem (uint32_t w, bool dec)
 {
-    const size_t slot = tma_slot_bytes (w);
-    return ((4 * (size_t)w + 15) & ~(size_t)15) + ((w + 16 + 15) & ~15u) + (size_t)PB_RING * slot + (dec ? slot : 0) + 16;
+    const size_t slot = tma_slot_bytes (w), wp = (w + 7) & ~7u;
+    return 4 * wp + ((wp + 16 + 15) & ~(size_t)15) + (size_t)PB_RING * slot + (dec ? slot : 0) + 16;
 }
 bool pb_is_wide (uint32_t w, uint64_t len) { return w > 65535 || len >= (1ull << 32) || pb_rows_smem (w, true) > PB_SMEM_MAX; }
 

@@ -46,13 +46,14 @@ static inline uint4 make_uint4 (uint32_t x, uint32_t y, uint32_t z, uint32_t w) 
 
 // ---------------------------------------------------------------- the emulator's interface
 namespace simt {
-struct Thread { uint3 tid, bid; dim3 bdim, gdim; };
+struct Thread { uint3 tid, bid; dim3 bdim, gdim; uint32_t or_gen = 0; };
 extern thread_local Thread *cur;                                            // the fibre that is running on this OS thread
 void  launch (dim3 grid, dim3 block, size_t dyn_smem, const std::function<void ()> &body);
 void *dyn_smem ();
 enum Kind { K_SHFL_IDX, K_SHFL_UP, K_SHFL_DOWN, K_SHFL_XOR, K_BALLOT, K_REDUCE_ADD, K_REDUCE_OR, K_REDUCE_AND, K_REDUCE_MIN, K_REDUCE_MAX, K_MATCH_ANY, K_SYNCWARP };
 uint64_t collective (const char *file, int line, Kind kind, uint32_t mask, uint64_t v, int arg, int width);
 void     syncthreads (const char *file, int line);
+int      syncthreads_or (const char *file, int line, int pred);
 }
 #define threadIdx (simt::cur->tid)
 #define blockIdx  (simt::cur->bid)
@@ -82,6 +83,7 @@ template <class T> inline T shfl (const char *f, int l, Kind k, uint32_t mask, T
 #define __match_any_sync(m, v) ((uint32_t)simt::collective (__FILE__, __LINE__, simt::K_MATCH_ANY, (m), simt::to_bits (v), 0, 32))
 #define __syncwarp(...)       ((void)simt::collective (__FILE__, __LINE__, simt::K_SYNCWARP, simt::mask_or_full (__VA_ARGS__), 0, 0, 32))
 #define __syncthreads()       simt::syncthreads (__FILE__, __LINE__)
+#define __syncthreads_or(p)   simt::syncthreads_or (__FILE__, __LINE__, (p) ? 1 : 0)
 namespace simt { inline uint32_t mask_or_full () { return 0xffffffffu; } inline uint32_t mask_or_full (uint32_t m) { return m; } }
 
 // ---------------------------------------------------------------- integer / float intrinsics
@@ -109,6 +111,9 @@ static inline uint32_t __byte_perm (uint32_t x, uint32_t y, uint32_t s)        /
     return r;
 }
 static inline uint32_t __vcmpeq4 (uint32_t a, uint32_t b) { uint32_t r = 0; for (int i = 0; i < 4; i++) if (((a >> (8 * i)) & 0xff) == ((b >> (8 * i)) & 0xff)) r |= 0xffu << (8 * i); return r; }
+static inline uint32_t __vsub4 (uint32_t a, uint32_t b) { uint32_t r = 0; for (int i = 0; i < 4; i++) r |= ((((a >> (8 * i)) & 0xff) - ((b >> (8 * i)) & 0xff)) & 0xff) << (8 * i); return r; }
+static inline uint32_t __vcmpne4 (uint32_t a, uint32_t b) { return ~__vcmpeq4 (a, b); }
+static inline uint32_t __vcmpgtu4 (uint32_t a, uint32_t b) { uint32_t r = 0; for (int i = 0; i < 4; i++) if (((a >> (8 * i)) & 0xff) > ((b >> (8 * i)) & 0xff)) r |= 0xffu << (8 * i); return r; }
 static inline float    __uint_as_float (uint32_t u) { float f; memcpy (&f, &u, 4); return f; }
 static inline uint32_t __float_as_uint (float f) { uint32_t u; memcpy (&u, &f, 4); return u; }
 static inline long long __double_as_longlong (double d) { long long l; memcpy (&l, &d, 8); return l; }

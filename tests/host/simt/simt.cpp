@@ -67,6 +67,7 @@ struct Block {
     Fibre *running = nullptr;
     uint32_t n_done = 0, n_at_barrier = 0, barrier_gen = 0;
     bool progress = false;
+    int or_acc[3] = { 0, 0, 0 }; uint32_t or_gen = 0;                        // __syncthreads_or: three slots in rotation, see syncthreads_or
     const char *bar_file = nullptr; int bar_line = 0;                        // where the pending barrier's first thread waits
     uint32_t sched_rand = 12345;
     std::vector<uint8_t> dyn;
@@ -207,6 +208,20 @@ void syncthreads (const char *file, int line)
     while (me->state == WAIT_BLOCK) yield_to_scheduler ();
 }
 
+// __syncthreads_or: every thread ORs its predicate into the slot of this call, the barrier, everybody reads it.  The slot two
+// calls ahead is cleared by the readers: nobody writes to it before the NEXT call's barrier has released, which needs every
+// thread to have left this call.
+int syncthreads_or (const char *file, int line, int pred)
+{
+    Block *b = blk; Fibre *me = b->running;
+    const uint32_t gen = me->th.or_gen++ % 3;
+    b->or_acc[gen] |= pred;
+    syncthreads (file, line);
+    const int r = b->or_acc[gen];
+    b->or_acc[(gen + 2) % 3] = 0;
+    return r;
+}
+
 void *dyn_smem () { return blk->dyn.data (); }
 
 static const int lane_order = [] { const char *v = getenv ("SIMT_LANE_ORDER"); return !v ? 0 : !strcmp (v, "desc") ? 1 : !strcmp (v, "random") ? 2 : 0; } ();
@@ -214,11 +229,11 @@ static const int lane_order = [] { const char *v = getenv ("SIMT_LANE_ORDER"); r
 static void run_block (Block &b, dim3 grid, dim3 block, uint3 bid)
 {
     const uint32_t n = block.x * block.y * block.z;
-    b.n_done = b.n_at_barrier = 0;
+    b.n_done = b.n_at_barrier = 0; b.or_acc[0] = b.or_acc[1] = b.or_acc[2] = 0;
     for (uint32_t t = 0; t < n; t++) {
         Fibre &f = b.f[t];
         f.th.tid = uint3{ t % block.x, (t / block.x) % block.y, t / (block.x * block.y) };
-        f.th.bid = bid; f.th.bdim = block; f.th.gdim = grid;
+        f.th.bid = bid; f.th.bdim = block; f.th.gdim = grid; f.th.or_gen = 0;
         f.lane = t & 31; f.warp = t >> 5; f.state = RUN;
         // a fresh stack: six callee-saved registers, then the address simt_switch returns to
         uintptr_t top = ((uintptr_t)f.stack + STACK) & ~(uintptr_t)15;
