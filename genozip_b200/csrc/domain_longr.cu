@@ -21,7 +21,8 @@
 //           k_longr_prefix + k_longr_place (one warp per VBlock, ranks inside a tile from __match_any_sync, one atomic per
 //           channel and tile, consumed one tile later).
 //   decode  k_longr_decode: the next quality is only known once the previous base's channel is, so a VBlock decodes one base
-//           at a time — lane 0 of one warp per VBlock.  The chain per base is two dependent memory round trips (st[u], then
+//           at a time — lane 0 of one warp per VBlock; the other 31 lanes ask L2 for the table words of the contexts the
+//           step after next may land in (one candidate quality each).  The chain per base is two dependent memory round trips (st[u], then
 //           the channel's cursor) instead of the reference's four; the cursor of a channel is one 64-bit word that carries the
 //           index AND the next four qualities of the channel (refilled off the critical path).  Throughput comes from the
 //           number of VBlocks in flight.
@@ -30,6 +31,7 @@
 #include <string>
 #include "../../include/gzb200.h"
 #include "gzb_internal.cuh"
+#include "gzb_tma.cuh"
 #include "engine.h"
 
 using namespace gzb;
@@ -291,7 +293,6 @@ __global__ void __launch_bounds__(32) k_longr_decode (const LrVb *vbs)
     for (int i = lane; i < (int)NQ9; i += 32) tot[i] = 0x10101010u;
     for (int i = lane; i < 256; i += 32) { v2b[i] = V.v2b[i]; lut[i] = (uint8_t)acgt_code (i); lut[256 + i] = (uint8_t)acgt_code_comp (i); }
     __syncwarp ();
-    if (lane) return;
     uint32_t *st = V.st; unsigned long long *cur = V.cur;
     const uint8_t *values = V.values; const uint64_t total = V.total;
     const uint32_t va = (uint32_t)((uintptr_t)values & 3);                  // refills are aligned 4-byte loads
@@ -306,47 +307,63 @@ __global__ void __launch_bounds__(32) k_longr_decode (const LrVb *vbs)
         const bool rev = V.is_rev ? V.is_rev[li] : false;
         const uint8_t *lu = lut + (rev ? 256 : 0);
         uint32_t B = 0, u = 0, u_prev = 0xffffffffu, nv_prev = 0;
-        int32_t prev = 0;
+        int32_t prev = 0, qq = 0;
         bool missing = false;
         for (uint32_t e = 0; e < L + 3; e++) {
-            uint32_t val = u == u_prev ? nv_prev : st[u];
-            const uint32_t Qn = (u >> 12) & 0x1ffu, t_pre = tot[Qn];
-            int32_t qq = 0;
-            if (e >= 3) {
-                const uint32_t ch = Qn | (lr_chan_hi (val, t_pre, v2b) << 9);
-                uint32_t idx, vals;
-                if (ch == p_ch) { idx = p_idx; vals = p_vals; p_ch = 0xffffffffu; }
-                else {
-                    const unsigned long long c = cur[ch];
-                    if (p_ch != 0xffffffffu) { cur[p_ch] = ((unsigned long long)p_idx << 32) | p_vals; p_ch = 0xffffffffu; }
-                    idx = (uint32_t)(c >> 32); vals = (uint32_t)c;
+            if (lane == 0) {                                                // ---- the walk: lane 0
+                uint32_t val = u == u_prev ? nv_prev : st[u];
+                const uint32_t Qn = (u >> 12) & 0x1ffu, t_pre = tot[Qn];
+                qq = 0;
+                if (e >= 3) {
+                    const uint32_t ch = Qn | (lr_chan_hi (val, t_pre, v2b) << 9);
+                    uint32_t idx, vals;
+                    if (ch == p_ch) { idx = p_idx; vals = p_vals; p_ch = 0xffffffffu; }
+                    else {
+                        const unsigned long long c = cur[ch];
+                        if (p_ch != 0xffffffffu) { cur[p_ch] = ((unsigned long long)p_idx << 32) | p_vals; p_ch = 0xffffffffu; }
+                        idx = (uint32_t)(c >> 32); vals = (uint32_t)c;
+                    }
+                    qq = (int32_t)(vals & 0xffu);
+                    if (idx >= total) { bad = 1; qq = 0; }
+                    idx++; vals >>= 8;
+                    if (!((idx + va) & 3u)) { p_vals = idx < total ? *reinterpret_cast<const uint32_t *>(values + idx) : 0; p_ch = ch; p_idx = idx; }   // refill, off the chain
+                    else cur[ch] = ((unsigned long long)idx << 32) | vals;
+                    const uint32_t k = e - 3;
+                    out[rev ? L - 1 - k : k] = (uint8_t)(qq + '!');
                 }
-                qq = (int32_t)(vals & 0xffu);
-                if (idx >= total) { bad = 1; qq = 0; }
-                idx++; vals >>= 8;
-                if (!((idx + va) & 3u)) { p_vals = idx < total ? *reinterpret_cast<const uint32_t *>(values + idx) : 0; p_ch = ch; p_idx = idx; }   // refill, off the chain
-                else cur[ch] = ((unsigned long long)idx << 32) | vals;
-                const uint32_t k = e - 3;
-                out[rev ? L - 1 - k : k] = (uint8_t)(qq + '!');
-                missing = qq == 255;                                        // 255 + '!' == ' ': the line has no quality (:278)
+                uint32_t ae;
+                const uint32_t nv = lr_st_update (val, qq, ae);
+                st[u] = nv; tot[Qn] = lr_tot_update (t_pre, ae);
+                u_prev = u; nv_prev = nv;
+                // the context of the next event: base code of processing position e
+                const uint32_t b = e < L ? lu[seq[rev ? L - 1 - e : e]] : 0;
+                B = ((B << 2) | b) & 0xfffu;
+                u = B | (lr_difq (qq, prev) << 12) | ((uint32_t)(v2b[qq & 0xff] & 0x1f) << 16);
+                prev = qq;
             }
-            uint32_t ae;
-            const uint32_t nv = lr_st_update (val, qq, ae);
-            st[u] = nv; tot[Qn] = lr_tot_update (t_pre, ae);
-            u_prev = u; nv_prev = nv;
-            // the context of the next event: base code of processing position e
-            const uint32_t b = e < L ? lu[seq[rev ? L - 1 - e : e]] : 0;
-            B = ((B << 2) | b) & 0xfffu;
-            u = B | (lr_difq (qq, prev) << 12) | ((uint32_t)(v2b[qq & 0xff] & 0x1f) << 16);
-            prev = qq;
+            // ---- the other lanes: the context AFTER the next one depends on the next quality, which is not known yet — but it is
+            //      most likely within 16 of this one.  Each lane asks L2 for the table word of one candidate, so that the walk finds
+            //      it there (an L2 hit instead of a DRAM round trip on the chain).  A wrong guess costs nothing but the traffic.
+            const int32_t qb = __shfl_sync (FULL, qq, 0);
+            const uint32_t Bb = __shfl_sync (FULL, B, 0);
+            missing = e >= 3 && qb == 255;                                  // 255 + '!' == ' ': the line has no quality (:278)
             if (missing) break;                                             // after the state update, like RECON_ONE_QUAL
+            if (e + 1 < L + 3) {
+                const uint32_t b1 = e + 1 < L ? lu[seq[rev ? L - 2 - e : e + 1]] : 0;
+                const int32_t cq = min (93, max (0, qb - 15 + lane));
+                prefetch_l2 (st + ((((Bb << 2) | b1) & 0xfffu) | (lr_difq (cq, qb) << 12) | ((uint32_t)(v2b[cq] & 0x1f) << 16)));
+            }
         }
-        if (missing) out[0] = '*';                                          // sam_reconstruct_missing_quality (sam_qual.c:532-541); the rest of the line is undefined
-        if (V.missing) V.missing[li] = missing;
+        if (lane == 0) {
+            if (missing) out[0] = '*';                                      // sam_reconstruct_missing_quality (sam_qual.c:532-541); the rest of the line is undefined
+            if (V.missing) V.missing[li] = missing;
+        }
         out += L;
     }
-    if (p_ch != 0xffffffffu) cur[p_ch] = ((unsigned long long)p_idx << 32) | p_vals;
-    if (bad) *V.err = 2;
+    if (lane == 0) {
+        if (p_ch != 0xffffffffu) cur[p_ch] = ((unsigned long long)p_idx << 32) | p_vals;
+        if (bad) *V.err = 2;
+    }
 }
 
 // histogram of the quality values of a VBlock's lines (add_to_histogram, codec_longr.c:60-64)

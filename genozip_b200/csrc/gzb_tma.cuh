@@ -71,7 +71,12 @@ __device__ __forceinline__ void bulk_commit ()            { asm volatile ("cp.as
 template <int N> __device__ __forceinline__ void bulk_wait_read () { asm volatile ("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait_all ()  { asm volatile ("cp.async.bulk.wait_group %0;" :: "n"(N) : "memory"); }
 
+// a hint: bring the line of `p` into L2 (the walker of a latency-bound chain asks for the lines it may need two steps ahead)
+__device__ __forceinline__ void prefetch_l2 (const void *p) { asm volatile ("prefetch.global.L2 [%0];" :: "l"(p)); }
+
 #else   // ------------------------------------------------------------------ the emulator: synchronous stand-ins
+
+__device__ __forceinline__ void prefetch_l2 (const void *) {}
 
 __device__ __forceinline__ void mbar_init (uint64_t *bar, uint32_t) { *bar = 0; }
 __device__ __forceinline__ void mbar_fence_init () {}
