@@ -37,6 +37,8 @@ def parse():
     ap.add_argument("--vcf-lines", type=int, default=38000); ap.add_argument("--vcf-samples", type=int, default=1000)
     ap.add_argument("--lr-bases", type=int, default=16_000_000); ap.add_argument("--lr-read-len", type=int, default=50000)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-groups", type=int, default=int(os.environ.get("GZB_E2E_GROUPS", "3")),
+                    help="the host-buffer leg streams the step's VBlocks as this many groups (own engines and host threads each) that take turns on the PCIe link")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -300,9 +302,12 @@ def run_gpu(args):
         out = [torch.empty_like(t) for _ in range(world)]
         dist.all_gather(out, t)
 
+    detail = {}
+
     def timed(fn_zip, fn_piz, steps, warmup):
         tz = tp = 0.0
         kern = {"rans_enc": 0.0, "arith_enc": 0.0, "rans_dec": 0.0, "arith_dec": 0.0}
+        detail.clear()
         for i in range(warmup + steps):
             barrier()
             e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
@@ -310,15 +315,17 @@ def run_gpu(args):
                 e0.record(stream)
                 m = fn_zip()
                 section_list_gather(m[0] if isinstance(m, tuple) else m)
-                kz = path.kernel_ms
+                kz = path.kernel_ms; dz = dict(path.kernel_ms_detail)
                 e1.record(stream)
                 r = fn_piz(m[0] if isinstance(m, tuple) else m)
-                kp = path.kernel_ms
+                kp = path.kernel_ms; dp = dict(path.kernel_ms_detail)
                 e2.record(stream)
             barrier()
             if i >= warmup:
                 tz += e0.elapsed_time(e1); tp += e1.elapsed_time(e2)
                 kern["rans_enc"] += kz[0]; kern["arith_enc"] += kz[1]; kern["rans_dec"] += kp[0]; kern["arith_dec"] += kp[1]
+                for k_, v_ in dz.items(): detail["enc_" + k_] = detail.get("enc_" + k_, 0.0) + v_ / steps
+                for k_, v_ in dp.items(): detail["dec_" + k_] = detail.get("dec_" + k_, 0.0) + v_ / steps
         t = torch.tensor([tz, tp], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)                     # max over ranks
@@ -331,16 +338,45 @@ def run_gpu(args):
     clk = clocks.stop()
     value = world * txt_bytes / ((zip_ms + piz_ms) * 1e-3) / 1e9
 
-    # e2e: same step through the C-ABI with HOST (pinned) buffers — H2D of the inputs and D2H of the results inside
+    # e2e: same steps through the C-ABI with HOST (pinned) buffers — H2D of the inputs and D2H of the results inside.  The step's
+    # VBlocks go through as a stream of groups (fastq_path.HostStream): Ke zip steps back to back, then Ke piz steps, every group on
+    # its own engines and host thread, the groups taking turns on the PCIe link — what a dispatcher that keeps handing over VBlocks does.
     e2e = None
+    cpu_data = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_cpu = min(V, 4 * (os.cpu_count() or 1))
+        cpu_data = {k: [data[k][v].cpu().numpy() for v in range(n_cpu)] for k in data}
     if not args.no_e2e:
-        path.alloc_host(data)
-        ez, ep, _, (zr, pr) = timed(lambda: path.zip_host(), lambda m: path.piz_host(m), max(2, args.steps // 2), 1)
-        meta_h, h2d_z, d2h_z = zr
-        h2d_p, d2h_p = pr
-        assert torch.equal(path.h["seq_out"], path.h["seq"]) and torch.equal(path.h["qual_out"], path.h["qual"]), "host round trip failed"
+        from genozip_b200.fastq_path import HostStream
+        path.release_device()
+        eng.trim(); torch.cuda.empty_cache()
+        hs = HostStream(eng, V, args.reads, args.read_len, codecs, groups=args.e2e_groups)
+        hs.alloc(data)
+        del data
+        torch.cuda.empty_cache()
+        Ke = max(2, args.steps // 2)
+        hs.zip_steps(1); hs.piz_steps(1)                                  # warm-up step (buffers grow to their sizes) + correctness gate
+        assert hs.check(), "host round trip failed"
+        barrier()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            h2d_z, d2h_z = hs.zip_steps(Ke)
+            for _ in range(Ke):
+                section_list_gather([m for mm in hs.metas for m in mm])
+            e1.record(stream)
+            h2d_p, d2h_p = hs.piz_steps(Ke)
+            e2.record(stream)
+        barrier()
+        assert hs.check(), "host round trip failed"
+        t = torch.tensor([e0.elapsed_time(e1) / Ke, e1.elapsed_time(e2) / Ke], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ez, ep = t[0].item(), t[1].item()
         e2e = {"value": world * txt_bytes / ((ez + ep) * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(world * (h2d_z + h2d_p)), "d2h_bytes_per_step": int(world * (d2h_z + d2h_p)),
-               "zip_ms": ez, "piz_ms": ep}
+               "zip_ms": ez, "piz_ms": ep, "steps": Ke, "groups": len(hs.paths),
+               "how": "Ke zip steps back to back, then Ke piz steps; the step's VBlocks as `groups` groups on their own engines / host threads taking turns on the PCIe link"}
+        hs.close()
 
     # roofline of the dominant kernel: algorithmic bytes (N uncompressed + C compressed) / its launch time
     peaks = {}
@@ -356,27 +392,44 @@ def run_gpu(args):
             if n:
                 alg["rans" if codecs[s].startswith("RAN") else "arith"] += n + m["comp_len"][s]
     dom = max(kern, key=lambda k: kern[k])
-    dom_bytes = alg["rans" if dom.startswith("rans") else "arith"] // len(path.groups)    # each group launches the chain kernel once
+    dom_bytes = alg["rans" if dom.startswith("rans") else "arith"] // len(path.groups)    # each group launches the chain phase once
     achieved = dom_bytes / (kern[dom] * 1e-3) / 1e9 if kern[dom] > 0 else 0.0
-    kname = {"rans_enc": "k_rans_encode", "rans_dec": "k_rans_decode", "arith_enc": "k_arith_encode_t<0>", "arith_dec": "k_arith_decode_t<0>"}[dom]
-    traffic = None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        if kname in tj and tj[kname].get("vblocks") == V:
-            traffic = tj[kname]["bytes_per_launch"]
+    # the arithmetic chain phase is up to three kernels side by side (general / order-0 / split encoder): name the one that lasts longest
+    if dom.startswith("arith"):
+        side = "enc_" if dom.endswith("enc") else "dec_"
+        sub = max(("arith_general", "arith_o0", "arith_split"), key=lambda k: detail.get(side + k, 0.0))
+        kname = {"enc_arith_general": "k_arith_encode_t<0>", "enc_arith_o0": "k_arith_encode_t<1>", "enc_arith_split": "k_ar_split_code",
+                 "dec_arith_general": "k_arith_decode_t<0>", "dec_arith_o0": "k_arith_decode_t<1>", "dec_arith_split": "k_arith_decode_t<0>"}[side + sub]
+    else:
+        kname = {"rans_enc": "k_rans_encode", "rans_dec": "k_rans_decode"}[dom]
+    traffic = traffic_note = None
+    try:                                                        # dram__bytes of this kernel from the committed ncu --set full capture, scaled to this launch's VBlocks
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        ent = tj.get(kname)
+        if ent:
+            traffic = int(ent["bytes_per_launch"] * V / ent["vblocks"])
+            traffic_note = f"dram__bytes_read+write of {kname} captured at {ent['vblocks']} VBlocks ({ent.get('source', 'profiles/')}), scaled by {V}/{ent['vblocks']}"
     except Exception:
         pass
-    roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-            "peak_source": which_peak, "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": kern[dom],
-            "note": "entropy chains are dependency-bound (4 chains per rANS leaf, 1 per arithmetic leaf, fixed by the bitstream): the launch lasts as long as "
-                    "its longest leaf; traffic (dram__bytes) is null unless profiles/r01_traffic.json holds a capture of this very launch; "
-                    "profiles/r01_k_arith_decode.md has the single-leaf capture", "kernel_ms_per_step": kern}
+    # SURVEY §8d secondary bound: chains in flight x f_clk / cycles per symbol, from the longest arithmetic leaf (DIVRQUAL: 4 ranks per coder symbol)
+    f_clk = (clk.get("sm_mhz") or 1965.0) * 1e6
+    longest = max((m["len"].get("DIVRQUAL", 0) + 3) // 4 for m in meta) if dom.startswith("arith") else max(m["len"].get("NONREF_X", 0) // 4 for m in meta)
+    chain_bound = None
+    if longest and kern[dom] > 0:
+        cyc = kern[dom] * 1e-3 * f_clk / longest
+        chain_bound = {"longest_chain_symbols": int(longest), "cycles_per_symbol_in_batch": cyc, "chains_in_flight": V,
+                       "symbols_per_s": V * f_clk / cyc, "note": "the launch lasts as long as its longest dependency chain: one arithmetic chain (4 rANS chains) per leaf, fixed by the bitstream"}
+    roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
+            "peak_source": which_peak, "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": kern[dom], "chain_bound": chain_bound,
+            "note": "entropy chains are dependency-bound (4 chains per rANS leaf, 1 per arithmetic leaf, fixed by the bitstream): the chain phase lasts as long as "
+                    "its longest leaf; algorithmic bytes = N + C of the sections of the dominant coder's chain phase (its kernels run side by side)",
+            "kernel_ms_per_step": kern, "kernel_ms_detail": dict(detail)}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         n_vb = min(V, 4 * cores)                                # ~10-30 s of CPU work
-        dnp = {k: [data[k][v].cpu().numpy() for v in range(n_vb)] for k in data}
+        dnp = cpu_data
         tz, tp, kind = cpu_path_time(dnp, args.reads, args.read_len, codecs, cores, n_vb)
         nb = n_vb * txt_bytes_per_vb(args.reads, args.read_len)
         cpu = {"value": nb / (tz + tp) / 1e9, "unit": UNIT, "cores": cores, "kind": kind,

@@ -98,10 +98,11 @@ extern "C" int gzb_engine_create (int device, gzb_engine **out)
     e->device = device;
     e->sm_count = prop.multiProcessorCount;
     bool ok = cudaSetDevice (device) == cudaSuccess && cudaStreamCreateWithFlags (&e->stream, cudaStreamNonBlocking) == cudaSuccess;
-    cudaEvent_t *evs[5] = { &e->ev0, &e->ev1, &e->ev2, &e->ev3, &e->ev4 };
-    for (int i = 0; ok && i < 5; i++) ok = cudaEventCreate (evs[i]) == cudaSuccess;
+    cudaEvent_t *evs[6] = { &e->ev0, &e->ev1, &e->ev2, &e->ev3, &e->ev4, &e->ev5 };
+    for (int i = 0; ok && i < 6; i++) ok = cudaEventCreate (evs[i]) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags (&e->stream2, cudaStreamNonBlocking) == cudaSuccess
-            && cudaStreamCreateWithFlags (&e->stream3, cudaStreamNonBlocking) == cudaSuccess;
+            && cudaStreamCreateWithFlags (&e->stream3, cudaStreamNonBlocking) == cudaSuccess
+            && cudaStreamCreateWithFlags (&e->stream4, cudaStreamNonBlocking) == cudaSuccess;
     if (!ok) {                                                              // a half-made engine would fork its chains onto null streams
         g_last_error = std::string ("engine creation failed: ") + cudaGetErrorString (cudaGetLastError ());
         gzb_engine_destroy (e); return GZB_E_CUDA;
@@ -129,10 +130,11 @@ extern "C" void gzb_engine_destroy (gzb_engine *e)
     if (e->dq_buf) cudaFree (e->dq_buf);
     if (e->dq_session && e->dq_free) e->dq_free (e->dq_session);
     if (e->pin) cudaFreeHost (e->pin);
-    cudaEvent_t evs[5] = { e->ev0, e->ev1, e->ev2, e->ev3, e->ev4 };
+    cudaEvent_t evs[6] = { e->ev0, e->ev1, e->ev2, e->ev3, e->ev4, e->ev5 };
     for (cudaEvent_t ev : evs) if (ev) cudaEventDestroy (ev);
     if (e->stream2) cudaStreamDestroy (e->stream2);
     if (e->stream3) cudaStreamDestroy (e->stream3);
+    if (e->stream4) cudaStreamDestroy (e->stream4);
     if (e->stream) cudaStreamDestroy (e->stream);
     delete e;
 }
@@ -156,7 +158,18 @@ extern "C" int gzb_engine_sync (gzb_engine *e) { cudaSetDevice (e->device); CK (
 extern "C" int gzb_vb_device (uint32_t vblock_i, int n_devices) { return n_devices > 0 ? (int)((vblock_i ? vblock_i - 1 : 0) % (uint32_t)n_devices) : 0; }
 extern "C" uint64_t gzb_kernel_launches (gzb_engine *e) { return e->launches; }
 extern "C" float gzb_last_chain_ms (gzb_engine *e) { return e->last_chain_ms; }
-extern "C" float gzb_last_kernel_ms (gzb_engine *e, int which) { return which == 2 ? e->last_domain_ms : which ? e->last_arith_ms : e->last_rans_ms; }
+extern "C" float gzb_last_kernel_ms (gzb_engine *e, int which)
+{
+    switch (which) {
+        case 0:  return e->last_rans_ms;
+        case 1:  return e->last_arith_ms;
+        case 2:  return e->last_domain_ms;
+        case 3:  return e->last_o0_ms;
+        case 4:  return e->last_split_ms;
+        case 5:  return e->last_arith_all_ms;
+        default: return 0;
+    }
+}
 
 int engine_reserve (gzb_engine *e, size_t ws_bytes, size_t pin_bytes)
 {
@@ -374,6 +387,7 @@ static int compress_impl (gzb_engine *e, gzb_section *secs, uint32_t n, uint32_t
                       P.pack_arena = pk->dev ? (uint8_t *)pk->arena : c.take<uint8_t> (pk->cap + 16); }
             d_cursor       = c.take<unsigned long long> (1);
             d_overflow     = c.take<int> (1);
+            P.queue        = c.take<uint32_t> (Q_WORDS);
             d_hist0        = c.take<uint32_t> ((size_t)(nl ? nl : 1) * 256);
             d_in           = c.take<uint8_t> (in_total + 1);
             d_out          = c.take<uint8_t> (out_total + 1);
@@ -431,6 +445,7 @@ static int compress_impl (gzb_engine *e, gzb_section *secs, uint32_t n, uint32_t
         P.copy_parts = (n <= 64) ? 32 : (n <= 1024 ? 8 : 2);
         P.arena = Arena { d_arena, (unsigned long long)arena_est, d_cursor, d_overflow };
         P.ev_chain0 = e->ev0; P.ev_chain1 = e->ev1; P.ev_chain2 = e->ev2; P.ev_arith0 = e->ev3; P.st2 = e->stream2; P.ev_o0 = e->ev4; P.st3 = e->stream3;
+        P.ev_split = e->ev5; P.st4 = e->stream4; P.sm_count = e->sm_count;
 
         // ---- upload: metadata blob, inputs (small ones gathered through pinned staging)
         cudaStream_t st = e->stream;
@@ -443,7 +458,7 @@ static int compress_impl (gzb_engine *e, gzb_section *secs, uint32_t n, uint32_t
                                    [&] (uint32_t i) { return (S2[i].soft_fail || in_dev (i)) ? 0u : S2[i].n; });
             if (rc) return rc;
         }
-        CK (cudaMemsetAsync (d_cursor, 0, 512, st));
+        CK (cudaMemsetAsync (d_cursor, 0, 768, st));                       // cursor | overflow | queue counters (256-byte regions)
         CK (cudaMemsetAsync (d_hist0, 0, (size_t)(nl ? nl : 1) * 1024, st));
 
         // ---- run
@@ -463,10 +478,12 @@ static int compress_impl (gzb_engine *e, gzb_section *secs, uint32_t n, uint32_t
             e->arena_hint = arena_est;
             continue;
         }
-        float ms = 0; e->last_rans_ms = e->last_arith_ms = 0;
+        float ms = 0; e->last_rans_ms = e->last_arith_ms = e->last_o0_ms = e->last_split_ms = 0;
         if (P.n_rans_jobs) { cudaEventElapsedTime (&ms, e->ev0, e->ev1); e->last_rans_ms = ms; }
-        if (P.n_arith) { cudaEventElapsedTime (&ms, e->ev3, e->ev2); e->last_arith_ms = ms; }
-        e->last_chain_ms = e->last_rans_ms > e->last_arith_ms ? e->last_rans_ms : e->last_arith_ms;
+        if (P.n_arith) { cudaEventElapsedTime (&ms, e->ev3, e->ev2); e->last_arith_ms = ms; cudaEventElapsedTime (&ms, e->ev3, e->ev4); e->last_o0_ms = ms; }
+        if (P.n_arith && P.n_arith_big) { cudaEventElapsedTime (&ms, e->ev3, e->ev5); e->last_split_ms = ms; }
+        e->last_arith_all_ms = std::max (e->last_arith_ms, std::max (e->last_o0_ms, e->last_split_ms));
+        e->last_chain_ms = std::max (e->last_rans_ms, e->last_arith_all_ms);
 
         for (uint32_t i = 0; i < n; i++) {
             secs[i].status = res[i].status; secs[i].out_len = res[i].out_len;
@@ -598,6 +615,7 @@ extern "C" int gzb_uncompress_sections (gzb_engine *e, gzb_section *secs, uint32
             P.results    = c.take<SectionResult> (n);
             d_cursor     = c.take<unsigned long long> (1);
             d_overflow   = c.take<int> (1);
+            P.queue      = c.take<uint32_t> (Q_WORDS);
             d_in         = c.take<uint8_t> (in_total + 1);
             d_out        = c.take<uint8_t> (out_total + 1);
             d_planes     = c.take<uint8_t> (aux_total);
@@ -630,7 +648,7 @@ extern "C" int gzb_uncompress_sections (gzb_engine *e, gzb_section *secs, uint32
         P.n_rans_jobs = (uint32_t)rjobs.size (); P.arith_lpw = pick_arith_lpw (P.n_arith);
         P.parts = (n <= 64) ? 32 : (n <= 1024 ? 8 : 2);
         P.arena = Arena { d_arena, (unsigned long long)arena_est, d_cursor, d_overflow };
-        P.ev_chain0 = e->ev0; P.ev_chain1 = e->ev1; P.ev_chain2 = e->ev2; P.ev_arith0 = e->ev3; P.st2 = e->stream2; P.ev_o0 = e->ev4; P.st3 = e->stream3;
+        P.ev_chain0 = e->ev0; P.ev_chain1 = e->ev1; P.ev_chain2 = e->ev2; P.ev_arith0 = e->ev3; P.st2 = e->stream2; P.ev_o0 = e->ev4; P.st3 = e->stream3; P.sm_count = e->sm_count;
 
         cudaStream_t st = e->stream;
         memcpy (e->pin, meta.data (), meta_bytes);
@@ -642,7 +660,7 @@ extern "C" int gzb_uncompress_sections (gzb_engine *e, gzb_section *secs, uint32
                                    [&] (uint32_t i) { return in_dev (i) ? 0u : S2[i].in_len; });
             if (rc) return rc;
         }
-        CK (cudaMemsetAsync (d_cursor, 0, 512, st));
+        CK (cudaMemsetAsync (d_cursor, 0, 768, st));                       // cursor | overflow | queue counters (256-byte regions)
 
         dec_run (P, st);
         e->launches += P.launches;
@@ -656,10 +674,11 @@ extern "C" int gzb_uncompress_sections (gzb_engine *e, gzb_section *secs, uint32
         for (uint32_t i = 0; i < n; i++) if (!out_dev (i)) CK (cudaMemcpyAsync (secs[i].out, S2[i].out, S2[i].n, cudaMemcpyDeviceToHost, st));
         CK (cudaStreamSynchronize (st));
         if (h_over) { arena_est = (size_t)h_cursor + (h_cursor >> 2) + ((size_t)1 << 20); e->arena_hint_dec = arena_est; continue; }
-        float ms = 0; e->last_rans_ms = e->last_arith_ms = 0;
+        float ms = 0; e->last_rans_ms = e->last_arith_ms = e->last_o0_ms = e->last_split_ms = 0;
         if (P.n_rans_jobs) { cudaEventElapsedTime (&ms, e->ev0, e->ev1); e->last_rans_ms = ms; }
-        if (P.n_arith) { cudaEventElapsedTime (&ms, e->ev3, e->ev2); e->last_arith_ms = ms; }
-        e->last_chain_ms = e->last_rans_ms > e->last_arith_ms ? e->last_rans_ms : e->last_arith_ms;
+        if (P.n_arith) { cudaEventElapsedTime (&ms, e->ev3, e->ev2); e->last_arith_ms = ms; cudaEventElapsedTime (&ms, e->ev3, e->ev4); e->last_o0_ms = ms; }
+        e->last_arith_all_ms = std::max (e->last_arith_ms, e->last_o0_ms);
+        e->last_chain_ms = std::max (e->last_rans_ms, e->last_arith_all_ms);
         int rc = GZB_OK;
         for (uint32_t i = 0; i < n; i++) {
             secs[i].status = res[i].status; secs[i].out_len = res[i].status ? 0 : res[i].out_len;

@@ -796,8 +796,16 @@ void enc_run (EncPlanDev &P, cudaStream_t st)
     if (P.n_arith) {
         cudaStreamWaitEvent (P.st2, P.ev_chain0, 0);
         cudaEventRecord (P.ev_arith0, P.st2);
+        // the split encoder's three kernels (the long order-1 leaves) go first and, unless switched off, on a stream of their own:
+        // behind the general kernel on one stream they would wait for its last leaf before they start
+        const bool own = chain_tune ().split_stream && P.st4;
+        if (P.n_arith_big && own) {
+            cudaStreamWaitEvent (P.st4, P.ev_chain0, 0);
+            launch_arith_encode_split (P, P.st4); P.launches += 3;
+            cudaEventRecord (P.ev_split, P.st4);
+        }
         launch_arith_encode (P, P.st2); P.launches++;
-        if (P.n_arith_big) { launch_arith_encode_split (P, P.st2); P.launches += 3; }
+        if (P.n_arith_big && !own) { launch_arith_encode_split (P, P.st2); P.launches += 3; cudaEventRecord (P.ev_split, P.st2); }
         cudaEventRecord (P.ev_chain2, P.st2);
         cudaStreamWaitEvent (P.st3, P.ev_chain0, 0);
         launch_arith_encode_o0 (P, P.st3); P.launches++;
@@ -805,7 +813,7 @@ void enc_run (EncPlanDev &P, cudaStream_t st)
     }
     if (P.n_rans_jobs) { launch_rans_encode (P, st); P.launches++; }
     cudaEventRecord (P.ev_chain1, st);
-    if (P.n_arith) { cudaStreamWaitEvent (st, P.ev_chain2, 0); cudaStreamWaitEvent (st, P.ev_o0, 0); }
+    if (P.n_arith) { cudaStreamWaitEvent (st, P.ev_chain2, 0); cudaStreamWaitEvent (st, P.ev_o0, 0); if (P.n_arith_big) cudaStreamWaitEvent (st, P.ev_split, 0); }
     LAUNCH (k_leaf_final, (nl + 127) / 128, 128, P.leaves, P.dyn, nl);
     LAUNCH (k_section_final, (ns + 127) / 128, 128, P.sections, P.leaves, P.dyn, P.results, P.segs, P.stripe_hdr, ns);
     if (P.pack_off) LAUNCH (k_pack_place, 1, 1024, P.results, P.segs, P.pack_off, ns, P.pack_arena, P.pack_cap);

@@ -22,8 +22,10 @@ struct EncPlanDev {              // device pointers of one encode batch
     Arena          arena;
     int            rans_gpw, arith_lpw, copy_parts;
     bool           any_pack, any_o1;
-    cudaEvent_t    ev_chain0, ev_chain1, ev_chain2, ev_arith0, ev_o0;   // rANS kernel: chain0..chain1 on the main stream; arithmetic: arith0..chain2 on st2; order-0 arithmetic: .. ev_o0 on st3
-    cudaStream_t   st2, st3;
+    cudaEvent_t    ev_chain0, ev_chain1, ev_chain2, ev_arith0, ev_o0, ev_split;   // rANS kernel: chain0..chain1 on the main stream; arithmetic: arith0..chain2 on st2; order-0 arithmetic: .. ev_o0 on st3; split encoder: .. ev_split on st4
+    cudaStream_t   st2, st3, st4;
+    uint32_t      *queue;                                 // zeroed work counters of the persistent chain kernels (Q_* below)
+    int            sm_count;
     uint64_t       launches;
 };
 
@@ -38,8 +40,23 @@ struct DecPlanDev {
     int            rans_gpw, arith_lpw, parts;
     cudaEvent_t    ev_chain0, ev_chain1, ev_chain2, ev_arith0, ev_o0;
     cudaStream_t   st2, st3;
+    uint32_t      *queue;
+    int            sm_count;
     uint64_t       launches;
 };
+
+// The chain kernels are PERSISTENT: a fixed number of CTAs per SM, every warp takes the next leaf of the (longest-first) list from a
+// counter until the list is empty.  What is resident on an SM is then a choice, not the block scheduler's "as many as fit": the
+// long leaves, taken first, share an issue port with a few other warps instead of fifteen (a chain wants a slot every ~6 cycles).
+enum { Q_ARITH = 0, Q_ARITH_O0 = 1, Q_SPLIT_CODE = 2, Q_WORDS = 64 };
+struct ChainTune { int arith_ctas, arith_o0_ctas, run4, split_stream; };      // CTAs per SM of the two arithmetic kernels; GZB_AR_* (see chain_tune)
+const ChainTune &chain_tune ();
+__device__ __forceinline__ uint32_t queue_take (uint32_t *counter, int lane)
+{
+    uint32_t s = 0;
+    if (lane == 0) s = atomicAdd (counter, 1u);
+    return __shfl_sync (0xffffffffu, s, 0);
+}
 
 void upload_log_tables (const double *l10, const double *l12);
 void enc_run (EncPlanDev &P, cudaStream_t st);

@@ -192,6 +192,13 @@ class FastqCodecPath:
             e.close()
         self.engs = self.engs[:1]
 
+    def release_device(self):
+        """drop the device-resident leg's buffers (the host-buffer leg that follows allocates its own)"""
+        self.close()
+        for a in ("packed_d", "x_d", "linedom_d", "linediv_d", "dq_arena", "comp_arena", "names_dec_d", "seq_out_d", "qual_out_d", "dec_d"):
+            setattr(self, a, None)
+        self.dqs = {}
+
     @staticmethod
     def _sub(arr, v0, v1):
         """ctypes view of elements [v0, v1) of a ctypes array (shares memory)"""
@@ -203,7 +210,11 @@ class FastqCodecPath:
         return np.uint64(t.data_ptr()) + np.arange(t.shape[0], dtype=np.uint64) * np.uint64(t.stride(0) * t.element_size())
 
     def _kernel_ms(self, engs):
-        self.kernel_ms = tuple(float(np.max([self.L.gzb_last_kernel_ms(e.h, w) for e in engs])) for w in (0, 1))
+        """(rANS chain kernel, the arithmetic chain kernels — they run side by side: the longest) of the last call, max over the engines;
+        kernel_ms_detail: general / order-0 / split-encoder arithmetic kernels separately"""
+        ms = lambda w: float(np.max([self.L.gzb_last_kernel_ms(e.h, w) for e in engs]))
+        self.kernel_ms = (ms(0), ms(5))
+        self.kernel_ms_detail = {"rans": ms(0), "arith_general": ms(1), "arith_o0": ms(3), "arith_split": ms(4)}
 
     # ------------------------------------------------------------------ codec assignment (host policy, run on the GPU)
     def assign_codecs(self, data):
@@ -447,15 +458,28 @@ class FastqCodecPath:
                 raise errs[0]
         self._kernel_ms(self.engs)
 
-    def zip_host(self):
+    def zip_host(self, gate=None):
         """host buffers in, host buffers out; the DOMQ streams and the exception stream stay on the device between the complex codec
         and its sub-codec (GZB_OUT_DEVICE / GZB_SEC_IN_DEVICE) exactly as they stay inside one compute thread in the reference.
         The three independent pipelines of a FASTQ VBlock — QUAL (DOMQ + its four sub-streams), SEQ (ACGT + its exception
         stream) and the read-name contexts — run on one engine (host thread + stream) each, so the transfers of one
         overlap the entropy chains of another; QUAL's upload goes first because its chains are the longest.
+        `gate` (HostStream): a lock held while this VBlock group's bulk inputs cross PCIe, so that the groups of a stream take turns
+        uploading and one group's upload runs under another group's chains.
         Returns (meta, h2d_bytes, d2h_bytes)."""
         L, V, n, H = self.L, self.V, self.n, self.h
         meta = ZipMeta(V)
+        gate_left = [2]; gate_lock = threading.Lock()
+        if gate is not None:
+            gate.acquire()
+
+        def upload_done():                                       # QUAL and SEQ have both crossed: the next group may start its upload
+            if gate is None:
+                return
+            with gate_lock:
+                gate_left[0] -= 1
+                if gate_left[0] == 0:
+                    gate.release()
         for s in NAMES:
             meta.len[:, S_IDX[s]] = self.name_len[s]
         dev_in = np.zeros(len(STREAMS), np.uint32)
@@ -476,18 +500,24 @@ class FastqCodecPath:
                 self._domq_device(lambda v: H["qual"][v].data_ptr(), eng, meta, GZB_OUT_DEVICE, 0, first)
             finally:
                 qual_up.set()
-            if first < V:
-                self._domq_device(lambda v: H["qual"][v].data_ptr(), eng, meta, GZB_OUT_DEVICE, first, V)
+            try:
+                if first < V:
+                    self._domq_device(lambda v: H["qual"][v].data_ptr(), eng, meta, GZB_OUT_DEVICE, first, V)
+            finally:
+                upload_done()
             compress(eng, DQ, "comp_qual")
 
         def part_seq(eng):
             qual_up.wait()
             a = self.avb_np
-            a["seq"] = self._rows(H["seq"]); a["n_bases"] = n; a["packed"] = self._rows(H["packed"]); a["x"] = self._rows(self.x_d)
-            for v0 in range(0, V, 64):                          # bounded staging in the engine workspace
-                v1 = min(V, v0 + 64)
-                if L.gzb_acgt_pack_batch(eng.h, self._sub(self.avb, v0, v1), v1 - v0, GZB_OUT_DEVICE):
-                    raise GzbError(f"gzb_acgt_pack_batch: {eng._err()}")
+            try:
+                a["seq"] = self._rows(H["seq"]); a["n_bases"] = n; a["packed"] = self._rows(H["packed"]); a["x"] = self._rows(self.x_d)
+                for v0 in range(0, V, 64):                          # bounded staging in the engine workspace
+                    v1 = min(V, v0 + 64)
+                    if L.gzb_acgt_pack_batch(eng.h, self._sub(self.avb, v0, v1), v1 - v0, GZB_OUT_DEVICE):
+                        raise GzbError(f"gzb_acgt_pack_batch: {eng._err()}")
+            finally:
+                upload_done()
             meta.acgt_no_x[:] = a["x_all_zero"] != 0
             meta.len[:, S_IDX["NONREF_X"]] = np.where(meta.acgt_no_x, 0, n)
             compress(eng, ("NONREF_X",), "comp_seq")
@@ -503,7 +533,8 @@ class FastqCodecPath:
         d2h = V * (self.packed_len + 2 * self.n_reads) + int(meta.comp_len.sum())
         return meta, h2d, d2h
 
-    def piz_host(self, meta):
+    def piz_host(self, meta, gate=None):
+        """the inverse of zip_host.  `gate` (HostStream): a lock held while this group's reconstructed QUAL / SEQ cross PCIe."""
         L, V, n, H = self.L, self.V, self.n, self.h
         dev_out = np.zeros(len(STREAMS), np.uint32)
         for s in DQ + ("NONREF_X",):
@@ -518,17 +549,25 @@ class FastqCodecPath:
 
         self._fill_piz_descriptors(meta, self._rows(H["qual_out"]), self._rows(H["seq_out"]), self._rows(H["packed"]), self.line_len_h)
 
+        class _Held:                                             # the gate, or nothing
+            def __enter__(s_):
+                if gate is not None: gate.acquire()
+            def __exit__(s_, *a_):
+                if gate is not None: gate.release()
+
         def part_qual(eng):
             uncompress(eng, DQ)
-            if L.gzb_domq_reconstruct(eng.h, self.pvb, V, GZB_IN_DEVICE):
-                raise GzbError(f"gzb_domq_reconstruct: {eng._err()}")
+            with _Held():
+                if L.gzb_domq_reconstruct(eng.h, self.pvb, V, GZB_IN_DEVICE):
+                    raise GzbError(f"gzb_domq_reconstruct: {eng._err()}")
 
         def part_seq(eng):
             uncompress(eng, ("NONREF_X",))
-            for v0 in range(0, V, 64):
-                v1 = min(V, v0 + 64)
-                if L.gzb_acgt_unpack_batch(eng.h, self._sub(self.avb, v0, v1), v1 - v0, GZB_IN_DEVICE):
-                    raise GzbError(f"gzb_acgt_unpack_batch: {eng._err()}")
+            with _Held():
+                for v0 in range(0, V, 64):
+                    v1 = min(V, v0 + 64)
+                    if L.gzb_acgt_unpack_batch(eng.h, self._sub(self.avb, v0, v1), v1 - v0, GZB_IN_DEVICE):
+                        raise GzbError(f"gzb_acgt_unpack_batch: {eng._err()}")
 
         def part_names(eng):
             uncompress(eng, NAMES)
@@ -539,3 +578,78 @@ class FastqCodecPath:
         h2d = V * (4 * self.n_reads + self.packed_len) + int(meta.comp_len.sum())
         d2h = V * (n + n) + int(meta.len[:, host_out].sum())
         return h2d, d2h
+
+
+class HostStream:
+    """The host-buffer path as a STREAM of VBlock groups — what genozip's dispatcher does with VBlocks, at the granularity the GPU
+    wants: G groups, each a FastqCodecPath over V/G VBlocks with its own engines, device buffers and pinned host buffers, each
+    driven by its own host thread, step after step without a barrier in between.  The groups take turns on the PCIe link (a lock
+    around the bulk upload of zip and the bulk download of piz), so in steady state one group's inputs upload while the other
+    groups' entropy chains run and a third group's results go back: the chains are latency-bound (a group's chain phase lasts as
+    long as its longest leaf whatever its size) and the link is bandwidth-bound, so they overlap almost perfectly.
+    Results and byte counts are those of zip_host / piz_host, summed."""
+
+    def __init__(self, eng, V, n_reads, read_len, codec, groups=3, engine_factory=None):
+        G = max(1, min(groups, V))
+        self.bounds = [(V * g // G, V * (g + 1) // G) for g in range(G)]
+        mk = engine_factory or (lambda: type(eng)(eng.device))
+        self.own = [mk() for _ in range(G)]
+        self.paths = [FastqCodecPath(self.own[g], b - a, n_reads, read_len) for g, (a, b) in enumerate(self.bounds)]
+        for p in self.paths:
+            p.codec = dict(codec)
+        self.link = threading.Lock()
+        self.threads = ThreadPoolExecutor(G)
+        self.metas = None
+
+    def alloc(self, data, metas=None):
+        """pinned host buffers of every group (its slice of `data`); metas: per-group ZipMeta of a device pass (sizes the packed output buffers)"""
+        for p, (a, b) in zip(self.paths, self.bounds):
+            if metas is not None:
+                p.meta = metas[self.paths.index(p)]
+            p.alloc_host({k: v[a:b] for k, v in data.items()})
+
+    def _run(self, fn, K):
+        futs = [self.threads.submit(fn, g, K) for g in range(len(self.paths))]
+        errs, out = [], []
+        for f in futs:
+            try:
+                out.append(f.result())
+            except Exception as ex:
+                errs.append(ex)
+        if errs:
+            raise errs[0]
+        return out
+
+    def zip_steps(self, K=1):
+        """K zip passes of every group, back to back; returns (h2d_bytes, d2h_bytes) of ONE step (all groups)"""
+        def work(g, K):
+            r = None
+            for _ in range(K):
+                r = self.paths[g].zip_host(gate=self.link)
+            return r
+        res = self._run(work, K)
+        self.metas = [r[0] for r in res]
+        return sum(r[1] for r in res), sum(r[2] for r in res)
+
+    def piz_steps(self, K=1):
+        def work(g, K):
+            r = None
+            for _ in range(K):
+                r = self.paths[g].piz_host(self.metas[g], gate=self.link)
+            return r
+        res = self._run(work, K)
+        return sum(r[0] for r in res), sum(r[1] for r in res)
+
+    def check(self):
+        return all(torch.equal(p.h["seq_out"], p.h["seq"]) and torch.equal(p.h["qual_out"], p.h["qual"]) for p in self.paths)
+
+    @property
+    def launches(self):
+        return sum(p.launches for p in self.paths)
+
+    def close(self):
+        self.threads.shutdown(wait=True)
+        for p in self.paths:
+            p.close()
+        for e in self.own:
+            e.close()

@@ -70,8 +70,10 @@ int   gzb_vb_device (uint32_t vblock_i, int n_devices);           /* (vblock_i-1
 uint64_t gzb_kernel_launches (gzb_engine *e);                     /* kernels launched by this engine so far */
 /* Device-time of the dominant chain kernels of the LAST batch call, ms (CUDA events on the engine's stream) */
 float gzb_last_chain_ms (gzb_engine *e);
-/* the same, split by coder: which = 0 rANS chain kernel, 1 arithmetic chain kernel; which = 2: the dominant kernel of the last
- * PBWT / LONGR batch call (the row walk k_pbwt_rows, the channel walk k_longr_channels / k_longr_decode) */
+/* the same, split by coder: which = 0 rANS chain kernel, 1 general arithmetic chain kernel (order-1 / RLE leaves), 3 order-0 arithmetic
+ * chain kernel, 4 the split arithmetic encoder (bucket + model + code kernels of the long order-1 leaves), 5 the longest of 1, 3, 4
+ * (they run side by side); which = 2: the dominant kernel of the last PBWT / LONGR batch call (the row walk k_pbwt_rows, the channel
+ * walk k_longr_channels / k_longr_decode) */
 float gzb_last_kernel_ms (gzb_engine *e, int which);
 
 /* ---------------------------------------------------------------- simple codecs: rANS 4x16 and adaptive arithmetic

@@ -1,0 +1,70 @@
+#!/usr/bin/env python
+"""Sweep of the chain phase's switches on the FASTQ workload inside ONE process (the data and the buffers are made once):
+
+    python tools/sweep_fastq.py --vblocks 512 --cfg GZB_AR_CTAS=4 --cfg GZB_AR_CTAS=16,GZB_AR0_CTAS=16 ...
+
+Each --cfg is a comma-separated list of VAR=value (libgzb200 reads these variables at every batch call, arith_chain.cu
+chain_tune).  Per configuration: one warm-up step, then `--steps` timed zip + piz passes with the inputs resident in HBM
+(CUDA events on the engine's stream), the chain kernels' own durations, and a round-trip check.  One JSON line each."""
+import argparse, json, os, sys
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--vblocks", type=int, default=512)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--reads", type=int, default=92000)
+    ap.add_argument("--read-len", type=int, default=150)
+    ap.add_argument("--cfg", action="append", default=[])
+    a = ap.parse_args()
+    import torch
+    from genozip_b200 import Engine
+    from genozip_b200.fastq_path import FastqCodecPath, synth_vblocks, txt_bytes_per_vb
+    dev = torch.device("cuda", 0)
+    eng = Engine(0)
+    path = FastqCodecPath(eng, a.vblocks, a.reads, a.read_len)
+    data = synth_vblocks(a.vblocks, a.reads, a.read_len, 1000, dev)
+    torch.cuda.empty_cache()
+    path.codec = json.load(open(os.path.join(ROOT, "bench_codecs.json")))
+    meta = path.zip_device(data); path.alloc_piz(meta); path.scrub_intermediates(); path.piz_device(meta)
+    torch.cuda.synchronize()
+    assert torch.equal(path.seq_out_d, data["seq"]) and torch.equal(path.qual_out_d, data["qual"]), "round trip failed"
+    txt = a.vblocks * txt_bytes_per_vb(a.reads, a.read_len)
+    keys = set()
+    for cfg in a.cfg:
+        keys |= {kv.split("=")[0] for kv in cfg.split(",") if kv}
+    for cfg in a.cfg or [""]:
+        for k in keys:
+            os.environ.pop(k, None)
+        for kv in cfg.split(","):
+            if kv:
+                k, v = kv.split("="); os.environ[k] = v
+        tz = tp = 0.0
+        kz = {}; kp = {}
+        for i in range(1 + a.steps):
+            torch.cuda.synchronize()
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            with torch.cuda.stream(path.stream):
+                e0.record(path.stream)
+                meta = path.zip_device(data); dz = dict(path.kernel_ms_detail)
+                e1.record(path.stream)
+                path.piz_device(meta); dp = dict(path.kernel_ms_detail)
+                e2.record(path.stream)
+            torch.cuda.synchronize()
+            if i:
+                tz += e0.elapsed_time(e1); tp += e1.elapsed_time(e2)
+                for k, v in dz.items(): kz[k] = kz.get(k, 0.0) + v
+                for k, v in dp.items(): kp[k] = kp.get(k, 0.0) + v
+        ok = bool(torch.equal(path.seq_out_d, data["seq"]) and torch.equal(path.qual_out_d, data["qual"]))
+        tz /= a.steps; tp /= a.steps
+        print(json.dumps({"cfg": cfg, "V": a.vblocks, "zip_ms": round(tz, 1), "piz_ms": round(tp, 1), "value_GBps": round(txt / ((tz + tp) * 1e-3) / 1e9, 2),
+                          "zip_kern": {k: round(v / a.steps, 1) for k, v in kz.items()}, "piz_kern": {k: round(v / a.steps, 1) for k, v in kp.items()},
+                          "round_trip": ok}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
