@@ -98,8 +98,8 @@ extern "C" int gzb_engine_create (int device, gzb_engine **out)
     e->device = device;
     e->sm_count = prop.multiProcessorCount;
     bool ok = cudaSetDevice (device) == cudaSuccess && cudaStreamCreateWithFlags (&e->stream, cudaStreamNonBlocking) == cudaSuccess;
-    cudaEvent_t *evs[6] = { &e->ev0, &e->ev1, &e->ev2, &e->ev3, &e->ev4, &e->ev5 };
-    for (int i = 0; ok && i < 6; i++) ok = cudaEventCreate (evs[i]) == cudaSuccess;
+    cudaEvent_t *evs[8] = { &e->ev0, &e->ev1, &e->ev2, &e->ev3, &e->ev4, &e->ev5, &e->ev6, &e->ev7 };
+    for (int i = 0; ok && i < 8; i++) ok = cudaEventCreate (evs[i]) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags (&e->stream2, cudaStreamNonBlocking) == cudaSuccess
             && cudaStreamCreateWithFlags (&e->stream3, cudaStreamNonBlocking) == cudaSuccess
             && cudaStreamCreateWithFlags (&e->stream4, cudaStreamNonBlocking) == cudaSuccess;
@@ -130,7 +130,7 @@ extern "C" void gzb_engine_destroy (gzb_engine *e)
     if (e->dq_buf) cudaFree (e->dq_buf);
     if (e->dq_session && e->dq_free) e->dq_free (e->dq_session);
     if (e->pin) cudaFreeHost (e->pin);
-    cudaEvent_t evs[6] = { e->ev0, e->ev1, e->ev2, e->ev3, e->ev4, e->ev5 };
+    cudaEvent_t evs[8] = { e->ev0, e->ev1, e->ev2, e->ev3, e->ev4, e->ev5, e->ev6, e->ev7 };
     for (cudaEvent_t ev : evs) if (ev) cudaEventDestroy (ev);
     if (e->stream2) cudaStreamDestroy (e->stream2);
     if (e->stream3) cudaStreamDestroy (e->stream3);
@@ -167,6 +167,7 @@ extern "C" float gzb_last_kernel_ms (gzb_engine *e, int which)
         case 3:  return e->last_o0_ms;
         case 4:  return e->last_split_ms;
         case 5:  return e->last_arith_all_ms;
+        case 6: case 7: case 8: return e->last_split_part_ms[which - 6];
         default: return 0;
     }
 }
@@ -355,7 +356,7 @@ static int compress_impl (gzb_engine *e, gzb_section *secs, uint32_t n, uint32_t
         if (L.coder == CODER_RANS) arena_est += (L.order_req & 1) ? std::min<size_t> (m * m * 20 + m * CTXB, 64 * 64 * 20 + 64 * CTXB + (size_t)L.n / 8) + 4096 : 4096 + 64;
         else {
             arena_est += std::min<size_t> ((size_t)256 * 264 * 4, 256 * 72 * 4 + (size_t)L.n / 8) + 258 * 12 * 4 + 64;
-            if ((L.order_req & 1) && L.n >= split_min) arena_est += 12 * (size_t)L.n + 257 * 4 + 64;   // split encoder: positions + records
+            if ((L.order_req & 1) && L.n >= split_min) arena_est += 12 * (size_t)L.n + (257 + 64) * 4 + 64;   // split encoder: positions + records
         }
     }
     if (e->arena_hint > arena_est) arena_est = e->arena_hint;
@@ -445,7 +446,7 @@ static int compress_impl (gzb_engine *e, gzb_section *secs, uint32_t n, uint32_t
         P.copy_parts = (n <= 64) ? 32 : (n <= 1024 ? 8 : 2);
         P.arena = Arena { d_arena, (unsigned long long)arena_est, d_cursor, d_overflow };
         P.ev_chain0 = e->ev0; P.ev_chain1 = e->ev1; P.ev_chain2 = e->ev2; P.ev_arith0 = e->ev3; P.st2 = e->stream2; P.ev_o0 = e->ev4; P.st3 = e->stream3;
-        P.ev_split = e->ev5; P.st4 = e->stream4; P.sm_count = e->sm_count;
+        P.ev_split = e->ev5; P.st4 = e->stream4; P.sm_count = e->sm_count; P.ev_prof[0] = e->ev6; P.ev_prof[1] = e->ev7;
 
         // ---- upload: metadata blob, inputs (small ones gathered through pinned staging)
         cudaStream_t st = e->stream;
@@ -481,7 +482,12 @@ static int compress_impl (gzb_engine *e, gzb_section *secs, uint32_t n, uint32_t
         float ms = 0; e->last_rans_ms = e->last_arith_ms = e->last_o0_ms = e->last_split_ms = 0;
         if (P.n_rans_jobs) { cudaEventElapsedTime (&ms, e->ev0, e->ev1); e->last_rans_ms = ms; }
         if (P.n_arith) { cudaEventElapsedTime (&ms, e->ev3, e->ev2); e->last_arith_ms = ms; cudaEventElapsedTime (&ms, e->ev3, e->ev4); e->last_o0_ms = ms; }
-        if (P.n_arith && P.n_arith_big) { cudaEventElapsedTime (&ms, e->ev3, e->ev5); e->last_split_ms = ms; }
+        if (P.n_arith && P.n_arith_big) {
+            cudaEventElapsedTime (&ms, e->ev3, e->ev5); e->last_split_ms = ms;
+            cudaEventElapsedTime (&e->last_split_part_ms[0], e->ev3, e->ev6);      // bucket (from the start of the chain phase), model, code
+            cudaEventElapsedTime (&e->last_split_part_ms[1], e->ev6, e->ev7);
+            cudaEventElapsedTime (&e->last_split_part_ms[2], e->ev7, e->ev5);
+        }
         e->last_arith_all_ms = std::max (e->last_arith_ms, std::max (e->last_o0_ms, e->last_split_ms));
         e->last_chain_ms = std::max (e->last_rans_ms, e->last_arith_all_ms);
 
@@ -649,6 +655,8 @@ extern "C" int gzb_uncompress_sections (gzb_engine *e, gzb_section *secs, uint32
         P.parts = (n <= 64) ? 32 : (n <= 1024 ? 8 : 2);
         P.arena = Arena { d_arena, (unsigned long long)arena_est, d_cursor, d_overflow };
         P.ev_chain0 = e->ev0; P.ev_chain1 = e->ev1; P.ev_chain2 = e->ev2; P.ev_arith0 = e->ev3; P.st2 = e->stream2; P.ev_o0 = e->ev4; P.st3 = e->stream3; P.sm_count = e->sm_count;
+        P.st4 = e->stream4; P.ev_long = e->ev5; P.long_min = chain_tune ().long_min; P.n_long_cand = 0;
+        while (P.n_long_cand < alist.size () && hs[alist[P.n_long_cand] >> 2].n >= P.long_min) P.n_long_cand++;
 
         cudaStream_t st = e->stream;
         memcpy (e->pin, meta.data (), meta_bytes);
@@ -677,7 +685,8 @@ extern "C" int gzb_uncompress_sections (gzb_engine *e, gzb_section *secs, uint32
         float ms = 0; e->last_rans_ms = e->last_arith_ms = e->last_o0_ms = e->last_split_ms = 0;
         if (P.n_rans_jobs) { cudaEventElapsedTime (&ms, e->ev0, e->ev1); e->last_rans_ms = ms; }
         if (P.n_arith) { cudaEventElapsedTime (&ms, e->ev3, e->ev2); e->last_arith_ms = ms; cudaEventElapsedTime (&ms, e->ev3, e->ev4); e->last_o0_ms = ms; }
-        e->last_arith_all_ms = std::max (e->last_arith_ms, e->last_o0_ms);
+        if (P.n_arith && P.n_long_cand) { cudaEventElapsedTime (&ms, e->ev3, e->ev5); e->last_split_ms = ms; }   // (which = 4 on the decode side: k_arith_decode_long)
+        e->last_arith_all_ms = std::max (e->last_arith_ms, std::max (e->last_o0_ms, e->last_split_ms));
         e->last_chain_ms = std::max (e->last_rans_ms, e->last_arith_all_ms);
         int rc = GZB_OK;
         for (uint32_t i = 0; i < n; i++) {

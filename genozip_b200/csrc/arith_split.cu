@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(SPLIT_WARPS * 32) k_ar_split_bucket (EncLeafDy
     EncLeafDyn &D = dyn[list[blockIdx.x]];
     if (!ar_split_leaf (D)) return;
     __shared__ uint32_t cur[SPLIT_WARPS][256];                               // counts, then write cursors, per warp segment and context
-    __shared__ uint32_t tot[256];
+    __shared__ uint32_t tot[256], cnt[256];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t n = D.eff_n;
     const uint8_t * __restrict__ in = D.eff_in;
@@ -40,8 +40,14 @@ __global__ void __launch_bounds__(SPLIT_WARPS * 32) k_ar_split_bucket (EncLeafDy
     __syncthreads ();
     for (uint32_t i = b + lane; i < e; i += 32) atomicAdd (&cur[warp][i ? in[i - 1] : 0], 1u);   // the context of symbol i (arith_dynamic.c:176: last = 0 at the start)
     __syncthreads ();
-    if (tid < 256) { uint32_t t = 0; for (int w = 0; w < SPLIT_WARPS; w++) t += cur[w][tid]; tot[tid] = t; }
+    if (tid < 256) { uint32_t t = 0; for (int w = 0; w < SPLIT_WARPS; w++) t += cur[w][tid]; tot[tid] = t; cnt[tid] = t; }
     __syncthreads ();
+    if (tid < 256) {                                                         // contexts by decreasing length of their sub-sequence: stage A takes the long ones first
+        const uint32_t mine = cnt[tid];
+        uint32_t rank = 0;
+        for (int c = 0; c < 256; c++) { const uint32_t o = cnt[c]; rank += (o > mine) || (o == mine && c < tid); }
+        reinterpret_cast<uint8_t *>(start + 257)[rank] = (uint8_t)tid;
+    }
     if (warp == 0) {                                                         // exclusive scan of the 256 totals: 8 per lane
         uint32_t s = 0, v[8];
         for (int k = 0; k < 8; k++) { v[k] = tot[8 * lane + k]; s += v[k]; }
@@ -94,46 +100,64 @@ __device__ __forceinline__ uint2 ar_model_rec (uint32_t *m, uint32_t maxs, ArCac
     return rec;
 }
 
-__global__ void __launch_bounds__(128) k_ar_split_model (EncLeafDyn *dyn, const uint32_t *list, uint32_t n_list)
+// Persistent warps take (rank, leaf) items from a counter, rank-major: every leaf's longest sub-sequence first, then every leaf's
+// second longest, ... — a (leaf, context) grid in index order would reach the last leaf's hot context only after all the others'
+// cold ones.  Within a sub-sequence a run of the context's top symbol is emitted by the lanes together: symbol k of the run
+// has cumFreq 0, freq f0 + 16k, totFreq tot + 16k (c_simple_model.h:123-146 applied k times; the halving bounds the run).
+__global__ void __launch_bounds__(128) k_ar_split_model (EncLeafDyn *dyn, const uint32_t *list, uint32_t n_list, uint32_t *queue)
 {
     const int lane = threadIdx.x & 31;
-    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;       // (leaf slot, context)
-    const uint32_t slot = w >> 8, ctx = w & 255;
-    if (slot >= n_list) return;
-    EncLeafDyn &D = dyn[list[slot]];
-    if (!ar_split_leaf (D)) return;
-    const uint32_t maxs = D.nsym;
-    if (ctx >= maxs) return;
-    const uint32_t j0 = D.split_start[ctx], j1 = D.split_start[ctx + 1];
-    if (j0 == j1) return;
-    const uint8_t * __restrict__ in = D.eff_in;
-    const uint32_t * __restrict__ pos = D.split_pos;
-    uint2 *recs = D.split_rec;
-    uint32_t *m = D.models + ctx * ar_stride (maxs);
-    ArCache c; ar_load (m, c);
-    bool dirty = false;
-    for (uint32_t j = j0; j < j1; j += 32) {
-        const uint32_t cnt = min (32u, j1 - j);
-        uint32_t my_p = 0, my_s = 0;
-        if ((uint32_t)lane < cnt) { my_p = pos[j + lane]; my_s = in[my_p]; }   // 32 symbols of the sub-sequence at once: the loads are off the chain
-        uint32_t my_x = 0, my_y = 0;
-        for (uint32_t t = 0; t < cnt; t++) {
-            const uint32_t s = __shfl_sync (0xffffffffu, my_s, t);
-            uint2 rec;
-            if ((c.e0 >> 16) == s && c.tot + AR_STEP <= AR_MAXF) {           // the top entry again: registers only (written back when another symbol comes)
-                rec.x = c.e0 << 16; rec.y = c.tot;
-                c.e0 += AR_STEP; c.tot += AR_STEP;
-                dirty = true;
-            }
-            else {
+    const uint32_t n_items = n_list * 256u;
+    for (;;) {
+        const uint32_t q = queue_take (queue, lane);
+        if (q >= n_items) return;
+        const uint32_t slot = q % n_list, rank = q / n_list;
+        EncLeafDyn &D = dyn[list[slot]];
+        if (!ar_split_leaf (D)) continue;
+        const uint32_t maxs = D.nsym;
+        const uint32_t ctx = reinterpret_cast<const uint8_t *>(D.split_start + 257)[rank];
+        if (ctx >= maxs) continue;
+        const uint32_t j0 = D.split_start[ctx], j1 = D.split_start[ctx + 1];
+        if (j0 == j1) continue;
+        const uint8_t * __restrict__ in = D.eff_in;
+        const uint32_t * __restrict__ pos = D.split_pos;
+        uint2 *recs = D.split_rec;
+        uint32_t *m = D.models + ctx * ar_stride (maxs);
+        ArCache c; ar_load (m, c);
+        bool dirty = false;
+        uint32_t nx_p = 0, nx_s = 0;
+        if (j0 + lane < j1) { nx_p = pos[j0 + lane]; nx_s = in[nx_p]; }
+        for (uint32_t j = j0; j < j1; j += 32) {
+            const uint32_t cnt = min (32u, j1 - j);
+            const uint32_t my_p = nx_p, my_s = nx_s;                           // 32 symbols of the sub-sequence at once; the next 32 are fetched under this group's work
+            if (j + 32 + lane < j1) { nx_p = pos[j + 32 + lane]; nx_s = in[nx_p]; }
+            uint32_t my_x = 0, my_y = 0;
+            uint32_t t = 0;
+            while (t < cnt) {
+                const uint32_t top = c.e0 >> 16;
+                const uint32_t hit = __ballot_sync (0xffffffffu, (uint32_t)lane < cnt && my_s == top) >> t;
+                uint32_t run = hit == 0xffffffffu ? 32u : (uint32_t)__ffs (~hit) - 1;   // symbols t .. t+run-1 are the top entry again
+                const uint32_t room = c.tot + AR_STEP <= AR_MAXF ? (AR_MAXF - c.tot) / AR_STEP : 0;
+                run = min (run, room);
+                if (run) {
+                    const uint32_t k = (uint32_t)lane - t;
+                    if (k < run) { my_x = (c.e0 + AR_STEP * k) << 16; my_y = c.tot + AR_STEP * k; }
+                    c.e0 += AR_STEP * run; c.tot += AR_STEP * run;
+                    dirty = true;
+                    t += run;
+                    continue;
+                }
                 if (dirty) { c.rtot = ar_rcp_below (c.tot); ar_flush (m, c); dirty = false; }
+                const uint32_t sy = __shfl_sync (0xffffffffu, my_s, t);
                 bool stale = false;
-                rec = ar_model_rec (m, maxs, c, s, lane, stale);
+                const uint2 rec = ar_model_rec (m, maxs, c, sy, lane, stale);
                 if (stale) ar_load (m, c);
+                if ((uint32_t)lane == t) { my_x = rec.x; my_y = rec.y; }
+                t++;
             }
-            if ((uint32_t)lane == t) { my_x = rec.x; my_y = rec.y; }
+            if ((uint32_t)lane < cnt) recs[my_p] = make_uint2 (my_x, my_y);
         }
-        if ((uint32_t)lane < cnt) recs[my_p] = make_uint2 (my_x, my_y);
+        if (dirty) { c.rtot = ar_rcp_below (c.tot); ar_flush (m, c); }
     }
 }
 
@@ -154,10 +178,12 @@ __global__ void __launch_bounds__(128) k_ar_split_code (const EncLeaf *leaves, E
     const uint8_t *limit = out + n + 8;
     uint32_t len = 0;
     bool full = false;
+    uint2 nx = make_uint2 (1u << 16, 1u);
+    if ((uint32_t)lane < n) nx = recs[lane];
     for (uint32_t i0 = 0; i0 < n && !full; i0 += 32) {
         const uint32_t cnt = min (32u, n - i0);
-        uint2 my = make_uint2 (1u << 16, 1u);
-        if ((uint32_t)lane < cnt) my = recs[i0 + lane];
+        const uint2 my = nx;                                                 // the next 32 records are fetched under this group's chain
+        if (i0 + 32 + lane < n) nx = recs[i0 + 32 + lane];
         const float my_r = ar_rcp_below (my.y);                              // 32 reciprocals at once, off the chain
         for (uint32_t t = 0; t < cnt; t++) {
             const uint32_t x = __shfl_sync (0xffffffffu, my.x, t), tot = __shfl_sync (0xffffffffu, my.y, t);
@@ -181,7 +207,12 @@ void launch_arith_encode_split (EncPlanDev &P, cudaStream_t st)
 {
     if (!P.n_arith_big) return;
     k_ar_split_bucket<<<P.n_arith_big, SPLIT_WARPS * 32, 0, st>>>(P.dyn, P.arith_list, P.n_arith_big);
-    k_ar_split_model<<<P.n_arith_big * 64, 128, 0, st>>>(P.dyn, P.arith_list, P.n_arith_big);
+    if (P.ev_prof[0]) cudaEventRecord (P.ev_prof[0], st);
+    {
+        const uint32_t want = P.n_arith_big * 64u, cap = (uint32_t)(P.sm_count > 0 ? P.sm_count : 148) * 8u;   // 8 CTAs = 32 warps per SM (64 registers per thread)
+        k_ar_split_model<<<want < cap ? want : cap, 128, 0, st>>>(P.dyn, P.arith_list, P.n_arith_big, P.queue + Q_SPLIT_MODEL);
+    }
+    if (P.ev_prof[1]) cudaEventRecord (P.ev_prof[1], st);
     k_ar_split_code<<<(P.n_arith_big + 3) / 4, 128, 0, st>>>(P.leaves, P.dyn, P.arith_list, P.n_arith_big);
 }
 

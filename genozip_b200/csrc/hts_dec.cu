@@ -417,6 +417,11 @@ void dec_run (DecPlanDev &P, cudaStream_t st)
     if (P.n_arith) {
         cudaStreamWaitEvent (P.st2, P.ev_chain0, 0);
         cudaEventRecord (P.ev_arith0, P.st2);
+        if (P.n_long_cand) {                                               // the long order-1 leaves first, on a stream of their own
+            cudaStreamWaitEvent (P.st4, P.ev_chain0, 0);
+            launch_arith_decode_long (P, P.st4); P.launches++;
+            cudaEventRecord (P.ev_long, P.st4);
+        }
         launch_arith_decode (P, P.st2); P.launches++;
         cudaEventRecord (P.ev_chain2, P.st2);
         cudaStreamWaitEvent (P.st3, P.ev_chain0, 0);
@@ -425,7 +430,7 @@ void dec_run (DecPlanDev &P, cudaStream_t st)
     }
     if (P.n_rans_jobs) { launch_rans_decode (P, st); P.launches++; }
     cudaEventRecord (P.ev_chain1, st);
-    if (P.n_arith) { cudaStreamWaitEvent (st, P.ev_chain2, 0); cudaStreamWaitEvent (st, P.ev_o0, 0); }
+    if (P.n_arith) { cudaStreamWaitEvent (st, P.ev_chain2, 0); cudaStreamWaitEvent (st, P.ev_o0, 0); if (P.n_long_cand) cudaStreamWaitEvent (st, P.ev_long, 0); }
     dim3 g (nslots, P.parts), gs (ns, P.parts);
     LAUNCH (k_dec_cat, g, 256, P.leaves, nslots);
     LAUNCH (k_dec_unpack, g, 256, P.leaves, P.results, nslots);

@@ -628,7 +628,7 @@ __global__ void k_arith_init (const EncLeaf *leaves, EncLeafDyn *dyn, const uint
         D.models = s_m = reinterpret_cast<uint32_t *>(arena.alloc (((unsigned long long)nctx * ar_stride (m + 1) + 258 * AR_RUN_STRIDE) * 4));
         if (s_m && D.eff_order && !(D.hdr[0] & F_RLE) && D.eff_n >= split_min) {       // long order-1 leaf: the split encoder (arith_split.cu)
             uint32_t *sp = reinterpret_cast<uint32_t *>(arena.alloc (4ull * D.eff_n));
-            uint32_t *ss = reinterpret_cast<uint32_t *>(arena.alloc (4ull * 257));
+            uint32_t *ss = reinterpret_cast<uint32_t *>(arena.alloc (4ull * (257 + 64)));     // start[257] + the contexts ranked by length (256 bytes)
             uint2    *sr = reinterpret_cast<uint2 *>(arena.alloc (8ull * D.eff_n));
             if (sp && ss && sr) { D.split_pos = sp; D.split_start = ss; D.split_rec = sr; }   // (else: the arena overflowed and the batch is replayed)
         }

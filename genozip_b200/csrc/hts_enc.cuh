@@ -24,6 +24,7 @@ struct EncPlanDev {              // device pointers of one encode batch
     bool           any_pack, any_o1;
     cudaEvent_t    ev_chain0, ev_chain1, ev_chain2, ev_arith0, ev_o0, ev_split;   // rANS kernel: chain0..chain1 on the main stream; arithmetic: arith0..chain2 on st2; order-0 arithmetic: .. ev_o0 on st3; split encoder: .. ev_split on st4
     cudaStream_t   st2, st3, st4;
+    cudaEvent_t    ev_prof[2];                            // after the split encoder's bucket / model kernels (their durations, for the bench's kernel table)
     uint32_t      *queue;                                 // zeroed work counters of the persistent chain kernels (Q_* below)
     int            sm_count;
     uint64_t       launches;
@@ -38,8 +39,9 @@ struct DecPlanDev {
     SectionResult *results;
     Arena          arena;
     int            rans_gpw, arith_lpw, parts;
-    cudaEvent_t    ev_chain0, ev_chain1, ev_chain2, ev_arith0, ev_o0;
-    cudaStream_t   st2, st3;
+    cudaEvent_t    ev_chain0, ev_chain1, ev_chain2, ev_arith0, ev_o0, ev_long;
+    cudaStream_t   st2, st3, st4;
+    uint32_t       n_long_cand, long_min;                 // the first n_long_cand entries of arith_list belong to sections of at least long_min bytes: candidates of k_arith_decode_long
     uint32_t      *queue;
     int            sm_count;
     uint64_t       launches;
@@ -48,8 +50,8 @@ struct DecPlanDev {
 // The chain kernels are PERSISTENT: a fixed number of CTAs per SM, every warp takes the next leaf of the (longest-first) list from a
 // counter until the list is empty.  What is resident on an SM is then a choice, not the block scheduler's "as many as fit": the
 // long leaves, taken first, share an issue port with a few other warps instead of fifteen (a chain wants a slot every ~6 cycles).
-enum { Q_ARITH = 0, Q_ARITH_O0 = 1, Q_SPLIT_CODE = 2, Q_WORDS = 64 };
-struct ChainTune { int arith_ctas, arith_o0_ctas, run4, split_stream; };      // CTAs per SM of the two arithmetic kernels; GZB_AR_* (see chain_tune)
+enum { Q_ARITH = 0, Q_ARITH_O0 = 1, Q_SPLIT_MODEL = 2, Q_ARITH_LONG = 3, Q_WORDS = 64 };
+struct ChainTune { int arith_ctas, arith_o0_ctas, run4, split_stream, long_ent; uint32_t long_min; };      // CTAs per SM of the two arithmetic kernels; GZB_AR_* (see chain_tune)
 const ChainTune &chain_tune ();
 __device__ __forceinline__ uint32_t queue_take (uint32_t *counter, int lane)
 {
@@ -68,5 +70,6 @@ void launch_arith_decode (DecPlanDev &P, cudaStream_t st);
 void launch_arith_encode_o0 (EncPlanDev &P, cudaStream_t st);
 void launch_arith_encode_split (EncPlanDev &P, cudaStream_t st);
 void launch_arith_decode_o0 (DecPlanDev &P, cudaStream_t st);
+void launch_arith_decode_long (DecPlanDev &P, cudaStream_t st);
 
 } // namespace gzb

@@ -167,7 +167,9 @@ class FastqCodecPath:
         self.dqs = {s: torch.empty((self.SB, c), **u8) for s, c in self.caps.items()}
         self.name_len = {"Q_TILE": n_reads, "Q_X": 4 * n_reads, "Q_Y": 4 * n_reads, "Q_MISC": n_reads}
         self.dq_arena = None                                                  # compact DOMQ streams of all V VBlocks
-        self.comp_arena = None                                                # packed compressed sections (device)
+        self.comp_arena = None                                                # packed compressed sections (device): the QUAL pipeline's
+        self.comp_arena2 = None                                               #   and the others'
+        self.device_pipelines = 2 if n_engines >= 2 else 1
         self.codec = {s: "RANB" for s in STREAMS}
         self.dvb = (DomqVb * V)(); self.pvb = (DomqPizVb * V)(); self.avb = (AcgtVb * V)()
         self.dvb_np, self.pvb_np, self.avb_np = struct_view(self.dvb), struct_view(self.pvb), struct_view(self.avb)
@@ -195,7 +197,7 @@ class FastqCodecPath:
     def release_device(self):
         """drop the device-resident leg's buffers (the host-buffer leg that follows allocates its own)"""
         self.close()
-        for a in ("packed_d", "x_d", "linedom_d", "linediv_d", "dq_arena", "comp_arena", "names_dec_d", "seq_out_d", "qual_out_d", "dec_d"):
+        for a in ("packed_d", "x_d", "linedom_d", "linediv_d", "dq_arena", "comp_arena", "comp_arena2", "names_dec_d", "seq_out_d", "qual_out_d", "dec_d"):
             setattr(self, a, None)
         self.dqs = {}
 
@@ -214,7 +216,7 @@ class FastqCodecPath:
         kernel_ms_detail: general / order-0 / split-encoder arithmetic kernels separately"""
         ms = lambda w: float(np.max([self.L.gzb_last_kernel_ms(e.h, w) for e in engs]))
         self.kernel_ms = (ms(0), ms(5))
-        self.kernel_ms_detail = {"rans": ms(0), "arith_general": ms(1), "arith_o0": ms(3), "arith_split": ms(4)}
+        self.kernel_ms_detail = {"rans": ms(0), "arith_general": ms(1), "arith_o0": ms(3), "arith_split": ms(4), "split_bucket": ms(6), "split_model": ms(7), "split_code": ms(8)}
 
     # ------------------------------------------------------------------ codec assignment (host policy, run on the GPU)
     def assign_codecs(self, data):
@@ -250,12 +252,13 @@ class FastqCodecPath:
         return data[s][v]
 
     # ------------------------------------------------------------------ the domain codecs of a batch
-    def _acgt_pack_device(self, data, meta, v0, v1):
+    def _acgt_pack_device(self, data, meta, v0, v1, eng=None):
+        eng = eng or self.eng
         a = self.avb_np
         a["seq"][v0:v1] = self._rows(data["seq"])[v0:v1]; a["n_bases"][v0:v1] = self.n
         a["packed"][v0:v1] = self._rows(self.packed_d)[v0:v1]; a["x"][v0:v1] = self._rows(self.x_d)[v0:v1]
-        if self.L.gzb_acgt_pack_batch(self.eng.h, self._sub(self.avb, v0, v1), v1 - v0, GZB_DEVICE_PTRS):
-            raise GzbError(f"gzb_acgt_pack_batch: {self.eng._err()}")
+        if self.L.gzb_acgt_pack_batch(eng.h, self._sub(self.avb, v0, v1), v1 - v0, GZB_DEVICE_PTRS):
+            raise GzbError(f"gzb_acgt_pack_batch: {eng._err()}")
         meta.acgt_no_x[v0:v1] = a["x_all_zero"][v0:v1] != 0
         meta.len[v0:v1, S_IDX["NONREF_X"]] = np.where(meta.acgt_no_x[v0:v1], 0, self.n)
 
@@ -354,17 +357,35 @@ class FastqCodecPath:
 
     # ------------------------------------------------------------------ ZIP, inputs resident in HBM
     def zip_device(self, data):
+        """inputs resident in HBM.  With two or more engines the QUAL pipeline (codec_domq_compress + its four sub-codec sections)
+        and the rest (codec_acgt_compress + the exception stream, the read-name contexts) run on one engine / host thread each: the
+        DOMQ passes of one overlap the entropy chains of the other — as two compute threads of the reference would."""
         V = self.V
         meta = ZipMeta(V)
-        self._acgt_pack_device(data, meta, 0, V)
-        self._domq_device(lambda v: data["qual"][v].data_ptr(), self.eng, meta, GZB_DEVICE_PTRS, 0, V)
         for s in NAMES:
             meta.len[:, S_IDX[s]] = self.name_len[s]
-        inp = self._in_ptrs(meta, {s: self._rows(data[s]) for s in NAMES}, self.dq_arena.data_ptr())
-        secs, a, vv, ss = self._section_array(meta, inp, STREAMS)
-        self._compress_packed(self.eng, secs, a, vv.size, GZB_DEVICE_PTRS, "comp_arena", False)
-        meta.comp_len[vv, ss] = a["out_len"][:vv.size]; meta.comp_ptr[vv, ss] = a["out"][:vv.size]
-        self._kernel_ms([self.eng])
+        name_rows = {s: self._rows(data[s]) for s in NAMES}
+
+        def compress(eng, names, arena):
+            inp = self._in_ptrs(meta, name_rows, self.dq_arena.data_ptr() if self.dq_arena is not None else 0)
+            secs, a, vv, ss = self._section_array(meta, inp, names)
+            self._compress_packed(eng, secs, a, vv.size, GZB_DEVICE_PTRS, arena, False)
+            meta.comp_len[vv, ss] = a["out_len"][:vv.size]; meta.comp_ptr[vv, ss] = a["out"][:vv.size]
+
+        def part_qual(eng):
+            self._domq_device(lambda v: data["qual"][v].data_ptr(), eng, meta, GZB_DEVICE_PTRS, 0, V)
+            compress(eng, DQ, "comp_arena")
+
+        def part_rest(eng):
+            self._acgt_pack_device(data, meta, 0, V, eng)
+            compress(eng, ("NONREF_X",) + NAMES, "comp_arena2")
+
+        if self.device_pipelines >= 2 and self.pool is not None and len(self.engs) >= 2:
+            self._run_parts([part_qual, part_rest])
+            self._kernel_ms(self.engs[:2])
+        else:
+            part_rest(self.eng); part_qual(self.eng)
+            self._kernel_ms([self.eng])
         self.meta = meta
         return meta
 
@@ -372,7 +393,7 @@ class FastqCodecPath:
         """the compressed section of stream s of VBlock v as a numpy array"""
         i = S_IDX[s]
         ln = int(meta.comp_len[v, i])
-        arena = self.h["comp_" + self._pipeline_of(s)] if host else self.comp_arena
+        arena = self.h["comp_" + self._pipeline_of(s)] if host else (self.comp_arena if s in DQ else self.comp_arena2)
         o = int(meta.comp_ptr[v, i]) - arena.data_ptr()
         return arena[o: o + ln].cpu().numpy()
 
@@ -410,18 +431,32 @@ class FastqCodecPath:
         a["x"] = np.where(meta.acgt_no_x, np.uint64(0), self._rows(self.x_d))
 
     def piz_device(self, meta):
-        L, eng = self.L, self.eng
+        L = self.L
         outp = self._in_ptrs(meta, {s: self._rows(self.names_dec_d[s]) for s in NAMES}, self.dq_arena.data_ptr())
-        secs, a, vv, ss = self._section_array(meta, meta.comp_ptr, STREAMS)
-        a["in_len"][:vv.size] = meta.comp_len[vv, ss]; a["out"][:vv.size] = outp[vv, ss]; a["out_cap"][:vv.size] = meta.len[vv, ss]
-        if vv.size:
-            eng.uncompress_raw(secs, vv.size, GZB_DEVICE_PTRS)
         self._fill_piz_descriptors(meta, self._rows(self.qual_out_d), self._rows(self.seq_out_d), self._rows(self.packed_d), self.line_len_d)
-        if L.gzb_domq_reconstruct(eng.h, self.pvb, self.V, GZB_DEVICE_PTRS):
-            raise GzbError(f"gzb_domq_reconstruct: {eng._err()}")
-        if L.gzb_acgt_unpack_batch(eng.h, self.avb, self.V, GZB_DEVICE_PTRS):
-            raise GzbError(f"gzb_acgt_unpack_batch: {eng._err()}")
-        self._kernel_ms([eng])
+
+        def uncompress(eng, names):
+            secs, a, vv, ss = self._section_array(meta, meta.comp_ptr, names)
+            a["in_len"][:vv.size] = meta.comp_len[vv, ss]; a["out"][:vv.size] = outp[vv, ss]; a["out_cap"][:vv.size] = meta.len[vv, ss]
+            if vv.size:
+                eng.uncompress_raw(secs, vv.size, GZB_DEVICE_PTRS)
+
+        def part_qual(eng):
+            uncompress(eng, DQ)
+            if L.gzb_domq_reconstruct(eng.h, self.pvb, self.V, GZB_DEVICE_PTRS):
+                raise GzbError(f"gzb_domq_reconstruct: {eng._err()}")
+
+        def part_rest(eng):
+            uncompress(eng, ("NONREF_X",) + NAMES)
+            if L.gzb_acgt_unpack_batch(eng.h, self.avb, self.V, GZB_DEVICE_PTRS):
+                raise GzbError(f"gzb_acgt_unpack_batch: {eng._err()}")
+
+        if self.device_pipelines >= 2 and self.pool is not None and len(self.engs) >= 2:
+            self._run_parts([part_qual, part_rest])
+            self._kernel_ms(self.engs[:2])
+        else:
+            part_qual(self.eng); part_rest(self.eng)
+            self._kernel_ms([self.eng])
 
     # ------------------------------------------------------------------ HOST-buffer path (e2e): what the C host would call
     def alloc_host(self, data):
@@ -456,7 +491,7 @@ class FastqCodecPath:
                     errs.append(ex)
             if errs:
                 raise errs[0]
-        self._kernel_ms(self.engs)
+        self._kernel_ms(self.engs)                                         # (host-buffer mode: every engine took part; the device mode narrows it afterwards)
 
     def zip_host(self, gate=None):
         """host buffers in, host buffers out; the DOMQ streams and the exception stream stay on the device between the complex codec

@@ -72,7 +72,7 @@ uint64_t gzb_kernel_launches (gzb_engine *e);                     /* kernels lau
 float gzb_last_chain_ms (gzb_engine *e);
 /* the same, split by coder: which = 0 rANS chain kernel, 1 general arithmetic chain kernel (order-1 / RLE leaves), 3 order-0 arithmetic
  * chain kernel, 4 the split arithmetic encoder (bucket + model + code kernels of the long order-1 leaves), 5 the longest of 1, 3, 4
- * (they run side by side); which = 2: the dominant kernel of the last PBWT / LONGR batch call (the row walk k_pbwt_rows, the channel
+ * (they run side by side), 6 / 7 / 8 the split encoder's bucket / model / code kernels; which = 2: the dominant kernel of the last PBWT / LONGR batch call (the row walk k_pbwt_rows, the channel
  * walk k_longr_channels / k_longr_decode) */
 float gzb_last_kernel_ms (gzb_engine *e, int which);
 
