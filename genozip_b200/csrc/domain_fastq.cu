@@ -183,28 +183,40 @@ __global__ void __launch_bounds__(256) k_domq_linehist (const DqVb *vbs, const u
     for (int i = tid; i < NQ * NQ; i += 256) h2[i] = 0;
     if (tid < NQ) lwd[tid] = 0;
     __syncthreads ();
-    for (uint32_t li = first + warp; li < last; li += 8) {
-        const uint32_t len = V.line_len[li];
-        if (!len) { if (lane == 0) { V.line_dom[li] = 0; V.line_diverse[li] = 0; } continue; }
-        for (int i = lane; i < 96; i += 32) lh[warp][i] = 0;
-        __syncwarp ();
-        const uint8_t *q = V.txt + V.line_off[li];
-        for (uint32_t i = lane; i < len; i += 32) atomicAdd (&lh[warp][q[i] - FIRST_Q], 1u);
-        __syncwarp ();
-        // dom = arg-max, ties -> the higher quality (:153-158)
-        uint32_t bc = 0, bq = 0;
-        for (int k = lane; k < NQ; k += 32) { uint32_t c = lh[warp][k]; if (c >= bc) { bc = c; bq = k; } }
-        for (int o = 16; o; o >>= 1) {
-            uint32_t oc = __shfl_xor_sync (0xffffffffu, bc, o), oq = __shfl_xor_sync (0xffffffffu, bq, o);
-            if (oc > bc || (oc == bc && oq > bq)) { bc = oc; bq = oq; }
+    // A warp takes 64 consecutive lines, 32 at a time: the lanes fetch the 32 lines' lengths and offsets together (one memory
+    // latency per 32 lines instead of two dependent ones per line) and write the 32 results together.
+    for (uint32_t g0 = first + warp * (LINES_PER_BLOCK / 8); g0 < min (last, first + (warp + 1) * (LINES_PER_BLOCK / 8)); g0 += 32) {
+        const uint32_t gl = g0 + lane, gend = min (last, first + (warp + 1) * (LINES_PER_BLOCK / 8));
+        const uint32_t my_len = gl < gend ? V.line_len[gl] : 0;
+        const uint64_t my_off = gl < gend ? V.line_off[gl] : 0;
+        uint32_t my_dom = 0, my_div = 0;
+        const uint32_t cnt = min (32u, gend - g0);
+        for (uint32_t t = 0; t < cnt; t++) {
+            const uint32_t len = __shfl_sync (0xffffffffu, my_len, t);
+            if (!len) continue;                                              // (dom 0, not diverse)
+            const uint8_t *q = V.txt + __shfl_sync (0xffffffffu, my_off, t);
+            for (int i = lane; i < 96; i += 32) lh[warp][i] = 0;
+            __syncwarp ();
+            for (uint32_t i0 = 0; i0 < len; i0 += 32) {                       // equal qualities of a 32-byte chunk are counted once, by their lowest lane
+                const uint32_t i = i0 + lane;
+                const uint32_t v = i < len ? (uint32_t)q[i] - FIRST_Q : 0x100u + lane;
+                const uint32_t peers = __match_any_sync (0xffffffffu, v);
+                if (i < len && (peers & ((1u << lane) - 1)) == 0) lh[warp][v] += __popc (peers);
+                __syncwarp ();
+            }
+            // dom = arg-max, ties -> the higher quality (:153-158)
+            uint32_t bc = 0, bq = 0;
+            for (int k = lane; k < NQ; k += 32) { uint32_t c = lh[warp][k]; if (c >= bc) { bc = c; bq = k; } }
+            for (int o = 16; o; o >>= 1) {
+                uint32_t oc = __shfl_xor_sync (0xffffffffu, bc, o), oq = __shfl_xor_sync (0xffffffffu, bq, o);
+                if (oc > bc || (oc == bc && oq > bq)) { bc = oc; bq = oq; }
+            }
+            if ((uint32_t)lane == t) { my_dom = bq; my_div = (100u * bc / len < 85u) ? 1 : 0; }   // DOMQ_THRESHOLD (:141,160)
+            if (lane == 0) atomicAdd (&lwd[bq], 1u);
+            for (int k = lane; k < NQ; k += 32) { uint32_t c = lh[warp][k]; if (c) atomicAdd (&h2[bq * NQ + k], c); }
+            __syncwarp ();
         }
-        if (lane == 0) {
-            V.line_dom[li] = (uint8_t)bq;
-            V.line_diverse[li] = (100u * bc / len < 85u) ? 1 : 0;                 // DOMQ_THRESHOLD (:141,160)
-            atomicAdd (&lwd[bq], 1u);
-        }
-        for (int k = lane; k < NQ; k += 32) { uint32_t c = lh[warp][k]; if (c) atomicAdd (&h2[bq * NQ + k], c); }
-        __syncwarp ();
+        if (gl < gend) { V.line_dom[gl] = (uint8_t)my_dom; V.line_diverse[gl] = (uint8_t)my_div; }
     }
     __syncthreads ();
     for (int i = tid; i < NQ * NQ; i += 256) if (h2[i]) atomicAdd (&V.hist[i], h2[i]);
@@ -277,17 +289,25 @@ __global__ void __launch_bounds__(256) k_domq_normalize (const DqVb *vbs, const 
     const DqVb &V = vbs[blk_vb[blockIdx.x]];
     const uint32_t first = blk_first[blockIdx.x], last = min (first + LINES_PER_BLOCK, V.n_lines);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (uint32_t li = first + warp; li < last; li += 8) {
-        const uint32_t len = V.line_len[li];
-        if (!len) continue;
-        const uint32_t cdom = V.dom_to_cdom[V.line_dom[li]];
-        const bool div = V.line_diverse[li];
-        const uint8_t *norm = V.normalize + cdom * NQ;
-        const uint8_t *q = V.txt + V.line_off[li];
-        uint8_t *dst = div ? V.divr + V.dv_off[li] : V.E + V.nd_off[li];
-        for (uint32_t i = lane; i < len; i += 32) dst[i] = norm[q[i] - FIRST_Q];
-        GZB_WARP_READS_DONE ();                                             // every lane has read line_dom[li]
-        if (lane == 0) { V.mplx[V.mx_idx[li]] = (uint8_t)(cdom | (div ? 0x80 : 0)); V.line_dom[li] = (uint8_t)cdom; }   // :436,446; ql->dom becomes cdom (:283-285)
+    // 64 consecutive lines per warp, 32 at a time: the lanes fetch the 32 lines' descriptors together, then the warp copies line by line
+    for (uint32_t g0 = first + warp * (LINES_PER_BLOCK / 8); g0 < min (last, first + (warp + 1) * (LINES_PER_BLOCK / 8)); g0 += 32) {
+        const uint32_t gl = g0 + lane, gend = min (last, first + (warp + 1) * (LINES_PER_BLOCK / 8));
+        uint32_t my_len = 0, my_cdom = 0, my_div = 0, my_dst = 0; uint64_t my_off = 0;
+        if (gl < gend) {
+            my_len = V.line_len[gl]; my_off = V.line_off[gl];
+            if (my_len) { my_cdom = V.dom_to_cdom[V.line_dom[gl]]; my_div = V.line_diverse[gl]; my_dst = my_div ? V.dv_off[gl] : V.nd_off[gl]; }
+        }
+        const uint32_t cnt = min (32u, gend - g0);
+        for (uint32_t t = 0; t < cnt; t++) {
+            const uint32_t len = __shfl_sync (0xffffffffu, my_len, t);
+            if (!len) continue;
+            const uint32_t cdom = __shfl_sync (0xffffffffu, my_cdom, t), div = __shfl_sync (0xffffffffu, my_div, t);
+            const uint8_t *norm = V.normalize + cdom * NQ;
+            const uint8_t *q = V.txt + __shfl_sync (0xffffffffu, my_off, t);
+            uint8_t *dst = (div ? V.divr : V.E) + __shfl_sync (0xffffffffu, my_dst, t);
+            for (uint32_t i = lane; i < len; i += 32) dst[i] = norm[q[i] - FIRST_Q];
+        }
+        if (gl < gend && my_len) { V.mplx[V.mx_idx[gl]] = (uint8_t)(my_cdom | (my_div ? 0x80 : 0)); V.line_dom[gl] = (uint8_t)my_cdom; }   // :436,446; ql->dom becomes cdom (:283-285)
     }
 }
 
@@ -669,6 +689,7 @@ struct DqLayout {
     std::vector<DqVb> h;           // host copies of the device descriptors
     DqVb *d_vbs = nullptr;
     uint32_t *d_bvb = nullptr, *d_bfirst = nullptr; uint32_t n_blocks = 0;
+    uint32_t *d_hist = nullptr, *d_lens = nullptr;   // [n_vbs][NQ*NQ+NQ] histograms, [n_vbs][8] stream lengths
     std::vector<uint8_t *> d_linedom, d_linediv;
 };
 
@@ -684,6 +705,8 @@ int dq_stage (gzb_engine *e, gzb_domq_vb *vbs, uint32_t n_vbs, bool devptr, bool
         c.off = 0;
         L.d_vbs = c.take<DqVb> (n_vbs);
         L.d_bvb = c.take<uint32_t> (bvb.size () + 1); L.d_bfirst = c.take<uint32_t> (bfirst.size () + 1);
+        L.d_hist = c.take<uint32_t> ((size_t)n_vbs * (NQ * NQ + NQ));       // the histograms and the stream lengths of all VBlocks, contiguous: one memset, one transfer
+        L.d_lens = c.take<uint32_t> ((size_t)n_vbs * 8);
         for (uint32_t v = 0; v < n_vbs; v++) {
             DqVb &D = L.h[v]; const gzb_domq_vb &S = vbs[v];
             uint64_t tot = 0;   // total quality bytes is unknown on the host in device mode: bound by txt_len
@@ -694,10 +717,10 @@ int dq_stage (gzb_engine *e, gzb_domq_vb *vbs, uint32_t n_vbs, bool devptr, bool
             D.line_len = devptr ? S.line_len : c.take<uint32_t> (S.n_lines + 1);
             D.line_dom = devptr ? S.line_dom : c.take<uint8_t> (S.n_lines + 1);
             D.line_diverse = devptr ? S.line_diverse : c.take<uint8_t> (S.n_lines + 1);
-            D.hist   = c.take<uint32_t> (NQ * NQ + NQ);
+            D.hist   = L.d_hist ? L.d_hist + (size_t)v * (NQ * NQ + NQ) : nullptr;
             D.nd_off = c.take<uint32_t> (S.n_lines + 1); D.dv_off = c.take<uint32_t> (S.n_lines + 1); D.mx_idx = c.take<uint32_t> (S.n_lines + 1);
             D.E      = c.take<uint8_t> (tot + 16);
-            D.lens   = c.take<uint32_t> (8);
+            D.lens   = L.d_lens ? L.d_lens + (size_t)v * 8 : nullptr;
             D.qual   = (devptr || outdev) ? (uint8_t *)S.qual : c.take<uint8_t> (2 * tot + 16);
             D.runs   = (devptr || outdev) ? (uint8_t *)S.runs : c.take<uint8_t> (tot + 16);
             D.mplx   = (devptr || outdev) ? (uint8_t *)S.mplx : c.take<uint8_t> (S.n_lines + 16);
@@ -744,20 +767,21 @@ extern "C" int gzb_domq_prepare (gzb_engine *e, gzb_domq_vb *vbs, uint32_t n_vbs
                 CK (cudaMemcpyAsync ((void *)D.line_len, vbs[v].line_len, (size_t)D.n_lines * 4, cudaMemcpyHostToDevice, st));
             }
         }
-        CK (cudaMemsetAsync (D.hist, 0, (NQ * NQ + NQ) * 4, st));
     }
+    const size_t hist_bytes = (size_t)n_vbs * (NQ * NQ + NQ) * 4;
+    rc = engine_reserve (e, 0, hist_bytes + (size_t)n_vbs * 32 + 256); if (rc) return rc;      // pinned landing area: histograms | lengths
+    uint32_t *const hist = reinterpret_cast<uint32_t *>(e->pin), *const lens = reinterpret_cast<uint32_t *>(e->pin + hist_bytes);
+    CK (cudaMemsetAsync (L->d_hist, 0, hist_bytes, st));
     CK (cudaMemcpyAsync (L->d_vbs, L->h.data (), n_vbs * sizeof (DqVb), cudaMemcpyHostToDevice, st));
     if (L->n_blocks) { k_domq_linehist<<<L->n_blocks, 256, 0, st>>>(L->d_vbs, L->d_bvb, L->d_bfirst); e->launches++; }
-    std::vector<uint32_t> hist ((size_t)n_vbs * (NQ * NQ + NQ));
-    for (uint32_t v = 0; v < n_vbs; v++)
-        CK (cudaMemcpyAsync (hist.data () + (size_t)v * (NQ * NQ + NQ), L->h[v].hist, (NQ * NQ + NQ) * 4, cudaMemcpyDeviceToHost, st));
+    CK (cudaMemcpyAsync (hist, L->d_hist, hist_bytes, cudaMemcpyDeviceToHost, st));
     CK (cudaStreamSynchronize (st));
 
     // host: compaction (:180-197) and per-dom rank tables (:199-247).  qsort's order among equal counts is whatever
     // this libc does — the same call with the same comparator the reference makes.
     for (uint32_t v = 0; v < n_vbs; v++) {
-        uint32_t (*H)[NQ] = reinterpret_cast<uint32_t (*)[NQ]>(hist.data () + (size_t)v * (NQ * NQ + NQ));
-        const uint32_t *lwd = hist.data () + (size_t)v * (NQ * NQ + NQ) + NQ * NQ;
+        uint32_t (*H)[NQ] = reinterpret_cast<uint32_t (*)[NQ]>(hist + (size_t)v * (NQ * NQ + NQ));
+        const uint32_t *lwd = hist + (size_t)v * (NQ * NQ + NQ) + NQ * NQ;
         gzb_domq_vb &S = vbs[v]; DqVb &D = L->h[v];
         memset (S.denorm, 0, sizeof S.denorm); memset (S.normalize, 0, sizeof S.normalize); memset (D.dom_to_cdom, 0, NQ);
         int num_doms = 0;
@@ -781,9 +805,8 @@ extern "C" int gzb_domq_prepare (gzb_engine *e, gzb_domq_vb *vbs, uint32_t n_vbs
     CK (cudaMemcpyAsync (L->d_vbs, L->h.data (), n_vbs * sizeof (DqVb), cudaMemcpyHostToDevice, st));
     k_domq_lineoffsets<<<n_vbs, 512, 0, st>>>(L->d_vbs); e->launches++;
     if (L->n_blocks) { k_domq_normalize<<<L->n_blocks, 256, 0, st>>>(L->d_vbs, L->d_bvb, L->d_bfirst); e->launches++; }
-    std::vector<uint32_t> lens ((size_t)n_vbs * 8);
+    CK (cudaMemcpyAsync (lens, L->d_lens, (size_t)n_vbs * 32, cudaMemcpyDeviceToHost, st));
     for (uint32_t v = 0; v < n_vbs; v++) {
-        CK (cudaMemcpyAsync (lens.data () + (size_t)v * 8, L->h[v].lens, 32, cudaMemcpyDeviceToHost, st));
         if (!devptr && vbs[v].n_lines) {
             if (vbs[v].line_dom) CK (cudaMemcpyAsync (vbs[v].line_dom, L->h[v].line_dom, vbs[v].n_lines, cudaMemcpyDeviceToHost, st));
             if (vbs[v].line_diverse) CK (cudaMemcpyAsync (vbs[v].line_diverse, L->h[v].line_diverse, vbs[v].n_lines, cudaMemcpyDeviceToHost, st));
@@ -809,11 +832,12 @@ extern "C" int gzb_domq_split (gzb_engine *e, gzb_domq_vb *vbs, uint32_t n_vbs, 
     if (!L || e->dq_n_vbs != n_vbs || e->dq_devptr != devptr) { e->err = "gzb_domq_split must follow gzb_domq_prepare on the same batch"; return GZB_E_BADARG; }
     cudaStream_t st = e->stream;
     k_domq_split<<<n_vbs, 512, 0, st>>>(L->d_vbs); e->launches++;
-    std::vector<uint32_t> lens ((size_t)n_vbs * 8);
-    for (uint32_t v = 0; v < n_vbs; v++) CK (cudaMemcpyAsync (lens.data () + (size_t)v * 8, L->h[v].lens, 32, cudaMemcpyDeviceToHost, st));
+    int rc = engine_reserve (e, 0, (size_t)n_vbs * 32 + 256); if (rc) return rc;
+    uint32_t *const lens = reinterpret_cast<uint32_t *>(e->pin);
+    CK (cudaMemcpyAsync (lens, L->d_lens, (size_t)n_vbs * 32, cudaMemcpyDeviceToHost, st));
     CK (cudaStreamSynchronize (st));
     for (uint32_t v = 0; v < n_vbs; v++) {
-        gzb_domq_vb &S = vbs[v]; const uint32_t *l = lens.data () + (size_t)v * 8;
+        gzb_domq_vb &S = vbs[v]; const uint32_t *l = lens + (size_t)v * 8;
         S.qual_len = l[0]; S.runs_len = l[1]; S.mplx_len = l[2]; S.divr_len = l[3];
         if (!devptr && !outdev) {
             if (S.qual_len > S.qual_cap || S.runs_len > S.runs_cap || S.mplx_len > S.mplx_cap || S.divr_len > S.divr_cap) { e->err = "DOMQ output capacity too small"; return GZB_E_BADARG; }

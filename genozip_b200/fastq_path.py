@@ -372,19 +372,29 @@ class FastqCodecPath:
             self._compress_packed(eng, secs, a, vv.size, GZB_DEVICE_PTRS, arena, False)
             meta.comp_len[vv, ss] = a["out_len"][:vv.size]; meta.comp_ptr[vv, ss] = a["out"][:vv.size]
 
+        # The chain kernels are long-running and fill the SMs' registers and shared memory: a short kernel launched after them (on any
+        # stream) only gets in when their CTAs retire.  So every bandwidth-shaped pass of the batch — ACGT pack, the DOMQ passes —
+        # runs BEFORE the first chain kernel of either pipeline is launched (measured: a DOMQ sub-batch behind the other pipeline's
+        # rANS chains waited 190 ms for its 13 ms of work).
+        domq_done = threading.Event()
+
         def part_qual(eng):
-            self._domq_device(lambda v: data["qual"][v].data_ptr(), eng, meta, GZB_DEVICE_PTRS, 0, V)
+            try:
+                self._domq_device(lambda v: data["qual"][v].data_ptr(), eng, meta, GZB_DEVICE_PTRS, 0, V)
+            finally:
+                domq_done.set()
             compress(eng, DQ, "comp_arena")
 
         def part_rest(eng):
             self._acgt_pack_device(data, meta, 0, V, eng)
+            domq_done.wait()
             compress(eng, ("NONREF_X",) + NAMES, "comp_arena2")
 
         if self.device_pipelines >= 2 and self.pool is not None and len(self.engs) >= 2:
             self._run_parts([part_qual, part_rest])
             self._kernel_ms(self.engs[:2])
         else:
-            part_rest(self.eng); part_qual(self.eng)
+            part_qual(self.eng); part_rest(self.eng)
             self._kernel_ms([self.eng])
         self.meta = meta
         return meta
@@ -521,6 +531,9 @@ class FastqCodecPath:
         for s in DQ + ("NONREF_X",):
             dev_in[S_IDX[s]] = GZB_SEC_IN_DEVICE                 # intermediate streams stay in HBM until their sub-codec
         qual_up = threading.Event()
+        passes_done = [threading.Event(), threading.Event()]        # the DOMQ passes / the ACGT pack of the whole group: chain kernels start after both (see zip_device)
+        if self.pool is None or len(self.engs) < 3:                 # (one engine: the parts run one after the other, nothing to wait for)
+            passes_done[0].set(); passes_done[1].set(); qual_up.set()
         name_rows = {s: self._rows(H[s]) for s in NAMES}
 
         def compress(eng, names, arena):
@@ -539,7 +552,8 @@ class FastqCodecPath:
                 if first < V:
                     self._domq_device(lambda v: H["qual"][v].data_ptr(), eng, meta, GZB_OUT_DEVICE, first, V)
             finally:
-                upload_done()
+                upload_done(); passes_done[0].set()
+            passes_done[1].wait()
             compress(eng, DQ, "comp_qual")
 
         def part_seq(eng):
@@ -552,13 +566,14 @@ class FastqCodecPath:
                     if L.gzb_acgt_pack_batch(eng.h, self._sub(self.avb, v0, v1), v1 - v0, GZB_OUT_DEVICE):
                         raise GzbError(f"gzb_acgt_pack_batch: {eng._err()}")
             finally:
-                upload_done()
+                upload_done(); passes_done[1].set()
             meta.acgt_no_x[:] = a["x_all_zero"] != 0
             meta.len[:, S_IDX["NONREF_X"]] = np.where(meta.acgt_no_x, 0, n)
+            passes_done[0].wait()
             compress(eng, ("NONREF_X",), "comp_seq")
 
         def part_names(eng):
-            qual_up.wait()
+            passes_done[0].wait(); passes_done[1].wait()
             compress(eng, NAMES, "comp_names")
 
         self._run_parts([part_qual, part_seq, part_names])

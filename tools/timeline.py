@@ -13,7 +13,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 TRACED = ("gzb_acgt_pack_batch", "gzb_acgt_unpack_batch", "gzb_domq_prepare", "gzb_domq_split", "gzb_domq_reconstruct",
-          "gzb_compress_sections", "gzb_uncompress_sections")
+          "gzb_compress_sections", "gzb_compress_sections_packed", "gzb_uncompress_sections", "gzb_copy_batch")
 
 
 class Tracer:
