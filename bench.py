@@ -37,8 +37,6 @@ def parse():
     ap.add_argument("--vcf-lines", type=int, default=38000); ap.add_argument("--vcf-samples", type=int, default=1000)
     ap.add_argument("--lr-bases", type=int, default=16_000_000); ap.add_argument("--lr-read-len", type=int, default=50000)
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-groups", type=int, default=int(os.environ.get("GZB_E2E_GROUPS", "3")),
-                    help="the host-buffer leg streams the step's VBlocks as this many groups (own engines and host threads each) that take turns on the PCIe link")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -234,6 +232,8 @@ def run_gpu(args):
         free_b, _ = torch.cuda.mem_get_info(dev)
         n = args.reads * args.read_len
         per_vb = 9.3 * n + 14 * args.reads + (6 << 20)          # inputs 2n, 2-bit words n/4, exception stream n, DOMQ streams ~0.4n, outputs 2n, engine workspace ~3.5n
+        if not args.no_e2e:
+            per_vb += 2.2 * n                                   # the pipelined host leg double-buffers the inputs and the outputs (its peak: 4n + 4n instead of 2n + 2n + the 2n of the generator's copy)
         V = int(max(8, min(768, (0.86 * free_b) // per_vb)))     # (measured on B200: 512 -> 17.7, 768 -> 22.2, 819 -> 21.7 GB/s: beyond ~768 the chain kernels are issue-bound)
         if not args.no_e2e:                                     # the host-buffer leg keeps pinned copies of inputs and outputs: ~4.6n per VBlock
             try:
@@ -338,45 +338,48 @@ def run_gpu(args):
     clk = clocks.stop()
     value = world * txt_bytes / ((zip_ms + piz_ms) * 1e-3) / 1e9
 
-    # e2e: same steps through the C-ABI with HOST (pinned) buffers — H2D of the inputs and D2H of the results inside.  The step's
-    # VBlocks go through as a stream of groups (fastq_path.HostStream): Ke zip steps back to back, then Ke piz steps, every group on
-    # its own engines and host thread, the groups taking turns on the PCIe link — what a dispatcher that keeps handing over VBlocks does.
+    # e2e: the same steps with HOST (page-locked) buffers in and out, every byte crossing PCIe inside the timed region, the way a host
+    # that keeps handing over VBlock batches drives the C-ABI (fastq_path.PipelinedHost): Ke zip steps back to back, then Ke piz steps;
+    # the next step's text is staged (gzb_stage_upload) and the previous step's results are fetched (gzb_stage_fetch) while the
+    # current step's kernels run on device buffers.
     e2e = None
     cpu_data = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n_cpu = min(V, 4 * (os.cpu_count() or 1))
         cpu_data = {k: [data[k][v].cpu().numpy() for v in range(n_cpu)] for k in data}
     if not args.no_e2e:
-        from genozip_b200.fastq_path import HostStream
-        path.release_device()
-        eng.trim(); torch.cuda.empty_cache()
-        hs = HostStream(eng, V, args.reads, args.read_len, codecs, groups=args.e2e_groups)
-        hs.alloc(data)
+        from genozip_b200.fastq_path import PipelinedHost
+        pin = lambda t: t.cpu().pin_memory()
+        host = {k: pin(v) for k, v in data.items()}
         del data
         torch.cuda.empty_cache()
-        Ke = max(2, args.steps // 2)
-        hs.zip_steps(1); hs.piz_steps(1)                                  # warm-up step (buffers grow to their sizes) + correctness gate
-        assert hs.check(), "host round trip failed"
+        path.seq_out_d = path.qual_out_d = path.names_dec_d = path.dec_d = None      # (the pipelined leg brings its own double-buffered outputs)
+        torch.cuda.empty_cache()
+        ph = PipelinedHost(path, host)
+        Ke = max(2, args.steps)
+        ph.zip_steps(1); ph.scrub(); ph.piz_steps(1)                      # warm-up step (buffers grow to their sizes) + correctness gate
+        assert ph.check(), "host round trip failed"
+        ph.scrub()
         barrier()
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         with torch.cuda.stream(stream):
             e0.record(stream)
-            h2d_z, d2h_z = hs.zip_steps(Ke)
+            h2d_z, d2h_z = ph.zip_steps(Ke)
             for _ in range(Ke):
-                section_list_gather([m for mm in hs.metas for m in mm])
+                section_list_gather(ph.meta)
             e1.record(stream)
-            h2d_p, d2h_p = hs.piz_steps(Ke)
+            h2d_p, d2h_p = ph.piz_steps(Ke)
             e2.record(stream)
         barrier()
-        assert hs.check(), "host round trip failed"
+        assert ph.check(), "host round trip failed"
         t = torch.tensor([e0.elapsed_time(e1) / Ke, e1.elapsed_time(e2) / Ke], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ez, ep = t[0].item(), t[1].item()
         e2e = {"value": world * txt_bytes / ((ez + ep) * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(world * (h2d_z + h2d_p)), "d2h_bytes_per_step": int(world * (d2h_z + d2h_p)),
-               "zip_ms": ez, "piz_ms": ep, "steps": Ke, "groups": len(hs.paths),
-               "how": "Ke zip steps back to back, then Ke piz steps; the step's VBlocks as `groups` groups on their own engines / host threads taking turns on the PCIe link"}
-        hs.close()
+               "zip_ms": ez, "piz_ms": ep, "steps": Ke,
+               "how": "Ke zip steps back to back, then Ke piz steps, host buffers in and out; the next step's text is staged and the previous step's results are fetched "
+                      "(gzb_stage_upload / gzb_stage_fetch) while the current step's kernels run; the first upload and the last fetch of each run are not hidden and are in the time"}
 
     # roofline of the dominant kernel: algorithmic bytes (N uncompressed + C compressed) / its launch time
     peaks = {}

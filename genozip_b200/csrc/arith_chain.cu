@@ -59,7 +59,9 @@ __global__ void __launch_bounds__(128) k_arith_encode_t (const EncLeaf *leaves, 
 //   GZB_AR0_CTAS    order-0 arithmetic kernel                                               default 4
 //   GZB_AR_RUN4     the decoder tries four run steps at once                                default 1
 //   GZB_AR_SPLIT_STREAM  the split encoder runs on its own stream beside the general kernel default 1
-//   GZB_AR_LONG_MIN order-1 leaves of at least this many symbols are decoded by k_arith_decode_long (off = none)   default 65536
+//   GZB_AR_LONG_MIN order-1 leaves of at least this many symbols are decoded by k_arith_decode_long (off = none)   default off
+//                   (measured, 768 VBlocks: alone the mirror takes the longest leaf from 332 to 305 / 286 ms (16 / 32 entries); beside the
+//                   rANS and order-0 kernels its shared memory costs them more residency than it gains: piz 445 -> 539 ms)
 //   GZB_AR_LONG_ENT entries per context it mirrors in shared memory: 16 or 32                  default 16
 const ChainTune &chain_tune ()                                               // (read at every call: a sweep inside one process changes the variables between batches)
 {
@@ -75,7 +77,7 @@ const ChainTune &chain_tune ()                                               // 
     c.run4 = geti ("GZB_AR_RUN4", 1, 0, 1);
     c.split_stream = geti ("GZB_AR_SPLIT_STREAM", 1, 0, 1);
     c.long_ent = geti ("GZB_AR_LONG_ENT", 16, 16, 32) >= 32 ? 32 : 16;
-    { const char *v = getenv ("GZB_AR_LONG_MIN"); c.long_min = !v || !*v ? 65536u : !strcmp (v, "off") ? 0xffffffffu : (uint32_t)strtoul (v, nullptr, 10); }
+    { const char *v = getenv ("GZB_AR_LONG_MIN"); c.long_min = !v || !*v || !strcmp (v, "off") ? 0xffffffffu : (uint32_t)strtoul (v, nullptr, 10); }
     return c;
 }
 

@@ -162,8 +162,13 @@ __global__ void __launch_bounds__(128) k_ar_split_model (EncLeafDyn *dyn, const 
 }
 
 // ------------------------------------------------------------------------------------------------ stage B
+// The loop-carried chain is range -> I2F -> FMUL -> F2I -> IMAD -> ISETP -> IMAD.  Everything else is kept off it: the 32 records of a
+// group and the reciprocals of their totals are staged in shared memory (one 16-byte load per symbol, issued one symbol ahead; the
+// next group's records are fetched from global memory one group ahead), the quotient's correction is a predicated increment (a
+// deficit above one — young models only — goes the long way through ar_div).
 __global__ void __launch_bounds__(128) k_ar_split_code (const EncLeaf *leaves, EncLeafDyn *dyn, const uint32_t *list, uint32_t n_list)
 {
+    __shared__ uint4 s_rec[4][2][32];                                        // per warp, two groups: cumFreq | freq << 16, totFreq, reciprocal, -
     const int lane = threadIdx.x & 31;
     const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (slot >= n_list) return;
@@ -182,15 +187,25 @@ __global__ void __launch_bounds__(128) k_ar_split_code (const EncLeaf *leaves, E
     if ((uint32_t)lane < n) nx = recs[lane];
     for (uint32_t i0 = 0; i0 < n && !full; i0 += 32) {
         const uint32_t cnt = min (32u, n - i0);
-        const uint2 my = nx;                                                 // the next 32 records are fetched under this group's chain
+        uint4 *buf = s_rec[threadIdx.x >> 5][(i0 >> 5) & 1];
+        const uint2 my = nx;
         if (i0 + 32 + lane < n) nx = recs[i0 + 32 + lane];
-        const float my_r = ar_rcp_below (my.y);                              // 32 reciprocals at once, off the chain
+        buf[lane] = make_uint4 (my.x, my.y, ar_f2u (ar_rcp_below (my.y)), 0u);
+        __syncwarp ();
+        uint4 r_next = buf[0];
         for (uint32_t t = 0; t < cnt; t++) {
-            const uint32_t x = __shfl_sync (0xffffffffu, my.x, t), tot = __shfl_sync (0xffffffffu, my.y, t);
-            const float rt = __shfl_sync (0xffffffffu, my_r, t);
-            const uint32_t r = ar_div (rc.range, tot, rt);                   // RC_Encode (c_range_coder.h:97-109)
+            const uint4 r_ = r_next;
+            r_next = buf[(t + 1) & 31];
+            const uint32_t tot = r_.y;
+#ifdef __CUDA_ARCH__
+            uint32_t q = __float2uint_rz (__fmul_rz (__uint2float_rz (rc.range), ar_u2f (r_.z)));
+            const uint32_t rem = rc.range - q * tot;                         // RC_Encode (c_range_coder.h:97-109): range / totFreq, exactly
+            if (rem >= tot) { if (rem - tot >= tot) q = ar_div (rc.range, tot, ar_u2f (r_.z)); else q++; }
+#else
+            const uint32_t q = rc.range / tot;
+#endif
             const uint32_t before = rc.low;
-            rc.low += (x & 0xffffu) * r; rc.range = (x >> 16) * r;
+            rc.low += (r_.x & 0xffffu) * q; rc.range = (r_.x >> 16) * q;
             rc.carry += rc.low < before;
             if (rc.range < AR_TOP) {
                 do { rc.range <<= 8; ar_shift_low (rc); } while (rc.range < AR_TOP);

@@ -7,7 +7,7 @@
 struct gzb_engine {
     int          device = 0;
     int          sm_count = 0;
-    cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr, stream4 = nullptr;   // stream2 / stream3 / stream4: the arithmetic chain kernels (general / order-0 / split encoder) run beside the rANS one
+    cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr, stream4 = nullptr, stream_copy = nullptr, stream_copy2 = nullptr;   // stream2 / stream3 / stream4: the arithmetic chain kernels (general / order-0 / split encoder) run beside the rANS one; stream_copy / stream_copy2: gzb_stage_upload / gzb_stage_fetch transfers
     cudaEvent_t  ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev4 = nullptr, ev5 = nullptr, ev6 = nullptr, ev7 = nullptr;   // ev0..ev1: rANS chain kernel, ev3..ev2: arithmetic chain kernel, ev3..ev4: order-0 arithmetic, ev3..ev5: split arithmetic encoder
     uint8_t     *ws = nullptr;   size_t ws_cap = 0; // device workspace (grow-only)
     uint8_t     *pin = nullptr;  size_t pin_cap = 0;// pinned host staging (grow-only)

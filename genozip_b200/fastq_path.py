@@ -170,6 +170,7 @@ class FastqCodecPath:
         self.comp_arena = None                                                # packed compressed sections (device): the QUAL pipeline's
         self.comp_arena2 = None                                               #   and the others'
         self.device_pipelines = 2 if n_engines >= 2 else 1
+        self.comp_used = {}                                                   # bytes of packed sections in each output buffer after the last zip
         self.codec = {s: "RANB" for s in STREAMS}
         self.dvb = (DomqVb * V)(); self.pvb = (DomqPizVb * V)(); self.avb = (AcgtVb * V)()
         self.dvb_np, self.pvb_np, self.avb_np = struct_view(self.dvb), struct_view(self.pvb), struct_view(self.avb)
@@ -353,6 +354,7 @@ class FastqCodecPath:
             if a["status"][:n].any():
                 i = int(np.nonzero(a["status"][:n])[0][0])
                 raise GzbError(f"section {i}: status {int(a['status'][i])}")
+            self.comp_used[arena_attr] = int(used.value)
             return
 
     # ------------------------------------------------------------------ ZIP, inputs resident in HBM
@@ -440,10 +442,13 @@ class FastqCodecPath:
         a["seq"] = seq_out_rows; a["n_bases"] = self.n; a["packed"] = packed_rows
         a["x"] = np.where(meta.acgt_no_x, np.uint64(0), self._rows(self.x_d))
 
-    def piz_device(self, meta):
+    def piz_device(self, meta, outs=None):
+        """outs: where the reconstructed streams go — {"seq", "qual", "Q_TILE", ...} device tensors [V, ...]; default: the buffers of alloc_piz"""
         L = self.L
-        outp = self._in_ptrs(meta, {s: self._rows(self.names_dec_d[s]) for s in NAMES}, self.dq_arena.data_ptr())
-        self._fill_piz_descriptors(meta, self._rows(self.qual_out_d), self._rows(self.seq_out_d), self._rows(self.packed_d), self.line_len_d)
+        if outs is None:
+            outs = dict(self.names_dec_d, seq=self.seq_out_d, qual=self.qual_out_d)
+        outp = self._in_ptrs(meta, {s: self._rows(outs[s]) for s in NAMES}, self.dq_arena.data_ptr())
+        self._fill_piz_descriptors(meta, self._rows(outs["qual"]), self._rows(outs["seq"]), self._rows(self.packed_d), self.line_len_d)
 
         def uncompress(eng, names):
             secs, a, vv, ss = self._section_array(meta, meta.comp_ptr, names)
@@ -503,28 +508,15 @@ class FastqCodecPath:
                 raise errs[0]
         self._kernel_ms(self.engs)                                         # (host-buffer mode: every engine took part; the device mode narrows it afterwards)
 
-    def zip_host(self, gate=None):
+    def zip_host(self):
         """host buffers in, host buffers out; the DOMQ streams and the exception stream stay on the device between the complex codec
         and its sub-codec (GZB_OUT_DEVICE / GZB_SEC_IN_DEVICE) exactly as they stay inside one compute thread in the reference.
         The three independent pipelines of a FASTQ VBlock — QUAL (DOMQ + its four sub-streams), SEQ (ACGT + its exception
         stream) and the read-name contexts — run on one engine (host thread + stream) each, so the transfers of one
         overlap the entropy chains of another; QUAL's upload goes first because its chains are the longest.
-        `gate` (HostStream): a lock held while this VBlock group's bulk inputs cross PCIe, so that the groups of a stream take turns
-        uploading and one group's upload runs under another group's chains.
         Returns (meta, h2d_bytes, d2h_bytes)."""
         L, V, n, H = self.L, self.V, self.n, self.h
         meta = ZipMeta(V)
-        gate_left = [2]; gate_lock = threading.Lock()
-        if gate is not None:
-            gate.acquire()
-
-        def upload_done():                                       # QUAL and SEQ have both crossed: the next group may start its upload
-            if gate is None:
-                return
-            with gate_lock:
-                gate_left[0] -= 1
-                if gate_left[0] == 0:
-                    gate.release()
         for s in NAMES:
             meta.len[:, S_IDX[s]] = self.name_len[s]
         dev_in = np.zeros(len(STREAMS), np.uint32)
@@ -552,7 +544,7 @@ class FastqCodecPath:
                 if first < V:
                     self._domq_device(lambda v: H["qual"][v].data_ptr(), eng, meta, GZB_OUT_DEVICE, first, V)
             finally:
-                upload_done(); passes_done[0].set()
+                passes_done[0].set()
             passes_done[1].wait()
             compress(eng, DQ, "comp_qual")
 
@@ -566,7 +558,7 @@ class FastqCodecPath:
                     if L.gzb_acgt_pack_batch(eng.h, self._sub(self.avb, v0, v1), v1 - v0, GZB_OUT_DEVICE):
                         raise GzbError(f"gzb_acgt_pack_batch: {eng._err()}")
             finally:
-                upload_done(); passes_done[1].set()
+                passes_done[1].set()
             meta.acgt_no_x[:] = a["x_all_zero"] != 0
             meta.len[:, S_IDX["NONREF_X"]] = np.where(meta.acgt_no_x, 0, n)
             passes_done[0].wait()
@@ -583,8 +575,8 @@ class FastqCodecPath:
         d2h = V * (self.packed_len + 2 * self.n_reads) + int(meta.comp_len.sum())
         return meta, h2d, d2h
 
-    def piz_host(self, meta, gate=None):
-        """the inverse of zip_host.  `gate` (HostStream): a lock held while this group's reconstructed QUAL / SEQ cross PCIe."""
+    def piz_host(self, meta):
+        """the inverse of zip_host"""
         L, V, n, H = self.L, self.V, self.n, self.h
         dev_out = np.zeros(len(STREAMS), np.uint32)
         for s in DQ + ("NONREF_X",):
@@ -599,25 +591,17 @@ class FastqCodecPath:
 
         self._fill_piz_descriptors(meta, self._rows(H["qual_out"]), self._rows(H["seq_out"]), self._rows(H["packed"]), self.line_len_h)
 
-        class _Held:                                             # the gate, or nothing
-            def __enter__(s_):
-                if gate is not None: gate.acquire()
-            def __exit__(s_, *a_):
-                if gate is not None: gate.release()
-
         def part_qual(eng):
             uncompress(eng, DQ)
-            with _Held():
-                if L.gzb_domq_reconstruct(eng.h, self.pvb, V, GZB_IN_DEVICE):
-                    raise GzbError(f"gzb_domq_reconstruct: {eng._err()}")
+            if L.gzb_domq_reconstruct(eng.h, self.pvb, V, GZB_IN_DEVICE):
+                raise GzbError(f"gzb_domq_reconstruct: {eng._err()}")
 
         def part_seq(eng):
             uncompress(eng, ("NONREF_X",))
-            with _Held():
-                for v0 in range(0, V, 64):
-                    v1 = min(V, v0 + 64)
-                    if L.gzb_acgt_unpack_batch(eng.h, self._sub(self.avb, v0, v1), v1 - v0, GZB_IN_DEVICE):
-                        raise GzbError(f"gzb_acgt_unpack_batch: {eng._err()}")
+            for v0 in range(0, V, 64):
+                v1 = min(V, v0 + 64)
+                if L.gzb_acgt_unpack_batch(eng.h, self._sub(self.avb, v0, v1), v1 - v0, GZB_IN_DEVICE):
+                    raise GzbError(f"gzb_acgt_unpack_batch: {eng._err()}")
 
         def part_names(eng):
             uncompress(eng, NAMES)
@@ -630,76 +614,106 @@ class FastqCodecPath:
         return h2d, d2h
 
 
-class HostStream:
-    """The host-buffer path as a STREAM of VBlock groups — what genozip's dispatcher does with VBlocks, at the granularity the GPU
-    wants: G groups, each a FastqCodecPath over V/G VBlocks with its own engines, device buffers and pinned host buffers, each
-    driven by its own host thread, step after step without a barrier in between.  The groups take turns on the PCIe link (a lock
-    around the bulk upload of zip and the bulk download of piz), so in steady state one group's inputs upload while the other
-    groups' entropy chains run and a third group's results go back: the chains are latency-bound (a group's chain phase lasts as
-    long as its longest leaf whatever its size) and the link is bandwidth-bound, so they overlap almost perfectly.
-    Results and byte counts are those of zip_host / piz_host, summed."""
+UPLOADS, FETCHES, ALL = 0, 1, 2                                             # gzb_stage_wait
 
-    def __init__(self, eng, V, n_reads, read_len, codec, groups=3, engine_factory=None):
-        G = max(1, min(groups, V))
-        self.bounds = [(V * g // G, V * (g + 1) // G) for g in range(G)]
-        mk = engine_factory or (lambda: type(eng)(eng.device))
-        self.own = [mk() for _ in range(G)]
-        self.paths = [FastqCodecPath(self.own[g], b - a, n_reads, read_len) for g, (a, b) in enumerate(self.bounds)]
-        for p in self.paths:
-            p.codec = dict(codec)
-        self.link = threading.Lock()
-        self.threads = ThreadPoolExecutor(G)
-        self.metas = None
 
-    def alloc(self, data, metas=None):
-        """pinned host buffers of every group (its slice of `data`); metas: per-group ZipMeta of a device pass (sizes the packed output buffers)"""
-        for p, (a, b) in zip(self.paths, self.bounds):
-            if metas is not None:
-                p.meta = metas[self.paths.index(p)]
-            p.alloc_host({k: v[a:b] for k, v in data.items()})
+class PipelinedHost:
+    """The host-buffer leg as a host that keeps handing over VBlock batches runs it (what genozip's dispatcher does with VBlocks): text
+    and sections cross PCIe on the engine's copy streams (gzb_stage_upload / gzb_stage_fetch) while the PREVIOUS / NEXT batch's
+    kernels run on device buffers (GZB_DEVICE_PTRS):
 
-    def _run(self, fn, K):
-        futs = [self.threads.submit(fn, g, K) for g in range(len(self.paths))]
-        errs, out = [], []
-        for f in futs:
-            try:
-                out.append(f.result())
-            except Exception as ex:
-                errs.append(ex)
-        if errs:
-            raise errs[0]
-        return out
+      zip   upload(k+1)  ||  [ACGT pack, DOMQ passes, entropy chains](k)   then fetch(2-bit words, packed sections)(k)
+      piz   upload(2-bit words, sections)(k+1), fetch(SEQ, QUAL, names)(k-1)  ||  [entropy chains, DOMQ / ACGT reconstruct](k)
+
+    The entropy chains are latency-bound and leave the copy engines idle; the transfers are bandwidth-bound and need no SM: two
+    input buffers (zip) and two output buffers (piz) on the device are all it takes.  Host buffers are page-locked."""
+
+    def __init__(self, path, data_host):
+        self.path, self.H = path, data_host                                  # data_host: pinned [V, ...] tensors seq, qual, Q_*
+        self.eng, self.L = path.eng, path.L
+        dev = path.dev
+        self.in_slots = [{k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in data_host.items()} for _ in range(2)]
+        self.out_slots = None
+        self.h_packed = _pin(torch.empty((path.V, path.packed_len + 32), dtype=torch.uint8))
+        self.h_comp = {}
+        pad = lambda k, v: (v.shape[0], v.shape[1] + (16 if k in NAMES else 0))   # (the read-name buffers carry the 16 bytes of slack alloc_piz gives them)
+        self.out_shape = {k: pad(k, v) for k, v in data_host.items()}
+        self.h_out = {k: _pin(torch.empty(self.out_shape[k], dtype=torch.uint8)) for k in data_host}
+        self.meta = None
+
+    def _up(self, dst, src, nbytes=None):
+        if self.L.gzb_stage_upload(self.eng.h, dst.data_ptr(), src.data_ptr(), dst.numel() * dst.element_size() if nbytes is None else nbytes):
+            raise GzbError(f"gzb_stage_upload: {self.eng._err()}")
+
+    def _down(self, dst, src, nbytes=None):
+        if self.L.gzb_stage_fetch(self.eng.h, dst.data_ptr(), src.data_ptr(), src.numel() * src.element_size() if nbytes is None else nbytes):
+            raise GzbError(f"gzb_stage_fetch: {self.eng._err()}")
+
+    def _wait(self, which=ALL):
+        if self.L.gzb_stage_wait(self.eng.h, which):
+            raise GzbError(f"gzb_stage_wait: {self.eng._err()}")
 
     def zip_steps(self, K=1):
-        """K zip passes of every group, back to back; returns (h2d_bytes, d2h_bytes) of ONE step (all groups)"""
-        def work(g, K):
-            r = None
-            for _ in range(K):
-                r = self.paths[g].zip_host(gate=self.link)
-            return r
-        res = self._run(work, K)
-        self.metas = [r[0] for r in res]
-        return sum(r[1] for r in res), sum(r[2] for r in res)
+        """K zip passes over the host buffers, back to back; returns (h2d_bytes, d2h_bytes) of ONE step"""
+        p = self.path
+        for k_, t in self.H.items():
+            self._up(self.in_slots[0][k_], t)
+        h2d = sum(t.numel() for t in self.H.values())
+        d2h = 0
+        meta = None
+        for k in range(K):
+            self._wait(ALL)                                                  # step k's text is on the device, step k-1's sections are on the host
+            if k + 1 < K:
+                for k_, t in self.H.items():
+                    self._up(self.in_slots[(k + 1) & 1][k_], t)               # crosses PCIe under this step's kernels
+            meta = p.zip_device(self.in_slots[k & 1])
+            self._down(self.h_packed, p.packed_d)
+            d2h = self.h_packed.numel()
+            for a in ("comp_arena", "comp_arena2"):
+                used = p.comp_used.get(a, 0)
+                if used:
+                    if a not in self.h_comp or self.h_comp[a].numel() < used:
+                        self.h_comp[a] = _pin(torch.empty(int(used * 1.05) + 4096, dtype=torch.uint8))
+                    self._down(self.h_comp[a], getattr(p, a), used)
+                    d2h += used
+        self._wait(ALL)
+        self.meta = meta
+        return h2d, d2h
+
+    def _upload_sections(self):
+        p = self.path
+        self._up(p.packed_d, self.h_packed)
+        n = self.h_packed.numel()
+        for a in ("comp_arena", "comp_arena2"):
+            used = p.comp_used.get(a, 0)
+            if used:
+                self._up(getattr(p, a), self.h_comp[a], used); n += used
+        return n
 
     def piz_steps(self, K=1):
-        def work(g, K):
-            r = None
-            for _ in range(K):
-                r = self.paths[g].piz_host(self.metas[g], gate=self.link)
-            return r
-        res = self._run(work, K)
-        return sum(r[0] for r in res), sum(r[1] for r in res)
+        """K piz passes: the sections and 2-bit words go up, SEQ / QUAL / the read-name contexts come back into the host output buffers"""
+        p, meta = self.path, self.meta
+        if self.out_slots is None:
+            self.out_slots = [{k: torch.empty(self.out_shape[k], dtype=torch.uint8, device=p.dev) for k in self.H} for _ in range(2)]
+        h2d = self._upload_sections()
+        d2h = 0
+        for k in range(K):
+            self._wait(UPLOADS)                                              # step k's sections are on the device
+            outs = self.out_slots[k & 1]
+            p.piz_device(meta, outs)
+            self._wait(FETCHES)                                              # step k-1's text reached the host under this step's chains
+            if k + 1 < K:
+                self._upload_sections()                                      # (the kernels of step k are done with the section buffers)
+            for k_, t in outs.items():
+                self._down(self.h_out[k_], t)                                 # crosses PCIe under the next step's chains
+            d2h = sum(t.numel() for t in outs.values())
+        self._wait(ALL)
+        return h2d, d2h
 
     def check(self):
-        return all(torch.equal(p.h["seq_out"], p.h["seq"]) and torch.equal(p.h["qual_out"], p.h["qual"]) for p in self.paths)
+        return all(torch.equal(self.h_out[k][:, :self.H[k].shape[1]], self.H[k]) for k in self.H)
 
-    @property
-    def launches(self):
-        return sum(p.launches for p in self.paths)
-
-    def close(self):
-        self.threads.shutdown(wait=True)
-        for p in self.paths:
-            p.close()
-        for e in self.own:
-            e.close()
+    def scrub(self):
+        """empty the host output buffers (a round-trip check then sees what piz_steps produced)"""
+        for t in self.h_out.values():
+            t.zero_()

@@ -57,6 +57,10 @@ class Copy(C.Structure):            # gzb_copy
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("len", C.c_uint64)]
 
 
+class DigestItem(C.Structure):      # gzb_digest_item
+    _fields_ = [("data", C.c_void_p), ("len", C.c_uint64), ("adler", C.c_uint32), ("reserved", C.c_uint32)]
+
+
 class LongrVb(C.Structure):         # gzb_longr_vb
     _fields_ = [("txt", C.c_void_p), ("txt_len", C.c_uint64), ("seq_off", C.c_void_p), ("qual_off", C.c_void_p),
                 ("len", C.c_void_p), ("is_rev", C.c_void_p), ("n_lines", C.c_uint32), ("value_to_bin", C.c_uint8 * 256),
@@ -131,6 +135,11 @@ def load():
     L.gzb_compress_sections_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32]
     L.gzb_copy_batch.restype = C.c_int
     L.gzb_copy_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    for f in ("gzb_stage_upload", "gzb_stage_fetch"):
+        getattr(L, f).restype = C.c_int; getattr(L, f).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.gzb_stage_wait.restype = C.c_int; L.gzb_stage_wait.argtypes = [C.c_void_p, C.c_int]
+    L.gzb_adler32_batch.restype = C.c_int
+    L.gzb_adler32_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
     L.gzb_pbwt_decode.restype = C.c_int
     L.gzb_pbwt_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64,
                                   C.POINTER(C.c_uint64), C.c_uint32]
@@ -267,6 +276,21 @@ class Engine:
         rc = self.L.gzb_uncompress_sections(self.h, secs, n, flags)
         if rc != 0:
             raise GzbError(f"gzb_uncompress_sections failed ({rc}): {self._err()}")
+
+    # ---- Adler-32 (host buffers; device pointers through adler32_ptrs) ----
+    def adler32(self, bufs):
+        """adler32 (1, data, len) of every buffer (compressor.c:151,161 z_digest) -> list of ints"""
+        arrs = [np.ascontiguousarray(b, dtype=np.uint8) for b in bufs]
+        return self.adler32_ptrs([(a.ctypes.data if a.size else 0, a.size) for a in arrs], 0)
+
+    def adler32_ptrs(self, ptr_len, flags):
+        items = (DigestItem * max(1, len(ptr_len)))()
+        for i, (p, n) in enumerate(ptr_len):
+            items[i].data = p; items[i].len = n
+        rc = self.L.gzb_adler32_batch(self.h, items, len(ptr_len), flags)
+        if rc != 0:
+            raise GzbError(f"gzb_adler32_batch failed ({rc}): {self._err()}")
+        return [int(items[i].adler) for i in range(len(ptr_len))]
 
     # ---- ACGT (host buffers) ----
     def acgt_pack(self, seq):

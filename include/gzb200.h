@@ -67,6 +67,14 @@ void *gzb_engine_stream (gzb_engine *e);                          /* the cudaStr
 int   gzb_engine_sync (gzb_engine *e);
 int   gzb_engine_trim (gzb_engine *e);                            /* frees the engine's grow-only device workspace and pinned staging (they come back on demand) */
 int   gzb_vb_device (uint32_t vblock_i, int n_devices);           /* (vblock_i-1) mod n_devices — the dispatcher's round-robin */
+/* staging (gzb_vb_stage): asynchronous host<->device transfers on the engine's copy stream, so that the host uploads
+ * the next batch's text (vb->txt_data) and fetches the previous batch's sections (vb->z_data) while the current batch's kernels
+ * run on buffers it passes with GZB_DEVICE_PTRS.  Host memory should be page-locked.  Uploads and fetches are two queues (the link is
+ * full duplex), each in order; gzb_stage_wait returns when every upload / every fetch / every transfer queued so far has completed. */
+enum { GZB_STAGE_UPLOADS = 0, GZB_STAGE_FETCHES = 1, GZB_STAGE_ALL = 2 };
+int   gzb_stage_upload (gzb_engine *e, void *dst_device, const void *src_host, uint64_t bytes);
+int   gzb_stage_fetch  (gzb_engine *e, void *dst_host, const void *src_device, uint64_t bytes);
+int   gzb_stage_wait   (gzb_engine *e, int which);
 uint64_t gzb_kernel_launches (gzb_engine *e);                     /* kernels launched by this engine so far */
 /* Device-time of the dominant chain kernels of the LAST batch call, ms (CUDA events on the engine's stream) */
 float gzb_last_chain_ms (gzb_engine *e);
@@ -107,6 +115,15 @@ int gzb_compress_sections_packed (gzb_engine *e, gzb_section *secs, uint32_t n, 
 /* n device-to-device copies in one launch (compacting the streams a complex codec produced into right-sized buffers) */
 typedef struct { const void *src; void *dst; uint64_t len; } gzb_copy;
 int gzb_copy_batch (gzb_engine *e, const gzb_copy *copies, uint32_t n);
+
+/* ---------------------------------------------------------------- Adler-32 of buffers that are in HBM
+ * adler32 (1, data, len) of n buffers in one call: the z_digest of every section body (src/compressor.c:151,161 — the reference
+ * computes it on the compute thread right after compressing; here the bodies are still in the packed device buffer of
+ * gzb_compress_sections_packed), the --verify-codec digest of the uncompressed data (:72-74), or a VBlock's reconstructed text
+ * (src/digest.c:62).  `adler` is the value adler32 () returns (the caller applies BGEN32).  Device pointers with
+ * GZB_DEVICE_PTRS / GZB_IN_DEVICE, else host memory (uploaded first). */
+typedef struct { const void *data; uint64_t len; uint32_t adler; uint32_t reserved; } gzb_digest_item;
+int gzb_adler32_batch (gzb_engine *e, gzb_digest_item *items, uint32_t n, uint32_t flags);
 
 /* ---------------------------------------------------------------- ACGT / XCGT (src/codec_acgt.c)
  * pack:   codec_acgt_compress up to the sub-codec call (:64-163): bases → LE 2-bit words + exception stream.

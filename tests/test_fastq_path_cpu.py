@@ -70,35 +70,34 @@ def test_fastq_path_host_driver(backend, n_engines, sub_batch):
 
 
 @pytest.mark.parametrize("backend", ["mock", "simt"])
-def test_host_stream_groups(backend):
-    """HostStream: VBlock groups with their own engines and host threads, several steps back to back, the PCIe gate taken in
-    turns — same sections as the single-group path, bit-exact round trip"""
-    from genozip_b200.fastq_path import FastqCodecPath, HostStream, synth_vblocks, STREAMS
+def test_pipelined_host(backend):
+    """PipelinedHost: several steps back to back, the next step's text staged while the current step's kernels run, results fetched
+    behind — same sections as the synchronous path, bit-exact round trip into the host output buffers"""
+    from genozip_b200.fastq_path import FastqCodecPath, PipelinedHost, synth_vblocks, STREAMS
     if backend == "simt":
         from simt_lib import simt_engine_class
         Eng = simt_engine_class()
     else:
         Eng = MockEngine
-    V, n_reads, read_len = 5, 300, 150
+    V, n_reads, read_len = 3, 300, 150
     data = synth_vblocks(V, n_reads, read_len, 11, torch.device("cpu"))
     ref_path = FastqCodecPath(Eng(0), V, n_reads, read_len, n_engines=1)
     codec = ref_path.assign_codecs(data)
     meta = ref_path.zip_device(data)
-    hs = HostStream(Eng(0), V, n_reads, read_len, codec, groups=2, engine_factory=lambda: Eng(0))
-    assert [b - a for a, b in hs.bounds] == [2, 3]
-    hs.alloc(data)
-    h2d, d2h = hs.zip_steps(K=2)
-    for p, (a, b) in zip(hs.paths, hs.bounds):
-        m = hs.metas[hs.paths.index(p)]
-        for v in range(a, b):
-            for s in STREAMS:
-                assert m[v - a]["len"][s] == meta[v]["len"][s]
-                if meta[v]["len"][s]:
-                    assert np.array_equal(p.section_bytes(m, v - a, s, host=True), ref_path.section_bytes(meta, v, s)), f"group section {s} of VB {v}"
-    for p in hs.paths:
-        p.h["seq_out"].zero_(); p.h["qual_out"].zero_(); p.scrub_intermediates()
-    h2d_p, d2h_p = hs.piz_steps(K=2)
-    assert hs.check()
+    path = FastqCodecPath(Eng(0), V, n_reads, read_len, n_engines=2)
+    path.codec = dict(codec)
+    path.alloc_piz(path.zip_device(data))                                  # (sizes the working buffers, like bench.py's device-resident leg before it)
+    ph = PipelinedHost(path, {k: v.clone() for k, v in data.items()})
+    h2d, d2h = ph.zip_steps(K=3)
+    for v in range(V):
+        for s in STREAMS:
+            assert ph.meta[v]["len"][s] == meta[v]["len"][s]
+            if meta[v]["len"][s]:
+                assert np.array_equal(path.section_bytes(ph.meta, v, s), ref_path.section_bytes(meta, v, s)), f"section {s} of VB {v}"
     n = n_reads * read_len
-    assert h2d >= 2 * V * n and d2h_p >= 2 * V * n
-    hs.close(); ref_path.close()
+    assert h2d >= 2 * V * n and 0 < d2h < V * n
+    path.scrub_intermediates(); path.packed_d.zero_(); path.comp_arena.zero_(); path.comp_arena2.zero_(); ph.scrub()
+    h2d_p, d2h_p = ph.piz_steps(K=3)
+    assert ph.check()
+    assert d2h_p >= 2 * V * n and 0 < h2d_p < V * n
+    path.close(); ref_path.close()

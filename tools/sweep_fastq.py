@@ -20,6 +20,8 @@ def main():
     ap.add_argument("--reads", type=int, default=92000)
     ap.add_argument("--read-len", type=int, default=150)
     ap.add_argument("--cfg", action="append", default=[])
+    ap.add_argument("--streams", default="", help="comma-separated stream names: time only the simple-codec sections of these streams (compress + uncompress on one engine), "
+                                                  "e.g. DIVRQUAL = the longest arithmetic chain of every VBlock without the other leaves around it")
     a = ap.parse_args()
     import torch
     from genozip_b200 import Engine
@@ -37,6 +39,9 @@ def main():
     keys = set()
     for cfg in a.cfg:
         keys |= {kv.split("=")[0] for kv in cfg.split(",") if kv}
+    if a.streams:
+        only_streams(a, path, data, meta, keys, txt)
+        return
     for cfg in a.cfg or [""]:
         for k in keys:
             os.environ.pop(k, None)
@@ -64,6 +69,46 @@ def main():
         print(json.dumps({"cfg": cfg, "V": a.vblocks, "zip_ms": round(tz, 1), "piz_ms": round(tp, 1), "value_GBps": round(txt / ((tz + tp) * 1e-3) / 1e9, 2),
                           "zip_kern": {k: round(v / a.steps, 1) for k, v in kz.items()}, "piz_kern": {k: round(v / a.steps, 1) for k, v in kp.items()},
                           "round_trip": ok}), flush=True)
+
+
+def only_streams(a, path, data, meta, keys, txt):
+    import torch
+    import numpy as np
+    from genozip_b200.fastq_path import NAMES, S_IDX, GZB_DEVICE_PTRS
+    names = tuple(a.streams.split(","))
+    eng = path.eng
+    name_rows = {s: path._rows(data[s]) for s in NAMES}
+    inp = path._in_ptrs(meta, name_rows, path.dq_arena.data_ptr())
+    outp = path._in_ptrs(meta, {s: path._rows(path.names_dec_d[s]) for s in NAMES}, path.dq_arena.data_ptr())
+    nsym = int(sum(meta.len[:, S_IDX[s]].sum() for s in names))
+    for cfg in a.cfg or [""]:
+        for k in keys:
+            os.environ.pop(k, None)
+        for kv in cfg.split(","):
+            if kv:
+                k, v = kv.split("="); os.environ[k] = v
+        res = []
+        for i in range(1 + a.steps):
+            torch.cuda.synchronize()
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            with torch.cuda.stream(path.stream):
+                e0.record(path.stream)
+                secs, arr, vv, ss = path._section_array(meta, inp, names)
+                path._compress_packed(eng, secs, arr, vv.size, GZB_DEVICE_PTRS, "comp_probe", False)
+                path._kernel_ms([eng]); dz = dict(path.kernel_ms_detail)
+                e1.record(path.stream)
+                comp_len = arr["out_len"][:vv.size].copy(); comp_ptr = arr["out"][:vv.size].copy()
+                secs2, arr2, vv2, ss2 = path._section_array(meta, inp, names)
+                arr2["in_"][:vv.size] = comp_ptr; arr2["in_len"][:vv.size] = comp_len; arr2["out"][:vv.size] = outp[vv2, ss2]; arr2["out_cap"][:vv.size] = meta.len[vv2, ss2]
+                eng.uncompress_raw(secs2, vv.size, GZB_DEVICE_PTRS)
+                path._kernel_ms([eng]); dp = dict(path.kernel_ms_detail)
+                e2.record(path.stream)
+            torch.cuda.synchronize()
+            if i:
+                res.append((e0.elapsed_time(e1), e1.elapsed_time(e2), dz, dp))
+        tz = sum(r[0] for r in res) / len(res); tp = sum(r[1] for r in res) / len(res)
+        print(json.dumps({"cfg": cfg, "streams": names, "V": a.vblocks, "uncompressed_bytes": nsym, "compress_ms": round(tz, 1), "uncompress_ms": round(tp, 1),
+                          "zip_kern": {k: round(v, 1) for k, v in res[-1][2].items()}, "piz_kern": {k: round(v, 1) for k, v in res[-1][3].items()}}), flush=True)
 
 
 if __name__ == "__main__":
