@@ -16,6 +16,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+ALL_CPUS = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else set()
 METRIC = "fastq_input_GBps_zip_plus_piz"
 UNIT = "GB/s"
 WORKLOAD = "fastq_illumina_150bp_paired_vb32MB (BASELINE configs[1] per-GPU share)"
@@ -214,6 +215,23 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
+def bind_to_gpu_cpus(gpu):
+    """run this rank on the CPUs NVML lists as local to its GPU, so that the pinned host buffers it allocates (first touch) and the
+    threads that feed the copy engines sit on the GPU's NUMA node; returns what was done, for the bench line"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1} & set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} cpus local to gpu {gpu}"
+    except Exception as ex:
+        return f"not bound ({type(ex).__name__})"
+    return "not bound"
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -225,6 +243,7 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_cpus(local)                             # page-locked buffers are then first-touched on the GPU's own NUMA node
     eng = Engine(local)
     from genozip_b200 import GzbError
     V = args.vblocks
@@ -232,8 +251,6 @@ def run_gpu(args):
         free_b, _ = torch.cuda.mem_get_info(dev)
         n = args.reads * args.read_len
         per_vb = 9.3 * n + 14 * args.reads + (6 << 20)          # inputs 2n, 2-bit words n/4, exception stream n, DOMQ streams ~0.4n, outputs 2n, engine workspace ~3.5n
-        if not args.no_e2e:
-            per_vb += 2.2 * n                                   # the pipelined host leg double-buffers the inputs and the outputs (its peak: 4n + 4n instead of 2n + 2n + the 2n of the generator's copy)
         V = int(max(8, min(768, (0.86 * free_b) // per_vb)))     # (measured on B200: 512 -> 17.7, 768 -> 22.2, 819 -> 21.7 GB/s: beyond ~768 the chain kernels are issue-bound)
         if not args.no_e2e:                                     # the host-buffer leg keeps pinned copies of inputs and outputs: ~4.6n per VBlock
             try:
@@ -349,13 +366,13 @@ def run_gpu(args):
         cpu_data = {k: [data[k][v].cpu().numpy() for v in range(n_cpu)] for k in data}
     if not args.no_e2e:
         from genozip_b200.fastq_path import PipelinedHost
-        pin = lambda t: t.cpu().pin_memory()
-        host = {k: pin(v) for k, v in data.items()}
+        host = {k: v.cpu() for k, v in data.items()}
         del data
         torch.cuda.empty_cache()
         path.seq_out_d = path.qual_out_d = path.names_dec_d = path.dec_d = None      # (the pipelined leg brings its own double-buffered outputs)
         torch.cuda.empty_cache()
         ph = PipelinedHost(path, host)
+        del host
         Ke = max(2, args.steps)
         ph.zip_steps(1); ph.scrub(); ph.piz_steps(1)                      # warm-up step (buffers grow to their sizes) + correctness gate
         assert ph.check(), "host round trip failed"
@@ -430,6 +447,10 @@ def run_gpu(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            os.sched_setaffinity(0, ALL_CPUS)                   # the CPU leg gets every host core again
+        except Exception:
+            pass
         cores = os.cpu_count() or 1
         n_vb = min(V, 4 * cores)                                # ~10-30 s of CPU work
         dnp = cpu_data
@@ -452,7 +473,7 @@ def run_gpu(args):
                        "txt_accounting": "input bytes = the FASTQ text the VBlocks represent (45-byte name line, SEQ, '+', QUAL, 4 newlines per read); of the name line, "
                                          "10 B/read of segmented read-name contexts flow through the path (the segmenter is out of scope); the same count in both arms",
                        "excluded": EXCLUDED, "sharding": "VBlocks round-robin by vblock_i, no data-path collective; NCCL all_gather of the section list only",
-                       "engines_per_gpu": len(path.engs), "device_groups": len(path.groups)},
+                       "engines_per_gpu": len(path.engs), "device_groups": len(path.groups), "cpu_binding": numa},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
         }))
     if world > 1:

@@ -137,37 +137,11 @@ extern "C" void gzb_engine_destroy (gzb_engine *e)
     if (e->stream2) cudaStreamDestroy (e->stream2);
     if (e->stream3) cudaStreamDestroy (e->stream3);
     if (e->stream4) cudaStreamDestroy (e->stream4);
+    if (e->stager && e->stager_free) e->stager_free (e->stager);            // (joins the feeder threads before their streams go)
     if (e->stream_copy) { cudaStreamSynchronize (e->stream_copy); cudaStreamDestroy (e->stream_copy); }
     if (e->stream_copy2) { cudaStreamSynchronize (e->stream_copy2); cudaStreamDestroy (e->stream_copy2); }
     if (e->stream) cudaStreamDestroy (e->stream);
     delete e;
-}
-
-// ------------------------------------------------------------------------------------------------ staging (gzb_vb_stage)
-// Asynchronous transfers on the engine's two copy streams (uploads, fetches: the link is full duplex): a host that keeps handing over VBlocks uploads the next batch's text
-// (vb->txt_data) and fetches the previous batch's z_data while the current batch's kernels run — the copy engines are idle during
-// the entropy chains, and the chains do not need the PCIe link.
-extern "C" int gzb_stage_upload (gzb_engine *e, void *dst_device, const void *src_host, uint64_t bytes)
-{
-    if (!e || (bytes && (!dst_device || !src_host))) return GZB_E_BADARG;
-    cudaSetDevice (e->device);
-    if (bytes) CK (cudaMemcpyAsync (dst_device, src_host, bytes, cudaMemcpyHostToDevice, e->stream_copy));
-    return GZB_OK;
-}
-extern "C" int gzb_stage_fetch (gzb_engine *e, void *dst_host, const void *src_device, uint64_t bytes)
-{
-    if (!e || (bytes && (!dst_host || !src_device))) return GZB_E_BADARG;
-    cudaSetDevice (e->device);
-    if (bytes) CK (cudaMemcpyAsync (dst_host, src_device, bytes, cudaMemcpyDeviceToHost, e->stream_copy2));
-    return GZB_OK;
-}
-extern "C" int gzb_stage_wait (gzb_engine *e, int which)
-{
-    if (!e) return GZB_E_BADARG;
-    cudaSetDevice (e->device);
-    if (which != GZB_STAGE_FETCHES) CK (cudaStreamSynchronize (e->stream_copy));
-    if (which != GZB_STAGE_UPLOADS) CK (cudaStreamSynchronize (e->stream_copy2));
-    return GZB_OK;
 }
 
 // give the grow-only workspace and staging back (a batch of another shape follows, or other engines need the memory)

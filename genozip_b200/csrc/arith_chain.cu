@@ -55,8 +55,9 @@ __global__ void __launch_bounds__(128) k_arith_encode_t (const EncLeaf *leaves, 
 }
 
 // CTAs per SM of the persistent chain kernels and the other switches of the chain phase, from the environment (A/B runs):
-//   GZB_AR_CTAS     general arithmetic kernel (order 1 / RLE leaves), 4 warps per CTA       default 4
-//   GZB_AR0_CTAS    order-0 arithmetic kernel                                               default 4
+//   GZB_AR_CTAS     general arithmetic kernel (order 1 / RLE leaves), 4 warps per CTA       default 2
+//                   (2 / 4 / 8 / 16 per SM measure the same within run-to-run noise; 2 leaves registers for the kernels beside them)
+//   GZB_AR0_CTAS    order-0 arithmetic kernel                                               default 2
 //   GZB_AR_RUN4     the decoder tries four run steps at once                                default 1
 //   GZB_AR_SPLIT_STREAM  the split encoder runs on its own stream beside the general kernel default 1
 //   GZB_AR_LONG_MIN order-1 leaves of at least this many symbols are decoded by k_arith_decode_long (off = none)   default off
@@ -72,8 +73,8 @@ const ChainTune &chain_tune ()                                               // 
         const int x = atoi (v);
         return x < lo ? lo : x > hi ? hi : x;
     };
-    c.arith_ctas = geti ("GZB_AR_CTAS", 4, 1, 16);
-    c.arith_o0_ctas = geti ("GZB_AR0_CTAS", 4, 1, 16);
+    c.arith_ctas = geti ("GZB_AR_CTAS", 2, 1, 16);
+    c.arith_o0_ctas = geti ("GZB_AR0_CTAS", 2, 1, 16);
     c.run4 = geti ("GZB_AR_RUN4", 1, 0, 1);
     c.split_stream = geti ("GZB_AR_SPLIT_STREAM", 1, 0, 1);
     c.long_ent = geti ("GZB_AR_LONG_ENT", 16, 16, 32) >= 32 ? 32 : 16;

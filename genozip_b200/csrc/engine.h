@@ -21,6 +21,9 @@ struct gzb_engine {
     void        *dq_session = nullptr;
     void       (*dq_free)(void *) = nullptr;
     uint32_t     dq_n_vbs = 0; bool dq_devptr = false;
+    // staging (stage.cu): the two feeder threads behind gzb_stage_upload / gzb_stage_fetch, made on first use
+    void        *stager = nullptr;
+    void       (*stager_free)(void *) = nullptr;
 };
 
 int engine_reserve (gzb_engine *e, size_t ws_bytes, size_t pin_bytes);

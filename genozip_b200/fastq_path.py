@@ -629,17 +629,27 @@ class PipelinedHost:
     input buffers (zip) and two output buffers (piz) on the device are all it takes.  Host buffers are page-locked."""
 
     def __init__(self, path, data_host):
-        self.path, self.H = path, data_host                                  # data_host: pinned [V, ...] tensors seq, qual, Q_*
+        """data_host: host tensors [V, ...] seq, qual, Q_* (copied into page-locked buffers; the read-name buffers get the 16 bytes of
+        slack per row that alloc_piz gives their decoded counterparts, so that one pair of device buffers serves as zip's input
+        slots and as piz's output slots)"""
+        self.path = path
         self.eng, self.L = path.eng, path.L
         dev = path.dev
-        self.in_slots = [{k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in data_host.items()} for _ in range(2)]
-        self.out_slots = None
+        self.width = {k: v.shape[1] for k, v in data_host.items()}
+        self.H = {}
+        for k, v in data_host.items():
+            t = _pin(torch.zeros((v.shape[0], v.shape[1] + (16 if k in NAMES else 0)), dtype=torch.uint8))
+            t[:, :v.shape[1]] = v
+            self.H[k] = t
+        self.slots = [{k: torch.empty(v.shape, dtype=torch.uint8, device=dev) for k, v in self.H.items()} for _ in range(2)]
         self.h_packed = _pin(torch.empty((path.V, path.packed_len + 32), dtype=torch.uint8))
         self.h_comp = {}
-        pad = lambda k, v: (v.shape[0], v.shape[1] + (16 if k in NAMES else 0))   # (the read-name buffers carry the 16 bytes of slack alloc_piz gives them)
-        self.out_shape = {k: pad(k, v) for k, v in data_host.items()}
-        self.h_out = {k: _pin(torch.empty(self.out_shape[k], dtype=torch.uint8)) for k in data_host}
+        self.h_out = {k: _pin(torch.empty(v.shape, dtype=torch.uint8)) for k, v in self.H.items()}
         self.meta = None
+        self.zbuf = self.pbuf = None                                          # double-buffered outputs of zip / 2-bit-word inputs of piz
+
+    def _inputs(self, slot):
+        return {k: t[:, :self.width[k]] for k, t in slot.items()}
 
     def _up(self, dst, src, nbytes=None):
         if self.L.gzb_stage_upload(self.eng.h, dst.data_ptr(), src.data_ptr(), dst.numel() * dst.element_size() if nbytes is None else nbytes):
@@ -654,19 +664,27 @@ class PipelinedHost:
             raise GzbError(f"gzb_stage_wait: {self.eng._err()}")
 
     def zip_steps(self, K=1):
-        """K zip passes over the host buffers, back to back; returns (h2d_bytes, d2h_bytes) of ONE step"""
+        """K zip passes over the host buffers, back to back; returns (h2d_bytes, d2h_bytes) of ONE step.  Step k's 2-bit words and packed
+        sections are fetched under step k+1's kernels (two sets of output buffers on the device)."""
         p = self.path
+        if self.zbuf is None:
+            self.zbuf = [dict(packed_d=p.packed_d, comp_arena=p.comp_arena, comp_arena2=p.comp_arena2),
+                         dict(packed_d=torch.empty_like(p.packed_d), comp_arena=None, comp_arena2=None)]
         for k_, t in self.H.items():
-            self._up(self.in_slots[0][k_], t)
+            self._up(self.slots[0][k_], t)
         h2d = sum(t.numel() for t in self.H.values())
         d2h = 0
         meta = None
         for k in range(K):
-            self._wait(ALL)                                                  # step k's text is on the device, step k-1's sections are on the host
+            self._wait(UPLOADS)                                              # step k's text is on the device
             if k + 1 < K:
                 for k_, t in self.H.items():
-                    self._up(self.in_slots[(k + 1) & 1][k_], t)               # crosses PCIe under this step's kernels
-            meta = p.zip_device(self.in_slots[k & 1])
+                    self._up(self.slots[(k + 1) & 1][k_], t)                  # crosses PCIe under this step's kernels
+            b = self.zbuf[k & 1]
+            p.packed_d, p.comp_arena, p.comp_arena2 = b["packed_d"], b["comp_arena"], b["comp_arena2"]
+            meta = p.zip_device(self._inputs(self.slots[k & 1]))
+            b["comp_arena"], b["comp_arena2"] = p.comp_arena, p.comp_arena2  # (made or grown by the call)
+            self._wait(FETCHES)                                              # step k-1's results reached the host under this step's kernels
             self._down(self.h_packed, p.packed_d)
             d2h = self.h_packed.numel()
             for a in ("comp_arena", "comp_arena2"):
@@ -677,13 +695,11 @@ class PipelinedHost:
                     self._down(self.h_comp[a], getattr(p, a), used)
                     d2h += used
         self._wait(ALL)
-        self.meta = meta
+        self.meta = meta                                                     # (its section addresses are inside the buffers the path is left with)
         return h2d, d2h
 
-    def _upload_sections(self):
-        p = self.path
-        self._up(p.packed_d, self.h_packed)
-        n = self.h_packed.numel()
+    def _upload_comp(self):
+        p, n = self.path, 0
         for a in ("comp_arena", "comp_arena2"):
             used = p.comp_used.get(a, 0)
             if used:
@@ -691,19 +707,25 @@ class PipelinedHost:
         return n
 
     def piz_steps(self, K=1):
-        """K piz passes: the sections and 2-bit words go up, SEQ / QUAL / the read-name contexts come back into the host output buffers"""
+        """K piz passes: the sections and 2-bit words go up, SEQ / QUAL / the read-name contexts come back into the host output buffers.
+        Step k+1's 2-bit words go up, and step k-1's text comes back, under step k's kernels."""
         p, meta = self.path, self.meta
-        if self.out_slots is None:
-            self.out_slots = [{k: torch.empty(self.out_shape[k], dtype=torch.uint8, device=p.dev) for k in self.H} for _ in range(2)]
-        h2d = self._upload_sections()
+        if self.pbuf is None:
+            other = [b["packed_d"] for b in (self.zbuf or []) if b["packed_d"] is not p.packed_d]
+            self.pbuf = [p.packed_d, other[0] if other else torch.empty_like(p.packed_d)]
+        self._up(self.pbuf[0], self.h_packed)
+        h2d = self.h_packed.numel() + self._upload_comp()
         d2h = 0
         for k in range(K):
-            self._wait(UPLOADS)                                              # step k's sections are on the device
-            outs = self.out_slots[k & 1]
+            self._wait(UPLOADS)                                              # step k's sections and 2-bit words are on the device
+            if k + 1 < K:
+                self._up(self.pbuf[(k + 1) & 1], self.h_packed)              # crosses PCIe under this step's chains
+            outs = self.slots[k & 1]
+            p.packed_d = self.pbuf[k & 1]
             p.piz_device(meta, outs)
             self._wait(FETCHES)                                              # step k-1's text reached the host under this step's chains
             if k + 1 < K:
-                self._upload_sections()                                      # (the kernels of step k are done with the section buffers)
+                self._upload_comp()                                          # (the kernels of step k are done with the section buffers; a few hundred MB)
             for k_, t in outs.items():
                 self._down(self.h_out[k_], t)                                 # crosses PCIe under the next step's chains
             d2h = sum(t.numel() for t in outs.values())
@@ -711,7 +733,7 @@ class PipelinedHost:
         return h2d, d2h
 
     def check(self):
-        return all(torch.equal(self.h_out[k][:, :self.H[k].shape[1]], self.H[k]) for k in self.H)
+        return all(torch.equal(self.h_out[k][:, :w], self.H[k][:, :w]) for k, w in self.width.items())
 
     def scrub(self):
         """empty the host output buffers (a round-trip check then sees what piz_steps produced)"""
