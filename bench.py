@@ -252,10 +252,10 @@ def run_gpu(args):
         n = args.reads * args.read_len
         per_vb = 9.3 * n + 14 * args.reads + (6 << 20)          # inputs 2n, 2-bit words n/4, exception stream n, DOMQ streams ~0.4n, outputs 2n, engine workspace ~3.5n
         V = int(max(8, min(768, (0.86 * free_b) // per_vb)))     # (measured on B200: 512 -> 17.7, 768 -> 22.2, 819 -> 21.7 GB/s: beyond ~768 the chain kernels are issue-bound)
-        if not args.no_e2e:                                     # the host-buffer leg keeps pinned copies of inputs and outputs: ~4.6n per VBlock
+        if not args.no_e2e:                                     # the host-buffer leg keeps page-locked inputs and outputs (4.3n per VBlock) + 2n while it makes them; every rank does
             try:
                 import psutil
-                V = int(max(8, min(V, (0.45 * psutil.virtual_memory().available) // (4.6 * n))))
+                V = int(max(8, min(V, (0.45 * psutil.virtual_memory().available / world) // (6.5 * n))))
             except Exception:
                 pass
     while True:                                                  # a batch that does not fit is halved (all ranks agree on the size)
