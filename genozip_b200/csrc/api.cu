@@ -63,7 +63,7 @@ static bool codec_info (int codec, uint8_t *coder, uint8_t *order)
 extern "C" uint32_t gzb_est_size (int codec, uint64_t n)
 {
     uint8_t coder, order;
-    if (!codec_info (codec, &coder, &order)) return 0;
+    if (!codec_info (codec, &coder, &order) || n > 0xffffffffull) return 0;  // (a section is at most 4 GB - 1: src/sections.h data_uncompressed_len is 32 bits)
     return 1024 + (coder == CODER_RANS ? rans_bound ((uint32_t)n, order) : arith_bound ((uint32_t)n, order));
 }
 
@@ -296,7 +296,7 @@ static int compress_impl (gzb_engine *e, gzb_section *secs, uint32_t n, uint32_t
         memset (&S, 0, sizeof S);
         if (pk) s.out_cap = gzb_est_size (s.codec, s.in_len);                 // packed: the buffer as a whole has a capacity, a section has none
         S.n = s.in_len; S.coder = coder; S.order = order; S.out_cap = s.out_cap;
-        S.soft_fail = s.out_cap < gzb_est_size (s.codec, s.in_len);           // the reference returns NULL → false under soft_fail
+        S.soft_fail = s.out_cap < gzb_est_size (s.codec, s.in_len) - 1024;    // the reference returns NULL → false under soft_fail when *out_size < the bound (rANS_static4x16pr.c:1158); est_size is bound + 1 KB
         S.stripe = (order & F_STRIPE) && S.n > 20;
         S.first_leaf = (uint32_t)hl.size ();
         if (S.soft_fail) { S.n_leaves = 0; continue; }
@@ -588,7 +588,9 @@ extern "C" int gzb_uncompress_sections (gzb_engine *e, gzb_section *secs, uint32
         gzb_section &s = secs[i];
         uint8_t coder, order;
         // the reference asserts on zero lengths (codec_htscodecs.c:103-104, 120-121)
-        if (!codec_info (s.codec, &coder, &order) || !s.in || !s.out || !s.in_len || !s.out_cap) { s.status = GZB_E_BADARG; e->err = "bad section"; return GZB_E_BADARG; }
+        if (!codec_info (s.codec, &coder, &order) || !s.in || !s.out || !s.in_len || !s.out_cap || s.out_cap >= 0x7fffffffu) {   // (the reference refuses out_sz >= INT_MAX)
+            s.status = GZB_E_BADARG; e->err = "bad section"; return GZB_E_BADARG;
+        }
         DecSection &S = hs[i]; memset (&S, 0, sizeof S);
         S.in_len = s.in_len; S.n = s.out_cap; S.coder = coder;
         if (!in_dev (i)) in_total += (S.in_len + 15) & ~15ull;
