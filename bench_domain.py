@@ -445,8 +445,9 @@ def run_gpu(args, ClockSampler):
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
         ent = tj.get(cls.dom_kernel[dom])
-        if ent and ent.get("vblocks") == V:
-            traffic = ent["bytes_per_launch"]
+        if ent:                                                 # the committed ncu capture, scaled to this launch's VBlocks (PBWT: same matrix size; LONGR: per base)
+            scale = V / ent["vblocks"] * (args.lr_bases / ent.get("bases_per_vblock", args.lr_bases) if args.workload == "longread" else 1.0)
+            traffic = int(ent["bytes_per_launch"] * scale)
     except Exception:
         pass
     roof = {"bound": "hbm", "kernel": cls.dom_kernel[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

@@ -42,6 +42,11 @@ namespace {
 
 constexpr uint32_t NCTX = 1u << 21, NCHAN = 1u << 16, NQ9 = 1u << 9;
 constexpr uint32_t FULL = 0xffffffffu;
+// k_longr_decode: the idle lanes ask L2 for the table words of the contexts the step after next may land in.  Measured on B200
+// (1 184 VBlocks of 2 M bases): piz 2.60 GB/s without, 2.34 GB/s with the hints, and 2.8 KB of DRAM reads per base (ncu,
+// profiles/r02_pbwt_longr.md: 412 GB for 148 M bases) — the tables of a thousand VBlocks are 9.5 GB, a hinted word is evicted
+// before the walk gets to it.  Off.
+constexpr bool LR_L2_HINTS = false;
 
 struct LrVb {
     const uint8_t *txt; const uint64_t *seq_off, *qual_off; const uint32_t *len; const uint8_t *is_rev;
@@ -348,7 +353,7 @@ __global__ void __launch_bounds__(32) k_longr_decode (const LrVb *vbs)
             const uint32_t Bb = __shfl_sync (FULL, B, 0);
             missing = e >= 3 && qb == 255;                                  // 255 + '!' == ' ': the line has no quality (:278)
             if (missing) break;                                             // after the state update, like RECON_ONE_QUAL
-            if (e + 1 < L + 3) {
+            if (LR_L2_HINTS && e + 1 < L + 3) {
                 const uint32_t b1 = e + 1 < L ? lu[seq[rev ? L - 2 - e : e + 1]] : 0;
                 const int32_t cq = min (93, max (0, qb - 15 + lane));
                 prefetch_l2 (st + ((((Bb << 2) | b1) & 0xfffu) | (lr_difq (cq, qb) << 12) | ((uint32_t)(v2b[cq] & 0x1f) << 16)));

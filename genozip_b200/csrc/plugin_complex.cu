@@ -288,6 +288,78 @@ extern "C" void gzb_codec_domq_reconstruct (VBlockP vb, Codec codec, ContextP ct
     if (++R->next + 1 == R->off.size ()) { delete R; *slot = nullptr; }
 }
 
+// ================================================================ NORMQ (src/codec_normq.c)
+namespace { struct NormqState { Codec sub = CODEC_NONE_; }; }
+
+extern "C" GZB_COMPRESS (gzb_codec_normq_compress)
+{
+    NEED (codec_state, name); NEED (local_alloc, name); NEED (local_set_len, name); NEED (local_data, name); NEED (assign_sub_codec, name); NEED (sub_est_size, name); NEED (header_set, name);
+    if (uncompressed || !get_line_cb) plugin_abort ("normq", name, "only callback option is supported");       // :33
+    void **slot = g_host2.codec_state (vb, ctx);
+    NormqState *S = (NormqState *)*slot;
+    if (soft_fail) {                                                         // first entry (:39: a second entry, after soft-failing, continues at the sub-codec)
+        Timer tm { vb, 5 };
+        Lines Q = gather_lines (vb, ctx, get_line_cb, name);
+        const uint32_t n_lines = (uint32_t)Q.len.size ();
+        gzb_normq_vb v; memset (&v, 0, sizeof v);
+        v.txt = Q.base ? Q.base : ""; v.txt_len = Q.span; v.line_off = Q.off.data (); v.line_len = Q.len.data (); v.is_rev = Q.rev.data (); v.n_lines = n_lines;
+        v.local = g_host2.local_alloc (vb, ctx, 0, Q.total + 16); v.local_cap = Q.total + 16;                   // buf_alloc_exact (:45)
+        {
+            EngineLease E (vb, name);
+            if (gzb_normq_gather (E.e, &v, 1, 0) != GZB_OK) plugin_abort ("gzb_normq_gather", name, gzb_last_error (E.e));
+        }
+        g_host2.local_set_len (ctx, 0, v.local_len);
+        if (g_host2.add_lines) g_host2.add_lines (3, n_lines);                                                   // z_file->normq_lines (:41-42)
+        delete S; S = new NormqState (); *slot = S;
+        S->sub = g_host2.assign_sub_codec (vb, ctx, 0);                                                          // :64-66
+        g_host2.header_set (header, GZB_HDR_SUB_CODEC, S->sub);
+    }
+    else if (!S) plugin_abort ("normq", name, "second entry without a first one");
+    uint64_t qlen = 0;
+    const char *qual = g_host2.local_data (ctx, 0, &qlen);
+    *uncompressed_len = (uint32_t)qlen;                                                                          // :70
+    if (*compressed_len < g_host2.sub_est_size (S->sub, qlen)) {                                                 // :73-77
+        if (soft_fail) return false;
+        plugin_abort ("normq", name, "compressed buffer too small and soft_fail is off");
+    }
+    const Codec sub = S->sub;
+    delete S; *slot = nullptr;
+    return sub_compress (sub, vb, ctx, header, qual, uncompressed_len, compressed, compressed_len, HARD_FAIL, name);   // :81
+}
+
+extern "C" void gzb_codec_normq_reconstruct (VBlockP vb, Codec codec, ContextP ctx, uint32_t len, bool reconstruct)
+{
+    (void)codec;
+    const char *name = "QUAL";
+    NEED (codec_state, name); NEED (recon_line_lens, name); NEED (recon_seq_table, name); NEED (local_data, name); NEED (recon_at, name); NEED (recon_advance, name);
+    Timer tm { vb, 5 };
+    void **slot = g_host2.codec_state (vb, ctx);
+    ReconStage *R = (ReconStage *)*slot;
+    if (!R) {                                                                // first line of the VBlock: all of them at once
+        R = new ReconStage ();
+        uint32_t n_lines = 0;
+        const uint32_t *lens = g_host2.recon_line_lens (vb, ctx, &n_lines);
+        const char *txt = nullptr; uint64_t txt_len = 0; const uint64_t *seq_off = nullptr; const uint8_t *is_rev = nullptr;
+        g_host2.recon_seq_table (vb, ctx, &txt, &txt_len, &seq_off, &is_rev);                                    // (only the strands are used: last_flags.rev_comp of every line, :97)
+        R->off.resize ((size_t)n_lines + 1); R->off[0] = 0;
+        for (uint32_t i = 0; i < n_lines; i++) R->off[i + 1] = R->off[i] + lens[i];
+        R->out.resize (R->off[n_lines] + 16); R->missing.assign ((size_t)n_lines + 1, 0);
+        gzb_normq_vb v; memset (&v, 0, sizeof v);
+        uint64_t l = 0;
+        v.local = g_host2.local_data (ctx, 0, &l); v.local_len = l;
+        v.line_len = lens; v.is_rev = is_rev; v.n_lines = n_lines;
+        v.out = R->out.data (); v.out_cap = R->off[n_lines] + 16; v.missing = R->missing.data ();
+        EngineLease E (vb, name);
+        if (gzb_normq_reconstruct (E.e, &v, 1, 0) != GZB_OK) plugin_abort ("gzb_normq_reconstruct", name, gzb_last_error (E.e));
+        *slot = R;
+    }
+    while (R->next + 1 < R->off.size () && R->off[R->next + 1] == R->off[R->next] && len) R->next++;
+    if (R->next + 1 >= R->off.size () || R->off[R->next + 1] - R->off[R->next] != len) plugin_abort ("normq reconstruct", name, "len differs from the line table");
+    if (R->missing[R->next]) { NEED (missing_quality, name); g_host2.missing_quality (vb, reconstruct); }       // :91-94
+    else if (reconstruct) { memcpy (g_host2.recon_at (vb), R->out.data () + R->off[R->next], len); g_host2.recon_advance (vb, (int32_t)len); }   // :96-101
+    if (++R->next + 1 == R->off.size ()) { delete R; *slot = nullptr; }
+}
+
 // ================================================================ PBWT
 extern "C" GZB_COMPRESS (gzb_codec_pbwt_compress)
 {

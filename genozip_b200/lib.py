@@ -57,6 +57,12 @@ class Copy(C.Structure):            # gzb_copy
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("len", C.c_uint64)]
 
 
+class NormqVb(C.Structure):         # gzb_normq_vb
+    _fields_ = [("txt", C.c_void_p), ("txt_len", C.c_uint64), ("line_off", C.c_void_p), ("line_len", C.c_void_p), ("is_rev", C.c_void_p),
+                ("n_lines", C.c_uint32), ("status", C.c_int32), ("local", C.c_void_p), ("local_cap", C.c_uint64), ("local_len", C.c_uint64),
+                ("out", C.c_void_p), ("out_cap", C.c_uint64), ("missing", C.c_void_p)]
+
+
 class DigestItem(C.Structure):      # gzb_digest_item
     _fields_ = [("data", C.c_void_p), ("len", C.c_uint64), ("adler", C.c_uint32), ("reserved", C.c_uint32)]
 
@@ -138,6 +144,8 @@ def load():
     for f in ("gzb_stage_upload", "gzb_stage_fetch"):
         getattr(L, f).restype = C.c_int; getattr(L, f).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     L.gzb_stage_wait.restype = C.c_int; L.gzb_stage_wait.argtypes = [C.c_void_p, C.c_int]
+    for f in ("gzb_normq_gather", "gzb_normq_reconstruct"):
+        getattr(L, f).restype = C.c_int; getattr(L, f).argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
     L.gzb_adler32_batch.restype = C.c_int
     L.gzb_adler32_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
     L.gzb_pbwt_decode.restype = C.c_int
@@ -276,6 +284,41 @@ class Engine:
         rc = self.L.gzb_uncompress_sections(self.h, secs, n, flags)
         if rc != 0:
             raise GzbError(f"gzb_uncompress_sections failed ({rc}): {self._err()}")
+
+    # ---- NORMQ (host buffers) ----
+    def normq_gather(self, vbs):
+        """vbs: list of (txt, line_off, line_len, is_rev or None) -> list of QUAL.local arrays (codec_normq_compress before its sub-codec)"""
+        arr = (NormqVb * max(1, len(vbs)))(); keep = []
+        for i, (txt, off, ln, rev) in enumerate(vbs):
+            txt = np.ascontiguousarray(txt, np.uint8); off = np.ascontiguousarray(off, np.uint64); ln = np.ascontiguousarray(ln, np.uint32)
+            rv = None if rev is None else np.ascontiguousarray(rev, np.uint8)
+            out = np.zeros(int(ln.sum()) + 16, np.uint8)
+            keep.append((txt, off, ln, rv, out))
+            a = arr[i]
+            a.txt = txt.ctypes.data if txt.size else None; a.txt_len = txt.size; a.line_off = off.ctypes.data if off.size else None
+            a.line_len = ln.ctypes.data if ln.size else None; a.is_rev = None if rv is None or not rv.size else rv.ctypes.data; a.n_lines = ln.size
+            a.local = out.ctypes.data; a.local_cap = out.size
+        rc = self.L.gzb_normq_gather(self.h, arr, len(vbs), 0)
+        if rc != 0:
+            raise GzbError(f"gzb_normq_gather failed ({rc}): {self._err()}")
+        return [k[4][:int(arr[i].local_len)].copy() for i, k in enumerate(keep)]
+
+    def normq_reconstruct(self, vbs):
+        """vbs: list of (local, line_len, is_rev or None) -> list of (out with line_len[i] bytes per line, missing flags); raises on a stream that does not fit"""
+        arr = (NormqVb * max(1, len(vbs)))(); keep = []
+        for i, (local, ln, rev) in enumerate(vbs):
+            local = np.ascontiguousarray(local, np.uint8); ln = np.ascontiguousarray(ln, np.uint32)
+            rv = None if rev is None else np.ascontiguousarray(rev, np.uint8)
+            out = np.zeros(int(ln.sum()) + 16, np.uint8); miss = np.zeros(ln.size + 1, np.uint8)
+            keep.append((local, ln, rv, out, miss))
+            a = arr[i]
+            a.local = local.ctypes.data if local.size else None; a.local_len = local.size; a.line_len = ln.ctypes.data if ln.size else None
+            a.is_rev = None if rv is None or not rv.size else rv.ctypes.data; a.n_lines = ln.size
+            a.out = out.ctypes.data; a.out_cap = out.size; a.missing = miss.ctypes.data
+        rc = self.L.gzb_normq_reconstruct(self.h, arr, len(vbs), 0)
+        if rc != 0:
+            raise GzbError(f"gzb_normq_reconstruct failed ({rc}): {self._err()}")
+        return [(k[3][:int(k[1].sum())].copy(), k[4][:k[1].size].copy()) for k in keep]
 
     # ---- Adler-32 (host buffers; device pointers through adler32_ptrs) ----
     def adler32(self, bufs):

@@ -199,6 +199,29 @@ typedef struct {
 } gzb_domq_piz_vb;
 int gzb_domq_reconstruct (gzb_engine *e, gzb_domq_piz_vb *vbs, uint32_t n_vbs, uint32_t flags);
 
+/* ---------------------------------------------------------------- NORMQ (src/codec_normq.c): the fallback quality codec of SAM / BAM
+ * gather:      codec_normq_compress before its sub-codec (:43-62): the quality strings of a VBlock copied into one buffer
+ *              (QUAL.local), a string reversed where its read is reverse-complemented (is_rev); line_len = what the line callback
+ *              returns (1 for a SAM line without quality: the byte ' ').     in  txt, line_off, line_len, is_rev    out  local, local_len
+ * reconstruct: codec_normq_reconstruct (:85-106) for every line of a VBlock at once: line_len[i] = the `len` of the i-th call
+ *              (the read's seq_len), is_rev[i] = last_flags.rev_comp.  A line whose byte in the stream is ' ' has no quality: it
+ *              consumes that one byte, `missing[i]` is set and the first byte of its slot is the '*' of
+ *              sam_reconstruct_missing_quality (src/sam_qual.c:532).          in  local, local_len, line_len, is_rev    out  out (line_len[i] bytes per line), missing
+ * GZB_E_CORRUPT when the stream does not match the lines.  Device pointers with GZB_DEVICE_PTRS (then local_cap / out_cap bound the work). */
+typedef struct gzb_normq_vb {
+    const void     *txt;        uint64_t txt_len;
+    const uint64_t *line_off;   /* gather */
+    const uint32_t *line_len;
+    const uint8_t  *is_rev;     /* may be NULL */
+    uint32_t        n_lines;
+    int32_t         status;
+    void           *local;      uint64_t local_cap, local_len;
+    void           *out;        uint64_t out_cap;
+    uint8_t        *missing;    /* reconstruct, optional */
+} gzb_normq_vb;
+int gzb_normq_gather      (gzb_engine *e, gzb_normq_vb *vbs, uint32_t n_vbs, uint32_t flags);
+int gzb_normq_reconstruct (gzb_engine *e, gzb_normq_vb *vbs, uint32_t n_vbs, uint32_t flags);
+
 /* ---------------------------------------------------------------- PBWT (src/codec_pbwt.c)
  * encode: codec_pbwt_compress (:244-287): haplotype matrix → RUNS (uint32) + FGRC ({allele:8,count:24}; the last
  *         two words are the 64-bit matrix length, :274-276).  Host-endian words.
@@ -329,8 +352,8 @@ typedef struct {
                                                                                                (ZCTX(values)->value_to_bin in ZIP, from SEC_COUNTS in PIZ, src/codec_longr.c:316-330).  DOMQ reconstruct: the
                                                                                                de-normalisation table from DOMQRUNS' dictionary: byte 0 = number of doms, then [num_doms][num_norm_qs] */
     void     (*pbwt_dims)       (VBlockP vb, ContextP ht_ctx, uint32_t *n_lines, uint32_t *ht_per_line, int set);   /* ht_ctx->HT_n_lines, ->ht_per_line (get; set != 0: store ht_per_line) */
-    void     (*add_lines)       (int which, uint64_t n);                                    /* z_file->domq_lines / longr_lines (src/codec_domq.c:489-492, src/codec_longr.c:181): 0 DOMQ dom, 1 DOMQ diverse, 2 LONGR */
-    void     (*account_time)    (VBlockP vb, int which, uint64_t nanosec);                  /* COPY_TIMER (compressor_domq …), src/profiler.h:18-24: 0 domq 1 acgt 2 xcgt 3 pbwt 4 longr */
+    void     (*add_lines)       (int which, uint64_t n);                                    /* z_file->domq_lines / longr_lines (src/codec_domq.c:489-492, src/codec_longr.c:181): 0 DOMQ dom, 1 DOMQ diverse, 2 LONGR, 3 NORMQ (z_file->normq_lines, src/codec_normq.c:41) */
+    void     (*account_time)    (VBlockP vb, int which, uint64_t nanosec);                  /* COPY_TIMER (compressor_domq …), src/profiler.h:18-24: 0 domq 1 acgt 2 xcgt 3 pbwt 4 longr 5 normq */
     /* ---- PIZ ---- */
     void     (*sub_uncompress)  (Codec c, VBlockP vb, ContextP ctx, uint8_t param, const char *compressed, uint32_t compressed_len,
                                  BufferP uncompressed_buf, uint64_t uncompressed_len, const char *name);               /* codec_args[c].uncompress */
@@ -353,6 +376,7 @@ GZB_COMPRESS (gzb_codec_domq_compress);                            /* src/codec_
 GZB_COMPRESS (gzb_codec_acgt_compress);                            /* src/codec_acgt.c:64-176 */
 GZB_COMPRESS (gzb_codec_pbwt_compress);                            /* src/codec_pbwt.c:244-287 */
 GZB_COMPRESS (gzb_codec_longr_compress);                           /* src/codec_longr.c:161-264 */
+GZB_COMPRESS (gzb_codec_normq_compress);                           /* src/codec_normq.c:31-82 (table row src/codec.h:102) */
 uint32_t gzb_codec_complex_est_size (Codec codec, uint64_t uncompressed_len);    /* src/codec.c codec_complex_est_size */
 uint32_t gzb_codec_longr_est_size   (Codec codec, uint64_t uncompressed_len);    /* src/codec_longr.c:53-56 */
 /* PIZ */
@@ -362,6 +386,7 @@ GZB_UNCOMPRESS (gzb_codec_pbwt_uncompress);                        /* src/codec_
 CodecReconstructFn gzb_codec_domq_reconstruct;                     /* src/codec_domq.c:774-809 */
 CodecReconstructFn gzb_codec_pbwt_reconstruct;                     /* src/codec_pbwt.c:406-449 */
 CodecReconstructFn gzb_codec_longr_reconstruct;                    /* src/codec_longr.c:342-373 */
+CodecReconstructFn gzb_codec_normq_reconstruct;                    /* src/codec_normq.c:85-106; recon_seq_table supplies every line's strand (last_flags.rev_comp) */
 
 /* ---------------------------------------------------------------- combining submission
  * comp_compress calls a codec once per section from every compute thread (src/compressor.c:82-86); one launch per section is

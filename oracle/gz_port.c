@@ -523,3 +523,43 @@ int orc_longr_decode2 (const uint8_t *txt, const uint64_t *seq_off, const uint32
     free (s.avg_sums); free (s.err_sums); free (next);
     return 0;
 }
+
+/* ================================================================ NORMQ (reference src/codec_normq.c)
+ * encode = codec_normq_compress before its sub-codec (:43-62): the lines' quality strings copied into one buffer, reversed where is_rev.
+ * decode = codec_normq_reconstruct (:85-106) line by line: a ' ' at the cursor is a line without quality (one byte consumed, '*' written by
+ * sam_reconstruct_missing_quality, sam_qual.c:532); out gets len[i] bytes per line (the '*' at the start of a missing line's slot), *used = the
+ * stream bytes consumed.  Returns -1 if the stream runs out. */
+uint64_t orc_normq_encode (const uint8_t *txt, const uint64_t *line_off, const uint32_t *line_len, const uint8_t *is_rev, uint32_t n_lines, uint8_t *local)
+{
+    uint64_t next = 0;
+    for (uint32_t li = 0; li < n_lines; li++) {
+        const uint32_t L = line_len[li];
+        if (!L) continue;                                                                 /* :53 */
+        const uint8_t *q = txt + line_off[li];
+        if (is_rev && is_rev[li]) for (uint32_t i = 0; i < L; i++) local[next + i] = q[L - 1 - i];   /* str_reverse :55 */
+        else memcpy (local + next, q, L);
+        next += L;
+    }
+    return next;
+}
+
+int orc_normq_decode (const uint8_t *local, uint64_t local_len, const uint32_t *len, const uint8_t *is_rev, uint32_t n_lines, uint8_t *out, uint8_t *missing, uint64_t *used)
+{
+    uint64_t next = 0;
+    for (uint32_t li = 0; li < n_lines; li++) {
+        const uint32_t L = len[li];
+        if (missing) missing[li] = 0;
+        if (!L) continue;
+        if (next >= local_len) return -1;
+        if (local[next] == ' ') { out[0] = '*'; if (missing) missing[li] = 1; next++; }  /* :91-94 */
+        else {
+            if (next + L > local_len) return -1;
+            if (is_rev && is_rev[li]) for (uint32_t i = 0; i < L; i++) out[i] = local[next + L - 1 - i];   /* :98 */
+            else memcpy (out, local + next, L);
+            next += L;
+        }
+        out += L;
+    }
+    *used = next;
+    return 0;
+}

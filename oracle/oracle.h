@@ -102,4 +102,9 @@ int  orc_longr_decode (const uint8_t *txt, const uint64_t *seq_off, const uint32
 
 #ifdef __cplusplus
 }
+
+/* NORMQ (src/codec_normq.c :43-62, :85-106) */
+uint64_t orc_normq_encode (const uint8_t *txt, const uint64_t *line_off, const uint32_t *line_len, const uint8_t *is_rev, uint32_t n_lines, uint8_t *local);
+int  orc_normq_decode (const uint8_t *local, uint64_t local_len, const uint32_t *len, const uint8_t *is_rev, uint32_t n_lines, uint8_t *out, uint8_t *missing, uint64_t *used);
+
 #endif

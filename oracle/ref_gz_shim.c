@@ -145,7 +145,12 @@ uint32_t base64_decode (STRp(b64_str), STR8c(out)) { memcpy (out, b64_str, b64_s
 void ctx_set_ltype (VBlockP vb, int ltype, ...) {}
 WordIndex ctx_peek_next_snip (VBlockP vb, ContextP ctx, pSTRp (snip)) { *snip = (rom)denorm_snip; *snip_len = denorm_snip_len; return 0; }   // DOMQRUNS' single snip: the de-normalisation table
 // PIZ / consensus-read paths of codec_domq.c that the encoder harness never takes
-void sam_reconstruct_missing_quality (VBlockP vb, ReconType reconstruct) { ABORT0 ("shim: sam_reconstruct_missing_quality"); }
+static bool shim_missing_ok;                                                 // the NORMQ harness reconstructs lines without quality
+void sam_reconstruct_missing_quality (VBlockP vb, ReconType reconstruct)
+{
+    if (!shim_missing_ok) ABORT0 ("shim: sam_reconstruct_missing_quality");
+    if (reconstruct) vb->txt_data.data[vb->txt_data.len++] = '*';             // RECONSTRUCT1 ('*') (sam_qual.c:534-535)
+}
 void sam_xcons_reconstruct_QUAL (VBlockP vb, ContextP ctx, uint32_t qual_len, bool reconstruct) { ABORT0 ("shim: sam_xcons_reconstruct_QUAL"); }
 void sam_xcons_split_qual_line (VBlockP vb, BufferP ql_buf) { ABORT0 ("shim: sam_xcons_split_qual_line"); }
 
@@ -436,6 +441,66 @@ int ref_longr_decode (const uint8_t *txt, const uint64_t *seq_off, const uint32_
     }
     if (vb->txt_data.len != total) return -5;
     memcpy (out, vb->txt_data.data, total);
+    free (vb);
+    return 0;
+}
+
+// ================================================================ NORMQ (the reference's compiled codec_normq.c)
+static const uint8_t *g_rev;
+static COMPRESSOR_CALLBACK (shim_get_line_rev)
+{
+    *line_data = (char *)g_txt + g_off[vb_line_i];
+    *line_data_len = g_len[vb_line_i];
+    if (is_rev) *is_rev = g_rev ? g_rev[vb_line_i] : 0;
+}
+
+// codec_normq_compress on n_lines quality strings: returns what it hands to its sub-codec (QUAL.local after the gather)
+int ref_normq_encode (const uint8_t *txt, uint64_t txt_len, const uint64_t *line_off, const uint32_t *line_len, const uint8_t *is_rev, uint32_t n_lines,
+                      uint8_t *local, uint64_t *local_len)
+{
+    shim_init ();
+    if (setjmp (on_abort)) return -1;
+    VBlockP vb = calloc (1, sizeof (VBlock));
+    vb->vblock_i = 1; vb->lines.len = n_lines;
+    g_txt = (uint8_t *)txt; g_off = line_off; g_len = line_len; g_rev = is_rev;
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n_lines; i++) total += line_len[i];
+    ContextP ctx = CTX (SAM_QUAL);
+    ctx->did_i = SAM_QUAL; strcpy (ctx->tag_name, "QUAL");
+    ctx->local.len = total;                                                 // callback-mode locals carry only their total length
+    SectionHeaderCtx header = {};
+    uint32_t ulen = (uint32_t)total, clen = (uint32_t)total + 1024;
+    char *comp = malloc (clen);
+    cap_out = NULL; cap_len = 0;
+    if (!codec_normq_compress (vb, ctx, (SectionHeaderP)&header, NULL, &ulen, shim_get_line_rev, comp, &clen, true, "QUAL")) return -3;
+    memcpy (local, cap_out, cap_len); *local_len = cap_len;
+    free (comp); buf_destroy_do (&ctx->local, __FUNCLINE); free (vb);
+    return 0;
+}
+
+// codec_normq_reconstruct line by line: out = what lands in txt_data (a line without quality contributes the one character '*')
+int ref_normq_decode (const uint8_t *local, uint64_t local_len, const uint32_t *len, const uint8_t *is_rev, uint32_t n_lines, uint8_t *out, uint64_t *out_len)
+{
+    shim_init_piz ();
+    if (setjmp (on_abort)) { shim_missing_ok = false; return -1; }
+    shim_missing_ok = true;
+    VBlockP vb = calloc (1, sizeof (VBlock));
+    vb->vblock_i = 1; vb->lines.len = n_lines; vb->data_type = DT_SAM;
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n_lines; i++) total += len[i];
+    ContextP c = CTX (SAM_QUAL);
+    c->did_i = SAM_QUAL; c->is_loaded = true;
+    buf_alloc_do (vb, &c->local, local_len + 8, 1, "local", __FUNCLINE);
+    memcpy (c->local.data, local, local_len); c->local.len = local_len;
+    buf_alloc_do (vb, &vb->txt_data, total + 64, 1, "txt_data", __FUNCLINE);
+    for (uint32_t i = 0; i < n_lines; i++) {
+        if (!len[i]) continue;
+        CTX (SAM_FLAG)->last_value.i = (is_rev && is_rev[i]) ? 0x10 : 0;      // last_flags.rev_comp (sam_private.h:531)
+        codec_normq_reconstruct (vb, CODEC_NORMQ, c, len[i], true);
+    }
+    shim_missing_ok = false;
+    *out_len = vb->txt_data.len;
+    memcpy (out, vb->txt_data.data, vb->txt_data.len);
     free (vb);
     return 0;
 }

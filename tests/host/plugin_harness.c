@@ -25,7 +25,7 @@ struct VBlock  {
     char **qual, **seq; uint32_t *qual_len, *seq_len; uint8_t *is_rev;
     const uint32_t *recon_lens; const char *seq_txt; uint64_t seq_txt_len; const uint64_t *seq_off;
     int64_t big_allele;
-    uint64_t lines_counter[3], time_ns[5];
+    uint64_t lines_counter[4], time_ns[6];
     int n_missing;
 };
 
@@ -267,6 +267,38 @@ int harness_domq (const uint8_t *txt, const uint64_t *off, const uint32_t *lens,
     if (vb->txt_out.len != total) return -5;
     memcpy (back, vb->txt_out.data, total);
     free (z); g_vb = NULL; vb->qual_len = NULL; vb_free (vb);
+    return 0;
+}
+
+/* NORMQ (SAM / BAM fallback): compress through comp_compress with the soft-fail retry (zip-side lengths: 1 for a line without quality, the
+ * byte ' '), then one reconstruct call per line with the read's seq_len; strands through the line callback (ZIP) and recon_seq_table (PIZ) */
+int harness_normq (const uint8_t *txt, const uint64_t *off, const uint32_t *zlens, const uint32_t *seq_lens, const uint8_t *is_rev, uint32_t n_lines, int sub_codec,
+                   uint8_t *local, uint64_t *local_len, uint8_t *comp, uint32_t *comp_len, uint8_t *back, uint64_t *back_len, int *n_soft_fails, int *n_missing, uint64_t *normq_lines)
+{
+    harness_init ();
+    if (setjmp (on_abort)) return -1;
+    g_assign = (Codec)sub_codec;
+    VBlockP vb = calloc (1, sizeof *vb); vb->vblock_i = 5; vb->n_lines = n_lines; g_vb = vb;
+    vb->qual = malloc (n_lines * sizeof (char *)); vb->qual_len = (uint32_t *)zlens; vb->is_rev = (uint8_t *)is_rev;
+    uint64_t total = 0, out_total = 0;
+    for (uint32_t i = 0; i < n_lines; i++) { vb->qual[i] = (char *)txt + off[i]; total += zlens[i]; out_total += seq_lens[i]; }
+    struct Context *q = &vb->ctx[0];
+    q->local.len = total;                                  /* callback-mode locals carry only their total length */
+    union SectionHeaderUnion hdr = { { 0 } };
+    uint32_t ulen = (uint32_t)total; char *z = NULL; *n_soft_fails = 0;
+    int rc = comp_compress (gzb_codec_normq_compress, gzb_codec_complex_est_size, 30 /* CODEC_NORMQ */, vb, q, &hdr, NULL, &ulen, cb_qual, 1, &z, comp_len, n_soft_fails);
+    if (rc) return rc;
+    memcpy (comp, z, *comp_len);
+    *local_len = q->local.len; if (q->local.len) memcpy (local, q->local.data, q->local.len);
+    *normq_lines = vb->lines_counter[3];
+    /* PIZ: the sub-codec has put QUAL.local back (here: it never left) */
+    vb->recon_lens = seq_lens; vb->seq_txt = "";           /* (recon_seq_table: only the strands are looked at) */
+    buf_alloc_ (&vb->txt_out, out_total + 64);
+    for (uint32_t i = 0; i < n_lines; i++)
+        if (seq_lens[i]) gzb_codec_normq_reconstruct (vb, 30, q, seq_lens[i], true);
+    *back_len = vb->txt_out.len; memcpy (back, vb->txt_out.data, vb->txt_out.len);
+    *n_missing = vb->n_missing;
+    free (z); g_vb = NULL; vb->qual_len = NULL; vb->is_rev = NULL; vb_free (vb);
     return 0;
 }
 

@@ -257,6 +257,35 @@ class MockLib:
                 _view(c.dst, c.len)[:] = _view(c.src, c.len)
         return 0
 
+    def gzb_normq_gather(self, h, vbs, n, flags):
+        for i in range(n):
+            a = vbs[i]
+            ln = _view(a.line_len, a.n_lines, np.uint32).copy() if a.n_lines else np.zeros(0, np.uint32)
+            off = _view(a.line_off, a.n_lines, np.uint64).copy() if a.n_lines else np.zeros(0, np.uint64)
+            rev = _view(a.is_rev, a.n_lines).copy() if a.is_rev and a.n_lines else None
+            out = orc.normq_encode(_view(a.txt, a.txt_len) if a.txt_len else np.zeros(1, np.uint8), off, ln, rev)
+            if out.size:
+                _view(a.local, out.size)[:] = out
+            a.local_len = out.size; a.status = 0
+        return 0
+
+    def gzb_normq_reconstruct(self, h, vbs, n, flags):
+        rc = 0
+        for i in range(n):
+            a = vbs[i]
+            ln = _view(a.line_len, a.n_lines, np.uint32).copy() if a.n_lines else np.zeros(0, np.uint32)
+            rev = _view(a.is_rev, a.n_lines).copy() if a.is_rev and a.n_lines else None
+            r = orc.normq_decode(_view(a.local, a.local_len).copy() if a.local_len else np.zeros(0, np.uint8), ln, rev)
+            if r is None:
+                a.status = -4; rc = -4; self.err = "NORMQ: the stream does not match the lines"; continue
+            out, miss = r
+            if out.size:
+                _view(a.out, out.size)[:] = out
+            if a.missing and miss.size:
+                _view(a.missing, miss.size)[:] = miss
+            a.status = 0
+        return rc
+
     def gzb_stage_upload(self, h, dst, src, n):
         if n:
             _view(dst, n)[:] = _view(src, n)

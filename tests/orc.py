@@ -389,3 +389,56 @@ def longr_decode(txt, seq_off, lens, is_rev, v2b, values, lens_be):
                                  _ptr(v2b), _ptr(v), _ptr(lens_be), _ptr(out))
     assert rc == 0
     return out[:tot]
+
+
+# ---------------------------------------------------------------- NORMQ (src/codec_normq.c)
+def normq_encode(txt, off, lens, is_rev):
+    """restatement of codec_normq_compress before its sub-codec -> QUAL.local"""
+    L = port()
+    L.orc_normq_encode.restype = C.c_uint64
+    L.orc_normq_encode.argtypes = [C.c_void_p] * 4 + [C.c_uint32, C.c_void_p]
+    txt = np.ascontiguousarray(txt, np.uint8); off = np.ascontiguousarray(off, np.uint64); lens = np.ascontiguousarray(lens, np.uint32)
+    rv = None if is_rev is None else np.ascontiguousarray(is_rev, np.uint8)
+    out = np.zeros(int(lens.sum()) + 8, np.uint8)
+    n = L.orc_normq_encode(_ptr(txt), _ptr(off), _ptr(lens), None if rv is None else _ptr(rv), lens.size, _ptr(out))
+    return out[:n].copy()
+
+
+def normq_decode(local, lens, is_rev):
+    """restatement of codec_normq_reconstruct for every line -> (len[i] bytes per line, missing flags); None if the stream does not fit the lines"""
+    L = port()
+    L.orc_normq_decode.restype = C.c_int
+    L.orc_normq_decode.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    local = np.ascontiguousarray(local, np.uint8); lens = np.ascontiguousarray(lens, np.uint32)
+    rv = None if is_rev is None else np.ascontiguousarray(is_rev, np.uint8)
+    out = np.zeros(int(lens.sum()) + 8, np.uint8); miss = np.zeros(lens.size + 1, np.uint8); used = C.c_uint64()
+    lo = local if local.size else np.zeros(1, np.uint8)
+    rc = L.orc_normq_decode(_ptr(lo), local.size, _ptr(lens), None if rv is None else _ptr(rv), lens.size, _ptr(out), _ptr(miss), C.byref(used))
+    if rc != 0 or used.value != local.size:
+        return None
+    return out[:int(lens.sum())].copy(), miss[:lens.size].copy()
+
+
+def ref_normq_encode(txt, off, lens, is_rev):
+    """the REFERENCE's compiled codec_normq_compress -> what it hands its sub-codec"""
+    txt = np.ascontiguousarray(txt, np.uint8); off = np.ascontiguousarray(off, np.uint64); lens = np.ascontiguousarray(lens, np.uint32)
+    rv = None if is_rev is None else np.ascontiguousarray(is_rev, np.uint8)
+    out = np.zeros(int(lens.sum()) + 1100, np.uint8); n = C.c_uint64()
+    G = gz_ref()
+    G.ref_normq_encode.restype = C.c_int
+    G.ref_normq_encode.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    _gz_check(G.ref_normq_encode(_ptr(txt), txt.size, _ptr(off), _ptr(lens), None if rv is None else _ptr(rv), lens.size, _ptr(out), C.byref(n)), "codec_normq_compress")
+    return out[:n.value].copy()
+
+
+def ref_normq_decode(local, lens, is_rev):
+    """the REFERENCE's compiled codec_normq_reconstruct, line by line -> txt_data (a line without quality is the one character '*')"""
+    local = np.ascontiguousarray(local, np.uint8); lens = np.ascontiguousarray(lens, np.uint32)
+    rv = None if is_rev is None else np.ascontiguousarray(is_rev, np.uint8)
+    out = np.zeros(int(lens.sum()) + 64, np.uint8); n = C.c_uint64()
+    G = gz_ref()
+    G.ref_normq_decode.restype = C.c_int
+    G.ref_normq_decode.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    lo = local if local.size else np.zeros(1, np.uint8)
+    _gz_check(G.ref_normq_decode(_ptr(lo), local.size, _ptr(lens), None if rv is None else _ptr(rv), lens.size, _ptr(out), C.byref(n)), "codec_normq_reconstruct")
+    return out[:n.value].copy()

@@ -84,7 +84,7 @@ def check_domq(H, qual, off, lens, sub="ARTb"):
     bufs = [np.zeros(2 * tot + 64, np.uint8), np.zeros(tot + 64, np.uint8), np.zeros(lens.size + 64, np.uint8), np.zeros(tot + 64, np.uint8)]
     ls = [C.c_uint32() for _ in range(4)]
     den = np.zeros(95 * 95, np.uint8); dl = C.c_uint32(); prm = C.c_uint8()
-    comp = np.zeros(2 * tot + 70000, np.uint8); cl = C.c_uint32(); back = np.zeros(tot + 64, np.uint8); sf = C.c_int(); cnt = np.zeros(3, np.uint64)
+    comp = np.zeros(2 * tot + 70000, np.uint8); cl = C.c_uint32(); back = np.zeros(tot + 64, np.uint8); sf = C.c_int(); cnt = np.zeros(4, np.uint64)
     args = []
     for b, l in zip(bufs, ls):
         args += [_p(b), C.byref(l)]
@@ -167,6 +167,27 @@ def check_longr(H, txt, seq_off, qual_off, seq_len, qual_len, is_rev, sub="ARTW"
     assert bytes(back[:len(exp)]) == bytes(exp) and nm.value == missing
 
 
+def check_normq(H, seed, n_lines, p_missing, sub="ARTB"):
+    """codec_normq_compress / codec_normq_reconstruct through the plug-in layer: strands through the line callback, lines without quality"""
+    from test_normq import _vb
+    txt, off, zlen, rev, seq_len, missing = _vb(seed=seed, n_lines=n_lines, p_missing=p_missing)
+    tot, otot = int(zlen.sum()), int(seq_len.sum())
+    local = np.zeros(tot + 64, np.uint8); comp = np.zeros(2 * tot + 70000, np.uint8); back = np.zeros(otot + 64, np.uint8)
+    ll, cl, bl, sf, nm, nl = C.c_uint64(), C.c_uint32(), C.c_uint64(), C.c_int(), C.c_int(), C.c_uint64()
+    _ok(H, H.harness_normq(_p(txt), _p(off), _p(zlen), _p(seq_len), _p(rev), zlen.size, CODEC[sub], _p(local), C.byref(ll), _p(comp), C.byref(cl),
+                           _p(back), C.byref(bl), C.byref(sf), C.byref(nm), C.byref(nl)))
+    want = orc.ref_normq_encode(txt, off, zlen, rev) if orc.have_gz_ref() else orc.normq_encode(txt, off, zlen, rev)
+    assert ll.value == want.size and np.array_equal(local[:want.size], want), "QUAL.local differs from codec_normq_compress's"
+    if want.size >= 50:
+        kind = "rans" if sub.startswith("RAN") else "arith"
+        assert np.array_equal(comp[:cl.value], orc.compress("ref" if orc.have_ref() else "port", kind, want, orc.ORDER[sub])), "QUAL section differs"
+    assert sf.value == 1, "the soft-fail re-entry of codec_normq_compress was not taken"
+    text = orc.ref_normq_decode(want, seq_len, rev) if orc.have_gz_ref() else None
+    if text is not None:
+        assert bl.value == text.size and np.array_equal(back[:text.size], text), "reconstructed text differs from codec_normq_reconstruct's"
+    assert nm.value == int(missing.sum()) and nl.value == zlen.size
+
+
 def run_all(H, big):
     r = np.random.default_rng(3)
     # simple codecs: contiguous and line by line, with and without the soft-fail retry
@@ -206,6 +227,9 @@ def run_all(H, big):
     for li in (1, 4):
         t2[int(qo[li])] = 32; ql[li] = 1
     check_longr(H, t2, so, qo, lens, ql, rev)
+    # NORMQ: reverse-complemented reads, lines without quality
+    check_normq(H, 21, 200 if not big else 20000, 0.0)
+    check_normq(H, 22, 150 if not big else 5000, 0.15, sub="RANB")
 
 
 def check_combiner(H):
