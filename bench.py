@@ -360,6 +360,7 @@ def run_gpu(args):
     # the next step's text is staged (gzb_stage_upload) and the previous step's results are fetched (gzb_stage_fetch) while the
     # current step's kernels run on device buffers.
     e2e = None
+    ph, e2e_err = None, ""
     cpu_data = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n_cpu = min(V, 4 * (os.cpu_count() or 1))
@@ -371,12 +372,23 @@ def run_gpu(args):
         torch.cuda.empty_cache()
         path.seq_out_d = path.qual_out_d = path.names_dec_d = path.dec_d = None      # (the pipelined leg brings its own double-buffered outputs)
         torch.cuda.empty_cache()
-        ph = PipelinedHost(path, host)
-        del host
+        ph, e2e_err = None, ""
+        try:                                                              # (page-locked memory is the box's, not this rank's: if it does not fit, every rank skips the leg)
+            ph = PipelinedHost(path, host)
+            del host
+            ph.zip_steps(1); ph.scrub(); ph.piz_steps(1)                  # warm-up step (buffers grow to their sizes) + correctness gate
+            assert ph.check(), "host round trip failed"
+            ph.scrub()
+        except (RuntimeError, MemoryError, GzbError) as ex:
+            if "memory" not in str(ex).lower():
+                raise
+            ph, e2e_err = None, f"{type(ex).__name__}: {str(ex)[:200]}"
+        if world > 1:
+            t = torch.tensor([1 if ph is not None else 0], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            if not int(t.item()):
+                ph, e2e_err = None, e2e_err or "another rank ran out of page-locked memory"
         Ke = max(2, args.steps)
-        ph.zip_steps(1); ph.scrub(); ph.piz_steps(1)                      # warm-up step (buffers grow to their sizes) + correctness gate
-        assert ph.check(), "host round trip failed"
-        ph.scrub()
+    if ph is not None:
         barrier()
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         with torch.cuda.stream(stream):
@@ -473,7 +485,8 @@ def run_gpu(args):
                        "txt_accounting": "input bytes = the FASTQ text the VBlocks represent (45-byte name line, SEQ, '+', QUAL, 4 newlines per read); of the name line, "
                                          "10 B/read of segmented read-name contexts flow through the path (the segmenter is out of scope); the same count in both arms",
                        "excluded": EXCLUDED, "sharding": "VBlocks round-robin by vblock_i, no data-path collective; NCCL all_gather of the section list only",
-                       "engines_per_gpu": len(path.engs), "device_groups": len(path.groups), "cpu_binding": numa},
+                       "engines_per_gpu": len(path.engs), "device_groups": len(path.groups), "cpu_binding": numa,
+                       **({"e2e_skipped": e2e_err} if (not args.no_e2e and e2e is None) else {})},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
         }))
     if world > 1:

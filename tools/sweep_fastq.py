@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--reads", type=int, default=92000)
     ap.add_argument("--read-len", type=int, default=150)
     ap.add_argument("--cfg", action="append", default=[])
+    ap.add_argument("--sub-batch", type=int, default=128, help="VBlocks per codec_domq_compress call (its worst-case scratch is 4n bytes per VBlock of a sub-batch)")
     ap.add_argument("--streams", default="", help="comma-separated stream names: time only the simple-codec sections of these streams (compress + uncompress on one engine), "
                                                   "e.g. DIVRQUAL = the longest arithmetic chain of every VBlock without the other leaves around it")
     a = ap.parse_args()
@@ -28,7 +29,7 @@ def main():
     from genozip_b200.fastq_path import FastqCodecPath, synth_vblocks, txt_bytes_per_vb
     dev = torch.device("cuda", 0)
     eng = Engine(0)
-    path = FastqCodecPath(eng, a.vblocks, a.reads, a.read_len)
+    path = FastqCodecPath(eng, a.vblocks, a.reads, a.read_len, sub_batch=a.sub_batch)
     data = synth_vblocks(a.vblocks, a.reads, a.read_len, 1000, dev)
     torch.cuda.empty_cache()
     path.codec = json.load(open(os.path.join(ROOT, "bench_codecs.json")))
