@@ -63,6 +63,15 @@ class NormqVb(C.Structure):         # gzb_normq_vb
                 ("out", C.c_void_p), ("out_cap", C.c_uint64), ("missing", C.c_void_p)]
 
 
+class LocalItem(C.Structure):       # gzb_local_item
+    _fields_ = [("data", C.c_void_p), ("n_elems", C.c_uint64), ("op", C.c_int32), ("status", C.c_int32)]
+
+
+LT_OPS = {"swap16": 1, "swap32": 2, "swap64": 3, "interlace8": 4, "interlace16": 5, "interlace32": 6, "interlace64": 7,
+          "deinterlace8": 8, "deinterlace16": 9, "deinterlace32": 10, "deinterlace64": 11}
+LT_WIDTH = {1: 2, 2: 4, 3: 8, 4: 1, 5: 2, 6: 4, 7: 8, 8: 1, 9: 2, 10: 4, 11: 8}
+
+
 class DigestItem(C.Structure):      # gzb_digest_item
     _fields_ = [("data", C.c_void_p), ("len", C.c_uint64), ("adler", C.c_uint32), ("reserved", C.c_uint32)]
 
@@ -146,6 +155,8 @@ def load():
     L.gzb_stage_wait.restype = C.c_int; L.gzb_stage_wait.argtypes = [C.c_void_p, C.c_int]
     for f in ("gzb_normq_gather", "gzb_normq_reconstruct"):
         getattr(L, f).restype = C.c_int; getattr(L, f).argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+    L.gzb_local_transform_batch.restype = C.c_int
+    L.gzb_local_transform_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
     L.gzb_adler32_batch.restype = C.c_int
     L.gzb_adler32_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
     L.gzb_pbwt_decode.restype = C.c_int
@@ -284,6 +295,21 @@ class Engine:
         rc = self.L.gzb_uncompress_sections(self.h, secs, n, flags)
         if rc != 0:
             raise GzbError(f"gzb_uncompress_sections failed ({rc}): {self._err()}")
+
+    # ---- zip_generate_local's transforms (host buffers, in place on copies) ----
+    def local_transform(self, items):
+        """items: list of (op name, numpy array of the operation's width) -> list of transformed arrays (zip.c:167-213 / buffer.c:337-353, 431-468)"""
+        arr = (LocalItem * max(1, len(items)))(); keep = []
+        for i, (op, a) in enumerate(items):
+            code = LT_OPS[op]
+            b = np.ascontiguousarray(a).copy()
+            assert b.dtype.itemsize == LT_WIDTH[code], (op, b.dtype)
+            keep.append(b)
+            arr[i].data = b.ctypes.data if b.size else None; arr[i].n_elems = b.size; arr[i].op = code
+        rc = self.L.gzb_local_transform_batch(self.h, arr, len(items), 0)
+        if rc != 0:
+            raise GzbError(f"gzb_local_transform_batch failed ({rc}): {self._err()}")
+        return keep
 
     # ---- NORMQ (host buffers) ----
     def normq_gather(self, vbs):

@@ -125,6 +125,17 @@ int gzb_copy_batch (gzb_engine *e, const gzb_copy *copies, uint32_t n);
 typedef struct { const void *data; uint64_t len; uint32_t adler; uint32_t reserved; } gzb_digest_item;
 int gzb_adler32_batch (gzb_engine *e, gzb_digest_item *items, uint32_t n, uint32_t flags);
 
+/* ---------------------------------------------------------------- zip_generate_local's transforms of a context's local buffer, in place
+ * (src/zip.c:167-213 -> src/buffer.c:337-353; PIZ inverses src/buffer.c:431-468, src/local_type.h:70-90) for a batch of buffers:
+ *   SWAP16/32/64        BGEN_u16/u32/u64_buf on a little-endian host (LT_UINT*, LT_hex*, LT_FLOAT*); its own inverse
+ *   INTERLACE8/16/32/64 interlace_d8_buf, BGEN_interlace_d16/32/64_buf (LT_INT*): INTERLACE (src/context.h:99), then big endian
+ *   DEINTERLACE*        BGEN_deinterlace_d*_buf: from big endian, then DEINTERLACE (src/context.h:100)
+ * n_elems counts elements of the operation's width; data must be aligned to it.  Device pointers with GZB_DEVICE_PTRS, else host memory. */
+enum { GZB_LT_SWAP16 = 1, GZB_LT_SWAP32, GZB_LT_SWAP64, GZB_LT_INTERLACE8, GZB_LT_INTERLACE16, GZB_LT_INTERLACE32, GZB_LT_INTERLACE64,
+       GZB_LT_DEINTERLACE8, GZB_LT_DEINTERLACE16, GZB_LT_DEINTERLACE32, GZB_LT_DEINTERLACE64 };
+typedef struct { void *data; uint64_t n_elems; int32_t op; int32_t status; } gzb_local_item;
+int gzb_local_transform_batch (gzb_engine *e, gzb_local_item *items, uint32_t n, uint32_t flags);
+
 /* ---------------------------------------------------------------- ACGT / XCGT (src/codec_acgt.c)
  * pack:   codec_acgt_compress up to the sub-codec call (:64-163): bases → LE 2-bit words + exception stream.
  *         `packed` receives gzb_acgt_packed_len(n) bytes; `x` (n bytes) may be NULL if the caller declares

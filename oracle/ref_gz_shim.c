@@ -504,3 +504,23 @@ int ref_normq_decode (const uint8_t *local, uint64_t local_len, const uint32_t *
     free (vb);
     return 0;
 }
+
+// ================================================================ zip_generate_local's transforms: the reference's own macros
+// (INTERLACE / DEINTERLACE of context.h:98-101, BGEN16/32/64 of endianness.h) in the loops of buffer.c:337-345, :431-468
+int ref_local_transform (int op, void *data, uint64_t n)
+{
+    switch (op) {
+        case 1:  { uint16_t *p = data; for (uint64_t i = 0; i < n; i++) p[i] = BGEN16 (p[i]); return 0; }
+        case 2:  { uint32_t *p = data; for (uint64_t i = 0; i < n; i++) p[i] = BGEN32 (p[i]); return 0; }
+        case 3:  { uint64_t *p = data; for (uint64_t i = 0; i < n; i++) p[i] = BGEN64 (p[i]); return 0; }
+        case 4:  { int8_t  *p = data; for (uint64_t i = 0; i < n; i++) p[i] =         (INTERLACE (int8_t,  p[i])); return 0; }
+        case 5:  { int16_t *p = data; for (uint64_t i = 0; i < n; i++) p[i] = BGEN16 (INTERLACE (int16_t, p[i])); return 0; }
+        case 6:  { int32_t *p = data; for (uint64_t i = 0; i < n; i++) p[i] = BGEN32 (INTERLACE (int32_t, p[i])); return 0; }
+        case 7:  { int64_t *p = data; for (uint64_t i = 0; i < n; i++) p[i] = BGEN64 (INTERLACE (int64_t, p[i])); return 0; }
+        case 8:  { uint8_t  *p = data; for (uint64_t i = 0; i < n; i++) { uint8_t  u = p[i];          ((int8_t  *)p)[i] = DEINTERLACE (int8_t,  u); } return 0; }
+        case 9:  { uint16_t *p = data; for (uint64_t i = 0; i < n; i++) { uint16_t u = BGEN16 (p[i]); ((int16_t *)p)[i] = DEINTERLACE (int16_t, u); } return 0; }
+        case 10: { uint32_t *p = data; for (uint64_t i = 0; i < n; i++) { uint32_t u = BGEN32 (p[i]); ((int32_t *)p)[i] = DEINTERLACE (int32_t, u); } return 0; }
+        case 11: { uint64_t *p = data; for (uint64_t i = 0; i < n; i++) { uint64_t u = BGEN64 (p[i]); ((int64_t *)p)[i] = DEINTERLACE (int64_t, u); } return 0; }
+        default: return -1;
+    }
+}

@@ -257,6 +257,18 @@ class MockLib:
                 _view(c.dst, c.len)[:] = _view(c.src, c.len)
         return 0
 
+    def gzb_local_transform_batch(self, h, items, n, flags):
+        names = {v: k for k, v in orc.LT_OPS.items()}
+        for i in range(n):
+            it = items[i]
+            w = {1: 2, 2: 4, 3: 8, 4: 1, 5: 2, 6: 4, 7: 8, 8: 1, 9: 2, 10: 4, 11: 8}[it.op]
+            dt = {1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[w]
+            if it.n_elems:
+                v = _view(it.data, it.n_elems, dt)
+                v[:] = orc.local_transform(names[it.op], v.copy()).view(dt)
+            it.status = 0
+        return 0
+
     def gzb_normq_gather(self, h, vbs, n, flags):
         for i in range(n):
             a = vbs[i]

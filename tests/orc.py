@@ -442,3 +442,40 @@ def ref_normq_decode(local, lens, is_rev):
     lo = local if local.size else np.zeros(1, np.uint8)
     _gz_check(G.ref_normq_decode(_ptr(lo), local.size, _ptr(lens), None if rv is None else _ptr(rv), lens.size, _ptr(out), C.byref(n)), "codec_normq_reconstruct")
     return out[:n.value].copy()
+
+
+# ---------------------------------------------------------------- zip_generate_local's transforms (src/zip.c:167-213)
+LT_OPS = {"swap16": 1, "swap32": 2, "swap64": 3, "interlace8": 4, "interlace16": 5, "interlace32": 6, "interlace64": 7,
+          "deinterlace8": 8, "deinterlace16": 9, "deinterlace32": 10, "deinterlace64": 11}
+
+
+def local_transform(op, a):
+    """numpy restatement: byte swap; INTERLACE (n >= 0 -> 2n, n < 0 -> -2n - 1, modulo the width) then big endian; and the inverse"""
+    a = np.ascontiguousarray(a).copy()
+    w = a.dtype.itemsize
+    U = {1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[w]
+    u = a.view(U)
+    if op.startswith("swap"):
+        return u.byteswap().view(a.dtype)
+    if op.startswith("interlace"):
+        s_ = u.view({1: np.int8, 2: np.int16, 4: np.int32, 8: np.int64}[w])
+        with np.errstate(over="ignore"):
+            neg = ((U(0) - u) << U(1)) - U(1)
+            pos = u << U(1)
+        return np.where(s_ < 0, neg, pos).astype(U).byteswap().view(a.dtype)
+    x = u.byteswap()
+    with np.errstate(over="ignore"):
+        odd = U(0) - ((x >> U(1)) + U(1))
+        even = x >> U(1)
+    return np.where(x & U(1), odd, even).astype(U).view(a.dtype)
+
+
+def ref_local_transform(op, a):
+    """the reference's own INTERLACE / DEINTERLACE / BGEN macros in buffer.c's loops (oracle/ref_gz_shim.c)"""
+    b = np.ascontiguousarray(a).copy()
+    G = gz_ref()
+    G.ref_local_transform.restype = C.c_int
+    G.ref_local_transform.argtypes = [C.c_int, C.c_void_p, C.c_uint64]
+    if b.size:
+        _gz_check(G.ref_local_transform(LT_OPS[op], _ptr(b), b.size), "local transform")
+    return b
