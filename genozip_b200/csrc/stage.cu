@@ -36,7 +36,7 @@ struct Feeder {
     void run ()
     {
         cudaSetDevice (device);
-        for (auto &e : ev) cudaEventCreateWithFlags (&e, cudaEventDisableTiming);
+        for (auto &e : ev) cudaEventCreateWithFlags (&e, cudaEventDisableTiming | cudaEventBlockingSync);   // (the feeder sleeps between pieces: it must not take a core from the compute threads)
         uint64_t issued = 0;                                                // pieces issued so far; piece i uses event i % DEPTH
         for (;;) {
             Job j;

@@ -172,7 +172,7 @@ typedef struct simt_stream_s { int id; } *cudaStream_t;
 typedef struct simt_event_s { double t; } *cudaEvent_t;
 enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1, cudaErrorInvalidDeviceFunction = 98, cudaErrorNoKernelImageForDevice = 209 };
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
-enum { cudaStreamNonBlocking = 1, cudaStreamDefault = 0, cudaEventDisableTiming = 2, cudaEventDefault = 0 };
+enum { cudaStreamNonBlocking = 1, cudaStreamDefault = 0, cudaEventDisableTiming = 2, cudaEventBlockingSync = 1, cudaEventDefault = 0 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 struct cudaDeviceProp { char name[256]; int major, minor, multiProcessorCount; size_t totalGlobalMem, sharedMemPerBlockOptin; };
 
