@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(128) k_arith_encode_t (const EncLeaf *leaves, 
 //   GZB_AR_CTAS     general arithmetic kernel (order 1 / RLE leaves), 4 warps per CTA       default 2
 //                   (2 / 4 / 8 / 16 per SM measure the same within run-to-run noise; 2 leaves registers for the kernels beside them)
 //   GZB_AR0_CTAS    order-0 arithmetic kernel                                               default 2
-//   GZB_AR_RUN4     the decoder tries four run steps at once                                default 1
+//   GZB_AR_RUN4     the decoder tries four run steps at once: 0 never, 1 all four or nothing, 2 the longest valid prefix   default 2
 //   GZB_AR_SPLIT_STREAM  the split encoder runs on its own stream beside the general kernel default 1
 //   GZB_AR_LONG_MIN order-1 leaves of at least this many symbols are decoded by k_arith_decode_long (off = none)   default off
 //                   (measured, 768 VBlocks: alone the mirror takes the longest leaf from 332 to 305 / 286 ms (16 / 32 entries); beside the
@@ -75,7 +75,7 @@ const ChainTune &chain_tune ()                                               // 
     };
     c.arith_ctas = geti ("GZB_AR_CTAS", 2, 1, 16);
     c.arith_o0_ctas = geti ("GZB_AR0_CTAS", 2, 1, 16);
-    c.run4 = geti ("GZB_AR_RUN4", 1, 0, 1);
+    c.run4 = geti ("GZB_AR_RUN4", 2, 0, 2);
     c.split_stream = geti ("GZB_AR_SPLIT_STREAM", 1, 0, 1);
     c.long_ent = geti ("GZB_AR_LONG_ENT", 16, 16, 32) >= 32 ? 32 : 16;
     { const char *v = getenv ("GZB_AR_LONG_MIN"); c.long_min = !v || !*v || !strcmp (v, "off") ? 0xffffffffu : (uint32_t)strtoul (v, nullptr, 10); }
@@ -129,8 +129,8 @@ __global__ void __launch_bounds__(128) k_arith_decode_t (DecLeaf *leaves, const 
             }
             ar_out_flush (o);
         }
-        else if (o1) ar_decode_leaf<true> (lit, maxs, rle, body, L.body_len, out, n, lane, run4 != 0);
-        else         ar_decode_leaf<false> (lit, maxs, rle, body, L.body_len, out, n, lane, run4 != 0);
+        else if (o1) ar_decode_leaf<true> (lit, maxs, rle, body, L.body_len, out, n, lane, run4);
+        else         ar_decode_leaf<false> (lit, maxs, rle, body, L.body_len, out, n, lane, run4);
     }
 }
 
@@ -247,23 +247,34 @@ __global__ void __launch_bounds__(32) k_arith_decode_long (DecLeaf *leaves, cons
         bool selfloop = (c.e0 >> 16) == ctx;
         uint32_t skip4 = 0, fail4 = 0;
         while (i < n && ok) {                                               // the loop of ar_decode_leaf<true>, model reads from the mirror
-            if (run4 && selfloop && skip4 == 0 && i + 4 <= n && c.tot + 4 * AR_STEP <= AR_MAXF && (o.pos & 3) == 0 && o.pos >= 4) {
+            if (run4 && selfloop && skip4 == 0 && i + 4 <= n && c.tot + 4 * AR_STEP <= AR_MAXF && (run4 == 2 || ((o.pos & 3) == 0 && o.pos >= 4))) {
                 const uint32_t f0 = c.e0 & 0xffffu;
                 const float rt1 = ar_rcp_below (c.tot + AR_STEP), rt2 = ar_rcp_below (c.tot + 2 * AR_STEP), rt3 = ar_rcp_below (c.tot + 3 * AR_STEP);
                 const uint32_t g1 = f0 * ar_div (rc.range, c.tot, c.rtot);
                 const uint32_t g2 = (f0 + AR_STEP) * ar_div (g1, c.tot + AR_STEP, rt1);
                 const uint32_t g3 = (f0 + 2 * AR_STEP) * ar_div (g2, c.tot + 2 * AR_STEP, rt2);
                 const uint32_t g4 = (f0 + 3 * AR_STEP) * ar_div (g3, c.tot + 3 * AR_STEP, rt3);
-                if (rc.code < g4 && g4 >= AR_TOP) {
-                    rc.range = g4;
-                    c.e0 += 4 * AR_STEP; c.tot += 4 * AR_STEP; c.rtot = ar_rcp_below (c.tot);
+                uint32_t k, gk;
+                if (run4 == 2) {
+                    if (rc.code < g4 && g3 >= AR_TOP)      { k = 4; gk = g4; }
+                    else if (rc.code < g3 && g2 >= AR_TOP) { k = 3; gk = g3; }
+                    else if (rc.code < g2 && g1 >= AR_TOP) { k = 2; gk = g2; }
+                    else if (rc.code < g1)                 { k = 1; gk = g1; }
+                    else                                   { k = 0; gk = 0; }
+                }
+                else { k = (rc.code < g4 && g4 >= AR_TOP) ? 4 : 0; gk = g4; }
+                if (k) {
+                    rc.range = gk;
+                    c.e0 += k * AR_STEP; c.tot += k * AR_STEP; c.rtot = ar_rcp_below (c.tot);
                     dirty = true;
-                    *reinterpret_cast<uint32_t *>(o.wptr) = (c.e0 >> 16) * 0x01010101u;
-                    o.wptr += 4; o.pos += 4;
-                    i += 4; fail4 = 0;
+                    if (k == 4 && (o.pos & 3) == 0 && o.pos >= 4) { *reinterpret_cast<uint32_t *>(o.wptr) = (c.e0 >> 16) * 0x01010101u; o.wptr += 4; o.pos += 4; }
+                    else for (uint32_t j = 0; j < k; j++) ar_out_put (o, c.e0 >> 16);
+                    i += k; fail4 = 0;
+                    if (rc.range < AR_TOP) ok = ar_dec_renorm (rc);
+                    else if (k < 4) skip4 = 1;                              // the run ended on another symbol: that one goes the single-step way
                     continue;
                 }
-                fail4 = fail4 < 4 ? fail4 + 1 : 4; skip4 = 1u << fail4;
+                fail4 = fail4 < 4 ? fail4 + 1 : 4; skip4 = run4 == 2 ? 2u : 1u << fail4;   // single steps before the next attempt
             }
             else if (skip4) skip4--;
             const uint32_t r = ar_div (rc.range, c.tot, c.rtot);

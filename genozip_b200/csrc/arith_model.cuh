@@ -407,7 +407,7 @@ AR_FN void ar_decode_tail (uint32_t *lit, uint32_t maxs, ArDec &rc, ArOut &o, ui
 
 // arith_uncompress_O0 / O1 (arith_dynamic.c:129-152, 200-226) and the RLE variants (:451-493, :564-608)
 template <bool O1>
-AR_FN void ar_decode_leaf (uint32_t *lit, uint32_t maxs, bool rle, const uint8_t *body, uint32_t body_len, uint8_t *out, uint32_t n, int lane, bool run4 = true)
+AR_FN void ar_decode_leaf (uint32_t *lit, uint32_t maxs, bool rle, const uint8_t *body, uint32_t body_len, uint8_t *out, uint32_t n, int lane, uint32_t run4 = 2)
 {
     const uint32_t stride = ar_stride (maxs);
     uint32_t *run = lit + (O1 ? 256 : 1) * stride;
@@ -427,26 +427,38 @@ AR_FN void ar_decode_leaf (uint32_t *lit, uint32_t maxs, bool rle, const uint8_t
         uint32_t skip4 = 0, fail4 = 0;                                       // back-off of the 4-step speculation below
         while (i < n && ok) {
             // FOUR RUN STEPS AT ONCE, speculatively.  A run step leaves the code alone (the top entry's cumulative frequency is 0)
-            // and only shrinks the range, so four of them are a straight line of four divisions: no renormalisation can be due in
-            // between if none is due at the end, the halving is excluded up front, and the four symbols are one aligned word of
-            // output.  If any of the four tests fails nothing has been changed and the single steps below take over.
-            if (run4 && selfloop && skip4 == 0 && i + 4 <= n && c.tot + 4 * AR_STEP <= AR_MAXF && (o.pos & 3) == 0 && o.pos >= 4) {
+            // and only shrinks the range, so four of them are a straight line of four divisions; the halving is excluded up front.
+            // The ranges only shrink (freq <= TotFreq), so the steps 1 .. k are what the single steps would have done iff code < g_k
+            // and no renormalisation was due before step k (g_(k-1) >= TOP): the longest such prefix is taken (mode 2; mode 1 takes all
+            // four or nothing), the renormalisation after step k is the ordinary one.  Nothing has been changed if k = 0.
+            if (run4 && selfloop && skip4 == 0 && i + 4 <= n && c.tot + 4 * AR_STEP <= AR_MAXF && (run4 == 2 || ((o.pos & 3) == 0 && o.pos >= 4))) {
                 const uint32_t f0 = c.e0 & 0xffffu;
                 const float rt1 = ar_rcp_below (c.tot + AR_STEP), rt2 = ar_rcp_below (c.tot + 2 * AR_STEP), rt3 = ar_rcp_below (c.tot + 3 * AR_STEP);
                 const uint32_t g1 = f0 * ar_div (rc.range, c.tot, c.rtot);
                 const uint32_t g2 = (f0 + AR_STEP) * ar_div (g1, c.tot + AR_STEP, rt1);
                 const uint32_t g3 = (f0 + 2 * AR_STEP) * ar_div (g2, c.tot + 2 * AR_STEP, rt2);
                 const uint32_t g4 = (f0 + 3 * AR_STEP) * ar_div (g3, c.tot + 3 * AR_STEP, rt3);
-                if (rc.code < g4 && g4 >= AR_TOP) {                          // g1 >= g2 >= g3 >= g4 (freq <= TotFreq): the last test and the last bound cover all four
-                    rc.range = g4;
-                    c.e0 += 4 * AR_STEP; c.tot += 4 * AR_STEP; c.rtot = ar_rcp_below (c.tot);
+                uint32_t k, gk;
+                if (run4 == 2) {
+                    if (rc.code < g4 && g3 >= AR_TOP)      { k = 4; gk = g4; }
+                    else if (rc.code < g3 && g2 >= AR_TOP) { k = 3; gk = g3; }
+                    else if (rc.code < g2 && g1 >= AR_TOP) { k = 2; gk = g2; }
+                    else if (rc.code < g1)                 { k = 1; gk = g1; }
+                    else                                   { k = 0; gk = 0; }
+                }
+                else { k = (rc.code < g4 && g4 >= AR_TOP) ? 4 : 0; gk = g4; }
+                if (k) {
+                    rc.range = gk;
+                    c.e0 += k * AR_STEP; c.tot += k * AR_STEP; c.rtot = ar_rcp_below (c.tot);
                     dirty = true;
-                    *reinterpret_cast<uint32_t *>(o.wptr) = (c.e0 >> 16) * 0x01010101u;
-                    o.wptr += 4; o.pos += 4;
-                    i += 4; fail4 = 0;
+                    if (k == 4 && (o.pos & 3) == 0 && o.pos >= 4) { *reinterpret_cast<uint32_t *>(o.wptr) = (c.e0 >> 16) * 0x01010101u; o.wptr += 4; o.pos += 4; }
+                    else for (uint32_t j = 0; j < k; j++) ar_out_put (o, c.e0 >> 16);
+                    i += k; fail4 = 0;
+                    if (rc.range < AR_TOP) ok = ar_dec_renorm (rc);
+                    else if (k < 4) skip4 = 1;                              // the run ended on another symbol: that one goes the single-step way
                     continue;
                 }
-                fail4 = fail4 < 4 ? fail4 + 1 : 4; skip4 = 1u << fail4;      // 2, 4, 8, 16 single steps before the next attempt
+                fail4 = fail4 < 4 ? fail4 + 1 : 4; skip4 = run4 == 2 ? 2u : 1u << fail4;   // single steps before the next attempt
             }
             else if (skip4) skip4--;
             const uint32_t r = ar_div (rc.range, c.tot, c.rtot);
