@@ -224,6 +224,11 @@ def bind_to_gpu_cpus(gpu):
         h = pynvml.nvmlDeviceGetHandleByIndex(gpu)
         words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
         cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1} & set(os.sched_getaffinity(0))
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if cpus and len(cpus) < 6 * world and len(cpus) < len(os.sched_getaffinity(0)):
+            # every rank runs ~6 busy host threads (two pipelines, two staging feeders, the interpreter); if the ranks of this box would
+            # all crowd onto one NUMA node's cores, spreading out is worth more than local page-locked memory
+            return f"not bound: {len(cpus)} cpus local to gpu {gpu} for up to {world} ranks"
         if cpus:
             os.sched_setaffinity(0, cpus)
             return f"{len(cpus)} cpus local to gpu {gpu}"
