@@ -257,12 +257,6 @@ def run_gpu(args):
         n = args.reads * args.read_len
         per_vb = 9.3 * n + 14 * args.reads + (6 << 20)          # inputs 2n, 2-bit words n/4, exception stream n, DOMQ streams ~0.4n, outputs 2n, engine workspace ~3.5n
         V = int(max(8, min(768, (0.86 * free_b) // per_vb)))     # (measured on B200: 512 -> 17.7, 768 -> 22.2, 819 -> 21.7 GB/s: beyond ~768 the chain kernels are issue-bound)
-        if not args.no_e2e:                                     # the host-buffer leg keeps page-locked inputs and outputs (4.3n per VBlock) + 2n while it makes them; every rank does
-            try:
-                import psutil
-                V = int(max(8, min(V, (0.45 * psutil.virtual_memory().available / world) // (6.5 * n))))
-            except Exception:
-                pass
     while True:                                                  # a batch that does not fit is halved (all ranks agree on the size)
         if world > 1:
             t = torch.tensor([V], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MIN); V = int(t.item())
@@ -370,17 +364,34 @@ def run_gpu(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n_cpu = min(V, 4 * (os.cpu_count() or 1))
         cpu_data = {k: [data[k][v].cpu().numpy() for v in range(n_cpu)] for k in data}
+    Ve = V
     if not args.no_e2e:
         from genozip_b200.fastq_path import PipelinedHost
-        host = {k: v.cpu() for k, v in data.items()}
-        del data
-        torch.cuda.empty_cache()
+        # the host leg keeps page-locked inputs and outputs (4.3n bytes per VBlock), and every rank of the box does: its batch is what the
+        # box's memory allows (the device-resident leg above is bounded by the GPU's memory alone)
+        try:
+            import psutil
+            Ve = int(max(8, min(V, (0.6 * psutil.virtual_memory().available / world) // (4.4 * args.reads * args.read_len))))
+        except Exception:
+            pass
+        Ve = max(8, min(Ve, int(os.environ.get("GZB_E2E_VBLOCKS", Ve))))   # (to exercise the smaller-batch branch on a box with plenty of memory)
+        if world > 1:
+            t = torch.tensor([Ve], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MIN); Ve = int(t.item())
         path.seq_out_d = path.qual_out_d = path.names_dec_d = path.dec_d = None      # (the pipelined leg brings its own double-buffered outputs)
+        if Ve < V:                                                        # a smaller batch for this leg: a path of its size
+            data = {k: v[:Ve].contiguous() for k, v in data.items()}
+            path.close(); path.release_device(); del path
+            import gc; gc.collect(); torch.cuda.empty_cache()
+            path = FastqCodecPath(eng, Ve, args.reads, args.read_len)
+            path.codec = dict(codecs)
+            path.alloc_piz(path.zip_device(data)); path.piz_device(path.meta)
+            path.seq_out_d = path.qual_out_d = path.names_dec_d = path.dec_d = None
         torch.cuda.empty_cache()
         ph, e2e_err = None, ""
         try:                                                              # (page-locked memory is the box's, not this rank's: if it does not fit, every rank skips the leg)
-            ph = PipelinedHost(path, host)
-            del host
+            ph = PipelinedHost(path, data)
+            del data
+            torch.cuda.empty_cache()
             ph.zip_steps(1); ph.scrub(); ph.piz_steps(1)                  # warm-up step (buffers grow to their sizes) + correctness gate
             assert ph.check(), "host round trip failed"
             ph.scrub()
@@ -410,7 +421,8 @@ def run_gpu(args):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ez, ep = t[0].item(), t[1].item()
-        e2e = {"value": world * txt_bytes / ((ez + ep) * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(world * (h2d_z + h2d_p)), "d2h_bytes_per_step": int(world * (d2h_z + d2h_p)),
+        e2e_bytes = Ve * txt_bytes_per_vb(args.reads, args.read_len)
+        e2e = {"value": world * e2e_bytes / ((ez + ep) * 1e-3) / 1e9, "unit": UNIT, "vblocks_per_gpu_per_step": Ve, "h2d_bytes_per_step": int(world * (h2d_z + h2d_p)), "d2h_bytes_per_step": int(world * (d2h_z + d2h_p)),
                "zip_ms": ez, "piz_ms": ep, "steps": Ke,
                "how": "Ke zip steps back to back, then Ke piz steps, host buffers in and out; the next step's text is staged and the previous step's results are fetched "
                       "(gzb_stage_upload / gzb_stage_fetch) while the current step's kernels run; the first upload and the last fetch of each run are not hidden and are in the time"}

@@ -629,7 +629,7 @@ class PipelinedHost:
     input buffers (zip) and two output buffers (piz) on the device are all it takes.  Host buffers are page-locked."""
 
     def __init__(self, path, data_host):
-        """data_host: host tensors [V, ...] seq, qual, Q_* (copied into page-locked buffers; the read-name buffers get the 16 bytes of
+        """data_host: host or device tensors [V, ...] seq, qual, Q_* (copied into page-locked buffers; the read-name buffers get the 16 bytes of
         slack per row that alloc_piz gives their decoded counterparts, so that one pair of device buffers serves as zip's input
         slots and as piz's output slots)"""
         self.path = path
@@ -637,9 +637,9 @@ class PipelinedHost:
         dev = path.dev
         self.width = {k: v.shape[1] for k, v in data_host.items()}
         self.H = {}
-        for k, v in data_host.items():
+        for k, v in data_host.items():                                       # (device tensors are copied straight into the page-locked buffers: no pageable copy in between)
             t = _pin(torch.zeros((v.shape[0], v.shape[1] + (16 if k in NAMES else 0)), dtype=torch.uint8))
-            t[:, :v.shape[1]] = v
+            t[:, :v.shape[1]].copy_(v)
             self.H[k] = t
         self.slots = [{k: torch.empty(v.shape, dtype=torch.uint8, device=dev) for k, v in self.H.items()} for _ in range(2)]
         self.h_packed = _pin(torch.empty((path.V, path.packed_len + 32), dtype=torch.uint8))
