@@ -66,6 +66,16 @@ __device__ __forceinline__ void acgt_pack_body (const uint8_t * __restrict__ seq
             #pragma unroll
             for (int k = 0; k < 8; k++) {
                 uint32_t cc = u[k], xo = 0;
+                // four bases at once when they are all upper-case A C G T (the rule): code = ((c >> 1) ^ (c >> 2)) & 3
+                // ('A' 0x41 -> 0, 'C' 0x43 -> 1, 'G' 0x47 -> 2, 'T' 0x54 -> 3), checked by mapping the codes back to characters
+                const uint32_t code4 = ((cc >> 1) ^ (cc >> 2)) & 0x03030303u;               // one 2-bit code per byte
+                const uint32_t sel = (code4 & 0x3u) | ((code4 >> 4) & 0x30u) | ((code4 >> 8) & 0x300u) | ((code4 >> 12) & 0x3000u);   // the four codes as byte selectors
+                if (__byte_perm (0x54474341u, 0, sel) == cc) {
+                    const uint32_t two = code4 | (code4 >> 6);                               // bytes 0,1 -> bits 0..3 ; bytes 2,3 -> bits 16..19
+                    word |= (uint64_t)((two | (two >> 12)) & 0xffu) << (8 * k);
+                    xe[k] = 0;
+                    continue;
+                }
                 #pragma unroll
                 for (int b = 0; b < 4; b++) {
                     uint32_t c = (cc >> (8 * b)) & 0xff;
