@@ -173,6 +173,7 @@ struct DqVb {                                      // device view of one VBlock'
     uint8_t  *E;               // normalised non-diverse concatenation
     uint8_t  *qual, *runs, *mplx, *divr;
     uint32_t *lens;            // [8]: qual_len, runs_len, mplx_len, divr_len, M (non-diverse total), last_line_len
+    void     *tiles, *toff;    // per tile of E: DqTile (k_dqs_count), DqTileOff (k_dqs_scan)
     uint32_t  n_lines;
     uint8_t   no_doms;
     uint8_t   pad[3];
@@ -181,56 +182,122 @@ struct DqVb {                                      // device view of one VBlock'
 };
 
 // ---- pass 1: per-line histogram, dom, diversity; per-dom histograms (codec_domq_calc_histogram :139-178)
+// One THREAD per line (a line is ~150 qualities, far too short for a warp: the earlier warp-per-line pass spent 2.2 warp
+// instructions per byte on match/ballot work).  The thread reads the aligned 16-byte blocks of its line, the next block in flight while
+// it counts the current one, and counts without a branch (32 lines in lock step diverge on anything that depends on the data, and
+// sm_100 has no byte-wise SIMD min/max): every byte increments the counter of its low 7 bits — 128 8-bit counters per thread in shared
+// memory (16 KB per CTA: the counting is a chain of dependent shared-memory read-modify-writes, only many resident warps hide it), laid
+// out so that the 32 lanes always touch 32 different banks; bytes of the first and last block that are not the line's
+// are turned into 0x7f first, a row nobody reads (like the rows below ' ').  One pass over the 95 rows then finds every line's arg-max
+// (ties -> the higher quality, :153-158) and, by ballot, the rows any of the warp's 32 lines uses; only those are added into the doms'
+// histograms — one REDUX per row when the 32 lines share their dom, which is the common case, accumulated per warp in shared memory
+// and flushed to the VBlock's histogram when the dom changes.  Lines above DQ_LONG_LINE qualities (the 8-bit counters) are counted by the warp as a whole.
 constexpr int LINES_PER_BLOCK = 512;
-__global__ void __launch_bounds__(256) k_domq_linehist (const DqVb *vbs, const uint32_t *blk_vb, const uint32_t *blk_first)
+constexpr uint32_t DQ_LONG_LINE = 255;
+__device__ __forceinline__ void dq_flush_acc (const DqVb &V, uint32_t *acc, uint32_t dom, int lane)
+{
+    for (int k = lane; k < 96; k += 32) {
+        const uint32_t c = acc[k];
+        if (c) { atomicAdd (&V.hist[k < NQ ? dom * NQ + k : NQ * NQ + dom], c); acc[k] = 0; }
+    }
+    __syncwarp ();
+}
+__global__ void __launch_bounds__(128) k_domq_linehist (const DqVb *vbs, const uint32_t *blk_vb, const uint32_t *blk_first)
 {
     const DqVb &V = vbs[blk_vb[blockIdx.x]];
     const uint32_t first = blk_first[blockIdx.x], last = min (first + LINES_PER_BLOCK, V.n_lines);
-    __shared__ uint32_t h2[NQ * NQ];
-    __shared__ uint32_t lwd[NQ];
-    __shared__ uint32_t lh[8][96];
+    __shared__ uint8_t cnt[128 * 128];                 // [character & 0x7f][lane][warp]
+    __shared__ uint32_t wacc[4][96];                   // per warp: [0..94] histogram of the lines of dom `cur`, [95] their number
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < NQ * NQ; i += 256) h2[i] = 0;
-    if (tid < NQ) lwd[tid] = 0;
+    for (int i = tid; i < 128 * 128 / 4; i += 128) reinterpret_cast<uint32_t *>(cnt)[i] = 0;
+    for (int i = lane; i < 96; i += 32) wacc[warp][i] = 0;
     __syncthreads ();
-    // A warp takes 64 consecutive lines, 32 at a time: the lanes fetch the 32 lines' lengths and offsets together (one memory
-    // latency per 32 lines instead of two dependent ones per line) and write the 32 results together.
-    for (uint32_t g0 = first + warp * (LINES_PER_BLOCK / 8); g0 < min (last, first + (warp + 1) * (LINES_PER_BLOCK / 8)); g0 += 32) {
-        const uint32_t gl = g0 + lane, gend = min (last, first + (warp + 1) * (LINES_PER_BLOCK / 8));
-        const uint32_t my_len = gl < gend ? V.line_len[gl] : 0;
-        const uint64_t my_off = gl < gend ? V.line_off[gl] : 0;
+    uint8_t *const mine = cnt + 4 * lane + warp;                                // counter of character c: mine[c * 128]
+    uint32_t *const acc = wacc[warp];
+    uint32_t cur = 0;
+    for (uint32_t g0 = first + warp * 32; g0 < last; g0 += 128) {
+        const uint32_t gl = g0 + lane;
+        const uint32_t len = gl < last ? V.line_len[gl] : 0;
+        const uint64_t off = gl < last ? V.line_off[gl] : 0;
+        const bool own = len && len <= DQ_LONG_LINE;
+        if (own) {
+            const uint32_t skip = (uint32_t)((uintptr_t)(V.txt + off) & 15), end = skip + len, nblk = (end + 15) >> 4;
+            const uint4 *blk = reinterpret_cast<const uint4 *>(V.txt + off - skip);   // (an aligned block that holds a byte of the line lies inside the line's allocation)
+            uint4 nxt = blk[0];
+            for (uint32_t b = 0; b < nblk; b++) {
+                const uint4 q = nxt;
+                if (b + 1 < nblk) nxt = blk[b + 1];
+                uint32_t w[4] = { q.x, q.y, q.z, q.w };
+                if (b == 0 || b + 1 == nblk) {
+                    #pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int p0 = (int)(b * 16) + 4 * j;
+                        const int lead = max (0, min (4, (int)skip - p0)), upto = max (0, min (4, (int)end - p0));      // bytes [lead, upto) of the word are the line's
+                        const uint32_t keep = (uint32_t)((0xffffffffull << (8 * lead)) & ~(0xffffffffull << (8 * upto)));
+                        w[j] = (w[j] & keep) | (0x7f7f7f7fu & ~keep);
+                    }
+                }
+                #pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    mine[(w[j] & 0x7f) * 128]++; mine[((w[j] >> 8) & 0x7f) * 128]++; mine[((w[j] >> 16) & 0x7f) * 128]++; mine[((w[j] >> 24) & 0x7f) * 128]++;
+                }
+            }
+        }
+        // arg-max of every line, and the rows in use
+        uint32_t bc = 0, bq = 0, used[3] = { 0, 0, 0 };
+        #pragma unroll
+        for (int k = 0; k < NQ; k++) {
+            const uint32_t c = own ? mine[(k + FIRST_Q) * 128] : 0;
+            if (c >= bc) { bc = c; bq = k; }
+            if (__any_sync (0xffffffffu, c)) used[k >> 5] |= 1u << (k & 31);
+        }
         uint32_t my_dom = 0, my_div = 0;
-        const uint32_t cnt = min (32u, gend - g0);
-        for (uint32_t t = 0; t < cnt; t++) {
-            const uint32_t len = __shfl_sync (0xffffffffu, my_len, t);
-            if (!len) continue;                                              // (dom 0, not diverse)
-            const uint8_t *q = V.txt + __shfl_sync (0xffffffffu, my_off, t);
-            for (int i = lane; i < 96; i += 32) lh[warp][i] = 0;
-            __syncwarp ();
-            for (uint32_t i0 = 0; i0 < len; i0 += 32) {                       // equal qualities of a 32-byte chunk are counted once, by their lowest lane
+        if (own) { my_dom = bq; my_div = (100u * bc / len < 85u) ? 1 : 0; }                       // DOMQ_THRESHOLD (:141,160)
+        const uint32_t act = __ballot_sync (0xffffffffu, own);
+        if (act) {
+            const uint32_t d0 = __shfl_sync (0xffffffffu, my_dom, __ffs (act) - 1);
+            const bool uniform = __ballot_sync (0xffffffffu, own && my_dom == d0) == act;
+            if (uniform && d0 != cur) { dq_flush_acc (V, acc, cur, lane); cur = d0; }
+            #pragma unroll
+            for (int wd = 0; wd < 3; wd++)
+                for (uint32_t m = used[wd]; m; m &= m - 1) {
+                    const uint32_t k = wd * 32 + __ffs (m) - 1;
+                    uint32_t c = 0;
+                    if (own) { c = mine[(k + FIRST_Q) * 128]; mine[(k + FIRST_Q) * 128] = 0; }
+                    if (uniform) { const uint32_t sum = __reduce_add_sync (0xffffffffu, c); if (lane == 0) acc[k] += sum; }
+                    else if (c) atomicAdd (&V.hist[my_dom * NQ + k], c);
+                }
+            if (uniform) { if (lane == 0) acc[95] += __popc (act); __syncwarp (); }
+            else if (own) atomicAdd (&V.hist[NQ * NQ + my_dom], 1u);
+        }
+        // the long lines of these 32, one at a time, by the whole warp: equal qualities of a 32-byte chunk are counted once, by their lowest lane
+        uint32_t longs = __ballot_sync (0xffffffffu, len > DQ_LONG_LINE);
+        if (longs) { dq_flush_acc (V, acc, cur, lane); }
+        while (longs) {
+            const int t = __ffs (longs) - 1; longs &= longs - 1;
+            const uint32_t ll = __shfl_sync (0xffffffffu, len, t);
+            const uint8_t *q = V.txt + __shfl_sync (0xffffffffu, off, t);
+            for (uint32_t i0 = 0; i0 < ll; i0 += 32) {
                 const uint32_t i = i0 + lane;
-                const uint32_t v = i < len ? (uint32_t)q[i] - FIRST_Q : 0x100u + lane;
+                const uint32_t v = i < ll ? (uint32_t)q[i] - FIRST_Q : 0x100u + lane;
                 const uint32_t peers = __match_any_sync (0xffffffffu, v);
-                if (i < len && (peers & ((1u << lane) - 1)) == 0) lh[warp][v] += __popc (peers);
+                if (v < (uint32_t)NQ && (peers & ((1u << lane) - 1)) == 0) acc[v] += __popc (peers);
                 __syncwarp ();
             }
-            // dom = arg-max, ties -> the higher quality (:153-158)
-            uint32_t bc = 0, bq = 0;
-            for (int k = lane; k < NQ; k += 32) { uint32_t c = lh[warp][k]; if (c >= bc) { bc = c; bq = k; } }
+            uint32_t lc = 0, lq = 0;
+            for (int k = lane; k < NQ; k += 32) { uint32_t c = acc[k]; if (c >= lc) { lc = c; lq = k; } }
             for (int o = 16; o; o >>= 1) {
-                uint32_t oc = __shfl_xor_sync (0xffffffffu, bc, o), oq = __shfl_xor_sync (0xffffffffu, bq, o);
-                if (oc > bc || (oc == bc && oq > bq)) { bc = oc; bq = oq; }
+                uint32_t oc = __shfl_xor_sync (0xffffffffu, lc, o), oq = __shfl_xor_sync (0xffffffffu, lq, o);
+                if (oc > lc || (oc == lc && oq > lq)) { lc = oc; lq = oq; }
             }
-            if ((uint32_t)lane == t) { my_dom = bq; my_div = (100u * bc / len < 85u) ? 1 : 0; }   // DOMQ_THRESHOLD (:141,160)
-            if (lane == 0) atomicAdd (&lwd[bq], 1u);
-            for (int k = lane; k < NQ; k += 32) { uint32_t c = lh[warp][k]; if (c) atomicAdd (&h2[bq * NQ + k], c); }
+            if (lane == t) { my_dom = lq; my_div = (100u * lc / ll < 85u) ? 1 : 0; }
+            if (lane == 0) acc[95] = 1;
             __syncwarp ();
+            dq_flush_acc (V, acc, lq, lane);
         }
-        if (gl < gend) { V.line_dom[gl] = (uint8_t)my_dom; V.line_diverse[gl] = (uint8_t)my_div; }
+        if (gl < last) { V.line_dom[gl] = (uint8_t)my_dom; V.line_diverse[gl] = (uint8_t)my_div; }
     }
-    __syncthreads ();
-    for (int i = tid; i < NQ * NQ; i += 256) if (h2[i]) atomicAdd (&V.hist[i], h2[i]);
-    if (tid < NQ && lwd[tid]) atomicAdd (&V.hist[NQ * NQ + tid], lwd[tid]);
+    dq_flush_acc (V, acc, cur, lane);
 }
 
 // ---- block scan helpers (512 threads)
@@ -321,70 +388,125 @@ __global__ void __launch_bounds__(256) k_domq_normalize (const DqVb *vbs, const 
     }
 }
 
-// ---- pass 3: stream split over the non-diverse concatenation (:421-500).  One CTA per VB walks E in tiles of
-// 512 threads x 8 elements, carrying (QUAL position, DOMQRUNS position, index of the last non-dom).
+// ---- pass 3: stream split over the non-diverse concatenation E (:421-500), tile-parallel.  What an element of E emits depends on
+// what precedes it only through (a) whether the previous element is a dom, which is E[i-1] itself, and (b) for a non-dom that ends a dom
+// run, where the previous non-dom is — inside a tile for every non-dom but the tile's first.  So: k_dqs_count sums each tile's
+// QUAL / DOMQRUNS bytes leaving the tile's first run open, k_dqs_scan (one CTA per VBlock) closes the open runs with a running maximum over
+// the tiles, turns the sums into offsets and emits the trailing run, and k_dqs_write writes every tile at its offsets.
+constexpr uint32_t DQ_TILE = 16384;                   // 256 threads x 64 elements
+struct DqTile { uint32_t cq, cr, first, last1; };     // QUAL bytes; DOMQRUNS bytes without the first run's; index of the first non-dom with a run open before it (or ~0); index + 1 of the last non-dom (0 = none)
+struct DqTileOff { uint32_t q, r, ln, first; };       // offsets into QUAL / DOMQRUNS, index + 1 of the last non-dom before the tile, DqTile.first
+
 __device__ __forceinline__ uint32_t put_run_bytes (uint8_t *runs, uint32_t pos, uint32_t r)      // codec_domq_add_runs :368-377
 {
     while (r) { uint32_t sub = r < 254 ? r : 254; runs[pos++] = (uint8_t)(r <= 254 ? sub : 255); r -= sub; }
     return pos;
 }
 
-__global__ void __launch_bounds__(512) k_domq_split (const DqVb *vbs)
+// The 64 elements of one thread as bit masks (bit j = element i0 + j): `nd` the non-doms, `ends` the non-doms that end a dom run (their
+// predecessor is a dom), and the index + 1 of the last non-dom of the tile before them (0 = none in this tile).  256 threads.  sm: 17 words.
+struct DqChunk { uint64_t nd, ends; uint32_t i0, tile_last, tile_last_total; };
+// bit k = byte k of w is not 0, for bytes <= 0x80 (E holds ranks < 95): no carry leaves a byte; the multiplication gathers bits 0, 8, 16, 24 at 24..27
+__device__ __forceinline__ uint32_t dq_nonzero4 (uint32_t w) { return (((((w + 0x7f7f7f7fu) & 0x80808080u) >> 7) * 0x01020408u) >> 24) & 0xf; }
+__device__ __forceinline__ uint64_t dq_nonzero16 (const uint4 q) { return dq_nonzero4 (q.x) | (dq_nonzero4 (q.y) << 4) | (dq_nonzero4 (q.z) << 8) | (dq_nonzero4 (q.w) << 12); }
+__device__ DqChunk dq_load_chunk (const DqVb &V, uint32_t M, uint32_t base, uint32_t *sm, uint8_t *s_last)
+{
+    DqChunk c;
+    c.i0 = base + threadIdx.x * 64;
+    const uint32_t n = c.i0 < M ? min (64u, M - c.i0) : 0;
+    c.nd = 0;
+    if (n) {                                                             // E is 256-byte aligned and padded by 64
+        const uint4 *p = reinterpret_cast<const uint4 *>(V.E + c.i0);
+        const uint4 q0 = p[0], q1 = p[1], q2 = p[2], q3 = p[3];
+        c.nd = dq_nonzero16 (q0) | (dq_nonzero16 (q1) << 16) | (dq_nonzero16 (q2) << 32) | (dq_nonzero16 (q3) << 48);
+        if (n < 64) c.nd &= (1ull << n) - 1;
+    }
+    s_last[threadIdx.x] = (uint8_t)(n < 64 || (c.nd >> 63));              // is my last element a non-dom (past the end counts as one)
+    const uint32_t my_last = c.nd ? c.i0 + 64 - __clzll ((long long)c.nd) : 0;
+    c.tile_last = block_excl_max (my_last, sm, &c.tile_last_total);      // (its barriers also publish s_last)
+    const uint32_t prev_dom = threadIdx.x ? !s_last[threadIdx.x - 1] : (base ? V.E[base - 1] == 0 : 0);
+    c.ends = c.nd & ~((c.nd << 1) | (prev_dom ? 0 : 1));
+    return c;
+}
+// QUAL bytes << 16 | DOMQRUNS bytes of the chunk.  A run that ends at a non-dom of this chunk began inside the chunk (one byte) unless it is
+// the chunk's first non-dom: then it reaches back to `ln`, or — ln = 0 — to an earlier tile: *open = its index, not counted.
+__device__ __forceinline__ uint32_t dq_chunk_bytes (const DqChunk &c, uint32_t ln, uint32_t *open)
+{
+    const uint32_t n_ends = __popcll (c.ends);
+    uint32_t cq = 2 * __popcll (c.nd) - n_ends, cr = n_ends;
+    if (c.ends && (c.ends & (0ull - c.ends)) == (c.nd & (0ull - c.nd))) {     // the first run end is the first non-dom
+        const uint32_t idx = c.i0 + __ffsll ((long long)c.ends) - 1;
+        if (ln) cr += (idx - ln + 253) / 254 - 1;
+        else { cr -= 1; *open = idx; }
+    }
+    return (cq << 16) | cr;
+}
+
+__global__ void __launch_bounds__(256) k_dqs_count (const DqVb *vbs)
+{
+    const DqVb &V = vbs[blockIdx.y];
+    const uint32_t M = V.lens[4], base = blockIdx.x * DQ_TILE;
+    if (base >= M) return;
+    __shared__ uint32_t sm[17];
+    __shared__ uint8_t s_last[256];
+    __shared__ uint32_t s_first;
+    if (threadIdx.x == 0) s_first = 0xffffffffu;
+    const DqChunk c = dq_load_chunk (V, M, base, sm, s_last);
+    uint32_t open = 0xffffffffu, tot;
+    const uint32_t mine = dq_chunk_bytes (c, c.tile_last, &open);
+    if (open != 0xffffffffu) s_first = open;                              // at most one thread: the one with the tile's first non-dom
+    block_excl_sum (mine, sm, &tot);
+    if (threadIdx.x == 0) reinterpret_cast<DqTile *>(V.tiles)[blockIdx.x] = DqTile { tot >> 16, tot & 0xffff, s_first, c.tile_last_total };
+}
+
+__global__ void __launch_bounds__(512) k_dqs_scan (const DqVb *vbs)
 {
     const DqVb &V = vbs[blockIdx.x];
+    const DqTile *T = reinterpret_cast<const DqTile *>(V.tiles); DqTileOff *O = reinterpret_cast<DqTileOff *>(V.toff);
     __shared__ uint32_t sm[17];
-    __shared__ uint8_t s_last[512];
-    const uint32_t M = V.lens[4];
-    const uint8_t no_doms = V.no_doms;
-    uint32_t qpos = 0, rpos = 0, last_nd1 = 0;          // last_nd1 = (index of last non-dom so far) + 1, 0 = none
-    uint32_t carry_prev_dom = 0;                        // was the element before this tile a dom?
-    for (uint32_t base = 0; base < M; base += 4096) {
-        const uint32_t i0 = base + threadIdx.x * 8;
-        uint8_t e[8];
-        #pragma unroll
-        for (int j = 0; j < 8; j++) e[j] = (i0 + j < M) ? V.E[i0 + j] : 0xff;     // 0xff = past the end (treated as non-dom, never written)
-        s_last[threadIdx.x] = e[7];
-        __syncthreads ();
-        uint32_t prev_dom = threadIdx.x ? (s_last[threadIdx.x - 1] == 0) : carry_prev_dom;
-        // local: last non-dom index (+1) within my 8
-        uint32_t my_last = 0;
-        #pragma unroll
-        for (int j = 0; j < 8; j++) if (e[j] != 0 && i0 + j < M) my_last = i0 + j + 1;
-        uint32_t tot_last;
-        uint32_t start_last = max (block_excl_max (my_last, sm, &tot_last), last_nd1);
-        // count bytes
-        uint32_t cq = 0, cr = 0, ln = start_last, pd = prev_dom;
-        #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            if (i0 + j >= M) break;
-            if (e[j] == 0) { pd = 1; continue; }
-            if (pd) { uint32_t r = i0 + j - ln; cr += (r + 253) / 254; cq += 1; }
-            else cq += 2;
-            ln = i0 + j + 1; pd = 0;
-        }
-        uint32_t tq, tr;
-        uint32_t oq = block_excl_sum (cq, sm, &tq) + qpos;
-        uint32_t orr = block_excl_sum (cr, sm, &tr) + rpos;
-        // write
-        ln = start_last; pd = prev_dom;
-        #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            if (i0 + j >= M) break;
-            if (e[j] == 0) { pd = 1; continue; }
-            if (pd) orr = put_run_bytes (V.runs, orr, i0 + j - ln);
-            else V.qual[oq++] = no_doms;
-            V.qual[oq++] = e[j];
-            ln = i0 + j + 1; pd = 0;
-        }
-        qpos += tq; rpos += tr; last_nd1 = max (last_nd1, tot_last);
-        carry_prev_dom = (s_last[511] == 0);
-        __syncthreads ();
+    const uint32_t M = V.lens[4], n_tiles = (M + DQ_TILE - 1) / DQ_TILE;
+    uint32_t qpos = 0, rpos = 0, last_nd1 = 0, t;
+    for (uint32_t b = 0; b < n_tiles; b += 512) {
+        const uint32_t k = b + threadIdx.x;
+        DqTile d = k < n_tiles ? T[k] : DqTile { 0, 0, 0xffffffffu, 0 };
+        const uint32_t ln = max (block_excl_max (d.last1, sm, &t), last_nd1); const uint32_t tl = t;
+        if (d.first != 0xffffffffu) d.cr += (d.first - ln + 253) / 254;
+        const uint32_t oq = block_excl_sum (d.cq, sm, &t) + qpos; const uint32_t tq = t;
+        const uint32_t orr = block_excl_sum (d.cr, sm, &t) + rpos; const uint32_t tr = t;
+        if (k < n_tiles) O[k] = DqTileOff { oq, orr, ln, d.first };
+        qpos += tq; rpos += tr; last_nd1 = max (last_nd1, tl);
     }
     if (threadIdx.x == 0) {
         uint32_t runlen = M - last_nd1;                                            // trailing dom run (:473-482)
-        if (runlen && (rpos || runlen < V.lens[5])) { rpos = put_run_bytes (V.runs, rpos, runlen); V.qual[qpos++] = no_doms; }
+        if (runlen && (rpos || runlen < V.lens[5])) { rpos = put_run_bytes (V.runs, rpos, runlen); V.qual[qpos++] = V.no_doms; }
         if (!qpos) V.qual[qpos++] = 'X';                                           // :497-500
         V.lens[0] = qpos; V.lens[1] = rpos;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_dqs_write (const DqVb *vbs)
+{
+    const DqVb &V = vbs[blockIdx.y];
+    const uint32_t M = V.lens[4], base = blockIdx.x * DQ_TILE;
+    if (base >= M) return;
+    __shared__ uint32_t sm[17];
+    __shared__ uint8_t s_last[256];
+    const DqTileOff o = reinterpret_cast<const DqTileOff *>(V.toff)[blockIdx.x];
+    const uint8_t no_doms = V.no_doms;
+    const DqChunk c = dq_load_chunk (V, M, base, sm, s_last);
+    // as counted by k_dqs_count (the tile's open run left out), so that the offsets agree: that run's bytes go to every chunk after it
+    uint32_t open = 0xffffffffu, t;
+    const uint32_t mine = dq_chunk_bytes (c, c.tile_last, &open);
+    const uint32_t ex = block_excl_sum (mine, sm, &t);
+    uint32_t oq = o.q + (ex >> 16), orr = o.r + (ex & 0xffff);
+    if (o.first != 0xffffffffu && o.first < c.i0) orr += (o.first - o.ln + 253) / 254;
+    uint32_t ln = max (c.tile_last, o.ln);
+    for (uint64_t m = c.nd; m; m &= m - 1) {
+        const int j = __ffsll ((long long)m) - 1;
+        if ((c.ends >> j) & 1) orr = put_run_bytes (V.runs, orr, c.i0 + j - ln);
+        else V.qual[oq++] = no_doms;
+        V.qual[oq++] = V.E[c.i0 + j];                                     // (in L1 since dq_load_chunk)
+        ln = c.i0 + j + 1;
     }
 }
 
@@ -698,7 +820,7 @@ namespace {
 struct DqLayout {
     std::vector<DqVb> h;           // host copies of the device descriptors
     DqVb *d_vbs = nullptr;
-    uint32_t *d_bvb = nullptr, *d_bfirst = nullptr; uint32_t n_blocks = 0;
+    uint32_t *d_bvb = nullptr, *d_bfirst = nullptr; uint32_t n_blocks = 0, max_tiles = 0;
     uint32_t *d_hist = nullptr, *d_lens = nullptr;   // [n_vbs][NQ*NQ+NQ] histograms, [n_vbs][8] stream lengths
     size_t pin_vbs = 0, pin_vbs_bytes = 0, pin_blocks = 0, pin_landing = 0;   // offsets into the engine's pinned staging: descriptors | line blocks | histograms, lengths
     std::vector<uint8_t *> d_linedom, d_linediv;
@@ -730,7 +852,9 @@ int dq_stage (gzb_engine *e, gzb_domq_vb *vbs, uint32_t n_vbs, bool devptr, bool
             D.line_diverse = devptr ? S.line_diverse : c.take<uint8_t> (S.n_lines + 1);
             D.hist   = L.d_hist ? L.d_hist + (size_t)v * (NQ * NQ + NQ) : nullptr;
             D.nd_off = c.take<uint32_t> (S.n_lines + 1); D.dv_off = c.take<uint32_t> (S.n_lines + 1); D.mx_idx = c.take<uint32_t> (S.n_lines + 1);
-            D.E      = c.take<uint8_t> (tot + 16);
+            D.E      = c.take<uint8_t> (tot + 64);
+            D.tiles  = c.take<DqTile> (tot / DQ_TILE + 2); D.toff = c.take<DqTileOff> (tot / DQ_TILE + 2);
+            L.max_tiles = std::max (L.max_tiles, (uint32_t)(tot / DQ_TILE + 1));
             D.lens   = L.d_lens ? L.d_lens + (size_t)v * 8 : nullptr;
             D.qual   = (devptr || outdev) ? (uint8_t *)S.qual : c.take<uint8_t> (2 * tot + 16);
             D.runs   = (devptr || outdev) ? (uint8_t *)S.runs : c.take<uint8_t> (tot + 16);
@@ -769,6 +893,7 @@ extern "C" int gzb_domq_prepare (gzb_engine *e, gzb_domq_vb *vbs, uint32_t n_vbs
 {
     if (!e || !vbs) return GZB_E_BADARG;
     if (!n_vbs) return GZB_OK;
+    if (n_vbs > 65535) { e->err = "gzb_domq_prepare: at most 65535 VBlocks per call"; return GZB_E_BADARG; }
     cudaSetDevice (e->device);
     const bool devptr = flags & GZB_DEVICE_PTRS, outdev = flags & GZB_OUT_DEVICE;
     cudaStream_t st = e->stream;
@@ -792,7 +917,7 @@ extern "C" int gzb_domq_prepare (gzb_engine *e, gzb_domq_vb *vbs, uint32_t n_vbs
     CK (cudaMemsetAsync (L->d_hist, 0, hist_bytes, st));
     memcpy (e->pin + L->pin_vbs, L->h.data (), n_vbs * sizeof (DqVb));
     CK (cudaMemcpyAsync (L->d_vbs, e->pin + L->pin_vbs, n_vbs * sizeof (DqVb), cudaMemcpyHostToDevice, st));
-    if (L->n_blocks) { k_domq_linehist<<<L->n_blocks, 256, 0, st>>>(L->d_vbs, L->d_bvb, L->d_bfirst); e->launches++; }
+    if (L->n_blocks) { k_domq_linehist<<<L->n_blocks, 128, 0, st>>>(L->d_vbs, L->d_bvb, L->d_bfirst); e->launches++; }
     CK (cudaMemcpyAsync (hist, L->d_hist, hist_bytes, cudaMemcpyDeviceToHost, st));
     CK (cudaStreamSynchronize (st));
 
@@ -851,7 +976,9 @@ extern "C" int gzb_domq_split (gzb_engine *e, gzb_domq_vb *vbs, uint32_t n_vbs, 
     DqLayout *L = reinterpret_cast<DqLayout *>(e->dq_session);
     if (!L || e->dq_n_vbs != n_vbs || e->dq_devptr != devptr) { e->err = "gzb_domq_split must follow gzb_domq_prepare on the same batch"; return GZB_E_BADARG; }
     cudaStream_t st = e->stream;
-    k_domq_split<<<n_vbs, 512, 0, st>>>(L->d_vbs); e->launches++;
+    k_dqs_count<<<dim3 (L->max_tiles, n_vbs), 256, 0, st>>>(L->d_vbs);
+    k_dqs_scan<<<n_vbs, 512, 0, st>>>(L->d_vbs);
+    k_dqs_write<<<dim3 (L->max_tiles, n_vbs), 256, 0, st>>>(L->d_vbs); e->launches += 3;
     int rc = engine_reserve (e, 0, (size_t)n_vbs * 32 + 256); if (rc) return rc;
     uint32_t *const lens = reinterpret_cast<uint32_t *>(e->pin);
     CK (cudaMemcpyAsync (lens, L->d_lens, (size_t)n_vbs * 32, cudaMemcpyDeviceToHost, st));

@@ -90,6 +90,8 @@ namespace simt { inline uint32_t mask_or_full () { return 0xffffffffu; } inline 
 template <class T> static inline T __ldg (const T *p) { return *p; }
 static inline int      __popc (uint32_t x) { return __builtin_popcount (x); }
 static inline int      __popcll (uint64_t x) { return __builtin_popcountll (x); }
+static inline int      __ffsll (long long x) { return __builtin_ffsll (x); }
+static inline int      __clzll (long long x) { return x ? __builtin_clzll ((unsigned long long)x) : 64; }
 static inline int      __ffs (int x) { return __builtin_ffs (x); }
 static inline int      __clz (int x) { return x ? __builtin_clz ((uint32_t)x) : 32; }
 static inline uint32_t __brev (uint32_t x) { uint32_t r = 0; for (int i = 0; i < 32; i++) r |= ((x >> i) & 1u) << (31 - i); return r; }
@@ -113,6 +115,8 @@ static inline uint32_t __byte_perm (uint32_t x, uint32_t y, uint32_t s)        /
 static inline uint32_t __vcmpeq4 (uint32_t a, uint32_t b) { uint32_t r = 0; for (int i = 0; i < 4; i++) if (((a >> (8 * i)) & 0xff) == ((b >> (8 * i)) & 0xff)) r |= 0xffu << (8 * i); return r; }
 static inline uint32_t __vsub4 (uint32_t a, uint32_t b) { uint32_t r = 0; for (int i = 0; i < 4; i++) r |= ((((a >> (8 * i)) & 0xff) - ((b >> (8 * i)) & 0xff)) & 0xff) << (8 * i); return r; }
 static inline uint32_t __vcmpne4 (uint32_t a, uint32_t b) { return ~__vcmpeq4 (a, b); }
+static inline uint32_t __vminu4 (uint32_t a, uint32_t b) { uint32_t r = 0; for (int i = 0; i < 4; i++) { uint32_t x = (a >> (8 * i)) & 0xff, y = (b >> (8 * i)) & 0xff; r |= (x < y ? x : y) << (8 * i); } return r; }
+static inline uint32_t __vmaxu4 (uint32_t a, uint32_t b) { uint32_t r = 0; for (int i = 0; i < 4; i++) { uint32_t x = (a >> (8 * i)) & 0xff, y = (b >> (8 * i)) & 0xff; r |= (x > y ? x : y) << (8 * i); } return r; }
 static inline uint32_t __vcmpgtu4 (uint32_t a, uint32_t b) { uint32_t r = 0; for (int i = 0; i < 4; i++) if (((a >> (8 * i)) & 0xff) > ((b >> (8 * i)) & 0xff)) r |= 0xffu << (8 * i); return r; }
 static inline float    __uint_as_float (uint32_t u) { float f; memcpy (&f, &u, 4); return f; }
 static inline uint32_t __float_as_uint (float f) { uint32_t u; memcpy (&u, &f, 4); return u; }

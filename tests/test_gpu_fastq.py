@@ -101,6 +101,36 @@ def test_domq_edges(eng):
     _check_domq(eng, vbs)
 
 
+def test_domq_tiles_and_long_lines(eng):
+    """The split works on 16384-element tiles (64-element chunks per thread) of the non-diverse concatenation and the histogram pass
+    gives lines above 4096 qualities to a whole warp: runs that cross one or several tile borders, non-doms on either side of a border, a tile of doms only, a trailing
+    run longer than a tile, long lines beside short ones (codec_domq.c:139-178, 421-500)."""
+    rng = np.random.default_rng(77)
+    vbs = []
+    for case in range(6):
+        n = 40000
+        q = np.full(n, ord("F"), np.uint8)
+        if case == 0:   pos = [63, 64, 127, 129, 16383, 16384, 32767, 32769, 39000]   # non-doms at chunk and tile borders
+        elif case == 1: pos = [0, 36000]                                        # one run across two tile borders, then a trailing one
+        elif case == 2: pos = [16384 * 2 - 1]                                   # a run ending exactly at a tile's last element
+        elif case == 3: pos = list(range(16380, 16390)) + list(range(60, 70)) + [32768]   # literal strings across the borders
+        elif case == 4: pos = sorted(rng.choice(n, 300, replace=False).tolist())
+        else:           pos = [n - 1]                                           # no trailing run
+        q[pos] = rng.choice(np.frombuffer(b"#,:", np.uint8), len(pos))
+        vbs.append((q,) + line_table(n // 200, 200))
+    # long lines (one warp each) between short ones, one of them diverse, one with a different dom
+    lens = [150, 5000, 150, 256, 9000, 257, 4096, 4097, 300, 20000, 1000, 1, 255]
+    parts = []
+    for i, L in enumerate(lens):
+        if i == 4:   line = rng.choice(np.frombuffer(b"#,:F", np.uint8), L)                         # diverse
+        elif i == 7: line = np.where(rng.random(L) < 0.9, ord(":"), ord("F")).astype(np.uint8)       # dom ':'
+        else:        line = np.where(rng.random(L) < 0.93, ord("F"), ord(",")).astype(np.uint8)
+        parts.append(line.astype(np.uint8))
+    off = np.cumsum([0] + lens[:-1]).astype(np.uint64)
+    vbs.append((np.concatenate(parts), off, np.array(lens, np.uint32)))
+    _check_domq(eng, vbs)
+
+
 def test_domq_full_vb_properties(eng):
     """BASELINE-size VBlock (92K reads x 150): round trip + stream-length identities instead of the slow oracle decode"""
     _, q = fastq_vb(92000, 150, 77)
