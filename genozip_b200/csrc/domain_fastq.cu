@@ -184,16 +184,22 @@ struct DqVb {                                      // device view of one VBlock'
 // ---- pass 1: per-line histogram, dom, diversity; per-dom histograms (codec_domq_calc_histogram :139-178)
 // One THREAD per line (a line is ~150 qualities, far too short for a warp: the earlier warp-per-line pass spent 2.2 warp
 // instructions per byte on match/ballot work).  The thread reads the aligned 16-byte blocks of its line, the next block in flight while
-// it counts the current one, and counts without a branch (32 lines in lock step diverge on anything that depends on the data, and
-// sm_100 has no byte-wise SIMD min/max): every byte increments the counter of its low 7 bits — 128 8-bit counters per thread in shared
-// memory (16 KB per CTA: the counting is a chain of dependent shared-memory read-modify-writes, only many resident warps hide it), laid
-// out so that the 32 lanes always touch 32 different banks; bytes of the first and last block that are not the line's
-// are turned into 0x7f first, a row nobody reads (like the rows below ' ').  One pass over the 95 rows then finds every line's arg-max
-// (ties -> the higher quality, :153-158) and, by ballot, the rows any of the warp's 32 lines uses; only those are added into the doms'
-// histograms — one REDUX per row when the 32 lines share their dom, which is the common case, accumulated per warp in shared memory
-// and flushed to the VBlock's histogram when the dom changes.  Lines above DQ_LONG_LINE qualities (the 8-bit counters) are counted by the warp as a whole.
+// it counts the current one, and counts without a branch (32 lines in lock step diverge on anything that depends on the data — a
+// version that kept the current run in registers executed every lane's run ends — and sm_100 has no byte-wise SIMD min/max): every byte
+// is one shared-memory atomic add whose result nobody waits for.  A thread owns 64 words: character c adds 1 << 16 * (c >> 6 & 1) to
+// word c & 63, i.e. two 16-bit counters per word, the 32 lanes always in 32 different banks; bytes of the first and last block that are
+// not the line's are turned into 0x7f first, a counter nobody reads (like those below ' ').  One pass over the 95 counters then finds
+// every line's arg-max (ties -> the higher quality, :153-158) and, by ballot, the qualities any of the warp's 32 lines uses; only
+// those are added into the doms' histograms — one REDUX per quality when the 32 lines share their dom, which is the common case,
+// accumulated per warp in shared memory and flushed to the VBlock's histogram when the dom changes.  Lines above DQ_LONG_LINE
+// qualities are counted by the warp as a whole.
+// Measured (profiles/r02_domq_kernels.md, r02_domq_full.md; 128 VBlocks = 1.77 GB per launch): 2.65 ms with half the instructions of the
+// warp-per-line pass (5.3 ms in round 1's terms per 128 VBlocks: 2.64 ms per 64).  8-bit load / add / store counters (lines <= 255 only)
+// took 2.45 ms at twice the resident warps: the pass is bound by L1/shared-memory wavefronts (a 16-byte load per lane touches 32 lines,
+// plus one or two shared-memory accesses per byte), not by occupancy or issue slots — ncu: wavefront pipe 46 %, short scoreboard 14 and
+// mio throttle 8 of 34 stall cycles per instruction.
 constexpr int LINES_PER_BLOCK = 512;
-constexpr uint32_t DQ_LONG_LINE = 255;
+constexpr uint32_t DQ_LONG_LINE = 4096;
 __device__ __forceinline__ void dq_flush_acc (const DqVb &V, uint32_t *acc, uint32_t dom, int lane)
 {
     for (int k = lane; k < 96; k += 32) {
@@ -206,15 +212,17 @@ __global__ void __launch_bounds__(128) k_domq_linehist (const DqVb *vbs, const u
 {
     const DqVb &V = vbs[blk_vb[blockIdx.x]];
     const uint32_t first = blk_first[blockIdx.x], last = min (first + LINES_PER_BLOCK, V.n_lines);
-    __shared__ uint8_t cnt[128 * 128];                 // [character & 0x7f][lane][warp]
+    __shared__ uint32_t cnt[64 * 128];                 // [character & 63][thread]: low half = that character, high half = character + 64
     __shared__ uint32_t wacc[4][96];                   // per warp: [0..94] histogram of the lines of dom `cur`, [95] their number
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < 128 * 128 / 4; i += 128) reinterpret_cast<uint32_t *>(cnt)[i] = 0;
+    for (int i = tid; i < 64 * 128; i += 128) cnt[i] = 0;
     for (int i = lane; i < 96; i += 32) wacc[warp][i] = 0;
     __syncthreads ();
-    uint8_t *const mine = cnt + 4 * lane + warp;                                // counter of character c: mine[c * 128]
+    uint32_t *const mine = cnt + tid;                  // mine[(c & 63) * 128]
     uint32_t *const acc = wacc[warp];
     uint32_t cur = 0;
+    #define DQ_COUNT(c_) { const uint32_t b_ = (c_); atomicAdd (&mine[(b_ & 63) * 128], 1u << ((b_ & 64) >> 2)); }
+    #define DQ_COUNTER(k_) ((mine[(((k_) + FIRST_Q) & 63) * 128] >> ((((k_) + FIRST_Q) & 64) >> 2)) & 0xffff)
     for (uint32_t g0 = first + warp * 32; g0 < last; g0 += 128) {
         const uint32_t gl = g0 + lane;
         const uint32_t len = gl < last ? V.line_len[gl] : 0;
@@ -238,16 +246,15 @@ __global__ void __launch_bounds__(128) k_domq_linehist (const DqVb *vbs, const u
                     }
                 }
                 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    mine[(w[j] & 0x7f) * 128]++; mine[((w[j] >> 8) & 0x7f) * 128]++; mine[((w[j] >> 16) & 0x7f) * 128]++; mine[((w[j] >> 24) & 0x7f) * 128]++;
-                }
+                for (int j = 0; j < 4; j++) { DQ_COUNT (w[j] & 0x7f); DQ_COUNT ((w[j] >> 8) & 0x7f); DQ_COUNT ((w[j] >> 16) & 0x7f); DQ_COUNT ((w[j] >> 24) & 0x7f); }
             }
         }
-        // arg-max of every line, and the rows in use
+        __syncwarp ();
+        // arg-max of every line, and the qualities in use
         uint32_t bc = 0, bq = 0, used[3] = { 0, 0, 0 };
         #pragma unroll
         for (int k = 0; k < NQ; k++) {
-            const uint32_t c = own ? mine[(k + FIRST_Q) * 128] : 0;
+            const uint32_t c = own ? DQ_COUNTER (k) : 0;
             if (c >= bc) { bc = c; bq = k; }
             if (__any_sync (0xffffffffu, c)) used[k >> 5] |= 1u << (k & 31);
         }
@@ -262,13 +269,19 @@ __global__ void __launch_bounds__(128) k_domq_linehist (const DqVb *vbs, const u
             for (int wd = 0; wd < 3; wd++)
                 for (uint32_t m = used[wd]; m; m &= m - 1) {
                     const uint32_t k = wd * 32 + __ffs (m) - 1;
-                    uint32_t c = 0;
-                    if (own) { c = mine[(k + FIRST_Q) * 128]; mine[(k + FIRST_Q) * 128] = 0; }
+                    const uint32_t c = own ? DQ_COUNTER (k) : 0;
                     if (uniform) { const uint32_t sum = __reduce_add_sync (0xffffffffu, c); if (lane == 0) acc[k] += sum; }
                     else if (c) atomicAdd (&V.hist[my_dom * NQ + k], c);
                 }
             if (uniform) { if (lane == 0) acc[95] += __popc (act); __syncwarp (); }
             else if (own) atomicAdd (&V.hist[NQ * NQ + my_dom], 1u);
+            // clear the words of the qualities in use (a thread counts 4 lines of <= 4096 characters in its CTA's life: what characters
+            // outside ' '..'~' leave behind in the other counters cannot carry from a low half into a high one)
+            if (own) {
+                #pragma unroll
+                for (int wd = 0; wd < 3; wd++)
+                    for (uint32_t m = used[wd]; m; m &= m - 1) mine[((wd * 32 + __ffs (m) - 1 + FIRST_Q) & 63) * 128] = 0;
+            }
         }
         // the long lines of these 32, one at a time, by the whole warp: equal qualities of a 32-byte chunk are counted once, by their lowest lane
         uint32_t longs = __ballot_sync (0xffffffffu, len > DQ_LONG_LINE);
@@ -297,6 +310,8 @@ __global__ void __launch_bounds__(128) k_domq_linehist (const DqVb *vbs, const u
         }
         if (gl < last) { V.line_dom[gl] = (uint8_t)my_dom; V.line_diverse[gl] = (uint8_t)my_div; }
     }
+    #undef DQ_COUNT
+    #undef DQ_COUNTER
     dq_flush_acc (V, acc, cur, lane);
 }
 

@@ -6,4 +6,3 @@ timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__byte
   python tools/sweep_fastq.py --vblocks 128 --steps 1 --cfg "" > gpurun_out/c29_ncu.log 2>&1
 python tools/ncu_table.py gpurun_out/r02_domq_kernels.csv 2>/dev/null | head -30
 timeout 600 python tools/sweep_fastq.py --vblocks 768 --steps 2 --cfg "" 2>&1 | tail -1 | cut -c1-200
-timeout 300 python tools/e2e_probe.py 2>&1 | grep -m14 "zip_device\|piz_device\|domq_prepare\|domq_split\|acgt_pack\|domq_reconstruct"
