@@ -268,7 +268,7 @@ int pick_arith_lpw (uint32_t n) { int l = 1; while (l < 32 && (uint64_t)n > 9472
 
 } // namespace
 
-namespace { struct PackOut { void *arena; uint64_t cap; uint64_t *used; bool dev; }; }
+namespace { struct PackOut { void *arena; uint64_t cap; uint64_t *used; bool dev; bool sizes_only = false; }; }   // sizes_only: no output at all, out_len of every section
 
 static int compress_impl (gzb_engine *e, gzb_section *secs, uint32_t n, uint32_t flags, const PackOut *pk)
 {
@@ -505,6 +505,7 @@ static int compress_impl (gzb_engine *e, gzb_section *secs, uint32_t n, uint32_t
             CK (cudaMemcpyAsync (off.data (), P.pack_off, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, st));
             CK (cudaStreamSynchronize (st));
             if (pk->used) *pk->used = off[n];
+            if (pk->sizes_only) { for (uint32_t i = 0; i < n; i++) secs[i].out = nullptr; return GZB_OK; }
             if (off[n] > pk->cap) {                                          // nothing was written: the caller grows the buffer and calls again
                 for (uint32_t i = 0; i < n; i++) { secs[i].status = GZB_SOFT_FAIL; secs[i].out_len = 0; secs[i].out = nullptr; }
                 e->err = "packed output: the buffer is too small";
@@ -534,6 +535,51 @@ extern "C" int gzb_compress_sections_packed (gzb_engine *e, gzb_section *secs, u
     if (!arena && arena_cap) return GZB_E_BADARG;
     PackOut pk { arena, arena_cap, arena_used, (flags & (GZB_DEVICE_PTRS | GZB_OUT_DEVICE)) != 0 };
     return compress_impl (e, secs, n, flags, &pk);
+}
+
+// ------------------------------------------------------------------------------------------------ codec assignment by size
+// codec_assign_best_codec (src/codec.c:234-389) compresses a sample of <= CODEC_ASSIGN_SAMPLE_SIZE bytes of a context's data with every
+// generic codec, one after the other, and sorts the results (sorter :128-173).  Here the samples of all the contexts that need a codec
+// are compressed with the eight simple codecs of this path as ONE batch — the same bytes the reference's calls produce, so the same
+// sizes — and nothing is written anywhere: only the lengths come back.
+extern "C" int gzb_assign_codecs (gzb_engine *e, gzb_assign_item *items, uint32_t n, uint32_t flags)
+{
+    if (!e || (!items && n)) return GZB_E_BADARG;
+    static const int codecs[8] = { GZB_CODEC_RANB, GZB_CODEC_RANW, GZB_CODEC_RANb, GZB_CODEC_RANw, GZB_CODEC_ARTB, GZB_CODEC_ARTW, GZB_CODEC_ARTb, GZB_CODEC_ARTw };
+    std::vector<gzb_section> secs; secs.reserve ((size_t)n * 8);
+    for (uint32_t i = 0; i < n; i++) {
+        gzb_assign_item &it = items[i];
+        it.sample_len = (uint32_t)std::min<uint64_t> (it.len, GZB_ASSIGN_SAMPLE_SIZE);
+        it.best = GZB_CODEC_UNKNOWN;
+        for (int k = 0; k < 8; k++) it.size[k] = 0;
+        if (it.sample_len < GZB_MIN_LEN_FOR_COMPRESSION) continue;             // "if too small - don't assign" (:317-318): the section goes out as CODEC_NONE (compressor.c:56-58)
+        if (!it.data) return GZB_E_BADARG;
+        for (int k = 0; k < 8; k++) {
+            gzb_section sc; memset (&sc, 0, sizeof sc);
+            sc.codec = codecs[k]; sc.in = it.data; sc.in_len = it.sample_len; sc.out_cap = 0xffffffffu;
+            secs.push_back (sc);
+        }
+    }
+    if (secs.empty ()) return GZB_OK;
+    uint64_t used = 0;
+    PackOut pk { nullptr, 0, &used, true, true };
+    int rc = compress_impl (e, secs.data (), (uint32_t)secs.size (), flags & (GZB_DEVICE_PTRS | GZB_IN_DEVICE), &pk);
+    if (rc) return rc;
+    size_t j = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        gzb_assign_item &it = items[i];
+        if (it.sample_len < GZB_MIN_LEN_FOR_COMPRESSION) continue;
+        // the sorter's last two rules, which are all that is left of it without the clock: smaller size first, equal sizes -> the lower codec
+        // (the non-packing variant, :167-169); CODEC_NONE competes with the sample's own length (:325)
+        uint64_t best_size = it.sample_len; int best = GZB_CODEC_NONE;
+        for (int k = 0; k < 8; k++, j++) {
+            if (secs[j].status != GZB_OK) { e->err = "gzb_assign_codecs: a sample failed to compress"; return secs[j].status; }
+            it.size[k] = secs[j].out_len;
+            if ((uint64_t)it.size[k] + GZB_SECTION_HEADER_BYTES < best_size) { best_size = (uint64_t)it.size[k] + GZB_SECTION_HEADER_BYTES; best = codecs[k]; }
+        }
+        it.best = best;
+    }
+    return GZB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ batched copies on the device

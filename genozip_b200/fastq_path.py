@@ -229,18 +229,13 @@ class FastqCodecPath:
         self._acgt_pack_device(data, meta, 0, 1)
         self._domq_device(lambda v: data["qual"][v].data_ptr(), self.engs[0], meta, GZB_DEVICE_PTRS, 0, 1)
         meta.len[0, [S_IDX[s] for s in NAMES]] = [self.name_len[s] for s in NAMES]
-        samples = {}
-        for s in STREAMS:
-            ln = int(meta.len[0, S_IDX[s]])
-            if ln:
-                samples[s] = self._stream_tensor(s, 0, data, meta)[:min(ln, 99999)].cpu().numpy().copy()
-        items = [(c, samples[s]) for s in samples for c in SIMPLE]
-        outs = self.eng.compress(items)
-        k = 0
-        for s in samples:
-            sizes = [outs[k + j].size for j in range(len(SIMPLE))]
-            k += len(SIMPLE)
-            self.codec[s] = SIMPLE[int(np.argmin(sizes))] if samples[s].size >= 50 else "RANB"   # <50 B would be CODEC_NONE (compressor.c:56-58)
+        present = [s for s in STREAMS if int(meta.len[0, S_IDX[s]])]
+        # one gzb_assign_codecs call: the first <= 99,999 bytes of every stream of VB 1, where they are in HBM, with the eight codecs; sizes only
+        res = self.eng.assign_codecs_ptrs([(self._stream_tensor(s, 0, data, meta).data_ptr(), int(meta.len[0, S_IDX[s]])) for s in present], GZB_DEVICE_PTRS)
+        for s, (best, sizes) in zip(present, res):
+            # a sample below 50 B would go out as CODEC_NONE (compressor.c:56-58), and so would one no codec shrinks: this path has no
+            # uncompressed sections, it keeps the smallest of the eight then
+            self.codec[s] = best if best in SIMPLE else (min(SIMPLE, key=lambda c: (sizes[c], SIMPLE.index(c))) if sizes else "RANB")
         return dict(self.codec)
 
     def _stream_tensor(self, s, v, data, meta):

@@ -76,6 +76,10 @@ class DigestItem(C.Structure):      # gzb_digest_item
     _fields_ = [("data", C.c_void_p), ("len", C.c_uint64), ("adler", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+class AssignItem(C.Structure):      # gzb_assign_item
+    _fields_ = [("data", C.c_void_p), ("len", C.c_uint64), ("sample_len", C.c_uint32), ("size", C.c_uint32 * 8), ("best", C.c_int32)]
+
+
 class LongrVb(C.Structure):         # gzb_longr_vb
     _fields_ = [("txt", C.c_void_p), ("txt_len", C.c_uint64), ("seq_off", C.c_void_p), ("qual_off", C.c_void_p),
                 ("len", C.c_void_p), ("is_rev", C.c_void_p), ("n_lines", C.c_uint32), ("value_to_bin", C.c_uint8 * 256),
@@ -159,6 +163,8 @@ def load():
     L.gzb_local_transform_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
     L.gzb_adler32_batch.restype = C.c_int
     L.gzb_adler32_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+    L.gzb_assign_codecs.restype = C.c_int
+    L.gzb_assign_codecs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
     L.gzb_pbwt_decode.restype = C.c_int
     L.gzb_pbwt_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64,
                                   C.POINTER(C.c_uint64), C.c_uint32]
@@ -360,6 +366,22 @@ class Engine:
         if rc != 0:
             raise GzbError(f"gzb_adler32_batch failed ({rc}): {self._err()}")
         return [int(items[i].adler) for i in range(len(ptr_len))]
+
+    def assign_codecs(self, bufs):
+        """codec_assign_best_codec's size criterion (codec.c:234-389) for host buffers -> [(best codec name or None, {codec name: body bytes})]"""
+        arrs = [np.ascontiguousarray(b, dtype=np.uint8) for b in bufs]
+        return self.assign_codecs_ptrs([(a.ctypes.data if a.size else 0, a.size) for a in arrs], 0)
+
+    def assign_codecs_ptrs(self, ptr_len, flags):
+        items = (AssignItem * max(1, len(ptr_len)))()
+        for i, (p, n) in enumerate(ptr_len):
+            items[i].data = p; items[i].len = n
+        rc = self.L.gzb_assign_codecs(self.h, items, len(ptr_len), flags)
+        if rc != 0:
+            raise GzbError(f"gzb_assign_codecs failed ({rc}): {self._err()}")
+        names = ("RANB", "RANW", "RANb", "RANw", "ARTB", "ARTW", "ARTb", "ARTw")
+        by_id = {v: k for k, v in CODEC.items()}; by_id[1] = "NONE"; by_id[0] = None
+        return [(by_id[int(items[i].best)], {nm: int(items[i].size[k]) for k, nm in enumerate(names)} if items[i].best else {}) for i in range(len(ptr_len))]
 
     # ---- ACGT (host buffers) ----
     def acgt_pack(self, seq):

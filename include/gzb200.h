@@ -112,6 +112,29 @@ int gzb_uncompress_sections (gzb_engine *e, gzb_section *secs, uint32_t n, uint3
  * or GZB_OUT_DEVICE, else host memory (one transfer for the whole batch). */
 int gzb_compress_sections_packed (gzb_engine *e, gzb_section *secs, uint32_t n, void *arena, uint64_t arena_cap, uint64_t *arena_used, uint32_t flags);
 
+/* ---------------------------------------------------------------- codec assignment by size
+ * codec_assign_best_codec (src/codec.c:234-389) without its clock: the first min (len, CODEC_ASSIGN_SAMPLE_SIZE) bytes of every item
+ * (src/codec.h:154; one item per context whose codec is still CODEC_UNKNOWN) are compressed with the eight simple codecs of this path
+ * in ONE batch; nothing is written, only the compressed lengths come back.  size[k] = body bytes with codec RANB, RANW, RANb, RANw,
+ * ARTB, ARTW, ARTb, ARTw (k = 0..7) — the bytes the reference's own test compressions produce.  best = what the sorter's size rules
+ * leave (:146-149,167-172): the smallest section (body + the 28-byte SectionHeader the reference's measurement includes, :331-333), equal
+ * sizes to the lower Codec value, CODEC_NONE if the bare sample (:325) is not larger than that; GZB_CODEC_UNKNOWN if the sample is
+ * below MIN_LEN_FOR_COMPRESSION (:317-318, the section then goes out as CODEC_NONE, compressor.c:56-58).  The reference also weighs
+ * clock () time and offers BZ2 / BSC / LZMA: host policy, out of scope — the adapter can still apply its sorter to size[] plus its own
+ * timings.  Device pointers with GZB_DEVICE_PTRS / GZB_IN_DEVICE, else host memory. */
+#define GZB_ASSIGN_SAMPLE_SIZE        99999u
+#define GZB_MIN_LEN_FOR_COMPRESSION   50u
+#define GZB_SECTION_HEADER_BYTES      28u
+#define GZB_CODEC_UNKNOWN             0
+typedef struct {
+    const void *data;          /* the context's local / b250 / dict data */
+    uint64_t    len;           /* its length in bytes */
+    uint32_t    sample_len;    /* out: bytes that were compressed */
+    uint32_t    size[8];       /* out: compressed body bytes per codec */
+    int32_t     best;          /* out: GZB_CODEC_* */
+} gzb_assign_item;
+int gzb_assign_codecs (gzb_engine *e, gzb_assign_item *items, uint32_t n, uint32_t flags);
+
 /* n device-to-device copies in one launch (compacting the streams a complex codec produced into right-sized buffers) */
 typedef struct { const void *src; void *dst; uint64_t len; } gzb_copy;
 int gzb_copy_batch (gzb_engine *e, const gzb_copy *copies, uint32_t n);

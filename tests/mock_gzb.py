@@ -308,6 +308,23 @@ class MockLib:
     def gzb_stage_wait(self, h, which):
         return 0
 
+    def gzb_assign_codecs(self, h, items, n, flags):
+        names = ("RANB", "RANW", "RANb", "RANw", "ARTB", "ARTW", "ARTb", "ARTw")
+        ids = (6, 7, 8, 9, 16, 17, 18, 19)
+        for i in range(n):
+            it = items[i]
+            it.sample_len = min(it.len, 99999); it.best = 0
+            if it.sample_len < 50:
+                continue
+            d = _view(it.data, it.sample_len).copy()
+            best, best_size = 1, it.sample_len
+            for k, nm in enumerate(names):
+                it.size[k] = orc.compress("port", "rans" if nm.startswith("RAN") else "arith", d, orc.ORDER[nm]).size
+                if it.size[k] + 28 < best_size:
+                    best, best_size = ids[k], it.size[k] + 28
+            it.best = best
+        return 0
+
     def gzb_adler32_batch(self, h, items, n, flags):
         import zlib
         for i in range(n):
@@ -355,6 +372,10 @@ class MockEngine:
 
     def compress(self, items):
         return [orc.compress("port", "rans" if c.startswith("RAN") else "arith", np.ascontiguousarray(d, np.uint8), orc.ORDER[c]) for c, d in items]
+
+    def assign_codecs_ptrs(self, ptr_len, flags):
+        from genozip_b200.lib import Engine
+        return Engine.assign_codecs_ptrs(self, ptr_len, flags)      # the real marshalling over MockLib.gzb_assign_codecs
 
 
 def install():
