@@ -58,8 +58,10 @@ static __device__ __noinline__ Ar0 ar0_halve (uint32_t *E, uint8_t *POS, uint32_
         const uint32_t en = E[p], prev = E[p - 1];
         __syncwarp ();
         if ((en & 0xffffu) > (prev & 0xffffu)) {
-            E[p - 1] = en; E[p] = prev;
-            if (POS) { POS[en >> 16] = (uint8_t)(p - 1); POS[prev >> 16] = (uint8_t)p; }
+            if (lane == 0) {
+                E[p - 1] = en; E[p] = prev;
+                if (POS) { POS[en >> 16] = (uint8_t)(p - 1); POS[prev >> 16] = (uint8_t)p; }
+            }
             if ((p & 7) == 0) {
                 const uint32_t d = (en & 0xffffu) - (prev & 0xffffu), owner = p >> 3;
                 if ((uint32_t)lane == owner - 1) a.s += d;
@@ -76,13 +78,18 @@ static __device__ __noinline__ Ar0 ar0_halve (uint32_t *E, uint8_t *POS, uint32_
 // entry p (current value e, predecessor prev when p > 0) was coded: Freq += STEP, TotFreq += STEP, halve, bubble (:131-145)
 __device__ __forceinline__ void ar0_update (uint32_t *E, uint8_t *POS, uint32_t maxs, Ar0 &a, uint32_t p, uint32_t e, uint32_t prev, int lane)
 {
+    // Every lane computes the same values; lane 0 alone stores them, and a __syncwarp () stands between its stores and the other
+    // lanes' next reads (the reads before this call ended with AR_READS_DONE): no two lanes ever touch a word of the model without a
+    // barrier in between (compute-sanitizer racecheck, profiles/r02_sanitizer.md).
     const uint32_t en = e + AR_STEP, owner = p >> 3;
-    if (a.tot + AR_STEP > AR_MAXF) { E[p] = en; const Ar0 t = ar0_halve (E, POS, maxs, a, p, lane); a = t; return; }
+    if (a.tot + AR_STEP > AR_MAXF) { if (lane == 0) E[p] = en; const Ar0 t = ar0_halve (E, POS, maxs, a, p, lane); a = t; return; }
     a.tot += AR_STEP; a.rtot = ar_rcp_below (a.tot);
     if ((uint32_t)lane == owner) a.s += AR_STEP; else if ((uint32_t)lane > owner) a.base += AR_STEP;
     if (p && (en & 0xffffu) > (prev & 0xffffu)) {
-        E[p - 1] = en; E[p] = prev;
-        if (POS) { POS[en >> 16] = (uint8_t)(p - 1); POS[prev >> 16] = (uint8_t)p; }
+        if (lane == 0) {
+            E[p - 1] = en; E[p] = prev;
+            if (POS) { POS[en >> 16] = (uint8_t)(p - 1); POS[prev >> 16] = (uint8_t)p; }
+        }
         if ((p & 7) == 0) {                                                  // the bubble step crossed a lane boundary
             const uint32_t d = (en & 0xffffu) - (prev & 0xffffu);
             if ((uint32_t)lane == owner - 1) a.s += d;
@@ -90,12 +97,14 @@ __device__ __forceinline__ void ar0_update (uint32_t *E, uint8_t *POS, uint32_t 
         }
         if (p == 1) a.e0 = en;
     }
-    else { E[p] = en; if (p == 0) a.e0 = en; }
+    else { if (lane == 0) E[p] = en; if (p == 0) a.e0 = en; }
+    __syncwarp ();
 }
 
 // copies the model into the global layout of arith_model.cuh (for the reference-exact tail after a corrupt / truncated stream)
-__device__ __forceinline__ void ar0_export (const uint32_t *E, const Ar0 &a, uint32_t *m, uint32_t maxs, int lane)
+__device__ __forceinline__ void ar0_export (uint32_t *E, const Ar0 &a, uint32_t *m, uint32_t maxs, int lane)
 {
+    if (lane == 0) E[0] = a.e0;                                              // (the top entry lives in a.e0 while it keeps being coded)
     __syncwarp ();
     for (uint32_t i = lane; i < maxs; i += 32) m[4 + i] = E[i];
     if (lane == 0) ar_store_head (m, a.tot, a.rtot);
@@ -113,12 +122,14 @@ __device__ __forceinline__ uint32_t ar0_decode_run (uint32_t *E, uint32_t maxs, 
         uint32_t sym;
         if (rc.code < t1 && a.tot + AR_STEP <= AR_MAXF) {                    // the top entry again: registers + one shared store
             rc.range = t1;
-            a.e0 += AR_STEP; E[0] = a.e0;
+            a.e0 += AR_STEP;                                                // (registers only: E[0] is written back when another entry is looked at)
             a.tot += AR_STEP; a.rtot = ar_rcp_below (a.tot);
             if (lane == 0) a.s += AR_STEP; else a.base += AR_STEP;
             sym = a.e0 >> 16;
         }
         else {
+            if (lane == 0) E[0] = a.e0;
+            __syncwarp ();
             const uint32_t T = (a.base + a.s) * r;                          // <= TotFreq * r <= range: no overflow
             const uint32_t ball = __ballot_sync (0xffffffffu, T > rc.code);
             if (!ball) { rc.range = r; ar_out_put (o, 0); return i + 1; }   // code/r >= TotFreq: the reference returns symbol 0 (:153-161)
@@ -153,11 +164,13 @@ __device__ __forceinline__ void ar0_encode_sym (uint32_t *E, uint8_t *POS, uint3
     const uint32_t r = ar_div (rc.range, a.tot, a.rtot);
     if ((a.e0 >> 16) == sym && a.tot + AR_STEP <= AR_MAXF) {
         rc.range = (a.e0 & 0xffffu) * r;
-        a.e0 += AR_STEP; E[0] = a.e0;
+        a.e0 += AR_STEP;                                                    // (registers only: E[0] is written back when another entry is looked at)
         a.tot += AR_STEP; a.rtot = ar_rcp_below (a.tot);
         if (lane == 0) a.s += AR_STEP; else a.base += AR_STEP;
         return;
     }
+    if (lane == 0) E[0] = a.e0;
+    __syncwarp ();
     const uint32_t p = POS[sym], owner = p >> 3, j = p & 7;
     const uint32_t e = E[p], prev = p ? E[p - 1] : 0u;
     uint32_t acc = __shfl_sync (0xffffffffu, a.base, owner);
