@@ -63,6 +63,13 @@ class NormqVb(C.Structure):         # gzb_normq_vb
                 ("out", C.c_void_p), ("out_cap", C.c_uint64), ("missing", C.c_void_p)]
 
 
+class OqVb(C.Structure):            # gzb_oq_vb
+    _fields_ = [("txt", C.c_void_p), ("txt_len", C.c_uint64), ("qual_off", C.c_void_p), ("qual_len", C.c_void_p), ("oq_off", C.c_void_p),
+                ("seq_len", C.c_void_p), ("n_lines", C.c_uint32), ("status", C.c_int32), ("key_bias", C.c_uint32), ("reserved", C.c_uint32),
+                ("channels", C.c_void_p), ("channels_cap", C.c_uint64), ("count", C.c_uint32 * 94), ("monochars", C.c_uint8 * 94), ("pad", C.c_uint8 * 2),
+                ("out", C.c_void_p), ("out_cap", C.c_uint64), ("out_off", C.c_void_p)]
+
+
 class LocalItem(C.Structure):       # gzb_local_item
     _fields_ = [("data", C.c_void_p), ("n_elems", C.c_uint64), ("op", C.c_int32), ("status", C.c_int32)]
 
@@ -157,7 +164,7 @@ def load():
     for f in ("gzb_stage_upload", "gzb_stage_fetch"):
         getattr(L, f).restype = C.c_int; getattr(L, f).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     L.gzb_stage_wait.restype = C.c_int; L.gzb_stage_wait.argtypes = [C.c_void_p, C.c_int]
-    for f in ("gzb_normq_gather", "gzb_normq_reconstruct"):
+    for f in ("gzb_normq_gather", "gzb_normq_reconstruct", "gzb_oq_mux", "gzb_oq_demux"):
         getattr(L, f).restype = C.c_int; getattr(L, f).argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
     L.gzb_local_transform_batch.restype = C.c_int
     L.gzb_local_transform_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
@@ -366,6 +373,53 @@ class Engine:
         if rc != 0:
             raise GzbError(f"gzb_adler32_batch failed ({rc}): {self._err()}")
         return [int(items[i].adler) for i in range(len(ptr_len))]
+
+    # ---- OQ (host buffers) ----
+    def oq_mux(self, vbs):
+        """vbs: list of (txt, qual_off, qual_len, oq_off, seq_len or None) -> list of (channels back to back, count[94], monochars[94])
+        (codec_oq_compress before its sub-codec)"""
+        arr = (OqVb * max(1, len(vbs)))(); keep = []
+        for i, (txt, qoff, qlen, ooff, sl) in enumerate(vbs):
+            txt = np.ascontiguousarray(txt, np.uint8); qoff = np.ascontiguousarray(qoff, np.uint64); qlen = np.ascontiguousarray(qlen, np.uint32)
+            ooff = np.ascontiguousarray(ooff, np.uint64); sl = None if sl is None else np.ascontiguousarray(sl, np.uint32)
+            ch = np.zeros(int(qlen.sum()) + 16, np.uint8)
+            keep.append((txt, qoff, qlen, ooff, sl, ch))
+            a = arr[i]
+            a.txt = txt.ctypes.data if txt.size else None; a.txt_len = txt.size; a.n_lines = qlen.size
+            a.qual_off = qoff.ctypes.data if qoff.size else None; a.qual_len = qlen.ctypes.data if qlen.size else None
+            a.oq_off = ooff.ctypes.data if ooff.size else None; a.seq_len = None if sl is None or not sl.size else sl.ctypes.data
+            a.channels = ch.ctypes.data; a.channels_cap = ch.size
+        rc = self.L.gzb_oq_mux(self.h, arr, len(vbs), 0)
+        if rc != 0:
+            raise GzbError(f"gzb_oq_mux failed ({rc}): {self._err()}")
+        out = []
+        for i, k in enumerate(keep):
+            cnt = np.array(arr[i].count[:], np.uint32)
+            out.append((k[5][:int(cnt.sum())].copy(), cnt, np.array(arr[i].monochars[:], np.uint8)))
+        return out
+
+    def oq_demux(self, vbs):
+        """vbs: list of (txt, qual_off, qual_len, out_off, out_size, key_bias, channels, count[94], monochars[94]) -> list of out arrays
+        (codec_oq_reconstruct for every line); raises when a channel is out of data"""
+        arr = (OqVb * max(1, len(vbs)))(); keep = []
+        for i, (txt, qoff, qlen, ooff, out_size, bias, ch, cnt, mono) in enumerate(vbs):
+            txt = np.ascontiguousarray(txt, np.uint8); qoff = np.ascontiguousarray(qoff, np.uint64); qlen = np.ascontiguousarray(qlen, np.uint32)
+            ooff = np.ascontiguousarray(ooff, np.uint64); ch = np.ascontiguousarray(ch, np.uint8)
+            ch = ch if ch.size else np.zeros(1, np.uint8)
+            out = np.zeros(out_size + 16, np.uint8)
+            keep.append((txt, qoff, qlen, ooff, ch, out, out_size))
+            a = arr[i]
+            a.txt = txt.ctypes.data if txt.size else None; a.txt_len = txt.size; a.n_lines = qlen.size; a.key_bias = bias
+            a.qual_off = qoff.ctypes.data if qoff.size else None; a.qual_len = qlen.ctypes.data if qlen.size else None
+            a.out_off = ooff.ctypes.data if ooff.size else None
+            a.channels = ch.ctypes.data; a.channels_cap = ch.size
+            for q in range(94):
+                a.count[q] = int(cnt[q]); a.monochars[q] = int(mono[q])
+            a.out = out.ctypes.data; a.out_cap = out_size
+        rc = self.L.gzb_oq_demux(self.h, arr, len(vbs), 0)
+        if rc != 0:
+            raise GzbError(f"gzb_oq_demux failed ({rc}): {self._err()}")
+        return [k[5][:k[6]].copy() for k in keep]
 
     def assign_codecs(self, bufs):
         """codec_assign_best_codec's size criterion (codec.c:234-389) for host buffers -> [(best codec name or None, {codec name: body bytes})]"""

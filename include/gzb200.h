@@ -256,6 +256,39 @@ typedef struct gzb_normq_vb {
 int gzb_normq_gather      (gzb_engine *e, gzb_normq_vb *vbs, uint32_t n_vbs, uint32_t flags);
 int gzb_normq_reconstruct (gzb_engine *e, gzb_normq_vb *vbs, uint32_t n_vbs, uint32_t flags);
 
+/* ---------------------------------------------------------------- OQ (src/codec_oq.c): a read's original quality string OQ:Z multiplexed by its QUAL
+ * mux:   codec_oq_compress before its sub-codec (:54-121).  The OQ character at position i of a line goes to channel QUAL[i] - '!' (94
+ *        channels); count[] = the QUAL characters of ALL lines per channel (the reference's count pass, :61-72, which sizes the channels),
+ *        while only the lines whose seq_len is not 0 are distributed (:94) — bytes nobody writes stay 0; monochars[q] = the character of a
+ *        channel that holds one character only, else 0 (:103-107: the reference then drops that channel and stores the 94 monochars with RANB).
+ *        oq_off[i] = dl->OQ as it is (0 for a line without OQ:Z: the reference reads the start of txt_data then, :91 — so does this).
+ *            in  txt, qual_off, qual_len, oq_off, seq_len (NULL = never 0)      out  channels (channel q at the sum of count[0..q)), count, monochars
+ * demux: codec_oq_reconstruct (:126-164) for every line of a VBlock at once: the reconstructed QUAL strings are the keys (key_bias = 33
+ *        when they are text, 0 when they are BAM values, :131), a monochar channel yields its character and consumes nothing.
+ *            in  txt, qual_off, qual_len, key_bias, channels + count (the channels that exist, back to back; count 0 for the others), monochars, out_off
+ *            out out (qual_len[i] bytes at out_off[i] per line)
+ * GZB_E_CORRUPT: a QUAL character outside '!'..'~', or a channel out of data (:152).  Device pointers with GZB_DEVICE_PTRS (then
+ * channels_cap / out_cap bound the work); with host buffers all of `out` is written (0 where no line lands). */
+typedef struct gzb_oq_vb {
+    const void     *txt;        uint64_t txt_len;
+    const uint64_t *qual_off;
+    const uint32_t *qual_len;
+    const uint64_t *oq_off;     /* mux */
+    const uint32_t *seq_len;    /* mux, may be NULL */
+    uint32_t        n_lines;
+    int32_t         status;
+    uint32_t        key_bias;   /* demux */
+    uint32_t        reserved;
+    void           *channels;   uint64_t channels_cap;
+    uint32_t        count[94];
+    uint8_t         monochars[94];
+    uint8_t         pad[2];
+    void           *out;        uint64_t out_cap;   /* demux */
+    const uint64_t *out_off;    /* demux */
+} gzb_oq_vb;
+int gzb_oq_mux   (gzb_engine *e, gzb_oq_vb *vbs, uint32_t n_vbs, uint32_t flags);
+int gzb_oq_demux (gzb_engine *e, gzb_oq_vb *vbs, uint32_t n_vbs, uint32_t flags);
+
 /* ---------------------------------------------------------------- PBWT (src/codec_pbwt.c)
  * encode: codec_pbwt_compress (:244-287): haplotype matrix → RUNS (uint32) + FGRC ({allele:8,count:24}; the last
  *         two words are the 64-bit matrix length, :274-276).  Host-endian words.

@@ -563,3 +563,59 @@ int orc_normq_decode (const uint8_t *local, uint64_t local_len, const uint32_t *
     *used = next;
     return 0;
 }
+
+/* ================================================================ OQ (reference src/codec_oq.c)
+ * mux   = codec_oq_compress before its sub-codec (:54-121): count pass over the QUAL of every line (:61-72), the OQ characters of the lines whose
+ *         SEQ.len is not 0 appended to channel QUAL[i] - 33 (:88-99; oq_off = dl->OQ, 0 for a line without OQ:Z), monochar channels (:103-107).
+ *         channels = the 94 channels back to back in channel order (count[q] bytes each; what no line wrote is 0).  Returns -1 on a QUAL
+ *         character outside '!'..'~'.
+ * demux = codec_oq_reconstruct (:126-164) line by line; channels = the channels that exist, back to back (count[q] bytes each).
+ *         Returns -1 when a channel is out of data (:152) or a key is out of range. */
+#define OQ_CH 94
+int orc_oq_mux (const uint8_t *txt, const uint64_t *qual_off, const uint32_t *qual_len, const uint64_t *oq_off, const uint32_t *seq_len, uint32_t n_lines,
+                uint8_t *channels, uint32_t *count, uint8_t *monochars)
+{
+    uint64_t next[OQ_CH], total = 0;
+    memset (count, 0, OQ_CH * sizeof (uint32_t));
+    for (uint32_t li = 0; li < n_lines; li++)                                             /* first pass (:61-72) */
+        for (uint32_t i = 0; i < qual_len[li]; i++) {
+            const unsigned q = (unsigned)txt[qual_off[li] + i] - 33u;
+            if (q >= OQ_CH) return -1;
+            count[q]++;
+        }
+    for (int q = 0; q < OQ_CH; q++) { next[q] = total; total += count[q]; }
+    memset (channels, 0, total);
+    for (uint32_t li = 0; li < n_lines; li++) {                                           /* second pass (:88-99) */
+        if (seq_len && !seq_len[li]) continue;                                            /* :94 */
+        const uint8_t *qual = txt + qual_off[li], *oq = txt + oq_off[li];
+        for (uint32_t i = 0; i < qual_len[li]; i++) channels[next[qual[i] - 33]++] = oq[i];
+    }
+    uint64_t at = 0;
+    for (int q = 0; q < OQ_CH; q++) {                                                     /* :103-107, str_is_monochar (strings.h:176-184) */
+        monochars[q] = 0;
+        if (count[q]) {
+            int same = 1;
+            for (uint32_t i = 1; i < count[q] && same; i++) same = channels[at + i] == channels[at];
+            if (same) monochars[q] = channels[at];
+        }
+        at += count[q];
+    }
+    return 0;
+}
+
+int orc_oq_demux (const uint8_t *txt, const uint64_t *qual_off, const uint32_t *qual_len, const uint64_t *out_off, uint32_t n_lines, uint32_t key_bias,
+                  const uint8_t *channels, const uint32_t *count, const uint8_t *monochars, uint8_t *out)
+{
+    uint64_t next[OQ_CH], after[OQ_CH], total = 0;
+    for (int q = 0; q < OQ_CH; q++) { next[q] = total; total += count[q]; after[q] = total; }
+    for (uint32_t li = 0; li < n_lines; li++) {
+        const uint8_t *qual = txt + qual_off[li]; uint8_t *recon = out + out_off[li];
+        for (uint32_t i = 0; i < qual_len[li]; i++) {
+            const unsigned ch = (unsigned)qual[i] - key_bias;                             /* :143 */
+            if (ch >= OQ_CH) return -1;
+            if (monochars[ch]) recon[i] = monochars[ch];                                  /* :145-146 */
+            else { if (next[ch] >= after[ch]) return -1; recon[i] = channels[next[ch]++]; }   /* :149-155 */
+        }
+    }
+    return 0;
+}

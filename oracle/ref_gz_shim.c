@@ -30,6 +30,7 @@
 #include "reconstruct.h"
 #include "profiler.h"
 #include "sam.h"
+#include "sam_private.h"
 #include "fastq.h"
 #include "vcf.h"
 #include "sections.h"
@@ -501,6 +502,104 @@ int ref_normq_decode (const uint8_t *local, uint64_t local_len, const uint32_t *
     shim_missing_ok = false;
     *out_len = vb->txt_data.len;
     memcpy (out, vb->txt_data.data, vb->txt_data.len);
+    free (vb);
+    return 0;
+}
+
+// ================================================================ OQ (the reference's compiled codec_oq.c)
+// context services codec_oq.c reaches for: its 94 channel contexts are looked up by dict_id (ctx_get_ctx / ECTX, context.h:174-207);
+// the hand-made VBlock has no dict_id map, so both land here: a linear search over the contexts the harness created
+#define SHIM_FIRST_DYN_DID 600
+ContextP ctx_get_unmapped_ctx (ContextArrayP ca, DataType dt, DictId dict_id, STRp(tag_name))
+{
+    if (ca->num_contexts < SHIM_FIRST_DYN_DID) ca->num_contexts = SHIM_FIRST_DYN_DID;
+    for (Did d = SHIM_FIRST_DYN_DID; d < ca->num_contexts; d++) if (ca->contexts[d].dict_id.num == dict_id.num) return &ca->contexts[d];
+    ContextP c = &ca->contexts[ca->num_contexts];
+    c->did_i = ca->num_contexts++; c->dict_id = dict_id;
+    return c;
+}
+Did ctx_get_unmapped_existing_did_i (ConstContextArrayP ca, DictId dict_id)
+{
+    for (Did d = SHIM_FIRST_DYN_DID; d < ca->num_contexts; d++) if (ca->contexts[d].dict_id.num == dict_id.num) return d;
+    return DID_NONE;
+}
+void ctx_update_zctx_txt_len (VBlockP vb, ContextP vctx, int64_t increment) {}
+void ctx_consolidate_statsA (VBlockP vb, Did parent, ContextP ctxs[], unsigned num_deps) {}
+DisplayPrintId dis_dict_id (DictId dict_id) { DisplayPrintId d = {}; memcpy (d.s, dict_id.id, 8); return d; }
+#define SHIM_OQ_DICT_ID_Q(q) DICT_ID_MAKE2_5(((char[]){'O', (q)+33, 'Q',':','Z'}))       /* codec_oq.c:15 */
+
+// codec_oq_compress on the lines of a hand-made SAM VBlock: channels back to back in channel order (count[q] bytes each), the monochars it hands to RANB
+int ref_oq_encode (const uint8_t *txt, uint64_t txt_len, const uint64_t *qual_off, const uint32_t *qual_len, const uint64_t *oq_off, const uint32_t *seq_len,
+                   uint32_t n_lines, uint8_t *channels, uint32_t *count, uint8_t *monochars)
+{
+    shim_init ();
+    if (setjmp (on_abort)) return -1;
+    VBlockP vb = calloc (1, sizeof (VBlock));
+    vb->vblock_i = 1; vb->data_type = DT_SAM;
+    buf_alloc_do (vb, &vb->txt_data, txt_len + 64, 1, "txt_data", __FUNCLINE);
+    memcpy (vb->txt_data.data, txt, txt_len); vb->txt_data.len = txt_len;
+    buf_alloc_do (vb, &vb->lines, (uint64_t)(n_lines + 1) * sizeof (ZipDataLineSAM), 1, "lines", __FUNCLINE);
+    memset (vb->lines.data, 0, (uint64_t)(n_lines + 1) * sizeof (ZipDataLineSAM)); vb->lines.len = n_lines;
+    for (uint32_t i = 0; i < n_lines; i++) {
+        ZipDataLineSAM *dl = B(ZipDataLineSAM, vb->lines, i);
+        dl->QUAL = (TxtWord){ .index = (uint32_t)qual_off[i], .len = qual_len[i] };
+        dl->OQ = (uint32_t)oq_off[i]; dl->SEQ.len = seq_len[i];
+    }
+    ContextP ctx = CTX (OPTION_OQ_Z);
+    ctx->did_i = OPTION_OQ_Z; strcpy (ctx->tag_name, "OQ:Z");
+    SectionHeaderCtx header = {};
+    uint32_t ulen = 0, clen = 4096;
+    char *comp = calloc (1, clen);
+    cap_out = NULL; cap_len = 0;
+    if (!codec_oq_compress (vb, ctx, (SectionHeaderP)&header, NULL, &ulen, NULL, comp, &clen, true, "OQ:Z")) return -3;
+    if (cap_len != 94 || header.sub_codec != CODEC_RANB) return -4;
+    memcpy (monochars, cap_out, 94);
+    uint64_t at = 0;
+    for (int q = 0; q < 94; q++) {
+        ContextP c = ctx_get_existing_ctx_do (vb, (DictId)SHIM_OQ_DICT_ID_Q(q), __FUNCLINE);
+        if (!c || !c->local.data) { count[q] = 0; continue; }
+        count[q] = c->local.len32;
+        if (!count[q] && monochars[q])                                      // the reference empties a monochar channel after filling it (:105): its bytes are still there,
+            for (uint32_t i = 0; i < n_lines; i++)                          // their number is what the count pass found (:61-72)
+                for (uint32_t k = 0; k < qual_len[i]; k++) count[q] += ((uint8_t)txt[qual_off[i] + k] - 33) == q;
+        memcpy (channels + at, c->local.data, count[q]); at += count[q];
+    }
+    free (comp); free (vb);
+    return 0;
+}
+
+// codec_oq_reconstruct line by line: the QUAL strings are in txt (as SAM_QUAL's last_txt), the OQ of every line lands at the end of txt_data
+int ref_oq_decode (const uint8_t *txt, uint64_t txt_len, const uint64_t *qual_off, const uint32_t *qual_len, const uint64_t *out_off, uint32_t n_lines, uint32_t key_bias,
+                   const uint8_t *channels, const uint32_t *count, const uint8_t *monochars, uint8_t *out, uint64_t out_size)
+{
+    shim_init_piz ();
+    if (setjmp (on_abort)) return -1;
+    flag.out_dt = key_bias ? DT_SAM : DT_BAM;                               // sam_diff (:131)
+    VBlockP vb = calloc (1, sizeof (VBlock));
+    vb->vblock_i = 1; vb->data_type = DT_SAM; vb->lines.len = n_lines;
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n_lines; i++) total += qual_len[i];
+    buf_alloc_do (vb, &vb->txt_data, txt_len + total + 64, 1, "txt_data", __FUNCLINE);
+    memcpy (vb->txt_data.data, txt, txt_len); vb->txt_data.len = txt_len;
+    ContextP ctx = CTX (OPTION_OQ_Z);
+    ctx->did_i = OPTION_OQ_Z; ctx->is_loaded = true;
+    buf_alloc_do (vb, &ctx->local, 94 + 8, 1, "local", __FUNCLINE);
+    memcpy (ctx->local.data, monochars, 94); ctx->local.len = 94;
+    uint64_t at = 0;
+    for (int q = 0; q < 94; q++) {
+        if (!count[q]) continue;                                            // a channel that is not in the file: ECTX returns NULL
+        ContextP c = ctx_get_unmapped_ctx (&vb->ca, DT_SAM, (DictId)SHIM_OQ_DICT_ID_Q(q), 0, 0);
+        buf_alloc_do (vb, &c->local, count[q] + 8, 1, "local", __FUNCLINE);
+        memcpy (c->local.data, channels + at, count[q]); c->local.len = count[q]; at += count[q];
+    }
+    ContextP qual_ctx = CTX (SAM_QUAL);
+    for (uint32_t i = 0; i < n_lines; i++) {
+        qual_ctx->last_txt = (TxtWord){ .index = (uint32_t)qual_off[i], .len = qual_len[i] };
+        const uint64_t before = vb->txt_data.len;
+        codec_oq_reconstruct (vb, CODEC_OQ, ctx, qual_len[i], true);
+        if (out_off[i] + qual_len[i] > out_size) return -2;
+        memcpy (out + out_off[i], vb->txt_data.data + before, qual_len[i]);
+    }
     free (vb);
     return 0;
 }

@@ -479,3 +479,53 @@ def ref_local_transform(op, a):
     if b.size:
         _gz_check(G.ref_local_transform(LT_OPS[op], _ptr(b), b.size), "local transform")
     return b
+
+
+# ---------------------------------------------------------------- OQ (src/codec_oq.c)
+def _oq_args(txt, qoff, qlen):
+    return (np.ascontiguousarray(txt, np.uint8), np.ascontiguousarray(qoff, np.uint64), np.ascontiguousarray(qlen, np.uint32))
+
+
+def oq_mux(txt, qoff, qlen, ooff, seq_len=None, lib="port"):
+    """codec_oq_compress before its sub-codec -> (channels back to back, count[94], monochars[94]); None on an invalid QUAL character.
+    lib = "port" (the restatement, oracle/gz_port.c) or "ref" (the reference's compiled codec_oq.c, oracle/_ref)"""
+    txt, qoff, qlen = _oq_args(txt, qoff, qlen)
+    ooff = np.ascontiguousarray(ooff, np.uint64)
+    sl = None if seq_len is None else np.ascontiguousarray(seq_len, np.uint32)
+    chan = np.zeros(int(qlen.sum()) + 8, np.uint8); count = np.zeros(94, np.uint32); mono = np.zeros(94, np.uint8)
+    if lib == "port":
+        L = port()
+        L.orc_oq_mux.restype = C.c_int
+        L.orc_oq_mux.argtypes = [C.c_void_p] * 5 + [C.c_uint32] + [C.c_void_p] * 3
+        rc = L.orc_oq_mux(_ptr(txt), _ptr(qoff), _ptr(qlen), _ptr(ooff), None if sl is None else _ptr(sl), qlen.size, _ptr(chan), _ptr(count), _ptr(mono))
+    else:
+        L = gz_ref()
+        L.ref_oq_encode.restype = C.c_int
+        L.ref_oq_encode.argtypes = [C.c_void_p, C.c_uint64] + [C.c_void_p] * 4 + [C.c_uint32] + [C.c_void_p] * 3
+        sl2 = qlen if sl is None else sl
+        rc = L.ref_oq_encode(_ptr(txt), txt.size, _ptr(qoff), _ptr(qlen), _ptr(ooff), _ptr(sl2), qlen.size, _ptr(chan), _ptr(count), _ptr(mono))
+    if rc != 0:
+        return None
+    return chan[:int(count.sum())].copy(), count, mono
+
+
+def oq_demux(txt, qoff, qlen, out_off, out_size, key_bias, channels, count, mono, lib="port"):
+    """codec_oq_reconstruct for every line -> out; None when a channel runs out of data"""
+    txt, qoff, qlen = _oq_args(txt, qoff, qlen)
+    ooff = np.ascontiguousarray(out_off, np.uint64)
+    ch = np.ascontiguousarray(channels, np.uint8); ch = ch if ch.size else np.zeros(1, np.uint8)
+    count = np.ascontiguousarray(count, np.uint32); mono = np.ascontiguousarray(mono, np.uint8)
+    out = np.zeros(out_size + 8, np.uint8)
+    if lib == "port":
+        L = port()
+        L.orc_oq_demux.restype = C.c_int
+        L.orc_oq_demux.argtypes = [C.c_void_p] * 4 + [C.c_uint32, C.c_uint32] + [C.c_void_p] * 4
+        rc = L.orc_oq_demux(_ptr(txt), _ptr(qoff), _ptr(qlen), _ptr(ooff), qlen.size, key_bias, _ptr(ch), _ptr(count), _ptr(mono), _ptr(out))
+    else:
+        L = gz_ref()
+        L.ref_oq_decode.restype = C.c_int
+        L.ref_oq_decode.argtypes = [C.c_void_p, C.c_uint64] + [C.c_void_p] * 3 + [C.c_uint32, C.c_uint32] + [C.c_void_p] * 3 + [C.c_void_p, C.c_uint64]
+        rc = L.ref_oq_decode(_ptr(txt), txt.size, _ptr(qoff), _ptr(qlen), _ptr(ooff), qlen.size, key_bias, _ptr(ch), _ptr(count), _ptr(mono), _ptr(out), out_size)
+    if rc != 0:
+        return None
+    return out[:out_size].copy()
