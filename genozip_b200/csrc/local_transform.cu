@@ -114,3 +114,111 @@ extern "C" int gzb_local_transform_batch (gzb_engine *e, gzb_local_item *items, 
     CK (cudaGetLastError ());
     return GZB_OK;
 }
+
+
+// ------------------------------------------------------------------------------------------------ matrix transposes of a local buffer
+// dyn_int_transpose (src/dyn_int.c:45-105, the case without copied samples): a local of rows x cols integers (one row per line, one
+// column per sample or per item of an array field) is stored column by column, so that a column's similar values are neighbours for the
+// codec: trans[c * rows + r] = data[r * cols + c]; a local that is not a rectangle is left alone (:75-78).  PIZ: BGEN_transpose_u8/16/32_buf
+// (src/buffer.c:364-391): back to row by row, then from big endian.  Out of place through the engine's workspace (the reference goes
+// through vb->scratch), 32 x 32 tiles through shared memory so that both the reads and the writes are coalesced.
+namespace {
+
+struct TrItem { const void *in; void *out; unsigned long long R, C; uint32_t width, swap; unsigned long long first_tile, tiles_c; };
+
+template <typename U> __device__ __forceinline__ void tr_tile (const TrItem &it, unsigned long long tile, U (*sm)[33])
+{
+    const unsigned long long tr = tile / it.tiles_c, tc = tile % it.tiles_c;
+    const U *in = reinterpret_cast<const U *>(it.in); U *out = reinterpret_cast<U *>(it.out);
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;                        // 256 threads: 8 rows of the tile at a time
+    for (int k = ty; k < 32; k += 8) {
+        const unsigned long long r = tr * 32 + k, c = tc * 32 + tx;
+        if (r < it.R && c < it.C) sm[k][tx] = in[r * it.C + c];
+    }
+    __syncthreads ();
+    for (int k = ty; k < 32; k += 8) {
+        const unsigned long long c = tc * 32 + k, r = tr * 32 + tx;                // out is C x R
+        if (r < it.R && c < it.C) { const U v = sm[tx][k]; out[c * it.R + r] = it.swap ? bswap (v) : v; }
+    }
+    __syncthreads ();
+}
+
+__global__ void __launch_bounds__(256) k_local_transpose (const TrItem *items, const uint32_t *tile_item, unsigned long long n_tiles)
+{
+    __shared__ uint32_t sm32[32][33];
+    for (unsigned long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const TrItem it = items[tile_item[t >> 10]];                                // tiles are listed in groups of 1024
+        const unsigned long long tile = t - it.first_tile;
+        if (it.width == 1)      tr_tile<uint8_t>  (it, tile, reinterpret_cast<uint8_t (*)[33]>(sm32));
+        else if (it.width == 2) tr_tile<uint16_t> (it, tile, reinterpret_cast<uint16_t (*)[33]>(sm32));
+        else                    tr_tile<uint32_t> (it, tile, sm32);
+    }
+}
+
+} // namespace
+
+extern "C" int gzb_local_transpose_batch (gzb_engine *e, gzb_transpose_item *items, uint32_t n, uint32_t flags)
+{
+    if (!e || (!items && n)) return GZB_E_BADARG;
+    if (!n) return GZB_OK;
+    cudaSetDevice (e->device);
+    const bool devptr = flags & GZB_DEVICE_PTRS;
+    std::vector<TrItem> h (n);
+    std::vector<uint32_t> tile_item;                                                // one entry per group of 1024 tiles
+    unsigned long long n_tiles = 0;
+    size_t bytes_total = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        gzb_transpose_item &it = items[i];
+        const uint32_t w = it.width;
+        if ((w != 1 && w != 2 && w != 4) || !it.cols || it.dir > 1 || (!it.data && it.n_elems) || ((uintptr_t)it.data & (w - 1))) { it.status = GZB_E_BADARG; e->err = "bad transpose item"; return GZB_E_BADARG; }
+        it.status = GZB_OK; it.transposed = 0;
+        h[i] = TrItem ();
+        if (!it.n_elems) continue;
+        if (it.n_elems % it.cols) {                                                  // not a rectangle
+            if (it.dir == GZB_TR_PIZ) { it.status = GZB_E_CORRUPT; e->err = "transposed local is not a rectangle"; return GZB_E_CORRUPT; }
+            continue;                                                               // ZIP: left as it is (dyn_int.c:75-78)
+        }
+        const unsigned long long rows = it.n_elems / it.cols;
+        // ZIP reads rows x cols and writes cols x rows; PIZ reads cols x rows and writes rows x cols
+        h[i].R = it.dir == GZB_TR_ZIP ? rows : it.cols; h[i].C = it.dir == GZB_TR_ZIP ? it.cols : rows;
+        h[i].width = w; h[i].swap = it.dir == GZB_TR_PIZ && w > 1;
+        h[i].tiles_c = (h[i].C + 31) / 32;
+        n_tiles = (n_tiles + 1023) & ~1023ull;                                      // every item starts a new group
+        h[i].first_tile = n_tiles;
+        const unsigned long long t = ((h[i].R + 31) / 32) * h[i].tiles_c;
+        tile_item.insert (tile_item.end (), (size_t)((t + 1023) / 1024), i);
+        n_tiles += t;
+        it.transposed = 1;
+        bytes_total += ((size_t)it.n_elems * w + 255) & ~(size_t)255;
+    }
+    if (!n_tiles) return GZB_OK;
+    auto al = [] (size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t o_ti = al (n * sizeof (TrItem)), o_data = o_ti + al ((tile_item.size () + 1) * 4);
+    int rc = engine_reserve (e, o_data + bytes_total * (devptr ? 1 : 2), o_data + 256); if (rc) return rc;
+    cudaStream_t st = e->stream;
+    size_t cur = o_data;
+    for (uint32_t i = 0; i < n; i++) {
+        if (!items[i].transposed) continue;
+        const size_t bytes = (size_t)items[i].n_elems * items[i].width, ab = al (bytes);
+        if (devptr) h[i].in = items[i].data;
+        else { h[i].in = e->ws + cur; CK (cudaMemcpyAsync (e->ws + cur, items[i].data, bytes, cudaMemcpyHostToDevice, st)); cur += ab; }
+        h[i].out = e->ws + cur; cur += ab;
+    }
+    // an item whose tile range ends inside a group of 1024 shares the group's entry with nobody (the next item starts a new group), but the
+    // kernel's loop runs over the padding too: give the padding tiles of a group to their item as tiles past its end
+    memcpy (e->pin, h.data (), n * sizeof (TrItem));
+    memcpy (e->pin + o_ti, tile_item.data (), tile_item.size () * 4);
+    CK (cudaMemcpyAsync (e->ws, e->pin, n * sizeof (TrItem), cudaMemcpyHostToDevice, st));
+    CK (cudaMemcpyAsync (e->ws + o_ti, e->pin + o_ti, tile_item.size () * 4, cudaMemcpyHostToDevice, st));
+    const unsigned long long padded = (n_tiles + 1023) & ~1023ull;
+    const uint32_t grid = (uint32_t)std::min<unsigned long long> (padded, 148ull * 16);
+    k_local_transpose<<<grid, 256, 0, st>>>(reinterpret_cast<const TrItem *>(e->ws), reinterpret_cast<const uint32_t *>(e->ws + o_ti), padded); e->launches++;
+    for (uint32_t i = 0; i < n; i++) {
+        if (!items[i].transposed) continue;
+        const size_t bytes = (size_t)items[i].n_elems * items[i].width;
+        CK (cudaMemcpyAsync (items[i].data, h[i].out, bytes, devptr ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    }
+    CK (cudaStreamSynchronize (st));
+    CK (cudaGetLastError ());
+    return GZB_OK;
+}

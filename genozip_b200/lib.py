@@ -70,6 +70,11 @@ class OqVb(C.Structure):            # gzb_oq_vb
                 ("out", C.c_void_p), ("out_cap", C.c_uint64), ("out_off", C.c_void_p)]
 
 
+class TransposeItem(C.Structure):   # gzb_transpose_item
+    _fields_ = [("data", C.c_void_p), ("n_elems", C.c_uint64), ("cols", C.c_uint32), ("width", C.c_uint8), ("dir", C.c_uint8),
+                ("transposed", C.c_uint8), ("pad", C.c_uint8), ("status", C.c_int32), ("reserved", C.c_int32)]
+
+
 class LocalItem(C.Structure):       # gzb_local_item
     _fields_ = [("data", C.c_void_p), ("n_elems", C.c_uint64), ("op", C.c_int32), ("status", C.c_int32)]
 
@@ -170,6 +175,8 @@ def load():
     L.gzb_local_transform_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
     L.gzb_adler32_batch.restype = C.c_int
     L.gzb_adler32_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+    L.gzb_local_transpose_batch.restype = C.c_int
+    L.gzb_local_transpose_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
     L.gzb_assign_codecs.restype = C.c_int
     L.gzb_assign_codecs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
     L.gzb_pbwt_decode.restype = C.c_int
@@ -373,6 +380,18 @@ class Engine:
         if rc != 0:
             raise GzbError(f"gzb_adler32_batch failed ({rc}): {self._err()}")
         return [int(items[i].adler) for i in range(len(ptr_len))]
+
+    def local_transpose(self, items, piz=False):
+        """items: list of (array of uint8/16/32, cols) -> list of (array, transposed flag): dyn_int_transpose (ZIP) or BGEN_transpose_u*_buf (PIZ)"""
+        arr = (TransposeItem * max(1, len(items)))(); keep = []
+        for i, (a, cols) in enumerate(items):
+            a = np.ascontiguousarray(a).copy()
+            keep.append(a)
+            arr[i].data = a.ctypes.data if a.size else None; arr[i].n_elems = a.size; arr[i].cols = cols; arr[i].width = a.dtype.itemsize; arr[i].dir = 1 if piz else 0
+        rc = self.L.gzb_local_transpose_batch(self.h, arr, len(items), 0)
+        if rc != 0:
+            raise GzbError(f"gzb_local_transpose_batch failed ({rc}): {self._err()}")
+        return [(a, bool(arr[i].transposed)) for i, a in enumerate(keep)]
 
     # ---- OQ (host buffers) ----
     def oq_mux(self, vbs):

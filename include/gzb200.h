@@ -159,6 +159,15 @@ enum { GZB_LT_SWAP16 = 1, GZB_LT_SWAP32, GZB_LT_SWAP64, GZB_LT_INTERLACE8, GZB_L
 typedef struct { void *data; uint64_t n_elems; int32_t op; int32_t status; } gzb_local_item;
 int gzb_local_transform_batch (gzb_engine *e, gzb_local_item *items, uint32_t n, uint32_t flags);
 
+/* Matrix transposes of a local buffer (a rows x cols matrix of 8 / 16 / 32-bit integers, one row per line):
+ *   GZB_TR_ZIP  dyn_int_transpose (src/dyn_int.c:45-105, without copied samples): trans[c * rows + r] = data[r * cols + c]; n_elems not a
+ *               multiple of cols: left as it is, transposed = 0 (:75-78).  Runs after the endianness transform, as in zip_generate_local (src/zip.c:213-214).
+ *   GZB_TR_PIZ  BGEN_transpose_u8/16/32_buf (src/buffer.c:364-391): back to row by row, then from big endian.
+ * Device pointers with GZB_DEVICE_PTRS, else host memory. */
+enum { GZB_TR_ZIP = 0, GZB_TR_PIZ = 1 };
+typedef struct { void *data; uint64_t n_elems; uint32_t cols; uint8_t width /* bytes: 1, 2, 4 */; uint8_t dir; uint8_t transposed /* out */; uint8_t pad; int32_t status; int32_t reserved; } gzb_transpose_item;
+int gzb_local_transpose_batch (gzb_engine *e, gzb_transpose_item *items, uint32_t n, uint32_t flags);
+
 /* ---------------------------------------------------------------- ACGT / XCGT (src/codec_acgt.c)
  * pack:   codec_acgt_compress up to the sub-codec call (:64-163): bases → LE 2-bit words + exception stream.
  *         `packed` receives gzb_acgt_packed_len(n) bytes; `x` (n bytes) may be NULL if the caller declares

@@ -619,3 +619,24 @@ int orc_oq_demux (const uint8_t *txt, const uint64_t *qual_off, const uint32_t *
     }
     return 0;
 }
+
+/* ================================================================ matrix transposes of a local buffer
+ * zip = dyn_int_transpose (reference src/dyn_int.c:45-105, no copied samples): a local that is not a rectangle is left alone (:75-78, returns 0),
+ *       else trans[c * rows + r] = data[r * cols + c] (:88-91), returns 1.
+ * piz = BGEN_transpose_u8/16/32_buf (src/buffer.c:364-391): target[r * cols + c] = transposed[c * rows + r], then every element from big endian. */
+int orc_local_transpose (void *data, uint64_t n, uint32_t width, uint32_t cols, int piz)
+{
+    if (!n || !cols) return 0;
+    if (n % cols) return piz ? -1 : 0;
+    const uint64_t rows = n / cols;
+    uint8_t *in = data, *tmp = malloc (n * width);
+    for (uint64_t r = 0; r < rows; r++)
+        for (uint64_t c = 0; c < cols; c++) {
+            const uint8_t *s = piz ? in + (c * rows + r) * width : in + (r * cols + c) * width;
+            uint8_t *d       = piz ? tmp + (r * cols + c) * width : tmp + (c * rows + r) * width;
+            for (uint32_t k = 0; k < width; k++) d[k] = piz ? s[width - 1 - k] : s[k];          /* BGEN on a little-endian host */
+        }
+    memcpy (data, tmp, n * width);
+    free (tmp);
+    return 1;
+}

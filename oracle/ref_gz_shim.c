@@ -604,6 +604,48 @@ int ref_oq_decode (const uint8_t *txt, uint64_t txt_len, const uint64_t *qual_of
     return 0;
 }
 
+// ================================================================ dyn_int_transpose (the reference's compiled dyn_int.c)
+// what dyn_int.o wants from the rest of the program: the local-type table (the reference's own macro), and diagnostics the harness never reaches
+const LocalTypeDesc lt_desc[NUM_LOCAL_TYPES] = LOCALTYPE_DESC;
+rom lt_name (LocalType lt) { return "lt"; }
+rom store_type_name (StoreType store) { return "store"; }
+DataTypeProperties dt_props[NUM_DATATYPES], dt_props_def;
+FileMode READ = "rb";
+StrText char_to_printable (char c) { StrText t = {}; t.s[0] = c; return t; }
+StrText1K str_time (void) { StrText1K t = {}; return t; }
+StrText1K seg_error (VBlockP vb) { StrText1K t = {}; return t; }
+noreturn void error_assertinp_failed (rom format, ...) { snprintf (abort_msg, sizeof abort_msg, "ASSINP %s", format); longjmp (on_abort, 1); }
+static uint32_t shim_num_samples;
+uint32_t vcf_header_get_num_samples (void) { return shim_num_samples; }
+StrText1K str_str_s_ (rom label, STRp(str)) { StrText1K t = {}; return t; }
+// lt_desc's file-to-native functions (buffer.c): the table needs their addresses, the harness never calls them
+#define SHIM_LT_FN(f) void f (BufferP buf, LocalType *lt) { ABORT0 ("shim: " #f); }
+SHIM_LT_FN (BGEN_deinterlace_d8_buf) SHIM_LT_FN (BGEN_deinterlace_d16_buf) SHIM_LT_FN (BGEN_deinterlace_d32_buf) SHIM_LT_FN (BGEN_deinterlace_d64_buf)
+SHIM_LT_FN (BGEN_ptranspose_u8_buf) SHIM_LT_FN (BGEN_ptranspose_u16_buf) SHIM_LT_FN (BGEN_ptranspose_u32_buf)
+SHIM_LT_FN (BGEN_transpose_u8_buf) SHIM_LT_FN (BGEN_transpose_u16_buf) SHIM_LT_FN (BGEN_transpose_u32_buf)
+SHIM_LT_FN (BGEN_u8_buf) SHIM_LT_FN (BGEN_u16_buf) SHIM_LT_FN (BGEN_u64_buf)
+
+// dyn_int_transpose on a local of n elements of `width` bytes: cols > 0 goes to local.n_cols (<= 255), cols_vcf to the number of samples
+// of the VCF header (n_cols stays 0).  *transposed = the ltype became LT_UINT*_TR.
+int ref_dyn_int_transpose (void *data, uint64_t n, uint32_t width, uint32_t cols, uint32_t cols_vcf, int *transposed)
+{
+    shim_init ();
+    if (setjmp (on_abort)) return -1;
+    VBlockP vb = calloc (1, sizeof (VBlock));
+    vb->vblock_i = 1; vb->data_type = DT_VCF;
+    shim_num_samples = cols_vcf;
+    ContextP ctx = CTX (VCF_COPY_SAMPLE + 1);
+    ctx->did_i = VCF_COPY_SAMPLE + 1; strcpy (ctx->tag_name, "shim");
+    ctx->ltype = width == 1 ? LT_UINT8 : width == 2 ? LT_UINT16 : LT_UINT32;
+    buf_alloc_do (vb, &ctx->local, n * width + 8, 1, "local", __FUNCLINE);
+    memcpy (ctx->local.data, data, n * width); ctx->local.len = n; ctx->local.n_cols = cols;
+    dyn_int_transpose (vb, ctx);
+    *transposed = ctx->ltype == LT_UINT8_TR || ctx->ltype == LT_UINT16_TR || ctx->ltype == LT_UINT32_TR;
+    memcpy (data, ctx->local.data, n * width);
+    free (vb);
+    return 0;
+}
+
 // ================================================================ zip_generate_local's transforms: the reference's own macros
 // (INTERLACE / DEINTERLACE of context.h:98-101, BGEN16/32/64 of endianness.h) in the loops of buffer.c:337-345, :431-468
 int ref_local_transform (int op, void *data, uint64_t n)

@@ -529,3 +529,27 @@ def oq_demux(txt, qoff, qlen, out_off, out_size, key_bias, channels, count, mono
     if rc != 0:
         return None
     return out[:out_size].copy()
+
+
+# ---------------------------------------------------------------- dyn_int_transpose / BGEN_transpose_u*_buf
+def local_transpose(a, cols, piz=False):
+    """restatement -> (array, transposed flag)"""
+    L = port()
+    L.orc_local_transpose.restype = C.c_int
+    L.orc_local_transpose.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int]
+    a = np.ascontiguousarray(a).copy()
+    rc = L.orc_local_transpose(_ptr(a) if a.size else None, a.size, a.dtype.itemsize, cols, 1 if piz else 0)
+    assert rc >= 0
+    return a, bool(rc)
+
+
+def ref_dyn_int_transpose(a, cols, cols_vcf=0):
+    """the reference's compiled dyn_int_transpose (oracle/_ref) -> (array, transposed flag)"""
+    L = gz_ref()
+    L.ref_dyn_int_transpose.restype = C.c_int
+    L.ref_dyn_int_transpose.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+    a = np.ascontiguousarray(a).copy()
+    tr = C.c_int(0)
+    rc = L.ref_dyn_int_transpose(_ptr(a), a.size, a.dtype.itemsize, cols, cols_vcf, C.byref(tr))
+    assert rc == 0, rc
+    return a, bool(tr.value)
