@@ -75,6 +75,11 @@ class TransposeItem(C.Structure):   # gzb_transpose_item
                 ("transposed", C.c_uint8), ("pad", C.c_uint8), ("status", C.c_int32), ("reserved", C.c_int32)]
 
 
+class B250Item(C.Structure):        # gzb_b250_item
+    _fields_ = [("b250", C.c_void_p), ("len", C.c_uint64), ("out", C.c_void_p), ("ni2wi", C.c_void_p), ("n_new", C.c_uint32), ("ol_len", C.c_uint32),
+                ("one_up_ok", C.c_uint8), ("pad", C.c_uint8 * 3), ("status", C.c_int32), ("out_len", C.c_uint64), ("n_words", C.c_uint64)]
+
+
 class LocalItem(C.Structure):       # gzb_local_item
     _fields_ = [("data", C.c_void_p), ("n_elems", C.c_uint64), ("op", C.c_int32), ("status", C.c_int32)]
 
@@ -175,6 +180,8 @@ def load():
     L.gzb_local_transform_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
     L.gzb_adler32_batch.restype = C.c_int
     L.gzb_adler32_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+    L.gzb_b250_generate_batch.restype = C.c_int
+    L.gzb_b250_generate_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
     L.gzb_local_transpose_batch.restype = C.c_int
     L.gzb_local_transpose_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
     L.gzb_assign_codecs.restype = C.c_int
@@ -380,6 +387,21 @@ class Engine:
         if rc != 0:
             raise GzbError(f"gzb_adler32_batch failed ({rc}): {self._err()}")
         return [int(items[i].adler) for i in range(len(ptr_len))]
+
+    def b250_generate(self, items):
+        """items: list of (b250 bytes as the segmenter left them, ni2wi int32 array, ol_len, one_up_ok) -> list of (converted bytes, n_words):
+        b250_zip_generate (b250.c:202-297)"""
+        arr = (B250Item * max(1, len(items)))(); keep = []
+        for i, (b, t, ol, up) in enumerate(items):
+            b = np.ascontiguousarray(b, np.uint8); t = np.ascontiguousarray(t, np.int32); out = np.zeros(b.size + 8, np.uint8)
+            keep.append((b, t, out))
+            a = arr[i]
+            a.b250 = b.ctypes.data if b.size else None; a.len = b.size; a.out = out.ctypes.data; a.ni2wi = t.ctypes.data if t.size else None
+            a.n_new = t.size; a.ol_len = ol; a.one_up_ok = 1 if up else 0
+        rc = self.L.gzb_b250_generate_batch(self.h, arr, len(items), 0)
+        if rc != 0:
+            raise GzbError(f"gzb_b250_generate_batch failed ({rc}): {self._err()}")
+        return [(k[2][k[0].size - int(arr[i].out_len):k[0].size].copy(), int(arr[i].n_words)) for i, k in enumerate(keep)]
 
     def local_transpose(self, items, piz=False):
         """items: list of (array of uint8/16/32, cols) -> list of (array, transposed flag): dyn_int_transpose (ZIP) or BGEN_transpose_u*_buf (PIZ)"""

@@ -168,6 +168,28 @@ enum { GZB_TR_ZIP = 0, GZB_TR_PIZ = 1 };
 typedef struct { void *data; uint64_t n_elems; uint32_t cols; uint8_t width /* bytes: 1, 2, 4 */; uint8_t dir; uint8_t transposed /* out */; uint8_t pad; int32_t status; int32_t reserved; } gzb_transpose_item;
 int gzb_local_transpose_batch (gzb_engine *e, gzb_transpose_item *items, uint32_t n, uint32_t flags);
 
+/* ---------------------------------------------------------------- b250_zip_generate (src/b250.c:202-297) for a batch of contexts
+ * `b250` = the context's b250 buffer as the segmenter left it (little-endian variable-length words, the type in the LAST byte, :137-164);
+ * `out` (len bytes, another buffer) receives the PIZ form (big endian, type first), right-aligned as the reference leaves it in its own
+ * buffer: the result is the last out_len bytes (the adapter points ctx->b250.data there, :276-281).  On the way node indices >= ol_len
+ * become ni2wi[node_index - ol_len] (node_index_to_word_index, src/context.h:109-112) and a word equal to its predecessor + 1 becomes
+ * ONE_UP when one_up_ok (nodes.len + ol_nodes.len32 > 1024, :247).  What follows in the reference — the pair-identical test and
+ * codec_assign_best_codec (:283-296) — stays with the caller (gzb_assign_codecs for the latter).
+ * GZB_E_CORRUPT: the words do not tile the buffer, or a word index that cannot be encoded.  Device pointers with GZB_DEVICE_PTRS. */
+typedef struct {
+    const void    *b250;     uint64_t len;
+    void          *out;
+    const int32_t *ni2wi;    /* B(WordIndex, vctx->nodes, i) after conversion */
+    uint32_t       n_new;    /* vctx->nodes.len */
+    uint32_t       ol_len;   /* vctx->ol_nodes.len32 */
+    uint8_t        one_up_ok;
+    uint8_t        pad[3];
+    int32_t        status;
+    uint64_t       out_len;  /* out */
+    uint64_t       n_words;  /* out */
+} gzb_b250_item;
+int gzb_b250_generate_batch (gzb_engine *e, gzb_b250_item *items, uint32_t n, uint32_t flags);
+
 /* ---------------------------------------------------------------- ACGT / XCGT (src/codec_acgt.c)
  * pack:   codec_acgt_compress up to the sub-codec call (:64-163): bases → LE 2-bit words + exception stream.
  *         `packed` receives gzb_acgt_packed_len(n) bytes; `x` (n bytes) may be NULL if the caller declares

@@ -640,3 +640,49 @@ int orc_local_transpose (void *data, uint64_t n, uint32_t width, uint32_t cols, 
     free (tmp);
     return 1;
 }
+
+/* ================================================================ b250_zip_generate (reference src/b250.c:202-297)
+ * The backward scan over the segmenter's words (type in the last byte, b250_seg_get_wi :64-86), node index -> word index for the words
+ * new to this VBlock (context.h:109-112), ONE_UP (:265-266), b250_set_wi in PIZ format (:89-121).  out (len bytes) gets the result
+ * right-aligned; returns its length, or -1 if the words do not tile the buffer / a word index cannot be encoded. */
+static int32_t b250_get_wi (const uint8_t *b, int64_t p, int *L)
+{
+    const uint8_t msb = b[p];
+    *L = (msb >> 7) == 0 ? 1 : (msb >> 6) == 2 ? 2 : (msb >> 5) == 6 ? 3 : 4;                     /* VARL_BYTES :47 */
+    if (p - *L + 1 < 0) return INT32_MIN;
+    if (*L == 1) return msb;
+    if (*L == 2) { const uint32_t w = b[p - 1] | ((uint32_t)b[p] << 8); return w == 0xBFFE ? -3 : w == 0xBFFF ? -4 : (int32_t)(w & 0x3fff) + 127; }
+    if (*L == 3) return (int32_t)((b[p - 2] | ((uint32_t)b[p - 1] << 8) | ((uint32_t)b[p] << 16)) & 0x1fffff) + 16509;
+    return (int32_t)((b[p - 3] | ((uint32_t)b[p - 2] << 8) | ((uint32_t)b[p - 1] << 16) | ((uint32_t)b[p] << 24)) & 0x1fffffff);
+}
+int64_t orc_b250_generate (const uint8_t *b250, uint64_t len, const int32_t *ni2wi, uint32_t n_new, uint32_t ol_len, int one_up_ok, uint8_t *out, uint64_t *n_words)
+{
+    int64_t src = (int64_t)len - 1, dst = (int64_t)len;                                            /* dst: one past where the next word ends */
+    *n_words = 0;
+    while (src >= 0) {
+        int L, pL = 0;
+        int32_t wi = b250_get_wi (b250, src, &L);
+        if (wi == INT32_MIN) return -1;
+        if (wi >= (int32_t)ol_len) { if ((uint32_t)wi - ol_len >= n_new) return -1; wi = ni2wi[wi - ol_len]; }
+        int32_t prev = -1;                                                                          /* WORD_INDEX_NONE */
+        if (src - L >= 0) {
+            prev = b250_get_wi (b250, src - L, &pL);
+            if (prev == INT32_MIN) return -1;
+            if (prev >= (int32_t)ol_len) { if ((uint32_t)prev - ol_len >= n_new) return -1; prev = ni2wi[prev - ol_len]; }
+        }
+        if (one_up_ok && prev >= 0 && wi >= 0 && wi == prev + 1) wi = -2;                          /* WORD_INDEX_ONE_UP */
+        uint32_t enc; int n;
+        if (wi >= 0 && wi <= 126) { enc = wi; n = 1; }
+        else if (wi >= 127 && wi <= 16508) { enc = (2u << 14) | (uint32_t)(wi - 127); n = 2; }
+        else if (wi >= 16509 && wi <= 2113660) { enc = (6u << 21) | (uint32_t)(wi - 16509); n = 3; }
+        else if (wi > 2113660 && wi <= (1 << 29) - 1) { enc = (7u << 29) | (uint32_t)wi; n = 4; }
+        else if (wi == -2) { enc = 127; n = 1; }
+        else if (wi == -3) { enc = 0xBFFE; n = 2; }
+        else if (wi == -4) { enc = 0xBFFF; n = 2; }
+        else return -1;
+        dst -= n;
+        for (int k = 0; k < n; k++) out[dst + k] = (uint8_t)(enc >> (8 * (n - 1 - k)));
+        src -= L; (*n_words)++;
+    }
+    return (int64_t)len - dst;
+}

@@ -34,6 +34,7 @@
 #include "fastq.h"
 #include "vcf.h"
 #include "sections.h"
+#include "b250.h"
 #include <stdarg.h>
 #include <setjmp.h>
 
@@ -642,6 +643,33 @@ int ref_dyn_int_transpose (void *data, uint64_t n, uint32_t width, uint32_t cols
     dyn_int_transpose (vb, ctx);
     *transposed = ctx->ltype == LT_UINT8_TR || ctx->ltype == LT_UINT16_TR || ctx->ltype == LT_UINT32_TR;
     memcpy (data, ctx->local.data, n * width);
+    free (vb);
+    return 0;
+}
+
+// ================================================================ b250_zip_generate (the reference's compiled b250.c)
+bool is_fastq_pair_2 (VBlockP vb) { return false; }
+bool fastq_zip_use_pair_identical (DictId dict_id) { return false; }
+void ctx_decrement_count (VBlockP vb, ContextP ctx, WordIndex node_index) {}
+
+// b250_zip_generate on a hand-made context: b250 = the segmenter's buffer, nodes = the word indices of the VBlock's new nodes.  out gets the converted
+// buffer (it is the tail of the input buffer in the reference), *out_len its length
+int ref_b250_generate (const uint8_t *b250, uint64_t len, const int32_t *ni2wi, uint32_t n_new, uint32_t ol_len, uint8_t *out, uint64_t *out_len)
+{
+    shim_init ();
+    if (setjmp (on_abort)) return -1;
+    VBlockP vb = calloc (1, sizeof (VBlock));
+    vb->vblock_i = 1; vb->data_type = DT_SAM;
+    ContextP ctx = CTX (SAM_RNAME);
+    ctx->did_i = SAM_RNAME; strcpy (ctx->tag_name, "shim"); ctx->dict_id.num = 12345; ctx->nodes_converted = true;
+    buf_alloc_do (vb, &ctx->b250, len + 8, 1, "b250", __FUNCLINE);
+    memcpy (ctx->b250.data, b250, len); ctx->b250.len = len; ctx->b250.count = 2;                    // (count only matters with all_the_same)
+    buf_alloc_do (vb, &ctx->nodes, (uint64_t)n_new * sizeof (WordIndex) + 8, 1, "nodes", __FUNCLINE);
+    memcpy (ctx->nodes.data, ni2wi, (uint64_t)n_new * sizeof (WordIndex)); ctx->nodes.len = n_new;
+    ctx->ol_nodes.len = ol_len;
+    b250_zip_generate (vb, ctx);
+    *out_len = ctx->b250.len;
+    memcpy (out, ctx->b250.data, ctx->b250.len);
     free (vb);
     return 0;
 }

@@ -553,3 +553,30 @@ def ref_dyn_int_transpose(a, cols, cols_vcf=0):
     rc = L.ref_dyn_int_transpose(_ptr(a), a.size, a.dtype.itemsize, cols, cols_vcf, C.byref(tr))
     assert rc == 0, rc
     return a, bool(tr.value)
+
+
+# ---------------------------------------------------------------- b250_zip_generate (src/b250.c:202-297)
+def b250_generate(b250, ni2wi, ol_len, one_up_ok, lib="port"):
+    """-> (converted buffer, n_words) or None (the words do not tile the buffer / a word index cannot be encoded).
+    lib = "ref": the reference's compiled b250.c — it decides one_up_ok itself (nodes.len + ol_nodes.len > 1024, :247)"""
+    b = np.ascontiguousarray(b250, np.uint8); t = np.ascontiguousarray(ni2wi, np.int32)
+    out = np.zeros(b.size + 8, np.uint8)
+    bp = _ptr(b) if b.size else _ptr(out); tp = _ptr(t) if t.size else _ptr(out)
+    if lib == "port":
+        L = port()
+        L.orc_b250_generate.restype = C.c_int64
+        L.orc_b250_generate.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
+        nw = C.c_uint64()
+        n = L.orc_b250_generate(bp, b.size, tp, t.size, ol_len, 1 if one_up_ok else 0, _ptr(out), C.byref(nw))
+        if n < 0:
+            return None
+        return out[b.size - n:b.size].copy(), int(nw.value)
+    L = gz_ref()
+    L.ref_b250_generate.restype = C.c_int
+    L.ref_b250_generate.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+    assert one_up_ok == (t.size + ol_len > 1024)
+    n = C.c_uint64()
+    rc = L.ref_b250_generate(bp, b.size, tp, t.size, ol_len, _ptr(out), C.byref(n))
+    if rc != 0:
+        return None
+    return out[:n.value].copy(), None
