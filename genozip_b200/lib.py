@@ -80,6 +80,12 @@ class B250Item(C.Structure):        # gzb_b250_item
                 ("one_up_ok", C.c_uint8), ("pad", C.c_uint8 * 3), ("status", C.c_int32), ("out_len", C.c_uint64), ("n_words", C.c_uint64)]
 
 
+class HompVb(C.Structure):          # gzb_homp_vb
+    _fields_ = [("txt", C.c_void_p), ("txt_len", C.c_uint64), ("str_off", C.c_void_p), ("str_len", C.c_void_p), ("seq_off", C.c_void_p),
+                ("n_lines", C.c_uint32), ("status", C.c_int32), ("local", C.c_void_p), ("local_cap", C.c_uint64), ("local_len", C.c_uint64),
+                ("new_len", C.c_void_p), ("out", C.c_void_p), ("out_cap", C.c_uint64), ("missing", C.c_void_p)]
+
+
 class LocalItem(C.Structure):       # gzb_local_item
     _fields_ = [("data", C.c_void_p), ("n_elems", C.c_uint64), ("op", C.c_int32), ("status", C.c_int32)]
 
@@ -180,6 +186,8 @@ def load():
     L.gzb_local_transform_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
     L.gzb_adler32_batch.restype = C.c_int
     L.gzb_adler32_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+    for f in ("gzb_homp_condense", "gzb_homp_expand"):
+        getattr(L, f).restype = C.c_int; getattr(L, f).argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_uint32]
     L.gzb_b250_generate_batch.restype = C.c_int
     L.gzb_b250_generate_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
     L.gzb_local_transpose_batch.restype = C.c_int
@@ -387,6 +395,41 @@ class Engine:
         if rc != 0:
             raise GzbError(f"gzb_adler32_batch failed ({rc}): {self._err()}")
         return [int(items[i].adler) for i in range(len(ptr_len))]
+
+    # ---- HOMP / T0 (host buffers) ----
+    def hp_condense(self, mode, vbs):
+        """vbs: list of (txt, str_off, str_len, seq_off) -> list of (condensed strings back to back, new lengths): the first pass of
+        codec_homp_compress (mode 0) / codec_t0_compress (mode 1)"""
+        arr = (HompVb * max(1, len(vbs)))(); keep = []
+        for i, (txt, so, sl, qo) in enumerate(vbs):
+            txt = np.ascontiguousarray(txt, np.uint8); so = np.ascontiguousarray(so, np.uint64); sl = np.ascontiguousarray(sl, np.uint32); qo = np.ascontiguousarray(qo, np.uint64)
+            out = np.zeros(int(sl.sum()) + 16, np.uint8); nl = np.zeros(sl.size + 1, np.uint32)
+            keep.append((txt, so, sl, qo, out, nl))
+            a = arr[i]
+            a.txt = txt.ctypes.data if txt.size else None; a.txt_len = txt.size; a.n_lines = sl.size
+            a.str_off = so.ctypes.data if so.size else None; a.str_len = sl.ctypes.data if sl.size else None; a.seq_off = qo.ctypes.data if qo.size else None
+            a.local = out.ctypes.data; a.local_cap = out.size; a.new_len = nl.ctypes.data
+        rc = self.L.gzb_homp_condense(self.h, arr, len(vbs), mode, 0)
+        if rc != 0:
+            raise GzbError(f"gzb_homp_condense failed ({rc}): {self._err()}")
+        return [(k[4][:int(arr[i].local_len)].copy(), k[5][:k[2].size].copy()) for i, k in enumerate(keep)]
+
+    def hp_expand(self, mode, vbs):
+        """vbs: list of (local, txt, seq_off, lens) -> list of (lens[i] bytes per line, missing flags): codec_homp_reconstruct / codec_t0_reconstruct for every line"""
+        arr = (HompVb * max(1, len(vbs)))(); keep = []
+        for i, (local, txt, qo, sl) in enumerate(vbs):
+            local = np.ascontiguousarray(local, np.uint8); txt = np.ascontiguousarray(txt, np.uint8); qo = np.ascontiguousarray(qo, np.uint64); sl = np.ascontiguousarray(sl, np.uint32)
+            out = np.zeros(int(sl.sum()) + 16, np.uint8); miss = np.zeros(sl.size + 1, np.uint8)
+            keep.append((local, txt, qo, sl, out, miss))
+            a = arr[i]
+            a.txt = txt.ctypes.data if txt.size else None; a.txt_len = txt.size; a.n_lines = sl.size
+            a.str_len = sl.ctypes.data if sl.size else None; a.seq_off = qo.ctypes.data if qo.size else None
+            a.local = local.ctypes.data if local.size else None; a.local_len = local.size
+            a.out = out.ctypes.data; a.out_cap = out.size; a.missing = miss.ctypes.data
+        rc = self.L.gzb_homp_expand(self.h, arr, len(vbs), mode, 0)
+        if rc != 0:
+            raise GzbError(f"gzb_homp_expand failed ({rc}): {self._err()}")
+        return [(k[4][:int(k[3].sum())].copy(), k[5][:k[3].size].copy()) for k in keep]
 
     def b250_generate(self, items):
         """items: list of (b250 bytes as the segmenter left them, ni2wi int32 array, ol_len, one_up_ok) -> list of (converted bytes, n_words):

@@ -287,6 +287,34 @@ typedef struct gzb_normq_vb {
 int gzb_normq_gather      (gzb_engine *e, gzb_normq_vb *vbs, uint32_t n_vbs, uint32_t flags);
 int gzb_normq_reconstruct (gzb_engine *e, gzb_normq_vb *vbs, uint32_t n_vbs, uint32_t flags);
 
+/* ---------------------------------------------------------------- HOMP and T0 (src/codec_homp.c, src/codec_t0.c): Ultima's homopolymer codecs
+ * condense: the first pass of codec_homp_compress (:132-190, mode GZB_HP_HOMP, the string is QUAL) / codec_t0_compress (:69-109, mode
+ *           GZB_HP_T0, the string is t0:Z): every homopolymer run of the read's SEQ keeps the part of its string that is not implied — the
+ *           first half of a palindrome up to its first 'I' (HOMP), one character of a constant run (T0) — or, when the run does not
+ *           comply, its first character | 0x80 and the rest.  The condensed strings come back to back in `local` (what the sub-codec
+ *           reads through the line callback after sam_update_qual_len / sam_ultima_update_t0_len), new_len[i] = each line's new length.
+ *               in  txt, str_off, str_len, seq_off (SEQ has the string's length), n_lines      out  local, local_len, new_len (optional)
+ * expand:   codec_homp_reconstruct (:213-276) / codec_t0_reconstruct (:137-179) for every line of a VBlock in order: str_len[i] = the `len`
+ *           of the i-th call.  HOMP: a line whose next byte is ' ' has no quality (one byte consumed, missing[i] set, the '*' of
+ *           sam_reconstruct_missing_quality at the start of its slot).  Its deep / translated-to-FASTQ variants (:222-234) are not covered.
+ *               in  local, local_len, txt + seq_off (the reconstructed SEQ), str_len      out  out (str_len[i] bytes per line, back to back), missing
+ * GZB_E_CORRUPT when the stream does not match the lines.  Device pointers with GZB_DEVICE_PTRS (then local_cap / out_cap bound the work). */
+enum { GZB_HP_HOMP = 0, GZB_HP_T0 = 1 };
+typedef struct gzb_homp_vb {
+    const void     *txt;        uint64_t txt_len;
+    const uint64_t *str_off;    /* condense */
+    const uint32_t *str_len;
+    const uint64_t *seq_off;
+    uint32_t        n_lines;
+    int32_t         status;
+    void           *local;      uint64_t local_cap, local_len;
+    uint32_t       *new_len;    /* condense, optional */
+    void           *out;        uint64_t out_cap;
+    uint8_t        *missing;    /* expand, optional */
+} gzb_homp_vb;
+int gzb_homp_condense (gzb_engine *e, gzb_homp_vb *vbs, uint32_t n_vbs, int mode, uint32_t flags);
+int gzb_homp_expand   (gzb_engine *e, gzb_homp_vb *vbs, uint32_t n_vbs, int mode, uint32_t flags);
+
 /* ---------------------------------------------------------------- OQ (src/codec_oq.c): a read's original quality string OQ:Z multiplexed by its QUAL
  * mux:   codec_oq_compress before its sub-codec (:54-121).  The OQ character at position i of a line goes to channel QUAL[i] - '!' (94
  *        channels); count[] = the QUAL characters of ALL lines per channel (the reference's count pass, :61-72, which sizes the channels),

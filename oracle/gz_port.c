@@ -686,3 +686,63 @@ int64_t orc_b250_generate (const uint8_t *b250, uint64_t len, const int32_t *ni2
     }
     return (int64_t)len - dst;
 }
+
+/* ================================================================ HOMP and T0 (reference src/codec_homp.c, src/codec_t0.c)
+ * mode 0 = HOMP (the string is QUAL), 1 = T0 (the string is t0:Z).
+ * condense = the first pass of codec_homp_compress (:132-190) / codec_t0_compress (:69-109): the condensed strings back to back, new_len per line.
+ * expand   = codec_homp_reconstruct (:213-276) / codec_t0_reconstruct (:137-179) line by line; returns -1 when the stream does not match. */
+static unsigned hp_len_at (const uint8_t *seq, uint32_t len, uint32_t i) { uint32_t k = i + 1; while (k < len && seq[k] == seq[i]) k++; return k - i; }   /* strings.h:194-201 */
+uint64_t orc_hp_condense (int mode, const uint8_t *txt, const uint64_t *str_off, const uint32_t *str_len, const uint64_t *seq_off, uint32_t n_lines, uint8_t *local, uint32_t *new_len)
+{
+    uint64_t at = 0;
+    for (uint32_t li = 0; li < n_lines; li++) {
+        const uint8_t *s = txt + str_off[li], *seq = txt + seq_off[li]; const uint32_t len = str_len[li];
+        uint8_t *d = local + at; uint32_t n = 0;
+        if (mode == 0 ? len <= 1 : len == 0) { memcpy (d, s, len); n = len; }                      /* homp :137, t0 :75 */
+        else for (uint32_t i = 0; i < len; i++) {
+            const unsigned h = hp_len_at (seq, len, i);
+            if (h > 1) {
+                int ok = 1;
+                if (mode == 1) { for (unsigned k = 1; k < h && ok; k++) ok = s[i + k] == s[i]; }     /* t0 :84 */
+                else { uint8_t prev = 0; for (unsigned k = 0; k < (h + 1) / 2; k++) { uint8_t a = s[i + k], m = s[i + h - 1 - k]; if (a != m || (prev == 'I' && a != 'I')) { ok = 0; break; } prev = a; } }   /* homp :152-165 */
+                if (ok) { if (mode == 1) d[n++] = s[i]; else for (unsigned k = 0; k < (h + 1) / 2; k++) { d[n++] = s[i + k]; if (s[i + k] == 'I') break; } }   /* :167-170 */
+                else { d[n++] = s[i] | 0x80; for (unsigned k = 1; k < h; k++) d[n++] = s[i + k]; }  /* :171-176 */
+                i += h - 1;
+            }
+            else d[n++] = s[i];
+        }
+        if (new_len) new_len[li] = n;
+        at += n;
+    }
+    return at;
+}
+int orc_hp_expand (int mode, const uint8_t *local, uint64_t local_len, const uint8_t *txt, const uint64_t *seq_off, const uint32_t *len, uint32_t n_lines, uint8_t *out, uint8_t *missing)
+{
+    uint64_t next = 0;
+    for (uint32_t li = 0; li < n_lines; li++) {
+        const uint32_t L = len[li]; const uint8_t *seq = txt + seq_off[li];
+        if (missing) missing[li] = 0;
+        if (!L) continue;
+        if (next >= local_len) return -1;
+        if (mode == 0 && local[next] == ' ') { out[0] = '*'; if (missing) missing[li] = 1; next++; out += L; continue; }   /* homp :241-244 */
+        uint32_t n = 0;
+        for (uint32_t i = 0; i < L; i++) {
+            const unsigned h = hp_len_at (seq, L, i);
+            if (next >= local_len) return -1;
+            if (h > 1) {
+                if (local[next] & 0x80) { if (next + h > local_len) return -1; out[n++] = local[next++] & 0x7f; for (unsigned k = 1; k < h; k++) out[n++] = local[next++]; }
+                else if (mode == 1) { const uint8_t c = local[next++]; for (unsigned k = 0; k < h; k++) out[n++] = c; }
+                else {
+                    uint8_t prev = 0;
+                    for (unsigned k = 0; k < (h + 1) / 2; k++) { if (prev != 'I') { if (next >= local_len) return -1; prev = local[next++]; } out[n++] = prev; }
+                    uint32_t m = n - 1 - (h & 1);
+                    for (unsigned k = 0; k < h / 2; k++) out[n++] = out[m--];
+                }
+                i += h - 1;
+            }
+            else out[n++] = local[next++];
+        }
+        out += L;
+    }
+    return next == local_len ? 0 : -1;
+}

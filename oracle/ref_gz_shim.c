@@ -160,6 +160,12 @@ void sam_xcons_split_qual_line (VBlockP vb, BufferP ql_buf) { ABORT0 ("shim: sam
 static uint8_t *cap_out; static uint32_t cap_len;
 static COMPRESS (shim_store)
 {
+    if (!uncompressed && get_line_cb) {                                    // a sub-codec reads its data line by line (codec_homp.c:202, codec_t0.c:121)
+        uint32_t at = 0;
+        for (uint32_t li = 0; li < vb->lines.len32; li++) { char *d; uint32_t n; get_line_cb (vb, ctx, li, &d, &n, *uncompressed_len - at, NULL); memcpy (compressed + at, d, n); at += n; }
+        *compressed_len = at; cap_out = (uint8_t *)compressed; cap_len = at;
+        return true;
+    }
     memcpy (compressed, uncompressed, *uncompressed_len);
     *compressed_len = *uncompressed_len;
     cap_out = (uint8_t *)compressed; cap_len = *uncompressed_len;
@@ -672,6 +678,83 @@ int ref_b250_generate (const uint8_t *b250, uint64_t len, const int32_t *ni2wi, 
     memcpy (out, ctx->b250.data, ctx->b250.len);
     free (vb);
     return 0;
+}
+
+// ================================================================ HOMP and T0 (the reference's compiled codec_homp.c, codec_t0.c)
+static uint32_t *g_newlen;                                                  // the lines' lengths as the codec shortens them
+static COMPRESSOR_CALLBACK (shim_get_line_newlen)
+{
+    *line_data = (char *)g_txt + g_off[vb_line_i];
+    *line_data_len = g_newlen[vb_line_i];
+    if (is_rev) *is_rev = 0;
+}
+void sam_update_qual_len (VBlockP vb, uint32_t line_i, uint32_t new_len)      { g_newlen[line_i] = new_len; }
+void fastq_update_qual_len (VBlockP vb, uint32_t line_i, uint32_t new_len)    { g_newlen[line_i] = new_len; }
+void sam_ultima_update_t0_len (VBlockP vb, uint32_t line_i, uint32_t new_len) { g_newlen[line_i] = new_len; }
+COMPRESSOR_CALLBACK (sam_zip_t0) { shim_get_line_newlen (vb, ctx, vb_line_i, line_data, line_data_len, maximum_size, is_rev); }
+QualHistType did_i_to_qht (Did did_i) { return QHT_QUAL; }
+
+// codec_homp_compress (mode 0) / codec_t0_compress (mode 1) on n_lines strings: what the sub-codec receives (the condensed strings, line by line)
+int ref_hp_condense (int mode, const uint8_t *txt, uint64_t txt_len, const uint64_t *str_off, const uint32_t *str_len, const uint64_t *seq_off, uint32_t n_lines,
+                     uint8_t *local, uint64_t *local_len, uint32_t *new_len)
+{
+    shim_init ();
+    if (setjmp (on_abort)) return -1;
+    VBlockP vb = calloc (1, sizeof (VBlock));
+    vb->vblock_i = 1; vb->lines.len = n_lines; vb->data_type = DT_SAM;
+    g_txt = malloc (txt_len + 1); memcpy (g_txt, txt, txt_len);             // the codec condenses the lines in place
+    g_off = str_off; g_len = str_len; g_seq_off = seq_off; g_seq_len = NULL; g_is_rev = NULL;
+    g_newlen = new_len; memcpy (g_newlen, str_len, (uint64_t)n_lines * 4);
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n_lines; i++) total += str_len[i];
+    ContextP ctx = CTX (mode == 0 ? SAM_QUAL : OPTION_t0_Z);
+    ctx->did_i = mode == 0 ? SAM_QUAL : OPTION_t0_Z; strcpy (ctx->tag_name, mode == 0 ? "QUAL" : "t0:Z");
+    ctx->local.len = total;
+    SectionHeaderCtx header = {};
+    uint32_t ulen = (uint32_t)total, clen = (uint32_t)total + 4096;
+    char *comp = malloc (clen);
+    cap_out = NULL; cap_len = 0;
+    bool ok = mode == 0 ? codec_homp_compress (vb, ctx, (SectionHeaderP)&header, NULL, &ulen, shim_get_line_newlen, comp, &clen, true, "QUAL")
+                        : codec_t0_compress   (vb, ctx, (SectionHeaderP)&header, NULL, &ulen, shim_get_line_newlen, comp, &clen, true, "t0:Z");
+    if (!ok) return -3;
+    if (ctx->local.len32 != cap_len) return -4;                             // the codec keeps local.len in step with the lines (:184, t0 :104)
+    memcpy (local, cap_out, cap_len); *local_len = cap_len;
+    free (comp); free (g_txt); free (vb);
+    return 0;
+}
+
+// codec_homp_reconstruct / codec_t0_reconstruct line by line
+int ref_hp_expand (int mode, const uint8_t *local, uint64_t local_len, const uint8_t *txt, const uint64_t *seq_off, const uint32_t *len, uint32_t n_lines, uint8_t *out, uint64_t *out_len)
+{
+    shim_init_piz ();
+    if (setjmp (on_abort)) { shim_missing_ok = false; return -1; }
+    shim_missing_ok = true;
+    VBlockP vb = calloc (1, sizeof (VBlock));
+    vb->vblock_i = 1; vb->lines.len = n_lines; vb->data_type = DT_SAM;
+    flag.out_dt = DT_SAM;
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n_lines; i++) total += len[i];
+    ContextP c = CTX (mode == 0 ? SAM_QUAL : OPTION_t0_Z);
+    c->did_i = mode == 0 ? SAM_QUAL : OPTION_t0_Z; c->is_loaded = true;
+    buf_alloc_do (vb, &c->local, local_len + 8, 1, "local", __FUNCLINE);
+    memcpy (c->local.data, local, local_len); c->local.len = local_len;
+    buf_alloc_do (vb, &vb->txt_data, total + 64, 1, "txt_data", __FUNCLINE);
+    uint64_t at = 0;
+    for (uint32_t i = 0; i < n_lines; i++) {
+        if (!len[i]) continue;
+        cur_seq = (rom)txt + seq_off[i]; cur_is_rev = false; vb->seq_len = len[i];
+        const uint64_t before = vb->txt_data.len;
+        if (mode == 0) codec_homp_reconstruct (vb, CODEC_HOMP, c, len[i], true); else codec_t0_reconstruct (vb, CODEC_T0, c, len[i], true);
+        if (c->next_local > local_len) { shim_missing_ok = false; return -2; }
+        // a line without quality contributes one '*': lay the lines out in slots of len[i] bytes like the flat entry points do
+        memcpy (out + at, vb->txt_data.data + before, vb->txt_data.len - before);
+        at += len[i];
+    }
+    shim_missing_ok = false;
+    *out_len = at;
+    const int rc = c->next_local == local_len ? 0 : -2;
+    free (vb);
+    return rc;
 }
 
 // ================================================================ zip_generate_local's transforms: the reference's own macros

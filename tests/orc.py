@@ -580,3 +580,45 @@ def b250_generate(b250, ni2wi, ol_len, one_up_ok, lib="port"):
     if rc != 0:
         return None
     return out[:n.value].copy(), None
+
+
+# ---------------------------------------------------------------- HOMP / T0 (src/codec_homp.c, src/codec_t0.c)
+def hp_condense(mode, txt, str_off, str_len, seq_off, lib="port"):
+    """-> (condensed strings back to back, new length of every line)"""
+    txt = np.ascontiguousarray(txt, np.uint8); so = np.ascontiguousarray(str_off, np.uint64); sl = np.ascontiguousarray(str_len, np.uint32)
+    qo = np.ascontiguousarray(seq_off, np.uint64)
+    out = np.zeros(int(sl.sum()) + 8, np.uint8); nl = np.zeros(sl.size + 1, np.uint32)
+    if lib == "port":
+        L = port()
+        L.orc_hp_condense.restype = C.c_uint64
+        L.orc_hp_condense.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_uint32, C.c_void_p, C.c_void_p]
+        n = L.orc_hp_condense(mode, _ptr(txt), _ptr(so), _ptr(sl), _ptr(qo), sl.size, _ptr(out), _ptr(nl))
+    else:
+        L = gz_ref()
+        L.ref_hp_condense.restype = C.c_int
+        L.ref_hp_condense.argtypes = [C.c_int, C.c_void_p, C.c_uint64] + [C.c_void_p] * 3 + [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        ln = C.c_uint64()
+        rc = L.ref_hp_condense(mode, _ptr(txt), txt.size, _ptr(so), _ptr(sl), _ptr(qo), sl.size, _ptr(out), C.byref(ln), _ptr(nl))
+        assert rc == 0, rc
+        n = ln.value
+    return out[:n].copy(), nl[:sl.size].copy()
+
+
+def hp_expand(mode, local, txt, seq_off, lens, lib="port"):
+    """-> (lens[i] bytes per line back to back, missing flags or None); None when the stream does not match the lines"""
+    local = np.ascontiguousarray(local, np.uint8); txt = np.ascontiguousarray(txt, np.uint8)
+    qo = np.ascontiguousarray(seq_off, np.uint64); sl = np.ascontiguousarray(lens, np.uint32)
+    out = np.zeros(int(sl.sum()) + 8, np.uint8); lo = local if local.size else np.zeros(1, np.uint8)
+    if lib == "port":
+        L = port()
+        L.orc_hp_expand.restype = C.c_int
+        L.orc_hp_expand.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        miss = np.zeros(sl.size + 1, np.uint8)
+        rc = L.orc_hp_expand(mode, _ptr(lo), local.size, _ptr(txt), _ptr(qo), _ptr(sl), sl.size, _ptr(out), _ptr(miss))
+        return None if rc != 0 else (out[:int(sl.sum())].copy(), miss[:sl.size].copy())
+    L = gz_ref()
+    L.ref_hp_expand.restype = C.c_int
+    L.ref_hp_expand.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    n = C.c_uint64()
+    rc = L.ref_hp_expand(mode, _ptr(lo), local.size, _ptr(txt), _ptr(qo), _ptr(sl), sl.size, _ptr(out), C.byref(n))
+    return None if rc != 0 else (out[:int(sl.sum())].copy(), None)
