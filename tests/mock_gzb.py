@@ -269,6 +269,95 @@ class MockLib:
             it.status = 0
         return 0
 
+    # ---- the steps either side of the codecs, and the round-2 quality codecs
+    def gzb_b250_generate_batch(self, h, items, n, flags):
+        rc = 0
+        for i in range(n):
+            a = items[i]
+            r = orc.b250_generate(_view(a.b250, a.len).copy(), _view(a.ni2wi, a.n_new, np.int32).copy(), a.ol_len, bool(a.one_up_ok))
+            if r is None:
+                a.status = -4; rc = -4; self.err = "b250: the backward scan does not end at the start of the buffer"; continue
+            out, nw = r
+            if out.size:
+                _view(a.out, a.len)[a.len - out.size:] = out
+            a.out_len = out.size; a.n_words = nw; a.status = 0
+        return rc
+
+    def gzb_local_transpose_batch(self, h, items, n, flags):
+        for i in range(n):
+            a = items[i]
+            dt = {1: np.uint8, 2: np.uint16, 4: np.uint32}[a.width]
+            a.transposed = 0; a.status = 0
+            if not a.n_elems:
+                continue
+            if a.n_elems % a.cols:
+                if a.dir == 1:
+                    a.status = -4; self.err = "transposed local is not a rectangle"; return -4
+                continue
+            out, tr = orc.local_transpose(_view(a.data, a.n_elems, dt).copy(), a.cols, piz=a.dir == 1)
+            _view(a.data, a.n_elems, dt)[:] = out
+            a.transposed = 1
+        return 0
+
+    def gzb_oq_mux(self, h, vbs, n, flags):
+        for i in range(n):
+            a = vbs[i]
+            nl = a.n_lines
+            sl = _view(a.seq_len, nl, np.uint32).copy() if a.seq_len else None
+            r = orc.oq_mux(_view(a.txt, a.txt_len).copy(), _view(a.qual_off, nl, np.uint64).copy(), _view(a.qual_len, nl, np.uint32).copy(),
+                           _view(a.oq_off, nl, np.uint64).copy(), sl)
+            if r is None:
+                a.status = -4; self.err = "OQ: a QUAL character outside '!'..'~'"; return -4
+            ch, cnt, mono = r
+            if ch.size:
+                _view(a.channels, ch.size)[:] = ch
+            for q in range(94):
+                a.count[q] = int(cnt[q]); a.monochars[q] = int(mono[q])
+            a.status = 0
+        return 0
+
+    def gzb_oq_demux(self, h, vbs, n, flags):
+        for i in range(n):
+            a = vbs[i]
+            nl = a.n_lines
+            cnt = np.array(a.count[:], np.uint32); mono = np.array(a.monochars[:], np.uint8)
+            out = orc.oq_demux(_view(a.txt, a.txt_len).copy(), _view(a.qual_off, nl, np.uint64).copy(), _view(a.qual_len, nl, np.uint32).copy(),
+                               _view(a.out_off, nl, np.uint64).copy(), a.out_cap, a.key_bias, _view(a.channels, int(cnt.sum())).copy(), cnt, mono)
+            if out is None:
+                a.status = -4; self.err = "OQ: a channel is out of data"; return -4
+            if out.size:
+                _view(a.out, out.size)[:] = out
+            a.status = 0
+        return 0
+
+    def gzb_homp_condense(self, h, vbs, n, mode, flags):
+        for i in range(n):
+            a = vbs[i]
+            nl = a.n_lines
+            out, newlen = orc.hp_condense(mode, _view(a.txt, a.txt_len).copy(), _view(a.str_off, nl, np.uint64).copy(), _view(a.str_len, nl, np.uint32).copy(),
+                                          _view(a.seq_off, nl, np.uint64).copy())
+            if out.size:
+                _view(a.local, out.size)[:] = out
+            if a.new_len and nl:
+                _view(a.new_len, nl, np.uint32)[:] = newlen
+            a.local_len = out.size; a.status = 0
+        return 0
+
+    def gzb_homp_expand(self, h, vbs, n, mode, flags):
+        for i in range(n):
+            a = vbs[i]
+            nl = a.n_lines
+            r = orc.hp_expand(mode, _view(a.local, a.local_len).copy(), _view(a.txt, a.txt_len).copy(), _view(a.seq_off, nl, np.uint64).copy(), _view(a.str_len, nl, np.uint32).copy())
+            if r is None:
+                a.status = -4; self.err = "HOMP / T0: the stream does not match the lines"; return -4
+            out, miss = r
+            if out.size:
+                _view(a.out, out.size)[:] = out
+            if a.missing and nl:
+                _view(a.missing, nl)[:] = miss
+            a.status = 0
+        return 0
+
     def gzb_normq_gather(self, h, vbs, n, flags):
         for i in range(n):
             a = vbs[i]
