@@ -7,6 +7,10 @@
 //          whose SEQ.len is not 0 (:88-99), monochar test (:103-107)
 //   demux  codec_oq_reconstruct (:126-164) for every line of a VBlock at once
 //
+// SMUX (src/codec_smux.c), the quality codec of MGI reads, is the same operation with other keys: QUAL[i] goes to the channel of the BASE at
+// position i (A, C, G, T, anything else: 5 channels), a reverse-complemented read walked backwards with complemented bases (:217-239); only the
+// fifth channel is tested for monochar (its character then travels in the section header's param, :246-253).
+//
 // Both are a STABLE distribution by key, the shape of arith_split.cu's bucket kernel: one CTA per VBlock, 32 warps owning 32
 // consecutive ranges of lines; a count pass, a scan over (channel, warp), then every warp walks its lines again 32 characters at a
 // time and ranks equal keys by lane (__match_any_sync), which keeps the order inside the chunk; cursors per (warp, channel) in shared memory.
@@ -25,26 +29,54 @@ constexpr int OQ_CH = 94, OQ_WARPS = 32, OQ_PAD = 96;
 
 struct OqVb {
     const uint8_t  *txt;
-    const uint64_t *qual_off;
-    const uint32_t *qual_len;
-    const uint64_t *oq_off;      // mux
-    const uint32_t *seq_len;     // mux, may be NULL
+    const uint64_t *a_off;       // OQ: the QUAL string (the keys).  SMUX: the QUAL string (the values; mux only)
+    const uint32_t *a_len;       //     its length.                  SMUX mux: QUAL's length; demux: the `len` of the reconstruct call
+    const uint64_t *b_off;       // OQ mux: the OQ string (dl->OQ).   SMUX: the SEQ string (the keys)
+    const uint32_t *b_len;       // OQ mux: SEQ.len or NULL (0 = the line is not distributed, :94).  SMUX mux: SEQ's length
+    const uint8_t  *is_rev;      // SMUX, may be NULL
     uint8_t        *out;         // demux
     const uint64_t *out_off;     // demux
     uint8_t        *chan;
     uint32_t       *count;       // [94]  mux: out; demux: in
     uint8_t        *mono;        // [94]  mux: out; demux: in
     uint32_t       *info;        // [0] error
-    uint32_t        n_lines, key_bias;
+    uint32_t        n_lines, key_bias, kind, n_ch;   // kind 0 OQ (94 channels), 1 SMUX (5)
     unsigned long long chan_cap;
 };
 
-// one chunk of <= 32 characters of a line: ranks among equal keys, in lane order.  Returns the key (OQ_PAD + lane for an inactive lane).
-__device__ __forceinline__ uint32_t oq_rank (uint32_t key, bool act, int lane, uint32_t &peers)
+__device__ __forceinline__ uint32_t smux_enc (uint8_t c, bool comp)        // _nuke_encode / _nuke_encode_comp (src/reference.c:78-84)
 {
-    const uint32_t k = act ? key : (uint32_t)OQ_PAD + 32u + lane;
-    peers = __match_any_sync (0xffffffffu, k);
-    return k;
+    const uint32_t k = c == 'A' ? 0u : c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : 4u;
+    return (comp && k < 4) ? 3u - k : k;
+}
+
+// One line as the kernel walks it: n elements in the order the reference visits them; element t has the key key (t), its value is read from
+// (mux) or written to (demux) position at (t) of the line's string.
+struct OqLine {
+    const uint8_t *keys; const uint8_t *vals; uint8_t *dst;
+    uint32_t n, rev, last_key_only, bias, kind;
+    bool dist;
+    __device__ __forceinline__ uint32_t at (uint32_t t) const { return rev ? n - 1 - t : t; }
+    __device__ __forceinline__ uint32_t key (uint32_t t) const
+    {
+        if (kind == 0) return (uint32_t)keys[t] - bias;
+        return last_key_only ? smux_enc (keys[last_key_only - 1], true) : smux_enc (keys[at (t)], rev);
+    }
+};
+template <int DEMUX> __device__ __forceinline__ OqLine oq_line (const OqVb &V, uint32_t l)
+{
+    OqLine L; L.kind = V.kind; L.bias = V.key_bias; L.rev = 0; L.last_key_only = 0; L.dist = true; L.dst = nullptr; L.vals = nullptr;
+    if (V.kind == 0) {
+        L.n = V.a_len[l]; L.keys = V.txt + V.a_off[l];
+        if (DEMUX) L.dst = V.out + V.out_off[l];
+        else { L.vals = V.txt + V.b_off[l]; L.dist = !V.b_len || V.b_len[l] != 0; }   // (dl->OQ = 0 reads the start of the text, as the reference does, codec_oq.c:91)
+        return L;
+    }
+    L.keys = V.txt + V.b_off[l]; L.rev = V.is_rev ? V.is_rev[l] : 0;
+    if (DEMUX) { L.n = V.a_len[l]; if (L.n && L.keys[0] == '*') L.n = 1; L.dst = V.out + V.out_off[l]; return L; }      // codec_smux.c:278-279
+    L.n = V.a_len[l]; L.vals = V.txt + V.a_off[l];
+    if (L.n == 1 && L.rev && L.vals[0] == ' ') { L.last_key_only = V.b_len[l]; L.rev = 0; }   // a reversed read without quality: the channel of its LAST base (:207-208,229-232)
+    return L;
 }
 
 template <int DEMUX>
@@ -52,31 +84,30 @@ __global__ void __launch_bounds__(OQ_WARPS * 32) k_oq (const OqVb *vbs)
 {
     const OqVb &V = vbs[blockIdx.x];
     __shared__ uint32_t cur[OQ_WARPS][OQ_PAD];        // per warp and channel: characters distributed (count, then cursor)
-    __shared__ uint32_t all[OQ_WARPS][OQ_PAD];        // mux: characters of every line, distributed or not (:61-72 counts them all)
+    __shared__ uint32_t all[OQ_WARPS][OQ_PAD];        // mux: characters of every line, distributed or not (codec_oq.c:61-72 counts them all)
     __shared__ uint32_t tot[OQ_PAD], base[OQ_PAD];
     __shared__ uint8_t  s_mono[OQ_PAD];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n_ch = V.n_ch;
     for (int i = tid; i < OQ_WARPS * OQ_PAD; i += OQ_WARPS * 32) { (&cur[0][0])[i] = 0; (&all[0][0])[i] = 0; }
-    if (tid < OQ_PAD) s_mono[tid] = (DEMUX && tid < OQ_CH) ? V.mono[tid] : 0;
+    if (tid < OQ_PAD) s_mono[tid] = (DEMUX && (uint32_t)tid < n_ch) ? V.mono[tid] : 0;
     __syncthreads ();
     const uint32_t per = (V.n_lines + OQ_WARPS - 1) / OQ_WARPS;
     const uint32_t l0 = min (V.n_lines, (uint32_t)warp * per), l1 = min (V.n_lines, l0 + per);
     bool bad = false;
     // ---- count
     for (uint32_t l = l0; l < l1; l++) {
-        const uint32_t len = V.qual_len[l];
-        const uint8_t *q = V.txt + V.qual_off[l];
-        const bool dist = DEMUX || !V.seq_len || V.seq_len[l] != 0;
-        for (uint32_t i0 = 0; i0 < len; i0 += 32) {
-            const uint32_t i = i0 + lane;
-            const bool act = i < len;
-            uint32_t key = act ? (uint32_t)q[i] - V.key_bias : 0;
-            if (act && key >= (uint32_t)OQ_CH) { bad = true; key = 0; }
-            uint32_t peers;
-            const uint32_t k = oq_rank (key, act, lane, peers);
+        const OqLine L = oq_line<DEMUX> (V, l);
+        for (uint32_t t0 = 0; t0 < L.n; t0 += 32) {
+            const uint32_t t = t0 + lane;
+            const bool act = t < L.n;
+            uint32_t key = act ? L.key (t) : 0;
+            if (act && key >= n_ch) { bad = true; key = 0; }
+            const uint32_t k = act ? key : (uint32_t)OQ_PAD + 32u + lane;
+            const uint32_t peers = __match_any_sync (0xffffffffu, k);
             if (act && (peers & ((1u << lane) - 1)) == 0) {                 // the lowest lane of a group of equal keys counts the group
                 if (!DEMUX) all[warp][k] += __popc (peers);
-                if (dist && !(DEMUX && s_mono[k])) cur[warp][k] += __popc (peers);
+                if (L.dist && !(DEMUX && s_mono[k])) cur[warp][k] += __popc (peers);
             }
             __syncwarp ();
         }
@@ -86,7 +117,7 @@ __global__ void __launch_bounds__(OQ_WARPS * 32) k_oq (const OqVb *vbs)
     // ---- channel offsets and the cursors of every warp
     if (tid < OQ_PAD) {
         uint32_t t = 0;
-        if (tid < OQ_CH) { if (DEMUX) t = V.count[tid]; else for (int w = 0; w < OQ_WARPS; w++) t += all[w][tid]; }
+        if ((uint32_t)tid < n_ch) { if (DEMUX) t = V.count[tid]; else for (int w = 0; w < OQ_WARPS; w++) t += all[w][tid]; }
         tot[tid] = t;
     }
     __syncthreads ();
@@ -100,46 +131,45 @@ __global__ void __launch_bounds__(OQ_WARPS * 32) k_oq (const OqVb *vbs)
         if (lane == 31 && (unsigned long long)x > V.chan_cap) V.info[0] = 2;
     }
     __syncthreads ();
-    if (tid < OQ_CH) {
+    if ((uint32_t)tid < n_ch) {
         uint32_t x = base[tid];
         for (int w = 0; w < OQ_WARPS; w++) { const uint32_t c = cur[w][tid]; cur[w][tid] = x; x += c; }
-        if (DEMUX && x > base[tid] + tot[tid]) V.info[0] = 3;               // "channel is out of data" (:152-153)
+        if (DEMUX && x > base[tid] + tot[tid]) V.info[0] = 3;               // "channel is out of data" (codec_oq.c:152-153, codec_smux.c:301)
         if (!DEMUX) V.count[tid] = tot[tid];
     }
     __syncthreads ();
     if (V.info[0]) return;
     // ---- distribute
+    bool blank = false;
     for (uint32_t l = l0; l < l1; l++) {
-        const uint32_t len = V.qual_len[l];
-        if (!DEMUX && V.seq_len && V.seq_len[l] == 0) continue;             // :94
-        const uint8_t *q = V.txt + V.qual_off[l];
-        const uint8_t *oq = DEMUX ? nullptr : V.txt + V.oq_off[l];          // (dl->OQ = 0 reads the start of the text, as the reference does, :91)
-        uint8_t *o = DEMUX ? V.out + V.out_off[l] : nullptr;
-        for (uint32_t i0 = 0; i0 < len; i0 += 32) {
-            const uint32_t i = i0 + lane;
-            const bool act = i < len;
-            const uint32_t key = act ? (uint32_t)q[i] - V.key_bias : 0;
-            uint32_t peers;
-            const uint32_t k = oq_rank (key, act, lane, peers);
+        const OqLine L = oq_line<DEMUX> (V, l);
+        if (!L.dist) continue;                                              // codec_oq.c:94
+        for (uint32_t t0 = 0; t0 < L.n; t0 += 32) {
+            const uint32_t t = t0 + lane;
+            const bool act = t < L.n;
+            const uint32_t key = act ? L.key (t) : 0;
+            const uint32_t k = act ? key : (uint32_t)OQ_PAD + 32u + lane;
+            const uint32_t peers = __match_any_sync (0xffffffffu, k);
             const bool mono = DEMUX && act && s_mono[k];
             const uint32_t b = (act && !mono) ? cur[warp][k] : 0;
             __syncwarp ();
             if (act) {
                 const uint32_t pos = b + __popc (peers & ((1u << lane) - 1));
-                if (DEMUX) o[i] = mono ? s_mono[k] : V.chan[pos];
-                else V.chan[pos] = oq[i];
+                if (DEMUX) { const uint8_t c = mono ? s_mono[k] : V.chan[pos]; L.dst[L.at (t)] = c; if (V.kind == 1 && c == ' ') blank = true; }
+                else V.chan[pos] = L.last_key_only ? (uint8_t)' ' : L.vals[L.at (t)];
                 if (!mono && (peers >> lane) == 1) cur[warp][k] = b + __popc (peers);   // the highest lane of the group moves the cursor
             }
             __syncwarp ();
         }
     }
+    if (blank) V.info[0] = 4;                                               // a read without quality (codec_smux.c:307-310): how much a line consumes then depends on the data
     if (DEMUX) return;
-    // ---- monochar channels (:103-107): str_is_monochar over the channel's count_q bytes (what no line wrote stays 0)
+    // ---- monochar channels (codec_oq.c:103-107; SMUX: the fifth channel only, codec_smux.c:246): str_is_monochar over the channel's bytes (what no line wrote stays 0)
     __syncthreads ();
-    for (int k = warp; k < OQ_CH; k += OQ_WARPS) {
+    for (uint32_t k = warp; k < n_ch; k += OQ_WARPS) {
         const uint32_t n = tot[k];
         uint8_t m = 0;
-        if (n) {
+        if (n && (V.kind == 0 || k == 4)) {
             const uint8_t *c = V.chan + base[k];
             const uint8_t first = c[0];
             bool same = true;
@@ -163,9 +193,19 @@ struct Carver {
     }
 };
 
-int oq_run (gzb_engine *e, gzb_oq_vb *vbs, uint32_t n_vbs, uint32_t flags, int demux)
+// what both public structs boil down to
+struct OqHost {
+    const void *txt; uint64_t txt_len;
+    const uint64_t *a_off; const uint32_t *a_len; const uint64_t *b_off; const uint32_t *b_len; const uint8_t *is_rev;
+    uint32_t n_lines, key_bias, kind, n_ch;
+    void *channels; uint64_t channels_cap; uint32_t *count; uint8_t *mono;
+    void *out; uint64_t out_cap; const uint64_t *out_off;
+    int32_t *status;
+};
+
+int oq_run (gzb_engine *e, std::vector<OqHost> &vbs, uint32_t flags, int demux)
 {
-    if (!e || (!vbs && n_vbs)) return GZB_E_BADARG;
+    const uint32_t n_vbs = (uint32_t)vbs.size ();
     if (!n_vbs) return GZB_OK;
     cudaSetDevice (e->device);
     const bool devptr = flags & GZB_DEVICE_PTRS;
@@ -173,14 +213,16 @@ int oq_run (gzb_engine *e, gzb_oq_vb *vbs, uint32_t n_vbs, uint32_t flags, int d
     std::vector<OqVb> h (n_vbs);
     std::vector<uint64_t> total (n_vbs, 0), chan_bytes (n_vbs, 0);
     for (uint32_t v = 0; v < n_vbs; v++) {
-        gzb_oq_vb &S = vbs[v]; S.status = GZB_OK;
-        if ((S.n_lines && (!S.qual_off || !S.qual_len || (demux ? (!S.out_off || !S.out) : !S.oq_off))) || (!S.txt && S.txt_len) || (!S.channels && S.channels_cap)) return GZB_E_BADARG;
-        if (!devptr) for (uint32_t i = 0; i < S.n_lines; i++) total[v] += S.qual_len[i];
+        OqHost &S = vbs[v]; *S.status = GZB_OK;
+        const bool need_a_off = S.kind == 0 || !demux, need_b_off = S.kind == 1 || !demux;
+        if ((S.n_lines && (!S.a_len || (need_a_off && !S.a_off) || (need_b_off && !S.b_off) || (S.kind == 1 && !demux && !S.b_len) || (demux && (!S.out_off || !S.out)))) ||
+            (!S.txt && S.txt_len) || (!S.channels && S.channels_cap)) return GZB_E_BADARG;
+        if (!devptr) for (uint32_t i = 0; i < S.n_lines; i++) total[v] += S.a_len[i];
         else total[v] = demux ? S.out_cap : S.channels_cap;
-        if (demux) for (int k = 0; k < OQ_CH; k++) chan_bytes[v] += S.count[k];
+        if (demux) for (uint32_t k = 0; k < S.n_ch; k++) chan_bytes[v] += S.count[k];
         else chan_bytes[v] = devptr ? S.channels_cap : total[v];
-        if (chan_bytes[v] > S.channels_cap || (demux && !devptr && total[v] > S.out_cap)) { e->err = "OQ: a buffer is too small"; return GZB_E_BADARG; }
-        if (chan_bytes[v] > 0xffffffffull) { e->err = "OQ: more than 4 GB of channels in a VBlock"; return GZB_E_BADARG; }
+        if (chan_bytes[v] > S.channels_cap || (demux && !devptr && total[v] > S.out_cap)) { e->err = "OQ / SMUX: a buffer is too small"; return GZB_E_BADARG; }
+        if (chan_bytes[v] > 0xffffffffull) { e->err = "OQ / SMUX: more than 4 GB of channels in a VBlock"; return GZB_E_BADARG; }
     }
     Carver c { nullptr, 0 };
     OqVb *d_vbs = nullptr; uint32_t *d_info = nullptr, *d_count = nullptr; uint8_t *d_mono = nullptr;
@@ -190,18 +232,19 @@ int oq_run (gzb_engine *e, gzb_oq_vb *vbs, uint32_t n_vbs, uint32_t flags, int d
         d_vbs = c.take<OqVb> (n_vbs); d_info = c.take<uint32_t> ((size_t)n_vbs * 4);
         d_count = c.take<uint32_t> ((size_t)n_vbs * OQ_PAD); d_mono = c.take<uint8_t> ((size_t)n_vbs * OQ_PAD);
         for (uint32_t v = 0; v < n_vbs; v++) {
-            const gzb_oq_vb &S = vbs[v]; OqVb &D = h[v];
-            D.n_lines = S.n_lines; D.key_bias = demux ? S.key_bias : 33u; D.chan_cap = S.channels_cap;
+            const OqHost &S = vbs[v]; OqVb &D = h[v];
+            D.n_lines = S.n_lines; D.key_bias = S.key_bias; D.chan_cap = S.channels_cap; D.kind = S.kind; D.n_ch = S.n_ch;
             D.info = d_info ? d_info + 4 * (size_t)v : nullptr;
             D.count = d_count ? d_count + (size_t)OQ_PAD * v : nullptr; D.mono = d_mono ? d_mono + (size_t)OQ_PAD * v : nullptr;
-            D.txt      = devptr ? (const uint8_t *)S.txt : c.take<uint8_t> (S.txt_len + 16);
-            D.qual_off = devptr ? S.qual_off : c.take<uint64_t> ((size_t)S.n_lines + 1);
-            D.qual_len = devptr ? S.qual_len : c.take<uint32_t> ((size_t)S.n_lines + 1);
-            D.oq_off   = demux ? nullptr : devptr ? S.oq_off : c.take<uint64_t> ((size_t)S.n_lines + 1);
-            D.seq_len  = (demux || !S.seq_len) ? nullptr : devptr ? S.seq_len : c.take<uint32_t> ((size_t)S.n_lines + 1);
-            D.out_off  = !demux ? nullptr : devptr ? S.out_off : c.take<uint64_t> ((size_t)S.n_lines + 1);
-            D.out      = !demux ? nullptr : devptr ? (uint8_t *)S.out : c.take<uint8_t> (S.out_cap + 16);
-            D.chan     = devptr ? (uint8_t *)S.channels : c.take<uint8_t> (chan_bytes[v] + 16);
+            D.txt     = devptr ? (const uint8_t *)S.txt : c.take<uint8_t> (S.txt_len + 16);
+            D.a_len   = devptr ? S.a_len : c.take<uint32_t> ((size_t)S.n_lines + 1);
+            D.a_off   = !S.a_off ? nullptr : devptr ? S.a_off : c.take<uint64_t> ((size_t)S.n_lines + 1);
+            D.b_off   = !S.b_off ? nullptr : devptr ? S.b_off : c.take<uint64_t> ((size_t)S.n_lines + 1);
+            D.b_len   = !S.b_len ? nullptr : devptr ? S.b_len : c.take<uint32_t> ((size_t)S.n_lines + 1);
+            D.is_rev  = !S.is_rev ? nullptr : devptr ? S.is_rev : c.take<uint8_t> ((size_t)S.n_lines + 1);
+            D.out_off = !demux ? nullptr : devptr ? S.out_off : c.take<uint64_t> ((size_t)S.n_lines + 1);
+            D.out     = !demux ? nullptr : devptr ? (uint8_t *)S.out : c.take<uint8_t> (S.out_cap + 16);
+            D.chan    = devptr ? (uint8_t *)S.channels : c.take<uint8_t> (chan_bytes[v] + 16);
         }
         if (pass == 0) { int rc = engine_reserve (e, c.off, desc_bytes + meta_bytes + 512); if (rc) return rc; c.base = e->ws; }
     }
@@ -209,15 +252,16 @@ int oq_run (gzb_engine *e, gzb_oq_vb *vbs, uint32_t n_vbs, uint32_t flags, int d
     uint8_t  *p_mono  = e->pin + desc_bytes + (size_t)n_vbs * OQ_PAD * 4;
     uint32_t *p_info  = reinterpret_cast<uint32_t *>(e->pin + desc_bytes + (size_t)n_vbs * (OQ_PAD * 4 + OQ_PAD));
     for (uint32_t v = 0; v < n_vbs; v++) {
-        const gzb_oq_vb &S = vbs[v]; OqVb &D = h[v];
+        const OqHost &S = vbs[v]; OqVb &D = h[v];
         memset (p_count + (size_t)OQ_PAD * v, 0, OQ_PAD * 4); memset (p_mono + (size_t)OQ_PAD * v, 0, OQ_PAD);
-        if (demux) { memcpy (p_count + (size_t)OQ_PAD * v, S.count, OQ_CH * 4); memcpy (p_mono + (size_t)OQ_PAD * v, S.monochars, OQ_CH); }
+        if (demux) { memcpy (p_count + (size_t)OQ_PAD * v, S.count, S.n_ch * 4); memcpy (p_mono + (size_t)OQ_PAD * v, S.mono, S.n_ch); }
         if (devptr) { if (!demux && chan_bytes[v]) CK (cudaMemsetAsync (D.chan, 0, chan_bytes[v], st)); continue; }
         if (S.n_lines) {
-            CK (cudaMemcpyAsync ((void *)D.qual_off, S.qual_off, (size_t)S.n_lines * 8, cudaMemcpyHostToDevice, st));
-            CK (cudaMemcpyAsync ((void *)D.qual_len, S.qual_len, (size_t)S.n_lines * 4, cudaMemcpyHostToDevice, st));
-            if (D.oq_off)  CK (cudaMemcpyAsync ((void *)D.oq_off, S.oq_off, (size_t)S.n_lines * 8, cudaMemcpyHostToDevice, st));
-            if (D.seq_len) CK (cudaMemcpyAsync ((void *)D.seq_len, S.seq_len, (size_t)S.n_lines * 4, cudaMemcpyHostToDevice, st));
+            CK (cudaMemcpyAsync ((void *)D.a_len, S.a_len, (size_t)S.n_lines * 4, cudaMemcpyHostToDevice, st));
+            if (D.a_off)   CK (cudaMemcpyAsync ((void *)D.a_off, S.a_off, (size_t)S.n_lines * 8, cudaMemcpyHostToDevice, st));
+            if (D.b_off)   CK (cudaMemcpyAsync ((void *)D.b_off, S.b_off, (size_t)S.n_lines * 8, cudaMemcpyHostToDevice, st));
+            if (D.b_len)   CK (cudaMemcpyAsync ((void *)D.b_len, S.b_len, (size_t)S.n_lines * 4, cudaMemcpyHostToDevice, st));
+            if (D.is_rev)  CK (cudaMemcpyAsync ((void *)D.is_rev, S.is_rev, S.n_lines, cudaMemcpyHostToDevice, st));
             if (D.out_off) CK (cudaMemcpyAsync ((void *)D.out_off, S.out_off, (size_t)S.n_lines * 8, cudaMemcpyHostToDevice, st));
         }
         if (S.txt_len) CK (cudaMemcpyAsync ((void *)D.txt, S.txt, S.txt_len, cudaMemcpyHostToDevice, st));
@@ -242,16 +286,17 @@ int oq_run (gzb_engine *e, gzb_oq_vb *vbs, uint32_t n_vbs, uint32_t flags, int d
     CK (cudaStreamSynchronize (st));
     int rc = GZB_OK;
     for (uint32_t v = 0; v < n_vbs; v++) {
-        gzb_oq_vb &S = vbs[v];
+        OqHost &S = vbs[v];
         const uint32_t err = p_info[4 * v];
         if (err) {
-            S.status = err == 2 ? GZB_E_BADARG : GZB_E_CORRUPT; rc = S.status;
-            e->err = err == 1 ? "OQ: a QUAL character outside '!'..'~'" : err == 2 ? "OQ: the channel buffer is too small" : "OQ: a channel is out of data";
+            *S.status = err == 2 ? GZB_E_BADARG : err == 4 ? GZB_E_UNSUPPORTED : GZB_E_CORRUPT; rc = *S.status;
+            e->err = err == 1 ? "OQ / SMUX: a key outside the channels" : err == 2 ? "OQ / SMUX: the channel buffer is too small" : err == 3 ? "OQ / SMUX: a channel is out of data"
+                   : "SMUX: a read without quality — how much such a line consumes depends on the data: reconstruct these VBlocks line by line";
             continue;
         }
         if (!demux) {
-            memcpy (S.count, p_count + (size_t)OQ_PAD * v, OQ_CH * 4); memcpy (S.monochars, p_mono + (size_t)OQ_PAD * v, OQ_CH);
-            uint64_t nb = 0; for (int k = 0; k < OQ_CH; k++) nb += S.count[k];
+            memcpy (S.count, p_count + (size_t)OQ_PAD * v, S.n_ch * 4); memcpy (S.mono, p_mono + (size_t)OQ_PAD * v, S.n_ch);
+            uint64_t nb = 0; for (uint32_t k = 0; k < S.n_ch; k++) nb += S.count[k];
             if (!devptr && nb) CK (cudaMemcpyAsync (S.channels, h[v].chan, nb, cudaMemcpyDeviceToHost, st));
         }
         else if (!devptr && S.out_cap) CK (cudaMemcpyAsync (S.out, h[v].out, S.out_cap, cudaMemcpyDeviceToHost, st));
@@ -260,7 +305,36 @@ int oq_run (gzb_engine *e, gzb_oq_vb *vbs, uint32_t n_vbs, uint32_t flags, int d
     return rc;
 }
 
+int oq_public (gzb_engine *e, gzb_oq_vb *vbs, uint32_t n_vbs, uint32_t flags, int demux)
+{
+    if (!e || (!vbs && n_vbs)) return GZB_E_BADARG;
+    std::vector<OqHost> h (n_vbs);
+    for (uint32_t v = 0; v < n_vbs; v++) {
+        gzb_oq_vb &S = vbs[v];
+        h[v] = OqHost { S.txt, S.txt_len, S.qual_off, S.qual_len, demux ? nullptr : S.oq_off, demux ? nullptr : S.seq_len, nullptr, S.n_lines, demux ? S.key_bias : 33u, 0, (uint32_t)OQ_CH,
+                        S.channels, S.channels_cap, S.count, S.monochars, S.out, S.out_cap, S.out_off, &S.status };
+    }
+    return oq_run (e, h, flags, demux);
+}
+int smux_public (gzb_engine *e, gzb_smux_vb *vbs, uint32_t n_vbs, uint32_t flags, int demux)
+{
+    if (!e || (!vbs && n_vbs)) return GZB_E_BADARG;
+    std::vector<OqHost> h (n_vbs);
+    std::vector<uint8_t> mono ((size_t)n_vbs * 8, 0);
+    for (uint32_t v = 0; v < n_vbs; v++) {
+        gzb_smux_vb &S = vbs[v];
+        if (demux) mono[8 * (size_t)v + 4] = S.n_param;
+        h[v] = OqHost { S.txt, S.txt_len, demux ? nullptr : S.qual_off, S.qual_len, S.seq_off, demux ? nullptr : S.seq_len, S.is_rev, S.n_lines, 0, 1, 5,
+                        S.channels, S.channels_cap, S.count, &mono[8 * (size_t)v], S.out, S.out_cap, S.out_off, &S.status };
+    }
+    const int rc = oq_run (e, h, flags, demux);
+    if (!demux) for (uint32_t v = 0; v < n_vbs; v++) vbs[v].n_param = mono[8 * (size_t)v + 4];
+    return rc;
+}
+
 } // namespace
 
-extern "C" int gzb_oq_mux   (gzb_engine *e, gzb_oq_vb *vbs, uint32_t n_vbs, uint32_t flags) { return oq_run (e, vbs, n_vbs, flags, 0); }
-extern "C" int gzb_oq_demux (gzb_engine *e, gzb_oq_vb *vbs, uint32_t n_vbs, uint32_t flags) { return oq_run (e, vbs, n_vbs, flags, 1); }
+extern "C" int gzb_oq_mux     (gzb_engine *e, gzb_oq_vb *vbs, uint32_t n_vbs, uint32_t flags)   { return oq_public (e, vbs, n_vbs, flags, 0); }
+extern "C" int gzb_oq_demux   (gzb_engine *e, gzb_oq_vb *vbs, uint32_t n_vbs, uint32_t flags)   { return oq_public (e, vbs, n_vbs, flags, 1); }
+extern "C" int gzb_smux_mux   (gzb_engine *e, gzb_smux_vb *vbs, uint32_t n_vbs, uint32_t flags) { return smux_public (e, vbs, n_vbs, flags, 0); }
+extern "C" int gzb_smux_demux (gzb_engine *e, gzb_smux_vb *vbs, uint32_t n_vbs, uint32_t flags) { return smux_public (e, vbs, n_vbs, flags, 1); }

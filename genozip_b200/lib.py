@@ -86,6 +86,13 @@ class HompVb(C.Structure):          # gzb_homp_vb
                 ("new_len", C.c_void_p), ("out", C.c_void_p), ("out_cap", C.c_uint64), ("missing", C.c_void_p)]
 
 
+class SmuxVb(C.Structure):          # gzb_smux_vb
+    _fields_ = [("txt", C.c_void_p), ("txt_len", C.c_uint64), ("qual_off", C.c_void_p), ("qual_len", C.c_void_p), ("seq_off", C.c_void_p),
+                ("seq_len", C.c_void_p), ("is_rev", C.c_void_p), ("n_lines", C.c_uint32), ("status", C.c_int32),
+                ("channels", C.c_void_p), ("channels_cap", C.c_uint64), ("count", C.c_uint32 * 5), ("n_param", C.c_uint8), ("pad", C.c_uint8 * 3),
+                ("out", C.c_void_p), ("out_cap", C.c_uint64), ("out_off", C.c_void_p)]
+
+
 class LocalItem(C.Structure):       # gzb_local_item
     _fields_ = [("data", C.c_void_p), ("n_elems", C.c_uint64), ("op", C.c_int32), ("status", C.c_int32)]
 
@@ -180,7 +187,7 @@ def load():
     for f in ("gzb_stage_upload", "gzb_stage_fetch"):
         getattr(L, f).restype = C.c_int; getattr(L, f).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     L.gzb_stage_wait.restype = C.c_int; L.gzb_stage_wait.argtypes = [C.c_void_p, C.c_int]
-    for f in ("gzb_normq_gather", "gzb_normq_reconstruct", "gzb_oq_mux", "gzb_oq_demux"):
+    for f in ("gzb_normq_gather", "gzb_normq_reconstruct", "gzb_oq_mux", "gzb_oq_demux", "gzb_smux_mux", "gzb_smux_demux"):
         getattr(L, f).restype = C.c_int; getattr(L, f).argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
     L.gzb_local_transform_batch.restype = C.c_int
     L.gzb_local_transform_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
@@ -395,6 +402,52 @@ class Engine:
         if rc != 0:
             raise GzbError(f"gzb_adler32_batch failed ({rc}): {self._err()}")
         return [int(items[i].adler) for i in range(len(ptr_len))]
+
+    # ---- SMUX (host buffers) ----
+    def smux_mux(self, vbs):
+        """vbs: list of (txt, qual_off, qual_len, seq_off, seq_len, is_rev or None) -> list of (5 channels back to back, count[5], n_param)"""
+        arr = (SmuxVb * max(1, len(vbs)))(); keep = []
+        for i, (txt, qoff, qlen, soff, slen, rev) in enumerate(vbs):
+            txt = np.ascontiguousarray(txt, np.uint8); qoff = np.ascontiguousarray(qoff, np.uint64); qlen = np.ascontiguousarray(qlen, np.uint32)
+            soff = np.ascontiguousarray(soff, np.uint64); slen = np.ascontiguousarray(slen, np.uint32); rv = None if rev is None else np.ascontiguousarray(rev, np.uint8)
+            ch = np.zeros(int(qlen.sum()) + 16, np.uint8)
+            keep.append((txt, qoff, qlen, soff, slen, rv, ch))
+            a = arr[i]
+            a.txt = txt.ctypes.data if txt.size else None; a.txt_len = txt.size; a.n_lines = qlen.size
+            a.qual_off = qoff.ctypes.data if qoff.size else None; a.qual_len = qlen.ctypes.data if qlen.size else None
+            a.seq_off = soff.ctypes.data if soff.size else None; a.seq_len = slen.ctypes.data if slen.size else None
+            a.is_rev = None if rv is None or not rv.size else rv.ctypes.data
+            a.channels = ch.ctypes.data; a.channels_cap = ch.size
+        rc = self.L.gzb_smux_mux(self.h, arr, len(vbs), 0)
+        if rc != 0:
+            raise GzbError(f"gzb_smux_mux failed ({rc}): {self._err()}")
+        out = []
+        for i, k in enumerate(keep):
+            cnt = np.array(arr[i].count[:], np.uint32)
+            out.append((k[6][:int(cnt.sum())].copy(), cnt, int(arr[i].n_param)))
+        return out
+
+    def smux_demux(self, vbs):
+        """vbs: list of (txt, seq_off, lens, is_rev or None, out_off, out_size, channels, count[5], n_param) -> list of out arrays"""
+        arr = (SmuxVb * max(1, len(vbs)))(); keep = []
+        for i, (txt, soff, lens, rev, ooff, out_size, ch, cnt, par) in enumerate(vbs):
+            txt = np.ascontiguousarray(txt, np.uint8); soff = np.ascontiguousarray(soff, np.uint64); lens = np.ascontiguousarray(lens, np.uint32)
+            ooff = np.ascontiguousarray(ooff, np.uint64); rv = None if rev is None else np.ascontiguousarray(rev, np.uint8)
+            ch = np.ascontiguousarray(ch, np.uint8); ch = ch if ch.size else np.zeros(1, np.uint8)
+            out = np.zeros(out_size + 16, np.uint8)
+            keep.append((txt, soff, lens, ooff, rv, ch, out, out_size))
+            a = arr[i]
+            a.txt = txt.ctypes.data if txt.size else None; a.txt_len = txt.size; a.n_lines = lens.size
+            a.qual_len = lens.ctypes.data if lens.size else None; a.seq_off = soff.ctypes.data if soff.size else None
+            a.is_rev = None if rv is None or not rv.size else rv.ctypes.data; a.out_off = ooff.ctypes.data if ooff.size else None
+            a.channels = ch.ctypes.data; a.channels_cap = ch.size; a.n_param = par
+            for b in range(5):
+                a.count[b] = int(cnt[b])
+            a.out = out.ctypes.data; a.out_cap = out_size
+        rc = self.L.gzb_smux_demux(self.h, arr, len(vbs), 0)
+        if rc != 0:
+            raise GzbError(f"gzb_smux_demux failed ({rc}): {self._err()}")
+        return [k[6][:k[7]].copy() for k in keep]
 
     # ---- HOMP / T0 (host buffers) ----
     def hp_condense(self, mode, vbs):

@@ -44,6 +44,7 @@ enum {
     GZB_E_CUDA      = -2,   /* a CUDA call failed (see gzb_last_error) */
     GZB_E_BADARG    = -3,
     GZB_E_CORRUPT   = -4,   /* malformed compressed data (the reference ASSERTs, src/codec_htscodecs.c:106-111) */
+    GZB_E_UNSUPPORTED = -5, /* valid input that the bulk form of an entry point does not cover (stated at that entry point) */
 };
 
 typedef struct gzb_engine gzb_engine;   /* one per (host thread, GPU): a CUDA stream + reusable device arena */
@@ -347,6 +348,38 @@ typedef struct gzb_oq_vb {
 } gzb_oq_vb;
 int gzb_oq_mux   (gzb_engine *e, gzb_oq_vb *vbs, uint32_t n_vbs, uint32_t flags);
 int gzb_oq_demux (gzb_engine *e, gzb_oq_vb *vbs, uint32_t n_vbs, uint32_t flags);
+
+/* ---------------------------------------------------------------- SMUX (src/codec_smux.c): MGI's quality codec — QUAL multiplexed by the base
+ * mux:   codec_smux_compress (:180-262): QUAL[i] goes to the channel of SEQ[i] — A, C, G, T, anything else (_nuke_encode, src/reference.c:78-84):
+ *        5 channels; a reverse-complemented read (is_rev) is walked from its last position with complemented bases (:236-239); a read
+ *        without quality (qual_len 1, ' ') puts its ' ' in the channel of its first base, of its LAST base when reversed (:223-232).
+ *        count[] = bytes per channel; n_param = the character of the fifth channel when it holds one character only, else 0 (the
+ *        reference then drops that channel and sends the character in the section header's param, :246-253).
+ *            in  txt, qual_off, qual_len, seq_off, seq_len, is_rev (NULL = none)      out  channels (channel b at the sum of count[0..b)), count, n_param
+ * demux: codec_smux_reconstruct (:273-355) for every line of a VBlock at once (output in the read's own orientation: SAM / BAM / FASTQ out of
+ *        FASTQ; not its SAM-to-FASTQ translation, :328-330): qual_len[i] = the `len` of the i-th call (1 when SEQ is "*", :278-279).
+ *        A read without quality consumes ONE byte whatever its length — known only from the byte itself — so a VBlock whose channels hold a
+ *        ' ' is refused with GZB_E_UNSUPPORTED (reconstruct it line by line); FASTQ never has one.
+ *            in  txt + seq_off, qual_len, is_rev, channels + count (those that exist, back to back), n_param, out_off      out  out
+ * GZB_E_CORRUPT: a channel out of data (:301).  Device pointers with GZB_DEVICE_PTRS (then channels_cap / out_cap bound the work). */
+typedef struct gzb_smux_vb {
+    const void     *txt;        uint64_t txt_len;
+    const uint64_t *qual_off;   /* mux */
+    const uint32_t *qual_len;
+    const uint64_t *seq_off;
+    const uint32_t *seq_len;    /* mux */
+    const uint8_t  *is_rev;     /* may be NULL */
+    uint32_t        n_lines;
+    int32_t         status;
+    void           *channels;   uint64_t channels_cap;
+    uint32_t        count[5];
+    uint8_t         n_param;
+    uint8_t         pad[3];
+    void           *out;        uint64_t out_cap;   /* demux */
+    const uint64_t *out_off;    /* demux */
+} gzb_smux_vb;
+int gzb_smux_mux   (gzb_engine *e, gzb_smux_vb *vbs, uint32_t n_vbs, uint32_t flags);
+int gzb_smux_demux (gzb_engine *e, gzb_smux_vb *vbs, uint32_t n_vbs, uint32_t flags);
 
 /* ---------------------------------------------------------------- PBWT (src/codec_pbwt.c)
  * encode: codec_pbwt_compress (:244-287): haplotype matrix → RUNS (uint32) + FGRC ({allele:8,count:24}; the last

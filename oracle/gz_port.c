@@ -746,3 +746,54 @@ int orc_hp_expand (int mode, const uint8_t *local, uint64_t local_len, const uin
     }
     return next == local_len ? 0 : -1;
 }
+
+/* ================================================================ SMUX (reference src/codec_smux.c)
+ * mux   = codec_smux_compress (:180-262); channels = the 5 channels back to back (count[b] bytes each), *n_param = the fifth channel's character when monochar.
+ * demux = codec_smux_reconstruct (:273-355) line by line, output in the read's own orientation; a read without quality writes the '*' of
+ *         sam_reconstruct_missing_quality at the start of its slot (slots are len[i] bytes).  -1: a channel is out of data. */
+static unsigned smux_enc (uint8_t c, int comp) { unsigned k = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 4; return (comp && k < 4) ? 3 - k : k; }   /* reference.c:78-84 */
+int orc_smux_mux (const uint8_t *txt, const uint64_t *qual_off, const uint32_t *qual_len, const uint64_t *seq_off, const uint32_t *seq_len, const uint8_t *is_rev,
+                  uint32_t n_lines, uint8_t *channels, uint32_t *count, uint8_t *n_param)
+{
+    uint64_t next[5], total = 0;
+    memset (count, 0, 5 * sizeof (uint32_t));
+    for (int pass = 0; pass < 2; pass++) {
+        for (uint32_t li = 0; li < n_lines; li++) {
+            const uint8_t *qual = txt + qual_off[li], *seq = txt + seq_off[li]; const uint32_t ql = qual_len[li], sl = seq_len[li];
+            const int rev = is_rev ? is_rev[li] : 0;
+            if (!ql) continue;
+            if (!rev)                      for (uint32_t i = 0; i < ql; i++)  { unsigned b = smux_enc (seq[i], 0); if (pass) channels[next[b]++] = qual[i]; else count[b]++; }
+            else if (ql == 1 && qual[0] == ' ')                               { unsigned b = smux_enc (seq[sl - 1], 1); if (pass) channels[next[b]++] = ' '; else count[b]++; }
+            else                           for (int32_t i = ql - 1; i >= 0; i--) { unsigned b = smux_enc (seq[i], 1); if (pass) channels[next[b]++] = qual[i]; else count[b]++; }
+        }
+        if (!pass) for (int b = 0; b < 5; b++) { next[b] = total; total += count[b]; }
+    }
+    *n_param = 0;
+    if (count[4]) {                                                                     /* :246-253 */
+        const uint8_t *c = channels + total - count[4]; int same = 1;
+        for (uint32_t i = 1; i < count[4] && same; i++) same = c[i] == c[0];
+        if (same) *n_param = c[0];
+    }
+    return 0;
+}
+int orc_smux_demux (const uint8_t *txt, const uint64_t *seq_off, const uint32_t *len, const uint8_t *is_rev, const uint64_t *out_off, uint32_t n_lines,
+                    const uint8_t *channels, const uint32_t *count, uint8_t n_param, uint8_t *out, uint8_t *missing)
+{
+    uint64_t next[5], after[5], total = 0;
+    for (int b = 0; b < 5; b++) { next[b] = total; total += count[b]; after[b] = total; }
+    for (uint32_t li = 0; li < n_lines; li++) {
+        const uint8_t *seq = txt + seq_off[li]; uint8_t *recon = out + out_off[li];
+        uint32_t L = len[li]; const int rev = is_rev ? is_rev[li] : 0;
+        if (missing) missing[li] = 0;
+        if (!L) continue;
+        if (seq[0] == '*') L = 1;                                                       /* :278-279 */
+        for (uint32_t t = 0; t < L; t++) {
+            const uint32_t i = rev ? L - 1 - t : t;
+            const unsigned b = smux_enc (seq[i], rev);
+            if (b == 4 && n_param) recon[i] = n_param;
+            else { if (next[b] >= after[b]) return -1; recon[i] = channels[next[b]++]; }
+            if (recon[i] == ' ') { recon[i] = 0; recon[0] = '*'; if (missing) missing[li] = 1; break; }   /* :307-310 */
+        }
+    }
+    return 0;
+}

@@ -757,6 +757,79 @@ int ref_hp_expand (int mode, const uint8_t *local, uint64_t local_len, const uin
     return rc;
 }
 
+// ================================================================ SMUX (the reference's compiled codec_smux.c)
+COMPRESSOR_CALLBACK (fastq_zip_qual) { shim_get_qual_rev (vb, ctx, vb_line_i, line_data, line_data_len, maximum_size, is_rev); }   // (codec_smux_calc_stats only: never called here)
+COMPRESSOR_CALLBACK (sam_zip_qual)   { shim_get_qual_rev (vb, ctx, vb_line_i, line_data, line_data_len, maximum_size, is_rev); }
+// codec_smux_compress on n_lines reads: the five channel contexts' locals back to back, the header param
+int ref_smux_mux (const uint8_t *txt, uint64_t txt_len, const uint64_t *qual_off, const uint32_t *qual_len, const uint64_t *seq_off, const uint32_t *seq_len, const uint8_t *is_rev,
+                  uint32_t n_lines, uint8_t *channels, uint32_t *count, uint8_t *n_param)
+{
+    shim_init ();
+    if (setjmp (on_abort)) return -1;
+    VBlockP vb = calloc (1, sizeof (VBlock));
+    vb->vblock_i = 1; vb->lines.len = n_lines; vb->data_type = DT_SAM;
+    g_txt = (uint8_t *)txt; g_off = qual_off; g_len = qual_len; g_seq_off = seq_off; g_seq_len = seq_len; g_is_rev = is_rev;
+    ContextP ctx = CTX (SAM_QUAL);
+    ctx->did_i = SAM_QUAL; strcpy (ctx->tag_name, "QUAL"); ctx->dict_id = (DictId)_SAM_QUAL;
+    SectionHeaderCtx header = {};
+    uint32_t ulen = 0, clen = 64;
+    char comp[64] = {};
+    if (!codec_smux_compress (vb, ctx, (SectionHeaderP)&header, NULL, &ulen, shim_get_qual_rev, comp, &clen, true, "QUAL")) return -3;
+    *n_param = header.param;
+    uint64_t at = 0;
+    for (Did d = SHIM_FIRST_DYN_DID; d < vb->ca.num_contexts; d++) {       // created in the order A, C, G, T, N (decl_smux_ctxs_zip, :16-21)
+        ContextP c = &vb->ca.contexts[d]; const int b = d - SHIM_FIRST_DYN_DID;
+        if (b >= 5) return -4;
+        count[b] = c->local.len32;
+        if (b == 4 && header.param && !count[b])                             // dropped (:249-252): its bytes are still there, as many as the lines hold bases that are not A, C, G, T
+            for (uint32_t i = 0; i < n_lines; i++) {
+                const uint8_t *sq = txt + seq_off[i];
+                if (qual_len[i] == 1 && txt[qual_off[i]] == ' ' && is_rev && is_rev[i]) { const uint8_t ch = sq[seq_len[i] - 1]; count[b] += !(ch == 'A' || ch == 'C' || ch == 'G' || ch == 'T'); }
+                else for (uint32_t k = 0; k < qual_len[i]; k++) count[b] += !(sq[k] == 'A' || sq[k] == 'C' || sq[k] == 'G' || sq[k] == 'T');
+            }
+        if (c->local.data && count[b]) { memcpy (channels + at, c->local.data, count[b]); at += count[b]; }
+    }
+    free (vb);
+    return 0;
+}
+
+// codec_smux_reconstruct line by line (SAM in, SAM out): every line's bytes at out_off[i]; a read without quality contributes the one character '*'
+int ref_smux_demux (const uint8_t *txt, uint64_t txt_len, const uint64_t *seq_off, const uint32_t *len, const uint8_t *is_rev, const uint64_t *out_off, uint32_t n_lines,
+                    const uint8_t *channels, const uint32_t *count, uint8_t n_param, uint8_t *out, uint64_t out_size)
+{
+    shim_init_piz ();
+    if (setjmp (on_abort)) { shim_missing_ok = false; return -1; }
+    shim_missing_ok = true;
+    flag.out_dt = DT_SAM;
+    VBlockP vb = calloc (1, sizeof (VBlock));
+    vb->vblock_i = 1; vb->lines.len = n_lines; vb->data_type = DT_SAM;
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n_lines; i++) total += len[i];
+    buf_alloc_do (vb, &vb->txt_data, total + 64, 1, "txt_data", __FUNCLINE);
+    ContextP ctx = CTX (SAM_QUAL);
+    ctx->did_i = SAM_QUAL; ctx->is_loaded = true; ctx->dict_id = (DictId)_SAM_QUAL; ctx->local.param = n_param;
+    static const char base_of[5] = { 'A', 'C', 'G', 'T', 'N' };
+    uint64_t at = 0;
+    for (int b = 0; b < 5; b++) {
+        if (!count[b]) continue;                                            // a channel that is not in the file: ECTX returns NULL
+        const char *id = ctx->dict_id.id;
+        ContextP c = ctx_get_unmapped_ctx (&vb->ca, DT_SAM, (DictId)DICT_ID_MAKEF_8(((char[]){base_of[b], base_of[b], base_of[b], '-', (id[0] & 0x7f) | 0x40, id[1], id[2], id[3]})), 0, 0);
+        buf_alloc_do (vb, &c->local, count[b] + 8, 1, "local", __FUNCLINE);
+        memcpy (c->local.data, channels + at, count[b]); c->local.len = count[b]; at += count[b];
+    }
+    for (uint32_t i = 0; i < n_lines; i++) {
+        if (!len[i]) continue;
+        cur_seq = (rom)txt + seq_off[i]; cur_is_rev = is_rev ? is_rev[i] : false; vb->seq_len = len[i];
+        const uint64_t before = vb->txt_data.len;
+        codec_smux_reconstruct (vb, CODEC_SMUX, ctx, len[i], true);
+        if (out_off[i] + (vb->txt_data.len - before) > out_size) { shim_missing_ok = false; return -2; }
+        memcpy (out + out_off[i], vb->txt_data.data + before, vb->txt_data.len - before);
+    }
+    shim_missing_ok = false;
+    free (vb);
+    return 0;
+}
+
 // ================================================================ zip_generate_local's transforms: the reference's own macros
 // (INTERLACE / DEINTERLACE of context.h:98-101, BGEN16/32/64 of endianness.h) in the loops of buffer.c:337-345, :431-468
 int ref_local_transform (int op, void *data, uint64_t n)

@@ -330,6 +330,38 @@ class MockLib:
             a.status = 0
         return 0
 
+    def gzb_smux_mux(self, h, vbs, n, flags):
+        for i in range(n):
+            a = vbs[i]
+            nl = a.n_lines
+            rev = _view(a.is_rev, nl).copy() if a.is_rev and nl else None
+            ch, cnt, par = orc.smux_mux(_view(a.txt, a.txt_len).copy(), _view(a.qual_off, nl, np.uint64).copy(), _view(a.qual_len, nl, np.uint32).copy(),
+                                        _view(a.seq_off, nl, np.uint64).copy(), _view(a.seq_len, nl, np.uint32).copy(), rev)
+            if ch.size:
+                _view(a.channels, ch.size)[:] = ch
+            for b in range(5):
+                a.count[b] = int(cnt[b])
+            a.n_param = par; a.status = 0
+        return 0
+
+    def gzb_smux_demux(self, h, vbs, n, flags):
+        for i in range(n):
+            a = vbs[i]
+            nl = a.n_lines
+            rev = _view(a.is_rev, nl).copy() if a.is_rev and nl else None
+            cnt = np.array(a.count[:], np.uint32)
+            ch = _view(a.channels, int(cnt.sum())).copy()
+            if (ch == 32).any():
+                a.status = -5; self.err = "SMUX: a read without quality"; return -5
+            out = orc.smux_demux(_view(a.txt, a.txt_len).copy(), _view(a.seq_off, nl, np.uint64).copy(), _view(a.qual_len, nl, np.uint32).copy(), rev,
+                                 _view(a.out_off, nl, np.uint64).copy(), a.out_cap, ch, cnt, a.n_param)
+            if out is None:
+                a.status = -4; self.err = "OQ / SMUX: a channel is out of data"; return -4
+            if out.size:
+                _view(a.out, out.size)[:] = out
+            a.status = 0
+        return 0
+
     def gzb_homp_condense(self, h, vbs, n, mode, flags):
         for i in range(n):
             a = vbs[i]

@@ -622,3 +622,44 @@ def hp_expand(mode, local, txt, seq_off, lens, lib="port"):
     n = C.c_uint64()
     rc = L.ref_hp_expand(mode, _ptr(lo), local.size, _ptr(txt), _ptr(qo), _ptr(sl), sl.size, _ptr(out), C.byref(n))
     return None if rc != 0 else (out[:int(sl.sum())].copy(), None)
+
+
+# ---------------------------------------------------------------- SMUX (src/codec_smux.c)
+def smux_mux(txt, qoff, qlen, soff, slen, is_rev=None, lib="port"):
+    """codec_smux_compress -> (the 5 channels back to back, count[5], n_param)"""
+    txt = np.ascontiguousarray(txt, np.uint8); qoff = np.ascontiguousarray(qoff, np.uint64); qlen = np.ascontiguousarray(qlen, np.uint32)
+    soff = np.ascontiguousarray(soff, np.uint64); slen = np.ascontiguousarray(slen, np.uint32)
+    rv = None if is_rev is None else np.ascontiguousarray(is_rev, np.uint8)
+    chan = np.zeros(int(qlen.sum()) + 8, np.uint8); count = np.zeros(5, np.uint32); par = C.c_uint8(0)
+    rvp = None if rv is None else _ptr(rv)
+    if lib == "port":
+        L = port()
+        L.orc_smux_mux.restype = C.c_int
+        L.orc_smux_mux.argtypes = [C.c_void_p] * 6 + [C.c_uint32] + [C.c_void_p] * 3
+        rc = L.orc_smux_mux(_ptr(txt), _ptr(qoff), _ptr(qlen), _ptr(soff), _ptr(slen), rvp, qlen.size, _ptr(chan), _ptr(count), C.byref(par))
+    else:
+        L = gz_ref()
+        L.ref_smux_mux.restype = C.c_int
+        L.ref_smux_mux.argtypes = [C.c_void_p, C.c_uint64] + [C.c_void_p] * 5 + [C.c_uint32] + [C.c_void_p] * 3
+        rc = L.ref_smux_mux(_ptr(txt), txt.size, _ptr(qoff), _ptr(qlen), _ptr(soff), _ptr(slen), rvp, qlen.size, _ptr(chan), _ptr(count), C.byref(par))
+    assert rc == 0, rc
+    return chan[:int(count.sum())].copy(), count, int(par.value)
+
+
+def smux_demux(txt, soff, lens, is_rev, out_off, out_size, channels, count, n_param, lib="port"):
+    """codec_smux_reconstruct for every line -> out (None when a channel runs out of data)"""
+    txt = np.ascontiguousarray(txt, np.uint8); soff = np.ascontiguousarray(soff, np.uint64); lens = np.ascontiguousarray(lens, np.uint32)
+    ooff = np.ascontiguousarray(out_off, np.uint64); rv = None if is_rev is None else np.ascontiguousarray(is_rev, np.uint8)
+    ch = np.ascontiguousarray(channels, np.uint8); ch = ch if ch.size else np.zeros(1, np.uint8); count = np.ascontiguousarray(count, np.uint32)
+    out = np.zeros(out_size + 8, np.uint8); rvp = None if rv is None else _ptr(rv)
+    if lib == "port":
+        L = port()
+        L.orc_smux_demux.restype = C.c_int
+        L.orc_smux_demux.argtypes = [C.c_void_p] * 5 + [C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint8, C.c_void_p, C.c_void_p]
+        rc = L.orc_smux_demux(_ptr(txt), _ptr(soff), _ptr(lens), rvp, _ptr(ooff), lens.size, _ptr(ch), _ptr(count), n_param, _ptr(out), None)
+    else:
+        L = gz_ref()
+        L.ref_smux_demux.restype = C.c_int
+        L.ref_smux_demux.argtypes = [C.c_void_p, C.c_uint64] + [C.c_void_p] * 4 + [C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint8, C.c_void_p, C.c_uint64]
+        rc = L.ref_smux_demux(_ptr(txt), txt.size, _ptr(soff), _ptr(lens), rvp, _ptr(ooff), lens.size, _ptr(ch), _ptr(count), n_param, _ptr(out), out_size)
+    return None if rc != 0 else out[:out_size].copy()
