@@ -10,8 +10,10 @@
 // SMUX (src/codec_smux.c), the quality codec of MGI reads, is the same operation with other keys: QUAL[i] goes to the channel of the BASE at
 // position i (A, C, G, T, anything else: 5 channels), a reverse-complemented read walked backwards with complemented bases (:217-239); only the
 // fifth channel is tested for monochar (its character then travels in the section header's param, :246-253).
+// TMPL (src/codec_tmpl.c), the quality codec of Element reads, again: QUAL[i] goes to the channel of TEMPLATE[i] - '!', the template being
+// the most frequent quality of every read position (found once, in segconf); what a read has beyond the template goes to one more stream.
 //
-// Both are a STABLE distribution by key, the shape of arith_split.cu's bucket kernel: one CTA per VBlock, 32 warps owning 32
+// All three are a STABLE distribution by key, the shape of arith_split.cu's bucket kernel: one CTA per VBlock, 32 warps owning 32
 // consecutive ranges of lines; a count pass, a scan over (channel, warp), then every warp walks its lines again 32 characters at a
 // time and ranks equal keys by lane (__match_any_sync), which keeps the order inside the chunk; cursors per (warp, channel) in shared memory.
 #include <cstring>
@@ -40,8 +42,9 @@ struct OqVb {
     uint32_t       *count;       // [94]  mux: out; demux: in
     uint8_t        *mono;        // [94]  mux: out; demux: in
     uint32_t       *info;        // [0] error
-    uint32_t        n_lines, key_bias, kind, n_ch;   // kind 0 OQ (94 channels), 1 SMUX (5)
+    uint32_t        n_lines, key_bias, kind, n_ch;   // kind 0 OQ (94 channels), 1 SMUX (5), 2 TMPL (94 + the excess stream)
     unsigned long long chan_cap;
+    const uint8_t  *tmpl; uint32_t tmpl_len;         // TMPL
 };
 
 __device__ __forceinline__ uint32_t smux_enc (uint8_t c, bool comp)        // _nuke_encode / _nuke_encode_comp (src/reference.c:78-84)
@@ -54,18 +57,24 @@ __device__ __forceinline__ uint32_t smux_enc (uint8_t c, bool comp)        // _n
 // (mux) or written to (demux) position at (t) of the line's string.
 struct OqLine {
     const uint8_t *keys; const uint8_t *vals; uint8_t *dst;
-    uint32_t n, rev, last_key_only, bias, kind;
+    uint32_t n, rev, last_key_only, bias, kind, tmpl_len;
     bool dist;
     __device__ __forceinline__ uint32_t at (uint32_t t) const { return rev ? n - 1 - t : t; }
     __device__ __forceinline__ uint32_t key (uint32_t t) const
     {
         if (kind == 0) return (uint32_t)keys[t] - bias;
+        if (kind == 2) return t < tmpl_len ? (uint32_t)keys[t] - 33u : 94u;      // keys = the template (codec_tmpl.c:171-178); 94 = the excess stream
         return last_key_only ? smux_enc (keys[last_key_only - 1], true) : smux_enc (keys[at (t)], rev);
     }
 };
 template <int DEMUX> __device__ __forceinline__ OqLine oq_line (const OqVb &V, uint32_t l)
 {
-    OqLine L; L.kind = V.kind; L.bias = V.key_bias; L.rev = 0; L.last_key_only = 0; L.dist = true; L.dst = nullptr; L.vals = nullptr;
+    OqLine L; L.kind = V.kind; L.bias = V.key_bias; L.rev = 0; L.last_key_only = 0; L.dist = true; L.dst = nullptr; L.vals = nullptr; L.tmpl_len = V.tmpl_len;
+    if (V.kind == 2) {
+        L.n = V.a_len[l]; L.keys = V.tmpl;
+        if (DEMUX) L.dst = V.out + V.out_off[l]; else L.vals = V.txt + V.a_off[l];
+        return L;
+    }
     if (V.kind == 0) {
         L.n = V.a_len[l]; L.keys = V.txt + V.a_off[l];
         if (DEMUX) L.dst = V.out + V.out_off[l];
@@ -169,7 +178,7 @@ __global__ void __launch_bounds__(OQ_WARPS * 32) k_oq (const OqVb *vbs)
     for (uint32_t k = warp; k < n_ch; k += OQ_WARPS) {
         const uint32_t n = tot[k];
         uint8_t m = 0;
-        if (n && (V.kind == 0 || k == 4)) {
+        if (n && (V.kind == 0 || (V.kind == 1 && k == 4))) {
             const uint8_t *c = V.chan + base[k];
             const uint8_t first = c[0];
             bool same = true;
@@ -201,6 +210,7 @@ struct OqHost {
     void *channels; uint64_t channels_cap; uint32_t *count; uint8_t *mono;
     void *out; uint64_t out_cap; const uint64_t *out_off;
     int32_t *status;
+    const uint8_t *tmpl = nullptr; uint32_t tmpl_len = 0;                    // TMPL: host memory always
 };
 
 int oq_run (gzb_engine *e, std::vector<OqHost> &vbs, uint32_t flags, int demux)
@@ -214,7 +224,8 @@ int oq_run (gzb_engine *e, std::vector<OqHost> &vbs, uint32_t flags, int demux)
     std::vector<uint64_t> total (n_vbs, 0), chan_bytes (n_vbs, 0);
     for (uint32_t v = 0; v < n_vbs; v++) {
         OqHost &S = vbs[v]; *S.status = GZB_OK;
-        const bool need_a_off = S.kind == 0 || !demux, need_b_off = S.kind == 1 || !demux;
+        const bool need_a_off = S.kind == 0 || !demux, need_b_off = S.kind == 1 || (S.kind == 0 && !demux);
+        if (S.kind == 2 && S.tmpl_len && !S.tmpl) return GZB_E_BADARG;
         if ((S.n_lines && (!S.a_len || (need_a_off && !S.a_off) || (need_b_off && !S.b_off) || (S.kind == 1 && !demux && !S.b_len) || (demux && (!S.out_off || !S.out)))) ||
             (!S.txt && S.txt_len) || (!S.channels && S.channels_cap)) return GZB_E_BADARG;
         if (!devptr) for (uint32_t i = 0; i < S.n_lines; i++) total[v] += S.a_len[i];
@@ -245,6 +256,7 @@ int oq_run (gzb_engine *e, std::vector<OqHost> &vbs, uint32_t flags, int demux)
             D.out_off = !demux ? nullptr : devptr ? S.out_off : c.take<uint64_t> ((size_t)S.n_lines + 1);
             D.out     = !demux ? nullptr : devptr ? (uint8_t *)S.out : c.take<uint8_t> (S.out_cap + 16);
             D.chan    = devptr ? (uint8_t *)S.channels : c.take<uint8_t> (chan_bytes[v] + 16);
+            D.tmpl    = S.kind == 2 ? c.take<uint8_t> ((size_t)S.tmpl_len + 16) : nullptr; D.tmpl_len = S.tmpl_len;
         }
         if (pass == 0) { int rc = engine_reserve (e, c.off, desc_bytes + meta_bytes + 512); if (rc) return rc; c.base = e->ws; }
     }
@@ -255,6 +267,7 @@ int oq_run (gzb_engine *e, std::vector<OqHost> &vbs, uint32_t flags, int demux)
         const OqHost &S = vbs[v]; OqVb &D = h[v];
         memset (p_count + (size_t)OQ_PAD * v, 0, OQ_PAD * 4); memset (p_mono + (size_t)OQ_PAD * v, 0, OQ_PAD);
         if (demux) { memcpy (p_count + (size_t)OQ_PAD * v, S.count, S.n_ch * 4); memcpy (p_mono + (size_t)OQ_PAD * v, S.mono, S.n_ch); }
+        if (S.kind == 2 && S.tmpl_len) CK (cudaMemcpyAsync ((void *)D.tmpl, S.tmpl, S.tmpl_len, cudaMemcpyHostToDevice, st));   // (pageable, tiny)
         if (devptr) { if (!demux && chan_bytes[v]) CK (cudaMemsetAsync (D.chan, 0, chan_bytes[v], st)); continue; }
         if (S.n_lines) {
             CK (cudaMemcpyAsync ((void *)D.a_len, S.a_len, (size_t)S.n_lines * 4, cudaMemcpyHostToDevice, st));
@@ -332,8 +345,25 @@ int smux_public (gzb_engine *e, gzb_smux_vb *vbs, uint32_t n_vbs, uint32_t flags
     return rc;
 }
 
+int tmpl_public (gzb_engine *e, gzb_tmpl_vb *vbs, uint32_t n_vbs, uint32_t flags, int demux)
+{
+    if (!e || (!vbs && n_vbs)) return GZB_E_BADARG;
+    std::vector<OqHost> h (n_vbs);
+    std::vector<uint8_t> mono ((size_t)n_vbs * OQ_PAD, 0);
+    for (uint32_t v = 0; v < n_vbs; v++) {
+        gzb_tmpl_vb &S = vbs[v];
+        h[v] = OqHost { S.txt, S.txt_len, demux ? nullptr : S.qual_off, S.qual_len, nullptr, nullptr, nullptr, S.n_lines, 33u, 2, 95,
+                        S.channels, S.channels_cap, S.count, &mono[(size_t)OQ_PAD * v], S.out, S.out_cap, S.out_off, &S.status };
+        h[v].tmpl = (const uint8_t *)S.tmpl; h[v].tmpl_len = S.tmpl_len;
+        for (uint32_t i = 0; i < S.tmpl_len; i++) if (h[v].tmpl[i] < 33 || h[v].tmpl[i] > 126) { e->err = "TMPL: a template character outside '!'..'~'"; return GZB_E_BADARG; }
+    }
+    return oq_run (e, h, flags, demux);
+}
+
 } // namespace
 
+extern "C" int gzb_tmpl_mux   (gzb_engine *e, gzb_tmpl_vb *vbs, uint32_t n_vbs, uint32_t flags) { return tmpl_public (e, vbs, n_vbs, flags, 0); }
+extern "C" int gzb_tmpl_demux (gzb_engine *e, gzb_tmpl_vb *vbs, uint32_t n_vbs, uint32_t flags) { return tmpl_public (e, vbs, n_vbs, flags, 1); }
 extern "C" int gzb_oq_mux     (gzb_engine *e, gzb_oq_vb *vbs, uint32_t n_vbs, uint32_t flags)   { return oq_public (e, vbs, n_vbs, flags, 0); }
 extern "C" int gzb_oq_demux   (gzb_engine *e, gzb_oq_vb *vbs, uint32_t n_vbs, uint32_t flags)   { return oq_public (e, vbs, n_vbs, flags, 1); }
 extern "C" int gzb_smux_mux   (gzb_engine *e, gzb_smux_vb *vbs, uint32_t n_vbs, uint32_t flags) { return smux_public (e, vbs, n_vbs, flags, 0); }

@@ -93,6 +93,12 @@ class SmuxVb(C.Structure):          # gzb_smux_vb
                 ("out", C.c_void_p), ("out_cap", C.c_uint64), ("out_off", C.c_void_p)]
 
 
+class TmplVb(C.Structure):          # gzb_tmpl_vb
+    _fields_ = [("txt", C.c_void_p), ("txt_len", C.c_uint64), ("qual_off", C.c_void_p), ("qual_len", C.c_void_p), ("n_lines", C.c_uint32), ("status", C.c_int32),
+                ("tmpl", C.c_void_p), ("tmpl_len", C.c_uint32), ("reserved", C.c_uint32), ("channels", C.c_void_p), ("channels_cap", C.c_uint64),
+                ("count", C.c_uint32 * 95), ("pad", C.c_uint32), ("out", C.c_void_p), ("out_cap", C.c_uint64), ("out_off", C.c_void_p)]
+
+
 class LocalItem(C.Structure):       # gzb_local_item
     _fields_ = [("data", C.c_void_p), ("n_elems", C.c_uint64), ("op", C.c_int32), ("status", C.c_int32)]
 
@@ -187,7 +193,7 @@ def load():
     for f in ("gzb_stage_upload", "gzb_stage_fetch"):
         getattr(L, f).restype = C.c_int; getattr(L, f).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     L.gzb_stage_wait.restype = C.c_int; L.gzb_stage_wait.argtypes = [C.c_void_p, C.c_int]
-    for f in ("gzb_normq_gather", "gzb_normq_reconstruct", "gzb_oq_mux", "gzb_oq_demux", "gzb_smux_mux", "gzb_smux_demux"):
+    for f in ("gzb_normq_gather", "gzb_normq_reconstruct", "gzb_oq_mux", "gzb_oq_demux", "gzb_smux_mux", "gzb_smux_demux", "gzb_tmpl_mux", "gzb_tmpl_demux"):
         getattr(L, f).restype = C.c_int; getattr(L, f).argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
     L.gzb_local_transform_batch.restype = C.c_int
     L.gzb_local_transform_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
@@ -448,6 +454,47 @@ class Engine:
         if rc != 0:
             raise GzbError(f"gzb_smux_demux failed ({rc}): {self._err()}")
         return [k[6][:k[7]].copy() for k in keep]
+
+    # ---- TMPL (host buffers) ----
+    def tmpl_mux(self, vbs):
+        """vbs: list of (txt, qual_off, qual_len, template) -> list of (channels 0..93 and the excess back to back, count[95])"""
+        arr = (TmplVb * max(1, len(vbs)))(); keep = []
+        for i, (txt, qoff, qlen, tmpl) in enumerate(vbs):
+            txt = np.ascontiguousarray(txt, np.uint8); qoff = np.ascontiguousarray(qoff, np.uint64); qlen = np.ascontiguousarray(qlen, np.uint32); tmpl = np.ascontiguousarray(tmpl, np.uint8)
+            ch = np.zeros(int(qlen.sum()) + 16, np.uint8)
+            keep.append((txt, qoff, qlen, tmpl, ch))
+            a = arr[i]
+            a.txt = txt.ctypes.data if txt.size else None; a.txt_len = txt.size; a.n_lines = qlen.size
+            a.qual_off = qoff.ctypes.data if qoff.size else None; a.qual_len = qlen.ctypes.data if qlen.size else None
+            a.tmpl = tmpl.ctypes.data if tmpl.size else None; a.tmpl_len = tmpl.size
+            a.channels = ch.ctypes.data; a.channels_cap = ch.size
+        rc = self.L.gzb_tmpl_mux(self.h, arr, len(vbs), 0)
+        if rc != 0:
+            raise GzbError(f"gzb_tmpl_mux failed ({rc}): {self._err()}")
+        out = []
+        for i, k in enumerate(keep):
+            cnt = np.array(arr[i].count[:], np.uint32)
+            out.append((k[4][:int(cnt.sum())].copy(), cnt))
+        return out
+
+    def tmpl_demux(self, vbs):
+        """vbs: list of (lens, out_off, out_size, template, channels, count[95]) -> list of out arrays"""
+        arr = (TmplVb * max(1, len(vbs)))(); keep = []
+        for i, (lens, ooff, out_size, tmpl, ch, cnt) in enumerate(vbs):
+            lens = np.ascontiguousarray(lens, np.uint32); ooff = np.ascontiguousarray(ooff, np.uint64); tmpl = np.ascontiguousarray(tmpl, np.uint8)
+            ch = np.ascontiguousarray(ch, np.uint8); ch = ch if ch.size else np.zeros(1, np.uint8); out = np.zeros(out_size + 16, np.uint8)
+            keep.append((lens, ooff, tmpl, ch, out, out_size))
+            a = arr[i]
+            a.n_lines = lens.size; a.qual_len = lens.ctypes.data if lens.size else None; a.out_off = ooff.ctypes.data if ooff.size else None
+            a.tmpl = tmpl.ctypes.data if tmpl.size else None; a.tmpl_len = tmpl.size
+            a.channels = ch.ctypes.data; a.channels_cap = ch.size
+            for q in range(95):
+                a.count[q] = int(cnt[q])
+            a.out = out.ctypes.data; a.out_cap = out_size
+        rc = self.L.gzb_tmpl_demux(self.h, arr, len(vbs), 0)
+        if rc != 0:
+            raise GzbError(f"gzb_tmpl_demux failed ({rc}): {self._err()}")
+        return [k[4][:k[5]].copy() for k in keep]
 
     # ---- HOMP / T0 (host buffers) ----
     def hp_condense(self, mode, vbs):

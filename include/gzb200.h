@@ -381,6 +381,30 @@ typedef struct gzb_smux_vb {
 int gzb_smux_mux   (gzb_engine *e, gzb_smux_vb *vbs, uint32_t n_vbs, uint32_t flags);
 int gzb_smux_demux (gzb_engine *e, gzb_smux_vb *vbs, uint32_t n_vbs, uint32_t flags);
 
+/* ---------------------------------------------------------------- TMPL (src/codec_tmpl.c): Element's quality codec — QUAL multiplexed by a template
+ * The template (found once per component in segconf, codec_tmpl_segconf_finalize :22-107: the most frequent quality of every read position)
+ * is the caller's: tmpl / tmpl_len, host memory.
+ * mux:   codec_tmpl_compress (:145-210): QUAL[i] goes to channel tmpl[i] - '!' for i < tmpl_len; what a read has beyond the template goes,
+ *        in line order, to the excess stream ((ctx+1)->local, :180-182) — channel 94 here.
+ *            in  txt, qual_off, qual_len, tmpl      out  channels (channel q at the sum of count[0..q)), count[95]
+ * demux: codec_tmpl_reconstruct (:216-259) for every line of a VBlock at once: qual_len[i] = the `len` of the i-th call.
+ *            in  qual_len, tmpl, channels + count, out_off      out  out
+ * GZB_E_CORRUPT: a channel out of data.  Device pointers with GZB_DEVICE_PTRS (then channels_cap / out_cap bound the work). */
+typedef struct gzb_tmpl_vb {
+    const void     *txt;        uint64_t txt_len;   /* mux */
+    const uint64_t *qual_off;   /* mux */
+    const uint32_t *qual_len;
+    uint32_t        n_lines;
+    int32_t         status;
+    const void     *tmpl;       uint32_t tmpl_len;  uint32_t reserved;
+    void           *channels;   uint64_t channels_cap;
+    uint32_t        count[95];  uint32_t pad;
+    void           *out;        uint64_t out_cap;   /* demux */
+    const uint64_t *out_off;    /* demux */
+} gzb_tmpl_vb;
+int gzb_tmpl_mux   (gzb_engine *e, gzb_tmpl_vb *vbs, uint32_t n_vbs, uint32_t flags);
+int gzb_tmpl_demux (gzb_engine *e, gzb_tmpl_vb *vbs, uint32_t n_vbs, uint32_t flags);
+
 /* ---------------------------------------------------------------- PBWT (src/codec_pbwt.c)
  * encode: codec_pbwt_compress (:244-287): haplotype matrix → RUNS (uint32) + FGRC ({allele:8,count:24}; the last
  *         two words are the 64-bit matrix length, :274-276).  Host-endian words.

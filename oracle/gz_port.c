@@ -797,3 +797,36 @@ int orc_smux_demux (const uint8_t *txt, const uint64_t *seq_off, const uint32_t 
     }
     return 0;
 }
+
+/* ================================================================ TMPL (reference src/codec_tmpl.c)
+ * mux   = codec_tmpl_compress (:145-210): channels 0..93 by the template, 94 = the excess beyond the template ((ctx+1)->local), back to back.
+ * demux = codec_tmpl_reconstruct (:216-259) line by line.  -1: a channel is out of data. */
+int orc_tmpl_mux (const uint8_t *txt, const uint64_t *qual_off, const uint32_t *qual_len, uint32_t n_lines, const uint8_t *tmpl, uint32_t tmpl_len, uint8_t *channels, uint32_t *count)
+{
+    uint64_t next[95], total = 0;
+    memset (count, 0, 95 * sizeof (uint32_t));
+    for (int pass = 0; pass < 2; pass++) {
+        for (uint32_t li = 0; li < n_lines; li++) {
+            const uint8_t *q = txt + qual_off[li];
+            for (uint32_t i = 0; i < qual_len[li]; i++) {
+                const unsigned ch = i < tmpl_len ? (unsigned)tmpl[i] - 33u : 94u;
+                if (ch > 94) return -1;
+                if (pass) channels[next[ch]++] = q[i]; else count[ch]++;
+            }
+        }
+        if (!pass) for (int c = 0; c < 95; c++) { next[c] = total; total += count[c]; }
+    }
+    return 0;
+}
+int orc_tmpl_demux (const uint32_t *len, const uint64_t *out_off, uint32_t n_lines, const uint8_t *tmpl, uint32_t tmpl_len, const uint8_t *channels, const uint32_t *count, uint8_t *out)
+{
+    uint64_t next[95], after[95], total = 0;
+    for (int c = 0; c < 95; c++) { next[c] = total; total += count[c]; after[c] = total; }
+    for (uint32_t li = 0; li < n_lines; li++)
+        for (uint32_t i = 0; i < len[li]; i++) {
+            const unsigned ch = i < tmpl_len ? (unsigned)tmpl[i] - 33u : 94u;
+            if (ch > 94 || next[ch] >= after[ch]) return -1;
+            out[out_off[li] + i] = channels[next[ch]++];
+        }
+    return 0;
+}

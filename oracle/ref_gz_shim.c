@@ -830,6 +830,51 @@ int ref_smux_demux (const uint8_t *txt, uint64_t txt_len, const uint64_t *seq_of
     return 0;
 }
 
+// ================================================================ TMPL (the reference's compiled codec_tmpl.c)
+ContextP ctx_get_zctx_from_vctx (ConstContextP vctx, bool create_if_missing, bool follow_alias) { return &z_file->ca.contexts[vctx->did_i]; }   // the z-side twin: same slot
+void ctx_segconf_set_hard_coded_lcodec (Did did_i, Codec codec) {}
+void buf_insert_do (VBlockP vb, BufferP buf, unsigned width, uint64_t insert_at, const void *new_data, uint64_t new_data_len, rom name, FUNCLINE)
+{
+    if (insert_at != buf->len) ABORT0 ("shim: buf_insert_do only appends");
+    buf_alloc_do (vb, buf, (buf->len + new_data_len) * width + 64, 1.5, name, func, code_line);
+    memcpy (buf->data + buf->len * width, new_data, new_data_len * width);
+    buf->len += new_data_len;
+}
+
+// codec_tmpl_segconf_finalize (the template: the most frequent quality per position) + codec_tmpl_compress on n_lines quality strings.
+// Returns 1 when the reference finds the template not dominant enough (:67-74), else 0 with the template, the 94 channels and the excess back to back
+int ref_tmpl_mux (const uint8_t *txt, uint64_t txt_len, const uint64_t *qual_off, const uint32_t *qual_len, uint32_t n_lines, uint32_t tmpl_len,
+                  uint8_t *tmpl_out, uint8_t *channels, uint32_t *count)
+{
+    shim_init ();
+    if (setjmp (on_abort)) return -1;
+    VBlockP vb = calloc (1, sizeof (VBlock));
+    vb->vblock_i = 1; vb->lines.len = n_lines; vb->data_type = DT_FASTQ;
+    g_txt = (uint8_t *)txt; g_off = qual_off; g_len = qual_len;
+    segconf.std_seq_len = tmpl_len;
+    ContextP ctx = CTX (FASTQ_QUAL);
+    ctx->did_i = FASTQ_QUAL; strcpy (ctx->tag_name, "QUAL"); (ctx + 1)->did_i = FASTQ_QUAL + 1;
+    ContextP zctx = &z_file->ca.contexts[FASTQ_QUAL];
+    memset (zctx, 0, 2 * sizeof (Context)); zctx->did_i = FASTQ_QUAL; (zctx + 1)->did_i = FASTQ_QUAL + 1;
+    codec_tmpl_segconf_finalize (vb, FASTQ_QUAL, shim_get_line);
+    if (!zctx->tmpl_calculated) { free (vb); return 1; }
+    memcpy (tmpl_out, (zctx + 1)->template.data, tmpl_len);
+    SectionHeaderCtx header = {};
+    uint32_t ulen = 0, clen = 64; char comp[64] = {};
+    if (!codec_tmpl_compress (vb, ctx, (SectionHeaderP)&header, NULL, &ulen, shim_get_line, comp, &clen, true, "QUAL")) return -3;
+    uint64_t at = 0;
+    DictId tmpl_dict_id = (DictId)DICT_ID_MAKEF_4("tmpl");                   // codec_tmpl.c:77
+    for (int q = 0; q < 94; q++) {
+        Did d = ctx_get_unmapped_existing_did_i (&vb->ca, sub_dict_id (tmpl_dict_id, q + 33));
+        count[q] = d == DID_NONE ? 0 : vb->ca.contexts[d].local.len32;
+        if (count[q]) { memcpy (channels + at, vb->ca.contexts[d].local.data, count[q]); at += count[q]; }
+    }
+    count[94] = (ctx + 1)->local.len32;
+    if (count[94]) memcpy (channels + at, (ctx + 1)->local.data, count[94]);
+    free (vb);
+    return 0;
+}
+
 // ================================================================ zip_generate_local's transforms: the reference's own macros
 // (INTERLACE / DEINTERLACE of context.h:98-101, BGEN16/32/64 of endianness.h) in the loops of buffer.c:337-345, :431-468
 int ref_local_transform (int op, void *data, uint64_t n)

@@ -330,6 +330,32 @@ class MockLib:
             a.status = 0
         return 0
 
+    def gzb_tmpl_mux(self, h, vbs, n, flags):
+        for i in range(n):
+            a = vbs[i]
+            nl = a.n_lines
+            ch, cnt = orc.tmpl_mux(_view(a.txt, a.txt_len).copy(), _view(a.qual_off, nl, np.uint64).copy(), _view(a.qual_len, nl, np.uint32).copy(), _view(a.tmpl, a.tmpl_len).copy())
+            if ch.size:
+                _view(a.channels, ch.size)[:] = ch
+            for q in range(95):
+                a.count[q] = int(cnt[q])
+            a.status = 0
+        return 0
+
+    def gzb_tmpl_demux(self, h, vbs, n, flags):
+        for i in range(n):
+            a = vbs[i]
+            nl = a.n_lines
+            cnt = np.array(a.count[:], np.uint32)
+            out = orc.tmpl_demux(_view(a.qual_len, nl, np.uint32).copy(), _view(a.out_off, nl, np.uint64).copy(), a.out_cap, _view(a.tmpl, a.tmpl_len).copy(),
+                                 _view(a.channels, int(cnt.sum())).copy(), cnt)
+            if out is None:
+                a.status = -4; self.err = "OQ / SMUX: a channel is out of data"; return -4
+            if out.size:
+                _view(a.out, out.size)[:] = out
+            a.status = 0
+        return 0
+
     def gzb_smux_mux(self, h, vbs, n, flags):
         for i in range(n):
             a = vbs[i]

@@ -663,3 +663,40 @@ def smux_demux(txt, soff, lens, is_rev, out_off, out_size, channels, count, n_pa
         L.ref_smux_demux.argtypes = [C.c_void_p, C.c_uint64] + [C.c_void_p] * 4 + [C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint8, C.c_void_p, C.c_uint64]
         rc = L.ref_smux_demux(_ptr(txt), txt.size, _ptr(soff), _ptr(lens), rvp, _ptr(ooff), lens.size, _ptr(ch), _ptr(count), n_param, _ptr(out), out_size)
     return None if rc != 0 else out[:out_size].copy()
+
+
+# ---------------------------------------------------------------- TMPL (src/codec_tmpl.c)
+def tmpl_mux(txt, qoff, qlen, tmpl):
+    """restatement of codec_tmpl_compress -> (channels 0..93 and the excess back to back, count[95])"""
+    L = port()
+    L.orc_tmpl_mux.restype = C.c_int
+    L.orc_tmpl_mux.argtypes = [C.c_void_p] * 3 + [C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    txt = np.ascontiguousarray(txt, np.uint8); qoff = np.ascontiguousarray(qoff, np.uint64); qlen = np.ascontiguousarray(qlen, np.uint32)
+    tmpl = np.ascontiguousarray(tmpl, np.uint8); t = tmpl if tmpl.size else np.zeros(1, np.uint8)
+    chan = np.zeros(int(qlen.sum()) + 8, np.uint8); count = np.zeros(95, np.uint32)
+    assert L.orc_tmpl_mux(_ptr(txt), _ptr(qoff), _ptr(qlen), qlen.size, _ptr(t), tmpl.size, _ptr(chan), _ptr(count)) == 0
+    return chan[:int(count.sum())].copy(), count
+
+
+def tmpl_demux(lens, out_off, out_size, tmpl, channels, count):
+    L = port()
+    L.orc_tmpl_demux.restype = C.c_int
+    L.orc_tmpl_demux.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lens = np.ascontiguousarray(lens, np.uint32); ooff = np.ascontiguousarray(out_off, np.uint64); tmpl = np.ascontiguousarray(tmpl, np.uint8)
+    t = tmpl if tmpl.size else np.zeros(1, np.uint8)
+    ch = np.ascontiguousarray(channels, np.uint8); ch = ch if ch.size else np.zeros(1, np.uint8); count = np.ascontiguousarray(count, np.uint32)
+    out = np.zeros(out_size + 8, np.uint8)
+    rc = L.orc_tmpl_demux(_ptr(lens), _ptr(ooff), lens.size, _ptr(t), tmpl.size, _ptr(ch), _ptr(count), _ptr(out))
+    return None if rc != 0 else out[:out_size].copy()
+
+
+def ref_tmpl_mux(txt, qoff, qlen, tmpl_len):
+    """the reference's compiled codec_tmpl.c: segconf_finalize (finds the template) + compress -> (template, channels, count[95]) or None (template not dominant)"""
+    L = gz_ref()
+    L.ref_tmpl_mux.restype = C.c_int
+    L.ref_tmpl_mux.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    txt = np.ascontiguousarray(txt, np.uint8); qoff = np.ascontiguousarray(qoff, np.uint64); qlen = np.ascontiguousarray(qlen, np.uint32)
+    tmpl = np.zeros(tmpl_len + 8, np.uint8); chan = np.zeros(int(qlen.sum()) + 8, np.uint8); count = np.zeros(95, np.uint32)
+    rc = L.ref_tmpl_mux(_ptr(txt), txt.size, _ptr(qoff), _ptr(qlen), qlen.size, tmpl_len, _ptr(tmpl), _ptr(chan), _ptr(count))
+    assert rc >= 0, rc
+    return None if rc == 1 else (tmpl[:tmpl_len].copy(), chan[:int(count.sum())].copy(), count)
