@@ -13,7 +13,10 @@
 // TMPL (src/codec_tmpl.c), the quality codec of Element reads, again: QUAL[i] goes to the channel of TEMPLATE[i] - '!', the template being
 // the most frequent quality of every read position (found once, in segconf); what a read has beyond the template goes to one more stream.
 //
-// All three are a STABLE distribution by key, the shape of arith_split.cu's bucket kernel: one CTA per VBlock, 32 warps owning 32
+// PACB (src/codec_pacb.c), the quality codec of PacBio reads: the channel of QUAL[i] is 7 * (min (np, max_np) - 1) + K, np the read's number of
+// passes and K one of 7 classes of the base's surroundings (inside / at the start of a homopolymer of 1, 2, 3+ bases, A/T or C/G, :19-27).
+//
+// All four are a STABLE distribution by key, the shape of arith_split.cu's bucket kernel: one CTA per VBlock, 32 warps owning 32
 // consecutive ranges of lines; a count pass, a scan over (channel, warp), then every warp walks its lines again 32 characters at a
 // time and ranks equal keys by lane (__match_any_sync), which keeps the order inside the chunk; cursors per (warp, channel) in shared memory.
 #include <cstring>
@@ -45,8 +48,18 @@ struct OqVb {
     uint32_t        n_lines, key_bias, kind, n_ch;   // kind 0 OQ (94 channels), 1 SMUX (5), 2 TMPL (94 + the excess stream)
     unsigned long long chan_cap;
     const uint8_t  *tmpl; uint32_t tmpl_len;         // TMPL
+    const uint8_t  *np0;                             // PACB: per line min (np, max_np) - 1, or NULL (FASTQ, CLR: always 0)
 };
 
+__device__ __forceinline__ uint32_t pacb_K (const uint8_t *seq, uint32_t len, uint32_t i)      // QUAL_get_K_value (src/codec_pacb.c:19-27)
+{
+    const uint8_t b = seq[i];
+    const uint32_t at = (b == 'A' || b == 'T') ? 1u : 0u;
+    if (i > 0 && seq[i - 1] == b) return 6;
+    if (i == len - 1 || seq[i + 1] != b) return 4 + at;
+    if (i == len - 2 || seq[i + 2] != b) return 2 + at;
+    return at;
+}
 __device__ __forceinline__ uint32_t smux_enc (uint8_t c, bool comp)        // _nuke_encode / _nuke_encode_comp (src/reference.c:78-84)
 {
     const uint32_t k = c == 'A' ? 0u : c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : 4u;
@@ -64,12 +77,18 @@ struct OqLine {
     {
         if (kind == 0) return (uint32_t)keys[t] - bias;
         if (kind == 2) return t < tmpl_len ? (uint32_t)keys[t] - 33u : 94u;      // keys = the template (codec_tmpl.c:171-178); 94 = the excess stream
+        if (kind == 3) return bias + pacb_K (keys, n, t);                       // bias = 7 * np0 of the line (codec_pacb.c:138-140)
         return last_key_only ? smux_enc (keys[last_key_only - 1], true) : smux_enc (keys[at (t)], rev);
     }
 };
 template <int DEMUX> __device__ __forceinline__ OqLine oq_line (const OqVb &V, uint32_t l)
 {
     OqLine L; L.kind = V.kind; L.bias = V.key_bias; L.rev = 0; L.last_key_only = 0; L.dist = true; L.dst = nullptr; L.vals = nullptr; L.tmpl_len = V.tmpl_len;
+    if (V.kind == 3) {
+        L.n = V.a_len[l]; L.keys = V.txt + V.b_off[l]; L.bias = V.np0 ? 7u * V.np0[l] : 0;
+        if (DEMUX) L.dst = V.out + V.out_off[l]; else L.vals = V.txt + V.a_off[l];
+        return L;
+    }
     if (V.kind == 2) {
         L.n = V.a_len[l]; L.keys = V.tmpl;
         if (DEMUX) L.dst = V.out + V.out_off[l]; else L.vals = V.txt + V.a_off[l];
@@ -164,7 +183,7 @@ __global__ void __launch_bounds__(OQ_WARPS * 32) k_oq (const OqVb *vbs)
             __syncwarp ();
             if (act) {
                 const uint32_t pos = b + __popc (peers & ((1u << lane) - 1));
-                if (DEMUX) { const uint8_t c = mono ? s_mono[k] : V.chan[pos]; L.dst[L.at (t)] = c; if (V.kind == 1 && c == ' ') blank = true; }
+                if (DEMUX) { const uint8_t c = mono ? s_mono[k] : V.chan[pos]; L.dst[L.at (t)] = c; if ((V.kind == 1 || V.kind == 3) && c == ' ') blank = true; }
                 else V.chan[pos] = L.last_key_only ? (uint8_t)' ' : L.vals[L.at (t)];
                 if (!mono && (peers >> lane) == 1) cur[warp][k] = b + __popc (peers);   // the highest lane of the group moves the cursor
             }
@@ -211,6 +230,7 @@ struct OqHost {
     void *out; uint64_t out_cap; const uint64_t *out_off;
     int32_t *status;
     const uint8_t *tmpl = nullptr; uint32_t tmpl_len = 0;                    // TMPL: host memory always
+    const uint8_t *np0 = nullptr;                                            // PACB
 };
 
 int oq_run (gzb_engine *e, std::vector<OqHost> &vbs, uint32_t flags, int demux)
@@ -224,7 +244,7 @@ int oq_run (gzb_engine *e, std::vector<OqHost> &vbs, uint32_t flags, int demux)
     std::vector<uint64_t> total (n_vbs, 0), chan_bytes (n_vbs, 0);
     for (uint32_t v = 0; v < n_vbs; v++) {
         OqHost &S = vbs[v]; *S.status = GZB_OK;
-        const bool need_a_off = S.kind == 0 || !demux, need_b_off = S.kind == 1 || (S.kind == 0 && !demux);
+        const bool need_a_off = S.kind == 0 || !demux, need_b_off = S.kind == 1 || S.kind == 3 || (S.kind == 0 && !demux);
         if (S.kind == 2 && S.tmpl_len && !S.tmpl) return GZB_E_BADARG;
         if ((S.n_lines && (!S.a_len || (need_a_off && !S.a_off) || (need_b_off && !S.b_off) || (S.kind == 1 && !demux && !S.b_len) || (demux && (!S.out_off || !S.out)))) ||
             (!S.txt && S.txt_len) || (!S.channels && S.channels_cap)) return GZB_E_BADARG;
@@ -257,6 +277,7 @@ int oq_run (gzb_engine *e, std::vector<OqHost> &vbs, uint32_t flags, int demux)
             D.out     = !demux ? nullptr : devptr ? (uint8_t *)S.out : c.take<uint8_t> (S.out_cap + 16);
             D.chan    = devptr ? (uint8_t *)S.channels : c.take<uint8_t> (chan_bytes[v] + 16);
             D.tmpl    = S.kind == 2 ? c.take<uint8_t> ((size_t)S.tmpl_len + 16) : nullptr; D.tmpl_len = S.tmpl_len;
+            D.np0     = !S.np0 ? nullptr : devptr ? S.np0 : c.take<uint8_t> ((size_t)S.n_lines + 1);
         }
         if (pass == 0) { int rc = engine_reserve (e, c.off, desc_bytes + meta_bytes + 512); if (rc) return rc; c.base = e->ws; }
     }
@@ -275,6 +296,7 @@ int oq_run (gzb_engine *e, std::vector<OqHost> &vbs, uint32_t flags, int demux)
             if (D.b_off)   CK (cudaMemcpyAsync ((void *)D.b_off, S.b_off, (size_t)S.n_lines * 8, cudaMemcpyHostToDevice, st));
             if (D.b_len)   CK (cudaMemcpyAsync ((void *)D.b_len, S.b_len, (size_t)S.n_lines * 4, cudaMemcpyHostToDevice, st));
             if (D.is_rev)  CK (cudaMemcpyAsync ((void *)D.is_rev, S.is_rev, S.n_lines, cudaMemcpyHostToDevice, st));
+            if (D.np0)     CK (cudaMemcpyAsync ((void *)D.np0, S.np0, S.n_lines, cudaMemcpyHostToDevice, st));
             if (D.out_off) CK (cudaMemcpyAsync ((void *)D.out_off, S.out_off, (size_t)S.n_lines * 8, cudaMemcpyHostToDevice, st));
         }
         if (S.txt_len) CK (cudaMemcpyAsync ((void *)D.txt, S.txt, S.txt_len, cudaMemcpyHostToDevice, st));
@@ -304,7 +326,7 @@ int oq_run (gzb_engine *e, std::vector<OqHost> &vbs, uint32_t flags, int demux)
         if (err) {
             *S.status = err == 2 ? GZB_E_BADARG : err == 4 ? GZB_E_UNSUPPORTED : GZB_E_CORRUPT; rc = *S.status;
             e->err = err == 1 ? "OQ / SMUX: a key outside the channels" : err == 2 ? "OQ / SMUX: the channel buffer is too small" : err == 3 ? "OQ / SMUX: a channel is out of data"
-                   : "SMUX: a read without quality — how much such a line consumes depends on the data: reconstruct these VBlocks line by line";
+                   : "SMUX / PACB: a read without quality — how much such a line consumes depends on the data: reconstruct these VBlocks line by line";
             continue;
         }
         if (!demux) {
@@ -360,8 +382,25 @@ int tmpl_public (gzb_engine *e, gzb_tmpl_vb *vbs, uint32_t n_vbs, uint32_t flags
     return oq_run (e, h, flags, demux);
 }
 
+int pacb_public (gzb_engine *e, gzb_pacb_vb *vbs, uint32_t n_vbs, uint32_t flags, int demux)
+{
+    if (!e || (!vbs && n_vbs)) return GZB_E_BADARG;
+    std::vector<OqHost> h (n_vbs);
+    std::vector<uint8_t> mono ((size_t)n_vbs * OQ_PAD, 0);
+    for (uint32_t v = 0; v < n_vbs; v++) {
+        gzb_pacb_vb &S = vbs[v];
+        if (S.max_np < 1 || S.max_np > 12 || (S.max_np > 1 && S.n_lines && !S.np0)) { e->err = "PACB: max_np must be 1..12 (MAX_np), np0 given when it is above 1"; return GZB_E_BADARG; }
+        h[v] = OqHost { S.txt, S.txt_len, demux ? nullptr : S.qual_off, S.qual_len, S.seq_off, nullptr, nullptr, S.n_lines, 0, 3, 7u * S.max_np,
+                        S.channels, S.channels_cap, S.count, &mono[(size_t)OQ_PAD * v], S.out, S.out_cap, S.out_off, &S.status };
+        h[v].np0 = S.max_np > 1 ? S.np0 : nullptr;
+    }
+    return oq_run (e, h, flags, demux);
+}
+
 } // namespace
 
+extern "C" int gzb_pacb_mux   (gzb_engine *e, gzb_pacb_vb *vbs, uint32_t n_vbs, uint32_t flags) { return pacb_public (e, vbs, n_vbs, flags, 0); }
+extern "C" int gzb_pacb_demux (gzb_engine *e, gzb_pacb_vb *vbs, uint32_t n_vbs, uint32_t flags) { return pacb_public (e, vbs, n_vbs, flags, 1); }
 extern "C" int gzb_tmpl_mux   (gzb_engine *e, gzb_tmpl_vb *vbs, uint32_t n_vbs, uint32_t flags) { return tmpl_public (e, vbs, n_vbs, flags, 0); }
 extern "C" int gzb_tmpl_demux (gzb_engine *e, gzb_tmpl_vb *vbs, uint32_t n_vbs, uint32_t flags) { return tmpl_public (e, vbs, n_vbs, flags, 1); }
 extern "C" int gzb_oq_mux     (gzb_engine *e, gzb_oq_vb *vbs, uint32_t n_vbs, uint32_t flags)   { return oq_public (e, vbs, n_vbs, flags, 0); }

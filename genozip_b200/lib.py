@@ -99,6 +99,12 @@ class TmplVb(C.Structure):          # gzb_tmpl_vb
                 ("count", C.c_uint32 * 95), ("pad", C.c_uint32), ("out", C.c_void_p), ("out_cap", C.c_uint64), ("out_off", C.c_void_p)]
 
 
+class PacbVb(C.Structure):          # gzb_pacb_vb
+    _fields_ = [("txt", C.c_void_p), ("txt_len", C.c_uint64), ("qual_off", C.c_void_p), ("qual_len", C.c_void_p), ("seq_off", C.c_void_p), ("np0", C.c_void_p),
+                ("n_lines", C.c_uint32), ("status", C.c_int32), ("max_np", C.c_uint32), ("reserved", C.c_uint32), ("channels", C.c_void_p), ("channels_cap", C.c_uint64),
+                ("count", C.c_uint32 * 84), ("out", C.c_void_p), ("out_cap", C.c_uint64), ("out_off", C.c_void_p)]
+
+
 class LocalItem(C.Structure):       # gzb_local_item
     _fields_ = [("data", C.c_void_p), ("n_elems", C.c_uint64), ("op", C.c_int32), ("status", C.c_int32)]
 
@@ -193,7 +199,7 @@ def load():
     for f in ("gzb_stage_upload", "gzb_stage_fetch"):
         getattr(L, f).restype = C.c_int; getattr(L, f).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     L.gzb_stage_wait.restype = C.c_int; L.gzb_stage_wait.argtypes = [C.c_void_p, C.c_int]
-    for f in ("gzb_normq_gather", "gzb_normq_reconstruct", "gzb_oq_mux", "gzb_oq_demux", "gzb_smux_mux", "gzb_smux_demux", "gzb_tmpl_mux", "gzb_tmpl_demux"):
+    for f in ("gzb_normq_gather", "gzb_normq_reconstruct", "gzb_oq_mux", "gzb_oq_demux", "gzb_smux_mux", "gzb_smux_demux", "gzb_tmpl_mux", "gzb_tmpl_demux", "gzb_pacb_mux", "gzb_pacb_demux"):
         getattr(L, f).restype = C.c_int; getattr(L, f).argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
     L.gzb_local_transform_batch.restype = C.c_int
     L.gzb_local_transform_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
@@ -453,6 +459,49 @@ class Engine:
         rc = self.L.gzb_smux_demux(self.h, arr, len(vbs), 0)
         if rc != 0:
             raise GzbError(f"gzb_smux_demux failed ({rc}): {self._err()}")
+        return [k[6][:k[7]].copy() for k in keep]
+
+    # ---- PACB (host buffers) ----
+    def pacb_mux(self, vbs):
+        """vbs: list of (txt, qual_off, qual_len, seq_off, np0 or None, max_np) -> list of (channels back to back, count[84])"""
+        arr = (PacbVb * max(1, len(vbs)))(); keep = []
+        for i, (txt, qoff, qlen, soff, np0, max_np) in enumerate(vbs):
+            txt = np.ascontiguousarray(txt, np.uint8); qoff = np.ascontiguousarray(qoff, np.uint64); qlen = np.ascontiguousarray(qlen, np.uint32); soff = np.ascontiguousarray(soff, np.uint64)
+            n0 = None if np0 is None else np.ascontiguousarray(np0, np.uint8); ch = np.zeros(int(qlen.sum()) + 16, np.uint8)
+            keep.append((txt, qoff, qlen, soff, n0, ch))
+            a = arr[i]
+            a.txt = txt.ctypes.data if txt.size else None; a.txt_len = txt.size; a.n_lines = qlen.size; a.max_np = max_np
+            a.qual_off = qoff.ctypes.data if qoff.size else None; a.qual_len = qlen.ctypes.data if qlen.size else None; a.seq_off = soff.ctypes.data if soff.size else None
+            a.np0 = None if n0 is None or not n0.size else n0.ctypes.data
+            a.channels = ch.ctypes.data; a.channels_cap = ch.size
+        rc = self.L.gzb_pacb_mux(self.h, arr, len(vbs), 0)
+        if rc != 0:
+            raise GzbError(f"gzb_pacb_mux failed ({rc}): {self._err()}")
+        out = []
+        for i, k in enumerate(keep):
+            cnt = np.array(arr[i].count[:], np.uint32)
+            out.append((k[5][:int(cnt.sum())].copy(), cnt))
+        return out
+
+    def pacb_demux(self, vbs):
+        """vbs: list of (txt, seq_off, lens, np0 or None, max_np, out_off, out_size, channels, count[84]) -> list of out arrays"""
+        arr = (PacbVb * max(1, len(vbs)))(); keep = []
+        for i, (txt, soff, lens, np0, max_np, ooff, out_size, ch, cnt) in enumerate(vbs):
+            txt = np.ascontiguousarray(txt, np.uint8); soff = np.ascontiguousarray(soff, np.uint64); lens = np.ascontiguousarray(lens, np.uint32); ooff = np.ascontiguousarray(ooff, np.uint64)
+            n0 = None if np0 is None else np.ascontiguousarray(np0, np.uint8)
+            ch = np.ascontiguousarray(ch, np.uint8); ch = ch if ch.size else np.zeros(1, np.uint8); out = np.zeros(out_size + 16, np.uint8)
+            keep.append((txt, soff, lens, ooff, n0, ch, out, out_size))
+            a = arr[i]
+            a.txt = txt.ctypes.data if txt.size else None; a.txt_len = txt.size; a.n_lines = lens.size; a.max_np = max_np
+            a.qual_len = lens.ctypes.data if lens.size else None; a.seq_off = soff.ctypes.data if soff.size else None; a.out_off = ooff.ctypes.data if ooff.size else None
+            a.np0 = None if n0 is None or not n0.size else n0.ctypes.data
+            a.channels = ch.ctypes.data; a.channels_cap = ch.size
+            for c in range(84):
+                a.count[c] = int(cnt[c])
+            a.out = out.ctypes.data; a.out_cap = out_size
+        rc = self.L.gzb_pacb_demux(self.h, arr, len(vbs), 0)
+        if rc != 0:
+            raise GzbError(f"gzb_pacb_demux failed ({rc}): {self._err()}")
         return [k[6][:k[7]].copy() for k in keep]
 
     # ---- TMPL (host buffers) ----

@@ -405,6 +405,33 @@ typedef struct gzb_tmpl_vb {
 int gzb_tmpl_mux   (gzb_engine *e, gzb_tmpl_vb *vbs, uint32_t n_vbs, uint32_t flags);
 int gzb_tmpl_demux (gzb_engine *e, gzb_tmpl_vb *vbs, uint32_t n_vbs, uint32_t flags);
 
+/* ---------------------------------------------------------------- PACB (src/codec_pacb.c): PacBio's quality codec — QUAL multiplexed by passes and surroundings
+ * mux:   codec_pacb_compress (:164-236): QUAL[i] goes to channel 7 * np0 + K, np0[line] = min (np:i, max_np) - 1 (0 for FASTQ and CLR data:
+ *        max_np = 1, np0 may be NULL) and K = QUAL_get_K_value (:19-27), one of 7 classes of SEQ around position i; 7 * max_np channels
+ *        (max_np <= 12).  A read without quality (qual_len 1, ' ') is one element of a one-base sequence (:135).
+ *            in  txt, qual_off, qual_len, seq_off, np0, max_np      out  channels (channel c at the sum of count[0..c)), count[84]
+ * demux: codec_pacb_reconstruct (:262-326) for every line of a VBlock at once (the read's own orientation, not the SAM-to-FASTQ translation
+ *        :296-303): qual_len[i] = the `len` of the i-th call.  As with SMUX, a VBlock whose channels hold a ' ' (a read without quality
+ *        consumes one byte whatever its length, :313-317) is refused with GZB_E_UNSUPPORTED.
+ *            in  txt + seq_off, qual_len, np0, max_np, channels + count, out_off      out  out
+ * GZB_E_CORRUPT: a channel out of data (:309).  Device pointers with GZB_DEVICE_PTRS (then channels_cap / out_cap bound the work). */
+typedef struct gzb_pacb_vb {
+    const void     *txt;        uint64_t txt_len;
+    const uint64_t *qual_off;   /* mux */
+    const uint32_t *qual_len;
+    const uint64_t *seq_off;
+    const uint8_t  *np0;        /* may be NULL when max_np is 1 */
+    uint32_t        n_lines;
+    int32_t         status;
+    uint32_t        max_np;     uint32_t reserved;
+    void           *channels;   uint64_t channels_cap;
+    uint32_t        count[84];
+    void           *out;        uint64_t out_cap;   /* demux */
+    const uint64_t *out_off;    /* demux */
+} gzb_pacb_vb;
+int gzb_pacb_mux   (gzb_engine *e, gzb_pacb_vb *vbs, uint32_t n_vbs, uint32_t flags);
+int gzb_pacb_demux (gzb_engine *e, gzb_pacb_vb *vbs, uint32_t n_vbs, uint32_t flags);
+
 /* ---------------------------------------------------------------- PBWT (src/codec_pbwt.c)
  * encode: codec_pbwt_compress (:244-287): haplotype matrix → RUNS (uint32) + FGRC ({allele:8,count:24}; the last
  *         two words are the 64-bit matrix length, :274-276).  Host-endian words.

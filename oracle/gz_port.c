@@ -830,3 +830,54 @@ int orc_tmpl_demux (const uint32_t *len, const uint64_t *out_off, uint32_t n_lin
         }
     return 0;
 }
+
+/* ================================================================ PACB (reference src/codec_pacb.c)
+ * mux   = codec_pacb_compress (:164-236): channel = 7 * np0 + QUAL_get_K_value (:19-27); channels back to back, count[7 * max_np].
+ * demux = codec_pacb_reconstruct (:262-326) line by line; a read without quality writes '*' at the start of its slot.  -1: a channel is out of data. */
+static unsigned pacb_K (const uint8_t *seq, uint32_t len, uint32_t i)
+{
+    const uint8_t b = seq[i]; const unsigned at = (b == 'A' || b == 'T');
+    if (i > 0 && seq[i - 1] == b) return 6;
+    if (i == len - 1 || seq[i + 1] != b) return 4 + at;
+    if (i == len - 2 || seq[i + 2] != b) return 2 + at;
+    return at;
+}
+int orc_pacb_mux (const uint8_t *txt, const uint64_t *qual_off, const uint32_t *qual_len, const uint64_t *seq_off, const uint8_t *np0, uint32_t max_np, uint32_t n_lines,
+                  uint8_t *channels, uint32_t *count)
+{
+    const uint32_t n_ch = 7 * max_np;
+    uint64_t next[84], total = 0;
+    memset (count, 0, 84 * sizeof (uint32_t));
+    for (int pass = 0; pass < 2; pass++) {
+        for (uint32_t li = 0; li < n_lines; li++) {
+            const uint8_t *q = txt + qual_off[li], *seq = txt + seq_off[li]; const uint32_t L = qual_len[li];   /* a read without quality: L = 1 (:135) */
+            const unsigned base = (np0 && max_np > 1) ? 7u * np0[li] : 0;
+            for (uint32_t i = 0; i < L; i++) {
+                const unsigned ch = base + pacb_K (seq, L, i);
+                if (ch >= n_ch) return -1;
+                if (pass) channels[next[ch]++] = q[i]; else count[ch]++;
+            }
+        }
+        if (!pass) for (uint32_t c = 0; c < n_ch; c++) { next[c] = total; total += count[c]; }
+    }
+    return 0;
+}
+int orc_pacb_demux (const uint8_t *txt, const uint64_t *seq_off, const uint32_t *len, const uint8_t *np0, uint32_t max_np, const uint64_t *out_off, uint32_t n_lines,
+                    const uint8_t *channels, const uint32_t *count, uint8_t *out)
+{
+    const uint32_t n_ch = 7 * max_np;
+    uint64_t next[84], after[84], total = 0;
+    for (uint32_t c = 0; c < n_ch; c++) { next[c] = total; total += count[c]; after[c] = total; }
+    for (uint32_t li = 0; li < n_lines; li++) {
+        const uint8_t *seq = txt + seq_off[li]; uint8_t *recon = out + out_off[li];
+        const unsigned base = (np0 && max_np > 1) ? 7u * np0[li] : 0;
+        for (uint32_t i = 0; i < len[li]; i++) {
+            const unsigned ch = base + pacb_K (seq, len[li], i);
+            if (ch >= n_ch || next[ch] >= after[ch]) return -1;
+            const uint8_t score = channels[next[ch]++];
+            if (score == ' ') { recon[0] = '*'; break; }                                   /* :313-317 */
+            recon[i] = score;
+        }
+    }
+    return 0;
+}

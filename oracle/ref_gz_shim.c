@@ -42,7 +42,8 @@
 Flags flag;
 SegConf segconf;
 static File the_z_file;
-FileP z_file = &the_z_file, txt_file = NULL;
+static File the_txt_file;
+FileP z_file = &the_z_file, txt_file = NULL;   // (txt_file points at the_txt_file only inside the PACB harness)
 FILE *info_stream;
 VBlockP evb = NULL;
 
@@ -871,6 +872,93 @@ int ref_tmpl_mux (const uint8_t *txt, uint64_t txt_len, const uint64_t *qual_off
     }
     count[94] = (ctx + 1)->local.len32;
     if (count[94]) memcpy (channels + at, (ctx + 1)->local.data, count[94]);
+    free (vb);
+    return 0;
+}
+
+// ================================================================ PACB (the reference's compiled codec_pacb.c)
+static const uint8_t *g_np0;
+int32_t sam_zip_get_np (VBlockP vb, LineIType line_i) { return g_np0 ? g_np0[line_i] + 1 : 1; }
+uint32_t sam_zip_get_seq_len (VBlockP vb, uint32_t line_i)   { return g_len[line_i]; }
+uint32_t fastq_zip_get_seq_len (VBlockP vb, uint32_t line_i) { return g_len[line_i]; }
+DictId dict_id_make (STRp(str), DictIdType dict_id_type) { ABORT0 ("shim: dict_id_make"); }
+bool container_peek_has_item (VBlockP vb, ContextP ctx, DictId item_dict_id, bool consume) { ABORT0 ("shim: container_peek_has_item"); }
+int32_t reconstruct_from_ctx_do (VBlockP vb, Did did_i, char sep, ReconType reconstruct, rom func) { ABORT0 ("shim: reconstruct_from_ctx_do"); }
+static int32_t g_cur_np;
+ValueType reconstruct_peek (VBlockP vb, ContextP ctx, pSTRp(txt)) { ValueType v = { .i = g_cur_np }; return v; }
+
+static void shim_pacb_setup (VBlockP vb, uint32_t max_np)
+{
+    memset (&the_txt_file, 0, sizeof the_txt_file); the_txt_file.data_type = DT_SAM; txt_file = &the_txt_file;
+    if (max_np > 1) bitset_set ((uint64_t *)segconf.has_bits, OPTION_np_i);              // get_max_np (:56-59): MAX_np = 12 with np:i in the file, else 1
+    ContextP zctx = &z_file->ca.contexts[SAM_QUAL];
+    memset (zctx, 0, sizeof (Context)); zctx->did_i = SAM_QUAL;
+    buf_alloc_do (NULL, &zctx->subdicts, (uint64_t)7 * max_np * sizeof (DictId) + 8, 1, "subdicts", __FUNCLINE);
+    for (uint32_t c = 0; c < 7 * max_np; c++) B(DictId, zctx->subdicts, 0)[c].num = 0x5041434200ull + c;   // any distinct ids: the channel contexts are found by them
+    zctx->subdicts.len = 7 * max_np;
+}
+
+// codec_pacb_compress on n_lines reads: the 7 * max_np channel contexts' locals back to back.  max_np must be 1 or 12 (the reference knows no other).
+int ref_pacb_mux (const uint8_t *txt, uint64_t txt_len, const uint64_t *qual_off, const uint32_t *qual_len, const uint64_t *seq_off, const uint8_t *np0, uint32_t max_np,
+                  uint32_t n_lines, uint8_t *channels, uint32_t *count)
+{
+    shim_init ();
+    if (setjmp (on_abort)) { txt_file = NULL; return -1; }
+    VBlockP vb = calloc (1, sizeof (VBlock));
+    vb->vblock_i = 1; vb->lines.len = n_lines; vb->data_type = DT_SAM;
+    g_txt = (uint8_t *)txt; g_off = qual_off; g_len = qual_len; g_seq_off = seq_off; g_seq_len = NULL; g_is_rev = NULL; g_np0 = np0;
+    shim_pacb_setup (vb, max_np);
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n_lines; i++) total += qual_len[i];
+    ContextP ctx = CTX (SAM_QUAL);
+    ctx->did_i = SAM_QUAL; strcpy (ctx->tag_name, "QUAL"); ctx->local.len = total;
+    SectionHeaderCtx header = {};
+    uint32_t ulen = 0, clen = 64; char comp[64] = {};
+    if (!codec_pacb_compress (vb, ctx, (SectionHeaderP)&header, NULL, &ulen, shim_get_line, comp, &clen, true, "QUAL")) { txt_file = NULL; return -3; }
+    uint64_t at = 0;
+    for (uint32_t c = 0; c < 7 * max_np; c++) {
+        ContextP sc = &vb->ca.contexts[SHIM_FIRST_DYN_DID + c];                // created in channel order (codec_pacb_init_ctxs :34-35)
+        count[c] = sc->local.len32;
+        if (count[c]) { memcpy (channels + at, sc->local.data, count[c]); at += count[c]; }
+    }
+    txt_file = NULL; free (vb);
+    return 0;
+}
+
+// codec_pacb_reconstruct line by line; every line's bytes at out_off[i] (a read without quality: the one character '*')
+int ref_pacb_demux (const uint8_t *txt, uint64_t txt_len, const uint64_t *seq_off, const uint32_t *len, const uint8_t *np0, uint32_t max_np, const uint64_t *out_off, uint32_t n_lines,
+                    const uint8_t *channels, const uint32_t *count, uint8_t *out, uint64_t out_size)
+{
+    shim_init_piz ();
+    if (setjmp (on_abort)) { shim_missing_ok = false; txt_file = NULL; return -1; }
+    shim_missing_ok = true;
+    flag.out_dt = DT_SAM;
+    VBlockP vb = calloc (1, sizeof (VBlock));
+    vb->vblock_i = 1; vb->lines.len = n_lines; vb->data_type = DT_SAM;
+    shim_pacb_setup (vb, max_np);
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n_lines; i++) total += len[i];
+    buf_alloc_do (vb, &vb->txt_data, total + 64, 1, "txt_data", __FUNCLINE);
+    ContextP ctx = CTX (SAM_QUAL);
+    ctx->did_i = SAM_QUAL; ctx->is_loaded = true;
+    CTX (OPTION_np_i)->is_loaded = true;
+    ContextP zctx = &z_file->ca.contexts[SAM_QUAL];
+    uint64_t at = 0;
+    for (uint32_t c = 0; c < 7 * max_np; c++) {                                // every channel context exists (ECTX must not return NULL, :286-289)
+        ContextP sc = ctx_get_unmapped_ctx (&vb->ca, DT_SAM, *B(DictId, zctx->subdicts, c), 0, 0);
+        buf_alloc_do (vb, &sc->local, count[c] + 8, 1, "local", __FUNCLINE);
+        memcpy (sc->local.data, channels + at, count[c]); sc->local.len = count[c]; at += count[c];
+    }
+    for (uint32_t i = 0; i < n_lines; i++) {
+        if (!len[i]) continue;
+        cur_seq = (rom)txt + seq_off[i]; cur_is_rev = false; g_cur_np = np0 ? np0[i] + 1 : 1;
+        CTX (OPTION_np_i)->last_value.i = g_cur_np; CTX (OPTION_np_i)->last_line_i = vb->line_i;   // np:i of this line was reconstructed before QUAL (codec_pacb_piz_get_np :243-245)
+        const uint64_t before = vb->txt_data.len;
+        codec_pacb_reconstruct (vb, CODEC_PACB, ctx, len[i], true);
+        if (out_off[i] + (vb->txt_data.len - before) > out_size) { shim_missing_ok = false; txt_file = NULL; return -2; }
+        memcpy (out + out_off[i], vb->txt_data.data + before, vb->txt_data.len - before);
+    }
+    shim_missing_ok = false; txt_file = NULL;
     free (vb);
     return 0;
 }

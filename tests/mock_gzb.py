@@ -330,6 +330,38 @@ class MockLib:
             a.status = 0
         return 0
 
+    def gzb_pacb_mux(self, h, vbs, n, flags):
+        for i in range(n):
+            a = vbs[i]
+            nl = a.n_lines
+            np0 = _view(a.np0, nl).copy() if a.np0 and nl else None
+            ch, cnt = orc.pacb_mux(_view(a.txt, a.txt_len).copy(), _view(a.qual_off, nl, np.uint64).copy(), _view(a.qual_len, nl, np.uint32).copy(),
+                                   _view(a.seq_off, nl, np.uint64).copy(), np0, a.max_np)
+            if ch.size:
+                _view(a.channels, ch.size)[:] = ch
+            for c in range(84):
+                a.count[c] = int(cnt[c])
+            a.status = 0
+        return 0
+
+    def gzb_pacb_demux(self, h, vbs, n, flags):
+        for i in range(n):
+            a = vbs[i]
+            nl = a.n_lines
+            np0 = _view(a.np0, nl).copy() if a.np0 and nl else None
+            cnt = np.array(a.count[:], np.uint32)
+            ch = _view(a.channels, int(cnt.sum())).copy()
+            if (ch == 32).any():
+                a.status = -5; self.err = "SMUX / PACB: a read without quality"; return -5
+            out = orc.pacb_demux(_view(a.txt, a.txt_len).copy(), _view(a.seq_off, nl, np.uint64).copy(), _view(a.qual_len, nl, np.uint32).copy(), np0, a.max_np,
+                                 _view(a.out_off, nl, np.uint64).copy(), a.out_cap, ch, cnt)
+            if out is None:
+                a.status = -4; self.err = "OQ / SMUX: a channel is out of data"; return -4
+            if out.size:
+                _view(a.out, out.size)[:] = out
+            a.status = 0
+        return 0
+
     def gzb_tmpl_mux(self, h, vbs, n, flags):
         for i in range(n):
             a = vbs[i]

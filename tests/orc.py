@@ -700,3 +700,41 @@ def ref_tmpl_mux(txt, qoff, qlen, tmpl_len):
     rc = L.ref_tmpl_mux(_ptr(txt), txt.size, _ptr(qoff), _ptr(qlen), qlen.size, tmpl_len, _ptr(tmpl), _ptr(chan), _ptr(count))
     assert rc >= 0, rc
     return None if rc == 1 else (tmpl[:tmpl_len].copy(), chan[:int(count.sum())].copy(), count)
+
+
+# ---------------------------------------------------------------- PACB (src/codec_pacb.c)
+def pacb_mux(txt, qoff, qlen, soff, np0, max_np, lib="port"):
+    """codec_pacb_compress -> (the 7 * max_np channels back to back, count[84])"""
+    txt = np.ascontiguousarray(txt, np.uint8); qoff = np.ascontiguousarray(qoff, np.uint64); qlen = np.ascontiguousarray(qlen, np.uint32); soff = np.ascontiguousarray(soff, np.uint64)
+    n0 = None if np0 is None else np.ascontiguousarray(np0, np.uint8)
+    chan = np.zeros(int(qlen.sum()) + 8, np.uint8); count = np.zeros(84, np.uint32); n0p = None if n0 is None else _ptr(n0)
+    if lib == "port":
+        L = port()
+        L.orc_pacb_mux.restype = C.c_int
+        L.orc_pacb_mux.argtypes = [C.c_void_p] * 5 + [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        rc = L.orc_pacb_mux(_ptr(txt), _ptr(qoff), _ptr(qlen), _ptr(soff), n0p, max_np, qlen.size, _ptr(chan), _ptr(count))
+    else:
+        L = gz_ref()
+        L.ref_pacb_mux.restype = C.c_int
+        L.ref_pacb_mux.argtypes = [C.c_void_p, C.c_uint64] + [C.c_void_p] * 4 + [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        rc = L.ref_pacb_mux(_ptr(txt), txt.size, _ptr(qoff), _ptr(qlen), _ptr(soff), n0p, max_np, qlen.size, _ptr(chan), _ptr(count))
+    assert rc == 0, rc
+    return chan[:int(count.sum())].copy(), count
+
+
+def pacb_demux(txt, soff, lens, np0, max_np, out_off, out_size, channels, count, lib="port"):
+    txt = np.ascontiguousarray(txt, np.uint8); soff = np.ascontiguousarray(soff, np.uint64); lens = np.ascontiguousarray(lens, np.uint32); ooff = np.ascontiguousarray(out_off, np.uint64)
+    n0 = None if np0 is None else np.ascontiguousarray(np0, np.uint8); n0p = None if n0 is None else _ptr(n0)
+    ch = np.ascontiguousarray(channels, np.uint8); ch = ch if ch.size else np.zeros(1, np.uint8); count = np.ascontiguousarray(count, np.uint32)
+    out = np.zeros(out_size + 8, np.uint8)
+    if lib == "port":
+        L = port()
+        L.orc_pacb_demux.restype = C.c_int
+        L.orc_pacb_demux.argtypes = [C.c_void_p] * 4 + [C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        rc = L.orc_pacb_demux(_ptr(txt), _ptr(soff), _ptr(lens), n0p, max_np, _ptr(ooff), lens.size, _ptr(ch), _ptr(count), _ptr(out))
+    else:
+        L = gz_ref()
+        L.ref_pacb_demux.restype = C.c_int
+        L.ref_pacb_demux.argtypes = [C.c_void_p, C.c_uint64] + [C.c_void_p] * 3 + [C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        rc = L.ref_pacb_demux(_ptr(txt), txt.size, _ptr(soff), _ptr(lens), n0p, max_np, _ptr(ooff), lens.size, _ptr(ch), _ptr(count), _ptr(out), out_size)
+    return None if rc != 0 else out[:out_size].copy()
