@@ -58,7 +58,7 @@ def rand_quals(r, off, lens):
 
 
 def fuzz_domq(r, eng):
-    off, lens = rand_lines(r, int(r.choice([3, 40, 400])), int(r.choice([2, 60, 300, 2600])))
+    off, lens = rand_lines(r, int(r.choice([3, 40, 400])), int(r.choice([2, 60, 300, 2600, 6000])))   # (above 4096: the histogram pass gives the line to a whole warp)
     q = rand_quals(r, off, lens)
     g = eng.domq_encode([(q, off, lens)])[0]
     ref = orc.ref_domq_encode(q, off, lens)
