@@ -36,10 +36,13 @@ def test_damaged_streams():
 
 @pytest.mark.skipif(not orc.have_gz_ref(), reason="oracle/_ref/libgz_ref.so not built")
 def test_genozip_codec_kernels():
-    """ACGT / DOMQ / PBWT / LONGR kernels against the reference's compiled codec objects on random VBlocks (tools/fuzz_simt_gz.py)"""
+    """ACGT / DOMQ / PBWT / LONGR kernels against the reference's compiled codec objects on random VBlocks (tools/fuzz_simt_gz.py), then the
+    round-2 kernels: OQ, SMUX, PACB, HOMP / T0, b250"""
     import fuzz_simt_gz
-    count = fuzz_simt_gz.run(600, 103, max_cases=160)
+    count = fuzz_simt_gz.run(600, 103, which=["domq", "acgt", "pbwt", "longr"], max_cases=160)
     assert all(v >= 40 for v in count.values()), count
+    count = fuzz_simt_gz.run(600, 104, which=["oq", "smux", "pacb", "homp", "b250"], max_cases=100)
+    assert all(v >= 20 for v in count.values()), count
 
 
 def _rejects(eng, codec, comp, n):

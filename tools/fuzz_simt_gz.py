@@ -136,7 +136,117 @@ def fuzz_longr(r, eng):
     return n
 
 
-FUZZERS = {"domq": fuzz_domq, "acgt": fuzz_acgt, "pbwt": fuzz_pbwt, "longr": fuzz_longr}
+# ---- round 2: the steps either side of the codecs and the other quality codecs, against the reference's compiled b250.c, codec_oq.c,
+# codec_smux.c, codec_pacb.c, codec_homp.c, codec_t0.c
+def rand_reads(r, max_lines=200, max_len=400):
+    """a text holding, per read, SEQ (with homopolymer runs), QUAL and a second quality-like string, at random places"""
+    n_lines = int(r.integers(1, max_lines))
+    parts, pos, so, qo, oo, lens = [np.frombuffer(b"@", np.uint8)], 1, [], [], [], []
+    for _ in range(n_lines):
+        L = int(r.integers(1, max_len))
+        seq = np.repeat(r.choice(np.frombuffer(b"ACGTN", np.uint8), L, p=[.24, .24, .24, .24, .04]), r.choice([1, 1, 1, 2, 3, 7], L))[:L].astype(np.uint8)
+        k = int(r.choice([2, 4, 40]))
+        qual = (33 + r.integers(0, k, L) * (r.random(L) < float(r.choice([0.1, 0.5, 1.0])))).astype(np.uint8)
+        if r.random() < 0.5:                                                  # Ultima-like: mirror the qualities inside every run
+            i = 0
+            while i < L:
+                h = 1
+                while i + h < L and seq[i + h] == seq[i]: h += 1
+                half = qual[i:i + (h + 1) // 2].copy(); qual[i:i + h] = np.concatenate([half, half[:h // 2][::-1]]); i += h
+        oq = (33 + np.clip(qual.astype(np.int32) - 33 + r.integers(-1, 2, L), 0, 93)).astype(np.uint8)
+        for arr, lst in ((seq, so), (qual, qo), (oq, oo)):
+            lst.append(pos); parts.append(arr); pos += L
+            fill = r.integers(65, 91, int(r.integers(0, 5))).astype(np.uint8); parts.append(fill); pos += fill.size
+        lens.append(L)
+    return np.concatenate(parts), np.array(so, np.uint64), np.array(qo, np.uint64), np.array(oo, np.uint64), np.array(lens, np.uint32)
+
+
+def _off(lens):
+    return np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint64)
+
+
+def fuzz_oq(r, eng):
+    txt, so, qo, oo, lens = rand_reads(r)
+    g = eng.oq_mux([(txt, qo, lens, oo, None)])[0]
+    ref = orc.oq_mux(txt, qo, lens, oo, None, "ref")
+    assert all(np.array_equal(a, b) for a, b in zip(g, ref)), "OQ: kernels != reference codec_oq.c"
+    cnt = np.where(g[2] != 0, 0, g[1]).astype(np.uint32); at = np.concatenate([[0], np.cumsum(g[1])]).astype(np.int64)
+    keep = [g[0][at[q]:at[q + 1]] for q in range(94) if cnt[q]]
+    ch = np.concatenate(keep) if keep else np.zeros(0, np.uint8)
+    want = np.concatenate([txt[int(o):int(o) + int(l)] for o, l in zip(oo, lens)])
+    assert np.array_equal(eng.oq_demux([(txt, qo, lens, _off(lens), int(lens.sum()), 33, ch, cnt, g[2])])[0], want), "OQ: kernels' demux"
+    assert np.array_equal(orc.oq_demux(txt, qo, lens, _off(lens), int(lens.sum()), 33, ch, cnt, g[2], "ref"), want), "OQ: reference's reconstruct"
+    return int(lens.sum())
+
+
+def fuzz_smux(r, eng):
+    txt, so, qo, oo, lens = rand_reads(r)
+    rev = (r.random(lens.size) < 0.4).astype(np.uint8) if r.random() < 0.6 else None
+    g = eng.smux_mux([(txt, qo, lens, so, lens, rev)])[0]
+    ref = orc.smux_mux(txt, qo, lens, so, lens, rev, "ref")
+    assert np.array_equal(g[0], ref[0]) and np.array_equal(g[1], ref[1]) and g[2] == ref[2], "SMUX: kernels != reference codec_smux.c"
+    cnt = g[1].copy(); ch = g[0]
+    if g[2]:
+        ch = ch[:int(cnt[:4].sum())]; cnt[4] = 0
+    want = np.concatenate([txt[int(o):int(o) + int(l)] for o, l in zip(qo, lens)])
+    assert np.array_equal(eng.smux_demux([(txt, so, lens, rev, _off(lens), int(lens.sum()), ch, cnt, g[2])])[0], want), "SMUX: kernels' demux"
+    assert np.array_equal(orc.smux_demux(txt, so, lens, rev, _off(lens), int(lens.sum()), ch, cnt, g[2], "ref"), want), "SMUX: reference's reconstruct"
+    return int(lens.sum())
+
+
+def fuzz_pacb(r, eng):
+    txt, so, qo, oo, lens = rand_reads(r)
+    max_np = int(r.choice([1, 12]))
+    np0 = r.integers(0, max_np, lens.size).astype(np.uint8) if max_np > 1 else None
+    g = eng.pacb_mux([(txt, qo, lens, so, np0, max_np)])[0]
+    ref = orc.pacb_mux(txt, qo, lens, so, np0, max_np, "ref")
+    assert np.array_equal(g[0], ref[0]) and np.array_equal(g[1], ref[1]), "PACB: kernels != reference codec_pacb.c"
+    want = np.concatenate([txt[int(o):int(o) + int(l)] for o, l in zip(qo, lens)])
+    assert np.array_equal(eng.pacb_demux([(txt, so, lens, np0, max_np, _off(lens), int(lens.sum()), g[0], g[1])])[0], want), "PACB: kernels' demux"
+    assert np.array_equal(orc.pacb_demux(txt, so, lens, np0, max_np, _off(lens), int(lens.sum()), g[0], g[1], "ref"), want), "PACB: reference's reconstruct"
+    return int(lens.sum())
+
+
+def fuzz_homp(r, eng):
+    txt, so, qo, oo, lens = rand_reads(r)
+    mode = int(r.integers(0, 2))
+    g = eng.hp_condense(mode, [(txt, qo, lens, so)])[0]
+    ref = orc.hp_condense(mode, txt, qo, lens, so, "ref")
+    assert np.array_equal(g[0], ref[0]) and np.array_equal(g[1], ref[1]), f"HOMP/T0 mode {mode}: kernels != reference"
+    want = np.concatenate([txt[int(o):int(o) + int(l)] for o, l in zip(qo, lens)])
+    assert np.array_equal(eng.hp_expand(mode, [(g[0], txt, so, lens)])[0][0], want), "HOMP/T0: kernels' expand"
+    assert np.array_equal(orc.hp_expand(mode, g[0], txt, so, lens, "ref")[0], want), "HOMP/T0: reference's reconstruct"
+    return int(lens.sum())
+
+
+def fuzz_b250(r, eng):
+    n_words = int(r.choice([0, 1, 2, 30, 31, 33, 500, 5000])); ol = int(r.choice([0, 5, 200, 5000, 3000000])); n_new = int(r.choice([0, 1, 40, 2000]))
+    ni2wi = (ol + r.permutation(n_new)).astype(np.int32)
+    out, wi = [], 0
+    for _ in range(n_words):
+        x = r.random()
+        if x < 0.3 and ol:   wi = (wi + 1) % ol; v, f4 = wi, False
+        elif x < 0.4:        v, f4 = (-3 if r.random() < 0.5 else -4), False
+        elif x < 0.6 and n_new: v, f4 = ol + int(r.integers(0, n_new)), True
+        elif ol:             wi = int(r.integers(0, ol)); v, f4 = wi, False
+        else:                v, f4 = -3, False
+        if f4 or v > 2113660: enc, n = (7 << 29) | v, 4
+        elif v == -3:  enc, n = 0xBFFE, 2
+        elif v == -4:  enc, n = 0xBFFF, 2
+        elif v <= 126: enc, n = v, 1
+        elif v <= 16508: enc, n = (2 << 14) | (v - 127), 2
+        else:          enc, n = (6 << 21) | (v - 16509), 3
+        out += [(enc >> (8 * k)) & 0xff for k in range(n)]
+    b = np.array(out, np.uint8)
+    up = ol + n_new > 1024
+    g = eng.b250_generate([(b, ni2wi, ol, up)])[0]
+    ref = orc.b250_generate(b, ni2wi, ol, up, "ref")
+    assert g[1] == n_words and np.array_equal(g[0], ref[0]), "b250: kernels != reference b250.c"
+    return b.size
+
+
+FUZZERS = {"domq": fuzz_domq, "acgt": fuzz_acgt, "pbwt": fuzz_pbwt, "longr": fuzz_longr,
+           "oq": fuzz_oq, "smux": fuzz_smux, "pacb": fuzz_pacb, "homp": fuzz_homp, "b250": fuzz_b250}
 
 
 def run(seconds, seed, which=None, verbose=False, max_cases=None):
