@@ -360,6 +360,105 @@ extern "C" void gzb_codec_normq_reconstruct (VBlockP vb, Codec codec, ContextP c
     if (++R->next + 1 == R->off.size ()) { delete R; *slot = nullptr; }
 }
 
+// ================================================================ HOMP and T0 (src/codec_homp.c, src/codec_t0.c)
+namespace {
+struct HompState { Codec sub = CODEC_NONE_; std::vector<char> data; };
+
+// first entry: every line condensed in place and its length updated (:132-190, t0 :69-109), then the sub-codec on the condensed strings — the
+// reference hands it the line callback (data = 0): the same bytes, here as one buffer.  A second entry (after a soft fail) goes straight to the sub-codec.
+bool homp_like_compress (int mode, VBlockP vb, ContextP ctx, SectionHeaderP header, const char *uncompressed, uint32_t *uncompressed_len, LocalGetLineCB get_line_cb,
+                         char *compressed, uint32_t *compressed_len, FailType soft_fail, const char *name)
+{
+    NEED (codec_state, name); NEED (seq_line, name); NEED (local_set_len, name); NEED (assign_sub_codec, name); NEED (sub_est_size, name); NEED (header_set, name); NEED (update_line_len, name);
+    if (uncompressed || !get_line_cb) plugin_abort (mode ? "t0" : "homp", name, "only callback option is supported");
+    void **slot = g_host2.codec_state (vb, ctx);
+    HompState *S = (HompState *)*slot;
+    if (soft_fail) {
+        Timer tm { vb, mode ? 7 : 6 };
+        Lines Q = gather_lines (vb, ctx, get_line_cb, name);
+        const uint32_t n_lines = (uint32_t)Q.len.size ();
+        std::vector<uint64_t> seq_off (n_lines), str_off (n_lines); std::vector<uint32_t> new_len (n_lines + 1, 0);
+        std::vector<char> txt; txt.reserve (2 * Q.total + 16);
+        const uint32_t skip_below = mode ? 1 : 2;                           // homp leaves a quality of length <= 1 alone (:137), t0 an empty string (:75): no SEQ is asked for
+        for (uint32_t i = 0; i < n_lines; i++) {
+            char *sq = nullptr; uint32_t sl = 0; bool r = false;
+            if (Q.len[i] >= skip_below) {
+                g_host2.seq_line (vb, ctx, i, &sq, &sl, &r);
+                if (sl != Q.len[i]) plugin_abort (mode ? "t0" : "homp", name, "expecting the string's length == seq_len");
+            }
+            seq_off[i] = txt.size (); txt.insert (txt.end (), sq, sq + sl);
+            str_off[i] = txt.size (); txt.insert (txt.end (), Q.ptr[i], Q.ptr[i] + Q.len[i]);
+        }
+        delete S; S = new HompState (); *slot = S;
+        S->data.resize (Q.total + 16);
+        gzb_homp_vb v; memset (&v, 0, sizeof v);
+        v.txt = txt.data (); v.txt_len = txt.size (); v.str_off = str_off.data (); v.str_len = Q.len.data (); v.seq_off = seq_off.data (); v.n_lines = n_lines;
+        v.local = S->data.data (); v.local_cap = S->data.size (); v.new_len = new_len.data ();
+        {
+            EngineLease E (vb, name);
+            if (gzb_homp_condense (E.e, &v, 1, mode, 0) != GZB_OK) plugin_abort ("gzb_homp_condense", name, gzb_last_error (E.e));
+        }
+        uint64_t at = 0;
+        for (uint32_t i = 0; i < n_lines; i++) {                            // in place, like the reference (:143,179-186)
+            memcpy (Q.ptr[i], S->data.data () + at, new_len[i]);
+            if (new_len[i] != Q.len[i]) g_host2.update_line_len (vb, ctx, i, new_len[i]);
+            at += new_len[i];
+        }
+        S->data.resize (v.local_len);
+        g_host2.local_set_len (ctx, 0, v.local_len);                        // ctx->local.len32 -= … (:184)
+        if (!mode && g_host2.add_lines) g_host2.add_lines (4, n_lines);     // z_file->homp_lines (:128-129)
+        S->sub = g_host2.assign_sub_codec (vb, ctx, 0);                     // :193-195
+        g_host2.header_set (header, GZB_HDR_SUB_CODEC, S->sub);
+    }
+    else if (!S) plugin_abort (mode ? "t0" : "homp", name, "second entry without a first one");
+    *uncompressed_len = (uint32_t)S->data.size ();                          // :199
+    if (*compressed_len < g_host2.sub_est_size (S->sub, S->data.size ())) { // :202-207
+        if (soft_fail) return false;
+        plugin_abort (mode ? "t0" : "homp", name, "compressed buffer too small and soft_fail is off");
+    }
+    const bool ok = sub_compress (S->sub, vb, ctx, header, S->data.data (), uncompressed_len, compressed, compressed_len, HARD_FAIL, name);
+    delete S; *slot = nullptr;
+    return ok;
+}
+
+void homp_like_reconstruct (int mode, VBlockP vb, ContextP ctx, uint32_t len, bool reconstruct)
+{
+    const char *name = mode ? "t0:Z" : "QUAL";
+    NEED (codec_state, name); NEED (recon_line_lens, name); NEED (recon_seq_table, name); NEED (local_data, name); NEED (recon_at, name); NEED (recon_advance, name);
+    Timer tm { vb, mode ? 7 : 6 };
+    void **slot = g_host2.codec_state (vb, ctx);
+    ReconStage *R = (ReconStage *)*slot;
+    if (!R) {                                                                // first line of the VBlock: all of them at once
+        R = new ReconStage ();
+        uint32_t n_lines = 0;
+        const uint32_t *lens = g_host2.recon_line_lens (vb, ctx, &n_lines);
+        const char *txt = nullptr; uint64_t txt_len = 0; const uint64_t *seq_off = nullptr; const uint8_t *is_rev = nullptr;
+        if (!g_host2.recon_seq_table (vb, ctx, &txt, &txt_len, &seq_off, &is_rev) || !seq_off) plugin_abort ("homp reconstruct", name, "the reads' SEQ is needed up front");
+        R->off.resize ((size_t)n_lines + 1); R->off[0] = 0;
+        for (uint32_t i = 0; i < n_lines; i++) R->off[i + 1] = R->off[i] + lens[i];
+        R->out.resize (R->off[n_lines] + 16); R->missing.assign ((size_t)n_lines + 1, 0);
+        gzb_homp_vb v; memset (&v, 0, sizeof v);
+        uint64_t l = 0;
+        v.local = g_host2.local_data (ctx, 0, &l); v.local_len = l;
+        v.txt = txt; v.txt_len = txt_len; v.seq_off = seq_off; v.str_len = lens; v.n_lines = n_lines;
+        v.out = R->out.data (); v.out_cap = R->off[n_lines] + 16; v.missing = R->missing.data ();
+        EngineLease E (vb, name);
+        if (gzb_homp_expand (E.e, &v, 1, mode, 0) != GZB_OK) plugin_abort ("gzb_homp_expand", name, gzb_last_error (E.e));
+        *slot = R;
+    }
+    while (R->next + 1 < R->off.size () && R->off[R->next + 1] == R->off[R->next] && len) R->next++;
+    if (R->next + 1 >= R->off.size () || R->off[R->next + 1] - R->off[R->next] != len) plugin_abort ("homp reconstruct", name, "len differs from the line table");
+    if (R->missing[R->next]) { NEED (missing_quality, name); g_host2.missing_quality (vb, reconstruct); }       // homp :241-244
+    else if (reconstruct) { memcpy (g_host2.recon_at (vb), R->out.data () + R->off[R->next], len); g_host2.recon_advance (vb, (int32_t)len); }
+    if (++R->next + 1 == R->off.size ()) { delete R; *slot = nullptr; }
+}
+}
+
+extern "C" GZB_COMPRESS (gzb_codec_homp_compress) { return homp_like_compress (GZB_HP_HOMP, vb, ctx, header, uncompressed, uncompressed_len, get_line_cb, compressed, compressed_len, soft_fail, name); }
+extern "C" GZB_COMPRESS (gzb_codec_t0_compress)   { return homp_like_compress (GZB_HP_T0,   vb, ctx, header, uncompressed, uncompressed_len, get_line_cb, compressed, compressed_len, soft_fail, name); }
+extern "C" void gzb_codec_homp_reconstruct (VBlockP vb, Codec codec, ContextP ctx, uint32_t len, bool reconstruct) { (void)codec; homp_like_reconstruct (GZB_HP_HOMP, vb, ctx, len, reconstruct); }
+extern "C" void gzb_codec_t0_reconstruct   (VBlockP vb, Codec codec, ContextP ctx, uint32_t len, bool reconstruct) { (void)codec; homp_like_reconstruct (GZB_HP_T0,   vb, ctx, len, reconstruct); }
+
 // ================================================================ PBWT
 extern "C" GZB_COMPRESS (gzb_codec_pbwt_compress)
 {

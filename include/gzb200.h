@@ -562,8 +562,8 @@ typedef struct {
                                                                                                (ZCTX(values)->value_to_bin in ZIP, from SEC_COUNTS in PIZ, src/codec_longr.c:316-330).  DOMQ reconstruct: the
                                                                                                de-normalisation table from DOMQRUNS' dictionary: byte 0 = number of doms, then [num_doms][num_norm_qs] */
     void     (*pbwt_dims)       (VBlockP vb, ContextP ht_ctx, uint32_t *n_lines, uint32_t *ht_per_line, int set);   /* ht_ctx->HT_n_lines, ->ht_per_line (get; set != 0: store ht_per_line) */
-    void     (*add_lines)       (int which, uint64_t n);                                    /* z_file->domq_lines / longr_lines (src/codec_domq.c:489-492, src/codec_longr.c:181): 0 DOMQ dom, 1 DOMQ diverse, 2 LONGR, 3 NORMQ (z_file->normq_lines, src/codec_normq.c:41) */
-    void     (*account_time)    (VBlockP vb, int which, uint64_t nanosec);                  /* COPY_TIMER (compressor_domq …), src/profiler.h:18-24: 0 domq 1 acgt 2 xcgt 3 pbwt 4 longr 5 normq */
+    void     (*add_lines)       (int which, uint64_t n);                                    /* z_file->domq_lines / longr_lines (src/codec_domq.c:489-492, src/codec_longr.c:181): 0 DOMQ dom, 1 DOMQ diverse, 2 LONGR, 3 NORMQ (z_file->normq_lines, src/codec_normq.c:41), 4 HOMP (z_file->homp_lines, src/codec_homp.c:128-129) */
+    void     (*account_time)    (VBlockP vb, int which, uint64_t nanosec);                  /* COPY_TIMER (compressor_domq …), src/profiler.h:18-24: 0 domq 1 acgt 2 xcgt 3 pbwt 4 longr 5 normq 6 homp 7 t0 */
     /* ---- PIZ ---- */
     void     (*sub_uncompress)  (Codec c, VBlockP vb, ContextP ctx, uint8_t param, const char *compressed, uint32_t compressed_len,
                                  BufferP uncompressed_buf, uint64_t uncompressed_len, const char *name);               /* codec_args[c].uncompress */
@@ -576,6 +576,8 @@ typedef struct {
     int64_t  (*pbwt_big_allele) (VBlockP vb);                                               /* reconstruct_from_local_int (vb, CTX(FORMAT_GT_HT_BIG), 0, RECON_OFF) */
     bool     (*drop_curr_line)  (VBlockP vb);
     void     (*missing_quality) (VBlockP vb, bool reconstruct);                             /* sam_reconstruct_missing_quality */
+    /* ---- added for HOMP / T0 (may be NULL when those entry points are not used) ---- */
+    void     (*update_line_len) (VBlockP vb, ContextP ctx, uint32_t vb_line_i, uint32_t new_len);   /* sam_update_qual_len / fastq_update_qual_len / sam_ultima_update_t0_len (src/codec_homp.c:183, src/codec_t0.c:103) */
 } gzb_plugin_host2;
 void gzb_plugin_register2 (const gzb_plugin_host2 *host);
 void gzb_plugin_shutdown (void);                                   /* destroys the pooled engines (process exit / plug-in unregistered) */
@@ -587,6 +589,8 @@ GZB_COMPRESS (gzb_codec_acgt_compress);                            /* src/codec_
 GZB_COMPRESS (gzb_codec_pbwt_compress);                            /* src/codec_pbwt.c:244-287 */
 GZB_COMPRESS (gzb_codec_longr_compress);                           /* src/codec_longr.c:161-264 */
 GZB_COMPRESS (gzb_codec_normq_compress);                           /* src/codec_normq.c:31-82 (table row src/codec.h:102) */
+GZB_COMPRESS (gzb_codec_homp_compress);                            /* src/codec_homp.c:121-205: the lines condensed in place, their lengths updated, then the sub-codec */
+GZB_COMPRESS (gzb_codec_t0_compress);                              /* src/codec_t0.c:58-124 */
 uint32_t gzb_codec_complex_est_size (Codec codec, uint64_t uncompressed_len);    /* src/codec.c codec_complex_est_size */
 uint32_t gzb_codec_longr_est_size   (Codec codec, uint64_t uncompressed_len);    /* src/codec_longr.c:53-56 */
 /* PIZ */
@@ -596,6 +600,8 @@ GZB_UNCOMPRESS (gzb_codec_pbwt_uncompress);                        /* src/codec_
 CodecReconstructFn gzb_codec_domq_reconstruct;                     /* src/codec_domq.c:774-809 */
 CodecReconstructFn gzb_codec_pbwt_reconstruct;                     /* src/codec_pbwt.c:406-449 */
 CodecReconstructFn gzb_codec_longr_reconstruct;                    /* src/codec_longr.c:342-373 */
+CodecReconstructFn gzb_codec_homp_reconstruct;                     /* src/codec_homp.c:213-276; recon_seq_table supplies every line's SEQ (deep / SAM-to-FASTQ variants :222-234 not covered) */
+CodecReconstructFn gzb_codec_t0_reconstruct;                       /* src/codec_t0.c:137-179 */
 CodecReconstructFn gzb_codec_normq_reconstruct;                    /* src/codec_normq.c:85-106; recon_seq_table supplies every line's strand (last_flags.rev_comp) */
 
 /* ---------------------------------------------------------------- combining submission

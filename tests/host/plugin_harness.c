@@ -25,7 +25,7 @@ struct VBlock  {
     char **qual, **seq; uint32_t *qual_len, *seq_len; uint8_t *is_rev;
     const uint32_t *recon_lens; const char *seq_txt; uint64_t seq_txt_len; const uint64_t *seq_off;
     int64_t big_allele;
-    uint64_t lines_counter[4], time_ns[6];
+    uint64_t lines_counter[6], time_ns[8];
     int n_missing;
 };
 
@@ -114,6 +114,7 @@ static char *a_recon_at (VBlockP vb) { return vb->txt_out.data + vb->txt_out.len
 static void a_recon_advance (VBlockP vb, int32_t n) { vb->txt_out.len += n; }
 static int64_t a_big_allele (VBlockP vb) { return vb->big_allele; }
 static bool a_drop (VBlockP vb) { (void)vb; return false; }
+static void a_update_line_len (VBlockP vb, ContextP c, uint32_t i, uint32_t n) { (void)c; vb->qual_len[i] = n; }   /* sam_update_qual_len / sam_ultima_update_t0_len */
 static void a_missing_quality (VBlockP vb, bool reconstruct) { if (reconstruct) { *a_recon_at (vb) = '*'; vb->txt_out.len++; } vb->n_missing++; }   /* sam_reconstruct_missing_quality */
 
 static void harness_init (void)
@@ -122,7 +123,7 @@ static void harness_init (void)
     static const gzb_plugin_host2 h2 = {
         a_local_alloc, a_local_data, a_local_set_len, a_local_free, a_local_prm8, a_scratch_alloc, a_scratch_free, a_acgt_no_x, a_header_set,
         a_assign, a_sub_compress, a_sub_est, a_seg_denorm, a_seq_line, a_codec_table, a_pbwt_dims, a_add_lines_vb, a_account,
-        a_sub_uncompress, a_packed_buffer, a_state, a_recon_lens, a_recon_seq_table, a_recon_at, a_recon_advance, a_big_allele, a_drop, a_missing_quality };
+        a_sub_uncompress, a_packed_buffer, a_state, a_recon_lens, a_recon_seq_table, a_recon_at, a_recon_advance, a_big_allele, a_drop, a_missing_quality, a_update_line_len };
     codec_table_init ();
     gzb_plugin_register (&h1, 0);
     gzb_plugin_register2 (&h2);
@@ -258,7 +259,7 @@ int harness_domq (const uint8_t *txt, const uint64_t *off, const uint32_t *lens,
     memcpy (comp, z, *comp_len);
 #define OUT(k, p, l) *l = (uint32_t)q[k].local.len; if (*l) memcpy (p, q[k].local.data, *l);
     OUT (0, qual, qual_len) OUT (1, runs, runs_len) OUT (2, mplx, mplx_len) OUT (3, divr, divr_len)
-    memcpy (counters, vb->lines_counter, sizeof vb->lines_counter);
+    memcpy (counters, vb->lines_counter, 4 * sizeof (uint64_t));
     /* PIZ: the sub-codec has already put QUAL.local back (here: it never left); the other three come from their own sections */
     vb->recon_lens = lens;
     buf_alloc_ (&vb->txt_out, total + 64);
@@ -299,6 +300,45 @@ int harness_normq (const uint8_t *txt, const uint64_t *off, const uint32_t *zlen
     *back_len = vb->txt_out.len; memcpy (back, vb->txt_out.data, vb->txt_out.len);
     *n_missing = vb->n_missing;
     free (z); g_vb = NULL; vb->qual_len = NULL; vb->is_rev = NULL; vb_free (vb);
+    return 0;
+}
+
+/* HOMP (mode 0) / T0 (mode 1): the lines condensed in place with their lengths updated, the sub-codec on the condensed strings, then one reconstruct call per line */
+int harness_homp (int mode, const uint8_t *txt, uint64_t txt_len, const uint64_t *str_off, const uint64_t *seq_off, const uint32_t *lens, uint32_t n_lines, int sub_codec,
+                  uint8_t *local, uint64_t *local_len, uint32_t *new_lens, uint8_t *comp, uint32_t *comp_len, uint8_t *back, uint64_t *back_len,
+                  int *n_soft_fails, int *n_missing, uint64_t *homp_lines)
+{
+    harness_init ();
+    if (setjmp (on_abort)) return -1;
+    g_assign = (Codec)sub_codec;
+    VBlockP vb = calloc (1, sizeof *vb); vb->vblock_i = 6; vb->n_lines = n_lines; g_vb = vb;
+    char *work = malloc (txt_len + 16); memcpy (work, txt, txt_len);             /* the codec condenses the strings in place */
+    vb->qual = malloc (n_lines * sizeof (char *)); vb->seq = malloc (n_lines * sizeof (char *));
+    vb->qual_len = malloc ((n_lines + 1) * 4); vb->seq_len = malloc ((n_lines + 1) * 4);
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n_lines; i++) { vb->qual[i] = work + str_off[i]; vb->seq[i] = work + seq_off[i]; vb->qual_len[i] = vb->seq_len[i] = lens[i]; total += lens[i]; }
+    struct Context *q = &vb->ctx[0];
+    q->local.len = total;                                  /* callback-mode locals carry only their total length */
+    union SectionHeaderUnion hdr = { { 0 } };
+    uint32_t ulen = (uint32_t)total; char *z = NULL; *n_soft_fails = 0;
+    int rc = comp_compress (mode ? gzb_codec_t0_compress : gzb_codec_homp_compress, gzb_codec_complex_est_size, mode ? 28 /* CODEC_T0 */ : 27 /* CODEC_HOMP */, vb, q, &hdr, NULL, &ulen, cb_qual, 1, &z, comp_len, n_soft_fails);
+    if (rc) return rc;
+    memcpy (comp, z, *comp_len);
+    /* what the sub-codec saw = the lines as they are now, one after the other */
+    uint64_t at = 0;
+    for (uint32_t i = 0; i < n_lines; i++) { memcpy (local + at, vb->qual[i], vb->qual_len[i]); at += vb->qual_len[i]; new_lens[i] = vb->qual_len[i]; }
+    *local_len = at;
+    if (q->local.len != at) return -5;                     /* ctx->local.len32 kept in step (codec_homp.c:184) */
+    *homp_lines = vb->lines_counter[4];
+    /* PIZ: the sub-codec put the condensed strings back into the context's local; SEQ of every read is known up front */
+    memcpy (buf_alloc_ (&q->local, at + 16), local, at); q->local.len = at;
+    vb->recon_lens = lens; vb->seq_txt = (const char *)txt; vb->seq_txt_len = txt_len; vb->seq_off = seq_off;
+    buf_alloc_ (&vb->txt_out, total + 64);
+    for (uint32_t i = 0; i < n_lines; i++)
+        if (lens[i]) (mode ? gzb_codec_t0_reconstruct : gzb_codec_homp_reconstruct) (vb, mode ? 28 : 27, q, lens[i], true);
+    *back_len = vb->txt_out.len; memcpy (back, vb->txt_out.data, vb->txt_out.len);
+    *n_missing = vb->n_missing;
+    free (z); free (work); free (vb->qual_len); free (vb->seq_len); vb->qual_len = NULL; vb->seq_len = NULL; g_vb = NULL; vb_free (vb);
     return 0;
 }
 

@@ -188,6 +188,28 @@ def check_normq(H, seed, n_lines, p_missing, sub="ARTB"):
     assert nm.value == int(missing.sum()) and nl.value == zlen.size
 
 
+def check_homp(H, mode, seed, n_lines, sub="ARTB"):
+    """codec_homp_compress / codec_t0_compress and their reconstruct through the plug-in layer: the lines condensed in place with their lengths
+    updated, the soft-fail re-entry, one reconstruct call per line"""
+    from test_homp_t0 import ultima_like
+    txt, so, sl, qo = ultima_like(n_lines, seed, mode, noise=0.1)
+    tot = int(sl.sum())
+    local = np.zeros(tot + 64, np.uint8); newl = np.zeros(sl.size + 1, np.uint32); comp = np.zeros(2 * tot + 70000, np.uint8); back = np.zeros(tot + 64, np.uint8)
+    ll, cl, bl, sf, nm, nl = C.c_uint64(), C.c_uint32(), C.c_uint64(), C.c_int(), C.c_int(), C.c_uint64()
+    _ok(H, H.harness_homp(mode, _p(txt), C.c_uint64(txt.size), _p(so), _p(qo), _p(sl), sl.size, CODEC[sub], _p(local), C.byref(ll), _p(newl), _p(comp), C.byref(cl),
+                          _p(back), C.byref(bl), C.byref(sf), C.byref(nm), C.byref(nl)))
+    want, want_len = orc.hp_condense(mode, txt, so, sl, qo, "ref" if orc.have_gz_ref() else "port")
+    assert ll.value == want.size and np.array_equal(local[:want.size], want), "the condensed lines differ from the reference's"
+    assert np.array_equal(newl[:sl.size], want_len), "the updated line lengths differ"
+    if want.size >= 50:
+        kind = "rans" if sub.startswith("RAN") else "arith"
+        assert np.array_equal(comp[:cl.value], orc.compress("ref" if orc.have_ref() else "port", kind, want, orc.ORDER[sub])), "the section differs"
+    assert sf.value == 1, "the soft-fail re-entry was not taken"
+    text = np.concatenate([txt[int(o):int(o) + int(l)] for o, l in zip(so, sl)])
+    assert bl.value == text.size and np.array_equal(back[:text.size], text), "reconstructed text differs"
+    assert nm.value == 0 and nl.value == (sl.size if mode == 0 else 0)
+
+
 def run_all(H, big):
     r = np.random.default_rng(3)
     # simple codecs: contiguous and line by line, with and without the soft-fail retry
@@ -230,6 +252,9 @@ def run_all(H, big):
     # NORMQ: reverse-complemented reads, lines without quality
     check_normq(H, 21, 200 if not big else 20000, 0.0)
     check_normq(H, 22, 150 if not big else 5000, 0.15, sub="RANB")
+    # HOMP and T0: lines condensed in place, lengths updated through the adapter
+    check_homp(H, 0, 31, 120 if not big else 3000)
+    check_homp(H, 1, 32, 120 if not big else 3000, sub="RANB")
 
 
 def check_combiner(H):
