@@ -102,8 +102,9 @@ class ZipMeta:
     """what a zip pass leaves behind for the piz pass and the section list: per VBlock and stream the uncompressed length, the
     compressed length and where the compressed section lies (address inside the packed output buffer)."""
 
-    def __init__(self, V):
+    def __init__(self, V, streams=None):
         self.V = V
+        self.streams = STREAMS = list(streams if streams is not None else globals()["STREAMS"])
         self.len = np.zeros((V, len(STREAMS)), np.int64)
         self.comp_len = np.zeros((V, len(STREAMS)), np.int64)
         self.comp_ptr = np.zeros((V, len(STREAMS)), np.uint64)
@@ -116,8 +117,8 @@ class ZipMeta:
         return self.V
 
     def __getitem__(self, v):
-        return dict(len={s: int(self.len[v, i]) for i, s in enumerate(STREAMS)},
-                    comp_len={s: int(self.comp_len[v, i]) for i, s in enumerate(STREAMS) if self.len[v, i]},
+        return dict(len={s: int(self.len[v, i]) for i, s in enumerate(self.streams)},
+                    comp_len={s: int(self.comp_len[v, i]) for i, s in enumerate(self.streams) if self.len[v, i]},
                     acgt_no_x=bool(self.acgt_no_x[v]), num_norm_qs=int(self.num_norm_qs[v]),
                     denorm=bytes(self.denorm[v, :int(self.num_norm_qs[v]) * int(self.num_doms[v])]))
 
@@ -142,10 +143,18 @@ class FastqCodecPath:
     The host-buffer path gives each of the three independent pipelines of a FASTQ VBlock (QUAL, SEQ, read names) its own engine
     (host thread + CUDA stream) so that transfers overlap the entropy chains (zip_host / piz_host)."""
 
-    def __init__(self, eng: Engine, V, n_reads, read_len, n_engines=3, sub_batch=128):
+    def __init__(self, eng: Engine, V, n_reads, read_len, n_engines=3, sub_batch=128, fields=None, seq_len=None):
+        """fields: {context name: bytes per VBlock} of the b250 / local streams that go through the simple codecs beside QUAL and SEQ
+        (default: the four read-name contexts of a FASTQ VBlock); seq_len: bases handed to codec_acgt per VBlock (default: every base
+        of the reads, FASTQ's NONREF.local; an aligned BAM VBlock hands over only the bases its reference does not explain)."""
         self.eng, self.L = eng, eng.L
         self.V, self.n_reads, self.read_len = V, n_reads, read_len
         self.n = n = n_reads * read_len
+        self.n_seq = n_seq = n if seq_len is None else int(seq_len)
+        fields = dict(fields) if fields is not None else {"Q_TILE": n_reads, "Q_X": 4 * n_reads, "Q_Y": 4 * n_reads, "Q_MISC": n_reads}
+        self.NAMES = tuple(fields)
+        self.STREAMS = list(DQ) + ["NONREF_X"] + list(self.NAMES)
+        self.S_IDX = {s: i for i, s in enumerate(self.STREAMS)}
         dev = torch.device(getattr(eng, "torch_device", None) or f"cuda:{eng.device}")   # (the CPU test suite drives this class through a mock engine)
         self.dev = dev
         n_engines = max(1, n_engines)
@@ -153,25 +162,25 @@ class FastqCodecPath:
         self.pool = ThreadPoolExecutor(n_engines) if n_engines > 1 else None
         self.stream = torch.cuda.ExternalStream(self.L.gzb_engine_stream(eng.h), device=dev) if dev.type == "cuda" else None
         self.SB = max(1, min(sub_batch, V))
-        self.packed_len = int(self.L.gzb_acgt_packed_len(n))
+        self.packed_len = int(self.L.gzb_acgt_packed_len(n_seq))
         u8 = dict(dtype=torch.uint8, device=dev)
         self.line_off_h = _pin(torch.arange(n_reads, dtype=torch.int64) * read_len)
         self.line_len_h = _pin(torch.full((n_reads,), read_len, dtype=torch.int32))
         self.line_off_d, self.line_len_d = self.line_off_h.to(dev), self.line_len_h.to(dev)
         self.packed_d = torch.empty((V, self.packed_len + 32), **u8)
-        self.x_d = torch.empty((V, n), **u8)
+        self.x_d = torch.empty((V, n_seq), **u8)
         self.linedom_d = torch.empty((V, n_reads), **u8)
         self.linediv_d = torch.empty((V, n_reads), **u8)
         self.caps = {"QUAL": 2 * n + 16, "DOMQRUNS": n + 16, "QUALMPLX": n_reads + 16, "DIVRQUAL": n + 16}
         # worst-case scratch of one sub-batch per engine that runs codec_domq_compress (engine 0 only)
         self.dqs = {s: torch.empty((self.SB, c), **u8) for s, c in self.caps.items()}
-        self.name_len = {"Q_TILE": n_reads, "Q_X": 4 * n_reads, "Q_Y": 4 * n_reads, "Q_MISC": n_reads}
+        self.name_len = {s: int(b) for s, b in fields.items()}
         self.dq_arena = None                                                  # compact DOMQ streams of all V VBlocks
         self.comp_arena = None                                                # packed compressed sections (device): the QUAL pipeline's
         self.comp_arena2 = None                                               #   and the others'
         self.device_pipelines = 2 if n_engines >= 2 else 1
         self.comp_used = {}                                                   # bytes of packed sections in each output buffer after the last zip
-        self.codec = {s: "RANB" for s in STREAMS}
+        self.codec = {s: "RANB" for s in self.STREAMS}
         self.dvb = (DomqVb * V)(); self.pvb = (DomqPizVb * V)(); self.avb = (AcgtVb * V)()
         self.dvb_np, self.pvb_np, self.avb_np = struct_view(self.dvb), struct_view(self.pvb), struct_view(self.avb)
         self.meta = None
@@ -225,13 +234,13 @@ class FastqCodecPath:
         in-scope simple codecs: compress the first <=99,999 bytes (CODEC_ASSIGN_SAMPLE_SIZE, src/codec.h:154) of VB 1's
         stream with each and keep the smallest, ties to the lower Codec value.  The reference also weighs clock() time
         (timing-dependent, H5) — not reproduced.  Samples are compressed on the GPU (same bytes as the reference)."""
-        meta = ZipMeta(self.V)
+        meta = ZipMeta(self.V, self.STREAMS)
         self._acgt_pack_device(data, meta, 0, 1)
         self._domq_device(lambda v: data["qual"][v].data_ptr(), self.engs[0], meta, GZB_DEVICE_PTRS, 0, 1)
-        meta.len[0, [S_IDX[s] for s in NAMES]] = [self.name_len[s] for s in NAMES]
-        present = [s for s in STREAMS if int(meta.len[0, S_IDX[s]])]
+        meta.len[0, [self.S_IDX[s] for s in self.NAMES]] = [self.name_len[s] for s in self.NAMES]
+        present = [s for s in self.STREAMS if int(meta.len[0, self.S_IDX[s]])]
         # one gzb_assign_codecs call: the first <= 99,999 bytes of every stream of VB 1, where they are in HBM, with the eight codecs; sizes only
-        res = self.eng.assign_codecs_ptrs([(self._stream_tensor(s, 0, data, meta).data_ptr(), int(meta.len[0, S_IDX[s]])) for s in present], GZB_DEVICE_PTRS)
+        res = self.eng.assign_codecs_ptrs([(self._stream_tensor(s, 0, data, meta).data_ptr(), int(meta.len[0, self.S_IDX[s]])) for s in present], GZB_DEVICE_PTRS)
         for s, (best, sizes) in zip(present, res):
             # a sample below 50 B would go out as CODEC_NONE (compressor.c:56-58), and so would one no codec shrinks: this path has no
             # uncompressed sections, it keeps the smallest of the eight then
@@ -242,7 +251,7 @@ class FastqCodecPath:
         """device tensor holding stream s of VBlock v (whole capacity for the inputs; the real length for the DOMQ streams)"""
         if s in DQ:
             o = int(meta.dq_off[v, DQ.index(s)])
-            return self.dq_arena[o: o + int(meta.len[v, S_IDX[s]])]
+            return self.dq_arena[o: o + int(meta.len[v, self.S_IDX[s]])]
         if s == "NONREF_X":
             return self.x_d[v]
         return data[s][v]
@@ -251,12 +260,12 @@ class FastqCodecPath:
     def _acgt_pack_device(self, data, meta, v0, v1, eng=None):
         eng = eng or self.eng
         a = self.avb_np
-        a["seq"][v0:v1] = self._rows(data["seq"])[v0:v1]; a["n_bases"][v0:v1] = self.n
+        a["seq"][v0:v1] = self._rows(data["seq"])[v0:v1]; a["n_bases"][v0:v1] = self.n_seq
         a["packed"][v0:v1] = self._rows(self.packed_d)[v0:v1]; a["x"][v0:v1] = self._rows(self.x_d)[v0:v1]
         if self.L.gzb_acgt_pack_batch(eng.h, self._sub(self.avb, v0, v1), v1 - v0, GZB_DEVICE_PTRS):
             raise GzbError(f"gzb_acgt_pack_batch: {eng._err()}")
         meta.acgt_no_x[v0:v1] = a["x_all_zero"][v0:v1] != 0
-        meta.len[v0:v1, S_IDX["NONREF_X"]] = np.where(meta.acgt_no_x[v0:v1], 0, self.n)
+        meta.len[v0:v1, self.S_IDX["NONREF_X"]] = np.where(meta.acgt_no_x[v0:v1], 0, self.n_seq)
 
     def _dq_reserve(self, need, used, total_guess):
         """the compact buffer of the DOMQ streams: sized from the first sub-batch, grown (contents kept) if that was too little"""
@@ -298,31 +307,31 @@ class FastqCodecPath:
             cursor = need
             meta.dq_off[b0:b1] = offs
             for j, s in enumerate(DQ):
-                meta.len[b0:b1, S_IDX[s]] = lens[:, j]
+                meta.len[b0:b1, self.S_IDX[s]] = lens[:, j]
             meta.num_norm_qs[b0:b1] = d["num_norm_qs"][b0:b1]; meta.num_doms[b0:b1] = d["num_doms"][b0:b1]
             meta.denorm[b0:b1] = d["denorm"][b0:b1]
         meta._dq_cursor = cursor
 
     def _section_array(self, meta, in_ptr, names, sflags=0):
         """gzb_section descriptors of the non-empty streams `names` of every VBlock, VBlock-major; returns (array, view, v index, stream index)"""
-        cols = [S_IDX[s] for s in names]
+        cols = [self.S_IDX[s] for s in names]
         ln = meta.len[:, cols]
         vv, jj = np.nonzero(ln)
         ss = np.asarray(cols)[jj]
         secs = (Section * max(1, vv.size))(); a = struct_view(secs)
-        a["codec"][:vv.size] = np.asarray([CODEC[self.codec[s]] for s in STREAMS], np.int32)[ss]
+        a["codec"][:vv.size] = np.asarray([CODEC[self.codec[s]] for s in self.STREAMS], np.int32)[ss]
         a["in_"][:vv.size] = in_ptr[vv, ss]; a["in_len"][:vv.size] = ln[vv, jj]
         a["sflags"][:vv.size] = np.asarray(sflags, np.uint32)[ss] if not np.isscalar(sflags) else sflags
         return secs, a, vv, ss
 
     def _in_ptrs(self, meta, name_rows, dq_base):
         """[V, 9] addresses of the uncompressed streams: DOMQ streams in the compact buffer, the exception stream, the read-name contexts"""
-        p = np.zeros((self.V, len(STREAMS)), np.uint64)
+        p = np.zeros((self.V, len(self.STREAMS)), np.uint64)
         for j, s in enumerate(DQ):
-            p[:, S_IDX[s]] = np.uint64(dq_base) + meta.dq_off[:, j].astype(np.uint64)
-        p[:, S_IDX["NONREF_X"]] = self._rows(self.x_d)
-        for s in NAMES:
-            p[:, S_IDX[s]] = name_rows[s]
+            p[:, self.S_IDX[s]] = np.uint64(dq_base) + meta.dq_off[:, j].astype(np.uint64)
+        p[:, self.S_IDX["NONREF_X"]] = self._rows(self.x_d)
+        for s in self.NAMES:
+            p[:, self.S_IDX[s]] = name_rows[s]
         return p
 
     def _compress_packed(self, eng, secs, a, n, flags, arena_attr, host):
@@ -358,10 +367,10 @@ class FastqCodecPath:
         and the rest (codec_acgt_compress + the exception stream, the read-name contexts) run on one engine / host thread each: the
         DOMQ passes of one overlap the entropy chains of the other — as two compute threads of the reference would."""
         V = self.V
-        meta = ZipMeta(V)
-        for s in NAMES:
-            meta.len[:, S_IDX[s]] = self.name_len[s]
-        name_rows = {s: self._rows(data[s]) for s in NAMES}
+        meta = ZipMeta(V, self.STREAMS)
+        for s in self.NAMES:
+            meta.len[:, self.S_IDX[s]] = self.name_len[s]
+        name_rows = {s: self._rows(data[s]) for s in self.NAMES}
 
         def compress(eng, names, arena):
             inp = self._in_ptrs(meta, name_rows, self.dq_arena.data_ptr() if self.dq_arena is not None else 0)
@@ -385,7 +394,7 @@ class FastqCodecPath:
         def part_rest(eng):
             self._acgt_pack_device(data, meta, 0, V, eng)
             domq_done.wait()
-            compress(eng, ("NONREF_X",) + NAMES, "comp_arena2")
+            compress(eng, ("NONREF_X",) + self.NAMES, "comp_arena2")
 
         if self.device_pipelines >= 2 and self.pool is not None and len(self.engs) >= 2:
             self._run_parts([part_qual, part_rest])
@@ -398,7 +407,7 @@ class FastqCodecPath:
 
     def section_bytes(self, meta, v, s, host=False):
         """the compressed section of stream s of VBlock v as a numpy array"""
-        i = S_IDX[s]
+        i = self.S_IDX[s]
         ln = int(meta.comp_len[v, i])
         arena = self.h["comp_" + self._pipeline_of(s)] if host else (self.comp_arena if s in DQ else self.comp_arena2)
         o = int(meta.comp_ptr[v, i]) - arena.data_ptr()
@@ -411,8 +420,8 @@ class FastqCodecPath:
     # ------------------------------------------------------------------ PIZ, inputs resident in HBM
     def alloc_piz(self, meta):
         u8 = dict(dtype=torch.uint8, device=self.dev)
-        self.names_dec_d = {s: torch.empty((self.V, self.name_len[s] + 16), **u8) for s in NAMES}
-        self.seq_out_d = torch.empty((self.V, self.n), **u8)
+        self.names_dec_d = {s: torch.empty((self.V, self.name_len[s] + 16), **u8) for s in self.NAMES}
+        self.seq_out_d = torch.empty((self.V, self.n_seq), **u8)
         self.qual_out_d = torch.empty((self.V, self.n), **u8)
         self.dec_d = self.names_dec_d                                          # (the decoded read-name contexts, by stream)
 
@@ -429,12 +438,12 @@ class FastqCodecPath:
         p, a = self.pvb_np, self.avb_np
         base = np.uint64(self.dq_arena.data_ptr())
         for j, (fld, s) in enumerate(zip(DQ_FLD, DQ)):
-            p[fld] = base + meta.dq_off[:, j].astype(np.uint64); p[fld + "_len"] = meta.len[:, S_IDX[s]]
+            p[fld] = base + meta.dq_off[:, j].astype(np.uint64); p[fld + "_len"] = meta.len[:, self.S_IDX[s]]
         p["denorm"] = np.uint64(meta.denorm.ctypes.data) + np.arange(self.V, dtype=np.uint64) * np.uint64(95 * 95)
         p["denorm_len"] = meta.num_norm_qs.astype(np.uint32) * meta.num_doms.astype(np.uint32); p["num_norm_qs"] = meta.num_norm_qs
         p["line_len"] = line_len.data_ptr(); p["n_lines"] = self.n_reads
         p["out"] = qual_out_rows; p["out_cap"] = self.n
-        a["seq"] = seq_out_rows; a["n_bases"] = self.n; a["packed"] = packed_rows
+        a["seq"] = seq_out_rows; a["n_bases"] = self.n_seq; a["packed"] = packed_rows
         a["x"] = np.where(meta.acgt_no_x, np.uint64(0), self._rows(self.x_d))
 
     def piz_device(self, meta, outs=None):
@@ -442,7 +451,7 @@ class FastqCodecPath:
         L = self.L
         if outs is None:
             outs = dict(self.names_dec_d, seq=self.seq_out_d, qual=self.qual_out_d)
-        outp = self._in_ptrs(meta, {s: self._rows(outs[s]) for s in NAMES}, self.dq_arena.data_ptr())
+        outp = self._in_ptrs(meta, {s: self._rows(outs[s]) for s in self.NAMES}, self.dq_arena.data_ptr())
         self._fill_piz_descriptors(meta, self._rows(outs["qual"]), self._rows(outs["seq"]), self._rows(self.packed_d), self.line_len_d)
 
         def uncompress(eng, names):
@@ -457,7 +466,7 @@ class FastqCodecPath:
                 raise GzbError(f"gzb_domq_reconstruct: {eng._err()}")
 
         def part_rest(eng):
-            uncompress(eng, ("NONREF_X",) + NAMES)
+            uncompress(eng, ("NONREF_X",) + self.NAMES)
             if L.gzb_acgt_unpack_batch(eng.h, self.avb, self.V, GZB_DEVICE_PTRS):
                 raise GzbError(f"gzb_acgt_unpack_batch: {eng._err()}")
 
@@ -479,11 +488,11 @@ class FastqCodecPath:
         hp = lambda *shape: _pin(torch.empty(shape, dtype=torch.uint8))
         self.h["packed"] = hp(V, self.packed_len + 32)
         self.h["linedom"] = hp(V, self.n_reads); self.h["linediv"] = hp(V, self.n_reads)
-        self.h["seq_out"] = hp(V, n); self.h["qual_out"] = hp(V, n)
-        self.h["dec"] = {s: hp(V, self.name_len[s] + 16) for s in NAMES}
+        self.h["seq_out"] = hp(V, self.n_seq); self.h["qual_out"] = hp(V, n)
+        self.h["dec"] = {s: hp(V, self.name_len[s] + 16) for s in self.NAMES}
         if self.meta is not None:                                            # packed section buffers of the three pipelines, sized from the device pass
-            for pl, names in (("qual", DQ), ("seq", ("NONREF_X",)), ("names", NAMES)):
-                need = int(((self.meta.comp_len[:, [S_IDX[s] for s in names]] + 15) & ~15).sum())
+            for pl, names in (("qual", DQ), ("seq", ("NONREF_X",)), ("names", self.NAMES)):
+                need = int(((self.meta.comp_len[:, [self.S_IDX[s] for s in names]] + 15) & ~15).sum())
                 self.h["comp_" + pl] = hp(int(need * 1.05) + 65536)
 
     def _run_parts(self, parts):
@@ -511,17 +520,17 @@ class FastqCodecPath:
         overlap the entropy chains of another; QUAL's upload goes first because its chains are the longest.
         Returns (meta, h2d_bytes, d2h_bytes)."""
         L, V, n, H = self.L, self.V, self.n, self.h
-        meta = ZipMeta(V)
-        for s in NAMES:
-            meta.len[:, S_IDX[s]] = self.name_len[s]
-        dev_in = np.zeros(len(STREAMS), np.uint32)
+        meta = ZipMeta(V, self.STREAMS)
+        for s in self.NAMES:
+            meta.len[:, self.S_IDX[s]] = self.name_len[s]
+        dev_in = np.zeros(len(self.STREAMS), np.uint32)
         for s in DQ + ("NONREF_X",):
-            dev_in[S_IDX[s]] = GZB_SEC_IN_DEVICE                 # intermediate streams stay in HBM until their sub-codec
+            dev_in[self.S_IDX[s]] = GZB_SEC_IN_DEVICE                 # intermediate streams stay in HBM until their sub-codec
         qual_up = threading.Event()
         passes_done = [threading.Event(), threading.Event()]        # the DOMQ passes / the ACGT pack of the whole group: chain kernels start after both (see zip_device)
         if self.pool is None or len(self.engs) < 3:                 # (one engine: the parts run one after the other, nothing to wait for)
             passes_done[0].set(); passes_done[1].set(); qual_up.set()
-        name_rows = {s: self._rows(H[s]) for s in NAMES}
+        name_rows = {s: self._rows(H[s]) for s in self.NAMES}
 
         def compress(eng, names, arena):
             inp = self._in_ptrs(meta, name_rows, self.dq_arena.data_ptr() if self.dq_arena is not None else 0)
@@ -547,7 +556,7 @@ class FastqCodecPath:
             qual_up.wait()
             a = self.avb_np
             try:
-                a["seq"] = self._rows(H["seq"]); a["n_bases"] = n; a["packed"] = self._rows(H["packed"]); a["x"] = self._rows(self.x_d)
+                a["seq"] = self._rows(H["seq"]); a["n_bases"] = self.n_seq; a["packed"] = self._rows(H["packed"]); a["x"] = self._rows(self.x_d)
                 for v0 in range(0, V, 64):                          # bounded staging in the engine workspace
                     v1 = min(V, v0 + 64)
                     if L.gzb_acgt_pack_batch(eng.h, self._sub(self.avb, v0, v1), v1 - v0, GZB_OUT_DEVICE):
@@ -555,28 +564,28 @@ class FastqCodecPath:
             finally:
                 passes_done[1].set()
             meta.acgt_no_x[:] = a["x_all_zero"] != 0
-            meta.len[:, S_IDX["NONREF_X"]] = np.where(meta.acgt_no_x, 0, n)
+            meta.len[:, self.S_IDX["NONREF_X"]] = np.where(meta.acgt_no_x, 0, self.n_seq)
             passes_done[0].wait()
             compress(eng, ("NONREF_X",), "comp_seq")
 
         def part_names(eng):
             passes_done[0].wait(); passes_done[1].wait()
-            compress(eng, NAMES, "comp_names")
+            compress(eng, self.NAMES, "comp_names")
 
         self._run_parts([part_qual, part_seq, part_names])
-        on_dev = [S_IDX[s] for s in DQ + ("NONREF_X",)]
-        host_in = np.ones(len(STREAMS), bool); host_in[on_dev] = False
-        h2d = V * (n + n + 12 * self.n_reads) + int(meta.len[:, host_in].sum())
+        on_dev = [self.S_IDX[s] for s in DQ + ("NONREF_X",)]
+        host_in = np.ones(len(self.STREAMS), bool); host_in[on_dev] = False
+        h2d = V * (n + self.n_seq + 12 * self.n_reads) + int(meta.len[:, host_in].sum())
         d2h = V * (self.packed_len + 2 * self.n_reads) + int(meta.comp_len.sum())
         return meta, h2d, d2h
 
     def piz_host(self, meta):
         """the inverse of zip_host"""
         L, V, n, H = self.L, self.V, self.n, self.h
-        dev_out = np.zeros(len(STREAMS), np.uint32)
+        dev_out = np.zeros(len(self.STREAMS), np.uint32)
         for s in DQ + ("NONREF_X",):
-            dev_out[S_IDX[s]] = GZB_SEC_OUT_DEVICE
-        outp = self._in_ptrs(meta, {s: self._rows(H["dec"][s]) for s in NAMES}, self.dq_arena.data_ptr())
+            dev_out[self.S_IDX[s]] = GZB_SEC_OUT_DEVICE
+        outp = self._in_ptrs(meta, {s: self._rows(H["dec"][s]) for s in self.NAMES}, self.dq_arena.data_ptr())
 
         def uncompress(eng, names):
             secs, a, vv, ss = self._section_array(meta, meta.comp_ptr, names, dev_out)
@@ -599,13 +608,13 @@ class FastqCodecPath:
                     raise GzbError(f"gzb_acgt_unpack_batch: {eng._err()}")
 
         def part_names(eng):
-            uncompress(eng, NAMES)
+            uncompress(eng, self.NAMES)
 
         self._run_parts([part_qual, part_seq, part_names])
-        on_dev = [S_IDX[s] for s in DQ + ("NONREF_X",)]
-        host_out = np.ones(len(STREAMS), bool); host_out[on_dev] = False
+        on_dev = [self.S_IDX[s] for s in DQ + ("NONREF_X",)]
+        host_out = np.ones(len(self.STREAMS), bool); host_out[on_dev] = False
         h2d = V * (4 * self.n_reads + self.packed_len) + int(meta.comp_len.sum())
-        d2h = V * (n + n) + int(meta.len[:, host_out].sum())
+        d2h = V * (n + self.n_seq) + int(meta.len[:, host_out].sum())
         return h2d, d2h
 
 
@@ -633,7 +642,7 @@ class PipelinedHost:
         self.width = {k: v.shape[1] for k, v in data_host.items()}
         self.H = {}
         for k, v in data_host.items():                                       # (device tensors are copied straight into the page-locked buffers: no pageable copy in between)
-            t = _pin(torch.zeros((v.shape[0], v.shape[1] + (16 if k in NAMES else 0)), dtype=torch.uint8))
+            t = _pin(torch.zeros((v.shape[0], v.shape[1] + (16 if k in path.NAMES else 0)), dtype=torch.uint8))
             t[:, :v.shape[1]].copy_(v)
             self.H[k] = t
         self.slots = [{k: torch.empty(v.shape, dtype=torch.uint8, device=dev) for k, v in self.H.items()} for _ in range(2)]
