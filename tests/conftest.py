@@ -33,9 +33,9 @@ def pytest_addoption(parser):
 
 def pytest_collection_modifyitems(config, items):
     if config.getoption("--dry-gpu") or config.getoption("--simt"):
-        skip = pytest.mark.skip(reason="--dry-gpu / --simt: needs torch device memory (covered by tests/test_fastq_path_cpu.py)")
+        skip = pytest.mark.skip(reason="--dry-gpu / --simt: needs torch device memory (covered by tests/test_fastq_path_cpu.py / test_bam_path_cpu.py)")
         for it in items:
-            if "test_gpu_fastq_path" in it.nodeid:
+            if "test_gpu_fastq_path" in it.nodeid or "test_zz_gpu_bam_path" in it.nodeid:
                 it.add_marker(skip)
             if "fullsize" in it.keywords:
                 it.add_marker(pytest.mark.skip(reason="--dry-gpu / --simt: BASELINE-size inputs are for the GPU"))
