@@ -33,8 +33,8 @@ def parse():
                     help="VBlocks per GPU per step (0 = as many as fit, at most 256: the chain kernels are latency-bound, so throughput grows with the batch)")
     ap.add_argument("--reads", type=int, default=92000, help="reads per VBlock (92,000 x 150 bp ~ 32 MB of FASTQ text)")
     ap.add_argument("--read-len", type=int, default=150)
-    ap.add_argument("--workload", default="fastq", choices=["fastq", "vcf", "longread"],
-                    help="fastq = BASELINE configs[1] (the headline metric); vcf = configs[3] (codec_pbwt); longread = configs[4] (codec_longr) — bench_domain.py")
+    ap.add_argument("--workload", default="fastq", choices=["fastq", "bam", "vcf", "longread"],
+                    help="fastq = BASELINE configs[1] (the headline metric); bam = configs[2] (aligned BAM VBlocks: DOMQ + the field streams, codec_acgt on NONREF only — genozip_b200/bam_path.py); vcf = configs[3] (codec_pbwt); longread = configs[4] (codec_longr) — bench_domain.py")
     ap.add_argument("--vcf-lines", type=int, default=38000); ap.add_argument("--vcf-samples", type=int, default=1000)
     ap.add_argument("--lr-bases", type=int, default=16_000_000); ap.add_argument("--lr-read-len", type=int, default=50000)
     ap.add_argument("--no-e2e", action="store_true")
@@ -88,13 +88,39 @@ class ClockSampler:
 _CPU = {}
 
 
+class Spec:
+    """what differs between the two read workloads that run the same path class (fastq_path.FastqCodecPath / bam_path.BamCodecPath)"""
+
+    def __init__(self, workload):
+        self.bam = workload == "bam"
+        if self.bam:
+            from genozip_b200 import bam_path as B
+            self.cls, self.synth, self.bytes_per_vb = B.BamCodecPath, B.synth_bam_vblocks, B.bam_bytes_per_vb
+            self.metric = "bam_input_GBps_zip_plus_piz"
+            self.workload = "bam_aligned_sorted_150bp_vb92Kreads (BASELINE configs[2] per-GPU share; post-seg streams, SURVEY 8d C3)"
+            self.excluded = "segmenter, reference / aligner, BGZF; LZMA of NONREF's 2-bit words (host, out of scope) — in both arms"
+            self.table = os.path.join(ROOT, "bench_codecs_bam.json")
+            self.accounting = ("input bytes = the uncompressed BAM records the VBlocks represent (block_size + 32 fixed bytes, 40-byte read name, one CIGAR op, "
+                               "4-bit SEQ, QUAL, ~28 B of aux fields per read); the segmenter is out of scope: what flows through the path is QUAL (1 B / base), "
+                               "NONREF (1.5 % of the bases), SQBITMAP (1 bit / base) and ~24.1 B / read of field, aux and QNAME contexts; the same count in both arms")
+        else:
+            from genozip_b200 import fastq_path as F
+            self.cls, self.synth, self.bytes_per_vb = F.FastqCodecPath, F.synth_vblocks, F.txt_bytes_per_vb
+            self.metric, self.workload, self.excluded, self.table = METRIC, WORKLOAD, EXCLUDED, CODEC_TABLE
+            self.accounting = ("input bytes = the FASTQ text the VBlocks represent (45-byte name line, SEQ, '+', QUAL, 4 newlines per read); of the name line, "
+                               "10 B/read of segmented read-name contexts flow through the path (the segmenter is out of scope); the same count in both arms")
+
+    def codecs(self):
+        return json.load(open(self.table))
+
+
 def _cpu_worker(wid, n_workers, n_vb, bar, q):
     """one host process: zip then piz of its share of the VBlocks, phases separated by barriers so that the parent
     times the whole pool (processes, not threads: the Python glue around the C calls must not serialise on the GIL)"""
     import orc
     data_np, n_reads, read_len, codec, impl = _CPU["data"], _CPU["n_reads"], _CPU["read_len"], _CPU["codec"], _CPU["impl"]
     off = (np.arange(n_reads, dtype=np.uint64) * np.uint64(read_len)); ln = np.full(n_reads, read_len, np.uint32)
-    names = ("Q_TILE", "Q_X", "Q_Y", "Q_MISC")
+    names = tuple(k for k in data_np if k not in ("seq", "qual"))      # the simple-codec contexts of the workload
     mine = list(range(wid, n_vb, n_workers))
     gz = orc.have_gz_ref()                                   # the reference's own compiled codec_domq.c / codec_acgt.c (-O3), else the restatement
     acgt_pack, domq_encode = (orc.ref_acgt_pack, orc.ref_domq_encode) if gz else (orc.acgt_pack, orc.domq_encode)
@@ -125,8 +151,9 @@ def _cpu_worker(wid, n_workers, n_vb, bar, q):
         e = dict(z["enc"]); e.update(qual=dec["QUAL"], runs=dec.get("DOMQRUNS", np.zeros(0, np.uint8)), mplx=dec["QUALMPLX"],
                                      divr=dec.get("DIVRQUAL", np.zeros(0, np.uint8)))
         q_ = domq_decode(e, ln)
-        s2 = acgt_unpack(z["packed"], None if z["allz"] else dec["NONREF_X"], n_reads * read_len)
+        s2 = acgt_unpack(z["packed"], None if z["allz"] else dec["NONREF_X"], data_np["seq"][v].size)
         ok = ok and np.array_equal(q_, data_np["qual"][v]) and np.array_equal(s2, data_np["seq"][v])
+        ok = ok and all(np.array_equal(dec[k], data_np[k][v]) for k in names)
     bar.wait()
     q.put((ok, sum(len(c) for z in zs for c, _ in z["comp"].values())))
 
@@ -157,13 +184,13 @@ def cpu_path_time(data_np, n_reads, read_len, codec, workers, n_vb):
     return t1 - t0, t2 - t1, kind
 
 
-def synth_numpy(V, n_reads, read_len, seed):
+def synth_numpy(V, n_reads, read_len, seed, synth=None):
     """the bytes of the GPU arm's first V VBlocks for the CPU-only arm: the same torch generator, on the GPU when the box has one
     (the GPU arm generates there, and CUDA's random streams differ from the CPU's), else on the CPU (same distribution, other bytes)"""
     import torch
     from genozip_b200.fastq_path import synth_vblocks
     dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
-    d = synth_vblocks(V, n_reads, read_len, seed, dev)
+    d = (synth or synth_vblocks)(V, n_reads, read_len, seed, dev)
     out = {k: [t[v].cpu().numpy() for v in range(V)] for k, t in d.items()}
     del d
     if dev.type == "cuda":
@@ -188,9 +215,10 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     n_vb = max(2 * cores, 8)                                 # two VBlocks per host process per step
-    from genozip_b200.fastq_path import txt_bytes_per_vb
-    data, gen = synth_numpy(n_vb, args.reads, args.read_len, 1000)          # = the GPU arm's rank-0 VBlocks 0 .. n_vb-1
-    codec = load_codecs()
+    spec = Spec(args.workload)
+    txt_bytes_per_vb = spec.bytes_per_vb
+    data, gen = synth_numpy(n_vb, args.reads, args.read_len, 1000, spec.synth)          # = the GPU arm's rank-0 VBlocks 0 .. n_vb-1
+    codec = spec.codecs()
     ts = []
     for i in range(args.warmup + args.steps):
         tz, tp, kind = cpu_path_time(data, args.reads, args.read_len, codec, cores, n_vb)
@@ -201,14 +229,14 @@ def run_reference(args):
     val = nbytes / (tz + tp) / 1e9
     sample = f"{n_vb} VBlocks x {args.reads} reads x {args.read_len} bp per step dealt to {cores} host processes"
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "impl": "reference", "metric": spec.metric, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * (tz + tp) / len(ts), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic", "zip_GBps": nbytes / tz / 1e9, "piz_GBps": nbytes / tp / 1e9,
-        "config": {"workload": WORKLOAD, "vblocks_per_step": n_vb,
+        "config": {"workload": spec.workload, "vblocks_per_step": n_vb,
                    "reads_per_vblock": args.reads, "read_len": args.read_len, "codecs": codec,
                    "compressed_bytes_per_vblock": _CPU.get("compressed_bytes", 0) / n_vb,
                    "data_generator": f"torch-{gen} (the GPU arm's rank-0 VBlocks 0..{n_vb - 1}" + (")" if gen == "cuda" else "; no GPU here: same distribution, other bytes)"),
-                   "excluded": EXCLUDED},
+                   "excluded": spec.excluded},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -241,7 +269,8 @@ def run_gpu(args):
     import torch
     import torch.distributed as dist
     from genozip_b200 import Engine
-    from genozip_b200.fastq_path import FastqCodecPath, synth_vblocks, txt_bytes_per_vb, STREAMS
+    spec = Spec(args.workload)
+    FastqCodecPath, synth_vblocks, txt_bytes_per_vb = spec.cls, spec.synth, spec.bytes_per_vb
 
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
@@ -292,14 +321,15 @@ def run_gpu(args):
         eng.close(); torch.cuda.empty_cache()
         eng = Engine(local)
         V = max(4, int(V * 0.8))
-    committed = load_codecs()
+    committed = spec.codecs()
     rederived_equal = committed == dict(codecs)
     codecs = committed                                         # both arms run the committed table (see CODEC_TABLE)
     path.codec = dict(codecs)
     if not rederived_equal:                                    # (sizes were planned for the re-derived table)
         meta = path.zip_device(data); path.scrub_intermediates(); path.piz_device(meta); torch.cuda.synchronize()
     assert torch.equal(path.seq_out_d, data["seq"]) and torch.equal(path.qual_out_d, data["qual"]), "round trip failed"
-    for s in ("Q_TILE", "Q_X", "Q_Y", "Q_MISC"):
+    STREAMS = list(path.STREAMS)
+    for s in path.NAMES:
         assert torch.equal(path.dec_d[s][:, :data[s].shape[1]], data[s]), f"round trip failed: {s}"
 
     txt_bytes = V * txt_bytes_per_vb(args.reads, args.read_len)
@@ -454,7 +484,7 @@ def run_gpu(args):
     traffic = traffic_note = None
     try:                                                        # dram__bytes of this kernel from the committed ncu --set full capture, scaled to this launch's VBlocks
         tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
-        ent = tj.get(kname)
+        ent = tj.get(kname) if not spec.bam else None            # (the capture is of the FASTQ workload's leaves)
         if ent:
             traffic = int(ent["bytes_per_launch"] * V / ent["vblocks"])
             traffic_note = f"dram__bytes_read+write of {kname} captured at {ent['vblocks']} VBlocks ({ent.get('source', 'profiles/')}), scaled by {V}/{ent['vblocks']}"
@@ -492,16 +522,15 @@ def run_gpu(args):
     if rank == 0:
         comp_total = sum(sum(m["comp_len"].values()) for m in meta)
         print(json.dumps({
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": spec.metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": zip_ms + piz_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "zip_GBps": world * txt_bytes / (zip_ms * 1e-3) / 1e9, "piz_GBps": world * txt_bytes / (piz_ms * 1e-3) / 1e9,
-            "config": {"workload": WORKLOAD, "vblocks_per_gpu_per_step": V,
+            "config": {"workload": spec.workload, "vblocks_per_gpu_per_step": V,
                        "reads_per_vblock": args.reads, "read_len": args.read_len, "txt_bytes_per_step_per_gpu": txt_bytes,
                        "codecs": codecs, "codecs_rederived_equal": rederived_equal, "compressed_bytes_per_vblock": comp_total / V, "l2": "inputs (>= 0.9 GB per step) are larger than L2; no flush needed",
                        "sections_per_step": sum(1 for m in meta for n in m["len"].values() if n), "compressed_bytes_per_step": comp_total,
-                       "txt_accounting": "input bytes = the FASTQ text the VBlocks represent (45-byte name line, SEQ, '+', QUAL, 4 newlines per read); of the name line, "
-                                         "10 B/read of segmented read-name contexts flow through the path (the segmenter is out of scope); the same count in both arms",
-                       "excluded": EXCLUDED, "sharding": "VBlocks round-robin by vblock_i, no data-path collective; NCCL all_gather of the section list only",
+                       "txt_accounting": spec.accounting,
+                       "excluded": spec.excluded, "sharding": "VBlocks round-robin by vblock_i, no data-path collective; NCCL all_gather of the section list only",
                        "engines_per_gpu": len(path.engs), "device_groups": len(path.groups), "cpu_binding": numa,
                        **({"e2e_skipped": e2e_err} if (not args.no_e2e and e2e is None) else {})},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
@@ -513,7 +542,7 @@ def run_gpu(args):
 if __name__ == "__main__":
     a = parse()
     a.seed_base = 0
-    if a.workload != "fastq":
+    if a.workload not in ("fastq", "bam"):
         import bench_domain
         bench_domain.run_reference(a) if a.impl == "reference" else bench_domain.run_gpu(a, ClockSampler)
     elif a.impl == "reference":

@@ -1,0 +1,21 @@
+"""CPU: `bench.py --impl reference` (the reference's CPU implementation of the path on the host cores — the arm the driver runs
+beside the GPU arm) prints the contract's JSON line for the read workloads, on the committed codec tables, and its own round trip
+holds (the worker asserts it)."""
+import json, os, subprocess, sys
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("workload,metric,table", [("fastq", "fastq_input_GBps_zip_plus_piz", "bench_codecs.json"),
+                                                   ("bam", "bam_input_GBps_zip_plus_piz", "bench_codecs_bam.json")])
+def test_reference_arm_line(workload, metric, table):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", workload, "--steps", "1", "--warmup", "0",
+                        "--reads", "2000"], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == metric and line["unit"] == "GB/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["steps"] == 1 and line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["config"]["codecs"] == json.load(open(os.path.join(ROOT, table)))
+    assert line["config"]["compressed_bytes_per_vblock"] > 0
