@@ -19,3 +19,14 @@ def test_reference_arm_line(workload, metric, table):
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["config"]["codecs"] == json.load(open(os.path.join(ROOT, table)))
     assert line["config"]["compressed_bytes_per_vblock"] > 0
+
+
+def test_committed_codec_tables_cover_the_paths_streams():
+    """both arms of bench.py run the committed tables: each names a simple codec for exactly the streams its path class compresses"""
+    sys.path.insert(0, ROOT)
+    from genozip_b200.fastq_path import STREAMS, SIMPLE
+    from genozip_b200.bam_path import bam_fields
+    fq = json.load(open(os.path.join(ROOT, "bench_codecs.json"))); bam = json.load(open(os.path.join(ROOT, "bench_codecs_bam.json")))
+    assert list(fq) == STREAMS and set(fq.values()) <= set(SIMPLE)
+    assert list(bam) == STREAMS[:5] + list(bam_fields(92000, 150)) and set(bam.values()) <= set(SIMPLE)
+    assert all(bam[s] == fq[s] for s in fq)          # the streams the two workloads share got the same codecs
