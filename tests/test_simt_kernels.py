@@ -18,18 +18,22 @@ QUICK = ("edge_sizes or acgt or domq_ragged or domq_edges or domq_fastq_batch or
 import pytest
 
 
-@pytest.mark.parametrize("order", ["desc", "random"])
-def test_kernels_do_not_depend_on_the_lane_order(order):
+def test_kernels_do_not_depend_on_the_lane_order():
     """between two rendez-vous points the emulator runs the lanes of a warp one after the other; results must not depend on which
     lane goes first (SIMT_LANE_ORDER) — code that only works because lane 0 happens to run first would rely on more than the
-    markers GZB_WARP_READS_DONE / AR_READS_DONE state"""
-    env = dict(os.environ, GZB_SIMT_QUICK="1", SIMT_LANE_ORDER=order)
+    markers GZB_WARP_READS_DONE / AR_READS_DONE state.  (The two orders run side by side: two processes.)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "host", "simt"))
+    import build as simt_build
+    simt_build.build()                                   # (built once here, not by the two processes at the same time)
     k = ("(edge_sizes and (RANB or ARTB or ARTw)) or acgt or domq_ragged or domq_edges or domq_tiles or pbwt or longr or share_warp "
          "or oq_batch or smux or tmpl or pacb or homp or b250 or transpose")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests"), "-m", "gpu", "--simt", "-k", k, "-x", "-q", "-p", "no:cacheprovider"],
-                       cwd=ROOT, capture_output=True, text=True, timeout=1500, env=env)
-    tail = (r.stdout + r.stderr)[-4000:]
-    assert r.returncode == 0 and " passed" in tail and "failed" not in tail, tail
+    ps = {order: subprocess.Popen([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests"), "-m", "gpu", "--simt", "-k", k, "-x", "-q", "-p", "no:cacheprovider"],
+                                  cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                                  env=dict(os.environ, GZB_SIMT_QUICK="1", SIMT_LANE_ORDER=order)) for order in ("desc", "random")}
+    outs = {order: (p.communicate(timeout=1500)[0], p.returncode) for order, p in ps.items()}
+    for order, (out, rc) in outs.items():
+        tail = out[-4000:]
+        assert rc == 0 and " passed" in tail and "failed" not in tail, (order, tail)
 
 
 def test_kernels_on_the_simt_emulator():
